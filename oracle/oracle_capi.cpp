@@ -1,0 +1,335 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.
+//
+// C entry points over the Eigen-free restatement (riccati_oracle.cpp,
+// kkt_oracle.cpp) so tests/ and bench.py's cpu_baseline can drive it through
+// ctypes.  Batches are problem-major: array X holds [batch][flat per-problem
+// index]; problems are independent and run one per OpenMP thread
+// (schedule(static)), which is how the reference's single-threaded solver would
+// be deployed across host cores.
+#include <omp.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <vector>
+
+#include "kkt_oracle.hpp"
+#include "riccati_oracle.hpp"
+
+using namespace sipoc_oracle;
+
+extern "C" {
+
+// Returns the LQR::FactorStatus-valued topology status; fills the CSR/order
+// arrays (sizes E+2, E, E+1, E+1) when valid.
+int oracle_compile_topology(int E, int root, const int *parents,
+                            const int *children, int *child_offsets,
+                            int *child_edges, int *preorder, int *postorder) {
+  Tree t{E, root, parents, children};
+  CompiledTree c = compile_tree(t);
+  if (c.status != SUCCESS) return c.status;
+  for (int i = 0; i < E + 2; ++i) child_offsets[i] = c.child_offsets[i];
+  for (int i = 0; i < E; ++i) child_edges[i] = c.child_edges[i];
+  for (int i = 0; i < E + 1; ++i) {
+    preorder[i] = c.preorder[i];
+    postorder[i] = c.postorder[i];
+  }
+  return SUCCESS;
+}
+
+// out[0..6] = per-problem element counts of the (n x n), (n), (n x m), (m x m),
+// (m), A and B flat arrays.
+void oracle_lqr_sizes(int E, int root, const int *parents, const int *children,
+                      const int *state_dims, const int *control_dims,
+                      int64_t *out) {
+  Tree t{E, root, parents, children};
+  FlatLayout L = make_layout(t, state_dims, control_dims);
+  out[0] = L.nn_off[E + 1];
+  out[1] = L.n_off[E + 1];
+  out[2] = L.nm_off[E];
+  out[3] = L.mm_off[E];
+  out[4] = L.m_off[E];
+  out[5] = L.a_off[E];
+  out[6] = L.b_off[E];
+}
+
+// mode bit 0: factor, bit 1: solve (solve implies a factor in the same call).
+// status[b] gets the FactorStatus of problem b; x/u/y are written only for
+// problems whose factor succeeded.  residual (nullable) gets the KKT residual
+// 2-norm per problem.  seconds (nullable) gets the wall time of the parallel
+// factor(+solve) region, workspaces allocated outside it.
+int oracle_lqr_batch(int E, int root, const int *parents, const int *children,
+                     const int *state_dims, const int *control_dims,
+                     int64_t batch, const double *Q, const double *M,
+                     const double *R, const double *q, const double *r,
+                     const double *A, const double *B, const double *c,
+                     const double *delta, double *x, double *u, double *y,
+                     int *status, double *residual, int mode, int repeats,
+                     int nthreads, double *seconds) {
+  Tree t{E, root, parents, children};
+  CompiledTree ct = compile_tree(t);
+  if (ct.status != SUCCESS) {
+    for (int64_t b = 0; b < batch; ++b) status[b] = ct.status;
+    return ct.status;
+  }
+  FlatLayout L = make_layout(t, state_dims, control_dims);
+  const int64_t s_nn = L.nn_off[E + 1], s_n = L.n_off[E + 1], s_nm = L.nm_off[E],
+                s_mm = L.mm_off[E], s_m = L.m_off[E], s_a = L.a_off[E],
+                s_b = L.b_off[E];
+  if (nthreads <= 0) nthreads = omp_get_max_threads();
+  std::vector<LqrWorkspace> ws(nthreads);
+  for (auto &w : ws) w.reserve(L, ct);
+  if (repeats < 1) repeats = 1;
+
+  const auto t0 = std::chrono::steady_clock::now();
+  for (int rep = 0; rep < repeats; ++rep) {
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+    for (int64_t b = 0; b < batch; ++b) {
+      LqrWorkspace &w = ws[omp_get_thread_num()];
+      LqrInput in{Q + b * s_nn, M + b * s_nm, R + b * s_mm, q + b * s_n,
+                  r + b * s_m,  A + b * s_a,  B + b * s_b,  c + b * s_n,
+                  delta + b * s_n};
+      const Status st = lqr_factor(ct, L, in, w);
+      status[b] = st;
+      if ((mode & 2) && st == SUCCESS) {
+        LqrOutput out{x + b * s_n, u + b * s_m, y + b * s_n};
+        lqr_solve(ct, L, in, w, out);
+      }
+    }
+  }
+  const auto t1 = std::chrono::steady_clock::now();
+  if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
+
+  if (residual && (mode & 2)) {
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+    for (int64_t b = 0; b < batch; ++b) {
+      if (status[b] != SUCCESS) {
+        residual[b] = -1.0;
+        continue;
+      }
+      LqrInput in{Q + b * s_nn, M + b * s_nm, R + b * s_mm, q + b * s_n,
+                  r + b * s_m,  A + b * s_a,  B + b * s_b,  c + b * s_n,
+                  delta + b * s_n};
+      LqrOutput out{x + b * s_n, u + b * s_m, y + b * s_n};
+      residual[b] = lqr_residual_norm(ct, L, in, out);
+    }
+  }
+  return SUCCESS;
+}
+
+// Residual only, for outputs computed elsewhere (the CUDA path).
+int oracle_lqr_residual_batch(int E, int root, const int *parents,
+                              const int *children, const int *state_dims,
+                              const int *control_dims, int64_t batch,
+                              const double *Q, const double *M, const double *R,
+                              const double *q, const double *r, const double *A,
+                              const double *B, const double *c,
+                              const double *delta, const double *x,
+                              const double *u, const double *y,
+                              double *residual) {
+  Tree t{E, root, parents, children};
+  CompiledTree ct = compile_tree(t);
+  if (ct.status != SUCCESS) return ct.status;
+  FlatLayout L = make_layout(t, state_dims, control_dims);
+  const int64_t s_nn = L.nn_off[E + 1], s_n = L.n_off[E + 1], s_nm = L.nm_off[E],
+                s_mm = L.mm_off[E], s_m = L.m_off[E], s_a = L.a_off[E],
+                s_b = L.b_off[E];
+#pragma omp parallel for schedule(static)
+  for (int64_t b = 0; b < batch; ++b) {
+    LqrInput in{Q + b * s_nn, M + b * s_nm, R + b * s_mm, q + b * s_n,
+                r + b * s_m,  A + b * s_a,  B + b * s_b,  c + b * s_n,
+                delta + b * s_n};
+    LqrOutput out{const_cast<double *>(x + b * s_n), const_cast<double *>(u + b * s_m),
+                  const_cast<double *>(y + b * s_n)};
+    residual[b] = lqr_residual_norm(ct, L, in, out);
+  }
+  return SUCCESS;
+}
+
+// out[0..2] = x_dim, y_dim, z_dim; out[3..15] = per-problem element counts of
+// node_hxx, node_jc, node_jg, edge_hxx, edge_hxu, edge_huu, edge_A, edge_B,
+// edge_jcx, edge_jcu, edge_jgx, edge_jgu; out[15] unused.
+void oracle_kkt_sizes(int E, int root, const int *parents, const int *children,
+                      const int *state_dims, const int *control_dims,
+                      const int *node_c, const int *node_g, const int *edge_c,
+                      const int *edge_g, int64_t *out) {
+  Tree t{E, root, parents, children};
+  ConstraintDims cd{node_c, node_g, edge_c, edge_g};
+  KktLayout K = make_kkt_layout(t, state_dims, control_dims, cd);
+  int64_t hxx_edge = 0;
+  for (int e = 0; e < E; ++e) {
+    const int np = state_dims[parents[e]];
+    hxx_edge += np * np;
+  }
+  out[0] = K.x_dim;
+  out[1] = K.y_dim;
+  out[2] = K.z_dim;
+  out[3] = K.lqr.nn_off[E + 1];
+  out[4] = K.jc_node_off[E + 1];
+  out[5] = K.jg_node_off[E + 1];
+  out[6] = hxx_edge;
+  out[7] = K.lqr.nm_off[E];
+  out[8] = K.lqr.mm_off[E];
+  out[9] = K.lqr.a_off[E];
+  out[10] = K.lqr.b_off[E];
+  out[11] = K.jcx_off[E];
+  out[12] = K.jcu_off[E];
+  out[13] = K.jgx_off[E];
+  out[14] = K.jgu_off[E];
+  out[15] = 0;
+}
+
+// Offsets of the flat-vector wire format (types.cpp:24-64): arrays sized
+// E+1 / E as appropriate.
+void oracle_kkt_offsets(int E, int root, const int *parents, const int *children,
+                        const int *state_dims, const int *control_dims,
+                        const int *node_c, const int *node_g, const int *edge_c,
+                        const int *edge_g, int *x_state, int *x_control,
+                        int *y_dyn, int *y_node_c, int *y_edge_c, int *z_node,
+                        int *z_edge) {
+  Tree t{E, root, parents, children};
+  ConstraintDims cd{node_c, node_g, edge_c, edge_g};
+  KktLayout K = make_kkt_layout(t, state_dims, control_dims, cd);
+  for (int i = 0; i <= E; ++i) {
+    x_state[i] = K.x_state[i];
+    y_dyn[i] = K.y_dyn[i];
+    y_node_c[i] = K.y_node_c[i];
+    z_node[i] = K.z_node[i];
+  }
+  for (int e = 0; e < E; ++e) {
+    x_control[e] = K.x_control[e];
+    y_edge_c[e] = K.y_edge_c[e];
+    z_edge[e] = K.z_edge[e];
+  }
+}
+
+// mode bit 0: factor, bit 1: solve, bit 2: residual norm ||K sol - b||_2 via
+// kkt_apply (tests/variable_dimensions_test.cpp:159-180).  ok[b] = 1 when
+// CallbackProvider::factor would return true.
+int oracle_kkt_batch(int E, int root, const int *parents, const int *children,
+                     const int *state_dims, const int *control_dims,
+                     const int *node_c, const int *node_g, const int *edge_c,
+                     const int *edge_g, int64_t batch, const double *node_hxx,
+                     const double *node_jc, const double *node_jg,
+                     const double *edge_hxx, const double *edge_hxu,
+                     const double *edge_huu, const double *edge_A,
+                     const double *edge_B, const double *edge_jcx,
+                     const double *edge_jcu, const double *edge_jgx,
+                     const double *edge_jgu, const double *w, const double *r1,
+                     const double *r2, const double *r3, const double *b,
+                     double *sol, int *ok, int *lqr_status, double *residual,
+                     int mode, int repeats, int nthreads, double *seconds) {
+  Tree t{E, root, parents, children};
+  CompiledTree ct = compile_tree(t);
+  if (ct.status != SUCCESS) {
+    for (int64_t i = 0; i < batch; ++i) ok[i] = 0;
+    return ct.status;
+  }
+  ConstraintDims cd{node_c, node_g, edge_c, edge_g};
+  KktLayout K = make_kkt_layout(t, state_dims, control_dims, cd);
+  int64_t sz[16];
+  oracle_kkt_sizes(E, root, parents, children, state_dims, control_dims, node_c,
+                   node_g, edge_c, edge_g, sz);
+  if (nthreads <= 0) nthreads = omp_get_max_threads();
+  std::vector<KktWorkspace> ws(nthreads);
+  for (auto &wk : ws) wk.reserve(K, ct);
+  if (repeats < 1) repeats = 1;
+  const int64_t kd = K.kkt_dim;
+
+  const auto t0 = std::chrono::steady_clock::now();
+  for (int rep = 0; rep < repeats; ++rep) {
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+    for (int64_t i = 0; i < batch; ++i) {
+      KktWorkspace &wk = ws[omp_get_thread_num()];
+      KktModel mdl{node_hxx + i * sz[3],  node_jc + i * sz[4],
+                   node_jg + i * sz[5],   edge_hxx + i * sz[6],
+                   edge_hxu + i * sz[7],  edge_huu + i * sz[8],
+                   edge_A + i * sz[9],    edge_B + i * sz[10],
+                   edge_jcx + i * sz[11], edge_jcu + i * sz[12],
+                   edge_jgx + i * sz[13], edge_jgu + i * sz[14]};
+      int st = -1;
+      const bool good = kkt_factor(ct, K, mdl, w + i * sz[2], r1 + i * sz[0],
+                                   r2 + i * sz[1], r3 + i * sz[2], wk, &st);
+      ok[i] = good ? 1 : 0;
+      if (lqr_status) lqr_status[i] = st;
+      if ((mode & 2) && good) {
+        kkt_solve(ct, K, mdl, b + i * kd, sol + i * kd, wk);
+      }
+    }
+  }
+  const auto t1 = std::chrono::steady_clock::now();
+  if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
+
+  if ((mode & 4) && residual) {
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+    for (int64_t i = 0; i < batch; ++i) {
+      if (!ok[i]) {
+        residual[i] = -1.0;
+        continue;
+      }
+      KktModel mdl{node_hxx + i * sz[3],  node_jc + i * sz[4],
+                   node_jg + i * sz[5],   edge_hxx + i * sz[6],
+                   edge_hxu + i * sz[7],  edge_huu + i * sz[8],
+                   edge_A + i * sz[9],    edge_B + i * sz[10],
+                   edge_jcx + i * sz[11], edge_jcu + i * sz[12],
+                   edge_jgx + i * sz[13], edge_jgu + i * sz[14]};
+      std::vector<double> prod(kd, 0.0);
+      const double *s = sol + i * kd;
+      kkt_apply(ct, K, mdl, w + i * sz[2], r1 + i * sz[0], r2 + i * sz[1],
+                r3 + i * sz[2], s, s + K.x_dim, s + K.x_dim + K.y_dim,
+                prod.data(), prod.data() + K.x_dim,
+                prod.data() + K.x_dim + K.y_dim);
+      double sq = 0.0;
+      for (int64_t j = 0; j < kd; ++j) {
+        const double d = prod[j] - b[i * kd + j];
+        sq += d * d;
+      }
+      residual[i] = std::sqrt(sq);
+    }
+  }
+  return SUCCESS;
+}
+
+// y += K x for one batch (add_Kx_to_y); x and y are [batch][kkt_dim].
+int oracle_kkt_apply_batch(int E, int root, const int *parents,
+                           const int *children, const int *state_dims,
+                           const int *control_dims, const int *node_c,
+                           const int *node_g, const int *edge_c,
+                           const int *edge_g, int64_t batch,
+                           const double *node_hxx, const double *node_jc,
+                           const double *node_jg, const double *edge_hxx,
+                           const double *edge_hxu, const double *edge_huu,
+                           const double *edge_A, const double *edge_B,
+                           const double *edge_jcx, const double *edge_jcu,
+                           const double *edge_jgx, const double *edge_jgu,
+                           const double *w, const double *r1, const double *r2,
+                           const double *r3, const double *x, double *y) {
+  Tree t{E, root, parents, children};
+  CompiledTree ct = compile_tree(t);
+  if (ct.status != SUCCESS) return ct.status;
+  ConstraintDims cd{node_c, node_g, edge_c, edge_g};
+  KktLayout K = make_kkt_layout(t, state_dims, control_dims, cd);
+  int64_t sz[16];
+  oracle_kkt_sizes(E, root, parents, children, state_dims, control_dims, node_c,
+                   node_g, edge_c, edge_g, sz);
+  const int64_t kd = K.kkt_dim;
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < batch; ++i) {
+    KktModel mdl{node_hxx + i * sz[3],  node_jc + i * sz[4],
+                 node_jg + i * sz[5],   edge_hxx + i * sz[6],
+                 edge_hxu + i * sz[7],  edge_huu + i * sz[8],
+                 edge_A + i * sz[9],    edge_B + i * sz[10],
+                 edge_jcx + i * sz[11], edge_jcu + i * sz[12],
+                 edge_jgx + i * sz[13], edge_jgu + i * sz[14]};
+    const double *xs = x + i * kd;
+    double *ys = y + i * kd;
+    kkt_apply(ct, K, mdl, w + i * sz[2], r1 + i * sz[0], r2 + i * sz[1],
+              r3 + i * sz[2], xs, xs + K.x_dim, xs + K.x_dim + K.y_dim, ys,
+              ys + K.x_dim, ys + K.x_dim + K.y_dim);
+  }
+  return SUCCESS;
+}
+
+int oracle_max_threads() { return omp_get_max_threads(); }
+
+}  // extern "C"
