@@ -1,0 +1,36 @@
+# Builds the C-ABI shared library of the engine (include/sipoc.h) for sm_100a,
+# in-tree, plus the CPU oracle used by the tests.  No CMake / Bazel needed.
+NVCC ?= /usr/local/cuda/bin/nvcc
+HOSTCXX ?= /usr/bin/g++
+ARCH := -gencode arch=compute_100a,code=sm_100a
+NVCCFLAGS := -std=c++17 -O3 -lineinfo $(ARCH) -ccbin $(HOSTCXX) -Xcompiler -fPIC \
+             -Xcompiler -Wall -cudart static --expt-relaxed-constexpr
+CSRC := sip_optimal_control_b200/csrc
+LIBDIR := sip_optimal_control_b200/lib
+OBJDIR := build/obj
+SRCS := $(CSRC)/api.cu $(CSRC)/generic_kernels.cu $(CSRC)/riccati_fast.cu \
+        $(CSRC)/workload.cu $(CSRC)/structure.cpp
+OBJS := $(patsubst $(CSRC)/%,$(OBJDIR)/%.o,$(SRCS))
+HDRS := $(wildcard $(CSRC)/*.cuh $(CSRC)/*.hpp) include/sipoc.h
+
+all: $(LIBDIR)/libsipoc.so oracle
+
+$(OBJDIR)/%.cu.o: $(CSRC)/%.cu $(HDRS)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVCCFLAGS) $(EXTRA) -c $< -o $@
+
+$(OBJDIR)/%.cpp.o: $(CSRC)/%.cpp $(HDRS)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVCCFLAGS) -x cu -c $< -o $@
+
+$(LIBDIR)/libsipoc.so: $(OBJS)
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(ARCH) -ccbin $(HOSTCXX) -shared -cudart static -o $@ $(OBJS)
+
+oracle:
+	$(MAKE) -C oracle liboracle.so
+
+clean:
+	rm -rf build $(LIBDIR)/libsipoc.so oracle/liboracle.so
+
+.PHONY: all oracle clean

@@ -1,0 +1,263 @@
+/*
+ * sipoc.h — C ABI of the B200-native batched regularized-LQR / Newton-KKT engine.
+ *
+ * Drop-in boundary for the Newton-KKT linear-solve path of
+ * joaospinto/sip_optimal_control.  One engine handle owns ONE problem
+ * structure (Topology + Dimensions, reference lqr.hpp:5-64) and a batch of B
+ * numerically independent problems of that structure, all resident on one
+ * CUDA device.  Every entry point is extern "C" with plain pointers and
+ * sizes; nothing here depends on PyTorch, Eigen or sip.
+ *
+ * Reference interfaces each group of entry points replaces (file:line are
+ * relative to the reference repository):
+ *
+ *   sipoc_create / sipoc_destroy      LQR::LQR + LQR::compile_topology
+ *                                     (lqr.hpp:189-191, lqr.cpp:563-643) and
+ *                                     CallbackProvider::CallbackProvider +
+ *                                     validate_input (helpers.cpp:11-26,
+ *                                     types.cpp:68-134)
+ *   sipoc_lqr_factor                  LQR::factor_with_status / LQR::factor
+ *                                     (lqr.hpp:192-193, lqr.cpp:645-733)
+ *   sipoc_lqr_solve                   LQR::solve (lqr.hpp:194, lqr.cpp:735-871)
+ *   sipoc_lqr_factor_solve            factor_with_status + solve back to back,
+ *                                     the loop body of BM_LQRFactorSolve
+ *                                     (benchmarks/lqr_benchmark.cpp:653-663)
+ *   sipoc_lqr_residual                compute_residual_norm
+ *                                     (tests/lqr_test.cpp:152-186, :371-409)
+ *   sipoc_kkt_factor                  CallbackProvider::factor, theta_dim == 0
+ *                                     (helpers.hpp:11-12, helpers.cpp:242-370)
+ *   sipoc_kkt_solve                   CallbackProvider::solve, theta_dim == 0
+ *                                     (helpers.hpp:13, helpers.cpp:749-900)
+ *   sipoc_kkt_apply                   CallbackProvider::add_Kx_to_y
+ *                                     (helpers.hpp:14-16, helpers.cpp:953-977)
+ *   sipoc_kkt_residual                the ||K sol - rhs|| harness
+ *                                     (tests/variable_dimensions_test.cpp:159-180,
+ *                                     benchmarks/newton_kkt_benchmark.cpp:106-120)
+ *   sipoc_*_sizes / sipoc_kkt_offsets Dimensions::get_*_dim (lqr.cpp:146-180),
+ *                                     populate_workspace_metadata (types.cpp:24-64)
+ *   *_host variants                   the same calls on HOST buffers in the
+ *                                     reference's own memory order (what a
+ *                                     thin C++ shim behind LQR / CallbackProvider
+ *                                     passes), including host<->device copies.
+ *
+ * DATA LAYOUT
+ *   "flat per-problem index": for each array the column-major blocks of all
+ *   nodes (resp. edges) concatenated in node (edge) index order — exactly the
+ *   memory a reference caller reaches through the double** tables of
+ *   LQR::Input (lqr.hpp:76-89) when the blocks are stored back to back.
+ *     Q: sum n_i*n_i   q,c,delta,x,y: sum n_i     (per node i)
+ *     M: n_parent*m_e  R: m_e*m_e  r,u: m_e  A: n_child*n_parent  B: n_child*m_e
+ *   HOST ("problem-major"):   X_host[b * size + flat]            b < batch
+ *   DEVICE ("engine layout"): X_dev[flat * batch_stride + b]     batch innermost,
+ *     batch_stride = sipoc_batch_stride() (batch rounded up to 32), so the
+ *     lanes that work on neighbouring problems read neighbouring addresses.
+ *   Q and R must be symmetric; like the reference's tests
+ *   (selfadjointView<Lower>, tests/lqr_test.cpp:159,164) the fast kernels read
+ *   only their lower triangles.
+ *
+ * ERRORS
+ *   Every call returns a sipoc_error; nothing throws across the ABI.  Numerical
+ *   failure is reported per problem with the reference's LQR::FactorStatus
+ *   values (lqr.hpp:68-74), first failure in post-order wins
+ *   (lqr.cpp:696-700,722-727).  x/u/y (sol) of a failed problem are unspecified.
+ *   There is no CPU fallback: without a CUDA device sipoc_create fails with
+ *   SIPOC_CUDA_ERROR.
+ *
+ * THREADING  A handle is not thread-safe; use one per host thread / stream.
+ */
+#ifndef SIPOC_H_
+#define SIPOC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SIPOC_VERSION 100
+
+typedef struct sipoc_engine sipoc_engine;
+
+typedef enum sipoc_error {
+  SIPOC_OK = 0,
+  SIPOC_INVALID_ARGUMENT = 1,
+  SIPOC_CUDA_ERROR = 2,
+  SIPOC_OUT_OF_MEMORY = 3,
+  SIPOC_INVALID_TOPOLOGY = 4,   /* InputValidationStatus::INVALID_TOPOLOGY   */
+  SIPOC_INVALID_DIMENSIONS = 5, /* InputValidationStatus::INVALID_DIMENSIONS */
+  SIPOC_UNSUPPORTED = 6,
+  SIPOC_NOT_FACTORED = 7
+} sipoc_error;
+
+/* Per-problem factor status == LQR::FactorStatus (lqr.hpp:68-74). */
+typedef enum sipoc_factor_status {
+  SIPOC_FACTOR_SUCCESS = 0,
+  SIPOC_FACTOR_INVALID_DELTA = 1,
+  SIPOC_FACTOR_F_FACTORIZATION_FAILURE = 2,
+  SIPOC_FACTOR_G_FACTORIZATION_FAILURE = 3,
+  SIPOC_FACTOR_INVALID_TOPOLOGY = 4
+} sipoc_factor_status;
+
+/* Topology (lqr.hpp:5-22) + Dimensions (lqr.hpp:24-33), shared by the batch.
+ * The four constraint-dimension arrays may be NULL (= all zero, lqr.cpp:98-112).
+ * theta_dim > 0 (Schur variables) is not supported by this engine. */
+typedef struct sipoc_structure {
+  int num_edges;
+  int root;
+  const int *edge_parents;  /* [num_edges]     */
+  const int *edge_children; /* [num_edges]     */
+  const int *state_dims;    /* [num_edges + 1] */
+  const int *control_dims;  /* [num_edges]     */
+  const int *node_c_dims;   /* [num_edges + 1] or NULL */
+  const int *node_g_dims;   /* [num_edges + 1] or NULL */
+  const int *edge_c_dims;   /* [num_edges]     or NULL */
+  const int *edge_g_dims;   /* [num_edges]     or NULL */
+  int theta_dim;            /* must be 0 */
+  int64_t batch;            /* number of problems on this device */
+  int device;               /* CUDA ordinal, -1 = current device */
+  int flags;                /* SIPOC_FLAG_* */
+} sipoc_structure;
+
+#define SIPOC_FLAG_FORCE_GENERIC 1 /* never pick a shape-specialised kernel */
+
+sipoc_error sipoc_create(const sipoc_structure *structure, sipoc_engine **out);
+void sipoc_destroy(sipoc_engine *engine);
+int sipoc_version(void);
+/* Message of the last failing call on this handle ("" if none). */
+const char *sipoc_last_error(const sipoc_engine *engine);
+/* Name of the kernel variant the handle dispatches LQR calls to. */
+const char *sipoc_kernel_variant(const sipoc_engine *engine);
+/* Compiled traversal orders (lqr.cpp:563-631); arrays sized E+2, E, E+1, E+1. */
+sipoc_error sipoc_get_topology(const sipoc_engine *engine, int *child_offsets,
+                               int *child_edges, int *preorder, int *postorder);
+/* Kernels launched by this handle so far (each launch of one of OUR kernels). */
+int64_t sipoc_launch_count(const sipoc_engine *engine);
+
+/* ---- sizes ------------------------------------------------------------- */
+typedef struct sipoc_lqr_sizes {
+  int64_t Q, M, R, q, r, A, B, c, delta; /* inputs, elements per problem  */
+  int64_t x, u, y;                       /* outputs, elements per problem */
+} sipoc_lqr_sizes;
+sipoc_error sipoc_lqr_get_sizes(const sipoc_engine *engine, sipoc_lqr_sizes *out);
+int64_t sipoc_batch(const sipoc_engine *engine);
+int64_t sipoc_batch_stride(const sipoc_engine *engine);
+
+/* ---- LQR, device buffers in engine layout ------------------------------- */
+typedef struct sipoc_lqr_input {
+  const double *Q, *M, *R, *q, *r, *A, *B, *c, *delta;
+} sipoc_lqr_input;
+typedef struct sipoc_lqr_output {
+  double *x, *u, *y;
+} sipoc_lqr_output;
+
+/* stream: a cudaStream_t passed as void* (NULL = default stream).
+ * status: device int[batch_stride], or NULL. */
+sipoc_error sipoc_lqr_factor(sipoc_engine *engine, const sipoc_lqr_input *in,
+                             int *status, void *stream);
+/* Uses q, r, c (and A, B, delta) of `in` plus the stored factorization. */
+sipoc_error sipoc_lqr_solve(sipoc_engine *engine, const sipoc_lqr_input *in,
+                            const sipoc_lqr_output *out, void *stream);
+/* One fused launch: factor + solve, keeping only what the rollout needs. */
+sipoc_error sipoc_lqr_factor_solve(sipoc_engine *engine, const sipoc_lqr_input *in,
+                                   const sipoc_lqr_output *out, int *status,
+                                   void *stream);
+/* residual_norm: device double[batch_stride] or NULL.  stats: device double[4]
+ * or NULL, overwritten with {sum of squared norms, max norm, #failed problems
+ * (status != 0; status may be NULL), #problems} over this device's batch —
+ * the 4 numbers a multi-GPU driver all-reduces. */
+sipoc_error sipoc_lqr_residual(sipoc_engine *engine, const sipoc_lqr_input *in,
+                               const sipoc_lqr_output *out, const int *status,
+                               double *residual_norm, double *stats, void *stream);
+
+/* ---- layout conversion (device <-> device) ------------------------------ */
+/* src: problem-major [batch][size]; dst: engine layout [size][batch_stride]. */
+sipoc_error sipoc_pack(sipoc_engine *engine, const double *src, double *dst,
+                       int64_t size, void *stream);
+sipoc_error sipoc_unpack(sipoc_engine *engine, const double *src, double *dst,
+                         int64_t size, void *stream);
+
+/* ---- LQR, host buffers, problem-major (the reference-facing call) ------- */
+/* Copies inputs host->device, converts layout, runs the fused factor+solve,
+ * converts back and copies x/u/y and status to the host.  Synchronous. */
+sipoc_error sipoc_lqr_factor_solve_host(sipoc_engine *engine,
+                                        const sipoc_lqr_input *host_in,
+                                        const sipoc_lqr_output *host_out,
+                                        int *host_status);
+/* factor-once / solve-many on host buffers (BM_LQRSolve semantics,
+ * lqr_benchmark.cpp:611-638): factor keeps the inputs and the factorization
+ * resident; solve re-reads only q, r, c from host_in. */
+sipoc_error sipoc_lqr_factor_host(sipoc_engine *engine, const sipoc_lqr_input *host_in,
+                                  int *host_status);
+sipoc_error sipoc_lqr_solve_host(sipoc_engine *engine, const sipoc_lqr_input *host_in,
+                                 const sipoc_lqr_output *host_out);
+
+/* ---- Newton-KKT (theta_dim == 0) ---------------------------------------- */
+/* Flat vectors use the reference wire format (types.cpp:24-64):
+ *   x = [x_0,u_0,...,x_{E-1},u_{E-1},x_E]
+ *   y = [dyn_0,node_c_0,...,dyn_E,node_c_E, edge_c_0..edge_c_{E-1}]
+ *   z = [node_g_0..node_g_E, edge_g_0..edge_g_{E-1}],  KKT vectors = [x|y|z]. */
+typedef struct sipoc_kkt_sizes {
+  int64_t x_dim, y_dim, z_dim, kkt_dim;
+  /* elements per problem of every model block array */
+  int64_t node_hxx, node_jc, node_jg;
+  int64_t edge_hxx, edge_hxu, edge_huu, edge_A, edge_B;
+  int64_t edge_jcx, edge_jcu, edge_jgx, edge_jgu;
+} sipoc_kkt_sizes;
+sipoc_error sipoc_kkt_get_sizes(const sipoc_engine *engine, sipoc_kkt_sizes *out);
+/* Offsets of every node / edge block in x, y, z (arrays sized E+1 or E). */
+sipoc_error sipoc_kkt_offsets(const sipoc_engine *engine, int *x_state, int *x_control,
+                              int *y_dyn, int *y_node_c, int *y_edge_c, int *z_node,
+                              int *z_edge);
+
+/* The ModelCallbackOutput blocks the reduction reads (types.hpp:48-89):
+ * node d2L_dx2, dc_dx, dg_dx; edge d2L_dx2, d2L_dxdu, d2L_du2, ddyn_dx,
+ * ddyn_du, dc_dx, dc_du, dg_dx, dg_du — flat, column-major per block. */
+typedef struct sipoc_kkt_model {
+  const double *node_hxx, *node_jc, *node_jg;
+  const double *edge_hxx, *edge_hxu, *edge_huu, *edge_A, *edge_B;
+  const double *edge_jcx, *edge_jcu, *edge_jgx, *edge_jgu;
+} sipoc_kkt_model;
+
+/* ok: device int[batch_stride]; 1 where CallbackProvider::factor returns true. */
+sipoc_error sipoc_kkt_factor(sipoc_engine *engine, const sipoc_kkt_model *model,
+                             const double *w, const double *r1, const double *r2,
+                             const double *r3, int *ok, void *stream);
+sipoc_error sipoc_kkt_solve(sipoc_engine *engine, const sipoc_kkt_model *model,
+                            const double *b, double *sol, void *stream);
+/* y += K(w, r1, r2, r3) x over [x|y|z] vectors (add_Kx_to_y). */
+sipoc_error sipoc_kkt_apply(sipoc_engine *engine, const sipoc_kkt_model *model,
+                            const double *w, const double *r1, const double *r2,
+                            const double *r3, const double *x, double *y,
+                            void *stream);
+/* ||K sol - b||_2 per problem and the 4 all-reducible statistics (see
+ * sipoc_lqr_residual); ok may be NULL. */
+sipoc_error sipoc_kkt_residual(sipoc_engine *engine, const sipoc_kkt_model *model,
+                               const double *w, const double *r1, const double *r2,
+                               const double *r3, const double *sol, const double *b,
+                               const int *ok, double *residual_norm, double *stats,
+                               void *stream);
+/* Host-buffer variants (problem-major), synchronous. */
+sipoc_error sipoc_kkt_factor_host(sipoc_engine *engine, const sipoc_kkt_model *host_model,
+                                  const double *w, const double *r1, const double *r2,
+                                  const double *r3, int *host_ok);
+sipoc_error sipoc_kkt_solve_host(sipoc_engine *engine, const double *b, double *sol);
+sipoc_error sipoc_kkt_apply_host(sipoc_engine *engine, const double *w, const double *r1,
+                                 const double *r2, const double *r3, const double *x,
+                                 double *y);
+
+/* ---- synthetic workloads (bench / test tooling) -------------------------- */
+/* Fills engine-layout device buffers with the distribution of the reference's
+ * LQRProblem generator (benchmarks/lqr_benchmark.cpp:61-96): A = I + 0.05 N,
+ * B = 0.1 N, M = 0, R = Z'Z + 1.01 I, Q = Z'Z + 1e-3 I, q, r, c ~ N(0,1),
+ * delta = 1e-3 + 0.1 U(0,1), from a counter-based generator keyed by
+ * (seed, problem_offset + b, array, element).  Uniform chains only. */
+sipoc_error sipoc_generate_lqr_benchmark(sipoc_engine *engine, uint64_t seed,
+                                         int64_t problem_offset, double *Q, double *M,
+                                         double *R, double *q, double *r, double *A,
+                                         double *B, double *c, double *delta,
+                                         void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIPOC_H_ */

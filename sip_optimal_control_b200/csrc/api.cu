@@ -1,0 +1,860 @@
+// C ABI of the engine (include/sipoc.h): handle management, dispatch between
+// the generic and the shape-specialised kernels, and the host-buffer entry
+// points that wrap copies + layout conversion around the device path.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/sipoc.h"
+#include "generic_kernels.cuh"
+#include "riccati_fast.cuh"
+#include "structure.hpp"
+#include "workload.cuh"
+
+using namespace sipoc;
+
+struct sipoc_engine {
+  HostStructure hs;
+  DevTables dt{};
+  int *d_tab = nullptr;
+  int device = 0;
+  int flags = 0;
+  int64_t batch = 0, ld = 0;
+  const FastPlan *fast = nullptr;
+  std::string variant;
+  std::string last_error;
+  int64_t launches = 0;
+  cudaStream_t host_stream = nullptr;
+
+  // Every device allocation the handle owns.
+  std::vector<void *> allocations;
+
+  // Generic factorization workspace (lazy).
+  LqrWs gws{};
+  bool gws_ready = false;
+  // Fast-path storage (lazy).
+  double *fast_store = nullptr, *fast_scratch = nullptr;
+  enum class Factored { NONE, GENERIC, FAST } factored = Factored::NONE;
+
+  // Newton-KKT reduction outputs (lazy).
+  KktWs kws{};
+  bool kws_ready = false;
+  int *kkt_lqr_status = nullptr;
+  bool kkt_factored = false;
+  double *kkt_product = nullptr;  // K * sol scratch of sipoc_kkt_residual
+
+  // Host-API resident buffers (lazy).
+  double *h_in[9] = {nullptr};
+  double *h_out[3] = {nullptr};
+  double *h_stage = nullptr;
+  int64_t h_stage_elems = 0;
+  int *h_status = nullptr;
+  bool host_lqr_ready = false;
+  bool host_lqr_factored = false;
+  double *hk_model[12] = {nullptr};
+  double *hk_reg[4] = {nullptr};  // w, r1, r2, r3
+  double *hk_vec[2] = {nullptr};  // b / x, sol / y
+  bool host_kkt_ready = false;
+};
+
+namespace {
+
+sipoc_error fail(sipoc_engine *e, sipoc_error code, const std::string &msg) {
+  if (e != nullptr) e->last_error = msg;
+  return code;
+}
+
+#define SIPOC_CUDA(e, call)                                                      \
+  do {                                                                           \
+    cudaError_t err__ = (call);                                                  \
+    if (err__ != cudaSuccess) {                                                  \
+      return fail((e),                                                           \
+                  err__ == cudaErrorMemoryAllocation ? SIPOC_OUT_OF_MEMORY       \
+                                                     : SIPOC_CUDA_ERROR,         \
+                  std::string(#call) + ": " + cudaGetErrorString(err__));        \
+    }                                                                            \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+sipoc_error dev_alloc(sipoc_engine *e, void **out, size_t bytes) {
+  *out = nullptr;
+  if (bytes == 0) bytes = 16;
+  SIPOC_CUDA(e, cudaMalloc(out, bytes));
+  e->allocations.push_back(*out);
+  return SIPOC_OK;
+}
+
+sipoc_error alloc_doubles(sipoc_engine *e, double **out, int64_t elems_per_problem) {
+  return dev_alloc(e, reinterpret_cast<void **>(out),
+                   static_cast<size_t>(std::max<int64_t>(elems_per_problem, 1)) *
+                       static_cast<size_t>(e->ld) * sizeof(double));
+}
+
+sipoc_error check_launch(sipoc_engine *e, const char *what) {
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess)
+    return fail(e, SIPOC_CUDA_ERROR, std::string(what) + ": " + cudaGetErrorString(err));
+  return SIPOC_OK;
+}
+
+void rebase(DevTables &t, const int *base) {
+  const int **fields[] = {
+      &t.parents,      &t.children,    &t.n,          &t.m,           &t.child_offsets,
+      &t.child_edges,  &t.preorder,    &t.postorder,  &t.in_edge,     &t.nn_off,
+      &t.n_off,        &t.nm_off,      &t.mm_off,     &t.m_off,       &t.a_off,
+      &t.b_off,        &t.w_off,       &t.k_off,      &t.hxx_edge_off, &t.node_c,
+      &t.node_g,       &t.edge_c,      &t.edge_g,     &t.x_state,     &t.y_dyn,
+      &t.y_node_c,     &t.z_node,      &t.x_control,  &t.y_edge_c,    &t.z_edge,
+      &t.jc_node_off,  &t.jg_node_off, &t.jcx_off,    &t.jcu_off,     &t.jgx_off,
+      &t.jgu_off,      &t.node_c_off,  &t.node_g_off, &t.edge_c_off,  &t.edge_g_off};
+  for (const int **f : fields) {
+    const size_t byte_off = reinterpret_cast<size_t>(*f);
+    *f = reinterpret_cast<const int *>(reinterpret_cast<const char *>(base) + byte_off);
+  }
+}
+
+sipoc_error ensure_generic_ws(sipoc_engine *e) {
+  if (e->gws_ready) return SIPOC_OK;
+  const HostStructure &h = e->hs;
+  sipoc_error rc;
+  const int64_t mn = std::max(1, h.max_n), mm = std::max(1, h.max_m);
+#define A_(field, elems) \
+  if ((rc = alloc_doubles(e, &e->gws.field, (elems))) != SIPOC_OK) return rc;
+  A_(W, h.w_off[h.E]);
+  A_(K, h.k_off[h.E]);
+  A_(V, h.nn_off[h.N]);
+  A_(Gf, h.mm_off[h.E]);
+  A_(Ff, h.nn_off[h.N]);
+  A_(sd, h.n_off[h.N]);
+  A_(sdi, h.n_off[h.N]);
+  A_(k, h.m_off[h.E]);
+  A_(v, h.n_off[h.N]);
+  A_(H, mm * mn);
+  A_(F, mn * mn);
+  A_(f, mn);
+  A_(g, mn);
+  A_(h, mm);
+#undef A_
+  e->gws_ready = true;
+  return SIPOC_OK;
+}
+
+sipoc_error ensure_fast_store(sipoc_engine *e) {
+  if (e->fast == nullptr || e->fast_store != nullptr) return SIPOC_OK;
+  sipoc_error rc = alloc_doubles(e, &e->fast_store, e->fast->store_elems(e->hs.E));
+  return rc;
+}
+
+sipoc_error ensure_fast_scratch(sipoc_engine *e) {
+  if (e->fast == nullptr || e->fast_scratch != nullptr) return SIPOC_OK;
+  return alloc_doubles(e, &e->fast_scratch, e->fast->scratch_elems(e->hs.E));
+}
+
+sipoc_error ensure_kkt_ws(sipoc_engine *e) {
+  if (e->kws_ready) return SIPOC_OK;
+  const HostStructure &h = e->hs;
+  sipoc_error rc;
+#define A_(field, elems) \
+  if ((rc = alloc_doubles(e, &e->kws.field, (elems))) != SIPOC_OK) return rc;
+  A_(Q_mod, h.nn_off[h.N]);
+  A_(M_mod, h.nm_off[h.E]);
+  A_(R_mod, h.mm_off[h.E]);
+  A_(q_mod, h.n_off[h.N]);
+  A_(r_mod, h.m_off[h.E]);
+  A_(c_mod, h.n_off[h.N]);
+  A_(dyn_r2, h.n_off[h.N]);
+  A_(node_c_r2_inv, h.node_c_off[h.N]);
+  A_(edge_c_r2_inv, h.edge_c_off[h.E]);
+  A_(node_mod_w_inv, h.node_g_off[h.N]);
+  A_(edge_mod_w_inv, h.edge_g_off[h.E]);
+  A_(x, h.n_off[h.N]);
+  A_(u, h.m_off[h.E]);
+  A_(y, h.n_off[h.N]);
+#undef A_
+  rc = dev_alloc(e, reinterpret_cast<void **>(&e->kkt_lqr_status),
+                 static_cast<size_t>(e->ld) * sizeof(int));
+  if (rc != SIPOC_OK) return rc;
+  e->kws_ready = true;
+  return SIPOC_OK;
+}
+
+LqrIn to_in(const sipoc_lqr_input *in) {
+  return LqrIn{in->Q, in->M, in->R, in->q, in->r, in->A, in->B, in->c, in->delta};
+}
+
+// --- device-path cores (shared by the device and host entry points) --------
+sipoc_error lqr_factor_core(sipoc_engine *e, const LqrIn &in, int *status,
+                            cudaStream_t s) {
+  sipoc_error rc;
+  if (e->fast != nullptr) {
+    if ((rc = ensure_fast_store(e)) != SIPOC_OK) return rc;
+    FastArgs a{in, LqrOut{}, status, e->fast_store, nullptr, e->batch, e->ld, e->hs.E};
+    e->launches += e->fast->factor(a, s);
+    e->factored = sipoc_engine::Factored::FAST;
+  } else {
+    if ((rc = ensure_generic_ws(e)) != SIPOC_OK) return rc;
+    launch_generic_lqr_factor(e->dt, in, e->gws, status, e->batch, e->ld, s);
+    e->launches += 1;
+    e->factored = sipoc_engine::Factored::GENERIC;
+  }
+  return check_launch(e, "lqr_factor");
+}
+
+sipoc_error lqr_solve_core(sipoc_engine *e, const LqrIn &in, const LqrOut &out,
+                           cudaStream_t s) {
+  sipoc_error rc;
+  if (e->factored == sipoc_engine::Factored::NONE)
+    return fail(e, SIPOC_NOT_FACTORED, "solve called before a factor on this handle");
+  if (e->factored == sipoc_engine::Factored::FAST) {
+    if ((rc = ensure_fast_scratch(e)) != SIPOC_OK) return rc;
+    FastArgs a{in, out, nullptr, e->fast_store, e->fast_scratch, e->batch, e->ld, e->hs.E};
+    e->launches += e->fast->solve(a, s);
+  } else {
+    launch_generic_lqr_solve(e->dt, in, e->gws, out, e->batch, e->ld, s);
+    e->launches += 1;
+  }
+  return check_launch(e, "lqr_solve");
+}
+
+sipoc_error lqr_factor_solve_core(sipoc_engine *e, const LqrIn &in, const LqrOut &out,
+                                  int *status, cudaStream_t s) {
+  sipoc_error rc;
+  if (e->fast != nullptr) {
+    if ((rc = ensure_fast_scratch(e)) != SIPOC_OK) return rc;
+    FastArgs a{in, out, status, nullptr, e->fast_scratch, e->batch, e->ld, e->hs.E};
+    e->launches += e->fast->factor_solve(a, s);
+    // The fused kernel keeps only the rollout spill, not a reusable factor.
+    e->factored = sipoc_engine::Factored::NONE;
+    return check_launch(e, "lqr_factor_solve");
+  }
+  if ((rc = lqr_factor_core(e, in, status, s)) != SIPOC_OK) return rc;
+  return lqr_solve_core(e, in, out, s);
+}
+
+bool null_in(const sipoc_lqr_input *in, bool need_matrices, bool need_vectors) {
+  if (in == nullptr) return true;
+  if (need_matrices && (!in->Q || !in->M || !in->R || !in->A || !in->B || !in->delta))
+    return true;
+  if (need_vectors && (!in->q || !in->r || !in->c || !in->A || !in->B || !in->delta))
+    return true;
+  return false;
+}
+
+int64_t lqr_in_size(const HostStructure &h, int i) {
+  switch (i) {
+    case 0: return h.nn_off[h.N];  // Q
+    case 1: return h.nm_off[h.E];  // M
+    case 2: return h.mm_off[h.E];  // R
+    case 3: return h.n_off[h.N];   // q
+    case 4: return h.m_off[h.E];   // r
+    case 5: return h.a_off[h.E];   // A
+    case 6: return h.b_off[h.E];   // B
+    case 7: return h.n_off[h.N];   // c
+    default: return h.n_off[h.N];  // delta
+  }
+}
+
+int64_t kkt_model_size(const HostStructure &h, int i) {
+  switch (i) {
+    case 0: return h.nn_off[h.N];
+    case 1: return h.jc_node_off[h.N];
+    case 2: return h.jg_node_off[h.N];
+    case 3: return h.hxx_edge_off[h.E];
+    case 4: return h.nm_off[h.E];
+    case 5: return h.mm_off[h.E];
+    case 6: return h.a_off[h.E];
+    case 7: return h.b_off[h.E];
+    case 8: return h.jcx_off[h.E];
+    case 9: return h.jcu_off[h.E];
+    case 10: return h.jgx_off[h.E];
+    default: return h.jgu_off[h.E];
+  }
+}
+
+sipoc_error ensure_stage(sipoc_engine *e, int64_t elems_per_problem) {
+  if (e->h_stage_elems >= elems_per_problem) return SIPOC_OK;
+  // Never shrinks; the old buffer stays owned by the handle until destroy.
+  sipoc_error rc = dev_alloc(e, reinterpret_cast<void **>(&e->h_stage),
+                             static_cast<size_t>(std::max<int64_t>(elems_per_problem, 1)) *
+                                 static_cast<size_t>(e->ld) * sizeof(double));
+  if (rc == SIPOC_OK) e->h_stage_elems = elems_per_problem;
+  return rc;
+}
+
+// host (problem-major) -> device engine layout
+sipoc_error upload(sipoc_engine *e, const double *host, double *dev, int64_t size) {
+  if (size == 0) return SIPOC_OK;
+  if (host == nullptr) return fail(e, SIPOC_INVALID_ARGUMENT, "NULL host input array");
+  SIPOC_CUDA(e, cudaMemcpyAsync(e->h_stage, host,
+                                static_cast<size_t>(size) * e->batch * sizeof(double),
+                                cudaMemcpyHostToDevice, e->host_stream));
+  launch_pack(e->h_stage, dev, size, e->batch, e->ld, e->host_stream);
+  e->launches += 1;
+  return check_launch(e, "pack");
+}
+
+sipoc_error download(sipoc_engine *e, const double *dev, double *host, int64_t size) {
+  if (size == 0) return SIPOC_OK;
+  if (host == nullptr) return fail(e, SIPOC_INVALID_ARGUMENT, "NULL host output array");
+  launch_unpack(dev, e->h_stage, size, e->batch, e->ld, e->host_stream);
+  e->launches += 1;
+  sipoc_error rc = check_launch(e, "unpack");
+  if (rc != SIPOC_OK) return rc;
+  SIPOC_CUDA(e, cudaMemcpyAsync(host, e->h_stage,
+                                static_cast<size_t>(size) * e->batch * sizeof(double),
+                                cudaMemcpyDeviceToHost, e->host_stream));
+  return SIPOC_OK;
+}
+
+sipoc_error ensure_host_lqr(sipoc_engine *e) {
+  if (e->host_lqr_ready) return SIPOC_OK;
+  const HostStructure &h = e->hs;
+  sipoc_error rc;
+  int64_t biggest = 1;
+  for (int i = 0; i < 9; ++i) {
+    if ((rc = alloc_doubles(e, &e->h_in[i], lqr_in_size(h, i))) != SIPOC_OK) return rc;
+    biggest = std::max(biggest, lqr_in_size(h, i));
+  }
+  const int64_t out_sizes[3] = {h.n_off[h.N], h.m_off[h.E], h.n_off[h.N]};
+  for (int i = 0; i < 3; ++i)
+    if ((rc = alloc_doubles(e, &e->h_out[i], out_sizes[i])) != SIPOC_OK) return rc;
+  if ((rc = ensure_stage(e, biggest)) != SIPOC_OK) return rc;
+  if (e->h_status == nullptr) {
+    rc = dev_alloc(e, reinterpret_cast<void **>(&e->h_status),
+                   static_cast<size_t>(e->ld) * sizeof(int));
+    if (rc != SIPOC_OK) return rc;
+  }
+  e->host_lqr_ready = true;
+  return SIPOC_OK;
+}
+
+sipoc_error ensure_host_kkt(sipoc_engine *e) {
+  if (e->host_kkt_ready) return SIPOC_OK;
+  const HostStructure &h = e->hs;
+  sipoc_error rc;
+  int64_t biggest = std::max<int64_t>(1, h.kkt_dim);
+  for (int i = 0; i < 12; ++i) {
+    if ((rc = alloc_doubles(e, &e->hk_model[i], kkt_model_size(h, i))) != SIPOC_OK) return rc;
+    biggest = std::max(biggest, kkt_model_size(h, i));
+  }
+  const int64_t reg_sizes[4] = {h.z_dim, h.x_dim, h.y_dim, h.z_dim};
+  for (int i = 0; i < 4; ++i)
+    if ((rc = alloc_doubles(e, &e->hk_reg[i], reg_sizes[i])) != SIPOC_OK) return rc;
+  for (int i = 0; i < 2; ++i)
+    if ((rc = alloc_doubles(e, &e->hk_vec[i], h.kkt_dim)) != SIPOC_OK) return rc;
+  if ((rc = ensure_stage(e, biggest)) != SIPOC_OK) return rc;
+  if (e->h_status == nullptr) {
+    rc = dev_alloc(e, reinterpret_cast<void **>(&e->h_status),
+                   static_cast<size_t>(e->ld) * sizeof(int));
+    if (rc != SIPOC_OK) return rc;
+  }
+  e->host_kkt_ready = true;
+  return SIPOC_OK;
+}
+
+KktModel to_model(const sipoc_kkt_model *m) {
+  return KktModel{m->node_hxx, m->node_jc,  m->node_jg, m->edge_hxx, m->edge_hxu, m->edge_huu,
+                  m->edge_A,   m->edge_B,   m->edge_jcx, m->edge_jcu, m->edge_jgx, m->edge_jgu};
+}
+
+bool model_has_null(const sipoc_kkt_model *m) {
+  return m == nullptr || !m->node_hxx || !m->node_jc || !m->node_jg || !m->edge_hxx ||
+         !m->edge_hxu || !m->edge_huu || !m->edge_A || !m->edge_B || !m->edge_jcx ||
+         !m->edge_jcu || !m->edge_jgx || !m->edge_jgu;
+}
+
+sipoc_error kkt_factor_core(sipoc_engine *e, const KktModel &mdl, const double *w,
+                            const double *r1, const double *r2, const double *r3, int *ok,
+                            cudaStream_t s) {
+  sipoc_error rc;
+  if ((rc = ensure_kkt_ws(e)) != SIPOC_OK) return rc;
+  launch_kkt_reduce(e->dt, mdl, w, r1, r2, r3, e->kws, ok, e->batch, e->ld, s);
+  e->launches += 2;
+  if ((rc = check_launch(e, "kkt_reduce")) != SIPOC_OK) return rc;
+  // helpers.cpp:362-368: LQR on (Q_mod, M_mod, R_mod, ddyn_dx, ddyn_du, dyn_r2).
+  LqrIn in{e->kws.Q_mod, e->kws.M_mod, e->kws.R_mod, nullptr, nullptr,
+           mdl.edge_A,   mdl.edge_B,   nullptr,      e->kws.dyn_r2};
+  if ((rc = lqr_factor_core(e, in, e->kkt_lqr_status, s)) != SIPOC_OK) return rc;
+  launch_kkt_finish_factor(e->kkt_lqr_status, ok, e->batch, s);
+  e->launches += 1;
+  e->kkt_factored = true;
+  return check_launch(e, "kkt_finish_factor");
+}
+
+sipoc_error kkt_solve_core(sipoc_engine *e, const KktModel &mdl, const double *b,
+                           double *sol, cudaStream_t s) {
+  if (!e->kkt_factored)
+    return fail(e, SIPOC_NOT_FACTORED, "kkt_solve called before kkt_factor");
+  launch_kkt_build_rhs(e->dt, mdl, e->kws, b, e->batch, e->ld, s);
+  e->launches += 1;
+  sipoc_error rc = check_launch(e, "kkt_build_rhs");
+  if (rc != SIPOC_OK) return rc;
+  LqrIn in{e->kws.Q_mod, e->kws.M_mod, e->kws.R_mod, e->kws.q_mod, e->kws.r_mod,
+           mdl.edge_A,   mdl.edge_B,   e->kws.c_mod, e->kws.dyn_r2};
+  LqrOut out{e->kws.x, e->kws.u, e->kws.y};
+  if ((rc = lqr_solve_core(e, in, out, s)) != SIPOC_OK) return rc;
+  launch_kkt_recover(e->dt, mdl, e->kws, b, sol, e->batch, e->ld, s);
+  e->launches += 1;
+  return check_launch(e, "kkt_recover");
+}
+
+}  // namespace
+
+// ===========================================================================
+extern "C" {
+
+int sipoc_version(void) { return SIPOC_VERSION; }
+
+sipoc_error sipoc_create(const sipoc_structure *s, sipoc_engine **out) {
+  if (out == nullptr) return SIPOC_INVALID_ARGUMENT;
+  *out = nullptr;
+  if (s == nullptr || s->batch <= 0) return SIPOC_INVALID_ARGUMENT;
+  sipoc_engine *e = new (std::nothrow) sipoc_engine();
+  if (e == nullptr) return SIPOC_OUT_OF_MEMORY;
+  std::string err;
+  sipoc_error rc = e->hs.build(*s, err);
+  if (rc != SIPOC_OK) {
+    delete e;
+    return rc;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    // No CPU fallback by design.
+    delete e;
+    return SIPOC_CUDA_ERROR;
+  }
+  int dev = s->device;
+  if (dev < 0 && cudaGetDevice(&dev) != cudaSuccess) {
+    delete e;
+    return SIPOC_CUDA_ERROR;
+  }
+  if (dev >= ndev) {
+    delete e;
+    return SIPOC_INVALID_ARGUMENT;
+  }
+  e->device = dev;
+  e->flags = s->flags;
+  e->batch = s->batch;
+  e->ld = (s->batch + 31) / 32 * 32;
+  DeviceGuard guard(dev);
+
+  DevTables t{};
+  std::vector<int> buf = e->hs.serialise(t);
+  void *d = nullptr;
+  if (cudaMalloc(&d, buf.size() * sizeof(int)) != cudaSuccess ||
+      cudaMemcpy(d, buf.data(), buf.size() * sizeof(int), cudaMemcpyHostToDevice) !=
+          cudaSuccess ||
+      cudaStreamCreateWithFlags(&e->host_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    if (d != nullptr) cudaFree(d);
+    delete e;
+    return SIPOC_CUDA_ERROR;
+  }
+  e->d_tab = static_cast<int *>(d);
+  e->allocations.push_back(d);
+  rebase(t, e->d_tab);
+  e->dt = t;
+
+  const HostStructure &h = e->hs;
+  if (!(e->flags & SIPOC_FLAG_FORCE_GENERIC) && h.is_chain && h.is_uniform && h.E >= 1)
+    e->fast = select_fast_plan(h.n[0], h.m[0]);
+  e->variant = e->fast != nullptr ? e->fast->name : "generic_thread_per_problem";
+  *out = e;
+  return SIPOC_OK;
+}
+
+void sipoc_destroy(sipoc_engine *e) {
+  if (e == nullptr) return;
+  {
+    DeviceGuard guard(e->device);
+    cudaDeviceSynchronize();
+    for (void *p : e->allocations) cudaFree(p);
+    if (e->host_stream != nullptr) cudaStreamDestroy(e->host_stream);
+  }
+  delete e;
+}
+
+const char *sipoc_last_error(const sipoc_engine *e) {
+  return e == nullptr ? "" : e->last_error.c_str();
+}
+
+const char *sipoc_kernel_variant(const sipoc_engine *e) {
+  return e == nullptr ? "" : e->variant.c_str();
+}
+
+int64_t sipoc_launch_count(const sipoc_engine *e) { return e == nullptr ? 0 : e->launches; }
+int64_t sipoc_batch(const sipoc_engine *e) { return e == nullptr ? 0 : e->batch; }
+int64_t sipoc_batch_stride(const sipoc_engine *e) { return e == nullptr ? 0 : e->ld; }
+
+sipoc_error sipoc_get_topology(const sipoc_engine *e, int *child_offsets, int *child_edges,
+                               int *preorder, int *postorder) {
+  if (e == nullptr) return SIPOC_INVALID_ARGUMENT;
+  const HostStructure &h = e->hs;
+  if (child_offsets) {
+    std::copy(h.child_offsets.begin(), h.child_offsets.end(), child_offsets);
+  }
+  if (child_edges) std::copy(h.child_edges.begin(), h.child_edges.end(), child_edges);
+  if (preorder) std::copy(h.preorder.begin(), h.preorder.end(), preorder);
+  if (postorder) std::copy(h.postorder.begin(), h.postorder.end(), postorder);
+  return SIPOC_OK;
+}
+
+sipoc_error sipoc_lqr_get_sizes(const sipoc_engine *e, sipoc_lqr_sizes *o) {
+  if (e == nullptr || o == nullptr) return SIPOC_INVALID_ARGUMENT;
+  const HostStructure &h = e->hs;
+  o->Q = h.nn_off[h.N];
+  o->M = h.nm_off[h.E];
+  o->R = h.mm_off[h.E];
+  o->q = o->c = o->delta = o->x = o->y = h.n_off[h.N];
+  o->r = o->u = h.m_off[h.E];
+  o->A = h.a_off[h.E];
+  o->B = h.b_off[h.E];
+  return SIPOC_OK;
+}
+
+sipoc_error sipoc_lqr_factor(sipoc_engine *e, const sipoc_lqr_input *in, int *status,
+                             void *stream) {
+  if (e == nullptr) return SIPOC_INVALID_ARGUMENT;
+  if (null_in(in, true, false)) return fail(e, SIPOC_INVALID_ARGUMENT, "NULL LQR input");
+  DeviceGuard guard(e->device);
+  return lqr_factor_core(e, to_in(in), status, static_cast<cudaStream_t>(stream));
+}
+
+sipoc_error sipoc_lqr_solve(sipoc_engine *e, const sipoc_lqr_input *in,
+                            const sipoc_lqr_output *out, void *stream) {
+  if (e == nullptr) return SIPOC_INVALID_ARGUMENT;
+  if (null_in(in, false, true) || out == nullptr || !out->x || !out->u || !out->y)
+    return fail(e, SIPOC_INVALID_ARGUMENT, "NULL LQR input / output");
+  DeviceGuard guard(e->device);
+  return lqr_solve_core(e, to_in(in), LqrOut{out->x, out->u, out->y},
+                        static_cast<cudaStream_t>(stream));
+}
+
+sipoc_error sipoc_lqr_factor_solve(sipoc_engine *e, const sipoc_lqr_input *in,
+                                   const sipoc_lqr_output *out, int *status, void *stream) {
+  if (e == nullptr) return SIPOC_INVALID_ARGUMENT;
+  if (null_in(in, true, true) || out == nullptr || !out->x || !out->u || !out->y)
+    return fail(e, SIPOC_INVALID_ARGUMENT, "NULL LQR input / output");
+  DeviceGuard guard(e->device);
+  return lqr_factor_solve_core(e, to_in(in), LqrOut{out->x, out->u, out->y}, status,
+                               static_cast<cudaStream_t>(stream));
+}
+
+sipoc_error sipoc_lqr_residual(sipoc_engine *e, const sipoc_lqr_input *in,
+                               const sipoc_lqr_output *out, const int *status,
+                               double *residual_norm, double *stats, void *stream) {
+  if (e == nullptr) return SIPOC_INVALID_ARGUMENT;
+  if (null_in(in, true, true) || out == nullptr || !out->x || !out->u || !out->y)
+    return fail(e, SIPOC_INVALID_ARGUMENT, "NULL LQR input / output");
+  DeviceGuard guard(e->device);
+  launch_lqr_residual(e->dt, to_in(in), LqrOut{out->x, out->u, out->y}, status,
+                      residual_norm, stats, e->batch, e->ld,
+                      static_cast<cudaStream_t>(stream));
+  e->launches += stats != nullptr ? 2 : 1;
+  return check_launch(e, "lqr_residual");
+}
+
+sipoc_error sipoc_pack(sipoc_engine *e, const double *src, double *dst, int64_t size,
+                       void *stream) {
+  if (e == nullptr || src == nullptr || dst == nullptr || size < 0)
+    return SIPOC_INVALID_ARGUMENT;
+  DeviceGuard guard(e->device);
+  launch_pack(src, dst, size, e->batch, e->ld, static_cast<cudaStream_t>(stream));
+  e->launches += 1;
+  return check_launch(e, "pack");
+}
+
+sipoc_error sipoc_unpack(sipoc_engine *e, const double *src, double *dst, int64_t size,
+                         void *stream) {
+  if (e == nullptr || src == nullptr || dst == nullptr || size < 0)
+    return SIPOC_INVALID_ARGUMENT;
+  DeviceGuard guard(e->device);
+  launch_unpack(src, dst, size, e->batch, e->ld, static_cast<cudaStream_t>(stream));
+  e->launches += 1;
+  return check_launch(e, "unpack");
+}
+
+// ---- host-buffer LQR --------------------------------------------------------
+static sipoc_error host_upload_lqr(sipoc_engine *e, const sipoc_lqr_input *in,
+                                   bool matrices, bool vectors) {
+  const double *src[9] = {in->Q, in->M, in->R, in->q, in->r, in->A, in->B, in->c, in->delta};
+  const bool is_vec[9] = {false, false, false, true, true, false, false, true, false};
+  for (int i = 0; i < 9; ++i) {
+    if ((is_vec[i] && !vectors) || (!is_vec[i] && !matrices)) continue;
+    sipoc_error rc = upload(e, src[i], e->h_in[i], lqr_in_size(e->hs, i));
+    if (rc != SIPOC_OK) return rc;
+  }
+  return SIPOC_OK;
+}
+
+static LqrIn host_resident_in(const sipoc_engine *e) {
+  return LqrIn{e->h_in[0], e->h_in[1], e->h_in[2], e->h_in[3], e->h_in[4],
+               e->h_in[5], e->h_in[6], e->h_in[7], e->h_in[8]};
+}
+
+static sipoc_error host_download_out(sipoc_engine *e, const sipoc_lqr_output *out) {
+  const HostStructure &h = e->hs;
+  sipoc_error rc;
+  if ((rc = download(e, e->h_out[0], out->x, h.n_off[h.N])) != SIPOC_OK) return rc;
+  // The staging buffer is reused: order copies on the stream (same stream, so
+  // the unpack of the next array waits for the previous D2H).
+  if ((rc = download(e, e->h_out[1], out->u, h.m_off[h.E])) != SIPOC_OK) return rc;
+  return download(e, e->h_out[2], out->y, h.n_off[h.N]);
+}
+
+sipoc_error sipoc_lqr_factor_solve_host(sipoc_engine *e, const sipoc_lqr_input *in,
+                                        const sipoc_lqr_output *out, int *host_status) {
+  if (e == nullptr || in == nullptr || out == nullptr) return SIPOC_INVALID_ARGUMENT;
+  DeviceGuard guard(e->device);
+  sipoc_error rc;
+  if ((rc = ensure_host_lqr(e)) != SIPOC_OK) return rc;
+  if ((rc = host_upload_lqr(e, in, true, true)) != SIPOC_OK) return rc;
+  rc = lqr_factor_solve_core(e, host_resident_in(e),
+                             LqrOut{e->h_out[0], e->h_out[1], e->h_out[2]}, e->h_status,
+                             e->host_stream);
+  if (rc != SIPOC_OK) return rc;
+  e->host_lqr_factored = false;
+  if ((rc = host_download_out(e, out)) != SIPOC_OK) return rc;
+  if (host_status != nullptr)
+    SIPOC_CUDA(e, cudaMemcpyAsync(host_status, e->h_status, e->batch * sizeof(int),
+                                  cudaMemcpyDeviceToHost, e->host_stream));
+  SIPOC_CUDA(e, cudaStreamSynchronize(e->host_stream));
+  return SIPOC_OK;
+}
+
+sipoc_error sipoc_lqr_factor_host(sipoc_engine *e, const sipoc_lqr_input *in,
+                                  int *host_status) {
+  if (e == nullptr || in == nullptr) return SIPOC_INVALID_ARGUMENT;
+  DeviceGuard guard(e->device);
+  sipoc_error rc;
+  if ((rc = ensure_host_lqr(e)) != SIPOC_OK) return rc;
+  if ((rc = host_upload_lqr(e, in, true, false)) != SIPOC_OK) return rc;
+  if ((rc = lqr_factor_core(e, host_resident_in(e), e->h_status, e->host_stream)) != SIPOC_OK)
+    return rc;
+  e->host_lqr_factored = true;
+  if (host_status != nullptr)
+    SIPOC_CUDA(e, cudaMemcpyAsync(host_status, e->h_status, e->batch * sizeof(int),
+                                  cudaMemcpyDeviceToHost, e->host_stream));
+  SIPOC_CUDA(e, cudaStreamSynchronize(e->host_stream));
+  return SIPOC_OK;
+}
+
+sipoc_error sipoc_lqr_solve_host(sipoc_engine *e, const sipoc_lqr_input *in,
+                                 const sipoc_lqr_output *out) {
+  if (e == nullptr || in == nullptr || out == nullptr) return SIPOC_INVALID_ARGUMENT;
+  if (!e->host_lqr_factored)
+    return fail(e, SIPOC_NOT_FACTORED, "sipoc_lqr_solve_host before sipoc_lqr_factor_host");
+  DeviceGuard guard(e->device);
+  sipoc_error rc;
+  if ((rc = host_upload_lqr(e, in, false, true)) != SIPOC_OK) return rc;
+  rc = lqr_solve_core(e, host_resident_in(e), LqrOut{e->h_out[0], e->h_out[1], e->h_out[2]},
+                      e->host_stream);
+  if (rc != SIPOC_OK) return rc;
+  if ((rc = host_download_out(e, out)) != SIPOC_OK) return rc;
+  SIPOC_CUDA(e, cudaStreamSynchronize(e->host_stream));
+  return SIPOC_OK;
+}
+
+// ---- Newton-KKT -------------------------------------------------------------
+sipoc_error sipoc_kkt_get_sizes(const sipoc_engine *e, sipoc_kkt_sizes *o) {
+  if (e == nullptr || o == nullptr) return SIPOC_INVALID_ARGUMENT;
+  const HostStructure &h = e->hs;
+  o->x_dim = h.x_dim;
+  o->y_dim = h.y_dim;
+  o->z_dim = h.z_dim;
+  o->kkt_dim = h.kkt_dim;
+  o->node_hxx = kkt_model_size(h, 0);
+  o->node_jc = kkt_model_size(h, 1);
+  o->node_jg = kkt_model_size(h, 2);
+  o->edge_hxx = kkt_model_size(h, 3);
+  o->edge_hxu = kkt_model_size(h, 4);
+  o->edge_huu = kkt_model_size(h, 5);
+  o->edge_A = kkt_model_size(h, 6);
+  o->edge_B = kkt_model_size(h, 7);
+  o->edge_jcx = kkt_model_size(h, 8);
+  o->edge_jcu = kkt_model_size(h, 9);
+  o->edge_jgx = kkt_model_size(h, 10);
+  o->edge_jgu = kkt_model_size(h, 11);
+  return SIPOC_OK;
+}
+
+sipoc_error sipoc_kkt_offsets(const sipoc_engine *e, int *x_state, int *x_control, int *y_dyn,
+                              int *y_node_c, int *y_edge_c, int *z_node, int *z_edge) {
+  if (e == nullptr) return SIPOC_INVALID_ARGUMENT;
+  const HostStructure &h = e->hs;
+  auto cp = [](const std::vector<int> &v, int *dst) {
+    if (dst != nullptr) std::copy(v.begin(), v.end(), dst);
+  };
+  cp(h.x_state, x_state);
+  cp(h.x_control, x_control);
+  cp(h.y_dyn, y_dyn);
+  cp(h.y_node_c, y_node_c);
+  cp(h.y_edge_c, y_edge_c);
+  cp(h.z_node, z_node);
+  cp(h.z_edge, z_edge);
+  return SIPOC_OK;
+}
+
+sipoc_error sipoc_kkt_factor(sipoc_engine *e, const sipoc_kkt_model *model, const double *w,
+                             const double *r1, const double *r2, const double *r3, int *ok,
+                             void *stream) {
+  if (e == nullptr) return SIPOC_INVALID_ARGUMENT;
+  if (model_has_null(model) || !w || !r1 || !r2 || !r3 || !ok)
+    return fail(e, SIPOC_INVALID_ARGUMENT, "NULL KKT factor argument");
+  DeviceGuard guard(e->device);
+  return kkt_factor_core(e, to_model(model), w, r1, r2, r3, ok,
+                         static_cast<cudaStream_t>(stream));
+}
+
+sipoc_error sipoc_kkt_solve(sipoc_engine *e, const sipoc_kkt_model *model, const double *b,
+                            double *sol, void *stream) {
+  if (e == nullptr) return SIPOC_INVALID_ARGUMENT;
+  if (model_has_null(model) || !b || !sol)
+    return fail(e, SIPOC_INVALID_ARGUMENT, "NULL KKT solve argument");
+  DeviceGuard guard(e->device);
+  return kkt_solve_core(e, to_model(model), b, sol, static_cast<cudaStream_t>(stream));
+}
+
+sipoc_error sipoc_kkt_apply(sipoc_engine *e, const sipoc_kkt_model *model, const double *w,
+                            const double *r1, const double *r2, const double *r3,
+                            const double *x, double *y, void *stream) {
+  if (e == nullptr) return SIPOC_INVALID_ARGUMENT;
+  if (model_has_null(model) || !w || !r1 || !r2 || !r3 || !x || !y)
+    return fail(e, SIPOC_INVALID_ARGUMENT, "NULL KKT apply argument");
+  DeviceGuard guard(e->device);
+  launch_kkt_apply(e->dt, to_model(model), w, r1, r2, r3, x, y, e->batch, e->ld,
+                   static_cast<cudaStream_t>(stream));
+  e->launches += 1;
+  return check_launch(e, "kkt_apply");
+}
+
+sipoc_error sipoc_kkt_residual(sipoc_engine *e, const sipoc_kkt_model *model, const double *w,
+                               const double *r1, const double *r2, const double *r3,
+                               const double *sol, const double *b, const int *ok,
+                               double *residual_norm, double *stats, void *stream) {
+  if (e == nullptr) return SIPOC_INVALID_ARGUMENT;
+  if (model_has_null(model) || !w || !r1 || !r2 || !r3 || !sol || !b)
+    return fail(e, SIPOC_INVALID_ARGUMENT, "NULL KKT residual argument");
+  DeviceGuard guard(e->device);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  sipoc_error rc;
+  if (e->kkt_product == nullptr &&
+      (rc = alloc_doubles(e, &e->kkt_product, e->hs.kkt_dim)) != SIPOC_OK)
+    return rc;
+  SIPOC_CUDA(e, cudaMemsetAsync(e->kkt_product, 0,
+                                static_cast<size_t>(std::max(1, e->hs.kkt_dim)) * e->ld *
+                                    sizeof(double),
+                                s));
+  launch_kkt_apply(e->dt, to_model(model), w, r1, r2, r3, sol, e->kkt_product, e->batch,
+                   e->ld, s);
+  launch_kkt_residual(e->dt, e->kkt_product, b, ok, residual_norm, stats, e->batch, e->ld, s);
+  e->launches += stats != nullptr ? 3 : 2;
+  return check_launch(e, "kkt_residual");
+}
+
+static KktModel host_resident_model(const sipoc_engine *e) {
+  return KktModel{e->hk_model[0], e->hk_model[1], e->hk_model[2],  e->hk_model[3],
+                  e->hk_model[4], e->hk_model[5], e->hk_model[6],  e->hk_model[7],
+                  e->hk_model[8], e->hk_model[9], e->hk_model[10], e->hk_model[11]};
+}
+
+sipoc_error sipoc_kkt_factor_host(sipoc_engine *e, const sipoc_kkt_model *m, const double *w,
+                                  const double *r1, const double *r2, const double *r3,
+                                  int *host_ok) {
+  if (e == nullptr || m == nullptr) return SIPOC_INVALID_ARGUMENT;
+  DeviceGuard guard(e->device);
+  sipoc_error rc;
+  if ((rc = ensure_host_kkt(e)) != SIPOC_OK) return rc;
+  const double *src[12] = {m->node_hxx, m->node_jc,  m->node_jg,  m->edge_hxx,
+                           m->edge_hxu, m->edge_huu, m->edge_A,   m->edge_B,
+                           m->edge_jcx, m->edge_jcu, m->edge_jgx, m->edge_jgu};
+  for (int i = 0; i < 12; ++i)
+    if ((rc = upload(e, src[i], e->hk_model[i], kkt_model_size(e->hs, i))) != SIPOC_OK)
+      return rc;
+  const double *reg[4] = {w, r1, r2, r3};
+  const int64_t reg_sizes[4] = {e->hs.z_dim, e->hs.x_dim, e->hs.y_dim, e->hs.z_dim};
+  for (int i = 0; i < 4; ++i)
+    if ((rc = upload(e, reg[i], e->hk_reg[i], reg_sizes[i])) != SIPOC_OK) return rc;
+  rc = kkt_factor_core(e, host_resident_model(e), e->hk_reg[0], e->hk_reg[1], e->hk_reg[2],
+                       e->hk_reg[3], e->h_status, e->host_stream);
+  if (rc != SIPOC_OK) return rc;
+  if (host_ok != nullptr)
+    SIPOC_CUDA(e, cudaMemcpyAsync(host_ok, e->h_status, e->batch * sizeof(int),
+                                  cudaMemcpyDeviceToHost, e->host_stream));
+  SIPOC_CUDA(e, cudaStreamSynchronize(e->host_stream));
+  return SIPOC_OK;
+}
+
+sipoc_error sipoc_kkt_solve_host(sipoc_engine *e, const double *b, double *sol) {
+  if (e == nullptr || b == nullptr || sol == nullptr) return SIPOC_INVALID_ARGUMENT;
+  if (!e->host_kkt_ready || !e->kkt_factored)
+    return fail(e, SIPOC_NOT_FACTORED, "sipoc_kkt_solve_host before sipoc_kkt_factor_host");
+  DeviceGuard guard(e->device);
+  sipoc_error rc;
+  if ((rc = upload(e, b, e->hk_vec[0], e->hs.kkt_dim)) != SIPOC_OK) return rc;
+  rc = kkt_solve_core(e, host_resident_model(e), e->hk_vec[0], e->hk_vec[1], e->host_stream);
+  if (rc != SIPOC_OK) return rc;
+  if ((rc = download(e, e->hk_vec[1], sol, e->hs.kkt_dim)) != SIPOC_OK) return rc;
+  SIPOC_CUDA(e, cudaStreamSynchronize(e->host_stream));
+  return SIPOC_OK;
+}
+
+sipoc_error sipoc_kkt_apply_host(sipoc_engine *e, const double *w, const double *r1,
+                                 const double *r2, const double *r3, const double *x,
+                                 double *y) {
+  if (e == nullptr || !w || !r1 || !r2 || !r3 || !x || !y) return SIPOC_INVALID_ARGUMENT;
+  if (!e->host_kkt_ready)
+    return fail(e, SIPOC_NOT_FACTORED,
+                "sipoc_kkt_apply_host needs the model uploaded by sipoc_kkt_factor_host");
+  DeviceGuard guard(e->device);
+  sipoc_error rc;
+  const double *reg[4] = {w, r1, r2, r3};
+  const int64_t reg_sizes[4] = {e->hs.z_dim, e->hs.x_dim, e->hs.y_dim, e->hs.z_dim};
+  for (int i = 0; i < 4; ++i)
+    if ((rc = upload(e, reg[i], e->hk_reg[i], reg_sizes[i])) != SIPOC_OK) return rc;
+  if ((rc = upload(e, x, e->hk_vec[0], e->hs.kkt_dim)) != SIPOC_OK) return rc;
+  if ((rc = upload(e, y, e->hk_vec[1], e->hs.kkt_dim)) != SIPOC_OK) return rc;
+  launch_kkt_apply(e->dt, host_resident_model(e), e->hk_reg[0], e->hk_reg[1], e->hk_reg[2],
+                   e->hk_reg[3], e->hk_vec[0], e->hk_vec[1], e->batch, e->ld, e->host_stream);
+  e->launches += 1;
+  if ((rc = check_launch(e, "kkt_apply")) != SIPOC_OK) return rc;
+  if ((rc = download(e, e->hk_vec[1], y, e->hs.kkt_dim)) != SIPOC_OK) return rc;
+  SIPOC_CUDA(e, cudaStreamSynchronize(e->host_stream));
+  return SIPOC_OK;
+}
+
+sipoc_error sipoc_generate_lqr_benchmark(sipoc_engine *e, uint64_t seed, int64_t problem_offset,
+                                         double *Q, double *M, double *R, double *q, double *r,
+                                         double *A, double *B, double *c, double *delta,
+                                         void *stream) {
+  if (e == nullptr) return SIPOC_INVALID_ARGUMENT;
+  if (!Q || !M || !R || !q || !r || !A || !B || !c || !delta)
+    return fail(e, SIPOC_INVALID_ARGUMENT, "NULL generator output");
+  const HostStructure &h = e->hs;
+  if (!(h.is_chain && h.is_uniform))
+    return fail(e, SIPOC_UNSUPPORTED, "the benchmark generator covers uniform chains only");
+  DeviceGuard guard(e->device);
+  e->launches += launch_generate_lqr_benchmark(seed, problem_offset, h.E, h.n[0],
+                                               h.E > 0 ? h.m[0] : 0, e->batch, e->ld, Q, M, R,
+                                               q, r, A, B, c, delta,
+                                               static_cast<cudaStream_t>(stream));
+  return check_launch(e, "generate_lqr_benchmark");
+}
+
+}  // extern "C"

@@ -1,0 +1,42 @@
+// Shape-specialised Riccati kernels for uniform chains (interface).
+//
+// A FastPlan is a set of kernels compiled for one (state_dim, control_dim)
+// pair; riccati_fast.cu instantiates the template for the BASELINE shapes and
+// the reference benchmark grid.  The engine falls back to the generic
+// thread-per-problem kernels for every other structure.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "generic_kernels.cuh"
+
+namespace sipoc {
+
+struct FastArgs {
+  LqrIn in;
+  LqrOut out;
+  int *status;      // device int[ld] or nullptr
+  double *store;    // factorization kept for later solves (W, K, LG per stage)
+  double *scratch;  // per-problem spill of the fused / solve rollout (v, k)
+  int64_t batch, ld;
+  int num_edges;
+};
+
+struct FastPlan {
+  const char *name;
+  int n, m;
+  // doubles per problem the engine must provide
+  int64_t (*store_elems)(int num_edges);
+  int64_t (*scratch_elems)(int num_edges);
+  // Each returns the number of kernels it launched.
+  int (*factor)(const FastArgs &, cudaStream_t);
+  int (*solve)(const FastArgs &, cudaStream_t);
+  int (*factor_solve)(const FastArgs &, cudaStream_t);
+};
+
+// nullptr when no specialised kernel exists for (n, m).
+const FastPlan *select_fast_plan(int n, int m);
+
+}  // namespace sipoc

@@ -1,0 +1,133 @@
+"""Host-side mirror of the reference's ``CallbackProvider`` (helpers.hpp:7-33).
+
+Batched and restricted to ``theta_dim == 0``: ``factor`` / ``solve`` /
+``add_Kx_to_y`` keep the reference's argument meaning; flat vectors use the
+reference wire format ``[x | y | z]`` (types.cpp:24-64) and every array gains a
+batch axis.  All computation goes through the C ABI (sipoc_kkt_*).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import numpy as np
+
+from . import _capi
+from ._capi import lib
+from .lqr import Dimensions, Engine, SipocError, Topology, _host_ptr, _ip
+
+
+def _model_struct(model: dict, host: bool, keep: list) -> _capi.KktModel:
+    s = _capi.KktModel()
+    for k in _capi.KKT_MODEL_FIELDS:
+        a = model[k]
+        if host:
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            keep.append(a)
+            # ctypes needs a non-NULL pointer even for empty blocks.
+            setattr(s, k, _host_ptr(a) if a.size else _host_ptr(np.zeros(1)))
+        else:
+            setattr(s, k, a.data_ptr())
+    return s
+
+
+class CallbackProvider:
+    """Batched Newton-KKT linear solve behind the reference's callback names."""
+
+    def __init__(self, dimensions: Dimensions, topology: Topology, batch: int = 1,
+                 device: Optional[int] = None, force_generic: bool = False):
+        self.engine = Engine(dimensions, topology, batch, device, force_generic)
+        self.batch = int(batch)
+        # validate_input(...) == SUCCESS  (helpers.cpp:25-26)
+        self.input_is_valid_ = self.engine.create_status == _capi.SIPOC_OK
+        if not self.input_is_valid_ and self.engine.create_status not in (
+                _capi.SIPOC_INVALID_TOPOLOGY, _capi.SIPOC_INVALID_DIMENSIONS):
+            raise SipocError(self.engine.create_status, "sipoc_create failed")
+
+    @property
+    def sizes(self) -> dict:
+        return self.engine.kkt_sizes
+
+    def offsets(self) -> dict:
+        E = self.engine.topology.num_edges
+        names_n = ("x_state", "y_dyn", "y_node_c", "z_node")
+        names_e = ("x_control", "y_edge_c", "z_edge")
+        o = {k: np.zeros(E + 1, np.int32) for k in names_n}
+        o.update({k: np.zeros(max(E, 1), np.int32) for k in names_e})
+        self.engine._check(lib.sipoc_kkt_offsets(
+            self.engine._handle, _ip(o["x_state"]), _ip(o["x_control"]), _ip(o["y_dyn"]),
+            _ip(o["y_node_c"]), _ip(o["y_edge_c"]), _ip(o["z_node"]), _ip(o["z_edge"])))
+        for k in names_e:
+            o[k] = o[k][:E]
+        return o
+
+    # -- device path ------------------------------------------------------------
+    def pack_model(self, host_model: dict) -> dict:
+        return {k: self.engine.pack(host_model[k]) for k in _capi.KKT_MODEL_FIELDS}
+
+    def factor(self, model: dict, w, r1, r2, r3, ok=None, stream=None):
+        """Returns a device int32 tensor: 1 where the reference's factor returns true."""
+        e = self.engine
+        if not self.input_is_valid_:
+            return np.zeros(self.batch, np.int32)  # helpers.cpp:244-246
+        ok = e.empty_int() if ok is None else ok
+        m = _model_struct(model, False, [])
+        e._check(lib.sipoc_kkt_factor(e._handle, ctypes.byref(m), w.data_ptr(), r1.data_ptr(),
+                                      r2.data_ptr(), r3.data_ptr(), ok.data_ptr(),
+                                      e.stream_ptr(stream)))
+        return ok
+
+    def solve(self, model: dict, b, sol, stream=None) -> None:
+        e = self.engine
+        m = _model_struct(model, False, [])
+        e._check(lib.sipoc_kkt_solve(e._handle, ctypes.byref(m), b.data_ptr(), sol.data_ptr(),
+                                     e.stream_ptr(stream)))
+
+    def add_Kx_to_y(self, model: dict, w, r1, r2, r3, x, y, stream=None) -> None:
+        """y += K(w, r1, r2, r3) x on [x|y|z] vectors (helpers.cpp:953-977)."""
+        e = self.engine
+        m = _model_struct(model, False, [])
+        e._check(lib.sipoc_kkt_apply(e._handle, ctypes.byref(m), w.data_ptr(), r1.data_ptr(),
+                                     r2.data_ptr(), r3.data_ptr(), x.data_ptr(), y.data_ptr(),
+                                     e.stream_ptr(stream)))
+
+    def residual(self, model: dict, w, r1, r2, r3, sol, b, ok=None, stream=None):
+        """(||K sol - b||_2 per problem, 4 all-reducible statistics)."""
+        e = self.engine
+        torch = e._torch()
+        norms = torch.zeros((e.batch_stride,), dtype=torch.float64, device=e.torch_device())
+        stats = torch.zeros((4,), dtype=torch.float64, device=e.torch_device())
+        m = _model_struct(model, False, [])
+        e._check(lib.sipoc_kkt_residual(
+            e._handle, ctypes.byref(m), w.data_ptr(), r1.data_ptr(), r2.data_ptr(),
+            r3.data_ptr(), sol.data_ptr(), b.data_ptr(),
+            None if ok is None else ok.data_ptr(), norms.data_ptr(), stats.data_ptr(),
+            e.stream_ptr(stream)))
+        return norms, stats
+
+    # -- host path ----------------------------------------------------------------
+    def factor_host(self, model: dict, w, r1, r2, r3) -> np.ndarray:
+        e, keep = self.engine, []
+        if not self.input_is_valid_:
+            return np.zeros(self.batch, np.int32)
+        m = _model_struct(model, True, keep)
+        regs = [np.ascontiguousarray(a, dtype=np.float64) for a in (w, r1, r2, r3)]
+        ok = np.zeros(self.batch, np.int32)
+        e._check(lib.sipoc_kkt_factor_host(e._handle, ctypes.byref(m),
+                                           *[_host_ptr(a) for a in regs], _host_ptr(ok)))
+        return ok
+
+    def solve_host(self, b: np.ndarray) -> np.ndarray:
+        e = self.engine
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        sol = np.zeros_like(b)
+        e._check(lib.sipoc_kkt_solve_host(e._handle, _host_ptr(b), _host_ptr(sol)))
+        return sol
+
+    def add_Kx_to_y_host(self, w, r1, r2, r3, x, y=None) -> np.ndarray:
+        e = self.engine
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (w, r1, r2, r3, x)]
+        y = np.zeros_like(arrs[4]) if y is None else np.array(y, dtype=np.float64, order="C")
+        e._check(lib.sipoc_kkt_apply_host(e._handle, *[_host_ptr(a) for a in arrs],
+                                          _host_ptr(y)))
+        return y

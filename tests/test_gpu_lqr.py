@@ -1,0 +1,246 @@
+"""GPU parity tests of the LQR path, all through the C ABI (libsipoc.so).
+
+Every case restates a reference test (tests/lqr_test.cpp) or a reference
+benchmark configuration and compares the CUDA result with the CPU oracle on the
+same inputs.  Tolerance: 1e-9 relative per problem on x, u, y (north_star); the
+reference's own residual bars (1e-12) are checked as well.
+"""
+import numpy as np
+import pytest
+
+import problem_gen as pg
+import reference_fixtures as fx
+from gpu_helpers import REL_TOL, assert_lqr_parity, gpu_lqr_factor_solve, rel_err, to_structs
+from oracle import pyoracle
+from oracle.pyoracle import Structure
+from sip_optimal_control_b200 import LQR, FactorStatus
+
+pytestmark = pytest.mark.gpu
+
+
+def _tile(one: dict, batch: int) -> dict:
+    return {k: np.repeat(v, batch, axis=0) for k, v in one.items()}
+
+
+# --- reference fixtures ---------------------------------------------------------
+@pytest.mark.parametrize("builder", [fx.nonuniform_delta_chain, fx.branch_tree,
+                                     fx.variable_dim_branch_tree, fx.five_node_tree])
+@pytest.mark.parametrize("fused", [True, False])
+def test_reference_fixtures_match_oracle(builder, fused):
+    # lqr_test.cpp:229-263, :411-429, :641-659, :982-1013
+    s, p = builder()
+    host = _tile(fx.pack_problem(**p), 3)
+    ref = pyoracle.lqr_factor_solve(s, host)
+    gpu, lqr = gpu_lqr_factor_solve(s, host, fused=fused)
+    assert (gpu["status"] == 0).all()
+    assert_lqr_parity(gpu, ref, 1e-12)
+    assert gpu["residual"].max() < 1e-12          # the reference's own bar
+    # the oracle's residual function agrees with the device one
+    r = pyoracle.lqr_residual(s, host, gpu["x"], gpu["u"], gpu["y"])
+    assert np.abs(r - gpu["residual"]).max() < 1e-13
+
+
+def test_matches_dense_kkt_on_five_node_tree():  # lqr_test.cpp:982-1013
+    s, p = fx.five_node_tree()
+    gpu, _ = gpu_lqr_factor_solve(s, fx.pack_problem(**p))
+    xs, us, ys = fx.dense_kkt_solve(s, p)
+    assert rel_err(gpu["x"], np.concatenate(xs)[None])[0] < 1e-10
+    assert rel_err(gpu["u"], np.concatenate(us)[None])[0] < 1e-10
+    assert rel_err(gpu["y"], np.concatenate(ys)[None])[0] < 1e-10
+
+
+def test_compiled_topology_orders():  # lqr_test.cpp:931-953
+    s, _ = fx.five_node_tree()
+    dims, topo = to_structs(s)
+    lqr = LQR(dims, topo, 2)
+    co, ce, pre, post = lqr.engine.compiled_topology()
+    assert co.tolist() == [0, 2, 4, 4, 4, 4]
+    assert ce.tolist() == [0, 1, 2, 3]
+    assert pre.tolist() == [0, 1, 3, 4, 2]
+    assert post.tolist() == [2, 4, 3, 1, 0]
+
+
+def test_invalid_topology_is_latched():  # lqr_test.cpp:452-464
+    s = Structure([0, 0], [1, 1], 0, [2, 2, 2], [1, 1])
+    dims, topo = to_structs(s)
+    lqr = LQR(dims, topo, 2)
+    assert lqr.traversal_status_ == FactorStatus.INVALID_TOPOLOGY
+    st = lqr.factor_with_status({})
+    assert (np.asarray(st) == FactorStatus.INVALID_TOPOLOGY).all()
+    assert not np.asarray(lqr.factor({})).any()
+
+
+# --- status codes (lqr_test.cpp:188-227), mixed inside one batch ----------------
+@pytest.mark.parametrize("force_generic", [True, False])
+def test_status_codes_per_problem(force_generic):
+    n, m, T = 2, 1, 2
+    s, p = fx.identity_chain(n, m, T)
+    host = _tile(fx.pack_problem(**p), 6)
+    sz = pyoracle.lqr_sizes(s)
+    # problem 1: delta[T][0] = 0 -> INVALID_DELTA (lqr_test.cpp:206-211)
+    host["delta"][1, T * n + 0] = 0.0
+    # problem 2: Q[T] = -2 I -> F failure (cf. lqr_test.cpp:213-219)
+    host["Q"][2, T * n * n:] = (-2.0 * np.eye(n)).flatten()
+    # problem 3: Q[T] = 0, R[T-1] = -1 -> G failure (cf. lqr_test.cpp:221-227)
+    host["Q"][3, T * n * n:] = 0.0
+    host["R"][3, (T - 1) * m * m] = -1.0
+    # problem 4: negative delta at the root AND a G failure deeper: post-order
+    # visits the leaf side first, so G wins (lqr.cpp:696-700 before :722-727).
+    host["delta"][4, 1] = -1.0
+    host["R"][4, (T - 1) * m * m] = -50.0
+    # problem 5 stays valid.
+    ref = pyoracle.lqr_factor_solve(s, host)
+    assert ref["status"].tolist() == [0, 1, 2, 3, 3, 0]
+    gpu, _ = gpu_lqr_factor_solve(s, host, force_generic=force_generic)
+    assert gpu["status"].tolist() == ref["status"].tolist()
+    good = ref["status"] == 0
+    assert_lqr_parity(gpu, ref, REL_TOL, mask=good)
+    assert gpu["stats"][2] == 4 and gpu["stats"][3] == 6   # failed, count
+    del sz
+
+
+def test_single_stage_failure_fixtures():  # lqr_test.cpp:213-227 verbatim (n=m=T=1)
+    s, p = fx.identity_chain(1, 1, 1)
+    p["Q"][1][0, 0] = -2.0
+    gpu, _ = gpu_lqr_factor_solve(s, fx.pack_problem(**p))
+    assert gpu["status"][0] == FactorStatus.F_FACTORIZATION_FAILURE
+    s, p = fx.identity_chain(1, 1, 1)
+    p["Q"][1][0, 0] = 0.0
+    p["R"][0][0, 0] = -1.0
+    gpu, _ = gpu_lqr_factor_solve(s, fx.pack_problem(**p))
+    assert gpu["status"][0] == FactorStatus.G_FACTORIZATION_FAILURE
+
+
+# --- benchmark-distribution chains (lqr_benchmark.cpp:61-96, :537-545) -----------
+SHAPES = [(4, 1, 16), (4, 1, 100), (6, 2, 32), (8, 3, 16), (12, 4, 50), (16, 4, 16),
+          (5, 2, 7), (3, 3, 4)]
+
+
+@pytest.mark.parametrize("n,m,T", SHAPES)
+@pytest.mark.parametrize("force_generic", [True, False])
+def test_benchmark_chains_match_oracle(n, m, T, force_generic):
+    batch = 37  # ragged: not a multiple of the warp / tile size
+    s, host = pg.lqr_benchmark_batch(n, m, T, batch, seed=100 + n + m + T,
+                                     dense_M=(T % 2 == 0))
+    ref = pyoracle.lqr_factor_solve(s, host)
+    assert (ref["status"] == 0).all()
+    gpu, lqr = gpu_lqr_factor_solve(s, host, force_generic=force_generic)
+    assert (gpu["status"] == 0).all()
+    assert_lqr_parity(gpu, ref, REL_TOL)
+    # residual parity: both are rounding noise relative to the data; compare
+    # on the scale of the right-hand side.
+    scale = np.linalg.norm(np.concatenate([host["q"], host["r"], host["c"]], axis=1), axis=1)
+    assert (gpu["residual"] / scale).max() < 1e-9
+    assert np.abs(gpu["residual"] - ref["residual"]).max() / scale.max() < 1e-9
+    assert np.isclose(gpu["stats"][1], gpu["residual"].max())
+    assert np.isclose(gpu["stats"][0], (gpu["residual"] ** 2).sum())
+    assert gpu["stats"][3] == batch
+    if not force_generic and (n, m) in ((4, 1), (12, 4), (6, 2), (8, 3), (16, 4)):
+        assert "generic" not in lqr.engine.kernel_variant, lqr.engine.kernel_variant
+
+
+@pytest.mark.parametrize("n,m,T", [(4, 1, 20), (12, 4, 10), (5, 2, 7)])
+def test_factor_once_solve_many(n, m, T):
+    # BM_LQRSolve semantics (lqr_benchmark.cpp:611-638): re-solve with new
+    # q, r, c against a kept factorization.
+    batch = 19
+    s, host = pg.lqr_benchmark_batch(n, m, T, batch, seed=7)
+    dims, topo = to_structs(s)
+    lqr = LQR(dims, topo, batch)
+    inp = lqr.pack_input(host)
+    out = lqr.alloc_output()
+    status = lqr.factor_with_status(inp)
+    assert (status[:batch].cpu().numpy() == 0).all()
+    rng = np.random.default_rng(3)
+    for rep in range(3):
+        h2 = dict(host)
+        for k in ("q", "r", "c"):
+            h2[k] = rng.standard_normal(host[k].shape)
+            inp[k] = lqr.engine.pack(h2[k])
+        lqr.solve(inp, out)
+        gpu = lqr.unpack_output(out)
+        ref = pyoracle.lqr_factor_solve(s, h2)
+        assert_lqr_parity(gpu, ref, REL_TOL)
+
+
+def test_variable_dimension_chain_and_tree_batches():
+    # per-node dims like tests/variable_dimensions_test.cpp:266-271, tiled
+    # along a longer horizon, plus a deeper tree.
+    chain = Structure.chain(9, [2, 1, 3, 2, 1, 3, 2, 1, 3, 2], [1, 2, 1, 2, 1, 2, 1, 2, 1])
+    tree = Structure([0, 0, 1, 1, 2, 5], [1, 2, 3, 4, 5, 6], 0, [3, 2, 4, 1, 2, 3, 2],
+                     [2, 1, 1, 2, 3, 1])
+    for s in (chain, tree):
+        host = pg.variable_tree_batch(s, 45, seed=11)
+        ref = pyoracle.lqr_factor_solve(s, host)
+        assert (ref["status"] == 0).all()
+        for fused in (True, False):
+            gpu, lqr = gpu_lqr_factor_solve(s, host, fused=fused)
+            assert "generic" in lqr.engine.kernel_variant
+            assert (gpu["status"] == 0).all()
+            assert_lqr_parity(gpu, ref, 1e-11)
+            assert gpu["residual"].max() < 1e-10
+
+
+def test_host_buffer_entry_points():
+    # the reference-facing call: host arrays in, host arrays out
+    n, m, T, batch = 6, 2, 12, 21
+    s, host = pg.lqr_benchmark_batch(n, m, T, batch, seed=5, dense_M=True)
+    ref = pyoracle.lqr_factor_solve(s, host)
+    dims, topo = to_structs(s)
+    lqr = LQR(dims, topo, batch)
+    got = lqr.factor_solve_host(host)
+    assert (got["status"] == 0).all()
+    assert_lqr_parity(got, ref, REL_TOL)
+    # factor-once / solve-many on host buffers
+    st = lqr.factor_host(host)
+    assert (st == 0).all()
+    h2 = dict(host)
+    h2["q"] = host["q"] * 0.5 + 1.0
+    got2 = lqr.solve_host(h2)
+    ref2 = pyoracle.lqr_factor_solve(s, h2)
+    assert_lqr_parity(got2, ref2, REL_TOL)
+    assert lqr.engine.launch_count > 0
+
+
+def test_pack_unpack_round_trip_and_padding():
+    s = Structure.chain(3, 2, 1)
+    dims, topo = to_structs(s)
+    lqr = LQR(dims, topo, 45)
+    assert lqr.engine.batch_stride == 64
+    a = np.random.default_rng(0).standard_normal((45, 77))
+    dev = lqr.engine.pack(a)
+    assert tuple(dev.shape) == (77, 64)
+    assert np.array_equal(dev[:, :45].cpu().numpy(), a.T)
+    assert (dev[:, 45:].cpu().numpy() == 0).all()
+    assert np.array_equal(lqr.engine.unpack(dev, 77), a)
+
+
+def test_benchmark_generator_distribution():
+    # lqr_benchmark.cpp:61-96: structure of the generated data
+    n, m, T, batch = 6, 2, 9, 64
+    s = Structure.chain(T, n, m)
+    dims, topo = to_structs(s)
+    lqr = LQR(dims, topo, batch)
+    inp = lqr.generate_benchmark(seed=1234, problem_offset=0)
+    sz = lqr.engine.lqr_sizes
+    h = {k: lqr.engine.unpack(inp[k], sz[k]) for k in sz if k in inp}
+    Q = h["Q"].reshape(batch, T + 1, n, n)
+    R = h["R"].reshape(batch, T, m, m)
+    A = h["A"].reshape(batch, T, n, n)
+    assert np.array_equal(Q, np.swapaxes(Q, -1, -2)) and np.array_equal(R, np.swapaxes(R, -1, -2))
+    assert np.linalg.eigvalsh(Q).min() > 0 and np.linalg.eigvalsh(R).min() > 1.0
+    assert (h["M"] == 0).all()
+    assert h["delta"].min() >= 1e-3 and h["delta"].max() <= 0.101
+    assert abs(h["q"].mean()) < 0.1 and abs(h["q"].std() - 1.0) < 0.1
+    offdiag = A[:, :, ~np.eye(n, dtype=bool)]
+    assert abs(offdiag.std() - 0.05) < 0.01 and abs(np.diagonal(A, axis1=2, axis2=3).mean() - 1) < 0.02
+    # shards regenerate their own slice: offset 32 of the same seed == tail
+    lqr2 = LQR(dims, topo, 32)
+    inp2 = lqr2.generate_benchmark(seed=1234, problem_offset=32)
+    assert np.array_equal(lqr2.engine.unpack(inp2["A"], sz["A"]), h["A"][32:])
+    # and the generated problems solve to the oracle's answer
+    out = lqr.alloc_output()
+    st = lqr.factor_solve(inp, out)
+    assert (st[:batch].cpu().numpy() == 0).all()
+    ref = pyoracle.lqr_factor_solve(s, h)
+    assert_lqr_parity(lqr.unpack_output(out), ref, REL_TOL)
