@@ -1,0 +1,445 @@
+#!/usr/bin/env python
+"""Headline benchmark: batched regularized-LQR factor + solve, solves/sec in FP64.
+
+One *step* = one pass of the hot path over one batch of synthetic problems:
+the factor + solve of every problem of the batch (reference loop body of
+BM_LQRFactorSolve, benchmarks/lqr_benchmark.cpp:653-663) followed by the
+failure-flag reduction a Newton iteration all-reduces.  Inputs are resident in
+HBM in the engine layout when the timed region starts (``value``); ``e2e`` is
+the same metric through the host-buffer C-ABI call with the host<->device
+copies inside the timed region.
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --steps K --warmup W     # CPU reference arm
+
+For N > 1 launch under torch.distributed.run (one rank per GPU); the batch is
+sharded with no data-path collective, the only traffic being the all-reduce of
+the 4-double statistics vector per step.  Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# BASELINE.json configs: (state dim n, control dim m, horizon T, batch).
+WORKLOADS = {
+    "cartpole": dict(n=4, m=1, T=100, batch=16384),
+    "quadrotor": dict(n=12, m=4, T=50, batch=65536),
+    "humanoid": dict(n=64, m=24, T=32, batch=4096),
+}
+DEFAULT_WORKLOAD = "quadrotor"  # the config north_star quotes its target on
+METRIC = "batched LQR factor+solve solves/sec (FP64)"
+UNIT = "solves/s"
+FP64_PEAK_TFLOPS = 36.8  # DFMA peak measured on this pool (profiles/microbench)
+
+
+def algorithmic_bytes(n, m, T):
+    """compulsory in + out bytes of one factor+solve."""
+    inb = 8 * ((T + 1) * (n * n + 3 * n) + T * (n * n + 2 * n * m + m * m + m))
+    outb = 8 * ((T + 1) * 2 * n + T * m)
+    return inb, outb
+
+
+def algorithmic_flops(n, m, T):
+    """the reference's operation count of one factor+solve."""
+    factor = T * (19 * n ** 3 / 3 + 6 * m * n * n + 4 * m * m * n + m ** 3 / 3) \
+        + n ** 3 / 3 + 2 * (T + 1) * n * n
+    solve = T * (10 * n * n + 8 * n * m + 2 * m * m) + 4 * n * n
+    return factor + solve
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+# --------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md "clocks DURING the timed region")
+# --------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.samples = []  # (host time, sm MHz, max MHz, [reasons])
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "50", "-i", str(gpu_index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm, mx = float(parts[0]), float(parts[1])
+            except ValueError:
+                continue
+            reasons = [n for n, v in zip(self.NAMES, parts[2:6]) if v.lower().startswith("active")]
+            self.samples.append((time.time(), sm, mx, reasons))
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, t0: float, t1: float):
+        inside = [s for s in self.samples if t0 <= s[0] <= t1]
+        window = "timed region"
+        if not inside:  # region shorter than the sampling period
+            inside = [s for s in self.samples if t0 - 0.5 <= s[0] <= t1 + 0.2]
+            window = "timed region +-0.5 s"
+        if not inside:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        reasons = sorted({r for s in inside for r in s[3]})
+        return {"sm_mhz": float(np.median([s[1] for s in inside])),
+                "sm_max_mhz": float(max(s[2] for s in inside)), "reasons": reasons,
+                "samples": len(inside), "window": window}
+
+
+# --------------------------------------------------------------------------
+# host-side synthetic problems (reference arm / cpu baseline): the distribution
+# of benchmarks/lqr_benchmark.cpp:61-96, numpy stream.
+# --------------------------------------------------------------------------
+def host_problems(n, m, T, batch, seed):
+    rng = np.random.default_rng(seed)
+
+    def spd(count, d, shift):
+        Z = rng.standard_normal((batch, count, d, d))
+        return np.einsum("bckj,bcki->bcij", Z, Z) + shift * np.eye(d)
+
+    def cm(x):
+        return np.ascontiguousarray(np.swapaxes(x, -1, -2)).reshape(batch, -1)
+
+    return dict(
+        Q=cm(spd(T + 1, n, 1e-3)), M=np.zeros((batch, T * n * m)), R=cm(spd(T, m, 1.01)),
+        q=rng.standard_normal((batch, (T + 1) * n)), r=rng.standard_normal((batch, T * m)),
+        A=cm(0.05 * rng.standard_normal((batch, T, n, n)) + np.eye(n)),
+        B=cm(0.1 * rng.standard_normal((batch, T, n, m))),
+        c=rng.standard_normal((batch, (T + 1) * n)),
+        delta=1e-3 + 1e-1 * rng.random((batch, (T + 1) * n)))
+
+
+def cpu_time_sample(wl, sample, nthreads, repeats=1, host=None):
+    """Seconds for the oracle to factor+solve `sample` problems, `repeats` times."""
+    from oracle import pyoracle
+
+    s = pyoracle.Structure.chain(wl["T"], wl["n"], wl["m"])
+    if host is None:
+        host = host_problems(wl["n"], wl["m"], wl["T"], sample, seed=1234)
+    out = pyoracle.lqr_factor_solve(s, host, solve=True, residual=False, repeats=repeats,
+                                    nthreads=nthreads)
+    assert (out["status"] == 0).all()
+    return out["seconds"], host
+
+
+def cpu_baseline(wl, target_seconds=10.0):
+    """Oracle (port of the reference) across all host cores on a bounded sample."""
+    from oracle import pyoracle
+
+    cores = pyoracle.max_threads()
+    sample = max(cores * 8, 64)
+    _, host = cpu_time_sample(wl, sample, cores)  # warm-up: page in, spin up the threads
+    total, reps = 0.0, 0
+    while total < target_seconds and reps < 100000:
+        secs, _ = cpu_time_sample(wl, sample, cores, host=host)
+        total += secs
+        reps += 1
+    value = sample * reps / total
+    return {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{sample} problems of the workload x {reps} passes "
+                      f"({total:.1f} s), one problem per OpenMP thread, oracle/liboracle.so"}
+
+
+# --------------------------------------------------------------------------
+def run_reference(args, wl, name):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import pyoracle
+
+    cores = pyoracle.max_threads()
+    sample = max(cores * 4, 64)
+    _, host = cpu_time_sample(wl, sample, cores)
+    secs, _ = cpu_time_sample(wl, sample, cores, host=host)
+    # size one step to about one second of wall time
+    per_problem = secs / sample
+    sample = int(max(cores, min(65536, 1.0 / max(per_problem, 1e-9))))
+    sample = (sample + cores - 1) // cores * cores
+    host = host_problems(wl["n"], wl["m"], wl["T"], sample, seed=1234)
+    for _ in range(args.warmup):
+        cpu_time_sample(wl, sample, cores, host=host)
+    total = 0.0
+    for _ in range(args.steps):
+        s, _ = cpu_time_sample(wl, sample, cores, host=host)
+        total += s
+    value = sample * args.steps / total
+    desc = (f"{sample} problems per step, one problem per OpenMP thread over {cores} threads; "
+            "Eigen-free port of lqr.cpp (the reference itself needs Eigen, absent here)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": name, **wl, "batch": sample,
+                   "note": "host CPU arm: bounded sample of the workload per step"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------
+def load_traffic(variant, name):
+    """Per-launch DRAM traffic of the dominant kernel from the committed ncu capture."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f).get(name, {}).get(variant)
+    except Exception:
+        return None
+
+
+def run_ours(args, wl, name):
+    import torch
+    import torch.distributed as dist
+
+    from sip_optimal_control_b200 import LQR, Dimensions, Topology, _capi
+    from sip_optimal_control_b200._capi import lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus, (world, args.gpus)
+
+    n, m, T = wl["n"], wl["m"], wl["T"]
+    total_batch = wl["batch"] * (world if args.scaling == "weak" else 1)
+    batch = wl["batch"] if args.scaling == "weak" else wl["batch"] // world
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+
+    lqr = LQR(Dimensions.uniform(T, n, m), Topology.chain(T), batch, device=local_rank,
+              force_generic=args.force_generic)
+    eng = lqr.engine
+    inp = lqr.generate_benchmark(seed=args.seed, problem_offset=rank * batch)
+    out = lqr.alloc_output()
+    status = eng.empty_int()
+    stats = torch.zeros(4, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    sp = eng.stream_ptr(stream)
+
+    def step():
+        lqr.factor_solve(inp, out, status=status, stream=stream)
+        eng._check(lib.sipoc_status_stats(eng._handle, status.data_ptr(), stats.data_ptr(), sp))
+        if world > 1:
+            dist.all_reduce(stats)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches0 = eng.launch_count
+    lib.sipoc_profile_enable(eng._handle, 1)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.time()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    t1 = time.time()
+    ms_total = ev0.elapsed_time(ev1)
+    gpu_launches = eng.launch_count - launches0
+    failed_total, count_total = float(stats[2].item()), float(stats[3].item())
+
+    # per-kernel device time over the same timed region
+    kernels = {}
+    for i in range(lib.sipoc_profile_collect(eng._handle)):
+        nm, ms, cnt = ctypes.c_char_p(), ctypes.c_double(), ctypes.c_int64()
+        lib.sipoc_profile_get(eng._handle, i, ctypes.byref(nm), ctypes.byref(ms),
+                              ctypes.byref(cnt))
+        kernels[nm.value.decode()] = {"ms_per_launch": ms.value / max(cnt.value, 1),
+                                      "launches_per_step": cnt.value / args.steps,
+                                      "ms_per_step": ms.value / args.steps}
+    lib.sipoc_profile_enable(eng._handle, 0)
+
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = total_batch / (ms_per_step * 1e-3)
+
+    # correctness outside the timed region: KKT residual of every problem
+    norms, rstats = lqr.residual(inp, out, status)
+    if world > 1:
+        dist.all_reduce(rstats[1:2], op=dist.ReduceOp.MAX)
+    max_residual = float(rstats[1].item())
+
+    # ---- e2e: host buffers through the C-ABI, copies inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        sizes = eng.lqr_sizes
+        host_in, keep = {}, []
+        for k in _capi.LQR_INPUT_FIELDS:
+            pinned = torch.empty((batch, max(sizes[k], 1)), dtype=torch.float64, pin_memory=True)
+            tmp = torch.empty((batch, max(sizes[k], 1)), dtype=torch.float64, device=dev)
+            eng._check(lib.sipoc_unpack(eng._handle, inp[k].data_ptr(), tmp.data_ptr(),
+                                        sizes[k], sp))
+            pinned.copy_(tmp)
+            del tmp
+            host_in[k] = pinned.numpy()
+            keep.append(pinned)
+        host_out = {}
+        for k in _capi.LQR_OUTPUT_FIELDS:
+            pinned = torch.empty((batch, max(sizes[k], 1)), dtype=torch.float64, pin_memory=True)
+            host_out[k] = pinned.numpy()
+            keep.append(pinned)
+        torch.cuda.synchronize(dev)
+        if args.free_device_inputs_for_e2e:
+            inp = None
+            torch.cuda.empty_cache()
+        e2e_steps = max(1, min(args.steps, args.e2e_steps))
+        res = lqr.factor_solve_host(host_in, host_out)  # warm-up: allocates resident buffers
+        barrier()
+        te0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            res = lqr.factor_solve_host(host_in, host_out)
+        torch.cuda.synchronize(dev)
+        te = torch.tensor([time.perf_counter() - te0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        assert (res["status"] == 0).all()
+        h2d = sum(batch * sizes[k] * 8 for k in _capi.LQR_INPUT_FIELDS)
+        d2h = sum(batch * sizes[k] * 8 for k in _capi.LQR_OUTPUT_FIELDS) + batch * 4
+        e2e = {"value": total_batch * e2e_steps / float(te.item()), "unit": UNIT,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+               "call": "sipoc_lqr_factor_solve_host (pinned host buffers, problem-major)"}
+
+    if rank == 0:
+        sampler.stop()
+        clocks = sampler.summary(t0, t1)
+        inb, outb = algorithmic_bytes(n, m, T)
+        flops = algorithmic_flops(n, m, T)
+        peak, peak_kind = measured_peaks()
+        hot = {k: v for k, v in kernels.items() if k != "status_stats_kernel"}
+        hot_ms = sum(v["ms_per_step"] for v in hot.values())
+        dominant = max(hot, key=lambda k: hot[k]["ms_per_step"]) if hot else None
+        t_hbm = (inb + outb) * batch / (peak * 1e9)
+        t_f64 = flops * batch / (FP64_PEAK_TFLOPS * 1e12)
+        if t_hbm >= t_f64:
+            achieved = (inb + outb) * batch / (hot_ms * 1e-3) / 1e9
+            roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak}
+        else:
+            achieved = flops * batch / (hot_ms * 1e-3) / 1e12
+            roof = {"bound": "fp64", "achieved": achieved, "peak": FP64_PEAK_TFLOPS,
+                    "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS}
+        roof.update({
+            "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs; FP64 = DFMA microbench)",
+            "traffic": load_traffic(eng.kernel_variant, name),
+            "algorithmic_bytes_per_solve": inb + outb,
+            "algorithmic_flops_per_solve": flops,
+            "basis": "algorithmic bytes of one factor+solve x problems per step / summed "
+                     "device time of the hot-path kernels of the step (CUDA events per launch)",
+            "dominant_kernel": dominant,
+            "dominant_share": (hot[dominant]["ms_per_step"] / hot_ms) if dominant else None,
+            "kernels": kernels,
+        })
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": name, "n": n, "m": m, "T": T, "batch_per_gpu": batch,
+                       "global_batch": total_batch, "parallelism": f"batch-sharded x{world}",
+                       "kernel_variant": eng.kernel_variant,
+                       "l2": "inputs larger than L2 (no flush needed)"
+                       if (inb * batch > 2 * 126e6) else "inputs smaller than L2",
+                       "generator": "lqr_benchmark.cpp:61-96 distribution, counter-based RNG"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches),
+            "roofline": roof,
+            "check": {"failed_problems": failed_total, "problems": count_total,
+                      "max_kkt_residual": max_residual},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(wl)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
+    ap.add_argument("--horizon", type=int, default=0, help="override the horizon T")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--seed", type=int, default=2026)
+    ap.add_argument("--force-generic", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--free-device-inputs-for-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    wl = dict(WORKLOADS[args.workload])
+    if args.batch:
+        wl["batch"] = args.batch
+    if args.horizon:
+        wl["T"] = args.horizon
+    if args.impl == "reference":
+        return run_reference(args, wl, args.workload)
+    return run_ours(args, wl, args.workload)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -133,6 +133,17 @@ sipoc_error sipoc_get_topology(const sipoc_engine *engine, int *child_offsets,
 /* Kernels launched by this handle so far (each launch of one of OUR kernels). */
 int64_t sipoc_launch_count(const sipoc_engine *engine);
 
+/* Per-kernel device timing (bench tooling).  While enabled, every launch of one
+ * of OUR kernels through this handle is bracketed by CUDA events on the
+ * launching stream.  sipoc_profile_collect synchronises on them, folds the
+ * spans by kernel name and returns the number of distinct names;
+ * sipoc_profile_get reads entry `index` of that summary (name stays valid until
+ * the next enable / collect).  Enabling or disabling clears recorded spans. */
+sipoc_error sipoc_profile_enable(sipoc_engine *engine, int on);
+int sipoc_profile_collect(sipoc_engine *engine);
+sipoc_error sipoc_profile_get(const sipoc_engine *engine, int index, const char **name,
+                              double *total_ms, int64_t *launches);
+
 /* ---- sizes ------------------------------------------------------------- */
 typedef struct sipoc_lqr_sizes {
   int64_t Q, M, R, q, r, A, B, c, delta; /* inputs, elements per problem  */
@@ -168,6 +179,12 @@ sipoc_error sipoc_lqr_factor_solve(sipoc_engine *engine, const sipoc_lqr_input *
 sipoc_error sipoc_lqr_residual(sipoc_engine *engine, const sipoc_lqr_input *in,
                                const sipoc_lqr_output *out, const int *status,
                                double *residual_norm, double *stats, void *stream);
+
+/* stats: device double[4], overwritten with {0, 0, #problems with status != 0,
+ * #problems}: the failure / convergence flags of one Newton iteration in the
+ * same 4-slot form as sipoc_lqr_residual, ready for an all-reduce(sum). */
+sipoc_error sipoc_status_stats(sipoc_engine *engine, const int *status, double *stats,
+                               void *stream);
 
 /* ---- layout conversion (device <-> device) ------------------------------ */
 /* src: problem-major [batch][size]; dst: engine layout [size][batch_stride]. */

@@ -99,6 +99,12 @@ def _load() -> ctypes.CDLL:
     lib.sipoc_get_topology.argtypes = [E, c_int_p, c_int_p, c_int_p, c_int_p]
     lib.sipoc_launch_count.argtypes = [E]
     lib.sipoc_launch_count.restype = ctypes.c_int64
+    lib.sipoc_profile_enable.argtypes = [E, ctypes.c_int]
+    lib.sipoc_profile_collect.argtypes = [E]
+    lib.sipoc_profile_collect.restype = ctypes.c_int
+    lib.sipoc_profile_get.argtypes = [E, ctypes.c_int, ctypes.POINTER(ctypes.c_char_p),
+                                      ctypes.POINTER(ctypes.c_double),
+                                      ctypes.POINTER(ctypes.c_int64)]
     lib.sipoc_lqr_get_sizes.argtypes = [E, ctypes.POINTER(LqrSizes)]
     lib.sipoc_batch.argtypes = [E]
     lib.sipoc_batch.restype = ctypes.c_int64
@@ -109,6 +115,7 @@ def _load() -> ctypes.CDLL:
     lib.sipoc_lqr_solve.argtypes = [E, LI, LO, P]
     lib.sipoc_lqr_factor_solve.argtypes = [E, LI, LO, P, P]
     lib.sipoc_lqr_residual.argtypes = [E, LI, LO, P, P, P, P]
+    lib.sipoc_status_stats.argtypes = [E, P, P, P]
     lib.sipoc_pack.argtypes = [E, P, P, ctypes.c_int64, P]
     lib.sipoc_unpack.argtypes = [E, P, P, ctypes.c_int64, P]
     lib.sipoc_lqr_factor_solve_host.argtypes = [E, LI, LO, P]

@@ -12,6 +12,7 @@
 
 #include "../../include/sipoc.h"
 #include "generic_kernels.cuh"
+#include "profile.hpp"
 #include "riccati_fast.cuh"
 #include "structure.hpp"
 #include "workload.cuh"
@@ -29,6 +30,7 @@ struct sipoc_engine {
   std::string variant;
   std::string last_error;
   int64_t launches = 0;
+  Profiler prof;
   cudaStream_t host_stream = nullptr;
 
   // Every device allocation the handle owns.
@@ -205,12 +207,15 @@ sipoc_error lqr_factor_core(sipoc_engine *e, const LqrIn &in, int *status,
   sipoc_error rc;
   if (e->fast != nullptr) {
     if ((rc = ensure_fast_store(e)) != SIPOC_OK) return rc;
-    FastArgs a{in, LqrOut{}, status, e->fast_store, nullptr, e->batch, e->ld, e->hs.E};
+    FastArgs a{in, LqrOut{}, status, e->fast_store, nullptr, e->batch, e->ld, e->hs.E, &e->prof};
     e->launches += e->fast->factor(a, s);
     e->factored = sipoc_engine::Factored::FAST;
   } else {
     if ((rc = ensure_generic_ws(e)) != SIPOC_OK) return rc;
-    launch_generic_lqr_factor(e->dt, in, e->gws, status, e->batch, e->ld, s);
+    {
+      ProfScope ps(&e->prof, "generic_lqr_factor_kernel", s);
+      launch_generic_lqr_factor(e->dt, in, e->gws, status, e->batch, e->ld, s);
+    }
     e->launches += 1;
     e->factored = sipoc_engine::Factored::GENERIC;
   }
@@ -224,10 +229,13 @@ sipoc_error lqr_solve_core(sipoc_engine *e, const LqrIn &in, const LqrOut &out,
     return fail(e, SIPOC_NOT_FACTORED, "solve called before a factor on this handle");
   if (e->factored == sipoc_engine::Factored::FAST) {
     if ((rc = ensure_fast_scratch(e)) != SIPOC_OK) return rc;
-    FastArgs a{in, out, nullptr, e->fast_store, e->fast_scratch, e->batch, e->ld, e->hs.E};
+    FastArgs a{in, out, nullptr, e->fast_store, e->fast_scratch, e->batch, e->ld, e->hs.E, &e->prof};
     e->launches += e->fast->solve(a, s);
   } else {
-    launch_generic_lqr_solve(e->dt, in, e->gws, out, e->batch, e->ld, s);
+    {
+      ProfScope ps(&e->prof, "generic_lqr_solve_kernel", s);
+      launch_generic_lqr_solve(e->dt, in, e->gws, out, e->batch, e->ld, s);
+    }
     e->launches += 1;
   }
   return check_launch(e, "lqr_solve");
@@ -238,7 +246,7 @@ sipoc_error lqr_factor_solve_core(sipoc_engine *e, const LqrIn &in, const LqrOut
   sipoc_error rc;
   if (e->fast != nullptr) {
     if ((rc = ensure_fast_scratch(e)) != SIPOC_OK) return rc;
-    FastArgs a{in, out, status, nullptr, e->fast_scratch, e->batch, e->ld, e->hs.E};
+    FastArgs a{in, out, status, nullptr, e->fast_scratch, e->batch, e->ld, e->hs.E, &e->prof};
     e->launches += e->fast->factor_solve(a, s);
     // The fused kernel keeps only the rollout spill, not a reusable factor.
     e->factored = sipoc_engine::Factored::NONE;
@@ -305,7 +313,10 @@ sipoc_error upload(sipoc_engine *e, const double *host, double *dev, int64_t siz
   SIPOC_CUDA(e, cudaMemcpyAsync(e->h_stage, host,
                                 static_cast<size_t>(size) * e->batch * sizeof(double),
                                 cudaMemcpyHostToDevice, e->host_stream));
-  launch_pack(e->h_stage, dev, size, e->batch, e->ld, e->host_stream);
+  {
+    ProfScope ps(&e->prof, "pack_kernel", e->host_stream);
+    launch_pack(e->h_stage, dev, size, e->batch, e->ld, e->host_stream);
+  }
   e->launches += 1;
   return check_launch(e, "pack");
 }
@@ -313,7 +324,10 @@ sipoc_error upload(sipoc_engine *e, const double *host, double *dev, int64_t siz
 sipoc_error download(sipoc_engine *e, const double *dev, double *host, int64_t size) {
   if (size == 0) return SIPOC_OK;
   if (host == nullptr) return fail(e, SIPOC_INVALID_ARGUMENT, "NULL host output array");
-  launch_unpack(dev, e->h_stage, size, e->batch, e->ld, e->host_stream);
+  {
+    ProfScope ps(&e->prof, "unpack_kernel", e->host_stream);
+    launch_unpack(dev, e->h_stage, size, e->batch, e->ld, e->host_stream);
+  }
   e->launches += 1;
   sipoc_error rc = check_launch(e, "unpack");
   if (rc != SIPOC_OK) return rc;
@@ -385,7 +399,10 @@ sipoc_error kkt_factor_core(sipoc_engine *e, const KktModel &mdl, const double *
                             cudaStream_t s) {
   sipoc_error rc;
   if ((rc = ensure_kkt_ws(e)) != SIPOC_OK) return rc;
-  launch_kkt_reduce(e->dt, mdl, w, r1, r2, r3, e->kws, ok, e->batch, e->ld, s);
+  {
+    ProfScope ps(&e->prof, "kkt_reduce_kernel", s);
+    launch_kkt_reduce(e->dt, mdl, w, r1, r2, r3, e->kws, ok, e->batch, e->ld, s);
+  }
   e->launches += 2;
   if ((rc = check_launch(e, "kkt_reduce")) != SIPOC_OK) return rc;
   // helpers.cpp:362-368: LQR on (Q_mod, M_mod, R_mod, ddyn_dx, ddyn_du, dyn_r2).
@@ -402,7 +419,10 @@ sipoc_error kkt_solve_core(sipoc_engine *e, const KktModel &mdl, const double *b
                            double *sol, cudaStream_t s) {
   if (!e->kkt_factored)
     return fail(e, SIPOC_NOT_FACTORED, "kkt_solve called before kkt_factor");
-  launch_kkt_build_rhs(e->dt, mdl, e->kws, b, e->batch, e->ld, s);
+  {
+    ProfScope ps(&e->prof, "kkt_build_rhs_kernel", s);
+    launch_kkt_build_rhs(e->dt, mdl, e->kws, b, e->batch, e->ld, s);
+  }
   e->launches += 1;
   sipoc_error rc = check_launch(e, "kkt_build_rhs");
   if (rc != SIPOC_OK) return rc;
@@ -410,7 +430,10 @@ sipoc_error kkt_solve_core(sipoc_engine *e, const KktModel &mdl, const double *b
            mdl.edge_A,   mdl.edge_B,   e->kws.c_mod, e->kws.dyn_r2};
   LqrOut out{e->kws.x, e->kws.u, e->kws.y};
   if ((rc = lqr_solve_core(e, in, out, s)) != SIPOC_OK) return rc;
-  launch_kkt_recover(e->dt, mdl, e->kws, b, sol, e->batch, e->ld, s);
+  {
+    ProfScope ps(&e->prof, "kkt_recover_kernel", s);
+    launch_kkt_recover(e->dt, mdl, e->kws, b, sol, e->batch, e->ld, s);
+  }
   e->launches += 1;
   return check_launch(e, "kkt_recover");
 }
@@ -499,6 +522,31 @@ const char *sipoc_kernel_variant(const sipoc_engine *e) {
 }
 
 int64_t sipoc_launch_count(const sipoc_engine *e) { return e == nullptr ? 0 : e->launches; }
+
+sipoc_error sipoc_profile_enable(sipoc_engine *e, int on) {
+  if (e == nullptr) return SIPOC_INVALID_ARGUMENT;
+  DeviceGuard guard(e->device);
+  e->prof.reset();
+  e->prof.enable(on != 0);
+  return SIPOC_OK;
+}
+
+int sipoc_profile_collect(sipoc_engine *e) {
+  if (e == nullptr) return 0;
+  DeviceGuard guard(e->device);
+  return static_cast<int>(e->prof.summarise().size());
+}
+
+sipoc_error sipoc_profile_get(const sipoc_engine *e, int index, const char **name,
+                              double *total_ms, int64_t *launches) {
+  if (e == nullptr || index < 0 || index >= static_cast<int>(e->prof.summary().size()))
+    return SIPOC_INVALID_ARGUMENT;
+  const Profiler::Summary &s = e->prof.summary()[index];
+  if (name) *name = s.name.c_str();
+  if (total_ms) *total_ms = s.total_ms;
+  if (launches) *launches = s.launches;
+  return SIPOC_OK;
+}
 int64_t sipoc_batch(const sipoc_engine *e) { return e == nullptr ? 0 : e->batch; }
 int64_t sipoc_batch_stride(const sipoc_engine *e) { return e == nullptr ? 0 : e->ld; }
 
@@ -563,11 +611,28 @@ sipoc_error sipoc_lqr_residual(sipoc_engine *e, const sipoc_lqr_input *in,
   if (null_in(in, true, true) || out == nullptr || !out->x || !out->u || !out->y)
     return fail(e, SIPOC_INVALID_ARGUMENT, "NULL LQR input / output");
   DeviceGuard guard(e->device);
-  launch_lqr_residual(e->dt, to_in(in), LqrOut{out->x, out->u, out->y}, status,
-                      residual_norm, stats, e->batch, e->ld,
-                      static_cast<cudaStream_t>(stream));
+  {
+    ProfScope ps(&e->prof, "lqr_residual_kernel", static_cast<cudaStream_t>(stream));
+    launch_lqr_residual(e->dt, to_in(in), LqrOut{out->x, out->u, out->y}, status,
+                        residual_norm, stats, e->batch, e->ld,
+                        static_cast<cudaStream_t>(stream));
+  }
   e->launches += stats != nullptr ? 2 : 1;
   return check_launch(e, "lqr_residual");
+}
+
+sipoc_error sipoc_status_stats(sipoc_engine *e, const int *status, double *stats,
+                               void *stream) {
+  if (e == nullptr) return SIPOC_INVALID_ARGUMENT;
+  if (status == nullptr || stats == nullptr)
+    return fail(e, SIPOC_INVALID_ARGUMENT, "NULL status / stats");
+  DeviceGuard guard(e->device);
+  {
+    ProfScope ps(&e->prof, "status_stats_kernel", static_cast<cudaStream_t>(stream));
+    launch_status_stats(status, stats, e->batch, static_cast<cudaStream_t>(stream));
+  }
+  e->launches += 2;
+  return check_launch(e, "status_stats");
 }
 
 sipoc_error sipoc_pack(sipoc_engine *e, const double *src, double *dst, int64_t size,
@@ -761,9 +826,16 @@ sipoc_error sipoc_kkt_residual(sipoc_engine *e, const sipoc_kkt_model *model, co
                                 static_cast<size_t>(std::max(1, e->hs.kkt_dim)) * e->ld *
                                     sizeof(double),
                                 s));
-  launch_kkt_apply(e->dt, to_model(model), w, r1, r2, r3, sol, e->kkt_product, e->batch,
-                   e->ld, s);
-  launch_kkt_residual(e->dt, e->kkt_product, b, ok, residual_norm, stats, e->batch, e->ld, s);
+  {
+    ProfScope ps(&e->prof, "kkt_apply_kernel", s);
+    launch_kkt_apply(e->dt, to_model(model), w, r1, r2, r3, sol, e->kkt_product, e->batch,
+                     e->ld, s);
+  }
+  {
+    ProfScope ps(&e->prof, "kkt_residual_kernel", s);
+    launch_kkt_residual(e->dt, e->kkt_product, b, ok, residual_norm, stats, e->batch, e->ld,
+                        s);
+  }
   e->launches += stats != nullptr ? 3 : 2;
   return check_launch(e, "kkt_residual");
 }

@@ -829,6 +829,19 @@ unpack_kernel(const double *__restrict__ src, double *__restrict__ dst, int64_t 
   }
 }
 
+// stats = {0, 0, #problems with status != 0, #problems}: the per-iteration
+// convergence / failure flags a multi-GPU driver all-reduces.
+__global__ void __launch_bounds__(kThreads)
+status_stats_kernel(const int *status, double *stats, int64_t batch) {
+  double failed = 0.0, count = 0.0;
+  for (int64_t b = problem_index(); b < batch;
+       b += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    failed += status[b] != 0 ? 1.0 : 0.0;
+    count += 1.0;
+  }
+  accumulate_stats(0.0, 0.0, failed, count, stats);
+}
+
 __global__ void fill_int_kernel(int *dst, int value, int64_t count) {
   const int64_t i = problem_index();
   if (i < count) dst[i] = value;
@@ -918,6 +931,13 @@ void launch_unpack(const double *src, double *dst, int64_t size, int64_t batch, 
   if (size == 0) return;
   dim3 grid(static_cast<unsigned>((size + 31) / 32), static_cast<unsigned>((ld + 31) / 32));
   unpack_kernel<<<grid, dim3(32, 8), 0, s>>>(src, dst, size, batch, ld);
+}
+
+void launch_status_stats(const int *status, double *stats, int64_t batch, cudaStream_t s) {
+  zero_stats_kernel<<<1, 32, 0, s>>>(stats);
+  const int64_t blocks = (batch + kThreads - 1) / kThreads;
+  status_stats_kernel<<<static_cast<unsigned>(blocks < 592 ? blocks : 592), kThreads, 0, s>>>(
+      status, stats, batch);
 }
 
 void launch_fill_int(int *dst, int value, int64_t count, cudaStream_t s) {

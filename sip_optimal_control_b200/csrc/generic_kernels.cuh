@@ -96,6 +96,8 @@ void launch_pack(const double *src, double *dst, int64_t size, int64_t batch,
                  int64_t ld, cudaStream_t stream);
 void launch_unpack(const double *src, double *dst, int64_t size, int64_t batch,
                    int64_t ld, cudaStream_t stream);
+void launch_status_stats(const int *status, double *stats, int64_t batch,
+                         cudaStream_t stream);
 void launch_fill_int(int *dst, int value, int64_t count, cudaStream_t stream);
 
 // Number of kernel launches each launcher above performs (for launch_count).

@@ -11,6 +11,7 @@
 #include <cstdint>
 
 #include "generic_kernels.cuh"
+#include "profile.hpp"
 
 namespace sipoc {
 
@@ -22,6 +23,7 @@ struct FastArgs {
   double *scratch;  // per-problem spill of the fused / solve rollout (v, k)
   int64_t batch, ld;
   int num_edges;
+  Profiler *prof;   // per-kernel event timing (may be disabled)
 };
 
 struct FastPlan {
