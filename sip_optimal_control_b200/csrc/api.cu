@@ -201,11 +201,24 @@ LqrIn to_in(const sipoc_lqr_input *in) {
   return LqrIn{in->Q, in->M, in->R, in->q, in->r, in->A, in->B, in->c, in->delta};
 }
 
+// The sub-warp kernels stage operands with 16-byte cp.async: every engine-layout
+// array must be 16-byte aligned (any cudaMalloc / torch allocation is).  A
+// misaligned call is served by the generic kernels instead.
+bool aligned16(const LqrIn &in) {
+  const double *p[9] = {in.Q, in.M, in.R, in.q, in.r, in.A, in.B, in.c, in.delta};
+  for (const double *q : p)
+    if ((reinterpret_cast<uintptr_t>(q) & 15u) != 0) return false;
+  return true;
+}
+bool use_fast(const sipoc_engine *e, const LqrIn &in) {
+  return e->fast != nullptr && aligned16(in);
+}
+
 // --- device-path cores (shared by the device and host entry points) --------
 sipoc_error lqr_factor_core(sipoc_engine *e, const LqrIn &in, int *status,
                             cudaStream_t s) {
   sipoc_error rc;
-  if (e->fast != nullptr) {
+  if (use_fast(e, in)) {
     if ((rc = ensure_fast_store(e)) != SIPOC_OK) return rc;
     FastArgs a{in, LqrOut{}, status, e->fast_store, nullptr, e->batch, e->ld, e->hs.E, &e->prof};
     e->launches += e->fast->factor(a, s);
@@ -227,6 +240,9 @@ sipoc_error lqr_solve_core(sipoc_engine *e, const LqrIn &in, const LqrOut &out,
   sipoc_error rc;
   if (e->factored == sipoc_engine::Factored::NONE)
     return fail(e, SIPOC_NOT_FACTORED, "solve called before a factor on this handle");
+  if (e->factored == sipoc_engine::Factored::FAST && !aligned16(in))
+    return fail(e, SIPOC_INVALID_ARGUMENT,
+                "solve against a fast-path factorization needs 16-byte aligned arrays");
   if (e->factored == sipoc_engine::Factored::FAST) {
     if ((rc = ensure_fast_scratch(e)) != SIPOC_OK) return rc;
     FastArgs a{in, out, nullptr, e->fast_store, e->fast_scratch, e->batch, e->ld, e->hs.E, &e->prof};
@@ -244,12 +260,14 @@ sipoc_error lqr_solve_core(sipoc_engine *e, const LqrIn &in, const LqrOut &out,
 sipoc_error lqr_factor_solve_core(sipoc_engine *e, const LqrIn &in, const LqrOut &out,
                                   int *status, cudaStream_t s) {
   sipoc_error rc;
-  if (e->fast != nullptr) {
+  if (use_fast(e, in)) {
+    if ((rc = ensure_fast_store(e)) != SIPOC_OK) return rc;
     if ((rc = ensure_fast_scratch(e)) != SIPOC_OK) return rc;
-    FastArgs a{in, out, status, nullptr, e->fast_scratch, e->batch, e->ld, e->hs.E, &e->prof};
+    FastArgs a{in, out, status, e->fast_store, e->fast_scratch, e->batch, e->ld, e->hs.E,
+               &e->prof};
     e->launches += e->fast->factor_solve(a, s);
-    // The fused kernel keeps only the rollout spill, not a reusable factor.
-    e->factored = sipoc_engine::Factored::NONE;
+    // The backward kernel keeps W, K and G^-1, so later solves may reuse them.
+    e->factored = sipoc_engine::Factored::FAST;
     return check_launch(e, "lqr_factor_solve");
   }
   if ((rc = lqr_factor_core(e, in, status, s)) != SIPOC_OK) return rc;

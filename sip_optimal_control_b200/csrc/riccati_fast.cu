@@ -1,5 +1,1100 @@
+// Shape-specialised Riccati kernels for uniform chains (n, m compile-time).
+//
+// Three kernels per shape, all sm_100a, FP64:
+//
+//   riccati_backward_subwarp<N, M>   backward Riccati sweep (reference
+//       lqr.cpp:645-731) fused with the backward affine sweep of the solve
+//       (lqr.cpp:738-796).  FOUR LANES PER PROBLEM, eight problems per warp.
+//       Each stage's A, B, Q, M, R, q, r, c, delta are staged into shared
+//       memory with cp.async (16 B per lane, 64 B contiguous per matrix element
+//       = the 8 problems of the warp in the batch-interleaved HBM layout);
+//       the next stage's copy is issued as soon as the current stage has
+//       consumed its operands and lands while the factorizations run.
+//   riccati_backward_thread<N, M>    the same mathematics, one thread per
+//       problem with every matrix in registers, for tiny n (cartpole).
+//   affine_backward<N, M>            backward affine sweep alone (solve after
+//       a kept factorization), one thread per problem, streaming.
+//   rollout_forward<N, M>            root solve + forward rollout + costates
+//       (lqr.cpp:798-870), one thread per problem, streaming: every operand is
+//       read exactly once with fully coalesced 256 B warp requests.
+//
+// Per stage (edge k, parent node k, child node k+1) the backward kernels use
+// the "augmented Hessian" form of the recursion, algebraically identical to
+// the reference's statements but with ~35 % fewer flops:
+//     Z   = [B_k | A_k]                         (n x (m+n))
+//     S   = W_{k+1} Z                           W = V (I + D V)^-1, symmetric
+//     Psi = [R M'; M Q] + Z' S                  ((m+n) x (m+n), lower)
+//     G   = Psi_uu = L_G L_G'                   fail -> G_FACTORIZATION_FAILURE
+//     Lam = Psi_xu L_G^-T ;  K_k = -L_G^-T Lam'
+//     V_k = Psi_xx - Lam Lam'
+//     F   = I + D^1/2 V_k D^1/2 = L L'          fail -> F_FACTORIZATION_FAILURE
+//     W_k = D^-1/2 (I - L^-T L^-1) D^-1/2       (lqr.cpp:511-529)
+// and, for the affine part,
+//     g = v' - W'(delta' o v' - c') ;  [h; w] = [r; q] + Z' g
+//     t = L_G^-1 h ;  k_k = -L_G^-T t ;  v_k = w - Lam t.
+// The forward pass needs only (W, v) per node and (K, k) per edge:
+//     y' = v' + W' f ,  x' = f - delta' o (W' f) ,  f = c' - delta' o v' + A x + B u
+// because (I + D V)^-1 = I - D W.
 #include "riccati_fast.cuh"
 
+#include <cstdio>
+
 namespace sipoc {
-const FastPlan *select_fast_plan(int, int) { return nullptr; }
+namespace {
+
+constexpr int kGroup = 4;  // lanes per problem
+constexpr int kTile = 8;   // problems per warp
+
+__host__ __device__ constexpr int tri(int n) { return n * (n + 1) / 2; }
+// Column-major packed lower index, i >= j.
+__host__ __device__ constexpr int pk(int i, int j, int n) {
+  return j * n - j * (j - 1) / 2 + (i - j);
+}
+__host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
+__host__ __device__ constexpr int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// Per-problem element counts of the kept factorization and the rollout spill.
+template <int N, int M>
+struct FastSizes {
+  static __host__ __device__ constexpr int64_t oW(int) { return 0; }
+  static __host__ __device__ constexpr int64_t oK(int T) { return int64_t(T + 1) * tri(N); }
+  static __host__ __device__ constexpr int64_t oG(int T) { return oK(T) + int64_t(T) * N * M; }
+  static __host__ __device__ constexpr int64_t store(int T) { return oG(T) + int64_t(T) * tri(M); }
+  static __host__ __device__ constexpr int64_t ov(int) { return 0; }
+  static __host__ __device__ constexpr int64_t ok(int T) { return int64_t(T + 1) * N; }
+  static __host__ __device__ constexpr int64_t scratch(int T) { return ok(T) + int64_t(T) * M; }
+};
+
+__device__ __forceinline__ void cp_async16(double *smem, const double *gmem) {
+  const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() {
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+}
+
+// Streaming loads / stores: every operand is touched once per pass.
+__device__ __forceinline__ double ldcs(const double *p) { return __ldcs(p); }
+__device__ __forceinline__ void stcs(double *p, double v) { __stcs(p, v); }
+
+// ===========================================================================
+// Shared-memory map of one warp (rows of kTile doubles = 64 B).
+// ===========================================================================
+template <int N, int M>
+struct Smem {
+  static constexpr int NZ = N + M;
+  static constexpr int rZ = 0;                // [B | A], column-major, N rows per column
+  static constexpr int rQ = rZ + NZ * N;      // Q_k, packed lower
+  static constexpr int rM = rQ + tri(N);      // M_k, N x M column-major
+  static constexpr int rR = rM + N * M;       // R_k, packed lower
+  static constexpr int rq = rR + tri(M);      // q_k
+  static constexpr int rr = rq + N;           // r_k
+  static constexpr int rc = rr + M;           // c_{k+1}
+  static constexpr int rd = rc + N;           // delta_k (as staged)
+  static constexpr int kStaged = rd + N;
+  static constexpr int rW = kStaged;          // W of the last processed node, packed lower
+  static constexpr int rG = rW + tri(N);      // g
+  static constexpr int rV = rG + N;           // v of the last processed node
+  static constexpr int rDl = rV + N;          // delta of the last processed node
+  static constexpr int rSd = rDl + N;         // sqrt(delta), 1/sqrt(delta) of the node in flight
+  static constexpr int rSdi = rSd + N;
+  // Exchange region: first [Psi_uu packed | Psi_xu | h | Lambda], later F packed,
+  // later L^-1 packed.
+  static constexpr int rX = rSdi + N;
+  static constexpr int xGuu = rX;
+  static constexpr int xPxu = xGuu + tri(M);
+  static constexpr int xH = xPxu + N * M;
+  static constexpr int xLam = xH + M;
+  static constexpr int kXRows = cmax(tri(M) + 2 * N * M + M, tri(N));
+  static constexpr int kRows = rX + kXRows;
+  static constexpr int kBytes = kRows * kTile * int(sizeof(double));
+};
+
+// Copies `count` consecutive flat elements (rows of 8 problems) into shared
+// memory: lane l moves 16 B (problems 2(l&3), 2(l&3)+1) of row (l>>2) + 8 i.
+__device__ __forceinline__ void stage_rows(double *sm, int dst_row0, const double *g,
+                                           int64_t ld, int count, int lane) {
+  const int sub = lane & 3, rr = lane >> 2;
+#pragma unroll
+  for (int i0 = 0; i0 < count; i0 += 8) {
+    const int i = i0 + rr;
+    if (i < count)
+      cp_async16(sm + (dst_row0 + i) * kTile + sub * 2, g + static_cast<int64_t>(i) * ld + sub * 2);
+  }
+}
+
+template <int N>
+__device__ __forceinline__ void stage_lower(double *sm, int dst_row0, const double *g, int64_t ld,
+                                            int lane) {
+#pragma unroll
+  for (int j = 0; j < N; ++j)
+    stage_rows(sm, dst_row0 + pk(j, j, N), g + static_cast<int64_t>(j * N + j) * ld, ld, N - j,
+               lane);
+}
+
+// ===========================================================================
+// Backward sweep, four lanes per problem.
+// ===========================================================================
+template <int N, int M, bool SOLVE>
+__global__ void __launch_bounds__(32)
+riccati_backward_subwarp(LqrIn in, int *status_out, double *store, double *scratch,
+                         int64_t batch, int64_t ld, int T) {
+  using S = Smem<N, M>;
+  using Z = FastSizes<N, M>;
+  constexpr int SX = cdiv(N, kGroup);  // own state columns per lane
+  constexpr int SU = cdiv(M, kGroup);  // own control columns per lane
+  extern __shared__ __align__(16) double sm[];
+
+  const int lane = threadIdx.x;
+  const int prob = lane & (kTile - 1);
+  const int r = lane >> 3;
+  const int64_t b0 = static_cast<int64_t>(blockIdx.x) * kTile;
+  const int64_t b = b0 + prob;
+  const bool valid = b < batch;
+  const unsigned group_mask = 0x01010101u << prob;
+
+  // Own columns (cyclic): state column xj[s] = r + 4 s, control column uj[s].
+  int xj[SX], uj[SU], qcol[SX], rcol[SU];
+  bool xok[SX], uok[SU];
+#pragma unroll
+  for (int s = 0; s < SX; ++s) {
+    const int j = r + kGroup * s;
+    xok[s] = j < N;
+    xj[s] = xok[s] ? j : N - 1;
+    qcol[s] = xj[s] * N - xj[s] * (xj[s] - 1) / 2 - xj[s];  // packed row of (i, xj) = qcol + i
+  }
+#pragma unroll
+  for (int s = 0; s < SU; ++s) {
+    const int j = r + kGroup * s;
+    uok[s] = j < M;
+    uj[s] = uok[s] ? j : M - 1;
+    rcol[s] = uj[s] * M - uj[s] * (uj[s] - 1) / 2 - uj[s];
+  }
+
+#define SM(row) sm[(row) * kTile + prob]
+
+  const double *gA = in.A + b0, *gB = in.B + b0, *gQ = in.Q + b0, *gM = in.M + b0,
+               *gR = in.R + b0, *gq = in.q + b0, *gr = in.r + b0, *gc = in.c + b0,
+               *gd = in.delta + b0;
+  double *Wst = store + Z::oW(T) * ld + b;
+  double *Kst = store + Z::oK(T) * ld + b;
+  double *Gst = store + Z::oG(T) * ld + b;
+  double *vst = SOLVE ? scratch + Z::ov(T) * ld + b : nullptr;
+  double *kst = SOLVE ? scratch + Z::ok(T) * ld + b : nullptr;
+
+  auto issue_node = [&](int k) {
+    stage_lower<N>(sm, S::rQ, gQ + static_cast<int64_t>(k) * N * N * ld, ld, lane);
+    stage_rows(sm, S::rd, gd + static_cast<int64_t>(k) * N * ld, ld, N, lane);
+    if (SOLVE) stage_rows(sm, S::rq, gq + static_cast<int64_t>(k) * N * ld, ld, N, lane);
+  };
+  auto issue_edge = [&](int k) {
+    stage_rows(sm, S::rZ, gB + static_cast<int64_t>(k) * N * M * ld, ld, N * M, lane);
+    stage_rows(sm, S::rZ + N * M, gA + static_cast<int64_t>(k) * N * N * ld, ld, N * N, lane);
+    stage_rows(sm, S::rM, gM + static_cast<int64_t>(k) * N * M * ld, ld, N * M, lane);
+    stage_lower<M>(sm, S::rR, gR + static_cast<int64_t>(k) * M * M * ld, ld, lane);
+    if (SOLVE) {
+      stage_rows(sm, S::rr, gr + static_cast<int64_t>(k) * M * ld, ld, M, lane);
+      stage_rows(sm, S::rc, gc + static_cast<int64_t>(k + 1) * N * ld, ld, N, lane);
+    }
+  };
+
+  int status = SIPOC_FACTOR_SUCCESS;
+  bool bad_delta = false;
+
+  // delta, sqrt(delta), 1/sqrt(delta) of the node whose delta is staged in rd:
+  // each lane handles its own rows.
+  auto update_delta = [&]() {
+    bad_delta = false;
+#pragma unroll
+    for (int s = 0; s < SX; ++s) {
+      const double d = SM(S::rd + xj[s]);
+      if (xok[s]) {
+        bad_delta = bad_delta || !(d > 0.0);
+        const double sd = sqrt(d);
+        SM(S::rDl + xj[s]) = d;
+        SM(S::rSd + xj[s]) = sd;
+        SM(S::rSdi + xj[s]) = 1.0 / sd;
+      }
+    }
+  };
+
+  // Node processing: V (own columns, rows >= 4 s) and v (own entries) in
+  // registers -> W_k in shared memory and in the store, v_k in shared memory
+  // and in the spill.  compute_delta_sqrt + factor_F + compute_regularized_W
+  // (lqr.cpp:475-529).
+  auto process_node = [&](int k, double (&V)[SX][N], double (&vv)[SX]) {
+    double sdo[SX], sdio[SX];
+#pragma unroll
+    for (int s = 0; s < SX; ++s) {
+      sdo[s] = SM(S::rSd + xj[s]);
+      sdio[s] = SM(S::rSdi + xj[s]);
+    }
+#pragma unroll
+    for (int s = 0; s < SX; ++s)
+#pragma unroll
+      for (int i = kGroup * s; i < N; ++i)
+        V[s][i] = SM(S::rSd + i) * V[s][i] * sdo[s] + (i == xj[s] ? 1.0 : 0.0);
+    __syncwarp();  // every lane is done with the exchange region (Lambda)
+#pragma unroll
+    for (int s = 0; s < SX; ++s) {
+#pragma unroll
+      for (int i = kGroup * s; i < N; ++i)
+        if (xok[s] && i >= xj[s]) SM(S::rX + qcol[s] + i) = V[s][i];
+      if (SOLVE && xok[s]) {
+        SM(S::rV + xj[s]) = vv[s];
+        if (valid) stcs(vst + static_cast<int64_t>(k * N + xj[s]) * ld, vv[s]);
+      }
+    }
+    __syncwarp();
+    if (__ballot_sync(0xffffffffu, bad_delta) & group_mask) {
+      if (status == SIPOC_FACTOR_SUCCESS) status = SIPOC_FACTOR_INVALID_DELTA;
+    }
+
+    // Cholesky of F, replicated in the four lanes (registers only, no exchange).
+    double L[tri(N)], dinv[N];
+#pragma unroll
+    for (int t = 0; t < tri(N); ++t) L[t] = SM(S::rX + t);
+    bool f_ok = true;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      double x = L[pk(j, j, N)];
+#pragma unroll
+      for (int p = 0; p < j; ++p) x -= L[pk(j, p, N)] * L[pk(j, p, N)];
+      f_ok = f_ok && (x > 0.0);
+      const double d = rsqrt(x);
+      dinv[j] = d;
+#pragma unroll
+      for (int i = j + 1; i < N; ++i) {
+        double t = L[pk(i, j, N)];
+#pragma unroll
+        for (int p = 0; p < j; ++p) t -= L[pk(i, p, N)] * L[pk(j, p, N)];
+        L[pk(i, j, N)] = t * d;
+      }
+    }
+    if (!f_ok && status == SIPOC_FACTOR_SUCCESS) status = SIPOC_FACTOR_F_FACTORIZATION_FAILURE;
+    __syncwarp();  // every lane has read F
+
+    // Own columns of L^-1 (forward substitution on e_xj), kept in registers and
+    // published (packed lower) for the other lanes.
+    double Li[SX][N];
+#pragma unroll
+    for (int s = 0; s < SX; ++s) {
+#pragma unroll
+      for (int i = kGroup * s; i < N; ++i) {
+        double t = (i == xj[s]) ? 1.0 : 0.0;
+#pragma unroll
+        for (int p = kGroup * s; p < i; ++p) t -= L[pk(i, p, N)] * Li[s][p];
+        Li[s][i] = t * dinv[i];
+        if (xok[s] && i >= xj[s]) SM(S::rX + qcol[s] + i) = Li[s][i];
+      }
+    }
+    __syncwarp();
+
+    // W = D^-1/2 (I - L^-T L^-1) D^-1/2, own columns, rows >= 4 s.
+#pragma unroll
+    for (int s = 0; s < SX; ++s) {
+#pragma unroll
+      for (int i = kGroup * s; i < N; ++i) {
+        double fin = 0.0;
+#pragma unroll
+        for (int p = i; p < N; ++p) fin += SM(S::rX + pk(p, i, N)) * Li[s][p];
+        const double w = SM(S::rSdi + i) * ((i == xj[s] ? 1.0 : 0.0) - fin) * sdio[s];
+        if (xok[s] && i >= xj[s]) {
+          SM(S::rW + qcol[s] + i) = w;
+          if (valid) stcs(Wst + (static_cast<int64_t>(k) * tri(N) + qcol[s] + i) * ld, w);
+        }
+      }
+    }
+    __syncwarp();
+  };
+
+  // ---- terminal node: V = Q_T, v = q_T ------------------------------------
+  issue_node(T);
+  cp_async_commit();
+  cp_async_wait_all();
+  __syncwarp();
+  {
+    double V[SX][N], vv[SX];
+#pragma unroll
+    for (int s = 0; s < SX; ++s) {
+#pragma unroll
+      for (int i = kGroup * s; i < N; ++i) V[s][i] = SM(S::rQ + qcol[s] + i);
+      vv[s] = SOLVE ? SM(S::rq + xj[s]) : 0.0;
+    }
+    update_delta();
+    __syncwarp();
+    if (T > 0) {
+      issue_node(T - 1);
+      issue_edge(T - 1);
+      cp_async_commit();
+    }
+    process_node(T, V, vv);
+  }
+
+  // ---- stages T-1 ... 0 -----------------------------------------------------
+  for (int k = T - 1; k >= 0; --k) {
+    cp_async_wait_all();
+    __syncwarp();
+
+    // g = v' - W'(delta' o v' - c'), own rows  (lqr.cpp:778-782)
+    if (SOLVE) {
+      double f[N];
+#pragma unroll
+      for (int i = 0; i < N; ++i) f[i] = SM(S::rDl + i) * SM(S::rV + i) - SM(S::rc + i);
+#pragma unroll
+      for (int s = 0; s < SX; ++s) {
+        double acc = 0.0;
+#pragma unroll
+        for (int q = 0; q < N; ++q) {
+          // W'(xj, q) from the packed lower triangle
+          const int row = (q <= xj[s]) ? (pk(q, q, N) - q + xj[s]) : (qcol[s] + q);
+          acc += SM(S::rW + row) * f[q];
+        }
+        if (xok[s]) SM(S::rG + xj[s]) = SM(S::rV + xj[s]) - acc;
+      }
+    }
+
+    // S = W' Z, own columns of Z = [B | A].
+    double Su[SU][N], Sx[SX][N];
+    {
+      double zu[SU][N], zx[SX][N];
+#pragma unroll
+      for (int s = 0; s < SU; ++s)
+#pragma unroll
+        for (int p = 0; p < N; ++p) {
+          zu[s][p] = SM(S::rZ + uj[s] * N + p);
+          Su[s][p] = 0.0;
+        }
+#pragma unroll
+      for (int s = 0; s < SX; ++s)
+#pragma unroll
+        for (int p = 0; p < N; ++p) {
+          zx[s][p] = SM(S::rZ + (M + xj[s]) * N + p);
+          Sx[s][p] = 0.0;
+        }
+#pragma unroll
+      for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int i = j; i < N; ++i) {
+          const double w = SM(S::rW + pk(i, j, N));
+#pragma unroll
+          for (int s = 0; s < SU; ++s) {
+            Su[s][i] += w * zu[s][j];
+            if (i != j) Su[s][j] += w * zu[s][i];
+          }
+#pragma unroll
+          for (int s = 0; s < SX; ++s) {
+            Sx[s][i] += w * zx[s][j];
+            if (i != j) Sx[s][j] += w * zx[s][i];
+          }
+        }
+    }
+    __syncwarp();  // g complete; every lane is done with W', v', delta'
+
+    update_delta();  // node k: delta_k -> rDl, rSd, rSdi (own rows)
+
+    // Psi = [R M'; M Q] + Z' S, own columns (block-lower), and [h; w] = [r; q] + Z' g.
+    double Puu[SU][M], Pxu[SU][N], Pxx[SX][N], hu[SU], wx[SX];
+#pragma unroll
+    for (int s = 0; s < SU; ++s) {
+#pragma unroll
+      for (int i = kGroup * s; i < M; ++i) Puu[s][i] = SM(S::rR + rcol[s] + i);
+#pragma unroll
+      for (int x = 0; x < N; ++x) Pxu[s][x] = SM(S::rM + uj[s] * N + x);
+      hu[s] = SOLVE ? SM(S::rr + uj[s]) : 0.0;
+    }
+#pragma unroll
+    for (int s = 0; s < SX; ++s) {
+#pragma unroll
+      for (int i = kGroup * s; i < N; ++i) Pxx[s][i] = SM(S::rQ + qcol[s] + i);
+      wx[s] = SOLVE ? SM(S::rq + xj[s]) : 0.0;
+    }
+#pragma unroll
+    for (int p = 0; p < N; ++p) {
+      if (SOLVE) {
+        const double gp = SM(S::rG + p);
+#pragma unroll
+        for (int s = 0; s < SU; ++s) hu[s] += SM(S::rZ + uj[s] * N + p) * gp;
+#pragma unroll
+        for (int s = 0; s < SX; ++s) wx[s] += SM(S::rZ + (M + xj[s]) * N + p) * gp;
+      }
+#pragma unroll
+      for (int i = 0; i < M; ++i) {  // rows of B
+        const double z = SM(S::rZ + i * N + p);
+#pragma unroll
+        for (int s = 0; s < SU; ++s)
+          if (i >= kGroup * s) Puu[s][i] += z * Su[s][p];
+      }
+#pragma unroll
+      for (int x = 0; x < N; ++x) {  // rows of A
+        const double z = SM(S::rZ + (M + x) * N + p);
+#pragma unroll
+        for (int s = 0; s < SU; ++s) Pxu[s][x] += z * Su[s][p];
+#pragma unroll
+        for (int s = 0; s < SX; ++s)
+          if (x >= kGroup * s) Pxx[s][x] += z * Sx[s][p];
+      }
+    }
+    // Publish the control block: Psi_uu (packed lower), Psi_xu, h.
+#pragma unroll
+    for (int s = 0; s < SU; ++s) {
+      if (uok[s]) {
+#pragma unroll
+        for (int i = kGroup * s; i < M; ++i)
+          if (i >= uj[s]) SM(S::xGuu + rcol[s] + i) = Puu[s][i];
+#pragma unroll
+        for (int x = 0; x < N; ++x) SM(S::xPxu + uj[s] * N + x) = Pxu[s][x];
+        if (SOLVE) SM(S::xH + uj[s]) = hu[s];
+      }
+    }
+    __syncwarp();  // control block visible; staged operands of stage k consumed
+
+    if (k > 0) {
+      issue_node(k - 1);
+      issue_edge(k - 1);
+      cp_async_commit();
+    }
+
+    // Cholesky of G (replicated), Lambda (own rows), K (own columns), t, k.
+    double Lg[tri(M)], dg[M];
+#pragma unroll
+    for (int t = 0; t < tri(M); ++t) Lg[t] = SM(S::xGuu + t);
+    bool g_ok = true;
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+      double x = Lg[pk(j, j, M)];
+#pragma unroll
+      for (int p = 0; p < j; ++p) x -= Lg[pk(j, p, M)] * Lg[pk(j, p, M)];
+      g_ok = g_ok && (x > 0.0);
+      const double d = rsqrt(x);
+      dg[j] = d;
+#pragma unroll
+      for (int i = j + 1; i < M; ++i) {
+        double t = Lg[pk(i, j, M)];
+#pragma unroll
+        for (int p = 0; p < j; ++p) t -= Lg[pk(i, p, M)] * Lg[pk(j, p, M)];
+        Lg[pk(i, j, M)] = t * d;
+      }
+    }
+    if (!g_ok && status == SIPOC_FACTOR_SUCCESS) status = SIPOC_FACTOR_G_FACTORIZATION_FAILURE;
+
+    double tt[M];
+    if (SOLVE) {
+#pragma unroll
+      for (int a = 0; a < M; ++a) {
+        double t = SM(S::xH + a);
+#pragma unroll
+        for (int c = 0; c < a; ++c) t -= Lg[pk(a, c, M)] * tt[c];
+        tt[a] = t * dg[a];
+      }
+      // k_k = -L_G^-T t
+      double kk[M];
+#pragma unroll
+      for (int a = M - 1; a >= 0; --a) {
+        double t = tt[a];
+#pragma unroll
+        for (int c = a + 1; c < M; ++c) t -= Lg[pk(c, a, M)] * kk[c];
+        kk[a] = t * dg[a];
+      }
+      if (valid && r == 0) {
+#pragma unroll
+        for (int a = 0; a < M; ++a) stcs(kst + static_cast<int64_t>(k * M + a) * ld, -kk[a]);
+      }
+    }
+    {
+      // G^-1 = L_G^-T L_G^-1 (packed lower) for later solves against this factor.
+      double Gi[tri(M)];
+#pragma unroll
+      for (int j = 0; j < M; ++j)
+#pragma unroll
+        for (int i = j; i < M; ++i) {
+          double t = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+          for (int p = j; p < i; ++p) t -= Lg[pk(i, p, M)] * Gi[pk(p, j, M)];
+          Gi[pk(i, j, M)] = t * dg[i];
+        }
+      if (valid && r == 0) {
+#pragma unroll
+        for (int j = 0; j < M; ++j)
+#pragma unroll
+          for (int i = j; i < M; ++i) {
+            double t = 0.0;
+#pragma unroll
+            for (int p = i; p < M; ++p) t += Gi[pk(p, i, M)] * Gi[pk(p, j, M)];
+            stcs(Gst + (static_cast<int64_t>(k) * tri(M) + pk(i, j, M)) * ld, t);
+          }
+      }
+    }
+
+    double lam[SX][M];
+#pragma unroll
+    for (int s = 0; s < SX; ++s) {
+#pragma unroll
+      for (int a = 0; a < M; ++a) {
+        double t = SM(S::xPxu + a * N + xj[s]);
+#pragma unroll
+        for (int c = 0; c < a; ++c) t -= lam[s][c] * Lg[pk(a, c, M)];
+        lam[s][a] = t * dg[a];
+      }
+      if (xok[s]) {
+#pragma unroll
+        for (int a = 0; a < M; ++a) SM(S::xLam + a * N + xj[s]) = lam[s][a];
+      }
+      // K(:, xj) = -L_G^-T Lambda(xj, :)'
+      double kap[M];
+#pragma unroll
+      for (int a = M - 1; a >= 0; --a) {
+        double t = lam[s][a];
+#pragma unroll
+        for (int c = a + 1; c < M; ++c) t -= Lg[pk(c, a, M)] * kap[c];
+        kap[a] = t * dg[a];
+      }
+      if (valid && xok[s]) {
+#pragma unroll
+        for (int a = 0; a < M; ++a)
+          stcs(Kst + (static_cast<int64_t>(k) * N * M + xj[s] * M + a) * ld, -kap[a]);
+      }
+    }
+    __syncwarp();  // Lambda visible
+
+    // V_k = Psi_xx - Lambda Lambda', v_k = w - Lambda t (own columns).
+    double vv[SX];
+#pragma unroll
+    for (int s = 0; s < SX; ++s) {
+#pragma unroll
+      for (int i = kGroup * s; i < N; ++i) {
+        double t = Pxx[s][i];
+#pragma unroll
+        for (int a = 0; a < M; ++a) t -= SM(S::xLam + a * N + i) * lam[s][a];
+        Pxx[s][i] = t;
+      }
+      double t = wx[s];
+      if (SOLVE) {
+#pragma unroll
+        for (int a = 0; a < M; ++a) t -= lam[s][a] * tt[a];
+      }
+      vv[s] = t;
+    }
+    process_node(k, Pxx, vv);
+  }
+
+  if (status_out != nullptr && valid && r == 0) status_out[b] = status;
+#undef SM
+}
+
+// ===========================================================================
+// Backward sweep, one thread per problem, registers only (tiny n).
+// ===========================================================================
+template <int N, int M, bool SOLVE>
+__global__ void __launch_bounds__(64)
+riccati_backward_thread(LqrIn in, int *status_out, double *store, double *scratch,
+                        int64_t batch, int64_t ld, int T) {
+  using Z = FastSizes<N, M>;
+  const int64_t b = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  const size_t L_ = static_cast<size_t>(ld);
+#define G(ptr, e) ldcs((ptr) + static_cast<size_t>(e) * L_ + b)
+  double *Wst = store + Z::oW(T) * ld + b;
+  double *Kst = store + Z::oK(T) * ld + b;
+  double *Gst = store + Z::oG(T) * ld + b;
+  double *vst = SOLVE ? scratch + Z::ov(T) * ld + b : nullptr;
+  double *kst = SOLVE ? scratch + Z::ok(T) * ld + b : nullptr;
+
+  int status = SIPOC_FACTOR_SUCCESS;
+  double W[tri(N)], v[N], dl[N];
+
+  // V (packed lower), vv, delta of node k -> W, v, dl; stores W_k, v_k.
+  auto process_node = [&](int k, double (&V)[tri(N)], double (&vv)[N]) {
+    double sd[N], sdi[N];
+    bool d_ok = true;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const double d = G(in.delta, k * N + i);
+      d_ok = d_ok && (d > 0.0);
+      dl[i] = d;
+      sd[i] = sqrt(d);
+      sdi[i] = 1.0 / sd[i];
+    }
+    if (!d_ok && status == SIPOC_FACTOR_SUCCESS) status = SIPOC_FACTOR_INVALID_DELTA;
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+      for (int i = j; i < N; ++i)
+        V[pk(i, j, N)] = sd[i] * V[pk(i, j, N)] * sd[j] + (i == j ? 1.0 : 0.0);
+    double dinv[N];
+    bool f_ok = true;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      double x = V[pk(j, j, N)];
+#pragma unroll
+      for (int p = 0; p < j; ++p) x -= V[pk(j, p, N)] * V[pk(j, p, N)];
+      f_ok = f_ok && (x > 0.0);
+      const double d = rsqrt(x);
+      dinv[j] = d;
+#pragma unroll
+      for (int i = j + 1; i < N; ++i) {
+        double t = V[pk(i, j, N)];
+#pragma unroll
+        for (int p = 0; p < j; ++p) t -= V[pk(i, p, N)] * V[pk(j, p, N)];
+        V[pk(i, j, N)] = t * d;
+      }
+    }
+    if (!f_ok && status == SIPOC_FACTOR_SUCCESS) status = SIPOC_FACTOR_F_FACTORIZATION_FAILURE;
+    double Li[tri(N)];
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+      for (int i = j; i < N; ++i) {
+        double t = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+        for (int p = j; p < i; ++p) t -= V[pk(i, p, N)] * Li[pk(p, j, N)];
+        Li[pk(i, j, N)] = t * dinv[i];
+      }
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+      for (int i = j; i < N; ++i) {
+        double fin = 0.0;
+#pragma unroll
+        for (int p = i; p < N; ++p) fin += Li[pk(p, i, N)] * Li[pk(p, j, N)];
+        const double w = sdi[i] * ((i == j ? 1.0 : 0.0) - fin) * sdi[j];
+        W[pk(i, j, N)] = w;
+        stcs(Wst + (static_cast<int64_t>(k) * tri(N) + pk(i, j, N)) * ld, w);
+      }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      v[i] = vv[i];
+      if (SOLVE) stcs(vst + static_cast<int64_t>(k * N + i) * ld, vv[i]);
+    }
+  };
+
+  {
+    double V[tri(N)], vv[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+      for (int i = j; i < N; ++i) V[pk(i, j, N)] = G(in.Q, (T * N + j) * N + i);
+#pragma unroll
+    for (int i = 0; i < N; ++i) vv[i] = SOLVE ? G(in.q, T * N + i) : 0.0;
+    process_node(T, V, vv);
+  }
+
+  for (int k = T - 1; k >= 0; --k) {
+    // Z = [B | A]
+    double Zm[N + M][N];
+#pragma unroll
+    for (int a = 0; a < M; ++a)
+#pragma unroll
+      for (int p = 0; p < N; ++p) Zm[a][p] = G(in.B, (k * M + a) * N + p);
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+      for (int p = 0; p < N; ++p) Zm[M + j][p] = G(in.A, (k * N + j) * N + p);
+    double g[N];
+    if (SOLVE) {
+      double f[N];
+#pragma unroll
+      for (int i = 0; i < N; ++i) f[i] = dl[i] * v[i] - G(in.c, (k + 1) * N + i);
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        double acc = 0.0;
+#pragma unroll
+        for (int q = 0; q < N; ++q) acc += W[q <= i ? pk(i, q, N) : pk(q, i, N)] * f[q];
+        g[i] = v[i] - acc;
+      }
+    }
+    // S = W' Z
+    double Sm[N + M][N];
+#pragma unroll
+    for (int c = 0; c < N + M; ++c)
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        double acc = 0.0;
+#pragma unroll
+        for (int q = 0; q < N; ++q) acc += W[q <= i ? pk(i, q, N) : pk(q, i, N)] * Zm[c][q];
+        Sm[c][i] = acc;
+      }
+    // Psi (lower) and [h; w]
+    double Puu[tri(M)], Pxu[M][N], Pxx[tri(N)], hu[M], wx[N];
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+#pragma unroll
+      for (int i = j; i < M; ++i) {
+        double acc = G(in.R, (k * M + j) * M + i);
+#pragma unroll
+        for (int p = 0; p < N; ++p) acc += Zm[i][p] * Sm[j][p];
+        Puu[pk(i, j, M)] = acc;
+      }
+#pragma unroll
+      for (int x = 0; x < N; ++x) {
+        double acc = G(in.M, (k * M + j) * N + x);
+#pragma unroll
+        for (int p = 0; p < N; ++p) acc += Zm[M + x][p] * Sm[j][p];
+        Pxu[j][x] = acc;
+      }
+      double acc = 0.0;
+      if (SOLVE) {
+        acc = G(in.r, k * M + j);
+#pragma unroll
+        for (int p = 0; p < N; ++p) acc += Zm[j][p] * g[p];
+      }
+      hu[j] = acc;
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+#pragma unroll
+      for (int i = j; i < N; ++i) {
+        double acc = G(in.Q, (k * N + j) * N + i);
+#pragma unroll
+        for (int p = 0; p < N; ++p) acc += Zm[M + i][p] * Sm[M + j][p];
+        Pxx[pk(i, j, N)] = acc;
+      }
+      double acc = 0.0;
+      if (SOLVE) {
+        acc = G(in.q, k * N + j);
+#pragma unroll
+        for (int p = 0; p < N; ++p) acc += Zm[M + j][p] * g[p];
+      }
+      wx[j] = acc;
+    }
+    // Cholesky of G
+    double dg[M];
+    bool g_ok = true;
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+      double x = Puu[pk(j, j, M)];
+#pragma unroll
+      for (int p = 0; p < j; ++p) x -= Puu[pk(j, p, M)] * Puu[pk(j, p, M)];
+      g_ok = g_ok && (x > 0.0);
+      const double d = rsqrt(x);
+      dg[j] = d;
+#pragma unroll
+      for (int i = j + 1; i < M; ++i) {
+        double t = Puu[pk(i, j, M)];
+#pragma unroll
+        for (int p = 0; p < j; ++p) t -= Puu[pk(i, p, M)] * Puu[pk(j, p, M)];
+        Puu[pk(i, j, M)] = t * d;
+      }
+    }
+    if (!g_ok && status == SIPOC_FACTOR_SUCCESS) status = SIPOC_FACTOR_G_FACTORIZATION_FAILURE;
+    double tt[M];
+    if (SOLVE) {
+#pragma unroll
+      for (int a = 0; a < M; ++a) {
+        double t = hu[a];
+#pragma unroll
+        for (int c = 0; c < a; ++c) t -= Puu[pk(a, c, M)] * tt[c];
+        tt[a] = t * dg[a];
+      }
+      double kk[M];
+#pragma unroll
+      for (int a = M - 1; a >= 0; --a) {
+        double t = tt[a];
+#pragma unroll
+        for (int c = a + 1; c < M; ++c) t -= Puu[pk(c, a, M)] * kk[c];
+        kk[a] = t * dg[a];
+        stcs(kst + static_cast<int64_t>(k * M + a) * ld, -kk[a]);
+      }
+    }
+    {
+      double Gi[tri(M)];
+#pragma unroll
+      for (int j = 0; j < M; ++j)
+#pragma unroll
+        for (int i = j; i < M; ++i) {
+          double t = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+          for (int p = j; p < i; ++p) t -= Puu[pk(i, p, M)] * Gi[pk(p, j, M)];
+          Gi[pk(i, j, M)] = t * dg[i];
+        }
+#pragma unroll
+      for (int j = 0; j < M; ++j)
+#pragma unroll
+        for (int i = j; i < M; ++i) {
+          double t = 0.0;
+#pragma unroll
+          for (int p = i; p < M; ++p) t += Gi[pk(p, i, M)] * Gi[pk(p, j, M)];
+          stcs(Gst + (static_cast<int64_t>(k) * tri(M) + pk(i, j, M)) * ld, t);
+        }
+    }
+    // Lambda, K, V, v
+    double lam[N][M];
+#pragma unroll
+    for (int x = 0; x < N; ++x) {
+#pragma unroll
+      for (int a = 0; a < M; ++a) {
+        double t = Pxu[a][x];
+#pragma unroll
+        for (int c = 0; c < a; ++c) t -= lam[x][c] * Puu[pk(a, c, M)];
+        lam[x][a] = t * dg[a];
+      }
+      double kap[M];
+#pragma unroll
+      for (int a = M - 1; a >= 0; --a) {
+        double t = lam[x][a];
+#pragma unroll
+        for (int c = a + 1; c < M; ++c) t -= Puu[pk(c, a, M)] * kap[c];
+        kap[a] = t * dg[a];
+        stcs(Kst + (static_cast<int64_t>(k) * N * M + x * M + a) * ld, -kap[a]);
+      }
+    }
+    double vv[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+#pragma unroll
+      for (int i = j; i < N; ++i) {
+        double t = Pxx[pk(i, j, N)];
+#pragma unroll
+        for (int a = 0; a < M; ++a) t -= lam[i][a] * lam[j][a];
+        Pxx[pk(i, j, N)] = t;
+      }
+      double t = wx[j];
+      if (SOLVE) {
+#pragma unroll
+        for (int a = 0; a < M; ++a) t -= lam[j][a] * tt[a];
+      }
+      vv[j] = t;
+    }
+    process_node(k, Pxx, vv);
+  }
+  if (status_out != nullptr) status_out[b] = status;
+#undef G
+}
+
+// ===========================================================================
+// Backward affine sweep against a kept factorization (lqr.cpp:738-796).
+// ===========================================================================
+template <int N, int M>
+__global__ void __launch_bounds__(128)
+affine_backward(LqrIn in, const double *store, double *scratch, int64_t batch, int64_t ld,
+                int T) {
+  using Z = FastSizes<N, M>;
+  const int64_t b = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  const size_t L_ = static_cast<size_t>(ld);
+#define G(ptr, e) ldcs((ptr) + static_cast<size_t>(e) * L_ + b)
+  const double *Wst = store + Z::oW(T) * ld;
+  const double *Kst = store + Z::oK(T) * ld;
+  const double *Gst = store + Z::oG(T) * ld;
+  double *vst = scratch + Z::ov(T) * ld + b;
+  double *kst = scratch + Z::ok(T) * ld + b;
+
+  double v[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    v[i] = G(in.q, T * N + i);
+    stcs(vst + static_cast<int64_t>(T * N + i) * ld, v[i]);
+  }
+  for (int k = T - 1; k >= 0; --k) {
+    double f[N], g[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      f[i] = G(in.delta, (k + 1) * N + i) * v[i] - G(in.c, (k + 1) * N + i);
+      g[i] = v[i];
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+      for (int i = j; i < N; ++i) {
+        const double w = G(Wst, (k + 1) * tri(N) + pk(i, j, N));
+        g[i] -= w * f[j];
+        if (i != j) g[j] -= w * f[i];
+      }
+    double h[M];
+#pragma unroll
+    for (int a = 0; a < M; ++a) {
+      double acc = G(in.r, k * M + a);
+#pragma unroll
+      for (int p = 0; p < N; ++p) acc += G(in.B, (k * M + a) * N + p) * g[p];
+      h[a] = acc;
+    }
+    double kk[M];
+#pragma unroll
+    for (int a = 0; a < M; ++a) kk[a] = 0.0;
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+      for (int i = j; i < M; ++i) {
+        const double gi = G(Gst, k * tri(M) + pk(i, j, M));
+        kk[i] -= gi * h[j];
+        if (i != j) kk[j] -= gi * h[i];
+      }
+#pragma unroll
+    for (int a = 0; a < M; ++a) stcs(kst + static_cast<int64_t>(k * M + a) * ld, kk[a]);
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      double acc = G(in.q, k * N + j);
+#pragma unroll
+      for (int p = 0; p < N; ++p) acc += G(in.A, (k * N + j) * N + p) * g[p];
+#pragma unroll
+      for (int a = 0; a < M; ++a) acc += G(Kst, (k * N + j) * M + a) * h[a];
+      v[j] = acc;
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) stcs(vst + static_cast<int64_t>(k * N + i) * ld, v[i]);
+  }
+#undef G
+}
+
+// ===========================================================================
+// Root solve + forward rollout + costates (lqr.cpp:798-870).
+// ===========================================================================
+template <int N, int M>
+__global__ void __launch_bounds__(128)
+rollout_forward(LqrIn in, LqrOut out, const double *store, const double *scratch,
+                int64_t batch, int64_t ld, int T) {
+  using Z = FastSizes<N, M>;
+  const int64_t b = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  const size_t L_ = static_cast<size_t>(ld);
+#define G(ptr, e) ldcs((ptr) + static_cast<size_t>(e) * L_ + b)
+  const double *Wst = store + Z::oW(T) * ld;
+  const double *Kst = store + Z::oK(T) * ld;
+  const double *vst = scratch + Z::ov(T) * ld;
+  const double *kst = scratch + Z::ok(T) * ld;
+  double *xo = out.x + b, *uo = out.u + b, *yo = out.y + b;
+
+  double x[N];
+  {  // root: x_0 = -(I - D W)(delta o v - c), y_0 = v - W (delta o v - c)
+    double f[N], wf[N], vv[N], dd[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      vv[i] = G(vst, i);
+      dd[i] = G(in.delta, i);
+      f[i] = dd[i] * vv[i] - G(in.c, i);
+      wf[i] = 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+      for (int i = j; i < N; ++i) {
+        const double w = G(Wst, pk(i, j, N));
+        wf[i] += w * f[j];
+        if (i != j) wf[j] += w * f[i];
+      }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      x[i] = dd[i] * wf[i] - f[i];
+      stcs(xo + static_cast<size_t>(i) * L_, x[i]);
+      stcs(yo + static_cast<size_t>(i) * L_, vv[i] - wf[i]);
+    }
+  }
+  for (int k = 0; k < T; ++k) {
+    double u[M];
+#pragma unroll
+    for (int a = 0; a < M; ++a) u[a] = G(kst, k * M + a);
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+      for (int a = 0; a < M; ++a) u[a] += G(Kst, (k * N + j) * M + a) * x[j];
+#pragma unroll
+    for (int a = 0; a < M; ++a) stcs(uo + static_cast<size_t>(k * M + a) * L_, u[a]);
+    double f[N], vv[N], dd[N], wf[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      vv[i] = G(vst, (k + 1) * N + i);
+      dd[i] = G(in.delta, (k + 1) * N + i);
+      f[i] = G(in.c, (k + 1) * N + i) - dd[i] * vv[i];
+      wf[i] = 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+      for (int i = 0; i < N; ++i) f[i] += G(in.A, (k * N + j) * N + i) * x[j];
+#pragma unroll
+    for (int a = 0; a < M; ++a)
+#pragma unroll
+      for (int i = 0; i < N; ++i) f[i] += G(in.B, (k * M + a) * N + i) * u[a];
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+      for (int i = j; i < N; ++i) {
+        const double w = G(Wst, (k + 1) * tri(N) + pk(i, j, N));
+        wf[i] += w * f[j];
+        if (i != j) wf[j] += w * f[i];
+      }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      x[i] = f[i] - dd[i] * wf[i];
+      stcs(xo + static_cast<size_t>((k + 1) * N + i) * L_, x[i]);
+      stcs(yo + static_cast<size_t>((k + 1) * N + i) * L_, vv[i] + wf[i]);
+    }
+  }
+#undef G
+}
+
+// ===========================================================================
+// Plans
+// ===========================================================================
+template <int N, int M, bool SUBWARP>
+struct Plan {
+  static int64_t store_elems(int T) { return FastSizes<N, M>::store(T); }
+  static int64_t scratch_elems(int T) { return FastSizes<N, M>::scratch(T); }
+
+  template <bool SOLVE>
+  static void backward(const FastArgs &a, cudaStream_t s) {
+    if constexpr (SUBWARP) {
+      auto kern = riccati_backward_subwarp<N, M, SOLVE>;
+      constexpr int bytes = Smem<N, M>::kBytes;
+      if (bytes > 48 * 1024)
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+      const unsigned grid = static_cast<unsigned>((a.batch + kTile - 1) / kTile);
+      ProfScope ps(a.prof, "riccati_backward_subwarp", s);
+      kern<<<grid, 32, bytes, s>>>(a.in, a.status, a.store, a.scratch, a.batch, a.ld,
+                                   a.num_edges);
+    } else {
+      const unsigned grid = static_cast<unsigned>((a.batch + 63) / 64);
+      ProfScope ps(a.prof, "riccati_backward_thread", s);
+      riccati_backward_thread<N, M, SOLVE>
+          <<<grid, 64, 0, s>>>(a.in, a.status, a.store, a.scratch, a.batch, a.ld, a.num_edges);
+    }
+  }
+  static void forward(const FastArgs &a, cudaStream_t s) {
+    const unsigned grid = static_cast<unsigned>((a.batch + 127) / 128);
+    ProfScope ps(a.prof, "rollout_forward", s);
+    rollout_forward<N, M>
+        <<<grid, 128, 0, s>>>(a.in, a.out, a.store, a.scratch, a.batch, a.ld, a.num_edges);
+  }
+  static int factor(const FastArgs &a, cudaStream_t s) {
+    backward<false>(a, s);
+    return 1;
+  }
+  static int solve(const FastArgs &a, cudaStream_t s) {
+    const unsigned grid = static_cast<unsigned>((a.batch + 127) / 128);
+    {
+      ProfScope ps(a.prof, "affine_backward", s);
+      affine_backward<N, M>
+          <<<grid, 128, 0, s>>>(a.in, a.store, a.scratch, a.batch, a.ld, a.num_edges);
+    }
+    forward(a, s);
+    return 2;
+  }
+  static int factor_solve(const FastArgs &a, cudaStream_t s) {
+    backward<true>(a, s);
+    forward(a, s);
+    return 2;
+  }
+};
+
+template <int N, int M, bool SUBWARP>
+const FastPlan *make_plan(const char *name) {
+  using P = Plan<N, M, SUBWARP>;
+  static const FastPlan plan{name,         N,           M,         &P::store_elems,
+                             &P::scratch_elems, &P::factor, &P::solve, &P::factor_solve};
+  return &plan;
+}
+
+}  // namespace
+
+const FastPlan *select_fast_plan(int n, int m) {
+  if (n == 4 && m == 1) return make_plan<4, 1, false>("thread_per_problem_n4_m1");
+  if (n == 12 && m == 4) return make_plan<12, 4, true>("subwarp4_n12_m4");
+  if (n == 6 && m == 2) return make_plan<6, 2, true>("subwarp4_n6_m2");
+  if (n == 8 && m == 3) return make_plan<8, 3, true>("subwarp4_n8_m3");
+  return nullptr;
+}
+
 }  // namespace sipoc
