@@ -38,12 +38,22 @@
 #include "riccati_fast.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 
 namespace sipoc {
 namespace {
 
 constexpr int kGroup = 4;  // lanes per problem
 constexpr int kTile = 8;   // problems per warp
+
+// Warps per CTA of the sub-warp backward kernel (tuning knob, default 1).
+inline int backward_warps() {
+  static const int w = [] {
+    const char *e = getenv("SIPOC_BACKWARD_WARPS");
+    return e != nullptr ? atoi(e) : 1;
+  }();
+  return w;
+}
 
 __host__ __device__ constexpr int tri(int n) { return n * (n + 1) / 2; }
 // Column-major packed lower index, i >= j.
@@ -95,8 +105,8 @@ struct Smem {
   static constexpr int rc = rr + M;           // c_{k+1}
   static constexpr int rd = rc + N;           // delta_k (as staged)
   static constexpr int kStaged = rd + N;
-  static constexpr int rW = kStaged;          // W of the last processed node, packed lower
-  static constexpr int rG = rW + tri(N);      // g
+  static constexpr int rW = kStaged;          // W of the last processed node, full N x N
+  static constexpr int rG = rW + N * N;        // g
   static constexpr int rV = rG + N;           // v of the last processed node
   static constexpr int rDl = rV + N;          // delta of the last processed node
   static constexpr int rSd = rDl + N;         // sqrt(delta), 1/sqrt(delta) of the node in flight
@@ -115,45 +125,50 @@ struct Smem {
 
 // Copies `count` consecutive flat elements (rows of 8 problems) into shared
 // memory: lane l moves 16 B (problems 2(l&3), 2(l&3)+1) of row (l>>2) + 8 i.
-__device__ __forceinline__ void stage_rows(double *sm, int dst_row0, const double *g,
-                                           int64_t ld, int count, int lane) {
-  const int sub = lane & 3, rr = lane >> 2;
+// `dst` and `src` already include the lane's own row / chunk offset; ld8 = 8 ld.
+__device__ __forceinline__ void stage_run(double *dst, const double *src, int64_t ld8,
+                                          int count, int rr) {
 #pragma unroll
   for (int i0 = 0; i0 < count; i0 += 8) {
-    const int i = i0 + rr;
-    if (i < count)
-      cp_async16(sm + (dst_row0 + i) * kTile + sub * 2, g + static_cast<int64_t>(i) * ld + sub * 2);
+    if (i0 + 8 <= count || i0 + rr < count) cp_async16(dst + i0 * kTile, src);
+    src += ld8;
   }
 }
 
+// Lower triangle of a column-major N x N block -> packed lower rows.
 template <int N>
-__device__ __forceinline__ void stage_lower(double *sm, int dst_row0, const double *g, int64_t ld,
-                                            int lane) {
+__device__ __forceinline__ void stage_lower(double *dst, const double *src, int64_t ld,
+                                            int64_t ld8, int rr) {
 #pragma unroll
-  for (int j = 0; j < N; ++j)
-    stage_rows(sm, dst_row0 + pk(j, j, N), g + static_cast<int64_t>(j * N + j) * ld, ld, N - j,
-               lane);
+  for (int j = 0; j < N; ++j) {
+    stage_run(dst + pk(j, j, N) * kTile, src, ld8, N - j, rr);
+    src += (N + 1) * ld;
+  }
 }
 
 // ===========================================================================
-// Backward sweep, four lanes per problem.
+// Backward sweep, four lanes per problem, WARPS warps (8 problems each) per CTA.
 // ===========================================================================
-template <int N, int M, bool SOLVE>
-__global__ void __launch_bounds__(32)
+template <int N, int M, bool SOLVE, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS)
 riccati_backward_subwarp(LqrIn in, int *status_out, double *store, double *scratch,
                          int64_t batch, int64_t ld, int T) {
   using S = Smem<N, M>;
   using Z = FastSizes<N, M>;
   constexpr int SX = cdiv(N, kGroup);  // own state columns per lane
   constexpr int SU = cdiv(M, kGroup);  // own control columns per lane
-  extern __shared__ __align__(16) double sm[];
+  extern __shared__ __align__(16) double sm_all[];
 
-  const int lane = threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  double *sm = sm_all + warp * (S::kRows * kTile);
   const int prob = lane & (kTile - 1);
   const int r = lane >> 3;
-  const int64_t b0 = static_cast<int64_t>(blockIdx.x) * kTile;
+  int64_t b0 = (static_cast<int64_t>(blockIdx.x) * WARPS + warp) * kTile;
+  const bool tile_ok = b0 < batch;
+  if (b0 + kTile > ld) b0 = ld - kTile;  // spare warp of the last CTA: stay in bounds
   const int64_t b = b0 + prob;
-  const bool valid = b < batch;
+  const bool valid = tile_ok && b < batch;
   const unsigned group_mask = 0x01010101u << prob;
 
   // Own columns (cyclic): state column xj[s] = r + 4 s, control column uj[s].
@@ -176,36 +191,62 @@ riccati_backward_subwarp(LqrIn in, int *status_out, double *store, double *scrat
 
 #define SM(row) sm[(row) * kTile + prob]
 
-  const double *gA = in.A + b0, *gB = in.B + b0, *gQ = in.Q + b0, *gM = in.M + b0,
-               *gR = in.R + b0, *gq = in.q + b0, *gr = in.r + b0, *gc = in.c + b0,
-               *gd = in.delta + b0;
-  double *Wst = store + Z::oW(T) * ld + b;
-  double *Kst = store + Z::oK(T) * ld + b;
-  double *Gst = store + Z::oG(T) * ld + b;
-  double *vst = SOLVE ? scratch + Z::ov(T) * ld + b : nullptr;
-  double *kst = SOLVE ? scratch + Z::ok(T) * ld + b : nullptr;
+  // Staging: per-array running pointers to the block of the stage to fetch next
+  // (already offset by this lane's row / 16-byte chunk); they walk backward.
+  const int rr = lane >> 2;
+  const int64_t ld8 = ld * 8;
+  const int64_t lane_goff = rr * ld + (lane & 3) * 2 + b0;
+  double *sdst = sm + rr * kTile + (lane & 3) * 2;
+  const double *pQ = in.Q + static_cast<int64_t>(T) * N * N * ld + lane_goff;
+  const double *pd = in.delta + static_cast<int64_t>(T) * N * ld + lane_goff;
+  const double *pq = SOLVE ? in.q + static_cast<int64_t>(T) * N * ld + lane_goff : nullptr;
+  const double *pc = SOLVE ? in.c + static_cast<int64_t>(T) * N * ld + lane_goff : nullptr;
+  const double *pA = in.A + static_cast<int64_t>(T - 1) * N * N * ld + lane_goff;
+  const double *pB = in.B + static_cast<int64_t>(T - 1) * N * M * ld + lane_goff;
+  const double *pM = in.M + static_cast<int64_t>(T - 1) * N * M * ld + lane_goff;
+  const double *pR = in.R + static_cast<int64_t>(T - 1) * M * M * ld + lane_goff;
+  const double *pr = SOLVE ? in.r + static_cast<int64_t>(T - 1) * M * ld + lane_goff : nullptr;
 
-  auto issue_node = [&](int k) {
-    stage_lower<N>(sm, S::rQ, gQ + static_cast<int64_t>(k) * N * N * ld, ld, lane);
-    stage_rows(sm, S::rd, gd + static_cast<int64_t>(k) * N * ld, ld, N, lane);
-    if (SOLVE) stage_rows(sm, S::rq, gq + static_cast<int64_t>(k) * N * ld, ld, N, lane);
-  };
-  auto issue_edge = [&](int k) {
-    stage_rows(sm, S::rZ, gB + static_cast<int64_t>(k) * N * M * ld, ld, N * M, lane);
-    stage_rows(sm, S::rZ + N * M, gA + static_cast<int64_t>(k) * N * N * ld, ld, N * N, lane);
-    stage_rows(sm, S::rM, gM + static_cast<int64_t>(k) * N * M * ld, ld, N * M, lane);
-    stage_lower<M>(sm, S::rR, gR + static_cast<int64_t>(k) * M * M * ld, ld, lane);
+  // Node data of the node the pointers stand on, then step one node back.
+  auto issue_node = [&]() {
+    stage_lower<N>(sdst + S::rQ * kTile, pQ, ld, ld8, rr);
+    stage_run(sdst + S::rd * kTile, pd, ld8, N, rr);
+    pQ -= static_cast<int64_t>(N) * N * ld;
+    pd -= static_cast<int64_t>(N) * ld;
     if (SOLVE) {
-      stage_rows(sm, S::rr, gr + static_cast<int64_t>(k) * M * ld, ld, M, lane);
-      stage_rows(sm, S::rc, gc + static_cast<int64_t>(k + 1) * N * ld, ld, N, lane);
+      stage_run(sdst + S::rq * kTile, pq, ld8, N, rr);
+      pq -= static_cast<int64_t>(N) * ld;
     }
   };
+  // Edge data (and c of the edge's child node), then step one edge back.
+  auto issue_edge = [&]() {
+    stage_run(sdst + S::rZ * kTile, pB, ld8, N * M, rr);
+    stage_run(sdst + (S::rZ + N * M) * kTile, pA, ld8, N * N, rr);
+    stage_run(sdst + S::rM * kTile, pM, ld8, N * M, rr);
+    stage_lower<M>(sdst + S::rR * kTile, pR, ld, ld8, rr);
+    pB -= static_cast<int64_t>(N) * M * ld;
+    pA -= static_cast<int64_t>(N) * N * ld;
+    pM -= static_cast<int64_t>(N) * M * ld;
+    pR -= static_cast<int64_t>(M) * M * ld;
+    if (SOLVE) {
+      stage_run(sdst + S::rr * kTile, pr, ld8, M, rr);
+      stage_run(sdst + S::rc * kTile, pc, ld8, N, rr);
+      pr -= static_cast<int64_t>(M) * ld;
+      pc -= static_cast<int64_t>(N) * ld;
+    }
+  };
+
+  // Output pointers of the stage in flight (problem b), walking backward too.
+  double *Wst = store + (Z::oW(T) + static_cast<int64_t>(T) * tri(N)) * ld + b;
+  double *Kst = store + (Z::oK(T) + static_cast<int64_t>(T - 1) * N * M) * ld + b;
+  double *Gst = store + (Z::oG(T) + static_cast<int64_t>(T - 1) * tri(M)) * ld + b;
+  double *vst = SOLVE ? scratch + (Z::ov(T) + static_cast<int64_t>(T) * N) * ld + b : nullptr;
+  double *kst = SOLVE ? scratch + (Z::ok(T) + static_cast<int64_t>(T - 1) * M) * ld + b : nullptr;
 
   int status = SIPOC_FACTOR_SUCCESS;
   bool bad_delta = false;
 
-  // delta, sqrt(delta), 1/sqrt(delta) of the node whose delta is staged in rd:
-  // each lane handles its own rows.
+  // delta_k -> rDl, sqrt -> rSd, 1/sqrt -> rSdi, own rows  (lqr.cpp:475-485)
   auto update_delta = [&]() {
     bad_delta = false;
 #pragma unroll
@@ -221,11 +262,305 @@ riccati_backward_subwarp(LqrIn in, int *status_out, double *store, double *scrat
     }
   };
 
-  // Node processing: V (own columns, rows >= 4 s) and v (own entries) in
-  // registers -> W_k in shared memory and in the store, v_k in shared memory
-  // and in the spill.  compute_delta_sqrt + factor_F + compute_regularized_W
-  // (lqr.cpp:475-529).
-  auto process_node = [&](int k, double (&V)[SX][N], double (&vv)[SX]) {
+  issue_node();
+  cp_async_commit();
+
+  for (int k = T; k >= 0; --k) {
+    cp_async_wait_all();
+    // One CTA-wide barrier per stage keeps the warps of the CTA inside the same
+    // stretch of code, so they share instruction-cache lines.
+    if (WARPS > 1) __syncthreads(); else __syncwarp();
+
+    // V_k (own columns, rows >= 4 s) and v_k (own entries).
+    double V[SX][N], vv[SX];
+    if (k == T) {
+      // ---- terminal node: V = Q_T, v = q_T ----------------------------------
+#pragma unroll
+      for (int s = 0; s < SX; ++s) {
+#pragma unroll
+        for (int i = kGroup * s; i < N; ++i) V[s][i] = SM(S::rQ + qcol[s] + i);
+        vv[s] = SOLVE ? SM(S::rq + xj[s]) : 0.0;
+      }
+      update_delta();
+      __syncwarp();
+      if (T > 0) {
+        issue_node();
+        issue_edge();
+        cp_async_commit();
+      }
+    } else {
+      // ---- edge k: parent node k, child node k + 1 ---------------------------
+      // g = v' - W'(delta' o v' - c'), own rows  (lqr.cpp:778-782)
+      if (SOLVE) {
+        double f[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) f[i] = SM(S::rDl + i) * SM(S::rV + i) - SM(S::rc + i);
+#pragma unroll
+        for (int s = 0; s < SX; ++s) {
+          double acc = 0.0;
+#pragma unroll
+          for (int q = 0; q < N; ++q) acc += SM(S::rW + q * N + xj[s]) * f[q];  // W' symmetric
+          if (xok[s]) SM(S::rG + xj[s]) = SM(S::rV + xj[s]) - acc;
+        }
+      }
+      // Own columns of Z = [B | A] stay in registers for the whole stage.
+      double zu[SU][N], zx[SX][N];
+#pragma unroll
+      for (int s = 0; s < SU; ++s)
+#pragma unroll
+        for (int q = 0; q < N; ++q) zu[s][q] = SM(S::rZ + uj[s] * N + q);
+#pragma unroll
+      for (int s = 0; s < SX; ++s)
+#pragma unroll
+        for (int q = 0; q < N; ++q) zx[s][q] = SM(S::rZ + (M + xj[s]) * N + q);
+      __syncwarp();  // g complete; every lane is done with v', delta'
+
+      update_delta();  // node k
+
+      // Psi = [R M'; M Q] + Z' (W' Z), own columns (block-lower), and
+      // [h; w] = [r; q] + Z' g.  One ROLLED loop over the rows p of S = W' Z keeps
+      // the instruction footprint small: row p of S (own columns) is formed from
+      // row p of W' and immediately consumed by the rank-1 update of Psi.
+      double Puu[SU][M], Pxu[SU][N], hu[SU];
+#pragma unroll
+      for (int s = 0; s < SU; ++s) {
+#pragma unroll
+        for (int i = 0; i < M; ++i) Puu[s][i] = 0.0;
+#pragma unroll
+        for (int x = 0; x < N; ++x) Pxu[s][x] = 0.0;
+        hu[s] = 0.0;
+      }
+#pragma unroll
+      for (int s = 0; s < SX; ++s) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) V[s][i] = 0.0;
+        vv[s] = 0.0;
+      }
+      if (SOLVE) {  // [h; w] = Z' g with the own columns of Z already in registers
+#pragma unroll
+        for (int q = 0; q < N; ++q) {
+          const double gq = SM(S::rG + q);
+#pragma unroll
+          for (int s = 0; s < SU; ++s) hu[s] += zu[s][q] * gq;
+#pragma unroll
+          for (int s = 0; s < SX; ++s) vv[s] += zx[s][q] * gq;
+        }
+      }
+#pragma unroll 1
+      for (int p = 0; p < N; ++p) {
+        const double *wrow = sm + (S::rW + p * N) * kTile + prob;
+        const double *zrow = sm + (S::rZ + p) * kTile + prob;
+        double su[SU], sx[SX], su2[SU], sx2[SX];
+#pragma unroll
+        for (int s = 0; s < SU; ++s) su[s] = su2[s] = 0.0;
+#pragma unroll
+        for (int s = 0; s < SX; ++s) sx[s] = sx2[s] = 0.0;
+#pragma unroll
+        for (int q = 0; q < N; ++q) {
+          const double w = wrow[q * kTile];
+          if (q & 1) {
+#pragma unroll
+            for (int s = 0; s < SU; ++s) su2[s] += w * zu[s][q];
+#pragma unroll
+            for (int s = 0; s < SX; ++s) sx2[s] += w * zx[s][q];
+          } else {
+#pragma unroll
+            for (int s = 0; s < SU; ++s) su[s] += w * zu[s][q];
+#pragma unroll
+            for (int s = 0; s < SX; ++s) sx[s] += w * zx[s][q];
+          }
+        }
+#pragma unroll
+        for (int s = 0; s < SU; ++s) su[s] += su2[s];
+#pragma unroll
+        for (int s = 0; s < SX; ++s) sx[s] += sx2[s];
+#pragma unroll
+        for (int i = 0; i < M; ++i) {  // B(p, i)
+          const double z = zrow[i * N * kTile];
+#pragma unroll
+          for (int s = 0; s < SU; ++s)
+            if (i >= kGroup * s) Puu[s][i] += z * su[s];
+        }
+#pragma unroll
+        for (int x = 0; x < N; ++x) {  // A(p, x)
+          const double z = zrow[(M + x) * N * kTile];
+#pragma unroll
+          for (int s = 0; s < SU; ++s) Pxu[s][x] += z * su[s];
+#pragma unroll
+          for (int s = 0; s < SX; ++s)
+            if (x >= kGroup * s) V[s][x] += z * sx[s];
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < SU; ++s) {
+#pragma unroll
+        for (int i = kGroup * s; i < M; ++i) Puu[s][i] += SM(S::rR + rcol[s] + i);
+#pragma unroll
+        for (int x = 0; x < N; ++x) Pxu[s][x] += SM(S::rM + uj[s] * N + x);
+        if (SOLVE) hu[s] += SM(S::rr + uj[s]);
+      }
+#pragma unroll
+      for (int s = 0; s < SX; ++s) {
+#pragma unroll
+        for (int i = kGroup * s; i < N; ++i) V[s][i] += SM(S::rQ + qcol[s] + i);
+        if (SOLVE) vv[s] += SM(S::rq + xj[s]);
+      }
+      // Publish the control block: Psi_uu (packed lower), Psi_xu, h.
+#pragma unroll
+      for (int s = 0; s < SU; ++s) {
+        if (uok[s]) {
+#pragma unroll
+          for (int i = kGroup * s; i < M; ++i)
+            if (i >= uj[s]) SM(S::xGuu + rcol[s] + i) = Puu[s][i];
+#pragma unroll
+          for (int x = 0; x < N; ++x) SM(S::xPxu + uj[s] * N + x) = Pxu[s][x];
+          if (SOLVE) SM(S::xH + uj[s]) = hu[s];
+        }
+      }
+      __syncwarp();  // control block visible; staged operands of stage k consumed
+
+      if (k > 0) {
+        issue_node();
+        issue_edge();
+        cp_async_commit();
+      }
+
+      // Cholesky of G (replicated), Lambda (own rows), K (own columns), t, k.
+      double Lg[tri(M)], dg[M];
+#pragma unroll
+      for (int t = 0; t < tri(M); ++t) Lg[t] = SM(S::xGuu + t);
+      bool g_ok = true;
+#pragma unroll
+      for (int j = 0; j < M; ++j) {
+        double x = Lg[pk(j, j, M)];
+#pragma unroll
+        for (int q = 0; q < j; ++q) x -= Lg[pk(j, q, M)] * Lg[pk(j, q, M)];
+        g_ok = g_ok && (x > 0.0);
+        const double d = rsqrt(x);
+        dg[j] = d;
+#pragma unroll
+        for (int i = j + 1; i < M; ++i) {
+          double t = Lg[pk(i, j, M)];
+#pragma unroll
+          for (int q = 0; q < j; ++q) t -= Lg[pk(i, q, M)] * Lg[pk(j, q, M)];
+          Lg[pk(i, j, M)] = t * d;
+        }
+      }
+      if (!g_ok && status == SIPOC_FACTOR_SUCCESS) status = SIPOC_FACTOR_G_FACTORIZATION_FAILURE;
+
+      double tt[M];
+      if (SOLVE) {
+#pragma unroll
+        for (int a = 0; a < M; ++a) {
+          double t = SM(S::xH + a);
+#pragma unroll
+          for (int c = 0; c < a; ++c) t -= Lg[pk(a, c, M)] * tt[c];
+          tt[a] = t * dg[a];
+        }
+        // k_k = -L_G^-T t
+        double kk[M];
+#pragma unroll
+        for (int a = M - 1; a >= 0; --a) {
+          double t = tt[a];
+#pragma unroll
+          for (int c = a + 1; c < M; ++c) t -= Lg[pk(c, a, M)] * kk[c];
+          kk[a] = t * dg[a];
+        }
+        if (valid && r == 0) {
+          double *dst = kst;
+#pragma unroll
+          for (int a = 0; a < M; ++a) {
+            stcs(dst, -kk[a]);
+            dst += ld;
+          }
+        }
+        kst -= static_cast<int64_t>(M) * ld;
+      }
+      {
+        // G^-1 = L_G^-T L_G^-1 (packed lower) for later solves against this factor.
+        double Gi[tri(M)];
+#pragma unroll
+        for (int j = 0; j < M; ++j)
+#pragma unroll
+          for (int i = j; i < M; ++i) {
+            double t = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+            for (int q = j; q < i; ++q) t -= Lg[pk(i, q, M)] * Gi[pk(q, j, M)];
+            Gi[pk(i, j, M)] = t * dg[i];
+          }
+        if (valid && r == 0) {
+          double *dst = Gst;
+#pragma unroll
+          for (int j = 0; j < M; ++j)
+#pragma unroll
+            for (int i = j; i < M; ++i) {
+              double t = 0.0;
+#pragma unroll
+              for (int q = i; q < M; ++q) t += Gi[pk(q, i, M)] * Gi[pk(q, j, M)];
+              stcs(dst, t);
+              dst += ld;
+            }
+        }
+        Gst -= static_cast<int64_t>(tri(M)) * ld;
+      }
+
+      double lam[SX][M];
+#pragma unroll
+      for (int s = 0; s < SX; ++s) {
+#pragma unroll
+        for (int a = 0; a < M; ++a) {
+          double t = SM(S::xPxu + a * N + xj[s]);
+#pragma unroll
+          for (int c = 0; c < a; ++c) t -= lam[s][c] * Lg[pk(a, c, M)];
+          lam[s][a] = t * dg[a];
+        }
+        if (xok[s]) {
+#pragma unroll
+          for (int a = 0; a < M; ++a) SM(S::xLam + a * N + xj[s]) = lam[s][a];
+        }
+        // K(:, xj) = -L_G^-T Lambda(xj, :)'
+        double kap[M];
+#pragma unroll
+        for (int a = M - 1; a >= 0; --a) {
+          double t = lam[s][a];
+#pragma unroll
+          for (int c = a + 1; c < M; ++c) t -= Lg[pk(c, a, M)] * kap[c];
+          kap[a] = t * dg[a];
+        }
+        if (valid && xok[s]) {
+          double *dst = Kst + static_cast<int64_t>(xj[s] * M) * ld;
+#pragma unroll
+          for (int a = 0; a < M; ++a) {
+            stcs(dst, -kap[a]);
+            dst += ld;
+          }
+        }
+      }
+      Kst -= static_cast<int64_t>(N) * M * ld;
+      __syncwarp();  // Lambda visible
+
+      // V_k = Psi_xx - Lambda Lambda', v_k = w - Lambda t (own columns).
+#pragma unroll
+      for (int s = 0; s < SX; ++s) {
+#pragma unroll
+        for (int i = kGroup * s; i < N; ++i) {
+          double t = V[s][i];
+#pragma unroll
+          for (int a = 0; a < M; ++a) t -= SM(S::xLam + a * N + i) * lam[s][a];
+          V[s][i] = t;
+        }
+        if (SOLVE) {
+          double t = vv[s];
+#pragma unroll
+          for (int a = 0; a < M; ++a) t -= lam[s][a] * tt[a];
+          vv[s] = t;
+        }
+      }
+    }
+
+    // ---- node k: compute_delta_sqrt + factor_F + compute_regularized_W --------
+    // (lqr.cpp:475-529): V, v in registers -> W_k in shared memory and in the
+    // store, v_k in shared memory and in the spill.
     double sdo[SX], sdio[SX];
 #pragma unroll
     for (int s = 0; s < SX; ++s) {
@@ -245,9 +580,10 @@ riccati_backward_subwarp(LqrIn in, int *status_out, double *store, double *scrat
         if (xok[s] && i >= xj[s]) SM(S::rX + qcol[s] + i) = V[s][i];
       if (SOLVE && xok[s]) {
         SM(S::rV + xj[s]) = vv[s];
-        if (valid) stcs(vst + static_cast<int64_t>(k * N + xj[s]) * ld, vv[s]);
+        if (valid) stcs(vst + static_cast<int64_t>(xj[s]) * ld, vv[s]);
       }
     }
+    if (SOLVE) vst -= static_cast<int64_t>(N) * ld;
     __syncwarp();
     if (__ballot_sync(0xffffffffu, bad_delta) & group_mask) {
       if (status == SIPOC_FACTOR_SUCCESS) status = SIPOC_FACTOR_INVALID_DELTA;
@@ -262,7 +598,7 @@ riccati_backward_subwarp(LqrIn in, int *status_out, double *store, double *scrat
     for (int j = 0; j < N; ++j) {
       double x = L[pk(j, j, N)];
 #pragma unroll
-      for (int p = 0; p < j; ++p) x -= L[pk(j, p, N)] * L[pk(j, p, N)];
+      for (int q = 0; q < j; ++q) x -= L[pk(j, q, N)] * L[pk(j, q, N)];
       f_ok = f_ok && (x > 0.0);
       const double d = rsqrt(x);
       dinv[j] = d;
@@ -270,315 +606,46 @@ riccati_backward_subwarp(LqrIn in, int *status_out, double *store, double *scrat
       for (int i = j + 1; i < N; ++i) {
         double t = L[pk(i, j, N)];
 #pragma unroll
-        for (int p = 0; p < j; ++p) t -= L[pk(i, p, N)] * L[pk(j, p, N)];
+        for (int q = 0; q < j; ++q) t -= L[pk(i, q, N)] * L[pk(j, q, N)];
         L[pk(i, j, N)] = t * d;
       }
     }
     if (!f_ok && status == SIPOC_FACTOR_SUCCESS) status = SIPOC_FACTOR_F_FACTORIZATION_FAILURE;
-    __syncwarp();  // every lane has read F
 
-    // Own columns of L^-1 (forward substitution on e_xj), kept in registers and
-    // published (packed lower) for the other lanes.
-    double Li[SX][N];
+    // Own columns of F^-1 = L^-T L^-1: forward substitution on e_xj, then backward
+    // substitution, both against the lane's register copy of L (no exchange).
+    // W = D^-1/2 (I - F^-1) D^-1/2, rows >= 4 s of the own columns.
 #pragma unroll
     for (int s = 0; s < SX; ++s) {
+      double y[N];
 #pragma unroll
       for (int i = kGroup * s; i < N; ++i) {
         double t = (i == xj[s]) ? 1.0 : 0.0;
 #pragma unroll
-        for (int p = kGroup * s; p < i; ++p) t -= L[pk(i, p, N)] * Li[s][p];
-        Li[s][i] = t * dinv[i];
-        if (xok[s] && i >= xj[s]) SM(S::rX + qcol[s] + i) = Li[s][i];
+        for (int q = kGroup * s; q < i; ++q) t -= L[pk(i, q, N)] * y[q];
+        y[i] = t * dinv[i];
       }
-    }
-    __syncwarp();
-
-    // W = D^-1/2 (I - L^-T L^-1) D^-1/2, own columns, rows >= 4 s.
 #pragma unroll
-    for (int s = 0; s < SX; ++s) {
+      for (int i = N - 1; i >= kGroup * s; --i) {
+        double t = y[i];
+#pragma unroll
+        for (int q = i + 1; q < N; ++q) t -= L[pk(q, i, N)] * y[q];
+        y[i] = t * dinv[i];
+      }
+      double *dst = Wst + static_cast<int64_t>(qcol[s] + kGroup * s) * ld;
 #pragma unroll
       for (int i = kGroup * s; i < N; ++i) {
-        double fin = 0.0;
-#pragma unroll
-        for (int p = i; p < N; ++p) fin += SM(S::rX + pk(p, i, N)) * Li[s][p];
-        const double w = SM(S::rSdi + i) * ((i == xj[s] ? 1.0 : 0.0) - fin) * sdio[s];
+        const double w = SM(S::rSdi + i) * ((i == xj[s] ? 1.0 : 0.0) - y[i]) * sdio[s];
         if (xok[s] && i >= xj[s]) {
-          SM(S::rW + qcol[s] + i) = w;
-          if (valid) stcs(Wst + (static_cast<int64_t>(k) * tri(N) + qcol[s] + i) * ld, w);
+          SM(S::rW + xj[s] * N + i) = w;
+          SM(S::rW + i * N + xj[s]) = w;
+          if (valid) stcs(dst, w);
         }
+        dst += ld;
       }
     }
+    Wst -= static_cast<int64_t>(tri(N)) * ld;
     __syncwarp();
-  };
-
-  // ---- terminal node: V = Q_T, v = q_T ------------------------------------
-  issue_node(T);
-  cp_async_commit();
-  cp_async_wait_all();
-  __syncwarp();
-  {
-    double V[SX][N], vv[SX];
-#pragma unroll
-    for (int s = 0; s < SX; ++s) {
-#pragma unroll
-      for (int i = kGroup * s; i < N; ++i) V[s][i] = SM(S::rQ + qcol[s] + i);
-      vv[s] = SOLVE ? SM(S::rq + xj[s]) : 0.0;
-    }
-    update_delta();
-    __syncwarp();
-    if (T > 0) {
-      issue_node(T - 1);
-      issue_edge(T - 1);
-      cp_async_commit();
-    }
-    process_node(T, V, vv);
-  }
-
-  // ---- stages T-1 ... 0 -----------------------------------------------------
-  for (int k = T - 1; k >= 0; --k) {
-    cp_async_wait_all();
-    __syncwarp();
-
-    // g = v' - W'(delta' o v' - c'), own rows  (lqr.cpp:778-782)
-    if (SOLVE) {
-      double f[N];
-#pragma unroll
-      for (int i = 0; i < N; ++i) f[i] = SM(S::rDl + i) * SM(S::rV + i) - SM(S::rc + i);
-#pragma unroll
-      for (int s = 0; s < SX; ++s) {
-        double acc = 0.0;
-#pragma unroll
-        for (int q = 0; q < N; ++q) {
-          // W'(xj, q) from the packed lower triangle
-          const int row = (q <= xj[s]) ? (pk(q, q, N) - q + xj[s]) : (qcol[s] + q);
-          acc += SM(S::rW + row) * f[q];
-        }
-        if (xok[s]) SM(S::rG + xj[s]) = SM(S::rV + xj[s]) - acc;
-      }
-    }
-
-    // S = W' Z, own columns of Z = [B | A].
-    double Su[SU][N], Sx[SX][N];
-    {
-      double zu[SU][N], zx[SX][N];
-#pragma unroll
-      for (int s = 0; s < SU; ++s)
-#pragma unroll
-        for (int p = 0; p < N; ++p) {
-          zu[s][p] = SM(S::rZ + uj[s] * N + p);
-          Su[s][p] = 0.0;
-        }
-#pragma unroll
-      for (int s = 0; s < SX; ++s)
-#pragma unroll
-        for (int p = 0; p < N; ++p) {
-          zx[s][p] = SM(S::rZ + (M + xj[s]) * N + p);
-          Sx[s][p] = 0.0;
-        }
-#pragma unroll
-      for (int j = 0; j < N; ++j)
-#pragma unroll
-        for (int i = j; i < N; ++i) {
-          const double w = SM(S::rW + pk(i, j, N));
-#pragma unroll
-          for (int s = 0; s < SU; ++s) {
-            Su[s][i] += w * zu[s][j];
-            if (i != j) Su[s][j] += w * zu[s][i];
-          }
-#pragma unroll
-          for (int s = 0; s < SX; ++s) {
-            Sx[s][i] += w * zx[s][j];
-            if (i != j) Sx[s][j] += w * zx[s][i];
-          }
-        }
-    }
-    __syncwarp();  // g complete; every lane is done with W', v', delta'
-
-    update_delta();  // node k: delta_k -> rDl, rSd, rSdi (own rows)
-
-    // Psi = [R M'; M Q] + Z' S, own columns (block-lower), and [h; w] = [r; q] + Z' g.
-    double Puu[SU][M], Pxu[SU][N], Pxx[SX][N], hu[SU], wx[SX];
-#pragma unroll
-    for (int s = 0; s < SU; ++s) {
-#pragma unroll
-      for (int i = kGroup * s; i < M; ++i) Puu[s][i] = SM(S::rR + rcol[s] + i);
-#pragma unroll
-      for (int x = 0; x < N; ++x) Pxu[s][x] = SM(S::rM + uj[s] * N + x);
-      hu[s] = SOLVE ? SM(S::rr + uj[s]) : 0.0;
-    }
-#pragma unroll
-    for (int s = 0; s < SX; ++s) {
-#pragma unroll
-      for (int i = kGroup * s; i < N; ++i) Pxx[s][i] = SM(S::rQ + qcol[s] + i);
-      wx[s] = SOLVE ? SM(S::rq + xj[s]) : 0.0;
-    }
-#pragma unroll
-    for (int p = 0; p < N; ++p) {
-      if (SOLVE) {
-        const double gp = SM(S::rG + p);
-#pragma unroll
-        for (int s = 0; s < SU; ++s) hu[s] += SM(S::rZ + uj[s] * N + p) * gp;
-#pragma unroll
-        for (int s = 0; s < SX; ++s) wx[s] += SM(S::rZ + (M + xj[s]) * N + p) * gp;
-      }
-#pragma unroll
-      for (int i = 0; i < M; ++i) {  // rows of B
-        const double z = SM(S::rZ + i * N + p);
-#pragma unroll
-        for (int s = 0; s < SU; ++s)
-          if (i >= kGroup * s) Puu[s][i] += z * Su[s][p];
-      }
-#pragma unroll
-      for (int x = 0; x < N; ++x) {  // rows of A
-        const double z = SM(S::rZ + (M + x) * N + p);
-#pragma unroll
-        for (int s = 0; s < SU; ++s) Pxu[s][x] += z * Su[s][p];
-#pragma unroll
-        for (int s = 0; s < SX; ++s)
-          if (x >= kGroup * s) Pxx[s][x] += z * Sx[s][p];
-      }
-    }
-    // Publish the control block: Psi_uu (packed lower), Psi_xu, h.
-#pragma unroll
-    for (int s = 0; s < SU; ++s) {
-      if (uok[s]) {
-#pragma unroll
-        for (int i = kGroup * s; i < M; ++i)
-          if (i >= uj[s]) SM(S::xGuu + rcol[s] + i) = Puu[s][i];
-#pragma unroll
-        for (int x = 0; x < N; ++x) SM(S::xPxu + uj[s] * N + x) = Pxu[s][x];
-        if (SOLVE) SM(S::xH + uj[s]) = hu[s];
-      }
-    }
-    __syncwarp();  // control block visible; staged operands of stage k consumed
-
-    if (k > 0) {
-      issue_node(k - 1);
-      issue_edge(k - 1);
-      cp_async_commit();
-    }
-
-    // Cholesky of G (replicated), Lambda (own rows), K (own columns), t, k.
-    double Lg[tri(M)], dg[M];
-#pragma unroll
-    for (int t = 0; t < tri(M); ++t) Lg[t] = SM(S::xGuu + t);
-    bool g_ok = true;
-#pragma unroll
-    for (int j = 0; j < M; ++j) {
-      double x = Lg[pk(j, j, M)];
-#pragma unroll
-      for (int p = 0; p < j; ++p) x -= Lg[pk(j, p, M)] * Lg[pk(j, p, M)];
-      g_ok = g_ok && (x > 0.0);
-      const double d = rsqrt(x);
-      dg[j] = d;
-#pragma unroll
-      for (int i = j + 1; i < M; ++i) {
-        double t = Lg[pk(i, j, M)];
-#pragma unroll
-        for (int p = 0; p < j; ++p) t -= Lg[pk(i, p, M)] * Lg[pk(j, p, M)];
-        Lg[pk(i, j, M)] = t * d;
-      }
-    }
-    if (!g_ok && status == SIPOC_FACTOR_SUCCESS) status = SIPOC_FACTOR_G_FACTORIZATION_FAILURE;
-
-    double tt[M];
-    if (SOLVE) {
-#pragma unroll
-      for (int a = 0; a < M; ++a) {
-        double t = SM(S::xH + a);
-#pragma unroll
-        for (int c = 0; c < a; ++c) t -= Lg[pk(a, c, M)] * tt[c];
-        tt[a] = t * dg[a];
-      }
-      // k_k = -L_G^-T t
-      double kk[M];
-#pragma unroll
-      for (int a = M - 1; a >= 0; --a) {
-        double t = tt[a];
-#pragma unroll
-        for (int c = a + 1; c < M; ++c) t -= Lg[pk(c, a, M)] * kk[c];
-        kk[a] = t * dg[a];
-      }
-      if (valid && r == 0) {
-#pragma unroll
-        for (int a = 0; a < M; ++a) stcs(kst + static_cast<int64_t>(k * M + a) * ld, -kk[a]);
-      }
-    }
-    {
-      // G^-1 = L_G^-T L_G^-1 (packed lower) for later solves against this factor.
-      double Gi[tri(M)];
-#pragma unroll
-      for (int j = 0; j < M; ++j)
-#pragma unroll
-        for (int i = j; i < M; ++i) {
-          double t = (i == j) ? 1.0 : 0.0;
-#pragma unroll
-          for (int p = j; p < i; ++p) t -= Lg[pk(i, p, M)] * Gi[pk(p, j, M)];
-          Gi[pk(i, j, M)] = t * dg[i];
-        }
-      if (valid && r == 0) {
-#pragma unroll
-        for (int j = 0; j < M; ++j)
-#pragma unroll
-          for (int i = j; i < M; ++i) {
-            double t = 0.0;
-#pragma unroll
-            for (int p = i; p < M; ++p) t += Gi[pk(p, i, M)] * Gi[pk(p, j, M)];
-            stcs(Gst + (static_cast<int64_t>(k) * tri(M) + pk(i, j, M)) * ld, t);
-          }
-      }
-    }
-
-    double lam[SX][M];
-#pragma unroll
-    for (int s = 0; s < SX; ++s) {
-#pragma unroll
-      for (int a = 0; a < M; ++a) {
-        double t = SM(S::xPxu + a * N + xj[s]);
-#pragma unroll
-        for (int c = 0; c < a; ++c) t -= lam[s][c] * Lg[pk(a, c, M)];
-        lam[s][a] = t * dg[a];
-      }
-      if (xok[s]) {
-#pragma unroll
-        for (int a = 0; a < M; ++a) SM(S::xLam + a * N + xj[s]) = lam[s][a];
-      }
-      // K(:, xj) = -L_G^-T Lambda(xj, :)'
-      double kap[M];
-#pragma unroll
-      for (int a = M - 1; a >= 0; --a) {
-        double t = lam[s][a];
-#pragma unroll
-        for (int c = a + 1; c < M; ++c) t -= Lg[pk(c, a, M)] * kap[c];
-        kap[a] = t * dg[a];
-      }
-      if (valid && xok[s]) {
-#pragma unroll
-        for (int a = 0; a < M; ++a)
-          stcs(Kst + (static_cast<int64_t>(k) * N * M + xj[s] * M + a) * ld, -kap[a]);
-      }
-    }
-    __syncwarp();  // Lambda visible
-
-    // V_k = Psi_xx - Lambda Lambda', v_k = w - Lambda t (own columns).
-    double vv[SX];
-#pragma unroll
-    for (int s = 0; s < SX; ++s) {
-#pragma unroll
-      for (int i = kGroup * s; i < N; ++i) {
-        double t = Pxx[s][i];
-#pragma unroll
-        for (int a = 0; a < M; ++a) t -= SM(S::xLam + a * N + i) * lam[s][a];
-        Pxx[s][i] = t;
-      }
-      double t = wx[s];
-      if (SOLVE) {
-#pragma unroll
-        for (int a = 0; a < M; ++a) t -= lam[s][a] * tt[a];
-      }
-      vv[s] = t;
-    }
-    process_node(k, Pxx, vv);
   }
 
   if (status_out != nullptr && valid && r == 0) status_out[b] = status;
@@ -1034,17 +1101,29 @@ struct Plan {
   static int64_t store_elems(int T) { return FastSizes<N, M>::store(T); }
   static int64_t scratch_elems(int T) { return FastSizes<N, M>::scratch(T); }
 
+  template <bool SOLVE, int W>
+  static void launch_subwarp(const FastArgs &a, cudaStream_t s) {
+    auto kern = riccati_backward_subwarp<N, M, SOLVE, W>;
+    static const int pad = getenv("SIPOC_SMEM_PAD") ? atoi(getenv("SIPOC_SMEM_PAD")) : 0;
+    const int bytes = Smem<N, M>::kBytes * W + pad;
+    if (bytes > 48 * 1024)
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    const unsigned grid = static_cast<unsigned>((a.batch + kTile * W - 1) / (kTile * W));
+    ProfScope ps(a.prof, "riccati_backward_subwarp", s);
+    kern<<<grid, 32 * W, bytes, s>>>(a.in, a.status, a.store, a.scratch, a.batch, a.ld,
+                                     a.num_edges);
+  }
+
   template <bool SOLVE>
   static void backward(const FastArgs &a, cudaStream_t s) {
     if constexpr (SUBWARP) {
-      auto kern = riccati_backward_subwarp<N, M, SOLVE>;
-      constexpr int bytes = Smem<N, M>::kBytes;
-      if (bytes > 48 * 1024)
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-      const unsigned grid = static_cast<unsigned>((a.batch + kTile - 1) / kTile);
-      ProfScope ps(a.prof, "riccati_backward_subwarp", s);
-      kern<<<grid, 32, bytes, s>>>(a.in, a.status, a.store, a.scratch, a.batch, a.ld,
-                                   a.num_edges);
+      switch (backward_warps()) {
+        case 1: launch_subwarp<SOLVE, 1>(a, s); break;
+        case 2: launch_subwarp<SOLVE, 2>(a, s); break;
+        case 5: launch_subwarp<SOLVE, 5>(a, s); break;
+        case 4: launch_subwarp<SOLVE, 4>(a, s); break;
+        default: launch_subwarp<SOLVE, 1>(a, s); break;
+      }
     } else {
       const unsigned grid = static_cast<unsigned>((a.batch + 63) / 64);
       ProfScope ps(a.prof, "riccati_backward_thread", s);
