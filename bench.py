@@ -250,15 +250,20 @@ def run_ours(args, wl, name):
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, (world, args.gpus)
 
+    from sip_optimal_control_b200.sharding import shard_range
+
     n, m, T = wl["n"], wl["m"], wl["T"]
+    # weak: every GPU gets the workload's batch; strong: the workload's batch is
+    # cut into contiguous shards (sharding.shard_range).
     total_batch = wl["batch"] * (world if args.scaling == "weak" else 1)
-    batch = wl["batch"] if args.scaling == "weak" else wl["batch"] // world
+    first, last = shard_range(total_batch, rank, world)
+    batch = last - first
     sampler = ClockSampler(local_rank) if rank == 0 else None
 
     lqr = LQR(Dimensions.uniform(T, n, m), Topology.chain(T), batch, device=local_rank,
               force_generic=args.force_generic)
     eng = lqr.engine
-    inp = lqr.generate_benchmark(seed=args.seed, problem_offset=rank * batch)
+    inp = lqr.generate_benchmark(seed=args.seed, problem_offset=first)
     out = lqr.alloc_output()
     status = eng.empty_int()
     stats = torch.zeros(4, dtype=torch.float64, device=dev)

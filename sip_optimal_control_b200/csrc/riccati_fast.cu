@@ -1009,8 +1009,8 @@ affine_backward(LqrIn in, const double *store, double *scratch, int64_t batch, i
 // ===========================================================================
 // Root solve + forward rollout + costates (lqr.cpp:798-870).
 // ===========================================================================
-template <int N, int M>
-__global__ void __launch_bounds__(128)
+template <int N, int M, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
 rollout_forward(LqrIn in, LqrOut out, const double *store, const double *scratch,
                 int64_t batch, int64_t ld, int T) {
   using Z = FastSizes<N, M>;
@@ -1131,11 +1131,22 @@ struct Plan {
           <<<grid, 64, 0, s>>>(a.in, a.status, a.store, a.scratch, a.batch, a.ld, a.num_edges);
     }
   }
-  static void forward(const FastArgs &a, cudaStream_t s) {
-    const unsigned grid = static_cast<unsigned>((a.batch + 127) / 128);
+  template <int THREADS, int MINB>
+  static void launch_forward(const FastArgs &a, cudaStream_t s) {
+    const unsigned grid = static_cast<unsigned>((a.batch + THREADS - 1) / THREADS);
     ProfScope ps(a.prof, "rollout_forward", s);
-    rollout_forward<N, M>
-        <<<grid, 128, 0, s>>>(a.in, a.out, a.store, a.scratch, a.batch, a.ld, a.num_edges);
+    rollout_forward<N, M, THREADS, MINB>
+        <<<grid, THREADS, 0, s>>>(a.in, a.out, a.store, a.scratch, a.batch, a.ld, a.num_edges);
+  }
+  static void forward(const FastArgs &a, cudaStream_t s) {
+    static const int v = getenv("SIPOC_FWD_VARIANT") ? atoi(getenv("SIPOC_FWD_VARIANT")) : 0;
+    switch (v) {
+      case 1: launch_forward<128, 4>(a, s); break;
+      case 2: launch_forward<64, 10>(a, s); break;
+      case 3: launch_forward<64, 16>(a, s); break;
+      case 4: launch_forward<32, 24>(a, s); break;
+      default: launch_forward<128, 1>(a, s); break;
+    }
   }
   static int factor(const FastArgs &a, cudaStream_t s) {
     backward<false>(a, s);
