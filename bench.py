@@ -39,6 +39,10 @@ WORKLOADS = {
     "quadrotor": dict(n=12, m=4, T=50, batch=65536),
     "humanoid": dict(n=64, m=24, T=32, batch=4096),
 }
+# Config 4: Newton-KKT with inequality constraints and variable per-stage dims — the
+# pattern of tests/variable_dimensions_test.cpp:266-271 tiled along the horizon.
+KKT_WORKLOAD = dict(T=48, batch=8192, state=(2, 1, 3), control=(1, 2), node_c=(1, 0, 2),
+                    node_g=(0, 2, 1), edge_c=(1, 2), edge_g=(2, 1))
 DEFAULT_WORKLOAD = "quadrotor"  # the config north_star quotes its target on
 METRIC = "batched LQR factor+solve solves/sec (FP64)"
 UNIT = "solves/s"
@@ -418,13 +422,148 @@ def run_ours(args, wl, name):
     return 0
 
 
+def kkt_host_problem(dims, batch, seed, r2_max=1e9):
+    """newton_kkt_benchmark.cpp:171-240 distribution on a chain with the given dims."""
+    rng = np.random.default_rng(seed)
+    sd, cd = dims.state_dims, dims.control_dims
+    N, E = len(sd), len(cd)
+
+    def cm(x):
+        return np.ascontiguousarray(np.swapaxes(x, -1, -2)).reshape(batch, -1)
+
+    def spd(d, shift):
+        Z = rng.standard_normal((batch, d, d))
+        return np.einsum("bkj,bki->bij", Z, Z) + shift * np.eye(d)
+
+    m = {k: [] for k in ("node_hxx", "node_jc", "node_jg", "edge_hxx", "edge_hxu", "edge_huu",
+                         "edge_A", "edge_B", "edge_jcx", "edge_jcu", "edge_jgx", "edge_jgu")}
+    for i in range(N):
+        n = int(sd[i])
+        m["node_jc"].append(cm(0.1 * rng.standard_normal((batch, int(dims.node_c_dims[i]), n))))
+        m["node_jg"].append(cm(0.1 * rng.standard_normal((batch, int(dims.node_g_dims[i]), n))))
+        m["node_hxx"].append(cm(spd(n, 1e-3)))
+    for e in range(E):
+        npar, nch, mm = int(sd[e]), int(sd[e + 1]), int(cd[e])
+        c, g = int(dims.edge_c_dims[e]), int(dims.edge_g_dims[e])
+        A = 0.05 * rng.standard_normal((batch, nch, npar))
+        if nch == npar:
+            A = A + np.eye(nch)
+        m["edge_A"].append(cm(A))
+        m["edge_B"].append(cm(0.1 * rng.standard_normal((batch, nch, mm))))
+        m["edge_jcx"].append(cm(0.1 * rng.standard_normal((batch, c, npar))))
+        m["edge_jcu"].append(cm(0.1 * rng.standard_normal((batch, c, mm))))
+        m["edge_jgx"].append(cm(0.1 * rng.standard_normal((batch, g, npar))))
+        m["edge_jgu"].append(cm(0.1 * rng.standard_normal((batch, g, mm))))
+        m["edge_hxx"].append(np.zeros((batch, npar * npar)))
+        m["edge_hxu"].append(cm(0.01 * rng.standard_normal((batch, npar, mm))))
+        m["edge_huu"].append(cm(spd(mm, 1.0)))
+    model = {k: np.concatenate(v, axis=1) for k, v in m.items()}
+    x_dim, y_dim, z_dim = dims.get_x_dim(E), dims.get_y_dim(E), dims.get_z_dim(E)
+
+    def logu(shape, lo, hi):
+        return np.exp(np.log(lo) + (np.log(hi) - np.log(lo)) * rng.random(shape))
+
+    return (model, logu((batch, z_dim), 1e-2, 1e3), np.full((batch, x_dim), 1e-8),
+            logu((batch, y_dim), 1e-3, r2_max), logu((batch, z_dim), 1e-3, 1e1),
+            rng.standard_normal((batch, x_dim + y_dim + z_dim)))
+
+
+def run_kkt(args):
+    """Config 4: KKT factor + KKT solve + KKT residual per step, variable per-stage dims."""
+    import torch
+
+    from sip_optimal_control_b200 import CallbackProvider, Dimensions, Topology
+    from sip_optimal_control_b200._capi import lib
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    wl = dict(KKT_WORKLOAD)
+    if args.batch:
+        wl["batch"] = args.batch
+    T, batch = wl["T"], wl["batch"]
+    tile = lambda pat, count: np.array([pat[i % len(pat)] for i in range(count)], np.int32)
+    dims = Dimensions(0, tile(wl["state"], T + 1), tile(wl["control"], T),
+                      tile(wl["node_c"], T + 1), tile(wl["node_g"], T + 1),
+                      tile(wl["edge_c"], T), tile(wl["edge_g"], T))
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    sampler = ClockSampler(0)
+    cp = CallbackProvider(dims, Topology.chain(T), batch, device=0)
+    eng = cp.engine
+    model_h, w_h, r1_h, r2_h, r3_h, b_h = kkt_host_problem(dims, batch, args.seed)
+    model = cp.pack_model(model_h)
+    w, r1, r2, r3, b = (eng.pack(a) for a in (w_h, r1_h, r2_h, r3_h, b_h))
+    sol = eng.zeros(b_h.shape[1])
+    ok = eng.empty_int()
+    stream = torch.cuda.current_stream(dev)
+
+    def step():
+        cp.factor(model, w, r1, r2, r3, ok=ok, stream=stream)
+        cp.solve(model, b, sol, stream=stream)
+        return cp.residual(model, w, r1, r2, r3, sol, b, ok=ok, stream=stream)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize(dev)
+    launches0 = eng.launch_count
+    lib.sipoc_profile_enable(eng._handle, 1)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        norms, stats = step()
+    ev1.record(stream)
+    torch.cuda.synchronize(dev)
+    t1 = time.time()
+    ms_per_step = ev0.elapsed_time(ev1) / args.steps
+    gpu_launches = eng.launch_count - launches0
+    kernels = {}
+    for i in range(lib.sipoc_profile_collect(eng._handle)):
+        nm, ms, cnt = ctypes.c_char_p(), ctypes.c_double(), ctypes.c_int64()
+        lib.sipoc_profile_get(eng._handle, i, ctypes.byref(nm), ctypes.byref(ms),
+                              ctypes.byref(cnt))
+        kernels[nm.value.decode()] = {"ms_per_launch": ms.value / max(cnt.value, 1),
+                                      "ms_per_step": ms.value / args.steps}
+    lib.sipoc_profile_enable(eng._handle, 0)
+    sampler.stop()
+    st = stats.cpu().numpy()
+    # relative residual: ||K sol - b|| / ||b|| (r2 up to 1e9 scales the rows)
+    rel = (norms[:batch].cpu().numpy() / np.linalg.norm(b_h, axis=1)).max()
+    in_elems = sum(v.shape[1] for v in model_h.values()) + w_h.shape[1] + r1_h.shape[1] \
+        + r2_h.shape[1] + r3_h.shape[1] + b_h.shape[1]
+    alg_bytes = 8 * (in_elems + b_h.shape[1])
+    peak, peak_kind = measured_peaks()
+    hot_ms = sum(v["ms_per_step"] for v in kernels.values())
+    achieved = alg_bytes * batch / (hot_ms * 1e-3) / 1e9
+    dominant = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
+    line = {
+        "metric": "batched Newton-KKT factor+solve+residual solves/sec (FP64)",
+        "value": batch / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "newton_kkt", **{k: (list(v) if isinstance(v, tuple) else v)
+                                                for k, v in wl.items()},
+                   "kkt_dim": int(b_h.shape[1]), "kernel_variant": eng.kernel_variant,
+                   "generator": "newton_kkt_benchmark.cpp:171-240 distribution (r2 up to 1e9)"},
+        "clocks": sampler.summary(t0, t1), "e2e": None, "gpu_launches": int(gpu_launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "peak_source": peak_kind, "traffic": None,
+                     "algorithmic_bytes_per_solve": alg_bytes, "dominant_kernel": dominant,
+                     "kernels": kernels},
+        "check": {"failed_problems": float(st[2]), "problems": float(st[3]),
+                  "max_relative_kkt_residual": float(rel)},
+    }
+    print(json.dumps(line))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS) + ["newton_kkt"])
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
     ap.add_argument("--horizon", type=int, default=0, help="override the horizon T")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
@@ -436,6 +575,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.workload == "newton_kkt":
+        return run_kkt(args)
     wl = dict(WORKLOADS[args.workload])
     if args.batch:
         wl["batch"] = args.batch
