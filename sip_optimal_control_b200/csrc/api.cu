@@ -515,6 +515,9 @@ sipoc_error sipoc_create(const sipoc_structure *s, sipoc_engine **out) {
   const HostStructure &h = e->hs;
   if (!(e->flags & SIPOC_FLAG_FORCE_GENERIC) && h.is_chain && h.is_uniform && h.E >= 1)
     e->fast = select_fast_plan(h.n[0], h.m[0]);
+  if (e->fast == nullptr && !(e->flags & SIPOC_FLAG_FORCE_GENERIC) && h.is_chain &&
+      h.is_uniform && h.E >= 1)
+    e->fast = select_cta_plan(h.n[0], h.m[0]);
   e->variant = e->fast != nullptr ? e->fast->name : "generic_thread_per_problem";
   *out = e;
   return SIPOC_OK;

@@ -1,0 +1,729 @@
+// CTA-per-problem Riccati kernels for large state / control dimensions
+// (humanoid scale, n = 64, m = 24), sm_100a, FP64.
+//
+// One CTA of 8 warps owns one problem; every matrix of the stage lives in shared
+// memory (column-major, leading dimension == 4 mod 16 so that all FP64 tensor
+// core fragment loads are bank-conflict free) and every dense contraction is a
+// tiled product on the FP64 tensor cores, `mma.sync.m8n8k4.f64` (DMMA):
+// operands are delivered to the MMA as one double per lane, so a 256-FMA
+// instruction costs two 8-byte shared-memory loads per lane instead of the
+// 2 loads per 4 FMA a register-tiled DFMA product would need (shared memory
+// delivers 128 B / clk / SM, DFMA consumes 64 FMA / clk / SM).
+//
+// Stage algebra (same as riccati_fast.cu; Z = [A_k | B_k | 0], u padded to a
+// multiple of 16 with identity in R so the padded G stays positive definite):
+//   S    = W' Z                         cta_gemm
+//   Psi  = [Q M; M' R] + Z' S           cta_gemm (lower tiles)
+//   G^-1 = Psi_uu^-1                    blocked Cholesky + triangular inverse + L^-T L^-1
+//   K    = -G^-1 Psi_ux                 cta_gemm                    (lqr.cpp:703-713)
+//   V    = Psi_xx + Psi_ux' K           cta_gemm (lower tiles)      (lqr.cpp:715-719)
+//   F    = I + D^1/2 V D^1/2 ; W = D^-1/2 (I - F^-1) D^-1/2          (lqr.cpp:475-529)
+// Affine part: g = v' - W'(delta' o v' - c'); [w; h] = [q; r] + Z' g;
+//   k = -G^-1 h ; v = w + Psi_ux' k.                                (lqr.cpp:778-794)
+//
+// Global memory is the engine's batch-interleaved layout X[flat * ld + b]; one
+// problem's elements are therefore 8-byte accesses ld * 8 bytes apart.  They are
+// staged with 8-byte cp.async; neighbouring CTAs (problems b .. b+3) share every
+// 32-byte sector through L2, and the path is FP64-bound (25 flop / byte), so the
+// sector inefficiency costs L2 bandwidth only.
+#include <cstdio>
+#include <cstdlib>
+
+#include "riccati_fast.cuh"
+
+namespace sipoc {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+
+__host__ __device__ constexpr int tri(int n) { return n * (n + 1) / 2; }
+__host__ __device__ constexpr int pk(int i, int j, int n) {
+  return j * n - j * (j - 1) / 2 + (i - j);
+}
+__host__ __device__ constexpr int round16(int x) { return (x + 15) / 16 * 16; }
+// Smallest leading dimension >= rows with ld % 16 == 4.
+__host__ __device__ constexpr int pad_ld(int rows) {
+  int ld = rows;
+  while (ld % 16 != 4) ++ld;
+  return ld;
+}
+
+template <int N, int M>
+struct CtaSizes {  // per-problem element counts of the store / spill (same as FastSizes)
+  static __host__ __device__ constexpr int64_t oW(int) { return 0; }
+  static __host__ __device__ constexpr int64_t oK(int T) { return int64_t(T + 1) * tri(N); }
+  static __host__ __device__ constexpr int64_t oG(int T) { return oK(T) + int64_t(T) * N * M; }
+  static __host__ __device__ constexpr int64_t store(int T) { return oG(T) + int64_t(T) * tri(M); }
+  static __host__ __device__ constexpr int64_t ov(int) { return 0; }
+  static __host__ __device__ constexpr int64_t ok(int T) { return int64_t(T + 1) * N; }
+  static __host__ __device__ constexpr int64_t scratch(int T) { return ok(T) + int64_t(T) * M; }
+};
+
+__device__ __forceinline__ void cp_async8(double *smem, const double *gmem) {
+  const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() {
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+}
+
+// D(8x8) += A(8x4) B(4x8).  Lane l (g = l / 4, t = l % 4) holds A(g, t), B(t, g) and
+// C(g, 2t), C(g, 2t + 1).
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};\n"
+               : "+d"(c[0]), "+d"(c[1])
+               : "d"(a), "d"(b));
+}
+
+// Element (i, k) of op(A) for a column-major array with leading dimension ld.
+template <bool TRANS>
+__device__ __forceinline__ double op_at(const double *A, int ld, int i, int k) {
+  return TRANS ? A[i * ld + k] : A[k * ld + i];
+}
+
+// C (Mo x No) = (ACC ? C : 0) + sign * op(A) (Mo x K) * op(B) (K x No), all in shared
+// memory, column-major.  Mo, No multiples of 8, K a multiple of 4.  Work unit: a
+// 16 x 16 block (2 x 2 MMA tiles) per warp, blocks dealt round-robin to the warps;
+// LOWER computes only blocks on or below the block diagonal (whole blocks).
+template <bool TA, bool TB, bool ACC, bool LOWER>
+__device__ void cta_gemm(double *C, int ldc, const double *A, int lda, const double *B, int ldb,
+                         int Mo, int No, int K, double sign) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int tm = (Mo + 15) >> 4, tn = (No + 15) >> 4;
+  int slot = 0;
+  for (int ti = 0; ti < tm; ++ti) {
+    for (int tj = 0; tj < (LOWER ? ti + 1 : tn); ++tj, ++slot) {
+      if (slot % kWarps != warp) continue;
+      const int i0 = ti << 4, j0 = tj << 4;
+      const bool r1 = i0 + 8 < Mo, c1 = j0 + 8 < No;
+      double acc[2][2][2];
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          const bool live = (a == 0 || r1) && (b == 0 || c1);
+          const double *src = C + (j0 + 8 * b + 2 * t) * ldc + i0 + 8 * a + g;
+          acc[a][b][0] = (ACC && live) ? src[0] : 0.0;
+          acc[a][b][1] = (ACC && live) ? src[ldc] : 0.0;
+        }
+#pragma unroll 2
+      for (int k0 = 0; k0 < K; k0 += 4) {
+        const double a0 = sign * op_at<TA>(A, lda, i0 + g, k0 + t);
+        const double a1 = r1 ? sign * op_at<TA>(A, lda, i0 + 8 + g, k0 + t) : 0.0;
+        // op(B)(k, j): B column-major -> B[j * ldb + k]; transposed -> B[k * ldb + j].
+        const double b0 = TB ? B[(k0 + t) * ldb + j0 + g] : B[(j0 + g) * ldb + k0 + t];
+        const double b1 =
+            c1 ? (TB ? B[(k0 + t) * ldb + j0 + 8 + g] : B[(j0 + 8 + g) * ldb + k0 + t]) : 0.0;
+        dmma(acc[0][0], a0, b0);
+        dmma(acc[0][1], a0, b1);
+        dmma(acc[1][0], a1, b0);
+        dmma(acc[1][1], a1, b1);
+      }
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          if ((a == 0 || r1) && (b == 0 || c1)) {
+            double *dst = C + (j0 + 8 * b + 2 * t) * ldc + i0 + 8 * a + g;
+            dst[0] = acc[a][b][0];
+            dst[ldc] = acc[a][b][1];
+          }
+        }
+    }
+  }
+}
+
+// y[i] = base[i] + sign * sum_j op(A)(i, j) x[j],  i < rows, j < cols; four threads per
+// row (quarters of the columns) reduced with shuffles.  rows <= 64 per pass.
+template <bool TRANS>
+__device__ void cta_matvec(double *y, const double *base, const double *A, int lda,
+                           const double *x, int rows, int cols, double sign) {
+  const int tid = threadIdx.x, part = tid & 3;
+  for (int r0 = 0; r0 < rows; r0 += kThreads / 4) {
+    const int i = r0 + (tid >> 2);
+    double acc = 0.0;
+    if (i < rows) {
+      for (int j = part; j < cols; j += 4) acc += op_at<TRANS>(A, lda, i, j) * x[j];
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (i < rows && part == 0) y[i] = (base != nullptr ? base[i] : 0.0) + sign * acc;
+  }
+}
+
+// Cholesky factor L (packed lower) of the 8 x 8 block at `blk` and X = L^-1, in
+// registers.  Returns false when a pivot is <= 0.
+__device__ __forceinline__ bool chol8_and_inverse(const double *blk, int ld, double (&L)[36],
+                                                  double (&X)[36]) {
+  bool ok = true;
+  double d[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i >= j) L[pk(i, j, 8)] = blk[j * ld + i];
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    double x = L[pk(j, j, 8)];
+#pragma unroll
+    for (int p = 0; p < 8; ++p)
+      if (p < j) x -= L[pk(j, p, 8)] * L[pk(j, p, 8)];
+    ok = ok && (x > 0.0);
+    const double r = rsqrt(x);
+    d[j] = r;
+    L[pk(j, j, 8)] = x * r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i > j) {
+        double s = L[pk(i, j, 8)];
+#pragma unroll
+        for (int p = 0; p < 8; ++p)
+          if (p < j) s -= L[pk(i, p, 8)] * L[pk(j, p, 8)];
+        L[pk(i, j, 8)] = s * r;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i >= j) {
+        double s = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+        for (int p = 0; p < 8; ++p)
+          if (p >= j && p < i) s -= L[pk(i, p, 8)] * X[pk(p, j, 8)];
+        X[pk(i, j, 8)] = s * d[i];
+      }
+    }
+  }
+  return ok;
+}
+
+// In-place inverse of a symmetric positive definite n x n matrix given by its
+// LOWER triangle (n a multiple of 8, n <= 64): blocked right-looking Cholesky
+// (8-wide panels, DMMA trailing updates), block-column triangular inverse (one warp
+// per block column), then L^-T L^-1.  On return A holds the full symmetric inverse.
+// `scratch` is an n x ld array, `dinv` holds n / 8 blocks of 8 x 8.  Returns false
+// when a pivot is <= 0 (Eigen LLT's failure criterion).  All threads must call it.
+__device__ bool cta_spd_inverse(double *A, int ld, int n, double *scratch, double *dinv) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  bool ok = true;
+  const int nb = n >> 3;
+  for (int kb = 0; kb < nb; ++kb) {
+    const int c0 = kb << 3, c1 = c0 + 8, rem = n - c1;
+    // Every thread factors the 8 x 8 diagonal block redundantly in registers and
+    // inverts it; no exchange is needed before the panel update.
+    double L[36], X[36];
+    ok = chol8_and_inverse(A + c0 * ld + c0, ld, L, X) && ok;
+    // Panel: row r of L21 = A21(r, :) L11^-T, one thread per row.
+    if (tid < rem) {
+      double *row = A + c0 * ld + c1 + tid;
+      double a[8];
+#pragma unroll
+      for (int p = 0; p < 8; ++p) a[p] = row[p * ld];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        double s = 0.0;
+#pragma unroll
+        for (int p = 0; p <= j; ++p) s += a[p] * X[pk(j, p, 8)];
+        row[j * ld] = s;
+      }
+    }
+    if (tid == kThreads - 1) {  // publish L11 and L11^-1 (an otherwise idle thread)
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (i >= j) {
+            A[(c0 + j) * ld + c0 + i] = L[pk(i, j, 8)];
+            dinv[kb * 64 + j * 8 + i] = X[pk(i, j, 8)];
+          } else {
+            A[(c0 + j) * ld + c0 + i] = 0.0;
+            dinv[kb * 64 + j * 8 + i] = 0.0;
+          }
+        }
+    }
+    __syncthreads();
+    if (rem > 0) {
+      // A22 -= L21 L21'
+      cta_gemm<false, true, true, true>(A + c1 * ld + c1, ld, A + c0 * ld + c1, ld,
+                                        A + c0 * ld + c1, ld, rem, rem, 8, -1.0);
+      __syncthreads();
+    }
+  }
+
+  // Triangular inverse, block column kb by warp kb:  X_kk = inv(L_kk),
+  // X_ik = -inv(L_ii) sum_{p=kb}^{i-1} L_ip X_pk.
+  for (int kb = warp; kb < nb; kb += kWarps) {
+    for (int ib = 0; ib < nb; ++ib) {
+      double *dst = scratch + (kb * 8) * ld + ib * 8;  // block (ib, kb)
+      if (ib < kb) {
+        dst[(2 * t) * ld + g] = 0.0;
+        dst[(2 * t + 1) * ld + g] = 0.0;
+      } else if (ib == kb) {
+        dst[(2 * t) * ld + g] = dinv[kb * 64 + (2 * t) * 8 + g];
+        dst[(2 * t + 1) * ld + g] = dinv[kb * 64 + (2 * t + 1) * 8 + g];
+      } else {
+        double acc[2] = {0.0, 0.0};
+        for (int pb = kb; pb < ib; ++pb) {
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            const double a = A[(pb * 8 + 4 * s + t) * ld + ib * 8 + g];           // L_ip(g, 4s+t)
+            const double b = scratch[(kb * 8 + g) * ld + pb * 8 + 4 * s + t];     // X_pk(4s+t, g)
+            dmma(acc, a, b);
+          }
+        }
+        dst[(2 * t) * ld + g] = acc[0];  // park T in the destination block
+        dst[(2 * t + 1) * ld + g] = acc[1];
+        __syncwarp();
+        double res[2] = {0.0, 0.0};
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          const double a = -dinv[ib * 64 + (4 * s + t) * 8 + g];  // -inv(L_ii)(g, 4s+t)
+          const double b = dst[g * ld + 4 * s + t];               // T(4s+t, g)
+          dmma(res, a, b);
+        }
+        __syncwarp();
+        dst[(2 * t) * ld + g] = res[0];
+        dst[(2 * t + 1) * ld + g] = res[1];
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  // A = L^-T L^-1 (lower blocks, whole diagonal blocks), then mirror to the upper part.
+  cta_gemm<true, false, false, true>(A, ld, scratch, ld, scratch, ld, n, n, n, 1.0);
+  __syncthreads();
+  for (int e = tid; e < n * n; e += kThreads) {
+    const int i = e % n, j = e / n;
+    if (i > j) A[i * ld + j] = A[j * ld + i];
+  }
+  __syncthreads();
+  return ok;
+}
+
+// Shared-memory map (doubles).
+template <int N, int M>
+struct CtaSmem {
+  static constexpr int MP = round16(M);
+  static constexpr int NZ = N + MP;
+  static constexpr int LDN = pad_ld(N);    // matrices with N rows
+  static constexpr int LDM = pad_ld(MP);   // matrices with MP rows
+  static constexpr int oW = 0;                        // W' -> Psi_xx -> F -> W   (N x N)
+  static constexpr int oZ = oW + N * LDN;             // Z = [A | B | 0]          (N x NZ)
+  static constexpr int oS = oZ + NZ * LDN;            // S = W' Z; later scratch  (N x NZ)
+  static constexpr int oPux = oS + NZ * LDN;          // Psi_ux                   (MP x N)
+  static constexpr int oPuu = oPux + N * LDM;         // Psi_uu -> G^-1           (MP x MP)
+  static constexpr int oK = oPuu + MP * LDM;          // K                        (MP x N)
+  static constexpr int oGs = oK + N * LDM;            // scratch of the G inverse (MP x MP)
+  static constexpr int oDinv = oGs + MP * LDM;        // 8 x 8 diagonal inverses
+  static constexpr int oVec = oDinv + (N / 8) * 64;
+  static constexpr int vq = oVec, vr = vq + N, vc = vr + MP, vd = vc + N, vv = vd + N,
+                       vdl = vv + N, vsd = vdl + N, vsdi = vsd + N, vf = vsdi + N, vg = vf + N,
+                       vhw = vg + N, vkk = vhw + NZ, vEnd = vkk + MP;
+  static constexpr int kDoubles = vEnd;
+  static constexpr int kBytes = kDoubles * int(sizeof(double));
+};
+
+template <int N, int M, bool SOLVE>
+__global__ void __launch_bounds__(kThreads, 1)
+riccati_backward_cta(LqrIn in, int *status_out, double *store, double *scratch, int64_t batch,
+                     int64_t ld, int T) {
+  using S = CtaSmem<N, M>;
+  using Zs = CtaSizes<N, M>;
+  constexpr int MP = S::MP, NZ = S::NZ, LDN = S::LDN, LDM = S::LDM;
+  extern __shared__ __align__(16) double sm[];
+  const int tid = threadIdx.x;
+  const int64_t b = blockIdx.x;
+  const size_t L_ = static_cast<size_t>(ld);
+  double *Wp = sm + S::oW, *Zb = sm + S::oZ, *Sb = sm + S::oS, *Pux = sm + S::oPux,
+         *Puu = sm + S::oPuu, *Kb = sm + S::oK, *Gs = sm + S::oGs, *Dinv = sm + S::oDinv;
+  double *q_s = sm + S::vq, *r_s = sm + S::vr, *c_s = sm + S::vc, *d_s = sm + S::vd,
+         *v_s = sm + S::vv, *dl_s = sm + S::vdl, *sd_s = sm + S::vsd, *sdi_s = sm + S::vsdi,
+         *f_s = sm + S::vf, *g_s = sm + S::vg, *hw_s = sm + S::vhw, *kk_s = sm + S::vkk;
+
+  double *Wst = store + Zs::oW(T) * ld + b;
+  double *Kst = store + Zs::oK(T) * ld + b;
+  double *Gst = store + Zs::oG(T) * ld + b;
+  double *vst = SOLVE ? scratch + Zs::ov(T) * ld + b : nullptr;
+  double *kst = SOLVE ? scratch + Zs::ok(T) * ld + b : nullptr;
+
+  auto stage_edge_z = [&](int k) {  // A_k, B_k -> Z
+    const double *gA = in.A + static_cast<size_t>(k) * N * N * L_ + b;
+    for (int e = tid; e < N * N; e += kThreads) cp_async8(Zb + (e / N) * LDN + e % N, gA + e * L_);
+    const double *gB = in.B + static_cast<size_t>(k) * N * M * L_ + b;
+    for (int e = tid; e < N * M; e += kThreads)
+      cp_async8(Zb + (N + e / N) * LDN + e % N, gB + e * L_);
+  };
+  auto stage_edge_rest = [&](int k) {  // M_k' -> Psi_ux, R_k (lower) -> Psi_uu, vectors
+    const double *gM = in.M + static_cast<size_t>(k) * N * M * L_ + b;
+    for (int e = tid; e < N * M; e += kThreads)
+      cp_async8(Pux + (e % N) * LDM + e / N, gM + e * L_);  // M(x, u) -> Psi_ux(u, x)
+    const double *gR = in.R + static_cast<size_t>(k) * M * M * L_ + b;
+    for (int e = tid; e < M * M; e += kThreads)
+      if (e % M >= e / M) cp_async8(Puu + (e / M) * LDM + e % M, gR + e * L_);
+    if (tid < N) cp_async8(d_s + tid, in.delta + (static_cast<size_t>(k) * N + tid) * L_ + b);
+    if (SOLVE) {
+      if (tid < N) {
+        cp_async8(q_s + tid, in.q + (static_cast<size_t>(k) * N + tid) * L_ + b);
+        cp_async8(c_s + tid, in.c + (static_cast<size_t>(k + 1) * N + tid) * L_ + b);
+      }
+      if (tid < M) cp_async8(r_s + tid, in.r + (static_cast<size_t>(k) * M + tid) * L_ + b);
+    }
+  };
+  auto stage_q_lower = [&](int k) {  // Q_k (lower) -> Psi_xx buffer
+    const double *gQ = in.Q + static_cast<size_t>(k) * N * N * L_ + b;
+    for (int e = tid; e < N * N; e += kThreads)
+      if (e % N >= e / N) cp_async8(Wp + (e / N) * LDN + e % N, gQ + e * L_);
+  };
+
+  int status = SIPOC_FACTOR_SUCCESS;
+
+  // Node processing on the N x N matrix in Wp (lower triangle = V_k), v_k in hw_s[0..N):
+  // delta check, F, inverse, W (full, in Wp), stores W_k and v_k.
+  auto process_node = [&](int k) {
+    bool d_ok = true;
+    for (int i = tid; i < N; i += kThreads) {
+      const double d = d_s[i];
+      d_ok = d_ok && (d > 0.0);
+      const double sd = sqrt(d);
+      dl_s[i] = d;
+      sd_s[i] = sd;
+      sdi_s[i] = 1.0 / sd;
+      if (SOLVE) {
+        const double v = hw_s[i];
+        v_s[i] = v;
+        __stcs(vst + (static_cast<size_t>(k) * N + i) * L_, v);
+      }
+    }
+    const bool any_bad = __syncthreads_or(!d_ok);
+    if (any_bad && status == SIPOC_FACTOR_SUCCESS) status = SIPOC_FACTOR_INVALID_DELTA;
+    for (int e = tid; e < N * N; e += kThreads) {
+      const int i = e % N, j = e / N;
+      if (i >= j) Wp[j * LDN + i] = sd_s[i] * Wp[j * LDN + i] * sd_s[j] + (i == j ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    const bool f_ok = cta_spd_inverse(Wp, LDN, N, Sb, Dinv);
+    if (!__syncthreads_and(f_ok) && status == SIPOC_FACTOR_SUCCESS)
+      status = SIPOC_FACTOR_F_FACTORIZATION_FAILURE;
+    for (int e = tid; e < N * N; e += kThreads) {
+      const int i = e % N, j = e / N;
+      if (i >= j) {
+        const double w = sdi_s[i] * ((i == j ? 1.0 : 0.0) - Wp[j * LDN + i]) * sdi_s[j];
+        Wp[j * LDN + i] = w;
+        Wp[i * LDN + j] = w;
+        __stcs(Wst + (static_cast<size_t>(k) * tri(N) + pk(i, j, N)) * L_, w);
+      }
+    }
+    __syncthreads();
+  };
+
+  // ---- terminal node ----------------------------------------------------------
+  stage_q_lower(T);
+  if (tid < N) {
+    cp_async8(d_s + tid, in.delta + (static_cast<size_t>(T) * N + tid) * L_ + b);
+    if (SOLVE) cp_async8(hw_s + tid, in.q + (static_cast<size_t>(T) * N + tid) * L_ + b);
+  }
+  cp_async_commit();
+  cp_async_wait_all();
+  __syncthreads();
+  process_node(T);
+
+  for (int k = T - 1; k >= 0; --k) {
+    // Zero the padding (columns N+M.. of Z, rows / columns M.. of the u blocks) and
+    // fetch the stage.  Psi_uu gets identity on its padded diagonal.
+    for (int e = tid; e < (MP - M) * N; e += kThreads) Zb[(N + M + e / N) * LDN + e % N] = 0.0;
+    for (int e = tid; e < N * LDM; e += kThreads) Pux[e] = 0.0;
+    for (int e = tid; e < MP * LDM; e += kThreads) {
+      const int i = e % LDM, j = e / LDM;
+      Puu[e] = (i == j && i >= M && i < MP) ? 1.0 : 0.0;
+    }
+    if (tid < MP) r_s[tid] = 0.0;
+    __syncthreads();
+    stage_edge_z(k);
+    stage_edge_rest(k);
+    cp_async_commit();
+    cp_async_wait_all();
+    __syncthreads();
+
+    if (SOLVE) {
+      // g = v' - W'(delta' o v' - c')
+      for (int i = tid; i < N; i += kThreads) f_s[i] = dl_s[i] * v_s[i] - c_s[i];
+      __syncthreads();
+      cta_matvec<false>(g_s, v_s, Wp, LDN, f_s, N, N, -1.0);
+      __syncthreads();
+      // [w; h] = [q; r] + Z' g
+      cta_matvec<true>(hw_s, q_s, Zb, LDN, g_s, N, N, 1.0);
+      cta_matvec<true>(hw_s + N, r_s, Zb + N * LDN, LDN, g_s, MP, N, 1.0);
+    }
+    // S = W' Z
+    cta_gemm<false, false, false, false>(Sb, LDN, Wp, LDN, Zb, LDN, N, NZ, N, 1.0);
+    __syncthreads();
+    // Psi_xx base: Q_k lower into the (now free) W' buffer; overlaps the u-block products.
+    stage_q_lower(k);
+    cp_async_commit();
+    // Psi_ux += B' S_x ,  Psi_uu += B' S_u   (rows = u, K = N)
+    cta_gemm<true, false, true, false>(Pux, LDM, Zb + N * LDN, LDN, Sb, LDN, MP, N, N, 1.0);
+    cta_gemm<true, false, true, true>(Puu, LDM, Zb + N * LDN, LDN, Sb + N * LDN, LDN, MP, MP, N,
+                                      1.0);
+    cp_async_wait_all();
+    __syncthreads();
+    // Psi_xx += A' S_x (lower blocks)
+    cta_gemm<true, false, true, true>(Wp, LDN, Zb, LDN, Sb, LDN, N, N, N, 1.0);
+    __syncthreads();
+
+    // G^-1 (full, in Puu)
+    const bool g_ok = cta_spd_inverse(Puu, LDM, MP, Gs, Dinv);
+    if (!__syncthreads_and(g_ok) && status == SIPOC_FACTOR_SUCCESS)
+      status = SIPOC_FACTOR_G_FACTORIZATION_FAILURE;
+    // K = -G^-1 Psi_ux
+    cta_gemm<false, false, false, false>(Kb, LDM, Puu, LDM, Pux, LDM, MP, N, MP, -1.0);
+    if (SOLVE) cta_matvec<false>(kk_s, nullptr, Puu, LDM, hw_s + N, MP, MP, -1.0);  // k = -G^-1 h
+    __syncthreads();
+    // V = Psi_xx + Psi_ux' K (lower blocks);  v = w + Psi_ux' k
+    cta_gemm<true, false, true, true>(Wp, LDN, Pux, LDM, Kb, LDM, N, N, MP, 1.0);
+    if (SOLVE) cta_matvec<true>(hw_s, hw_s, Pux, LDM, kk_s, N, MP, 1.0);
+    // stores of the edge: K (M x N), G^-1 (packed lower), k
+    for (int e = tid; e < N * M; e += kThreads)
+      __stcs(Kst + (static_cast<size_t>(k) * N * M + e) * L_, Kb[(e / M) * LDM + e % M]);
+    for (int e = tid; e < M * M; e += kThreads) {
+      const int i = e % M, j = e / M;
+      if (i >= j)
+        __stcs(Gst + (static_cast<size_t>(k) * tri(M) + pk(i, j, M)) * L_, Puu[j * LDM + i]);
+    }
+    if (SOLVE && tid < M) __stcs(kst + (static_cast<size_t>(k) * M + tid) * L_, kk_s[tid]);
+    __syncthreads();
+    process_node(k);
+  }
+  if (status_out != nullptr && tid == 0) status_out[b] = status;
+}
+
+// Backward affine sweep against a kept factorization, one CTA per problem.
+template <int N, int M>
+__global__ void __launch_bounds__(kThreads)
+affine_backward_cta(LqrIn in, const double *store, double *scratch, int64_t batch, int64_t ld,
+                    int T) {
+  using Zs = CtaSizes<N, M>;
+  __shared__ double v[N], f[N], g[N], h[M], kk[M];
+  const int tid = threadIdx.x;
+  const int64_t b = blockIdx.x;
+  const size_t L_ = static_cast<size_t>(ld);
+#define G(ptr, e) __ldcs((ptr) + static_cast<size_t>(e) * L_ + b)
+  const double *Wst = store + Zs::oW(T) * ld;
+  const double *Kst = store + Zs::oK(T) * ld;
+  const double *Gst = store + Zs::oG(T) * ld;
+  double *vst = scratch + Zs::ov(T) * ld + b;
+  double *kst = scratch + Zs::ok(T) * ld + b;
+  for (int i = tid; i < N; i += kThreads) {
+    v[i] = G(in.q, T * N + i);
+    __stcs(vst + static_cast<size_t>(T * N + i) * L_, v[i]);
+  }
+  __syncthreads();
+  const int row = tid >> 2, part = tid & 3;  // 4 threads per output row (N <= 64)
+  for (int k = T - 1; k >= 0; --k) {
+    for (int i = tid; i < N; i += kThreads)
+      f[i] = G(in.delta, (k + 1) * N + i) * v[i] - G(in.c, (k + 1) * N + i);
+    __syncthreads();
+    {  // g = v - W' f
+      double acc = 0.0;
+      if (row < N)
+        for (int j = part; j < N; j += 4) {
+          const int i = row;
+          acc += G(Wst, (k + 1) * tri(N) + (i >= j ? pk(i, j, N) : pk(j, i, N))) * f[j];
+        }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      if (row < N && part == 0) g[row] = v[row] - acc;
+    }
+    __syncthreads();
+    {  // h = r + B' g
+      double acc = 0.0;
+      if (row < M)
+        for (int p = part; p < N; p += 4) acc += G(in.B, (k * M + row) * N + p) * g[p];
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      if (row < M && part == 0) h[row] = G(in.r, k * M + row) + acc;
+    }
+    __syncthreads();
+    {  // k = -G^-1 h
+      double acc = 0.0;
+      if (row < M)
+        for (int j = part; j < M; j += 4) {
+          const int i = row;
+          acc += G(Gst, k * tri(M) + (i >= j ? pk(i, j, M) : pk(j, i, M))) * h[j];
+        }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      if (row < M && part == 0) {
+        kk[row] = -acc;
+        __stcs(kst + static_cast<size_t>(k * M + row) * L_, -acc);
+      }
+    }
+    __syncthreads();
+    {  // v = q + A' g + K' h
+      double acc = 0.0;
+      if (row < N) {
+        for (int p = part; p < N; p += 4) acc += G(in.A, (k * N + row) * N + p) * g[p];
+        for (int a = part; a < M; a += 4) acc += G(Kst, (k * N + row) * M + a) * h[a];
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      __syncthreads();
+      if (row < N && part == 0) {
+        v[row] = G(in.q, k * N + row) + acc;
+        __stcs(vst + static_cast<size_t>(k * N + row) * L_, v[row]);
+      }
+    }
+    __syncthreads();
+  }
+#undef G
+}
+
+// Root solve + forward rollout + costates, one CTA per problem (lqr.cpp:798-870).
+template <int N, int M>
+__global__ void __launch_bounds__(kThreads)
+rollout_forward_cta(LqrIn in, LqrOut out, const double *store, const double *scratch,
+                    int64_t batch, int64_t ld, int T) {
+  using Zs = CtaSizes<N, M>;
+  __shared__ double x[N], u[M], f[N], wf[N], vv[N], dd[N];
+  const int tid = threadIdx.x;
+  const int64_t b = blockIdx.x;
+  const size_t L_ = static_cast<size_t>(ld);
+#define G(ptr, e) __ldcs((ptr) + static_cast<size_t>(e) * L_ + b)
+  const double *Wst = store + Zs::oW(T) * ld;
+  const double *Kst = store + Zs::oK(T) * ld;
+  const double *vst = scratch + Zs::ov(T) * ld;
+  const double *kst = scratch + Zs::ok(T) * ld;
+  double *xo = out.x + b, *uo = out.u + b, *yo = out.y + b;
+  const int row = tid >> 2, part = tid & 3;
+
+  auto w_times_f = [&](int node) {  // wf = W_node f  (packed symmetric)
+    double acc = 0.0;
+    if (row < N)
+      for (int j = part; j < N; j += 4) {
+        const int i = row;
+        acc += G(Wst, node * tri(N) + (i >= j ? pk(i, j, N) : pk(j, i, N))) * f[j];
+      }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (row < N && part == 0) wf[row] = acc;
+  };
+
+  for (int i = tid; i < N; i += kThreads) {
+    vv[i] = G(vst, i);
+    dd[i] = G(in.delta, i);
+    f[i] = dd[i] * vv[i] - G(in.c, i);
+  }
+  __syncthreads();
+  w_times_f(0);
+  __syncthreads();
+  for (int i = tid; i < N; i += kThreads) {
+    x[i] = dd[i] * wf[i] - f[i];
+    __stcs(xo + static_cast<size_t>(i) * L_, x[i]);
+    __stcs(yo + static_cast<size_t>(i) * L_, vv[i] - wf[i]);
+  }
+  __syncthreads();
+  for (int k = 0; k < T; ++k) {
+    {  // u = k + K x
+      double acc = 0.0;
+      if (row < M)
+        for (int j = part; j < N; j += 4) acc += G(Kst, (k * N + j) * M + row) * x[j];
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      if (row < M && part == 0) {
+        u[row] = G(kst, k * M + row) + acc;
+        __stcs(uo + static_cast<size_t>(k * M + row) * L_, u[row]);
+      }
+    }
+    for (int i = tid; i < N; i += kThreads) {
+      vv[i] = G(vst, (k + 1) * N + i);
+      dd[i] = G(in.delta, (k + 1) * N + i);
+    }
+    __syncthreads();
+    {  // f = c' - delta' o v' + A x + B u
+      double acc = 0.0;
+      if (row < N) {
+        for (int j = part; j < N; j += 4) acc += G(in.A, (k * N + j) * N + row) * x[j];
+        for (int a = part; a < M; a += 4) acc += G(in.B, (k * M + a) * N + row) * u[a];
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      if (row < N && part == 0) f[row] = G(in.c, (k + 1) * N + row) - dd[row] * vv[row] + acc;
+    }
+    __syncthreads();
+    w_times_f(k + 1);
+    __syncthreads();
+    for (int i = tid; i < N; i += kThreads) {
+      x[i] = f[i] - dd[i] * wf[i];
+      __stcs(xo + static_cast<size_t>((k + 1) * N + i) * L_, x[i]);
+      __stcs(yo + static_cast<size_t>((k + 1) * N + i) * L_, vv[i] + wf[i]);
+    }
+    __syncthreads();
+  }
+#undef G
+}
+
+template <int N, int M>
+struct CtaPlan {
+  static_assert(N % 16 == 0 && N <= 64, "state dimension must be a multiple of 16, at most 64");
+  static int64_t store_elems(int T) { return CtaSizes<N, M>::store(T); }
+  static int64_t scratch_elems(int T) { return CtaSizes<N, M>::scratch(T); }
+  template <bool SOLVE>
+  static void backward(const FastArgs &a, cudaStream_t s) {
+    auto kern = riccati_backward_cta<N, M, SOLVE>;
+    constexpr int bytes = CtaSmem<N, M>::kBytes;
+    if (bytes > 48 * 1024)
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    ProfScope ps(a.prof, "riccati_backward_cta", s);
+    kern<<<static_cast<unsigned>(a.batch), kThreads, bytes, s>>>(a.in, a.status, a.store,
+                                                                 a.scratch, a.batch, a.ld,
+                                                                 a.num_edges);
+  }
+  static void forward(const FastArgs &a, cudaStream_t s) {
+    ProfScope ps(a.prof, "rollout_forward_cta", s);
+    rollout_forward_cta<N, M><<<static_cast<unsigned>(a.batch), kThreads, 0, s>>>(
+        a.in, a.out, a.store, a.scratch, a.batch, a.ld, a.num_edges);
+  }
+  static int factor(const FastArgs &a, cudaStream_t s) {
+    backward<false>(a, s);
+    return 1;
+  }
+  static int solve(const FastArgs &a, cudaStream_t s) {
+    {
+      ProfScope ps(a.prof, "affine_backward_cta", s);
+      affine_backward_cta<N, M><<<static_cast<unsigned>(a.batch), kThreads, 0, s>>>(
+          a.in, a.store, a.scratch, a.batch, a.ld, a.num_edges);
+    }
+    forward(a, s);
+    return 2;
+  }
+  static int factor_solve(const FastArgs &a, cudaStream_t s) {
+    backward<true>(a, s);
+    forward(a, s);
+    return 2;
+  }
+};
+
+template <int N, int M>
+const FastPlan *make_cta_plan(const char *name) {
+  using P = CtaPlan<N, M>;
+  static const FastPlan plan{name,         N,           M,         &P::store_elems,
+                             &P::scratch_elems, &P::factor, &P::solve, &P::factor_solve};
+  return &plan;
+}
+
+}  // namespace
+
+const FastPlan *select_cta_plan(int n, int m) {
+  if (n == 64 && m == 24) return make_cta_plan<64, 24>("cta_dmma_n64_m24");
+  if (n == 16 && m == 4) return make_cta_plan<16, 4>("cta_dmma_n16_m4");
+  if (n == 32 && m == 8) return make_cta_plan<32, 8>("cta_dmma_n32_m8");
+  return nullptr;
+}
+
+}  // namespace sipoc

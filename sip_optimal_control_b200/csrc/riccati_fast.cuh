@@ -40,5 +40,8 @@ struct FastPlan {
 
 // nullptr when no specialised kernel exists for (n, m).
 const FastPlan *select_fast_plan(int n, int m);
+// CTA-per-problem DMMA kernels for large dimensions (riccati_cta.cu); nullptr when
+// (n, m) is not instantiated.
+const FastPlan *select_cta_plan(int n, int m);
 
 }  // namespace sipoc

@@ -113,7 +113,7 @@ def test_single_stage_failure_fixtures():  # lqr_test.cpp:213-227 verbatim (n=m=
 
 # --- benchmark-distribution chains (lqr_benchmark.cpp:61-96, :537-545) -----------
 SHAPES = [(4, 1, 16), (4, 1, 100), (6, 2, 32), (8, 3, 16), (12, 4, 50), (16, 4, 16),
-          (5, 2, 7), (3, 3, 4)]
+          (5, 2, 7), (3, 3, 4), (32, 8, 6), (64, 24, 4)]
 
 
 @pytest.mark.parametrize("n,m,T", SHAPES)
@@ -135,7 +135,7 @@ def test_benchmark_chains_match_oracle(n, m, T, force_generic):
     assert np.isclose(gpu["stats"][1], gpu["residual"].max())
     assert np.isclose(gpu["stats"][0], (gpu["residual"] ** 2).sum())
     assert gpu["stats"][3] == batch
-    if not force_generic and (n, m) in ((4, 1), (12, 4), (6, 2), (8, 3)):
+    if not force_generic and (n, m) in ((4, 1), (12, 4), (6, 2), (8, 3), (16, 4), (32, 8), (64, 24)):
         assert "generic" not in lqr.engine.kernel_variant, lqr.engine.kernel_variant
 
 
