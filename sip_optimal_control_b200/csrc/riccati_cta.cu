@@ -403,6 +403,10 @@ riccati_backward_cta(LqrIn in, int *status_out, double *store, double *scratch, 
     }
     const bool any_bad = __syncthreads_or(!d_ok);
     if (any_bad && status == SIPOC_FACTOR_SUCCESS) status = SIPOC_FACTOR_INVALID_DELTA;
+    if (k > 0) {  // M, R, q, r, c, delta of the next stage fly during the F inverse
+      stage_edge_rest(k - 1);
+      cp_async_commit();
+    }
     for (int e = tid; e < N * N; e += kThreads) {
       const int i = e % N, j = e / N;
       if (i >= j) Wp[j * LDN + i] = sd_s[i] * Wp[j * LDN + i] * sd_s[j] + (i == j ? 1.0 : 0.0);
@@ -423,6 +427,18 @@ riccati_backward_cta(LqrIn in, int *status_out, double *store, double *scratch, 
     __syncthreads();
   };
 
+  // Padding, written once: columns N+M.. of Z are zero, rows M.. of Psi_ux are zero,
+  // Psi_uu carries identity on its padded diagonal (blkdiag(G, I) keeps that shape
+  // through the inverse), r is zero beyond M.
+  for (int e = tid; e < (MP - M) * N; e += kThreads) Zb[(N + M + e / N) * LDN + e % N] = 0.0;
+  for (int e = tid; e < N * LDM; e += kThreads) Pux[e] = 0.0;
+  for (int e = tid; e < MP * LDM; e += kThreads) {
+    const int i = e % LDM, j = e / LDM;
+    Puu[e] = (i == j && i >= M && i < MP) ? 1.0 : 0.0;
+  }
+  if (tid < MP) r_s[tid] = 0.0;
+  __syncthreads();
+
   // ---- terminal node ----------------------------------------------------------
   stage_q_lower(T);
   if (tid < N) {
@@ -432,22 +448,13 @@ riccati_backward_cta(LqrIn in, int *status_out, double *store, double *scratch, 
   cp_async_commit();
   cp_async_wait_all();
   __syncthreads();
+  if (T > 0) {  // stage T-1's A, B fly while node T is processed
+    stage_edge_z(T - 1);
+    cp_async_commit();
+  }
   process_node(T);
 
   for (int k = T - 1; k >= 0; --k) {
-    // Zero the padding (columns N+M.. of Z, rows / columns M.. of the u blocks) and
-    // fetch the stage.  Psi_uu gets identity on its padded diagonal.
-    for (int e = tid; e < (MP - M) * N; e += kThreads) Zb[(N + M + e / N) * LDN + e % N] = 0.0;
-    for (int e = tid; e < N * LDM; e += kThreads) Pux[e] = 0.0;
-    for (int e = tid; e < MP * LDM; e += kThreads) {
-      const int i = e % LDM, j = e / LDM;
-      Puu[e] = (i == j && i >= M && i < MP) ? 1.0 : 0.0;
-    }
-    if (tid < MP) r_s[tid] = 0.0;
-    __syncthreads();
-    stage_edge_z(k);
-    stage_edge_rest(k);
-    cp_async_commit();
     cp_async_wait_all();
     __syncthreads();
 
@@ -476,6 +483,10 @@ riccati_backward_cta(LqrIn in, int *status_out, double *store, double *scratch, 
     // Psi_xx += A' S_x (lower blocks)
     cta_gemm<true, false, true, true>(Wp, LDN, Zb, LDN, Sb, LDN, N, N, N, 1.0);
     __syncthreads();
+    if (k > 0) {  // Z is consumed: A, B of the next stage fly during the rest of this one
+      stage_edge_z(k - 1);
+      cp_async_commit();
+    }
 
     // G^-1 (full, in Puu)
     const bool g_ok = cta_spd_inverse(Puu, LDM, MP, Gs, Dinv);
@@ -584,84 +595,87 @@ affine_backward_cta(LqrIn in, const double *store, double *scratch, int64_t batc
 #undef G
 }
 
-// Root solve + forward rollout + costates, one CTA per problem (lqr.cpp:798-870).
+// Root solve + forward rollout + costates (lqr.cpp:798-870).  FOUR problems per CTA,
+// one thread per (problem, row): the four problems are consecutive in the batch, so
+// every 32-byte sector a warp touches is fully used (4 doubles = 4 problems) and a
+// warp load covers 8 rows x 4 problems = 8 whole sectors.
 template <int N, int M>
 __global__ void __launch_bounds__(kThreads)
 rollout_forward_cta(LqrIn in, LqrOut out, const double *store, const double *scratch,
                     int64_t batch, int64_t ld, int T) {
+  static_assert(N * 4 <= kThreads && M <= N, "one thread per (problem, row)");
   using Zs = CtaSizes<N, M>;
-  __shared__ double x[N], u[M], f[N], wf[N], vv[N], dd[N];
+  __shared__ double x[N * 4], u[M * 4], f[N * 4];
   const int tid = threadIdx.x;
-  const int64_t b = blockIdx.x;
+  const int p = tid & 3, row = tid >> 2;
+  const int64_t b_raw = static_cast<int64_t>(blockIdx.x) * 4 + p;
+  const bool valid = b_raw < batch;
+  const int64_t b = valid ? b_raw : batch - 1;
   const size_t L_ = static_cast<size_t>(ld);
-#define G(ptr, e) __ldcs((ptr) + static_cast<size_t>(e) * L_ + b)
+#define G(ptr, e) __ldg((ptr) + static_cast<size_t>(e) * L_ + b)
   const double *Wst = store + Zs::oW(T) * ld;
   const double *Kst = store + Zs::oK(T) * ld;
   const double *vst = scratch + Zs::ov(T) * ld;
   const double *kst = scratch + Zs::ok(T) * ld;
   double *xo = out.x + b, *uo = out.u + b, *yo = out.y + b;
-  const int row = tid >> 2, part = tid & 3;
+  const bool xrow = row < N, urow = row < M;
 
-  auto w_times_f = [&](int node) {  // wf = W_node f  (packed symmetric)
+  auto w_row_times_f = [&](int node) {  // (W_node f)(row), W packed symmetric
     double acc = 0.0;
-    if (row < N)
-      for (int j = part; j < N; j += 4) {
-        const int i = row;
-        acc += G(Wst, node * tri(N) + (i >= j ? pk(i, j, N) : pk(j, i, N))) * f[j];
-      }
-    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-    if (row < N && part == 0) wf[row] = acc;
+#pragma unroll 8
+    for (int j = 0; j < N; ++j)
+      acc += G(Wst, node * tri(N) + (row >= j ? pk(row, j, N) : pk(j, row, N))) * f[j * 4 + p];
+    return acc;
   };
 
-  for (int i = tid; i < N; i += kThreads) {
-    vv[i] = G(vst, i);
-    dd[i] = G(in.delta, i);
-    f[i] = dd[i] * vv[i] - G(in.c, i);
+  double vv = 0.0, dd = 0.0, fi = 0.0;
+  if (xrow) {
+    vv = G(vst, row);
+    dd = G(in.delta, row);
+    fi = dd * vv - G(in.c, row);
+    f[row * 4 + p] = fi;
   }
   __syncthreads();
-  w_times_f(0);
-  __syncthreads();
-  for (int i = tid; i < N; i += kThreads) {
-    x[i] = dd[i] * wf[i] - f[i];
-    __stcs(xo + static_cast<size_t>(i) * L_, x[i]);
-    __stcs(yo + static_cast<size_t>(i) * L_, vv[i] - wf[i]);
+  if (xrow) {
+    const double wf = w_row_times_f(0);
+    const double xi = dd * wf - fi;
+    x[row * 4 + p] = xi;
+    if (valid) {
+      __stcs(xo + static_cast<size_t>(row) * L_, xi);
+      __stcs(yo + static_cast<size_t>(row) * L_, vv - wf);
+    }
   }
   __syncthreads();
   for (int k = 0; k < T; ++k) {
-    {  // u = k + K x
-      double acc = 0.0;
-      if (row < M)
-        for (int j = part; j < N; j += 4) acc += G(Kst, (k * N + j) * M + row) * x[j];
-      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-      if (row < M && part == 0) {
-        u[row] = G(kst, k * M + row) + acc;
-        __stcs(uo + static_cast<size_t>(k * M + row) * L_, u[row]);
+    if (urow) {  // u = k + K x
+      double acc = G(kst, k * M + row);
+#pragma unroll 8
+      for (int j = 0; j < N; ++j) acc += G(Kst, (k * N + j) * M + row) * x[j * 4 + p];
+      u[row * 4 + p] = acc;
+      if (valid) __stcs(uo + static_cast<size_t>(k * M + row) * L_, acc);
+    }
+    if (xrow) {
+      vv = G(vst, (k + 1) * N + row);
+      dd = G(in.delta, (k + 1) * N + row);
+      fi = G(in.c, (k + 1) * N + row) - dd * vv;
+#pragma unroll 8
+      for (int j = 0; j < N; ++j) fi += G(in.A, (k * N + j) * N + row) * x[j * 4 + p];
+    }
+    __syncthreads();
+    if (xrow) {  // f = c' - delta' o v' + A x + B u
+#pragma unroll 8
+      for (int a = 0; a < M; ++a) fi += G(in.B, (k * M + a) * N + row) * u[a * 4 + p];
+      f[row * 4 + p] = fi;
+    }
+    __syncthreads();
+    if (xrow) {
+      const double wf = w_row_times_f(k + 1);
+      const double xi = fi - dd * wf;
+      x[row * 4 + p] = xi;  // every thread finished reading x before the previous barrier
+      if (valid) {
+        __stcs(xo + static_cast<size_t>((k + 1) * N + row) * L_, xi);
+        __stcs(yo + static_cast<size_t>((k + 1) * N + row) * L_, vv + wf);
       }
-    }
-    for (int i = tid; i < N; i += kThreads) {
-      vv[i] = G(vst, (k + 1) * N + i);
-      dd[i] = G(in.delta, (k + 1) * N + i);
-    }
-    __syncthreads();
-    {  // f = c' - delta' o v' + A x + B u
-      double acc = 0.0;
-      if (row < N) {
-        for (int j = part; j < N; j += 4) acc += G(in.A, (k * N + j) * N + row) * x[j];
-        for (int a = part; a < M; a += 4) acc += G(in.B, (k * M + a) * N + row) * u[a];
-      }
-      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-      if (row < N && part == 0) f[row] = G(in.c, (k + 1) * N + row) - dd[row] * vv[row] + acc;
-    }
-    __syncthreads();
-    w_times_f(k + 1);
-    __syncthreads();
-    for (int i = tid; i < N; i += kThreads) {
-      x[i] = f[i] - dd[i] * wf[i];
-      __stcs(xo + static_cast<size_t>((k + 1) * N + i) * L_, x[i]);
-      __stcs(yo + static_cast<size_t>((k + 1) * N + i) * L_, vv[i] + wf[i]);
     }
     __syncthreads();
   }
@@ -686,7 +700,7 @@ struct CtaPlan {
   }
   static void forward(const FastArgs &a, cudaStream_t s) {
     ProfScope ps(a.prof, "rollout_forward_cta", s);
-    rollout_forward_cta<N, M><<<static_cast<unsigned>(a.batch), kThreads, 0, s>>>(
+    rollout_forward_cta<N, M><<<static_cast<unsigned>((a.batch + 3) / 4), kThreads, 0, s>>>(
         a.in, a.out, a.store, a.scratch, a.batch, a.ld, a.num_edges);
   }
   static int factor(const FastArgs &a, cudaStream_t s) {

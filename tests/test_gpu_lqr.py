@@ -139,7 +139,7 @@ def test_benchmark_chains_match_oracle(n, m, T, force_generic):
         assert "generic" not in lqr.engine.kernel_variant, lqr.engine.kernel_variant
 
 
-@pytest.mark.parametrize("n,m,T", [(4, 1, 20), (12, 4, 10), (5, 2, 7)])
+@pytest.mark.parametrize("n,m,T", [(4, 1, 20), (12, 4, 10), (5, 2, 7), (16, 4, 6), (64, 24, 3)])
 def test_factor_once_solve_many(n, m, T):
     # BM_LQRSolve semantics (lqr_benchmark.cpp:611-638): re-solve with new
     # q, r, c against a kept factorization.
