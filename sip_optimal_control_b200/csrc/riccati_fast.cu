@@ -111,15 +111,16 @@ struct Smem {
   static constexpr int rDl = rV + N;          // delta of the last processed node
   static constexpr int rSd = rDl + N;         // sqrt(delta), 1/sqrt(delta) of the node in flight
   static constexpr int rSdi = rSd + N;
-  // Exchange region: first [Psi_uu packed | Psi_xu | h | Lambda], later F packed,
-  // later L^-1 packed.
-  static constexpr int rX = rSdi + N;
+  // Exchange region, ALIASED onto the Q | M | R staging rows (their contents are
+  // consumed before the first exchange of a stage and re-fetched after the last):
+  // first [Psi_uu packed | Psi_xu (overwritten in place by Lambda) | h], later F packed.
+  static constexpr int rX = rQ;
   static constexpr int xGuu = rX;
   static constexpr int xPxu = xGuu + tri(M);
   static constexpr int xH = xPxu + N * M;
-  static constexpr int xLam = xH + M;
-  static constexpr int kXRows = cmax(tri(M) + 2 * N * M + M, tri(N));
-  static constexpr int kRows = rX + kXRows;
+  static constexpr int xLam = xPxu;
+  static_assert(tri(M) + N * M + M <= tri(N) + N * M + tri(M), "exchange region fits");
+  static constexpr int kRows = rSdi + N;
   static constexpr int kBytes = kRows * kTile * int(sizeof(double));
 };
 
@@ -207,32 +208,40 @@ riccati_backward_subwarp(LqrIn in, int *status_out, double *store, double *scrat
   const double *pR = in.R + static_cast<int64_t>(T - 1) * M * M * ld + lane_goff;
   const double *pr = SOLVE ? in.r + static_cast<int64_t>(T - 1) * M * ld + lane_goff : nullptr;
 
-  // Node data of the node the pointers stand on, then step one node back.
-  auto issue_node = [&]() {
-    stage_lower<N>(sdst + S::rQ * kTile, pQ, ld, ld8, rr);
+  // Z = [B | A] and the vectors of the stage the pointers stand on (q, delta of its
+  // node, r of its edge, c of the edge's child), then step back.  Issued as soon as
+  // the current stage has consumed its own copies.
+  auto issue_z_vec = [&](bool with_edge) {
     stage_run(sdst + S::rd * kTile, pd, ld8, N, rr);
-    pQ -= static_cast<int64_t>(N) * N * ld;
     pd -= static_cast<int64_t>(N) * ld;
     if (SOLVE) {
       stage_run(sdst + S::rq * kTile, pq, ld8, N, rr);
       pq -= static_cast<int64_t>(N) * ld;
     }
+    if (with_edge) {
+      stage_run(sdst + S::rZ * kTile, pB, ld8, N * M, rr);
+      stage_run(sdst + (S::rZ + N * M) * kTile, pA, ld8, N * N, rr);
+      pB -= static_cast<int64_t>(N) * M * ld;
+      pA -= static_cast<int64_t>(N) * N * ld;
+      if (SOLVE) {
+        stage_run(sdst + S::rr * kTile, pr, ld8, M, rr);
+        stage_run(sdst + S::rc * kTile, pc, ld8, N, rr);
+        pr -= static_cast<int64_t>(M) * ld;
+        pc -= static_cast<int64_t>(N) * ld;
+      }
+    }
   };
-  // Edge data (and c of the edge's child node), then step one edge back.
-  auto issue_edge = [&]() {
-    stage_run(sdst + S::rZ * kTile, pB, ld8, N * M, rr);
-    stage_run(sdst + (S::rZ + N * M) * kTile, pA, ld8, N * N, rr);
-    stage_run(sdst + S::rM * kTile, pM, ld8, N * M, rr);
-    stage_lower<M>(sdst + S::rR * kTile, pR, ld, ld8, rr);
-    pB -= static_cast<int64_t>(N) * M * ld;
-    pA -= static_cast<int64_t>(N) * N * ld;
-    pM -= static_cast<int64_t>(N) * M * ld;
-    pR -= static_cast<int64_t>(M) * M * ld;
-    if (SOLVE) {
-      stage_run(sdst + S::rr * kTile, pr, ld8, M, rr);
-      stage_run(sdst + S::rc * kTile, pc, ld8, N, rr);
-      pr -= static_cast<int64_t>(M) * ld;
-      pc -= static_cast<int64_t>(N) * ld;
+  // Q (lower), M, R (lower) of the stage the pointers stand on, then step back.  Their
+  // rows double as the exchange region, so they are fetched only after the last
+  // exchange of the current stage (the read of F).
+  auto issue_qmr = [&](bool with_edge) {
+    stage_lower<N>(sdst + S::rQ * kTile, pQ, ld, ld8, rr);
+    pQ -= static_cast<int64_t>(N) * N * ld;
+    if (with_edge) {
+      stage_run(sdst + S::rM * kTile, pM, ld8, N * M, rr);
+      stage_lower<M>(sdst + S::rR * kTile, pR, ld, ld8, rr);
+      pM -= static_cast<int64_t>(N) * M * ld;
+      pR -= static_cast<int64_t>(M) * M * ld;
     }
   };
 
@@ -262,7 +271,8 @@ riccati_backward_subwarp(LqrIn in, int *status_out, double *store, double *scrat
     }
   };
 
-  issue_node();
+  issue_z_vec(false);
+  issue_qmr(false);
   cp_async_commit();
 
   for (int k = T; k >= 0; --k) {
@@ -284,8 +294,7 @@ riccati_backward_subwarp(LqrIn in, int *status_out, double *store, double *scrat
       update_delta();
       __syncwarp();
       if (T > 0) {
-        issue_node();
-        issue_edge();
+        issue_z_vec(true);
         cp_async_commit();
       }
     } else {
@@ -405,6 +414,7 @@ riccati_backward_subwarp(LqrIn in, int *status_out, double *store, double *scrat
         for (int i = kGroup * s; i < N; ++i) V[s][i] += SM(S::rQ + qcol[s] + i);
         if (SOLVE) vv[s] += SM(S::rq + xj[s]);
       }
+      __syncwarp();  // every lane has taken its Q / M / R entries: their rows become X
       // Publish the control block: Psi_uu (packed lower), Psi_xu, h.
 #pragma unroll
       for (int s = 0; s < SU; ++s) {
@@ -420,8 +430,7 @@ riccati_backward_subwarp(LqrIn in, int *status_out, double *store, double *scrat
       __syncwarp();  // control block visible; staged operands of stage k consumed
 
       if (k > 0) {
-        issue_node();
-        issue_edge();
+        issue_z_vec(true);
         cp_async_commit();
       }
 
@@ -593,6 +602,11 @@ riccati_backward_subwarp(LqrIn in, int *status_out, double *store, double *scrat
     double L[tri(N)], dinv[N];
 #pragma unroll
     for (int t = 0; t < tri(N); ++t) L[t] = SM(S::rX + t);
+    __syncwarp();  // every lane has read F: the exchange rows are free again
+    if (k > 0) {
+      issue_qmr(true);
+      cp_async_commit();
+    }
     bool f_ok = true;
 #pragma unroll
     for (int j = 0; j < N; ++j) {
@@ -611,7 +625,6 @@ riccati_backward_subwarp(LqrIn in, int *status_out, double *store, double *scrat
       }
     }
     if (!f_ok && status == SIPOC_FACTOR_SUCCESS) status = SIPOC_FACTOR_F_FACTORIZATION_FAILURE;
-
     // Own columns of F^-1 = L^-T L^-1: forward substitution on e_xj, then backward
     // substitution, both against the lane's register copy of L (no exchange).
     // W = D^-1/2 (I - F^-1) D^-1/2, rows >= 4 s of the own columns.
