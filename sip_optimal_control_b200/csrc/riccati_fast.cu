@@ -60,7 +60,6 @@ __host__ __device__ constexpr int tri(int n) { return n * (n + 1) / 2; }
 __host__ __device__ constexpr int pk(int i, int j, int n) {
   return j * n - j * (j - 1) / 2 + (i - j);
 }
-__host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
 __host__ __device__ constexpr int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 // Per-problem element counts of the kept factorization and the rollout spill.
@@ -969,26 +968,49 @@ affine_backward(LqrIn in, const double *store, double *scratch, int64_t batch, i
     stcs(vst + static_cast<int64_t>(T * N + i) * ld, v[i]);
   }
   for (int k = T - 1; k >= 0; --k) {
+    // Operands are pulled into register arrays in three groups BEFORE the arithmetic
+    // that needs them, so each thread keeps ~100 independent loads in flight: at the
+    // small batches this kernel serves (one Newton-KKT solve after a kept factor) the
+    // latency of the dependent chain is hidden by memory-level parallelism, not by
+    // occupancy.
+    double wv[tri(N)], dv[N], cv[N];
+#pragma unroll
+    for (int t = 0; t < tri(N); ++t) wv[t] = G(Wst, (k + 1) * tri(N) + t);
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      dv[i] = G(in.delta, (k + 1) * N + i);
+      cv[i] = G(in.c, (k + 1) * N + i);
+    }
     double f[N], g[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      f[i] = G(in.delta, (k + 1) * N + i) * v[i] - G(in.c, (k + 1) * N + i);
+      f[i] = dv[i] * v[i] - cv[i];
       g[i] = v[i];
     }
 #pragma unroll
     for (int j = 0; j < N; ++j)
 #pragma unroll
       for (int i = j; i < N; ++i) {
-        const double w = G(Wst, (k + 1) * tri(N) + pk(i, j, N));
+        const double w = wv[pk(i, j, N)];
         g[i] -= w * f[j];
         if (i != j) g[j] -= w * f[i];
       }
+    double bv[N * M], kv[N * M], gv[tri(M)], rv[M];
+#pragma unroll
+    for (int t = 0; t < N * M; ++t) {
+      bv[t] = G(in.B, k * N * M + t);
+      kv[t] = G(Kst, k * N * M + t);
+    }
+#pragma unroll
+    for (int t = 0; t < tri(M); ++t) gv[t] = G(Gst, k * tri(M) + t);
+#pragma unroll
+    for (int a = 0; a < M; ++a) rv[a] = G(in.r, k * M + a);
     double h[M];
 #pragma unroll
     for (int a = 0; a < M; ++a) {
-      double acc = G(in.r, k * M + a);
+      double acc = rv[a];
 #pragma unroll
-      for (int p = 0; p < N; ++p) acc += G(in.B, (k * M + a) * N + p) * g[p];
+      for (int p = 0; p < N; ++p) acc += bv[a * N + p] * g[p];
       h[a] = acc;
     }
     double kk[M];
@@ -998,20 +1020,37 @@ affine_backward(LqrIn in, const double *store, double *scratch, int64_t batch, i
     for (int j = 0; j < M; ++j)
 #pragma unroll
       for (int i = j; i < M; ++i) {
-        const double gi = G(Gst, k * tri(M) + pk(i, j, M));
+        const double gi = gv[pk(i, j, M)];
         kk[i] -= gi * h[j];
         if (i != j) kk[j] -= gi * h[i];
       }
 #pragma unroll
     for (int a = 0; a < M; ++a) stcs(kst + static_cast<int64_t>(k * M + a) * ld, kk[a]);
+    constexpr int HALF = (N + 1) / 2;
 #pragma unroll
-    for (int j = 0; j < N; ++j) {
-      double acc = G(in.q, k * N + j);
+    for (int half = 0; half < 2; ++half) {
+      double av[HALF * N], qv[HALF];
 #pragma unroll
-      for (int p = 0; p < N; ++p) acc += G(in.A, (k * N + j) * N + p) * g[p];
+      for (int jj = 0; jj < HALF; ++jj) {
+        const int j = half * HALF + jj;
+        if (j < N) {
+          qv[jj] = G(in.q, k * N + j);
 #pragma unroll
-      for (int a = 0; a < M; ++a) acc += G(Kst, (k * N + j) * M + a) * h[a];
-      v[j] = acc;
+          for (int p = 0; p < N; ++p) av[jj * N + p] = G(in.A, (k * N + j) * N + p);
+        }
+      }
+#pragma unroll
+      for (int jj = 0; jj < HALF; ++jj) {
+        const int j = half * HALF + jj;
+        if (j < N) {
+          double acc = qv[jj];
+#pragma unroll
+          for (int p = 0; p < N; ++p) acc += av[jj * N + p] * g[p];
+#pragma unroll
+          for (int a = 0; a < M; ++a) acc += kv[j * M + a] * h[a];
+          v[j] = acc;
+        }
+      }
     }
 #pragma unroll
     for (int i = 0; i < N; ++i) stcs(vst + static_cast<int64_t>(k * N + i) * ld, v[i]);
