@@ -354,18 +354,48 @@ riccati_backward_subwarp(LqrIn in, int *status_out, double *store, double *scrat
           for (int s = 0; s < SX; ++s) vv[s] += zx[s][q] * gq;
         }
       }
+      // The first half of each W' row is fetched one iteration ahead (wpre), so the
+      // dot products start without waiting on shared memory; the second half and the
+      // Z row are in flight while they run.
+      constexpr int H = N / 2;
+      double wpre[H];
+#pragma unroll
+      for (int q = 0; q < H; ++q) wpre[q] = sm[(S::rW + q) * kTile + prob];
 #pragma unroll 1
       for (int p = 0; p < N; ++p) {
         const double *wrow = sm + (S::rW + p * N) * kTile + prob;
         const double *zrow = sm + (S::rZ + p) * kTile + prob;
+        double wlate[N - H];
+#pragma unroll
+        for (int q = H; q < N; ++q) wlate[q - H] = wrow[q * kTile];
         double su[SU], sx[SX], su2[SU], sx2[SX];
 #pragma unroll
         for (int s = 0; s < SU; ++s) su[s] = su2[s] = 0.0;
 #pragma unroll
         for (int s = 0; s < SX; ++s) sx[s] = sx2[s] = 0.0;
 #pragma unroll
-        for (int q = 0; q < N; ++q) {
-          const double w = wrow[q * kTile];
+        for (int q = 0; q < H; ++q) {
+          const double w = wpre[q];
+          if (q & 1) {
+#pragma unroll
+            for (int s = 0; s < SU; ++s) su2[s] += w * zu[s][q];
+#pragma unroll
+            for (int s = 0; s < SX; ++s) sx2[s] += w * zx[s][q];
+          } else {
+#pragma unroll
+            for (int s = 0; s < SU; ++s) su[s] += w * zu[s][q];
+#pragma unroll
+            for (int s = 0; s < SX; ++s) sx[s] += w * zx[s][q];
+          }
+        }
+        {  // prefetch the head of the next row (row 0 again on the last iteration)
+          const double *wnext = sm + (S::rW + (p + 1 < N ? p + 1 : 0) * N) * kTile + prob;
+#pragma unroll
+          for (int q = 0; q < H; ++q) wpre[q] = wnext[q * kTile];
+        }
+#pragma unroll
+        for (int q = H; q < N; ++q) {
+          const double w = wlate[q - H];
           if (q & 1) {
 #pragma unroll
             for (int s = 0; s < SU; ++s) su2[s] += w * zu[s][q];
@@ -606,22 +636,21 @@ riccati_backward_subwarp(LqrIn in, int *status_out, double *store, double *scrat
       issue_qmr(true);
       cp_async_commit();
     }
+    // Right-looking form: once column j is scaled, the trailing updates are independent
+    // FMAs, so the dependent chain per column is rsqrt -> mul -> one FMA.
     bool f_ok = true;
 #pragma unroll
     for (int j = 0; j < N; ++j) {
-      double x = L[pk(j, j, N)];
-#pragma unroll
-      for (int q = 0; q < j; ++q) x -= L[pk(j, q, N)] * L[pk(j, q, N)];
+      const double x = L[pk(j, j, N)];
       f_ok = f_ok && (x > 0.0);
       const double d = rsqrt(x);
       dinv[j] = d;
 #pragma unroll
-      for (int i = j + 1; i < N; ++i) {
-        double t = L[pk(i, j, N)];
+      for (int i = j + 1; i < N; ++i) L[pk(i, j, N)] *= d;
 #pragma unroll
-        for (int q = 0; q < j; ++q) t -= L[pk(i, q, N)] * L[pk(j, q, N)];
-        L[pk(i, j, N)] = t * d;
-      }
+      for (int c = j + 1; c < N; ++c)
+#pragma unroll
+        for (int i = c; i < N; ++i) L[pk(i, c, N)] -= L[pk(i, j, N)] * L[pk(c, j, N)];
     }
     if (!f_ok && status == SIPOC_FACTOR_SUCCESS) status = SIPOC_FACTOR_F_FACTORIZATION_FAILURE;
     // Own columns of F^-1 = L^-T L^-1: forward substitution on e_xj, then backward
@@ -629,20 +658,22 @@ riccati_backward_subwarp(LqrIn in, int *status_out, double *store, double *scrat
     // W = D^-1/2 (I - F^-1) D^-1/2, rows >= 4 s of the own columns.
 #pragma unroll
     for (int s = 0; s < SX; ++s) {
+      // Column-oriented (axpy) substitutions: each solved entry immediately updates
+      // the remaining right-hand side with independent FMAs.
       double y[N];
 #pragma unroll
-      for (int i = kGroup * s; i < N; ++i) {
-        double t = (i == xj[s]) ? 1.0 : 0.0;
+      for (int i = kGroup * s; i < N; ++i) y[i] = (i == xj[s]) ? 1.0 : 0.0;
 #pragma unroll
-        for (int q = kGroup * s; q < i; ++q) t -= L[pk(i, q, N)] * y[q];
-        y[i] = t * dinv[i];
+      for (int i = kGroup * s; i < N; ++i) {  // L y = e_xj
+        y[i] *= dinv[i];
+#pragma unroll
+        for (int q = i + 1; q < N; ++q) y[q] -= L[pk(q, i, N)] * y[i];
       }
 #pragma unroll
-      for (int i = N - 1; i >= kGroup * s; --i) {
-        double t = y[i];
+      for (int i = N - 1; i >= kGroup * s; --i) {  // L' x = y
+        y[i] *= dinv[i];
 #pragma unroll
-        for (int q = i + 1; q < N; ++q) t -= L[pk(q, i, N)] * y[q];
-        y[i] = t * dinv[i];
+        for (int q = kGroup * s; q < i; ++q) y[q] -= L[pk(i, q, N)] * y[i];
       }
       double *dst = Wst + static_cast<int64_t>(qcol[s] + kGroup * s) * ld;
 #pragma unroll
