@@ -111,6 +111,68 @@ def test_single_stage_failure_fixtures():  # lqr_test.cpp:213-227 verbatim (n=m=
     assert gpu["status"][0] == FactorStatus.G_FACTORIZATION_FAILURE
 
 
+
+@pytest.mark.parametrize("n,m,T", [(4, 1, 9), (12, 4, 6), (6, 2, 5), (16, 4, 4), (64, 24, 2)])
+@pytest.mark.parametrize("fused", [True, False])
+def test_status_codes_on_specialised_kernels(n, m, T, fused):
+    """Failure injection on the shape-specialised paths (thread / sub-warp / CTA):
+    same FactorStatus per problem as the oracle, healthy neighbours untouched."""
+    batch = 11
+    s, host = pg.lqr_benchmark_batch(n, m, T, batch, seed=5 + n)
+    host = {k: v.copy() for k, v in host.items()}
+    eye_n, eye_m = np.eye(n).flatten(), np.eye(m).flatten()
+    host["delta"][1, T * n + 0] = 0.0                                  # INVALID_DELTA at node T
+    host["Q"][2, T * n * n:] = -400.0 * eye_n                          # F failure at node T
+    host["R"][3, (T - 1) * m * m:] = -50.0 * eye_m                     # G failure at edge T-1
+    host["delta"][4, 1] = -1.0                                         # root delta AND ...
+    host["R"][4, (T - 1) * m * m:] = -50.0 * eye_m                     # ... G deeper: G wins
+    host["delta"][5, (T // 2) * n + n - 1] = -3.0                      # INVALID_DELTA mid-horizon
+    host["Q"][6, 0:n * n] = -400.0 * eye_n                             # F failure at the root
+    host["R"][7, 0:m * m] = -50.0 * eye_m                              # G failure at edge 0
+    ref = pyoracle.lqr_factor_solve(s, host)
+    assert ref["status"].tolist() == [0, 1, 2, 3, 3, 1, 2, 3, 0, 0, 0]
+    gpu, lqr = gpu_lqr_factor_solve(s, host, fused=fused)
+    assert "generic" not in lqr.engine.kernel_variant
+    assert gpu["status"].tolist() == ref["status"].tolist()
+    good = ref["status"] == 0
+    assert_lqr_parity(gpu, ref, REL_TOL, mask=good)
+    assert gpu["stats"][2] == 7 and gpu["stats"][3] == batch
+
+
+def test_status_stats_and_kernel_profile():
+    """sipoc_status_stats (the failure flags a Newton iteration all-reduces) and the
+    per-kernel event profiler of the C ABI."""
+    import ctypes
+
+    import torch
+
+    from sip_optimal_control_b200._capi import lib
+
+    n, m, T, batch = 12, 4, 5, 70
+    s, host = pg.lqr_benchmark_batch(n, m, T, batch, seed=3)
+    host["delta"][9, 0] = -1.0
+    host["delta"][40, n] = 0.0
+    dims, topo = to_structs(s)
+    lqr = LQR(dims, topo, batch)
+    eng = lqr.engine
+    inp, out = lqr.pack_input(host), lqr.alloc_output()
+    lib.sipoc_profile_enable(eng._handle, 1)
+    status = lqr.factor_solve(inp, out)
+    stats = torch.zeros(4, dtype=torch.float64, device=status.device)
+    eng._check(lib.sipoc_status_stats(eng._handle, status.data_ptr(), stats.data_ptr(),
+                                      eng.stream_ptr()))
+    assert stats.cpu().tolist() == [0.0, 0.0, 2.0, float(batch)]
+    names = {}
+    for i in range(lib.sipoc_profile_collect(eng._handle)):
+        nm, ms, cnt = ctypes.c_char_p(), ctypes.c_double(), ctypes.c_int64()
+        eng._check(lib.sipoc_profile_get(eng._handle, i, ctypes.byref(nm), ctypes.byref(ms),
+                                         ctypes.byref(cnt)))
+        names[nm.value.decode()] = (ms.value, cnt.value)
+    assert set(names) == {"riccati_backward_subwarp", "rollout_forward", "status_stats_kernel"}
+    assert all(ms > 0.0 and cnt == 1 for ms, cnt in names.values())
+    lib.sipoc_profile_enable(eng._handle, 0)
+    assert lib.sipoc_profile_collect(eng._handle) == 0
+
 # --- benchmark-distribution chains (lqr_benchmark.cpp:61-96, :537-545) -----------
 SHAPES = [(4, 1, 16), (4, 1, 100), (6, 2, 32), (8, 3, 16), (12, 4, 50), (16, 4, 16),
           (5, 2, 7), (3, 3, 4), (32, 8, 6), (64, 24, 4)]
