@@ -46,15 +46,6 @@ namespace {
 constexpr int kGroup = 4;  // lanes per problem
 constexpr int kTile = 8;   // problems per warp
 
-// Warps per CTA of the sub-warp backward kernel (tuning knob, default 1).
-inline int backward_warps() {
-  static const int w = [] {
-    const char *e = getenv("SIPOC_BACKWARD_WARPS");
-    return e != nullptr ? atoi(e) : 1;
-  }();
-  return w;
-}
-
 __host__ __device__ constexpr int tri(int n) { return n * (n + 1) / 2; }
 // Column-major packed lower index, i >= j.
 __host__ __device__ constexpr int pk(int i, int j, int n) {
@@ -1187,8 +1178,7 @@ struct Plan {
   template <bool SOLVE, int W>
   static void launch_subwarp(const FastArgs &a, cudaStream_t s) {
     auto kern = riccati_backward_subwarp<N, M, SOLVE, W>;
-    static const int pad = getenv("SIPOC_SMEM_PAD") ? atoi(getenv("SIPOC_SMEM_PAD")) : 0;
-    const int bytes = Smem<N, M>::kBytes * W + pad;
+    constexpr int bytes = Smem<N, M>::kBytes * W;
     if (bytes > 48 * 1024)
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     const unsigned grid = static_cast<unsigned>((a.batch + kTile * W - 1) / (kTile * W));
@@ -1200,13 +1190,10 @@ struct Plan {
   template <bool SOLVE>
   static void backward(const FastArgs &a, cudaStream_t s) {
     if constexpr (SUBWARP) {
-      switch (backward_warps()) {
-        case 1: launch_subwarp<SOLVE, 1>(a, s); break;
-        case 2: launch_subwarp<SOLVE, 2>(a, s); break;
-        case 5: launch_subwarp<SOLVE, 5>(a, s); break;
-        case 4: launch_subwarp<SOLVE, 4>(a, s); break;
-        default: launch_subwarp<SOLVE, 1>(a, s); break;
-      }
+      // One warp (8 problems) per CTA: warps of different CTAs drift apart, so the
+      // DFMA-heavy and the latency-bound phases of different tiles overlap on an SM
+      // (measured: 1 warp / CTA 5.97 ms, 4 warps / CTA in lockstep 7.40 ms).
+      launch_subwarp<SOLVE, 1>(a, s);
     } else {
       const unsigned grid = static_cast<unsigned>((a.batch + 63) / 64);
       ProfScope ps(a.prof, "riccati_backward_thread", s);
@@ -1222,14 +1209,9 @@ struct Plan {
         <<<grid, THREADS, 0, s>>>(a.in, a.out, a.store, a.scratch, a.batch, a.ld, a.num_edges);
   }
   static void forward(const FastArgs &a, cudaStream_t s) {
-    static const int v = getenv("SIPOC_FWD_VARIANT") ? atoi(getenv("SIPOC_FWD_VARIANT")) : 0;
-    switch (v) {
-      case 1: launch_forward<128, 4>(a, s); break;
-      case 2: launch_forward<64, 10>(a, s); break;
-      case 3: launch_forward<64, 16>(a, s); break;
-      case 4: launch_forward<32, 24>(a, s); break;
-      default: launch_forward<128, 1>(a, s); break;
-    }
+    // 128 threads, no register cap: the compiler then hoists a whole stage's loads
+    // (254 registers), which is what keeps HBM busy (capped variants were slower).
+    launch_forward<128, 1>(a, s);
   }
   static int factor(const FastArgs &a, cudaStream_t s) {
     backward<false>(a, s);
