@@ -708,12 +708,12 @@ riccati_backward_thread(LqrIn in, int *status_out, double *store, double *scratc
   double W[tri(N)], v[N], dl[N];
 
   // V (packed lower), vv, delta of node k -> W, v, dl; stores W_k, v_k.
-  auto process_node = [&](int k, double (&V)[tri(N)], double (&vv)[N]) {
+  auto process_node = [&](int k, double (&V)[tri(N)], double (&vv)[N], const double (&dk)[N]) {
     double sd[N], sdi[N];
     bool d_ok = true;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      const double d = G(in.delta, k * N + i);
+      const double d = dk[i];
       d_ok = d_ok && (d > 0.0);
       dl[i] = d;
       sd[i] = sqrt(d);
@@ -772,33 +772,69 @@ riccati_backward_thread(LqrIn in, int *status_out, double *store, double *scratc
     }
   };
 
+  // Inputs of the stage to process next, fetched one stage ahead: the loads are issued
+  // in the middle of the previous stage (once its products are formed and their
+  // registers are free) and land while its factorizations run.
+  double nA[N * N], nB[N * M], nQ[tri(N)], nM[N * M], nR[tri(M)], nq[N], nr[M], nc[N], nd[N];
+  auto fetch_stage = [&](int k) {
+#pragma unroll
+    for (int t = 0; t < N * M; ++t) {
+      nB[t] = G(in.B, k * N * M + t);
+      nM[t] = G(in.M, k * N * M + t);
+    }
+#pragma unroll
+    for (int t = 0; t < N * N; ++t) nA[t] = G(in.A, k * N * N + t);
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+      for (int i = j; i < N; ++i) nQ[pk(i, j, N)] = G(in.Q, (k * N + j) * N + i);
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+      for (int i = j; i < M; ++i) nR[pk(i, j, M)] = G(in.R, (k * M + j) * M + i);
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      nd[i] = G(in.delta, k * N + i);
+      nq[i] = SOLVE ? G(in.q, k * N + i) : 0.0;
+      nc[i] = SOLVE ? G(in.c, (k + 1) * N + i) : 0.0;
+    }
+#pragma unroll
+    for (int a = 0; a < M; ++a) nr[a] = SOLVE ? G(in.r, k * M + a) : 0.0;
+  };
+
   {
-    double V[tri(N)], vv[N];
+    double V[tri(N)], vv[N], dT[N];
 #pragma unroll
     for (int j = 0; j < N; ++j)
 #pragma unroll
       for (int i = j; i < N; ++i) V[pk(i, j, N)] = G(in.Q, (T * N + j) * N + i);
 #pragma unroll
-    for (int i = 0; i < N; ++i) vv[i] = SOLVE ? G(in.q, T * N + i) : 0.0;
-    process_node(T, V, vv);
+    for (int i = 0; i < N; ++i) {
+      vv[i] = SOLVE ? G(in.q, T * N + i) : 0.0;
+      dT[i] = G(in.delta, T * N + i);
+    }
+    if (T > 0) fetch_stage(T - 1);
+    process_node(T, V, vv, dT);
   }
 
   for (int k = T - 1; k >= 0; --k) {
-    // Z = [B | A]
-    double Zm[N + M][N];
+    // Z = [B | A] and the rest of the stage, from the prefetch registers.
+    double Zm[N + M][N], dk[N];
 #pragma unroll
     for (int a = 0; a < M; ++a)
 #pragma unroll
-      for (int p = 0; p < N; ++p) Zm[a][p] = G(in.B, (k * M + a) * N + p);
+      for (int p = 0; p < N; ++p) Zm[a][p] = nB[a * N + p];
 #pragma unroll
     for (int j = 0; j < N; ++j)
 #pragma unroll
-      for (int p = 0; p < N; ++p) Zm[M + j][p] = G(in.A, (k * N + j) * N + p);
+      for (int p = 0; p < N; ++p) Zm[M + j][p] = nA[j * N + p];
+#pragma unroll
+    for (int i = 0; i < N; ++i) dk[i] = nd[i];
     double g[N];
     if (SOLVE) {
       double f[N];
 #pragma unroll
-      for (int i = 0; i < N; ++i) f[i] = dl[i] * v[i] - G(in.c, (k + 1) * N + i);
+      for (int i = 0; i < N; ++i) f[i] = dl[i] * v[i] - nc[i];
 #pragma unroll
       for (int i = 0; i < N; ++i) {
         double acc = 0.0;
@@ -824,21 +860,21 @@ riccati_backward_thread(LqrIn in, int *status_out, double *store, double *scratc
     for (int j = 0; j < M; ++j) {
 #pragma unroll
       for (int i = j; i < M; ++i) {
-        double acc = G(in.R, (k * M + j) * M + i);
+        double acc = nR[pk(i, j, M)];
 #pragma unroll
         for (int p = 0; p < N; ++p) acc += Zm[i][p] * Sm[j][p];
         Puu[pk(i, j, M)] = acc;
       }
 #pragma unroll
       for (int x = 0; x < N; ++x) {
-        double acc = G(in.M, (k * M + j) * N + x);
+        double acc = nM[j * N + x];
 #pragma unroll
         for (int p = 0; p < N; ++p) acc += Zm[M + x][p] * Sm[j][p];
         Pxu[j][x] = acc;
       }
       double acc = 0.0;
       if (SOLVE) {
-        acc = G(in.r, k * M + j);
+        acc = nr[j];
 #pragma unroll
         for (int p = 0; p < N; ++p) acc += Zm[j][p] * g[p];
       }
@@ -848,19 +884,20 @@ riccati_backward_thread(LqrIn in, int *status_out, double *store, double *scratc
     for (int j = 0; j < N; ++j) {
 #pragma unroll
       for (int i = j; i < N; ++i) {
-        double acc = G(in.Q, (k * N + j) * N + i);
+        double acc = nQ[pk(i, j, N)];
 #pragma unroll
         for (int p = 0; p < N; ++p) acc += Zm[M + i][p] * Sm[M + j][p];
         Pxx[pk(i, j, N)] = acc;
       }
       double acc = 0.0;
       if (SOLVE) {
-        acc = G(in.q, k * N + j);
+        acc = nq[j];
 #pragma unroll
         for (int p = 0; p < N; ++p) acc += Zm[M + j][p] * g[p];
       }
       wx[j] = acc;
     }
+    if (k > 0) fetch_stage(k - 1);  // products formed: their registers take the next stage
     // Cholesky of G
     double dg[M];
     bool g_ok = true;
@@ -959,7 +996,7 @@ riccati_backward_thread(LqrIn in, int *status_out, double *store, double *scratc
       }
       vv[j] = t;
     }
-    process_node(k, Pxx, vv);
+    process_node(k, Pxx, vv, dk);
   }
   if (status_out != nullptr) status_out[b] = status;
 #undef G
@@ -1123,37 +1160,92 @@ rollout_forward(LqrIn in, LqrOut out, const double *store, const double *scratch
       stcs(yo + static_cast<size_t>(i) * L_, vv[i] - wf[i]);
     }
   }
+  // Small shapes (the whole stage fits the register file twice): operands of stage
+  // k + 1 are fetched while stage k is computed — none of them depends on x, so the
+  // only exposed latency is the first stage's.  Large shapes rely on the compiler
+  // hoisting a stage's loads (HBM-bound at 254 registers already).
+  constexpr bool PREFETCH = (N * N + 2 * N * M + tri(N) + 3 * N + M) <= 64;
+  constexpr int PA = PREFETCH ? N * N : 1, PB = PREFETCH ? N * M : 1, PW = PREFETCH ? tri(N) : 1,
+                PN = PREFETCH ? N : 1, PM = PREFETCH ? M : 1;
+  double nA[PA], nB[PB], nK[PB], nW[PW], nv[PN], nd[PN], nc[PN], nk[PM];
+  auto fetch = [&](int k) {
+    if constexpr (PREFETCH) {
+#pragma unroll
+      for (int t = 0; t < N * N; ++t) nA[t] = G(in.A, k * N * N + t);
+#pragma unroll
+      for (int t = 0; t < N * M; ++t) {
+        nB[t] = G(in.B, k * N * M + t);
+        nK[t] = G(Kst, k * N * M + t);
+      }
+#pragma unroll
+      for (int t = 0; t < tri(N); ++t) nW[t] = G(Wst, (k + 1) * tri(N) + t);
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        nv[i] = G(vst, (k + 1) * N + i);
+        nd[i] = G(in.delta, (k + 1) * N + i);
+        nc[i] = G(in.c, (k + 1) * N + i);
+      }
+#pragma unroll
+      for (int a = 0; a < M; ++a) nk[a] = G(kst, k * M + a);
+    }
+  };
+  if (T > 0) fetch(0);
   for (int k = 0; k < T; ++k) {
+    double cA[PA], cB[PB], cK[PB], cW[PW], cv[PN], cd[PN], cc[PN], ck[PM];
+    if constexpr (PREFETCH) {
+#pragma unroll
+      for (int t = 0; t < N * N; ++t) cA[t] = nA[t];
+#pragma unroll
+      for (int t = 0; t < N * M; ++t) {
+        cB[t] = nB[t];
+        cK[t] = nK[t];
+      }
+#pragma unroll
+      for (int t = 0; t < tri(N); ++t) cW[t] = nW[t];
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        cv[i] = nv[i];
+        cd[i] = nd[i];
+        cc[i] = nc[i];
+      }
+#pragma unroll
+      for (int a = 0; a < M; ++a) ck[a] = nk[a];
+      if (k + 1 < T) fetch(k + 1);
+    }
     double u[M];
 #pragma unroll
-    for (int a = 0; a < M; ++a) u[a] = G(kst, k * M + a);
+    for (int a = 0; a < M; ++a) u[a] = PREFETCH ? ck[a] : G(kst, k * M + a);
 #pragma unroll
     for (int j = 0; j < N; ++j)
 #pragma unroll
-      for (int a = 0; a < M; ++a) u[a] += G(Kst, (k * N + j) * M + a) * x[j];
+      for (int a = 0; a < M; ++a)
+        u[a] += (PREFETCH ? cK[j * M + a] : G(Kst, (k * N + j) * M + a)) * x[j];
 #pragma unroll
     for (int a = 0; a < M; ++a) stcs(uo + static_cast<size_t>(k * M + a) * L_, u[a]);
     double f[N], vv[N], dd[N], wf[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      vv[i] = G(vst, (k + 1) * N + i);
-      dd[i] = G(in.delta, (k + 1) * N + i);
-      f[i] = G(in.c, (k + 1) * N + i) - dd[i] * vv[i];
+      vv[i] = PREFETCH ? cv[i] : G(vst, (k + 1) * N + i);
+      dd[i] = PREFETCH ? cd[i] : G(in.delta, (k + 1) * N + i);
+      f[i] = (PREFETCH ? cc[i] : G(in.c, (k + 1) * N + i)) - dd[i] * vv[i];
       wf[i] = 0.0;
     }
 #pragma unroll
     for (int j = 0; j < N; ++j)
 #pragma unroll
-      for (int i = 0; i < N; ++i) f[i] += G(in.A, (k * N + j) * N + i) * x[j];
+      for (int i = 0; i < N; ++i)
+        f[i] += (PREFETCH ? cA[j * N + i] : G(in.A, (k * N + j) * N + i)) * x[j];
 #pragma unroll
     for (int a = 0; a < M; ++a)
 #pragma unroll
-      for (int i = 0; i < N; ++i) f[i] += G(in.B, (k * M + a) * N + i) * u[a];
+      for (int i = 0; i < N; ++i)
+        f[i] += (PREFETCH ? cB[a * N + i] : G(in.B, (k * M + a) * N + i)) * u[a];
 #pragma unroll
     for (int j = 0; j < N; ++j)
 #pragma unroll
       for (int i = j; i < N; ++i) {
-        const double w = G(Wst, (k + 1) * tri(N) + pk(i, j, N));
+        const double w =
+            PREFETCH ? cW[pk(i, j, N)] : G(Wst, (k + 1) * tri(N) + pk(i, j, N));
         wf[i] += w * f[j];
         if (i != j) wf[j] += w * f[i];
       }
