@@ -86,18 +86,23 @@ __device__ __forceinline__ void stcs(double *p, double v) { __stcs(p, v); }
 template <int N, int M>
 struct Smem {
   static constexpr int NZ = N + M;
-  static constexpr int rZ = 0;                // [B | A], column-major, N rows per column
-  static constexpr int rQ = rZ + NZ * N;      // Q_k, packed lower
-  static constexpr int rM = rQ + tri(N);      // M_k, N x M column-major
-  static constexpr int rR = rM + N * M;       // R_k, packed lower
+  // Column pitch of every array whose columns are read by different lanes of a problem
+  // at the same time (Z, M, W, Psi_xu): an ODD number of 64-byte rows, so the four
+  // lanes' rows alternate between the two halves of the 32 banks (pitch N = 12 put them
+  // all in one half: 4 wavefronts per load instead of 2).
+  static constexpr int P = (N % 2 == 0) ? N + 1 : N;
+  static constexpr int rZ = 0;                // [B | A], column-major, pitch P
+  static constexpr int rQ = rZ + NZ * P;      // Q_k, packed lower
+  static constexpr int rM = rQ + tri(N);      // M_k, N x M column-major, pitch P
+  static constexpr int rR = rM + M * P;       // R_k, packed lower
   static constexpr int rq = rR + tri(M);      // q_k
   static constexpr int rr = rq + N;           // r_k
   static constexpr int rc = rr + M;           // c_{k+1}
   static constexpr int rd = rc + N;           // delta_k (as staged)
   static constexpr int kStaged = rd + N;
-  static constexpr int rW = kStaged;          // W of the last processed node, full N x N
-  static constexpr int rG = rW + N * N;        // g
-  static constexpr int rV = rG + N;           // v of the last processed node
+  static constexpr int rW = kStaged;          // W of the last processed node, full, pitch P
+  static constexpr int rG = rc;               // g overwrites c (dead once f is formed)
+  static constexpr int rV = rW + N * P;       // v of the last processed node
   static constexpr int rDl = rV + N;          // delta of the last processed node
   static constexpr int rSd = rDl + N;         // sqrt(delta), 1/sqrt(delta) of the node in flight
   static constexpr int rSdi = rSd + N;
@@ -107,9 +112,9 @@ struct Smem {
   static constexpr int rX = rQ;
   static constexpr int xGuu = rX;
   static constexpr int xPxu = xGuu + tri(M);
-  static constexpr int xH = xPxu + N * M;
+  static constexpr int xH = xPxu + M * P;
   static constexpr int xLam = xPxu;
-  static_assert(tri(M) + N * M + M <= tri(N) + N * M + tri(M), "exchange region fits");
+  static_assert(tri(M) + M * P + M <= tri(N) + M * P + tri(M), "exchange region fits");
   static constexpr int kRows = rSdi + N;
   static constexpr int kBytes = kRows * kTile * int(sizeof(double));
 };
@@ -122,6 +127,22 @@ __device__ __forceinline__ void stage_run(double *dst, const double *src, int64_
 #pragma unroll
   for (int i0 = 0; i0 < count; i0 += 8) {
     if (i0 + 8 <= count || i0 + rr < count) cp_async16(dst + i0 * kTile, src);
+    src += ld8;
+  }
+}
+
+// `count` consecutive flat elements of a column-major block with N rows per column
+// -> shared-memory columns of pitch N + 1 (even N) rows.
+template <int N>
+__device__ __forceinline__ void stage_cols(double *dst0, const double *src, int64_t ld8,
+                                           int count, int lane) {
+  constexpr int P = (N % 2 == 0) ? N + 1 : N;
+  const int sub = lane & 3, rr = lane >> 2;
+#pragma unroll
+  for (int i0 = 0; i0 < count; i0 += 8) {
+    const int e = i0 + rr;
+    const int row = e + (P - N) * (e / N);
+    if (i0 + 8 <= count || e < count) cp_async16(dst0 + row * kTile + sub * 2, src);
     src += ld8;
   }
 }
@@ -209,8 +230,8 @@ riccati_backward_subwarp(LqrIn in, int *status_out, double *store, double *scrat
       pq -= static_cast<int64_t>(N) * ld;
     }
     if (with_edge) {
-      stage_run(sdst + S::rZ * kTile, pB, ld8, N * M, rr);
-      stage_run(sdst + (S::rZ + N * M) * kTile, pA, ld8, N * N, rr);
+      stage_cols<N>(sm + S::rZ * kTile, pB, ld8, N * M, lane);
+      stage_cols<N>(sm + (S::rZ + M * S::P) * kTile, pA, ld8, N * N, lane);
       pB -= static_cast<int64_t>(N) * M * ld;
       pA -= static_cast<int64_t>(N) * N * ld;
       if (SOLVE) {
@@ -228,7 +249,7 @@ riccati_backward_subwarp(LqrIn in, int *status_out, double *store, double *scrat
     stage_lower<N>(sdst + S::rQ * kTile, pQ, ld, ld8, rr);
     pQ -= static_cast<int64_t>(N) * N * ld;
     if (with_edge) {
-      stage_run(sdst + S::rM * kTile, pM, ld8, N * M, rr);
+      stage_cols<N>(sm + S::rM * kTile, pM, ld8, N * M, lane);
       stage_lower<M>(sdst + S::rR * kTile, pR, ld, ld8, rr);
       pM -= static_cast<int64_t>(N) * M * ld;
       pR -= static_cast<int64_t>(M) * M * ld;
@@ -294,11 +315,12 @@ riccati_backward_subwarp(LqrIn in, int *status_out, double *store, double *scrat
         double f[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) f[i] = SM(S::rDl + i) * SM(S::rV + i) - SM(S::rc + i);
+        __syncwarp();  // g is written over c
 #pragma unroll
         for (int s = 0; s < SX; ++s) {
           double acc = 0.0;
 #pragma unroll
-          for (int q = 0; q < N; ++q) acc += SM(S::rW + q * N + xj[s]) * f[q];  // W' symmetric
+          for (int q = 0; q < N; ++q) acc += SM(S::rW + q * S::P + xj[s]) * f[q];  // W' symmetric
           if (xok[s]) SM(S::rG + xj[s]) = SM(S::rV + xj[s]) - acc;
         }
       }
@@ -307,11 +329,11 @@ riccati_backward_subwarp(LqrIn in, int *status_out, double *store, double *scrat
 #pragma unroll
       for (int s = 0; s < SU; ++s)
 #pragma unroll
-        for (int q = 0; q < N; ++q) zu[s][q] = SM(S::rZ + uj[s] * N + q);
+        for (int q = 0; q < N; ++q) zu[s][q] = SM(S::rZ + uj[s] * S::P + q);
 #pragma unroll
       for (int s = 0; s < SX; ++s)
 #pragma unroll
-        for (int q = 0; q < N; ++q) zx[s][q] = SM(S::rZ + (M + xj[s]) * N + q);
+        for (int q = 0; q < N; ++q) zx[s][q] = SM(S::rZ + (M + xj[s]) * S::P + q);
       __syncwarp();  // g complete; every lane is done with v', delta'
 
       update_delta();  // node k
@@ -354,7 +376,7 @@ riccati_backward_subwarp(LqrIn in, int *status_out, double *store, double *scrat
       for (int q = 0; q < H; ++q) wpre[q] = sm[(S::rW + q) * kTile + prob];
 #pragma unroll 1
       for (int p = 0; p < N; ++p) {
-        const double *wrow = sm + (S::rW + p * N) * kTile + prob;
+        const double *wrow = sm + (S::rW + p * S::P) * kTile + prob;
         const double *zrow = sm + (S::rZ + p) * kTile + prob;
         double wlate[N - H];
 #pragma unroll
@@ -380,7 +402,7 @@ riccati_backward_subwarp(LqrIn in, int *status_out, double *store, double *scrat
           }
         }
         {  // prefetch the head of the next row (row 0 again on the last iteration)
-          const double *wnext = sm + (S::rW + (p + 1 < N ? p + 1 : 0) * N) * kTile + prob;
+          const double *wnext = sm + (S::rW + (p + 1 < N ? p + 1 : 0) * S::P) * kTile + prob;
 #pragma unroll
           for (int q = 0; q < H; ++q) wpre[q] = wnext[q * kTile];
         }
@@ -405,14 +427,14 @@ riccati_backward_subwarp(LqrIn in, int *status_out, double *store, double *scrat
         for (int s = 0; s < SX; ++s) sx[s] += sx2[s];
 #pragma unroll
         for (int i = 0; i < M; ++i) {  // B(p, i)
-          const double z = zrow[i * N * kTile];
+          const double z = zrow[i * S::P * kTile];
 #pragma unroll
           for (int s = 0; s < SU; ++s)
             if (i >= kGroup * s) Puu[s][i] += z * su[s];
         }
 #pragma unroll
         for (int x = 0; x < N; ++x) {  // A(p, x)
-          const double z = zrow[(M + x) * N * kTile];
+          const double z = zrow[(M + x) * S::P * kTile];
 #pragma unroll
           for (int s = 0; s < SU; ++s) Pxu[s][x] += z * su[s];
 #pragma unroll
@@ -425,7 +447,7 @@ riccati_backward_subwarp(LqrIn in, int *status_out, double *store, double *scrat
 #pragma unroll
         for (int i = kGroup * s; i < M; ++i) Puu[s][i] += SM(S::rR + rcol[s] + i);
 #pragma unroll
-        for (int x = 0; x < N; ++x) Pxu[s][x] += SM(S::rM + uj[s] * N + x);
+        for (int x = 0; x < N; ++x) Pxu[s][x] += SM(S::rM + uj[s] * S::P + x);
         if (SOLVE) hu[s] += SM(S::rr + uj[s]);
       }
 #pragma unroll
@@ -443,7 +465,7 @@ riccati_backward_subwarp(LqrIn in, int *status_out, double *store, double *scrat
           for (int i = kGroup * s; i < M; ++i)
             if (i >= uj[s]) SM(S::xGuu + rcol[s] + i) = Puu[s][i];
 #pragma unroll
-          for (int x = 0; x < N; ++x) SM(S::xPxu + uj[s] * N + x) = Pxu[s][x];
+          for (int x = 0; x < N; ++x) SM(S::xPxu + uj[s] * S::P + x) = Pxu[s][x];
           if (SOLVE) SM(S::xH + uj[s]) = hu[s];
         }
       }
@@ -538,14 +560,14 @@ riccati_backward_subwarp(LqrIn in, int *status_out, double *store, double *scrat
       for (int s = 0; s < SX; ++s) {
 #pragma unroll
         for (int a = 0; a < M; ++a) {
-          double t = SM(S::xPxu + a * N + xj[s]);
+          double t = SM(S::xPxu + a * S::P + xj[s]);
 #pragma unroll
           for (int c = 0; c < a; ++c) t -= lam[s][c] * Lg[pk(a, c, M)];
           lam[s][a] = t * dg[a];
         }
         if (xok[s]) {
 #pragma unroll
-          for (int a = 0; a < M; ++a) SM(S::xLam + a * N + xj[s]) = lam[s][a];
+          for (int a = 0; a < M; ++a) SM(S::xLam + a * S::P + xj[s]) = lam[s][a];
         }
         // K(:, xj) = -L_G^-T Lambda(xj, :)'
         double kap[M];
@@ -575,7 +597,7 @@ riccati_backward_subwarp(LqrIn in, int *status_out, double *store, double *scrat
         for (int i = kGroup * s; i < N; ++i) {
           double t = V[s][i];
 #pragma unroll
-          for (int a = 0; a < M; ++a) t -= SM(S::xLam + a * N + i) * lam[s][a];
+          for (int a = 0; a < M; ++a) t -= SM(S::xLam + a * S::P + i) * lam[s][a];
           V[s][i] = t;
         }
         if (SOLVE) {
@@ -671,8 +693,8 @@ riccati_backward_subwarp(LqrIn in, int *status_out, double *store, double *scrat
       for (int i = kGroup * s; i < N; ++i) {
         const double w = SM(S::rSdi + i) * ((i == xj[s] ? 1.0 : 0.0) - y[i]) * sdio[s];
         if (xok[s] && i >= xj[s]) {
-          SM(S::rW + xj[s] * N + i) = w;
-          SM(S::rW + i * N + xj[s]) = w;
+          SM(S::rW + xj[s] * S::P + i) = w;
+          SM(S::rW + i * S::P + xj[s]) = w;
           if (valid) stcs(dst, w);
         }
         dst += ld;
