@@ -727,7 +727,8 @@ template <int N, int M>
 const FastPlan *make_cta_plan(const char *name) {
   using P = CtaPlan<N, M>;
   static const FastPlan plan{name,         N,           M,         &P::store_elems,
-                             &P::scratch_elems, &P::factor, &P::solve, &P::factor_solve};
+                             &P::scratch_elems, &P::factor, &P::solve, &P::factor_solve,
+                             nullptr};
   return &plan;
 }
 

@@ -1282,6 +1282,276 @@ rollout_forward(LqrIn in, LqrOut out, const double *store, const double *scratch
 }
 
 // ===========================================================================
+// Newton-KKT solve against a kept factorization, uniform chains (helpers.cpp:749-894):
+// the rhs build is fused into the backward affine sweep and the dual recovery into the
+// forward rollout, which writes the flat [x | y | z] solution directly.
+// One thread per problem; constraint dimensions are runtime (per node / per edge).
+// ===========================================================================
+struct KktView {
+  DevTables t;
+  KktModel mdl;
+  KktWs ws;
+  const double *b;
+  double *sol;
+};
+
+template <int N, int M>
+__global__ void __launch_bounds__(128)
+affine_backward_kkt(KktView kv, const double *store, double *scratch, int64_t batch, int64_t ld,
+                    int T) {
+  using Z = FastSizes<N, M>;
+  const int64_t b = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  const size_t L_ = static_cast<size_t>(ld);
+  const DevTables &t = kv.t;
+#define G(ptr, e) __ldg((ptr) + static_cast<size_t>(e) * L_ + b)
+  const double *Wst = store + Z::oW(T) * ld;
+  const double *Kst = store + Z::oK(T) * ld;
+  const double *Gst = store + Z::oG(T) * ld;
+  double *vst = scratch + Z::ov(T) * ld + b;
+  double *kst = scratch + Z::ok(T) * ld + b;
+  const int xd = t.x_dim, yd = t.y_dim;
+
+  // q_mod of node k (node part): -b_x - Jc' Lc b_yc - Jg' Lg b_z      (helpers.cpp:752-778)
+  auto node_q = [&](int k, double (&qv)[N]) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) qv[i] = -G(kv.b, t.x_state[k] + i);
+    const int c = t.node_c[k], g = t.node_g[k];
+    for (int r = 0; r < c; ++r) {
+      const double wr = G(kv.ws.node_c_r2_inv, t.node_c_off[k] + r) * G(kv.b, xd + t.y_node_c[k] + r);
+#pragma unroll
+      for (int i = 0; i < N; ++i) qv[i] -= G(kv.mdl.node_jc, t.jc_node_off[k] + r + i * c) * wr;
+    }
+    for (int r = 0; r < g; ++r) {
+      const double wr =
+          G(kv.ws.node_mod_w_inv, t.node_g_off[k] + r) * G(kv.b, xd + yd + t.z_node[k] + r);
+#pragma unroll
+      for (int i = 0; i < N; ++i) qv[i] -= G(kv.mdl.node_jg, t.jg_node_off[k] + r + i * g) * wr;
+    }
+  };
+  // edge part of q_mod[parent] and r_mod of edge e                      (helpers.cpp:780-812)
+  auto edge_qr = [&](int e, double (&qv)[N], double (&rv)[M]) {
+#pragma unroll
+    for (int a = 0; a < M; ++a) rv[a] = -G(kv.b, t.x_control[e] + a);
+    const int c = t.edge_c[e], g = t.edge_g[e];
+    for (int r = 0; r < c; ++r) {
+      const double wr = G(kv.ws.edge_c_r2_inv, t.edge_c_off[e] + r) * G(kv.b, xd + t.y_edge_c[e] + r);
+#pragma unroll
+      for (int i = 0; i < N; ++i) qv[i] -= G(kv.mdl.edge_jcx, t.jcx_off[e] + r + i * c) * wr;
+#pragma unroll
+      for (int a = 0; a < M; ++a) rv[a] -= G(kv.mdl.edge_jcu, t.jcu_off[e] + r + a * c) * wr;
+    }
+    for (int r = 0; r < g; ++r) {
+      const double wr =
+          G(kv.ws.edge_mod_w_inv, t.edge_g_off[e] + r) * G(kv.b, xd + yd + t.z_edge[e] + r);
+#pragma unroll
+      for (int i = 0; i < N; ++i) qv[i] -= G(kv.mdl.edge_jgx, t.jgx_off[e] + r + i * g) * wr;
+#pragma unroll
+      for (int a = 0; a < M; ++a) rv[a] -= G(kv.mdl.edge_jgu, t.jgu_off[e] + r + a * g) * wr;
+    }
+  };
+
+  double v[N];
+  node_q(T, v);
+#pragma unroll
+  for (int i = 0; i < N; ++i) stcs(vst + static_cast<int64_t>(T * N + i) * ld, v[i]);
+  for (int k = T - 1; k >= 0; --k) {
+    double wv[tri(N)], f[N], g[N];
+#pragma unroll
+    for (int u = 0; u < tri(N); ++u) wv[u] = G(Wst, (k + 1) * tri(N) + u);
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      // c_mod = -b_ydyn (helpers.cpp:777), delta = dyn_r2
+      f[i] = G(kv.ws.dyn_r2, (k + 1) * N + i) * v[i] + G(kv.b, xd + t.y_dyn[k + 1] + i);
+      g[i] = v[i];
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+      for (int i = j; i < N; ++i) {
+        const double w = wv[pk(i, j, N)];
+        g[i] -= w * f[j];
+        if (i != j) g[j] -= w * f[i];
+      }
+    double qv[N], rv[M];
+    node_q(k, qv);
+    edge_qr(k, qv, rv);
+    double bv[N * M], kvv[N * M], gv[tri(M)];
+#pragma unroll
+    for (int u = 0; u < N * M; ++u) {
+      bv[u] = G(kv.mdl.edge_B, k * N * M + u);
+      kvv[u] = G(Kst, k * N * M + u);
+    }
+#pragma unroll
+    for (int u = 0; u < tri(M); ++u) gv[u] = G(Gst, k * tri(M) + u);
+    double h[M], kk[M];
+#pragma unroll
+    for (int a = 0; a < M; ++a) {
+      double acc = rv[a];
+#pragma unroll
+      for (int p = 0; p < N; ++p) acc += bv[a * N + p] * g[p];
+      h[a] = acc;
+      kk[a] = 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+      for (int i = j; i < M; ++i) {
+        const double gi = gv[pk(i, j, M)];
+        kk[i] -= gi * h[j];
+        if (i != j) kk[j] -= gi * h[i];
+      }
+#pragma unroll
+    for (int a = 0; a < M; ++a) stcs(kst + static_cast<int64_t>(k * M + a) * ld, kk[a]);
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      double acc = qv[j];
+#pragma unroll
+      for (int p = 0; p < N; ++p) acc += G(kv.mdl.edge_A, (k * N + j) * N + p) * g[p];
+#pragma unroll
+      for (int a = 0; a < M; ++a) acc += kvv[j * M + a] * h[a];
+      v[j] = acc;
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) stcs(vst + static_cast<int64_t>(k * N + i) * ld, v[i]);
+  }
+#undef G
+}
+
+template <int N, int M>
+__global__ void __launch_bounds__(128)
+rollout_forward_kkt(KktView kv, const double *store, const double *scratch, int64_t batch,
+                    int64_t ld, int T) {
+  using Z = FastSizes<N, M>;
+  const int64_t b = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  const size_t L_ = static_cast<size_t>(ld);
+  const DevTables &t = kv.t;
+#define G(ptr, e) __ldg((ptr) + static_cast<size_t>(e) * L_ + b)
+#define SOL(e) kv.sol[static_cast<size_t>(e) * L_ + b]
+  const double *Wst = store + Z::oW(T) * ld;
+  const double *Kst = store + Z::oK(T) * ld;
+  const double *vst = scratch + Z::ov(T) * ld;
+  const double *kst = scratch + Z::ok(T) * ld;
+  const int xd = t.x_dim, yd = t.y_dim;
+
+  // y_c = Lc (Jc x - b_yc), z = Lg (Jg x - b_z) of node k                (helpers.cpp:828-856)
+  auto recover_node = [&](int k, const double (&x)[N]) {
+    const int c = t.node_c[k], g = t.node_g[k];
+    for (int r = 0; r < c; ++r) {
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < N; ++j) s += G(kv.mdl.node_jc, t.jc_node_off[k] + r + j * c) * x[j];
+      s -= G(kv.b, xd + t.y_node_c[k] + r);
+      SOL(xd + t.y_node_c[k] + r) = G(kv.ws.node_c_r2_inv, t.node_c_off[k] + r) * s;
+    }
+    for (int r = 0; r < g; ++r) {
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < N; ++j) s += G(kv.mdl.node_jg, t.jg_node_off[k] + r + j * g) * x[j];
+      s -= G(kv.b, xd + yd + t.z_node[k] + r);
+      SOL(xd + yd + t.z_node[k] + r) = G(kv.ws.node_mod_w_inv, t.node_g_off[k] + r) * s;
+    }
+  };
+  // the same for the constraints of edge e (parent state x, control u)    (helpers.cpp:858-893)
+  auto recover_edge = [&](int e, const double (&x)[N], const double (&u)[M]) {
+    const int c = t.edge_c[e], g = t.edge_g[e];
+    for (int r = 0; r < c; ++r) {
+      double s = 0.0, s2 = 0.0;
+#pragma unroll
+      for (int j = 0; j < N; ++j) s += G(kv.mdl.edge_jcx, t.jcx_off[e] + r + j * c) * x[j];
+#pragma unroll
+      for (int a = 0; a < M; ++a) s2 += G(kv.mdl.edge_jcu, t.jcu_off[e] + r + a * c) * u[a];
+      s += s2;
+      s -= G(kv.b, xd + t.y_edge_c[e] + r);
+      SOL(xd + t.y_edge_c[e] + r) = G(kv.ws.edge_c_r2_inv, t.edge_c_off[e] + r) * s;
+    }
+    for (int r = 0; r < g; ++r) {
+      double s = 0.0, s2 = 0.0;
+#pragma unroll
+      for (int j = 0; j < N; ++j) s += G(kv.mdl.edge_jgx, t.jgx_off[e] + r + j * g) * x[j];
+#pragma unroll
+      for (int a = 0; a < M; ++a) s2 += G(kv.mdl.edge_jgu, t.jgu_off[e] + r + a * g) * u[a];
+      s += s2;
+      s -= G(kv.b, xd + yd + t.z_edge[e] + r);
+      SOL(xd + yd + t.z_edge[e] + r) = G(kv.ws.edge_mod_w_inv, t.edge_g_off[e] + r) * s;
+    }
+  };
+
+  double x[N];
+  {  // root
+    double f[N], wf[N], vv[N], dd[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      vv[i] = G(vst, i);
+      dd[i] = G(kv.ws.dyn_r2, i);
+      f[i] = dd[i] * vv[i] + G(kv.b, xd + t.y_dyn[0] + i);  // delta o v - c, c = -b_ydyn
+      wf[i] = 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+      for (int i = j; i < N; ++i) {
+        const double w = G(Wst, pk(i, j, N));
+        wf[i] += w * f[j];
+        if (i != j) wf[j] += w * f[i];
+      }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      x[i] = dd[i] * wf[i] - f[i];
+      SOL(t.x_state[0] + i) = x[i];
+      SOL(xd + t.y_dyn[0] + i) = vv[i] - wf[i];
+    }
+  }
+  for (int k = 0; k < T; ++k) {
+    double u[M];
+#pragma unroll
+    for (int a = 0; a < M; ++a) u[a] = G(kst, k * M + a);
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+      for (int a = 0; a < M; ++a) u[a] += G(Kst, (k * N + j) * M + a) * x[j];
+#pragma unroll
+    for (int a = 0; a < M; ++a) SOL(t.x_control[k] + a) = u[a];
+    recover_node(k, x);
+    recover_edge(k, x, u);
+    double f[N], vv[N], dd[N], wf[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      vv[i] = G(vst, (k + 1) * N + i);
+      dd[i] = G(kv.ws.dyn_r2, (k + 1) * N + i);
+      f[i] = -G(kv.b, xd + t.y_dyn[k + 1] + i) - dd[i] * vv[i];  // c' - delta' o v'
+      wf[i] = 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+      for (int i = 0; i < N; ++i) f[i] += G(kv.mdl.edge_A, (k * N + j) * N + i) * x[j];
+#pragma unroll
+    for (int a = 0; a < M; ++a)
+#pragma unroll
+      for (int i = 0; i < N; ++i) f[i] += G(kv.mdl.edge_B, (k * M + a) * N + i) * u[a];
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+      for (int i = j; i < N; ++i) {
+        const double w = G(Wst, (k + 1) * tri(N) + pk(i, j, N));
+        wf[i] += w * f[j];
+        if (i != j) wf[j] += w * f[i];
+      }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      x[i] = f[i] - dd[i] * wf[i];
+      SOL(t.x_state[k + 1] + i) = x[i];
+      SOL(xd + t.y_dyn[k + 1] + i) = vv[i] + wf[i];
+    }
+  }
+  recover_node(T, x);
+#undef SOL
+#undef G
+}
+
+// ===========================================================================
 // Plans
 // ===========================================================================
 template <int N, int M, bool SUBWARP>
@@ -1346,13 +1616,29 @@ struct Plan {
     forward(a, s);
     return 2;
   }
+  static int kkt_solve(const FastKktArgs &k, cudaStream_t s) {
+    const unsigned grid = static_cast<unsigned>((k.batch + 127) / 128);
+    const KktView view{*k.tables, *k.model, *k.ws, k.b, k.sol};
+    {
+      ProfScope ps(k.prof, "affine_backward_kkt", s);
+      affine_backward_kkt<N, M>
+          <<<grid, 128, 0, s>>>(view, k.store, k.scratch, k.batch, k.ld, k.num_edges);
+    }
+    {
+      ProfScope ps(k.prof, "rollout_forward_kkt", s);
+      rollout_forward_kkt<N, M>
+          <<<grid, 128, 0, s>>>(view, k.store, k.scratch, k.batch, k.ld, k.num_edges);
+    }
+    return 2;
+  }
 };
 
 template <int N, int M, bool SUBWARP>
 const FastPlan *make_plan(const char *name) {
   using P = Plan<N, M, SUBWARP>;
   static const FastPlan plan{name,         N,           M,         &P::store_elems,
-                             &P::scratch_elems, &P::factor, &P::solve, &P::factor_solve};
+                             &P::scratch_elems, &P::factor, &P::solve, &P::factor_solve,
+                             &P::kkt_solve};
   return &plan;
 }
 

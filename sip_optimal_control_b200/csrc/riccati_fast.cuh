@@ -26,6 +26,20 @@ struct FastArgs {
   Profiler *prof;   // per-kernel event timing (may be disabled)
 };
 
+// Newton-KKT solve against the plan's kept factorization (uniform chains).
+struct FastKktArgs {
+  const DevTables *tables;
+  const KktModel *model;
+  const KktWs *ws;   // weights and dyn_r2 written by the reduction
+  const double *b;   // rhs,      [x | y | z], engine layout
+  double *sol;       // solution, [x | y | z], engine layout
+  const double *store;
+  double *scratch;
+  int64_t batch, ld;
+  int num_edges;
+  Profiler *prof;
+};
+
 struct FastPlan {
   const char *name;
   int n, m;
@@ -36,6 +50,8 @@ struct FastPlan {
   int (*factor)(const FastArgs &, cudaStream_t);
   int (*solve)(const FastArgs &, cudaStream_t);
   int (*factor_solve)(const FastArgs &, cudaStream_t);
+  // Fused rhs build + affine sweep, rollout + dual recovery; nullptr = not provided.
+  int (*kkt_solve)(const FastKktArgs &, cudaStream_t);
 };
 
 // nullptr when no specialised kernel exists for (n, m).

@@ -155,3 +155,21 @@ def test_host_buffer_entry_points():
     assert rel_err(sol, ref["sol"]).max() < REL_TOL
     prod = cp.add_Kx_to_y_host(w, r1, r2, r3, sol)
     assert (np.linalg.norm(prod - rhs, axis=1) / np.linalg.norm(rhs, axis=1)).max() < 1e-9
+
+
+def test_fused_kkt_solve_path_large_batch():
+    """Above the dispatch threshold the uniform-chain solve runs the fused kernels (rhs
+    build inside the affine sweep, dual recovery inside the rollout); same parity bar."""
+    n, m, T, batch = 4, 1, 6, 32768 + 5
+    s = _uniform_kkt_structure(n, m, T)
+    model, w, r1, r2, r3, rhs = pg.newton_kkt_batch(s, batch, seed=21, r2_max=1e3)
+    sample = np.r_[0:64, batch - 64:batch]
+    sub = lambda a: a[sample]
+    ref = pyoracle.kkt_factor_solve(s, {k: sub(v) for k, v in model.items()}, sub(w), sub(r1),
+                                    sub(r2), sub(r3), sub(rhs))
+    gpu, cp, dev = _gpu_kkt(s, model, w, r1, r2, r3, rhs)
+    assert "generic" not in cp.engine.kernel_variant
+    assert gpu["ok"].all()
+    assert rel_err(gpu["sol"][sample], ref["sol"]).max() < 1e-9
+    scale = np.linalg.norm(rhs, axis=1)
+    assert (gpu["residual"] / scale).max() < 1e-9
