@@ -155,12 +155,11 @@ __device__ void cta_matvec(double *y, const double *base, const double *A, int l
   }
 }
 
-// Cholesky factor L (packed lower) of the 8 x 8 block at `blk` and X = L^-1, in
-// registers.  Returns false when a pivot is <= 0.
-__device__ __forceinline__ bool chol8_and_inverse(const double *blk, int ld, double (&L)[36],
-                                                  double (&X)[36]) {
+// Cholesky factor L (packed lower, diagonal included) of the 8 x 8 block at `blk`, in
+// registers; d[j] = 1 / L(j, j).  Right-looking, so the dependent chain per column is
+// rsqrt -> mul -> one FMA.  Returns false when a pivot is <= 0.
+__device__ __forceinline__ bool chol8(const double *blk, int ld, double (&L)[36], double (&d)[8]) {
   bool ok = true;
-  double d[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
 #pragma unroll
@@ -169,25 +168,26 @@ __device__ __forceinline__ bool chol8_and_inverse(const double *blk, int ld, dou
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    double x = L[pk(j, j, 8)];
-#pragma unroll
-    for (int p = 0; p < 8; ++p)
-      if (p < j) x -= L[pk(j, p, 8)] * L[pk(j, p, 8)];
+    const double x = L[pk(j, j, 8)];
     ok = ok && (x > 0.0);
     const double r = rsqrt(x);
     d[j] = r;
     L[pk(j, j, 8)] = x * r;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (i > j) {
-        double s = L[pk(i, j, 8)];
+    for (int i = 0; i < 8; ++i)
+      if (i > j) L[pk(i, j, 8)] *= r;
 #pragma unroll
-        for (int p = 0; p < 8; ++p)
-          if (p < j) s -= L[pk(i, p, 8)] * L[pk(j, p, 8)];
-        L[pk(i, j, 8)] = s * r;
-      }
+    for (int c = 0; c < 8; ++c) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (c > j && i >= c) L[pk(i, c, 8)] -= L[pk(i, j, 8)] * L[pk(c, j, 8)];
     }
   }
+  return ok;
+}
+
+// X = L^-1 (packed lower) of an 8 x 8 lower-triangular L with d[j] = 1 / L(j, j).
+__device__ __forceinline__ void inv8(const double (&L)[36], const double (&d)[8], double (&X)[36]) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
 #pragma unroll
@@ -201,52 +201,49 @@ __device__ __forceinline__ bool chol8_and_inverse(const double *blk, int ld, dou
       }
     }
   }
-  return ok;
 }
 
 // In-place inverse of a symmetric positive definite n x n matrix given by its
 // LOWER triangle (n a multiple of 8, n <= 64): blocked right-looking Cholesky
 // (8-wide panels, DMMA trailing updates), block-column triangular inverse (one warp
 // per block column), then L^-T L^-1.  On return A holds the full symmetric inverse.
-// `scratch` is an n x ld array, `dinv` holds n / 8 blocks of 8 x 8.  Returns false
+// `scratch` is an n x ld array, `dinv` holds n / 8 blocks of 8 x 8, `ddiag` n doubles.  Returns false
 // when a pivot is <= 0 (Eigen LLT's failure criterion).  All threads must call it.
-__device__ bool cta_spd_inverse(double *A, int ld, int n, double *scratch, double *dinv) {
+__device__ bool cta_spd_inverse(double *A, int ld, int n, double *scratch, double *dinv,
+                                double *ddiag) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   bool ok = true;
   const int nb = n >> 3;
   for (int kb = 0; kb < nb; ++kb) {
     const int c0 = kb << 3, c1 = c0 + 8, rem = n - c1;
-    // Every thread factors the 8 x 8 diagonal block redundantly in registers and
-    // inverts it; no exchange is needed before the panel update.
-    double L[36], X[36];
-    ok = chol8_and_inverse(A + c0 * ld + c0, ld, L, X) && ok;
-    // Panel: row r of L21 = A21(r, :) L11^-T, one thread per row.
-    if (tid < rem) {
-      double *row = A + c0 * ld + c1 + tid;
-      double a[8];
+    // The two warps that own panel rows factor the 8 x 8 diagonal block redundantly in
+    // registers (no exchange before the panel solve); the other six warps go straight
+    // to the barrier, so the FP64 pipes are not spent on eight copies of the same chain.
+    if (tid < 64) {
+      double L[36], d[8];
+      ok = chol8(A + c0 * ld + c0, ld, L, d) && ok;
+      if (tid < rem) {  // row r of L21:  x L11' = A21(r, :)
+        double *row = A + c0 * ld + c1 + tid;
+        double x[8];
 #pragma unroll
-      for (int p = 0; p < 8; ++p) a[p] = row[p * ld];
+        for (int j = 0; j < 8; ++j) {
+          double sacc = row[j * ld];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        double s = 0.0;
-#pragma unroll
-        for (int p = 0; p <= j; ++p) s += a[p] * X[pk(j, p, 8)];
-        row[j * ld] = s;
-      }
-    }
-    if (tid == kThreads - 1) {  // publish L11 and L11^-1 (an otherwise idle thread)
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if (i >= j) {
-            A[(c0 + j) * ld + c0 + i] = L[pk(i, j, 8)];
-            dinv[kb * 64 + j * 8 + i] = X[pk(i, j, 8)];
-          } else {
-            A[(c0 + j) * ld + c0 + i] = 0.0;
-            dinv[kb * 64 + j * 8 + i] = 0.0;
-          }
+          for (int p = 0; p < 8; ++p)
+            if (p < j) sacc -= x[p] * L[pk(j, p, 8)];
+          x[j] = sacc * d[j];
+          row[j * ld] = x[j];
         }
+      }
+      asm volatile("bar.sync 1, 64;" ::: "memory");  // both warps have read the block
+      if (tid == 63) {  // publish L11 (rem <= 56, so this thread owns no panel row)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          ddiag[c0 + j] = d[j];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) A[(c0 + j) * ld + c0 + i] = (i >= j) ? L[(i >= j) ? pk(i, j, 8) : 0] : 0.0;
+        }
+      }
     }
     __syncthreads();
     if (rem > 0) {
@@ -256,6 +253,26 @@ __device__ bool cta_spd_inverse(double *A, int ld, int n, double *scratch, doubl
       __syncthreads();
     }
   }
+
+  // Inverses of the diagonal blocks, one warp per block (off the Cholesky critical path).
+  for (int kb = warp; kb < nb; kb += kWarps) {
+    double L[36], d[8], X[36];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      d[j] = ddiag[kb * 8 + j];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i >= j) L[pk(i, j, 8)] = A[(kb * 8 + j) * ld + kb * 8 + i];
+    }
+    inv8(L, d, X);
+    if (lane == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dinv[kb * 64 + j * 8 + i] = (i >= j) ? X[(i >= j) ? pk(i, j, 8) : 0] : 0.0;
+    }
+  }
+  __syncthreads();
 
   // Triangular inverse, block column kb by warp kb:  X_kk = inv(L_kk),
   // X_ik = -inv(L_ii) sum_{p=kb}^{i-1} L_ip X_pk.
@@ -322,7 +339,8 @@ struct CtaSmem {
   static constexpr int oK = oPuu + MP * LDM;          // K                        (MP x N)
   static constexpr int oGs = oK + N * LDM;            // scratch of the G inverse (MP x MP)
   static constexpr int oDinv = oGs + MP * LDM;        // 8 x 8 diagonal inverses
-  static constexpr int oVec = oDinv + (N / 8) * 64;
+  static constexpr int oDd = oDinv + (N / 8) * 64;    // 1 / L(j, j) of the factor in flight
+  static constexpr int oVec = oDd + N;
   static constexpr int vq = oVec, vr = vq + N, vc = vr + MP, vd = vc + N, vv = vd + N,
                        vdl = vv + N, vsd = vdl + N, vsdi = vsd + N, vf = vsdi + N, vg = vf + N,
                        vhw = vg + N, vkk = vhw + NZ, vEnd = vkk + MP;
@@ -342,7 +360,8 @@ riccati_backward_cta(LqrIn in, int *status_out, double *store, double *scratch, 
   const int64_t b = blockIdx.x;
   const size_t L_ = static_cast<size_t>(ld);
   double *Wp = sm + S::oW, *Zb = sm + S::oZ, *Sb = sm + S::oS, *Pux = sm + S::oPux,
-         *Puu = sm + S::oPuu, *Kb = sm + S::oK, *Gs = sm + S::oGs, *Dinv = sm + S::oDinv;
+         *Puu = sm + S::oPuu, *Kb = sm + S::oK, *Gs = sm + S::oGs, *Dinv = sm + S::oDinv,
+         *Dd = sm + S::oDd;
   double *q_s = sm + S::vq, *r_s = sm + S::vr, *c_s = sm + S::vc, *d_s = sm + S::vd,
          *v_s = sm + S::vv, *dl_s = sm + S::vdl, *sd_s = sm + S::vsd, *sdi_s = sm + S::vsdi,
          *f_s = sm + S::vf, *g_s = sm + S::vg, *hw_s = sm + S::vhw, *kk_s = sm + S::vkk;
@@ -412,7 +431,7 @@ riccati_backward_cta(LqrIn in, int *status_out, double *store, double *scratch, 
       if (i >= j) Wp[j * LDN + i] = sd_s[i] * Wp[j * LDN + i] * sd_s[j] + (i == j ? 1.0 : 0.0);
     }
     __syncthreads();
-    const bool f_ok = cta_spd_inverse(Wp, LDN, N, Sb, Dinv);
+    const bool f_ok = cta_spd_inverse(Wp, LDN, N, Sb, Dinv, Dd);
     if (!__syncthreads_and(f_ok) && status == SIPOC_FACTOR_SUCCESS)
       status = SIPOC_FACTOR_F_FACTORIZATION_FAILURE;
     for (int e = tid; e < N * N; e += kThreads) {
@@ -489,7 +508,7 @@ riccati_backward_cta(LqrIn in, int *status_out, double *store, double *scratch, 
     }
 
     // G^-1 (full, in Puu)
-    const bool g_ok = cta_spd_inverse(Puu, LDM, MP, Gs, Dinv);
+    const bool g_ok = cta_spd_inverse(Puu, LDM, MP, Gs, Dinv, Dd);
     if (!__syncthreads_and(g_ok) && status == SIPOC_FACTOR_SUCCESS)
       status = SIPOC_FACTOR_G_FACTORIZATION_FAILURE;
     // K = -G^-1 Psi_ux
