@@ -13,7 +13,22 @@ SRCS := $(CSRC)/api.cu $(CSRC)/generic_kernels.cu $(CSRC)/riccati_fast.cu $(CSRC
 OBJS := $(patsubst $(CSRC)/%,$(OBJDIR)/%.o,$(SRCS))
 HDRS := $(wildcard $(CSRC)/*.cuh $(CSRC)/*.hpp) include/sipoc.h
 
-all: $(LIBDIR)/libsipoc.so oracle
+HOSTDIR := sip_optimal_control_b200/host
+HOSTSRC := $(HOSTDIR)/lqr.cpp $(HOSTDIR)/helpers.cpp
+HOSTHDR := $(HOSTDIR)/lqr.hpp $(HOSTDIR)/types.hpp $(HOSTDIR)/helpers.hpp include/sipoc.h
+HOSTFLAGS := -std=c++17 -O2 -Wall -Wextra -fPIC
+
+all: $(LIBDIR)/libsipoc.so $(LIBDIR)/libsipoc_host.so build/host_tests oracle
+
+# C++ host side (the reference's Topology / Dimensions / LQR / CallbackProvider classes
+# over the C ABI) and the restated reference tests that run against it.
+$(LIBDIR)/libsipoc_host.so: $(HOSTSRC) $(HOSTHDR) $(LIBDIR)/libsipoc.so
+	$(HOSTCXX) $(HOSTFLAGS) -shared -o $@ $(HOSTSRC) -L$(LIBDIR) -lsipoc -Wl,-rpath,'$$ORIGIN'
+
+build/host_tests: $(HOSTDIR)/host_tests.cpp $(LIBDIR)/libsipoc_host.so
+	@mkdir -p build
+	$(HOSTCXX) $(HOSTFLAGS) -o $@ $< -L$(LIBDIR) -lsipoc_host -lsipoc \
+	    -Wl,-rpath,'$$ORIGIN/../$(LIBDIR)'
 
 $(OBJDIR)/%.cu.o: $(CSRC)/%.cu $(HDRS)
 	@mkdir -p $(OBJDIR)
@@ -31,6 +46,6 @@ oracle:
 	$(MAKE) -C oracle liboracle.so
 
 clean:
-	rm -rf build $(LIBDIR)/libsipoc.so oracle/liboracle.so
+	rm -rf build $(LIBDIR)/libsipoc.so $(LIBDIR)/libsipoc_host.so oracle/liboracle.so
 
 .PHONY: all oracle clean
