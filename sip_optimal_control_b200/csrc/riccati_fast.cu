@@ -1554,6 +1554,9 @@ rollout_forward_kkt(KktView kv, const double *store, const double *scratch, int6
 // ===========================================================================
 // Plans
 // ===========================================================================
+// Below this many problems a thread-per-problem kernel launches one-warp blocks.
+constexpr int64_t kSmallBatch = 148 * 128 * 2;
+
 template <int N, int M, bool SUBWARP>
 struct Plan {
   static int64_t store_elems(int T) { return FastSizes<N, M>::store(T); }
@@ -1593,20 +1596,23 @@ struct Plan {
         <<<grid, THREADS, 0, s>>>(a.in, a.out, a.store, a.scratch, a.batch, a.ld, a.num_edges);
   }
   static void forward(const FastArgs &a, cudaStream_t s) {
-    // 128 threads, no register cap: the compiler then hoists a whole stage's loads
-    // (254 registers), which is what keeps HBM busy (capped variants were slower).
-    launch_forward<128, 1>(a, s);
+    // No register cap: the compiler then hoists a whole stage's loads (254 registers),
+    // which is what keeps HBM busy (capped variants were slower).  Small batches use
+    // one-warp blocks so that every SM gets work (8 192 problems are 64 blocks of 128).
+    if (a.batch >= kSmallBatch) launch_forward<128, 1>(a, s);
+    else launch_forward<32, 1>(a, s);
   }
   static int factor(const FastArgs &a, cudaStream_t s) {
     backward<false>(a, s);
     return 1;
   }
   static int solve(const FastArgs &a, cudaStream_t s) {
-    const unsigned grid = static_cast<unsigned>((a.batch + 127) / 128);
+    const int threads = a.batch >= kSmallBatch ? 128 : 32;
+    const unsigned grid = static_cast<unsigned>((a.batch + threads - 1) / threads);
     {
       ProfScope ps(a.prof, "affine_backward", s);
       affine_backward<N, M>
-          <<<grid, 128, 0, s>>>(a.in, a.store, a.scratch, a.batch, a.ld, a.num_edges);
+          <<<grid, threads, 0, s>>>(a.in, a.store, a.scratch, a.batch, a.ld, a.num_edges);
     }
     forward(a, s);
     return 2;
