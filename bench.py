@@ -254,6 +254,8 @@ def run_ours(args, wl, name):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL's banner ("NCCL version ...") belongs on stderr: stdout carries the JSON line.
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, (world, args.gpus)
 
