@@ -209,8 +209,13 @@ __device__ __forceinline__ void inv8(const double (&L)[36], const double (&d)[8]
 // per block column), then L^-T L^-1.  On return A holds the full symmetric inverse.
 // `scratch` is an n x ld array, `dinv` holds n / 8 blocks of 8 x 8, `ddiag` n doubles.  Returns false
 // when a pivot is <= 0 (Eigen LLT's failure criterion).  All threads must call it.
+// `idle(kb, nb)` is called in block step kb by the six warps that have no part in the
+// diagonal factor / panel solve: the caller uses it to issue the next stage's cp.async
+// copies off the critical path (issuing thousands of scattered 8-byte copies stalls the
+// issuing warp on the load/store queue, so it must not be a warp the factorization needs).
+template <class Idle>
 __device__ bool cta_spd_inverse(double *A, int ld, int n, double *scratch, double *dinv,
-                                double *ddiag) {
+                                double *ddiag, Idle idle) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   bool ok = true;
   const int nb = n >> 3;
@@ -244,6 +249,8 @@ __device__ bool cta_spd_inverse(double *A, int ld, int n, double *scratch, doubl
           for (int i = 0; i < 8; ++i) A[(c0 + j) * ld + c0 + i] = (i >= j) ? L[(i >= j) ? pk(i, j, 8) : 0] : 0.0;
         }
       }
+    } else {
+      idle(kb, nb);
     }
     __syncthreads();
     if (rem > 0) {
@@ -372,28 +379,42 @@ riccati_backward_cta(LqrIn in, int *status_out, double *store, double *scratch, 
   double *vst = SOLVE ? scratch + Zs::ov(T) * ld + b : nullptr;
   double *kst = SOLVE ? scratch + Zs::ok(T) * ld + b : nullptr;
 
-  auto stage_edge_z = [&](int k) {  // A_k, B_k -> Z
+  // Staging copies.  (t0, nt): the calling threads are tid in [t0, t0 + nt); (part, parts):
+  // this call moves the part-th of `parts` equal slices of the element range.
+  auto stage_edge_z = [&](int k, int t0, int nt, int part, int parts) {  // A_k, B_k -> Z
     const double *gA = in.A + static_cast<size_t>(k) * N * N * L_ + b;
-    for (int e = tid; e < N * N; e += kThreads) cp_async8(Zb + (e / N) * LDN + e % N, gA + e * L_);
     const double *gB = in.B + static_cast<size_t>(k) * N * M * L_ + b;
-    for (int e = tid; e < N * M; e += kThreads)
-      cp_async8(Zb + (N + e / N) * LDN + e % N, gB + e * L_);
+    constexpr int total = N * N + N * M;
+    const int per = (total + parts - 1) / parts;
+    const int hi = (part + 1) * per < total ? (part + 1) * per : total;
+    for (int e = part * per + (tid - t0); e < hi; e += nt) {
+      if (e < N * N) {
+        cp_async8(Zb + (e / N) * LDN + e % N, gA + e * L_);
+      } else {
+        const int f = e - N * N;
+        cp_async8(Zb + (N + f / N) * LDN + f % N, gB + f * L_);
+      }
+    }
   };
-  auto stage_edge_rest = [&](int k) {  // M_k' -> Psi_ux, R_k (lower) -> Psi_uu, vectors
+  // M_k' -> Psi_ux, R_k (lower) -> Psi_uu, vectors of stage k
+  auto stage_edge_rest = [&](int k, int t0, int nt) {
+    const int t = tid - t0;
     const double *gM = in.M + static_cast<size_t>(k) * N * M * L_ + b;
-    for (int e = tid; e < N * M; e += kThreads)
+    for (int e = t; e < N * M; e += nt)
       cp_async8(Pux + (e % N) * LDM + e / N, gM + e * L_);  // M(x, u) -> Psi_ux(u, x)
     const double *gR = in.R + static_cast<size_t>(k) * M * M * L_ + b;
-    for (int e = tid; e < M * M; e += kThreads)
+    for (int e = t; e < M * M; e += nt)
       if (e % M >= e / M) cp_async8(Puu + (e / M) * LDM + e % M, gR + e * L_);
-    if (tid < N) cp_async8(d_s + tid, in.delta + (static_cast<size_t>(k) * N + tid) * L_ + b);
-    if (SOLVE) {
-      if (tid < N) {
-        cp_async8(q_s + tid, in.q + (static_cast<size_t>(k) * N + tid) * L_ + b);
-        cp_async8(c_s + tid, in.c + (static_cast<size_t>(k + 1) * N + tid) * L_ + b);
+    for (int i = t; i < N; i += nt) {
+      cp_async8(d_s + i, in.delta + (static_cast<size_t>(k) * N + i) * L_ + b);
+      if (SOLVE) {
+        cp_async8(q_s + i, in.q + (static_cast<size_t>(k) * N + i) * L_ + b);
+        cp_async8(c_s + i, in.c + (static_cast<size_t>(k + 1) * N + i) * L_ + b);
       }
-      if (tid < M) cp_async8(r_s + tid, in.r + (static_cast<size_t>(k) * M + tid) * L_ + b);
     }
+    if (SOLVE)
+      for (int a = t; a < M; a += nt)
+        cp_async8(r_s + a, in.r + (static_cast<size_t>(k) * M + a) * L_ + b);
   };
   auto stage_q_lower = [&](int k) {  // Q_k (lower) -> Psi_xx buffer
     const double *gQ = in.Q + static_cast<size_t>(k) * N * N * L_ + b;
@@ -422,16 +443,19 @@ riccati_backward_cta(LqrIn in, int *status_out, double *store, double *scratch, 
     }
     const bool any_bad = __syncthreads_or(!d_ok);
     if (any_bad && status == SIPOC_FACTOR_SUCCESS) status = SIPOC_FACTOR_INVALID_DELTA;
-    if (k > 0) {  // M, R, q, r, c, delta of the next stage fly during the F inverse
-      stage_edge_rest(k - 1);
-      cp_async_commit();
-    }
     for (int e = tid; e < N * N; e += kThreads) {
       const int i = e % N, j = e / N;
       if (i >= j) Wp[j * LDN + i] = sd_s[i] * Wp[j * LDN + i] * sd_s[j] + (i == j ? 1.0 : 0.0);
     }
     __syncthreads();
-    const bool f_ok = cta_spd_inverse(Wp, LDN, N, Sb, Dinv, Dd);
+    // M, R, q, r, c, delta of the next stage (and, after the terminal node, its A and B)
+    // are issued by the idle warps of the F factorization's block steps.
+    const bool f_ok = cta_spd_inverse(Wp, LDN, N, Sb, Dinv, Dd, [&](int kb, int nb) {
+      if (k == 0) return;
+      if (kb == 0) stage_edge_rest(k - 1, 64, kThreads - 64);
+      if (k == T && kb >= 1 && kb < nb) stage_edge_z(k - 1, 64, kThreads - 64, kb - 1, nb - 1);
+      cp_async_commit();
+    });
     if (!__syncthreads_and(f_ok) && status == SIPOC_FACTOR_SUCCESS)
       status = SIPOC_FACTOR_F_FACTORIZATION_FAILURE;
     for (int e = tid; e < N * N; e += kThreads) {
@@ -467,10 +491,6 @@ riccati_backward_cta(LqrIn in, int *status_out, double *store, double *scratch, 
   cp_async_commit();
   cp_async_wait_all();
   __syncthreads();
-  if (T > 0) {  // stage T-1's A, B fly while node T is processed
-    stage_edge_z(T - 1);
-    cp_async_commit();
-  }
   process_node(T);
 
   for (int k = T - 1; k >= 0; --k) {
@@ -502,13 +522,14 @@ riccati_backward_cta(LqrIn in, int *status_out, double *store, double *scratch, 
     // Psi_xx += A' S_x (lower blocks)
     cta_gemm<true, false, true, true>(Wp, LDN, Zb, LDN, Sb, LDN, N, N, N, 1.0);
     __syncthreads();
-    if (k > 0) {  // Z is consumed: A, B of the next stage fly during the rest of this one
-      stage_edge_z(k - 1);
-      cp_async_commit();
-    }
 
-    // G^-1 (full, in Puu)
-    const bool g_ok = cta_spd_inverse(Puu, LDM, MP, Gs, Dinv, Dd);
+    // G^-1 (full, in Puu).  Z is consumed: A, B of the next stage are issued by the idle
+    // warps of the G factorization's block steps and fly during the rest of this stage.
+    const bool g_ok = cta_spd_inverse(Puu, LDM, MP, Gs, Dinv, Dd, [&](int kb, int nb) {
+      if (k == 0) return;
+      stage_edge_z(k - 1, 64, kThreads - 64, kb, nb);
+      cp_async_commit();
+    });
     if (!__syncthreads_and(g_ok) && status == SIPOC_FACTOR_SUCCESS)
       status = SIPOC_FACTOR_G_FACTORIZATION_FAILURE;
     // K = -G^-1 Psi_ux
