@@ -215,11 +215,15 @@ __device__ __forceinline__ void inv8(const double (&L)[36], const double (&d)[8]
 // issuing warp on the load/store queue, so it must not be a warp the factorization needs).
 template <class Idle>
 __device__ bool cta_spd_inverse(double *A, int ld, int n, double *scratch, double *dinv,
-                                double *ddiag, Idle idle) {
+                                double *ddiag, Idle idle, int n_live = -1) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   bool ok = true;
   const int nb = n >> 3;
-  for (int kb = 0; kb < nb; ++kb) {
+  // Rows / columns >= n_live are an identity padding block (their panel rows are exactly
+  // zero): the Cholesky leaves them untouched, only their trivial factor is recorded.
+  const int nb_live = n_live < 0 ? nb : (n_live + 7) >> 3;
+  for (int i = nb_live * 8 + tid; i < n; i += kThreads) ddiag[i] = 1.0;
+  for (int kb = 0; kb < nb_live; ++kb) {
     const int c0 = kb << 3, c1 = c0 + 8, rem = n - c1;
     // The two warps that own panel rows factor the 8 x 8 diagonal block redundantly in
     // registers (no exchange before the panel solve); the other six warps go straight
@@ -250,7 +254,7 @@ __device__ bool cta_spd_inverse(double *A, int ld, int n, double *scratch, doubl
         }
       }
     } else {
-      idle(kb, nb);
+      idle(kb, nb_live);
     }
     __syncthreads();
     if (rem > 0) {
@@ -416,6 +420,16 @@ riccati_backward_cta(LqrIn in, int *status_out, double *store, double *scratch, 
       for (int a = t; a < M; a += nt)
         cp_async8(r_s + a, in.r + (static_cast<size_t>(k) * M + a) * L_ + b);
   };
+  // Q_k (lower, packed) -> the K buffer, which is idle between the end of one stage and
+  // the K product of the next; unpacked into Psi_xx once W' has been consumed.
+  static_assert(N * LDM >= tri(N), "packed Q must fit the K buffer");
+  auto stage_q_packed = [&](int k, int t0, int nt) {
+    const double *gQ = in.Q + static_cast<size_t>(k) * N * N * L_ + b;
+    for (int e = tid - t0; e < N * N; e += nt) {
+      const int i = e % N, j = e / N;
+      if (i >= j) cp_async8(Kb + pk(i, j, N), gQ + e * L_);
+    }
+  };
   auto stage_q_lower = [&](int k) {  // Q_k (lower) -> Psi_xx buffer
     const double *gQ = in.Q + static_cast<size_t>(k) * N * N * L_ + b;
     for (int e = tid; e < N * N; e += kThreads)
@@ -453,6 +467,7 @@ riccati_backward_cta(LqrIn in, int *status_out, double *store, double *scratch, 
     const bool f_ok = cta_spd_inverse(Wp, LDN, N, Sb, Dinv, Dd, [&](int kb, int nb) {
       if (k == 0) return;
       if (kb == 0) stage_edge_rest(k - 1, 64, kThreads - 64);
+      if (kb == 1) stage_q_packed(k - 1, 64, kThreads - 64);
       if (k == T && kb >= 1 && kb < nb) stage_edge_z(k - 1, 64, kThreads - 64, kb - 1, nb - 1);
       cp_async_commit();
     });
@@ -510,14 +525,15 @@ riccati_backward_cta(LqrIn in, int *status_out, double *store, double *scratch, 
     // S = W' Z
     cta_gemm<false, false, false, false>(Sb, LDN, Wp, LDN, Zb, LDN, N, NZ, N, 1.0);
     __syncthreads();
-    // Psi_xx base: Q_k lower into the (now free) W' buffer; overlaps the u-block products.
-    stage_q_lower(k);
-    cp_async_commit();
+    // Psi_xx base: Q_k lower (prefetched, packed, in the K buffer) into the now free W' buffer.
+    for (int e = tid; e < N * N; e += kThreads) {
+      const int i = e % N, j = e / N;
+      if (i >= j) Wp[j * LDN + i] = Kb[pk(i, j, N)];
+    }
     // Psi_ux += B' S_x ,  Psi_uu += B' S_u   (rows = u, K = N)
     cta_gemm<true, false, true, false>(Pux, LDM, Zb + N * LDN, LDN, Sb, LDN, MP, N, N, 1.0);
     cta_gemm<true, false, true, true>(Puu, LDM, Zb + N * LDN, LDN, Sb + N * LDN, LDN, MP, MP, N,
                                       1.0);
-    cp_async_wait_all();
     __syncthreads();
     // Psi_xx += A' S_x (lower blocks)
     cta_gemm<true, false, true, true>(Wp, LDN, Zb, LDN, Sb, LDN, N, N, N, 1.0);
@@ -529,7 +545,7 @@ riccati_backward_cta(LqrIn in, int *status_out, double *store, double *scratch, 
       if (k == 0) return;
       stage_edge_z(k - 1, 64, kThreads - 64, kb, nb);
       cp_async_commit();
-    });
+    }, M);
     if (!__syncthreads_and(g_ok) && status == SIPOC_FACTOR_SUCCESS)
       status = SIPOC_FACTOR_G_FACTORIZATION_FAILURE;
     // K = -G^-1 Psi_ux
