@@ -44,6 +44,7 @@ struct sipoc_engine {
   bool gws_ready = false;
   // Fast-path storage (lazy).
   double *fast_store = nullptr, *fast_scratch = nullptr;
+  double *pm_in[9] = {nullptr};  // problem-major input copies (plans that ask for them)
   enum class Factored { NONE, GENERIC, FAST } factored = Factored::NONE;
 
   // Newton-KKT reduction outputs (lazy).
@@ -224,13 +225,45 @@ bool use_fast(const sipoc_engine *e, const LqrIn &in) {
   return e->fast != nullptr && aligned16(in);
 }
 
+int64_t lqr_in_size(const HostStructure &h, int i);
+
+// Plans whose backward kernel runs one problem per CTA read the inputs from
+// problem-major copies [problem][flat]; this transposes the arrays the call touches
+// (nine coalesced passes, a few percent of the factorization they feed).
+sipoc_error refresh_problem_major(sipoc_engine *e, const LqrIn &in, bool vectors, LqrIn *pm,
+                                  cudaStream_t s) {
+  *pm = LqrIn{};
+  if (e->fast == nullptr || !e->fast->problem_major_inputs) return SIPOC_OK;
+  const double *src[9] = {in.Q, in.M, in.R, in.q, in.r, in.A, in.B, in.c, in.delta};
+  const bool is_vector[9] = {false, false, false, true, true, false, false, true, false};
+  for (int i = 0; i < 9; ++i) {
+    if (is_vector[i] && !vectors) continue;
+    const int64_t size = lqr_in_size(e->hs, i);
+    if (e->pm_in[i] == nullptr) {
+      sipoc_error rc = dev_alloc(e, reinterpret_cast<void **>(&e->pm_in[i]),
+                                 static_cast<size_t>(std::max<int64_t>(size, 1)) *
+                                     static_cast<size_t>(e->batch) * sizeof(double));
+      if (rc != SIPOC_OK) return rc;
+    }
+    ProfScope ps(&e->prof, "unpack_kernel", s);
+    launch_unpack(src[i], e->pm_in[i], size, e->batch, e->ld, s);
+    e->launches += 1;
+  }
+  *pm = LqrIn{e->pm_in[0], e->pm_in[1], e->pm_in[2], e->pm_in[3], e->pm_in[4],
+              e->pm_in[5], e->pm_in[6], e->pm_in[7], e->pm_in[8]};
+  return SIPOC_OK;
+}
+
 // --- device-path cores (shared by the device and host entry points) --------
 sipoc_error lqr_factor_core(sipoc_engine *e, const LqrIn &in, int *status,
                             cudaStream_t s) {
   sipoc_error rc;
   if (use_fast(e, in)) {
     if ((rc = ensure_fast_store(e)) != SIPOC_OK) return rc;
-    FastArgs a{in, LqrOut{}, status, e->fast_store, nullptr, e->batch, e->ld, e->hs.E, &e->prof};
+    LqrIn pm;
+    if ((rc = refresh_problem_major(e, in, false, &pm, s)) != SIPOC_OK) return rc;
+    FastArgs a{in, pm, LqrOut{}, status, e->fast_store, nullptr, e->batch, e->ld, e->hs.E,
+               &e->prof};
     e->launches += e->fast->factor(a, s);
     e->factored = sipoc_engine::Factored::FAST;
   } else {
@@ -255,7 +288,8 @@ sipoc_error lqr_solve_core(sipoc_engine *e, const LqrIn &in, const LqrOut &out,
                 "solve against a fast-path factorization needs 16-byte aligned arrays");
   if (e->factored == sipoc_engine::Factored::FAST) {
     if ((rc = ensure_fast_scratch(e)) != SIPOC_OK) return rc;
-    FastArgs a{in, out, nullptr, e->fast_store, e->fast_scratch, e->batch, e->ld, e->hs.E, &e->prof};
+    FastArgs a{in, LqrIn{}, out, nullptr, e->fast_store, e->fast_scratch, e->batch, e->ld,
+               e->hs.E, &e->prof};
     e->launches += e->fast->solve(a, s);
   } else {
     {
@@ -273,7 +307,9 @@ sipoc_error lqr_factor_solve_core(sipoc_engine *e, const LqrIn &in, const LqrOut
   if (use_fast(e, in)) {
     if ((rc = ensure_fast_store(e)) != SIPOC_OK) return rc;
     if ((rc = ensure_fast_scratch(e)) != SIPOC_OK) return rc;
-    FastArgs a{in, out, status, e->fast_store, e->fast_scratch, e->batch, e->ld, e->hs.E,
+    LqrIn pm;
+    if ((rc = refresh_problem_major(e, in, true, &pm, s)) != SIPOC_OK) return rc;
+    FastArgs a{in, pm, out, status, e->fast_store, e->fast_scratch, e->batch, e->ld, e->hs.E,
                &e->prof};
     e->launches += e->fast->factor_solve(a, s);
     // The backward kernel keeps W, K and G^-1, so later solves may reuse them.

@@ -361,7 +361,7 @@ struct CtaSmem {
 
 template <int N, int M, bool SOLVE>
 __global__ void __launch_bounds__(kThreads, 1)
-riccati_backward_cta(LqrIn in, int *status_out, double *store, double *scratch, int64_t batch,
+riccati_backward_cta(LqrIn pm, int *status_out, double *store, double *scratch, int64_t batch,
                      int64_t ld, int T) {
   using S = CtaSmem<N, M>;
   using Zs = CtaSizes<N, M>;
@@ -383,57 +383,71 @@ riccati_backward_cta(LqrIn in, int *status_out, double *store, double *scratch, 
   double *vst = SOLVE ? scratch + Zs::ov(T) * ld + b : nullptr;
   double *kst = SOLVE ? scratch + Zs::ok(T) * ld + b : nullptr;
 
+  // Inputs come from the problem-major copies [problem][flat]: this CTA's problem is a
+  // contiguous run per array, so a warp's 32 eight-byte copies cover 8 whole sectors
+  // (the batch-interleaved layout would make them 32 sectors with 8 useful bytes each).
+  const size_t ub = static_cast<size_t>(b);
+  const double *bQ = pm.Q + ub * (static_cast<size_t>(T + 1) * N * N);
+  const double *bM = pm.M + ub * (static_cast<size_t>(T) * N * M);
+  const double *bR = pm.R + ub * (static_cast<size_t>(T) * M * M);
+  const double *bA = pm.A + ub * (static_cast<size_t>(T) * N * N);
+  const double *bB = pm.B + ub * (static_cast<size_t>(T) * N * M);
+  const double *bd = pm.delta + ub * (static_cast<size_t>(T + 1) * N);
+  const double *bq = SOLVE ? pm.q + ub * (static_cast<size_t>(T + 1) * N) : nullptr;
+  const double *bc = SOLVE ? pm.c + ub * (static_cast<size_t>(T + 1) * N) : nullptr;
+  const double *br = SOLVE ? pm.r + ub * (static_cast<size_t>(T) * M) : nullptr;
+
   // Staging copies.  (t0, nt): the calling threads are tid in [t0, t0 + nt); (part, parts):
   // this call moves the part-th of `parts` equal slices of the element range.
   auto stage_edge_z = [&](int k, int t0, int nt, int part, int parts) {  // A_k, B_k -> Z
-    const double *gA = in.A + static_cast<size_t>(k) * N * N * L_ + b;
-    const double *gB = in.B + static_cast<size_t>(k) * N * M * L_ + b;
+    const double *gA = bA + static_cast<size_t>(k) * N * N;
+    const double *gB = bB + static_cast<size_t>(k) * N * M;
     constexpr int total = N * N + N * M;
     const int per = (total + parts - 1) / parts;
     const int hi = (part + 1) * per < total ? (part + 1) * per : total;
     for (int e = part * per + (tid - t0); e < hi; e += nt) {
       if (e < N * N) {
-        cp_async8(Zb + (e / N) * LDN + e % N, gA + e * L_);
+        cp_async8(Zb + (e / N) * LDN + e % N, gA + e);
       } else {
         const int f = e - N * N;
-        cp_async8(Zb + (N + f / N) * LDN + f % N, gB + f * L_);
+        cp_async8(Zb + (N + f / N) * LDN + f % N, gB + f);
       }
     }
   };
   // M_k' -> Psi_ux, R_k (lower) -> Psi_uu, vectors of stage k
   auto stage_edge_rest = [&](int k, int t0, int nt) {
     const int t = tid - t0;
-    const double *gM = in.M + static_cast<size_t>(k) * N * M * L_ + b;
+    const double *gM = bM + static_cast<size_t>(k) * N * M;
     for (int e = t; e < N * M; e += nt)
-      cp_async8(Pux + (e % N) * LDM + e / N, gM + e * L_);  // M(x, u) -> Psi_ux(u, x)
-    const double *gR = in.R + static_cast<size_t>(k) * M * M * L_ + b;
+      cp_async8(Pux + (e % N) * LDM + e / N, gM + e);  // M(x, u) -> Psi_ux(u, x)
+    const double *gR = bR + static_cast<size_t>(k) * M * M;
     for (int e = t; e < M * M; e += nt)
-      if (e % M >= e / M) cp_async8(Puu + (e / M) * LDM + e % M, gR + e * L_);
+      if (e % M >= e / M) cp_async8(Puu + (e / M) * LDM + e % M, gR + e);
     for (int i = t; i < N; i += nt) {
-      cp_async8(d_s + i, in.delta + (static_cast<size_t>(k) * N + i) * L_ + b);
+      cp_async8(d_s + i, bd + static_cast<size_t>(k) * N + i);
       if (SOLVE) {
-        cp_async8(q_s + i, in.q + (static_cast<size_t>(k) * N + i) * L_ + b);
-        cp_async8(c_s + i, in.c + (static_cast<size_t>(k + 1) * N + i) * L_ + b);
+        cp_async8(q_s + i, bq + static_cast<size_t>(k) * N + i);
+        cp_async8(c_s + i, bc + static_cast<size_t>(k + 1) * N + i);
       }
     }
     if (SOLVE)
       for (int a = t; a < M; a += nt)
-        cp_async8(r_s + a, in.r + (static_cast<size_t>(k) * M + a) * L_ + b);
+        cp_async8(r_s + a, br + static_cast<size_t>(k) * M + a);
   };
   // Q_k (lower, packed) -> the K buffer, which is idle between the end of one stage and
   // the K product of the next; unpacked into Psi_xx once W' has been consumed.
   static_assert(N * LDM >= tri(N), "packed Q must fit the K buffer");
   auto stage_q_packed = [&](int k, int t0, int nt) {
-    const double *gQ = in.Q + static_cast<size_t>(k) * N * N * L_ + b;
+    const double *gQ = bQ + static_cast<size_t>(k) * N * N;
     for (int e = tid - t0; e < N * N; e += nt) {
       const int i = e % N, j = e / N;
-      if (i >= j) cp_async8(Kb + pk(i, j, N), gQ + e * L_);
+      if (i >= j) cp_async8(Kb + pk(i, j, N), gQ + e);
     }
   };
   auto stage_q_lower = [&](int k) {  // Q_k (lower) -> Psi_xx buffer
-    const double *gQ = in.Q + static_cast<size_t>(k) * N * N * L_ + b;
+    const double *gQ = bQ + static_cast<size_t>(k) * N * N;
     for (int e = tid; e < N * N; e += kThreads)
-      if (e % N >= e / N) cp_async8(Wp + (e / N) * LDN + e % N, gQ + e * L_);
+      if (e % N >= e / N) cp_async8(Wp + (e / N) * LDN + e % N, gQ + e);
   };
 
   int status = SIPOC_FACTOR_SUCCESS;
@@ -500,8 +514,8 @@ riccati_backward_cta(LqrIn in, int *status_out, double *store, double *scratch, 
   // ---- terminal node ----------------------------------------------------------
   stage_q_lower(T);
   if (tid < N) {
-    cp_async8(d_s + tid, in.delta + (static_cast<size_t>(T) * N + tid) * L_ + b);
-    if (SOLVE) cp_async8(hw_s + tid, in.q + (static_cast<size_t>(T) * N + tid) * L_ + b);
+    cp_async8(d_s + tid, bd + static_cast<size_t>(T) * N + tid);
+    if (SOLVE) cp_async8(hw_s + tid, bq + static_cast<size_t>(T) * N + tid);
   }
   cp_async_commit();
   cp_async_wait_all();
@@ -750,7 +764,7 @@ struct CtaPlan {
     if (bytes > 48 * 1024)
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     ProfScope ps(a.prof, "riccati_backward_cta", s);
-    kern<<<static_cast<unsigned>(a.batch), kThreads, bytes, s>>>(a.in, a.status, a.store,
+    kern<<<static_cast<unsigned>(a.batch), kThreads, bytes, s>>>(a.pm, a.status, a.store,
                                                                  a.scratch, a.batch, a.ld,
                                                                  a.num_edges);
   }
@@ -784,7 +798,7 @@ const FastPlan *make_cta_plan(const char *name) {
   using P = CtaPlan<N, M>;
   static const FastPlan plan{name,         N,           M,         &P::store_elems,
                              &P::scratch_elems, &P::factor, &P::solve, &P::factor_solve,
-                             nullptr};
+                             nullptr, true};
   return &plan;
 }
 

@@ -1644,7 +1644,7 @@ const FastPlan *make_plan(const char *name) {
   using P = Plan<N, M, SUBWARP>;
   static const FastPlan plan{name,         N,           M,         &P::store_elems,
                              &P::scratch_elems, &P::factor, &P::solve, &P::factor_solve,
-                             &P::kkt_solve};
+                             &P::kkt_solve, false};
   return &plan;
 }
 

@@ -17,6 +17,9 @@ namespace sipoc {
 
 struct FastArgs {
   LqrIn in;
+  // Problem-major copies [problem][flat] of the inputs (plans with
+  // problem_major_inputs; pointers are null otherwise or for arrays not refreshed).
+  LqrIn pm;
   LqrOut out;
   int *status;      // device int[ld] or nullptr
   double *store;    // factorization kept for later solves (W, K, LG per stage)
@@ -52,6 +55,10 @@ struct FastPlan {
   int (*factor_solve)(const FastArgs &, cudaStream_t);
   // Fused rhs build + affine sweep, rollout + dual recovery; nullptr = not provided.
   int (*kkt_solve)(const FastKktArgs &, cudaStream_t);
+  // The backward kernel wants FastArgs::pm: one problem per CTA reads whole sectors
+  // from a problem-major copy instead of 8 bytes per 32-byte sector of the
+  // batch-interleaved layout.
+  bool problem_major_inputs;
 };
 
 // nullptr when no specialised kernel exists for (n, m).
