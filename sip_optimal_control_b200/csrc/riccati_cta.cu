@@ -64,6 +64,10 @@ __device__ __forceinline__ void cp_async8(double *smem, const double *gmem) {
   const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem) : "memory");
 }
+__device__ __forceinline__ void cp_async16(double *smem, const double *gmem) {
+  const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() {
   asm volatile("cp.async.commit_group;\n" ::: "memory");
 }
@@ -85,56 +89,86 @@ __device__ __forceinline__ double op_at(const double *A, int ld, int i, int k) {
   return TRANS ? A[i * ld + k] : A[k * ld + i];
 }
 
-// C (Mo x No) = (ACC ? C : 0) + sign * op(A) (Mo x K) * op(B) (K x No), all in shared
-// memory, column-major.  Mo, No multiples of 8, K a multiple of 4.  Work unit: a
-// 16 x 16 block (2 x 2 MMA tiles) per warp, blocks dealt round-robin to the warps;
-// LOWER computes only blocks on or below the block diagonal (whole blocks).
-template <bool TA, bool TB, bool ACC, bool LOWER>
-__device__ void cta_gemm(double *C, int ldc, const double *A, int lda, const double *B, int ldb,
-                         int Mo, int No, int K, double sign) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const int tm = (Mo + 15) >> 4, tn = (No + 15) >> 4;
-  int slot = 0;
-  for (int ti = 0; ti < tm; ++ti) {
-    for (int tj = 0; tj < (LOWER ? ti + 1 : tn); ++tj, ++slot) {
-      if (slot % kWarps != warp) continue;
-      const int i0 = ti << 4, j0 = tj << 4;
-      const bool r1 = i0 + 8 < Mo, c1 = j0 + 8 < No;
-      double acc[2][2][2];
+// (row, column) of the s-th cell of a lower triangle enumerated row by row, s < 36.
+__constant__ unsigned char kTriRow[36] = {0, 1, 1, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 4, 5, 5, 5,
+                                          5, 5, 5, 6, 6, 6, 6, 6, 6, 6, 7, 7, 7, 7, 7, 7, 7, 7};
+__constant__ unsigned char kTriCol[36] = {0, 0, 1, 0, 1, 2, 0, 1, 2, 3, 0, 1, 2, 3, 4, 0, 1, 2,
+                                          3, 4, 5, 0, 1, 2, 3, 4, 5, 6, 0, 1, 2, 3, 4, 5, 6, 7};
+
+// One 16 x 16 block (2 x 2 MMA tiles) at (i0, j0) of
+//   C (Mo x No) = (ACC ? C : 0) + sign * op(A) (Mo x K) * op(B) (K x No),
+// all in shared memory, column-major; executed by one warp.  Mo, No multiples of 8, K a
+// multiple of 4.  KTRI starts the k range at i0 (op(A) upper triangular, i.e. A' of a
+// lower-triangular X).
+template <bool TA, bool TB, bool ACC, bool KTRI = false>
+__device__ __forceinline__ void gemm_block(double *C, int ldc, const double *A, int lda,
+                                           const double *B, int ldb, int Mo, int No, int K,
+                                           double sign, int i0, int j0) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const bool r1 = i0 + 8 < Mo, c1 = j0 + 8 < No;
+  double acc[2][2][2];
 #pragma unroll
-      for (int a = 0; a < 2; ++a)
+  for (int a = 0; a < 2; ++a)
 #pragma unroll
-        for (int b = 0; b < 2; ++b) {
-          const bool live = (a == 0 || r1) && (b == 0 || c1);
-          const double *src = C + (j0 + 8 * b + 2 * t) * ldc + i0 + 8 * a + g;
-          acc[a][b][0] = (ACC && live) ? src[0] : 0.0;
-          acc[a][b][1] = (ACC && live) ? src[ldc] : 0.0;
-        }
-#pragma unroll 2
-      for (int k0 = 0; k0 < K; k0 += 4) {
-        const double a0 = sign * op_at<TA>(A, lda, i0 + g, k0 + t);
-        const double a1 = r1 ? sign * op_at<TA>(A, lda, i0 + 8 + g, k0 + t) : 0.0;
-        // op(B)(k, j): B column-major -> B[j * ldb + k]; transposed -> B[k * ldb + j].
-        const double b0 = TB ? B[(k0 + t) * ldb + j0 + g] : B[(j0 + g) * ldb + k0 + t];
-        const double b1 =
-            c1 ? (TB ? B[(k0 + t) * ldb + j0 + 8 + g] : B[(j0 + 8 + g) * ldb + k0 + t]) : 0.0;
-        dmma(acc[0][0], a0, b0);
-        dmma(acc[0][1], a0, b1);
-        dmma(acc[1][0], a1, b0);
-        dmma(acc[1][1], a1, b1);
+    for (int b = 0; b < 2; ++b) {
+      const bool live = (a == 0 || r1) && (b == 0 || c1);
+      const double *src = C + (j0 + 8 * b + 2 * t) * ldc + i0 + 8 * a + g;
+      acc[a][b][0] = (ACC && live) ? src[0] : 0.0;
+      acc[a][b][1] = (ACC && live) ? src[ldc] : 0.0;
+    }
+  // op(A)(i, k): A column-major -> A[k * lda + i]; transposed -> A[i * lda + k].
+  // op(B)(k, j): B column-major -> B[j * ldb + k]; transposed -> B[k * ldb + j].
+  const double *pa0 = TA ? A + (i0 + g) * lda + t : A + t * lda + i0 + g;
+  const double *pb0 = TB ? B + t * ldb + j0 + g : B + (j0 + g) * ldb + t;
+  const int sa = TA ? 1 : lda, sb = TB ? ldb : 1;       // stride of one k step
+  const int oa = TA ? 8 * lda : 8, ob = TB ? 8 : 8 * ldb;  // offset of the second MMA tile
+#pragma unroll 4
+  for (int k0 = KTRI ? i0 : 0; k0 < K; k0 += 4) {
+    const double a0 = pa0[k0 * sa];
+    const double a1 = r1 ? pa0[k0 * sa + oa] : 0.0;
+    const double b0 = sign * pb0[k0 * sb];
+    const double b1 = c1 ? sign * pb0[k0 * sb + ob] : 0.0;
+    dmma(acc[0][0], a0, b0);
+    dmma(acc[0][1], a0, b1);
+    dmma(acc[1][0], a1, b0);
+    dmma(acc[1][1], a1, b1);
+  }
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      if ((a == 0 || r1) && (b == 0 || c1)) {
+        double *dst = C + (j0 + 8 * b + 2 * t) * ldc + i0 + 8 * a + g;
+        dst[0] = acc[a][b][0];
+        dst[ldc] = acc[a][b][1];
       }
-#pragma unroll
-      for (int a = 0; a < 2; ++a)
-#pragma unroll
-        for (int b = 0; b < 2; ++b) {
-          if ((a == 0 || r1) && (b == 0 || c1)) {
-            double *dst = C + (j0 + 8 * b + 2 * t) * ldc + i0 + 8 * a + g;
-            dst[0] = acc[a][b][0];
-            dst[ldc] = acc[a][b][1];
-          }
-        }
+    }
+}
+
+// Whole product on the CTA: 16 x 16 blocks dealt round-robin to the warps, slot numbers
+// starting at `first` (so that consecutive products of one phase share the deal);
+// LOWER computes only blocks on or below the block diagonal (whole blocks).  Returns
+// the next free slot number.
+template <bool TA, bool TB, bool ACC, bool LOWER, bool KTRI = false>
+__device__ int cta_gemm(double *C, int ldc, const double *A, int lda, const double *B, int ldb,
+                        int Mo, int No, int K, double sign, int first = 0) {
+  const int warp = threadIdx.x >> 5;
+  const int tm = (Mo + 15) >> 4, tn = (No + 15) >> 4;
+  const int count = LOWER ? tm * (tm + 1) / 2 : tm * tn;
+  // first local slot of this warp: smallest s >= 0 with (first + s) % kWarps == warp
+  int s = (warp - first) & (kWarps - 1);
+  int ti = 0, tj = s;  // (row, column) of slot s for the rectangular deal
+  if (!LOWER)
+    while (tj >= tn) { tj -= tn; ++ti; }
+  for (; s < count; s += kWarps) {
+    if (LOWER) { ti = kTriRow[s]; tj = kTriCol[s]; }
+    gemm_block<TA, TB, ACC, KTRI>(C, ldc, A, lda, B, ldb, Mo, No, K, sign, ti << 4, tj << 4);
+    if (!LOWER) {
+      tj += kWarps;
+      while (tj >= tn) { tj -= tn; ++ti; }
     }
   }
+  return first + count;
 }
 
 // y[i] = base[i] + sign * sum_j op(A)(i, j) x[j],  i < rows, j < cols; four threads per
@@ -154,6 +188,35 @@ __device__ void cta_matvec(double *y, const double *base, const double *A, int l
     if (i < rows && part == 0) y[i] = (base != nullptr ? base[i] : 0.0) + sign * acc;
   }
 }
+
+// Phase timing of the backward kernel (build with -DSIPOC_CTA_TIMING; block 0 prints the
+// cycles per phase summed over its stages).  Compiled out otherwise.
+#ifdef SIPOC_CTA_TIMING
+__device__ long long g_tick[24];
+#define TICK(slot)                                         \
+  do {                                                     \
+    __syncthreads();                                       \
+    if (threadIdx.x == 0 && blockIdx.x == 0) {             \
+      const long long now__ = clock64();                   \
+      g_tick[slot] += now__ - g_tick[23];                  \
+      g_tick[23] = now__;                                  \
+    }                                                      \
+  } while (0)
+// Thread-0-only lap timer (no barrier): for the panel warps' critical path.
+#define LAP(slot)                                          \
+  do {                                                     \
+    if (threadIdx.x == 0 && blockIdx.x == 0) {             \
+      const long long now__ = clock64();                   \
+      g_tick[slot] += now__ - lap__;                       \
+      lap__ = now__;                                       \
+    }                                                      \
+  } while (0)
+#define LAP_BEGIN() long long lap__ = clock64()
+#else
+#define TICK(slot) do { } while (0)
+#define LAP(slot) do { } while (0)
+#define LAP_BEGIN() do { } while (0)
+#endif
 
 // Cholesky factor L (packed lower, diagonal included) of the 8 x 8 block at `blk`, in
 // registers; d[j] = 1 / L(j, j).  Right-looking, so the dependent chain per column is
@@ -205,67 +268,166 @@ __device__ __forceinline__ void inv8(const double (&L)[36], const double (&d)[8]
 
 // In-place inverse of a symmetric positive definite n x n matrix given by its
 // LOWER triangle (n a multiple of 8, n <= 64): blocked right-looking Cholesky
-// (8-wide panels, DMMA trailing updates), block-column triangular inverse (one warp
-// per block column), then L^-T L^-1.  On return A holds the full symmetric inverse.
-// `scratch` is an n x ld array, `dinv` holds n / 8 blocks of 8 x 8, `ddiag` n doubles.  Returns false
-// when a pivot is <= 0 (Eigen LLT's failure criterion).  All threads must call it.
-// `idle(kb, nb)` is called in block step kb by the six warps that have no part in the
-// diagonal factor / panel solve: the caller uses it to issue the next stage's cp.async
-// copies off the critical path (issuing thousands of scattered 8-byte copies stalls the
-// issuing warp on the load/store queue, so it must not be a warp the factorization needs).
+// (8-wide panels with look-ahead, DMMA trailing updates), recursive triangular inverse,
+// then L^-T L^-1.  On return A holds the inverse: lower triangle always, the full
+// symmetric matrix when `mirror`.  `scratch` is an n x ld array, `tbuf` an (n / 2)-column
+// array of the same ld, `ddiag` n doubles.  Returns false when a pivot is <= 0 (Eigen
+// LLT's failure criterion).  All threads must call it.  `idle(kb, nb)` is called in
+// block step kb by the six warps that are not on the factorization's critical path: the
+// caller uses it to issue the next stage's cp.async copies.
 template <class Idle>
-__device__ bool cta_spd_inverse(double *A, int ld, int n, double *scratch, double *dinv,
-                                double *ddiag, Idle idle, int n_live = -1) {
+__device__ bool cta_spd_inverse(double *A, int ld, int n, double *scratch, double *tbuf,
+                                double *ddiag, Idle idle, int n_live = -1, bool mirror = true) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   bool ok = true;
   const int nb = n >> 3;
   // Rows / columns >= n_live are an identity padding block (their panel rows are exactly
   // zero): the Cholesky leaves them untouched, only their trivial factor is recorded.
   const int nb_live = n_live < 0 ? nb : (n_live + 7) >> 3;
-  for (int i = nb_live * 8 + tid; i < n; i += kThreads) ddiag[i] = 1.0;
+  const int nl = nb_live << 3;
+  for (int i = nl + tid; i < n; i += kThreads) ddiag[i] = 1.0;
+  // Blocks of `scratch` above the block diagonal: zero (read by the triangular inverse).
+  for (int blk = warp; blk < 64; blk += kWarps) {  // (bi, bj) over an 8 x 8 grid of blocks
+    const int bi = blk & 7, bj = blk >> 3;
+    if (bi < bj && bj < nb) {
+      double *z = scratch + ((bj << 3) + (lane >> 3)) * ld + (bi << 3) + (lane & 7);
+      z[0] = 0.0;
+      z[4 * ld] = 0.0;
+    }
+  }
+  TICK(10);
+  // Blocked Cholesky with look-ahead.  Warps 0-1 (the panel warps) own the critical
+  // path: factor the diagonal block kb, solve the panel below it, apply that panel to
+  // block column kb + 1 only, and go on to step kb + 1.  Warps 2-7 (the trailing warps)
+  // apply panel kb to block columns kb + 2.. meanwhile and then issue staging copies.
+  // Named barriers: 1 = the panel pair; 2 / 3 (step parity) = "panel kb is complete";
+  // 4 / 5 (step parity) = "the trailing update of step kb is complete", which the panel
+  // warps need before they touch block column kb + 2 in step kb + 1.  The parity keeps
+  // arrivals of consecutive steps on different barriers.
   for (int kb = 0; kb < nb_live; ++kb) {
-    const int c0 = kb << 3, c1 = c0 + 8, rem = n - c1;
-    // The two warps that own panel rows factor the 8 x 8 diagonal block redundantly in
-    // registers (no exchange before the panel solve); the other six warps go straight
-    // to the barrier, so the FP64 pipes are not spent on eight copies of the same chain.
+    const int c0 = kb << 3, c1 = c0 + 8, rem = nl - c1, par = kb & 1;
     if (tid < 64) {
+      // Both panel warps factor the 8 x 8 diagonal block redundantly in registers (no
+      // exchange before the panel solve).
       double L[36], d[8];
+      LAP_BEGIN();
       ok = chol8(A + c0 * ld + c0, ld, L, d) && ok;
-      if (tid < rem) {  // row r of L21:  x L11' = A21(r, :)
-        double *row = A + c0 * ld + c1 + tid;
-        double x[8];
+      LAP(17);
+      // Thread r < rem: row r of L21, x L11' = A21(r, :).  Threads 56..63: the rows of
+      // L11 itself by the same recurrence (kept in registers until both warps have read
+      // the block).
+      const bool diag_row = tid >= 56;
+      const int row_idx = diag_row ? c0 + (tid - 56) : c1 + tid;
+      double x[8];
+      if (tid < rem || diag_row) {
+        double *row = A + c0 * ld + row_idx;
+        double a[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = row[j * ld];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          double sacc = row[j * ld];
+          double sacc = a[j];
 #pragma unroll
           for (int p = 0; p < 8; ++p)
             if (p < j) sacc -= x[p] * L[pk(j, p, 8)];
           x[j] = sacc * d[j];
-          row[j * ld] = x[j];
+        }
+        if (!diag_row) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) row[j * ld] = x[j];
         }
       }
-      asm volatile("bar.sync 1, 64;" ::: "memory");  // both warps have read the block
-      if (tid == 63) {  // publish L11 (rem <= 56, so this thread owns no panel row)
+      LAP(18);
+      asm volatile("bar.sync 1, 64;" ::: "memory");  // panel written, block read by both
+      LAP(19);
+      if (rem > 8) {
+        __threadfence_block();
+        if (par == 0) asm volatile("bar.arrive 2, 256;" ::: "memory");
+        else asm volatile("bar.arrive 3, 256;" ::: "memory");
+      }
+      if (diag_row) {  // publish L11 (upper part zero) and 1 / L(j, j)
+        const int i = tid - 56;
+        double *row = A + c0 * ld + row_idx;
+        double di = d[0];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          ddiag[c0 + j] = d[j];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) A[(c0 + j) * ld + c0 + i] = (i >= j) ? L[(i >= j) ? pk(i, j, 8) : 0] : 0.0;
+          row[j * ld] = (j <= i) ? x[j] : 0.0;
+          if (j == i) di = d[j];
         }
+        ddiag[c0 + i] = di;
+      }
+      if (rem > 0) {
+        if (kb >= 1) {  // block column kb + 1 has received panel kb - 1 from the trailing warps
+          if (par == 1) asm volatile("bar.sync 4, 256;" ::: "memory");
+          else asm volatile("bar.sync 5, 256;" ::: "memory");
+        }
+        LAP(20);
+        // Look-ahead: A(c1.., c1..c1+8) -= L21 L21(0..8, :)'.  At most 7 row tiles, dealt
+        // alternately to the two warps; all of a warp's tiles are in flight together.
+        {
+          const int ntile = rem >> 3;
+          double acc[4][2], a[4][2], bb[2];
+#pragma unroll
+          for (int s2 = 0; s2 < 2; ++s2) bb[s2] = A[(c0 + 4 * s2 + t) * ld + c1 + g];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int mt = warp + 2 * u;
+            if (mt < ntile) {
+              const int r0 = c1 + (mt << 3);
+              acc[u][0] = A[(c1 + 2 * t) * ld + r0 + g];
+              acc[u][1] = A[(c1 + 2 * t + 1) * ld + r0 + g];
+#pragma unroll
+              for (int s2 = 0; s2 < 2; ++s2) a[u][s2] = -A[(c0 + 4 * s2 + t) * ld + r0 + g];
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int mt = warp + 2 * u;
+            if (mt < ntile) {
+              dmma(acc[u], a[u][0], bb[0]);
+              dmma(acc[u], a[u][1], bb[1]);
+              const int r0 = c1 + (mt << 3);
+              A[(c1 + 2 * t) * ld + r0 + g] = acc[u][0];
+              A[(c1 + 2 * t + 1) * ld + r0 + g] = acc[u][1];
+            }
+          }
+        }
+        LAP(21);
+        asm volatile("bar.sync 1, 64;" ::: "memory");
+        LAP(22);
       }
     } else {
+      if (rem > 8) {
+        if (par == 0) asm volatile("bar.sync 2, 256;" ::: "memory");
+        else asm volatile("bar.sync 3, 256;" ::: "memory");
+        // A(c2.., c2..) -= L21(8.., :) L21(8.., :)'  on 8 x 8 tiles of the lower triangle.
+        const int c2 = c1 + 8, nt2 = (rem - 8) >> 3;
+        for (int slot = warp - 2; slot < nt2 * (nt2 + 1) / 2; slot += kWarps - 2) {
+          const int ti = kTriRow[slot], tj = kTriCol[slot];
+          const int r0 = c2 + (ti << 3), q0 = c2 + (tj << 3);
+          double *cblk = A + (q0 + 2 * t) * ld + r0 + g;
+          double acc[2] = {cblk[0], cblk[ld]};
+#pragma unroll
+          for (int s2 = 0; s2 < 2; ++s2) {
+            const double a = -A[(c0 + 4 * s2 + t) * ld + r0 + g];
+            const double bb = A[(c0 + 4 * s2 + t) * ld + q0 + g];
+            dmma(acc, a, bb);
+          }
+          cblk[0] = acc[0];
+          cblk[ld] = acc[1];
+        }
+        __threadfence_block();
+        if (par == 0) asm volatile("bar.arrive 4, 256;" ::: "memory");
+        else asm volatile("bar.arrive 5, 256;" ::: "memory");
+      }
       idle(kb, nb_live);
     }
-    __syncthreads();
-    if (rem > 0) {
-      // A22 -= L21 L21'
-      cta_gemm<false, true, true, true>(A + c1 * ld + c1, ld, A + c0 * ld + c1, ld,
-                                        A + c0 * ld + c1, ld, rem, rem, 8, -1.0);
-      __syncthreads();
-    }
   }
+  __syncthreads();
+  TICK(11);
 
-  // Inverses of the diagonal blocks, one warp per block (off the Cholesky critical path).
+  // X = L^-1 in `scratch`.
+  // Level 0: the 8 x 8 diagonal blocks, one warp per block, in registers.
   for (int kb = warp; kb < nb; kb += kWarps) {
     double L[36], d[8], X[36];
 #pragma unroll
@@ -277,61 +439,87 @@ __device__ bool cta_spd_inverse(double *A, int ld, int n, double *scratch, doubl
     }
     inv8(L, d, X);
     if (lane == 0) {
+      double *dst = scratch + (kb * 8) * ld + kb * 8;
 #pragma unroll
       for (int j = 0; j < 8; ++j)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) dinv[kb * 64 + j * 8 + i] = (i >= j) ? X[(i >= j) ? pk(i, j, 8) : 0] : 0.0;
+        for (int i = 0; i < 8; ++i) dst[j * ld + i] = (i >= j) ? X[(i >= j) ? pk(i, j, 8) : 0] : 0.0;
     }
   }
   __syncthreads();
-
-  // Triangular inverse, block column kb by warp kb:  X_kk = inv(L_kk),
-  // X_ik = -inv(L_ii) sum_{p=kb}^{i-1} L_ip X_pk.
-  for (int kb = warp; kb < nb; kb += kWarps) {
-    for (int ib = 0; ib < nb; ++ib) {
-      double *dst = scratch + (kb * 8) * ld + ib * 8;  // block (ib, kb)
-      if (ib < kb) {
-        dst[(2 * t) * ld + g] = 0.0;
-        dst[(2 * t + 1) * ld + g] = 0.0;
-      } else if (ib == kb) {
-        dst[(2 * t) * ld + g] = dinv[kb * 64 + (2 * t) * 8 + g];
-        dst[(2 * t + 1) * ld + g] = dinv[kb * 64 + (2 * t + 1) * 8 + g];
-      } else {
-        double acc[2] = {0.0, 0.0};
-        for (int pb = kb; pb < ib; ++pb) {
+  TICK(13);
+  // Levels s = 8, 16, 32: with L = [L11 0; L21 L22] on 2s x 2s diagonal blocks,
+  // X21 = -X22 (L21 X11).  Every level is two batched products on 8 x 8 tiles dealt to
+  // all warps (T = L21 X11 into tbuf, then X21), so the dependent chain is
+  // 2 log2(n / 8) short products instead of n / 8 block rows.  The blocks of X above
+  // the diagonal were zeroed on entry, so every tile runs the full k range (equal trip
+  // counts let a warp interleave its tiles).
+  for (int sz = 8; sz < n; sz <<= 1) {
+    const int tc = sz >> 3, lt = 31 - __clz(tc);  // tile columns per pair (a power of two)
+    const int pairs = (n + 2 * sz - 1) >> (lt + 4);
+    const int total = pairs << (2 * lt);
+    for (int pass = 0; pass < 2; ++pass) {
+      // Two units per warp at a time, two accumulators per unit (even / odd k steps):
+      // four independent DMMA chains of sz / 8 links.
+      for (int u0 = warp; u0 < total; u0 += 2 * kWarps) {
+        const double *pa[2], *pb[2];
+        double *dst[2];
+        bool live[2];
 #pragma unroll
-          for (int s = 0; s < 2; ++s) {
-            const double a = A[(pb * 8 + 4 * s + t) * ld + ib * 8 + g];           // L_ip(g, 4s+t)
-            const double b = scratch[(kb * 8 + g) * ld + pb * 8 + 4 * s + t];     // X_pk(4s+t, g)
-            dmma(acc, a, b);
+        for (int z = 0; z < 2; ++z) {
+          const int unit = u0 + z * kWarps;
+          const int q = unit >> (2 * lt), w = unit & ((1 << (2 * lt)) - 1);
+          const int ti = w >> lt, tj = w & (tc - 1);
+          const int c0 = 2 * q * sz, r0 = c0 + sz;
+          live[z] = unit < total && r0 + (ti << 3) < n;
+          double *tq = tbuf + (q * sz) * ld;  // T of pair q: (rows of L21) x sz
+          if (pass == 0) {  // T = L21 X11
+            pa[z] = A + (c0 + t) * ld + r0 + (ti << 3) + g;
+            pb[z] = scratch + (c0 + (tj << 3) + g) * ld + c0 + t;
+            dst[z] = tq + ((tj << 3) + 2 * t) * ld + (ti << 3) + g;
+          } else {  // X21 = -X22 T
+            pa[z] = scratch + (r0 + t) * ld + r0 + (ti << 3) + g;
+            pb[z] = tq + ((tj << 3) + g) * ld + t;
+            dst[z] = scratch + (c0 + (tj << 3) + 2 * t) * ld + r0 + (ti << 3) + g;
           }
         }
-        dst[(2 * t) * ld + g] = acc[0];  // park T in the destination block
-        dst[(2 * t + 1) * ld + g] = acc[1];
-        __syncwarp();
-        double res[2] = {0.0, 0.0};
+        double acc[2][2][2] = {};
+        for (int k0 = 0; k0 < sz; k0 += 8) {
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          const double a = -dinv[ib * 64 + (4 * s + t) * 8 + g];  // -inv(L_ii)(g, 4s+t)
-          const double b = dst[g * ld + 4 * s + t];               // T(4s+t, g)
-          dmma(res, a, b);
+          for (int z = 0; z < 2; ++z) {
+            if (live[z]) {
+              const double a0 = pa[z][k0 * ld], a1 = pa[z][(k0 + 4) * ld];
+              const double b0 = pb[z][k0], b1 = pb[z][k0 + 4];
+              dmma(acc[z][0], a0, b0);
+              dmma(acc[z][1], a1, b1);
+            }
+          }
         }
-        __syncwarp();
-        dst[(2 * t) * ld + g] = res[0];
-        dst[(2 * t + 1) * ld + g] = res[1];
+        const double sgn = pass == 0 ? 1.0 : -1.0;
+#pragma unroll
+        for (int z = 0; z < 2; ++z) {
+          if (live[z]) {
+            dst[z][0] = sgn * (acc[z][0][0] + acc[z][1][0]);
+            dst[z][ld] = sgn * (acc[z][0][1] + acc[z][1][1]);
+          }
+        }
       }
-      __syncwarp();
+      __syncthreads();
     }
   }
+  TICK(14);
+  // A = L^-T L^-1 (lower blocks, whole diagonal blocks): (i, j) sums over k >= i only.
+  cta_gemm<true, false, false, true, true>(A, ld, scratch, ld, scratch, ld, n, n, n, 1.0);
   __syncthreads();
-  // A = L^-T L^-1 (lower blocks, whole diagonal blocks), then mirror to the upper part.
-  cta_gemm<true, false, false, true>(A, ld, scratch, ld, scratch, ld, n, n, n, 1.0);
-  __syncthreads();
-  for (int e = tid; e < n * n; e += kThreads) {
-    const int i = e % n, j = e / n;
-    if (i > j) A[i * ld + j] = A[j * ld + i];
+  TICK(15);
+  if (mirror) {
+    for (int e = tid; e < n * n; e += kThreads) {
+      const int i = e % n, j = e / n;
+      if (i > j) A[i * ld + j] = A[j * ld + i];
+    }
+    __syncthreads();
   }
-  __syncthreads();
+  TICK(16);
   return ok;
 }
 
@@ -349,8 +537,8 @@ struct CtaSmem {
   static constexpr int oPuu = oPux + N * LDM;         // Psi_uu -> G^-1           (MP x MP)
   static constexpr int oK = oPuu + MP * LDM;          // K                        (MP x N)
   static constexpr int oGs = oK + N * LDM;            // scratch of the G inverse (MP x MP)
-  static constexpr int oDinv = oGs + MP * LDM;        // 8 x 8 diagonal inverses
-  static constexpr int oDd = oDinv + (N / 8) * 64;    // 1 / L(j, j) of the factor in flight
+  static constexpr int oDd = oGs + MP * LDM;          // 1 / L(j, j) of the factor in flight
+  static_assert(2 * MP >= N, "the F inverse parks its T blocks in columns N.. of S");
   static constexpr int oVec = oDd + N;
   static constexpr int vq = oVec, vr = vq + N, vc = vr + MP, vd = vc + N, vv = vd + N,
                        vdl = vv + N, vsd = vdl + N, vsdi = vsd + N, vf = vsdi + N, vg = vf + N,
@@ -371,7 +559,7 @@ riccati_backward_cta(LqrIn pm, int *status_out, double *store, double *scratch, 
   const int64_t b = blockIdx.x;
   const size_t L_ = static_cast<size_t>(ld);
   double *Wp = sm + S::oW, *Zb = sm + S::oZ, *Sb = sm + S::oS, *Pux = sm + S::oPux,
-         *Puu = sm + S::oPuu, *Kb = sm + S::oK, *Gs = sm + S::oGs, *Dinv = sm + S::oDinv,
+         *Puu = sm + S::oPuu, *Kb = sm + S::oK, *Gs = sm + S::oGs,
          *Dd = sm + S::oDd;
   double *q_s = sm + S::vq, *r_s = sm + S::vr, *c_s = sm + S::vc, *d_s = sm + S::vd,
          *v_s = sm + S::vv, *dl_s = sm + S::vdl, *sd_s = sm + S::vsd, *sdi_s = sm + S::vsdi,
@@ -402,15 +590,19 @@ riccati_backward_cta(LqrIn pm, int *status_out, double *store, double *scratch, 
   auto stage_edge_z = [&](int k, int t0, int nt, int part, int parts) {  // A_k, B_k -> Z
     const double *gA = bA + static_cast<size_t>(k) * N * N;
     const double *gB = bB + static_cast<size_t>(k) * N * M;
-    constexpr int total = N * N + N * M;
+    // Columns of A and B are contiguous both in the problem-major copy and in Z: pairs
+    // of rows move as 16-byte copies.
+    static_assert(N % 2 == 0 && LDN % 2 == 0 && S::oZ % 2 == 0, "16-byte staging of Z");
+    constexpr int total = (N * N + N * M) / 2;
     const int per = (total + parts - 1) / parts;
     const int hi = (part + 1) * per < total ? (part + 1) * per : total;
-    for (int e = part * per + (tid - t0); e < hi; e += nt) {
+    for (int p = part * per + (tid - t0); p < hi; p += nt) {
+      const int e = 2 * p;
       if (e < N * N) {
-        cp_async8(Zb + (e / N) * LDN + e % N, gA + e);
+        cp_async16(Zb + (e / N) * LDN + e % N, gA + e);
       } else {
         const int f = e - N * N;
-        cp_async8(Zb + (N + f / N) * LDN + f % N, gB + f);
+        cp_async16(Zb + (N + f / N) * LDN + f % N, gB + f);
       }
     }
   };
@@ -476,15 +668,16 @@ riccati_backward_cta(LqrIn pm, int *status_out, double *store, double *scratch, 
       if (i >= j) Wp[j * LDN + i] = sd_s[i] * Wp[j * LDN + i] * sd_s[j] + (i == j ? 1.0 : 0.0);
     }
     __syncthreads();
+    TICK(8);
     // M, R, q, r, c, delta of the next stage (and, after the terminal node, its A and B)
     // are issued by the idle warps of the F factorization's block steps.
-    const bool f_ok = cta_spd_inverse(Wp, LDN, N, Sb, Dinv, Dd, [&](int kb, int nb) {
+    const bool f_ok = cta_spd_inverse(Wp, LDN, N, Sb, Sb + N * LDN, Dd, [&](int kb, int nb) {
       if (k == 0) return;
       if (kb == 0) stage_edge_rest(k - 1, 64, kThreads - 64);
       if (kb == 1) stage_q_packed(k - 1, 64, kThreads - 64);
       if (k == T && kb >= 1 && kb < nb) stage_edge_z(k - 1, 64, kThreads - 64, kb - 1, nb - 1);
       cp_async_commit();
-    });
+    }, -1, false);  // the W pass below reads the lower triangle only
     if (!__syncthreads_and(f_ok) && status == SIPOC_FACTOR_SUCCESS)
       status = SIPOC_FACTOR_F_FACTORIZATION_FAILURE;
     for (int e = tid; e < N * N; e += kThreads) {
@@ -497,6 +690,7 @@ riccati_backward_cta(LqrIn pm, int *status_out, double *store, double *scratch, 
       }
     }
     __syncthreads();
+    TICK(9);
   };
 
   // Padding, written once: columns N+M.. of Z are zero, rows M.. of Psi_ux are zero,
@@ -509,6 +703,12 @@ riccati_backward_cta(LqrIn pm, int *status_out, double *store, double *scratch, 
     Puu[e] = (i == j && i >= M && i < MP) ? 1.0 : 0.0;
   }
   if (tid < MP) r_s[tid] = 0.0;
+#ifdef SIPOC_CTA_TIMING
+  if (tid == 0 && b == 0) {
+    for (int i = 0; i < 23; ++i) g_tick[i] = 0;
+    g_tick[23] = clock64();
+  }
+#endif
   __syncthreads();
 
   // ---- terminal node ----------------------------------------------------------
@@ -523,8 +723,10 @@ riccati_backward_cta(LqrIn pm, int *status_out, double *store, double *scratch, 
   process_node(T);
 
   for (int k = T - 1; k >= 0; --k) {
+    TICK(0);
     cp_async_wait_all();
     __syncthreads();
+    TICK(1);
 
     if (SOLVE) {
       // g = v' - W'(delta' o v' - c')
@@ -536,32 +738,39 @@ riccati_backward_cta(LqrIn pm, int *status_out, double *store, double *scratch, 
       cta_matvec<true>(hw_s, q_s, Zb, LDN, g_s, N, N, 1.0);
       cta_matvec<true>(hw_s + N, r_s, Zb + N * LDN, LDN, g_s, MP, N, 1.0);
     }
+    TICK(2);
     // S = W' Z
     cta_gemm<false, false, false, false>(Sb, LDN, Wp, LDN, Zb, LDN, N, NZ, N, 1.0);
     __syncthreads();
+    TICK(3);
     // Psi_xx base: Q_k lower (prefetched, packed, in the K buffer) into the now free W' buffer.
     for (int e = tid; e < N * N; e += kThreads) {
       const int i = e % N, j = e / N;
       if (i >= j) Wp[j * LDN + i] = Kb[pk(i, j, N)];
     }
-    // Psi_ux += B' S_x ,  Psi_uu += B' S_u   (rows = u, K = N)
-    cta_gemm<true, false, true, false>(Pux, LDM, Zb + N * LDN, LDN, Sb, LDN, MP, N, N, 1.0);
-    cta_gemm<true, false, true, true>(Puu, LDM, Zb + N * LDN, LDN, Sb + N * LDN, LDN, MP, MP, N,
-                                      1.0);
     __syncthreads();
-    // Psi_xx += A' S_x (lower blocks)
-    cta_gemm<true, false, true, true>(Wp, LDN, Zb, LDN, Sb, LDN, N, N, N, 1.0);
+    // Psi_ux += B' S_x,  Psi_uu += B' S_u (rows = u, K = N),  Psi_xx += A' S_x (lower
+    // blocks): one deal of all their blocks over the warps.
+    {
+      int slot = cta_gemm<true, false, true, false>(Pux, LDM, Zb + N * LDN, LDN, Sb, LDN, MP, N, N,
+                                                    1.0, 0);
+      slot = cta_gemm<true, false, true, true>(Puu, LDM, Zb + N * LDN, LDN, Sb + N * LDN, LDN, MP,
+                                               MP, N, 1.0, slot);
+      cta_gemm<true, false, true, true>(Wp, LDN, Zb, LDN, Sb, LDN, N, N, N, 1.0, slot);
+    }
     __syncthreads();
+    TICK(5);
 
     // G^-1 (full, in Puu).  Z is consumed: A, B of the next stage are issued by the idle
     // warps of the G factorization's block steps and fly during the rest of this stage.
-    const bool g_ok = cta_spd_inverse(Puu, LDM, MP, Gs, Dinv, Dd, [&](int kb, int nb) {
+    const bool g_ok = cta_spd_inverse(Puu, LDM, MP, Gs, Sb, Dd, [&](int kb, int nb) {
       if (k == 0) return;
       stage_edge_z(k - 1, 64, kThreads - 64, kb, nb);
       cp_async_commit();
     }, M);
     if (!__syncthreads_and(g_ok) && status == SIPOC_FACTOR_SUCCESS)
       status = SIPOC_FACTOR_G_FACTORIZATION_FAILURE;
+    TICK(6);
     // K = -G^-1 Psi_ux
     cta_gemm<false, false, false, false>(Kb, LDM, Puu, LDM, Pux, LDM, MP, N, MP, -1.0);
     if (SOLVE) cta_matvec<false>(kk_s, nullptr, Puu, LDM, hw_s + N, MP, MP, -1.0);  // k = -G^-1 h
@@ -579,8 +788,19 @@ riccati_backward_cta(LqrIn pm, int *status_out, double *store, double *scratch, 
     }
     if (SOLVE && tid < M) __stcs(kst + (static_cast<size_t>(k) * M + tid) * L_, kk_s[tid]);
     __syncthreads();
+    TICK(7);
     process_node(k);
   }
+#ifdef SIPOC_CTA_TIMING
+  __syncthreads();
+  if (tid == 0 && b == 0) {
+    // 0 loop top, 1 staging wait, 2 affine, 3 S, 4 u-block, 5 Psi_xx, 6 G inverse (10..16 inside
+    // both inverses), 7 K / V / stores, 8 F build, 9 W finish; inside the inverses: 10 entry,
+    // 11 diagonal block + panel, 12 trailing update, 13 block inverses, 14 L^-1, 15 L^-T L^-1,
+    // 16 mirror.
+    for (int i = 0; i < 23; ++i) printf("tick %2d  %10lld cycles / stage\n", i, g_tick[i] / T);
+  }
+#endif
   if (status_out != nullptr && tid == 0) status_out[b] = status;
 }
 
