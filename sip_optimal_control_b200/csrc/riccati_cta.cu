@@ -36,6 +36,7 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
+constexpr int kPanelThreads = 32;  // warp 0 runs the Cholesky chain; the others stage
 
 __host__ __device__ constexpr int tri(int n) { return n * (n + 1) / 2; }
 __host__ __device__ constexpr int pk(int i, int j, int n) {
@@ -192,14 +193,15 @@ __device__ void cta_matvec(double *y, const double *base, const double *A, int l
 // Phase timing of the backward kernel (build with -DSIPOC_CTA_TIMING; block 0 prints the
 // cycles per phase summed over its stages).  Compiled out otherwise.
 #ifdef SIPOC_CTA_TIMING
-__device__ long long g_tick[24];
+__device__ unsigned long long g_tick[24];
+__shared__ long long tick_last__;
 #define TICK(slot)                                         \
   do {                                                     \
     __syncthreads();                                       \
     if (threadIdx.x == 0 && blockIdx.x == 0) {             \
       const long long now__ = clock64();                   \
-      g_tick[slot] += now__ - g_tick[23];                  \
-      g_tick[23] = now__;                                  \
+      atomicAdd(&g_tick[slot], (unsigned long long)(now__ - tick_last__)); \
+      tick_last__ = now__;                                 \
     }                                                      \
   } while (0)
 // Thread-0-only lap timer (no barrier): for the panel warps' critical path.
@@ -207,14 +209,23 @@ __device__ long long g_tick[24];
   do {                                                     \
     if (threadIdx.x == 0 && blockIdx.x == 0) {             \
       const long long now__ = clock64();                   \
-      g_tick[slot] += now__ - lap__;                       \
+      atomicAdd(&g_tick[slot], (unsigned long long)(now__ - lap__)); \
       lap__ = now__;                                       \
     }                                                      \
   } while (0)
 #define LAP_BEGIN() long long lap__ = clock64()
+#define LAP1(slot)                                         \
+  do {                                                     \
+    if (threadIdx.x == 32 && blockIdx.x == 0) {            \
+      const long long now__ = clock64();                   \
+      atomicAdd(&g_tick[slot], (unsigned long long)(now__ - lap__)); \
+      lap__ = now__;                                       \
+    }                                                      \
+  } while (0)
 #else
 #define TICK(slot) do { } while (0)
 #define LAP(slot) do { } while (0)
+#define LAP1(slot) do { } while (0)
 #define LAP_BEGIN() do { } while (0)
 #endif
 
@@ -249,23 +260,6 @@ __device__ __forceinline__ bool chol8(const double *blk, int ld, double (&L)[36]
   return ok;
 }
 
-// X = L^-1 (packed lower) of an 8 x 8 lower-triangular L with d[j] = 1 / L(j, j).
-__device__ __forceinline__ void inv8(const double (&L)[36], const double (&d)[8], double (&X)[36]) {
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (i >= j) {
-        double s = (i == j) ? 1.0 : 0.0;
-#pragma unroll
-        for (int p = 0; p < 8; ++p)
-          if (p >= j && p < i) s -= L[pk(i, p, 8)] * X[pk(p, j, 8)];
-        X[pk(i, j, 8)] = s * d[i];
-      }
-    }
-  }
-}
-
 // In-place inverse of a symmetric positive definite n x n matrix given by its
 // LOWER triangle (n a multiple of 8, n <= 64): blocked right-looking Cholesky
 // (8-wide panels with look-ahead, DMMA trailing updates), recursive triangular inverse,
@@ -273,7 +267,7 @@ __device__ __forceinline__ void inv8(const double (&L)[36], const double (&d)[8]
 // symmetric matrix when `mirror`.  `scratch` is an n x ld array, `tbuf` an (n / 2)-column
 // array of the same ld, `ddiag` n doubles.  Returns false when a pivot is <= 0 (Eigen
 // LLT's failure criterion).  All threads must call it.  `idle(kb, nb)` is called in
-// block step kb by the six warps that are not on the factorization's critical path: the
+// block step kb by the seven warps that are not on the factorization's critical path: the
 // caller uses it to issue the next stage's cp.async copies.
 template <class Idle>
 __device__ bool cta_spd_inverse(double *A, int ld, int n, double *scratch, double *tbuf,
@@ -296,115 +290,97 @@ __device__ bool cta_spd_inverse(double *A, int ld, int n, double *scratch, doubl
     }
   }
   TICK(10);
-  // Blocked Cholesky with look-ahead.  Warps 0-1 (the panel warps) own the critical
-  // path: factor the diagonal block kb, solve the panel below it, apply that panel to
-  // block column kb + 1 only, and go on to step kb + 1.  Warps 2-7 (the trailing warps)
-  // apply panel kb to block columns kb + 2.. meanwhile and then issue staging copies.
-  // Named barriers: 1 = the panel pair; 2 / 3 (step parity) = "panel kb is complete";
-  // 4 / 5 (step parity) = "the trailing update of step kb is complete", which the panel
-  // warps need before they touch block column kb + 2 in step kb + 1.  The parity keeps
-  // arrivals of consecutive steps on different barriers.
+  // Blocked Cholesky with look-ahead.  Warp 0 (the panel warp) owns the critical path:
+  // factor the diagonal block kb in registers, solve the panel below it (two rows per
+  // lane), update the next diagonal block with that panel, go on to step kb + 1 -- all
+  // inside one warp, so the chain only meets __syncwarp.  Warps 1-7 (the trailing
+  // warps) apply panel kb first to what the panel warp needs next -- the rest of block
+  // column kb + 1 and the diagonal block kb + 2 -- then to the remaining tiles of block
+  // columns kb + 2.., then issue staging copies.  Named barriers, alternating with the
+  // step parity so that arrivals of consecutive steps never meet on one barrier:
+  //   2 / 3  panel kb is complete          (panel warp arrives, trailing warps sync; it
+  //          also orders the trailing warps' steps among themselves)
+  //   4 / 5  the priority tiles of step kb are done (trailing warps arrive, the panel
+  //          warp syncs after the diagonal factor of step kb + 1)
   for (int kb = 0; kb < nb_live; ++kb) {
     const int c0 = kb << 3, c1 = c0 + 8, rem = nl - c1, par = kb & 1;
-    if (tid < 64) {
-      // Both panel warps factor the 8 x 8 diagonal block redundantly in registers (no
-      // exchange before the panel solve).
+    if (warp == 0) {
       double L[36], d[8];
       LAP_BEGIN();
       ok = chol8(A + c0 * ld + c0, ld, L, d) && ok;
       LAP(17);
-      // Thread r < rem: row r of L21, x L11' = A21(r, :).  Threads 56..63: the rows of
-      // L11 itself by the same recurrence (kept in registers until both warps have read
-      // the block).
-      const bool diag_row = tid >= 56;
-      const int row_idx = diag_row ? c0 + (tid - 56) : c1 + tid;
-      double x[8];
-      if (tid < rem || diag_row) {
-        double *row = A + c0 * ld + row_idx;
-        double a[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) a[j] = row[j * ld];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          double sacc = a[j];
-#pragma unroll
-          for (int p = 0; p < 8; ++p)
-            if (p < j) sacc -= x[p] * L[pk(j, p, 8)];
-          x[j] = sacc * d[j];
-        }
-        if (!diag_row) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) row[j * ld] = x[j];
-        }
-      }
+      if (kb >= 1 && rem > 0)  // the trailing warps of step kb - 1 updated this block column
+        asm volatile("bar.sync %0, 256;" ::"r"(5 - par) : "memory");
       LAP(18);
-      asm volatile("bar.sync 1, 64;" ::: "memory");  // panel written, block read by both
-      LAP(19);
-      if (rem > 8) {
-        __threadfence_block();
-        if (par == 0) asm volatile("bar.arrive 2, 256;" ::: "memory");
-        else asm volatile("bar.arrive 3, 256;" ::: "memory");
+      // Slot 0: row `lane` of L21; slot 1: row `lane + 32` of L21 (lanes 0..23), or row
+      // `lane - 24` of L11 itself by the same recurrence (lanes 24..31; rem <= 56).
+      // x L11' = A(row, c0..c0+8).
+      const bool diag_row = lane >= 24;
+      int row_idx[2] = {c1 + lane, diag_row ? c0 + (lane - 24) : c1 + 32 + lane};
+      bool live[2] = {lane < rem, diag_row || lane + 32 < rem};
+      double x[2][8];
+#pragma unroll
+      for (int z = 0; z < 2; ++z) {
+        if (live[z]) {
+          const double *row = A + c0 * ld + row_idx[z];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[z][j] = row[j * ld];
+        }
       }
-      if (diag_row) {  // publish L11 (upper part zero) and 1 / L(j, j)
-        const int i = tid - 56;
-        double *row = A + c0 * ld + row_idx;
+      // Right-looking: once x_j is known every later entry takes its term at once, so the
+      // dependent chain is one multiply and one FMA per column (same summation order as
+      // the row recurrence).
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+#pragma unroll
+        for (int z = 0; z < 2; ++z) {
+          x[z][j] *= d[j];
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            if (c > j) x[z][c] -= x[z][j] * L[pk(c, j, 8)];
+        }
+      }
+      __syncwarp();  // every lane has read the diagonal block
+#pragma unroll
+      for (int z = 0; z < 2; ++z) {
+        if (live[z]) {
+          double *row = A + c0 * ld + row_idx[z];
+          const int i = lane - 24;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) row[j * ld] = (z == 0 || !diag_row || j <= i) ? x[z][j] : 0.0;
+        }
+      }
+      if (diag_row) {  // 1 / L(i, i)
         double di = d[0];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          row[j * ld] = (j <= i) ? x[j] : 0.0;
-          if (j == i) di = d[j];
-        }
-        ddiag[c0 + i] = di;
+        for (int j = 1; j < 8; ++j)
+          if (j == lane - 24) di = d[j];
+        ddiag[c0 + lane - 24] = di;
       }
+      __syncwarp();
+      LAP(19);
+      if (rem > 8) asm volatile("bar.arrive %0, 256;" ::"r"(2 + par) : "memory");
       if (rem > 0) {
-        if (kb >= 1) {  // block column kb + 1 has received panel kb - 1 from the trailing warps
-          if (par == 1) asm volatile("bar.sync 4, 256;" ::: "memory");
-          else asm volatile("bar.sync 5, 256;" ::: "memory");
+        // A(c1..c1+8, c1..c1+8) -= L21(0..8, :) L21(0..8, :)'
+        double *cblk = A + (c1 + 2 * t) * ld + c1 + g;
+        double acc[2] = {cblk[0], cblk[ld]};
+#pragma unroll
+        for (int s2 = 0; s2 < 2; ++s2) {
+          const double a = A[(c0 + 4 * s2 + t) * ld + c1 + g];
+          dmma(acc, -a, a);
         }
-        LAP(20);
-        // Look-ahead: A(c1.., c1..c1+8) -= L21 L21(0..8, :)'.  At most 7 row tiles, dealt
-        // alternately to the two warps; all of a warp's tiles are in flight together.
-        {
-          const int ntile = rem >> 3;
-          double acc[4][2], a[4][2], bb[2];
-#pragma unroll
-          for (int s2 = 0; s2 < 2; ++s2) bb[s2] = A[(c0 + 4 * s2 + t) * ld + c1 + g];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int mt = warp + 2 * u;
-            if (mt < ntile) {
-              const int r0 = c1 + (mt << 3);
-              acc[u][0] = A[(c1 + 2 * t) * ld + r0 + g];
-              acc[u][1] = A[(c1 + 2 * t + 1) * ld + r0 + g];
-#pragma unroll
-              for (int s2 = 0; s2 < 2; ++s2) a[u][s2] = -A[(c0 + 4 * s2 + t) * ld + r0 + g];
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int mt = warp + 2 * u;
-            if (mt < ntile) {
-              dmma(acc[u], a[u][0], bb[0]);
-              dmma(acc[u], a[u][1], bb[1]);
-              const int r0 = c1 + (mt << 3);
-              A[(c1 + 2 * t) * ld + r0 + g] = acc[u][0];
-              A[(c1 + 2 * t + 1) * ld + r0 + g] = acc[u][1];
-            }
-          }
-        }
+        cblk[0] = acc[0];
+        cblk[ld] = acc[1];
+        __syncwarp();
         LAP(21);
-        asm volatile("bar.sync 1, 64;" ::: "memory");
-        LAP(22);
       }
     } else {
+      LAP_BEGIN();
       if (rem > 8) {
-        if (par == 0) asm volatile("bar.sync 2, 256;" ::: "memory");
-        else asm volatile("bar.sync 3, 256;" ::: "memory");
-        // A(c2.., c2..) -= L21(8.., :) L21(8.., :)'  on 8 x 8 tiles of the lower triangle.
-        const int c2 = c1 + 8, nt2 = (rem - 8) >> 3;
-        for (int slot = warp - 2; slot < nt2 * (nt2 + 1) / 2; slot += kWarps - 2) {
-          const int ti = kTriRow[slot], tj = kTriCol[slot];
-          const int r0 = c2 + (ti << 3), q0 = c2 + (tj << 3);
+        asm volatile("bar.sync %0, 256;" ::"r"(2 + par) : "memory");
+        LAP1(12);
+        // One 8 x 8 tile C(r0.., q0..) -= L21(r0.., :) L21(q0.., :)' of the trailing matrix.
+        auto tile = [&](int r0, int q0) {
           double *cblk = A + (q0 + 2 * t) * ld + r0 + g;
           double acc[2] = {cblk[0], cblk[ld]};
 #pragma unroll
@@ -415,36 +391,46 @@ __device__ bool cta_spd_inverse(double *A, int ld, int n, double *scratch, doubl
           }
           cblk[0] = acc[0];
           cblk[ld] = acc[1];
-        }
-        __threadfence_block();
-        if (par == 0) asm volatile("bar.arrive 4, 256;" ::: "memory");
-        else asm volatile("bar.arrive 5, 256;" ::: "memory");
+        };
+        // Priority tiles: block column kb + 1 below its diagonal block (warps 1..ntile-1)
+        // and the diagonal block kb + 2 (warp 7, never needed for the column: ntile <= 7).
+        const int ntile = rem >> 3, c2 = c1 + 8, nt2 = ntile - 1;
+        if (warp < ntile) tile(c1 + (warp << 3), c1);
+        if (warp == kWarps - 1) tile(c2, c2);
+        asm volatile("bar.arrive %0, 256;" ::"r"(4 + par) : "memory");
+        LAP1(4);
+        // The rest of A(c2.., c2..) on 8 x 8 tiles of the lower triangle (slot 0 is the
+        // diagonal block done above).
+        for (int slot = kWarps - warp; slot < nt2 * (nt2 + 1) / 2; slot += kWarps - 1)
+          tile(c2 + (kTriRow[slot] << 3), c2 + (kTriCol[slot] << 3));
+        LAP1(22);
       }
       idle(kb, nb_live);
+      LAP1(16);
     }
   }
   __syncthreads();
   TICK(11);
 
   // X = L^-1 in `scratch`.
-  // Level 0: the 8 x 8 diagonal blocks, one warp per block, in registers.
-  for (int kb = warp; kb < nb; kb += kWarps) {
-    double L[36], d[8], X[36];
+  // Level 0: the 8 x 8 diagonal blocks.  Lane 8 q + j of a warp computes column j of the
+  // inverse of the warp's q-th block by forward substitution on e_j (the entries above
+  // the diagonal come out as exact zeros), four blocks per warp.
+  for (int kb = warp * 4 + (lane >> 3); kb < nb && warp * 4 < nb; kb += kWarps * 4) {
+    const int j = lane & 7;
+    const double *blk = A + (kb * 8) * ld + kb * 8;
+    double xc[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      d[j] = ddiag[kb * 8 + j];
+    for (int i = 0; i < 8; ++i) {
+      double sacc = (i == j) ? 1.0 : 0.0;
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (i >= j) L[pk(i, j, 8)] = A[(kb * 8 + j) * ld + kb * 8 + i];
+      for (int p = 0; p < 8; ++p)
+        if (p < i) sacc -= blk[p * ld + i] * xc[p];
+      xc[i] = sacc * ddiag[kb * 8 + i];
     }
-    inv8(L, d, X);
-    if (lane == 0) {
-      double *dst = scratch + (kb * 8) * ld + kb * 8;
+    double *dst = scratch + (kb * 8 + j) * ld + kb * 8;
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) dst[j * ld + i] = (i >= j) ? X[(i >= j) ? pk(i, j, 8) : 0] : 0.0;
-    }
+    for (int i = 0; i < 8; ++i) dst[i] = xc[i];
   }
   __syncthreads();
   TICK(13);
@@ -663,9 +649,19 @@ riccati_backward_cta(LqrIn pm, int *status_out, double *store, double *scratch, 
     }
     const bool any_bad = __syncthreads_or(!d_ok);
     if (any_bad && status == SIPOC_FACTOR_SUCCESS) status = SIPOC_FACTOR_INVALID_DELTA;
-    for (int e = tid; e < N * N; e += kThreads) {
-      const int i = e % N, j = e / N;
-      if (i >= j) Wp[j * LDN + i] = sd_s[i] * Wp[j * LDN + i] * sd_s[j] + (i == j ? 1.0 : 0.0);
+    // F = I + D^1/2 V D^1/2 on the lower triangle, four entries per thread in flight.
+    for (int e0 = tid; e0 < N * N; e0 += 4 * kThreads) {
+      double val[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * kThreads, i = e % N, j = e / N;
+        if (e < N * N && i >= j) val[u] = Wp[j * LDN + i];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * kThreads, i = e % N, j = e / N;
+        if (e < N * N && i >= j) Wp[j * LDN + i] = sd_s[i] * val[u] * sd_s[j] + (i == j ? 1.0 : 0.0);
+      }
     }
     __syncthreads();
     TICK(8);
@@ -673,20 +669,30 @@ riccati_backward_cta(LqrIn pm, int *status_out, double *store, double *scratch, 
     // are issued by the idle warps of the F factorization's block steps.
     const bool f_ok = cta_spd_inverse(Wp, LDN, N, Sb, Sb + N * LDN, Dd, [&](int kb, int nb) {
       if (k == 0) return;
-      if (kb == 0) stage_edge_rest(k - 1, 64, kThreads - 64);
-      if (kb == 1) stage_q_packed(k - 1, 64, kThreads - 64);
-      if (k == T && kb >= 1 && kb < nb) stage_edge_z(k - 1, 64, kThreads - 64, kb - 1, nb - 1);
+      if (kb == 0) stage_edge_rest(k - 1, kPanelThreads, kThreads - kPanelThreads);
+      if (kb == 1) stage_q_packed(k - 1, kPanelThreads, kThreads - kPanelThreads);
+      if (k == T && kb >= 1 && kb < nb) stage_edge_z(k - 1, kPanelThreads, kThreads - kPanelThreads, kb - 1, nb - 1);
       cp_async_commit();
     }, -1, false);  // the W pass below reads the lower triangle only
     if (!__syncthreads_and(f_ok) && status == SIPOC_FACTOR_SUCCESS)
       status = SIPOC_FACTOR_F_FACTORIZATION_FAILURE;
-    for (int e = tid; e < N * N; e += kThreads) {
-      const int i = e % N, j = e / N;
-      if (i >= j) {
-        const double w = sdi_s[i] * ((i == j ? 1.0 : 0.0) - Wp[j * LDN + i]) * sdi_s[j];
-        Wp[j * LDN + i] = w;
-        Wp[i * LDN + j] = w;
-        __stcs(Wst + (static_cast<size_t>(k) * tri(N) + pk(i, j, N)) * L_, w);
+    // W = D^-1/2 (I - F^-1) D^-1/2: both triangles in shared memory, packed lower to the store.
+    for (int e0 = tid; e0 < N * N; e0 += 4 * kThreads) {
+      double val[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * kThreads, i = e % N, j = e / N;
+        if (e < N * N && i >= j) val[u] = Wp[j * LDN + i];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * kThreads, i = e % N, j = e / N;
+        if (e < N * N && i >= j) {
+          const double w = sdi_s[i] * ((i == j ? 1.0 : 0.0) - val[u]) * sdi_s[j];
+          Wp[j * LDN + i] = w;
+          Wp[i * LDN + j] = w;
+          __stcs(Wst + (static_cast<size_t>(k) * tri(N) + pk(i, j, N)) * L_, w);
+        }
       }
     }
     __syncthreads();
@@ -706,7 +712,7 @@ riccati_backward_cta(LqrIn pm, int *status_out, double *store, double *scratch, 
 #ifdef SIPOC_CTA_TIMING
   if (tid == 0 && b == 0) {
     for (int i = 0; i < 23; ++i) g_tick[i] = 0;
-    g_tick[23] = clock64();
+    tick_last__ = clock64();
   }
 #endif
   __syncthreads();
@@ -744,9 +750,18 @@ riccati_backward_cta(LqrIn pm, int *status_out, double *store, double *scratch, 
     __syncthreads();
     TICK(3);
     // Psi_xx base: Q_k lower (prefetched, packed, in the K buffer) into the now free W' buffer.
-    for (int e = tid; e < N * N; e += kThreads) {
-      const int i = e % N, j = e / N;
-      if (i >= j) Wp[j * LDN + i] = Kb[pk(i, j, N)];
+    for (int e0 = tid; e0 < N * N; e0 += 4 * kThreads) {
+      double val[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * kThreads, i = e % N, j = e / N;
+        if (e < N * N && i >= j) val[u] = Kb[pk(i, j, N)];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * kThreads, i = e % N, j = e / N;
+        if (e < N * N && i >= j) Wp[j * LDN + i] = val[u];
+      }
     }
     __syncthreads();
     // Psi_ux += B' S_x,  Psi_uu += B' S_u (rows = u, K = N),  Psi_xx += A' S_x (lower
@@ -765,7 +780,7 @@ riccati_backward_cta(LqrIn pm, int *status_out, double *store, double *scratch, 
     // warps of the G factorization's block steps and fly during the rest of this stage.
     const bool g_ok = cta_spd_inverse(Puu, LDM, MP, Gs, Sb, Dd, [&](int kb, int nb) {
       if (k == 0) return;
-      stage_edge_z(k - 1, 64, kThreads - 64, kb, nb);
+      stage_edge_z(k - 1, kPanelThreads, kThreads - kPanelThreads, kb, nb);
       cp_async_commit();
     }, M);
     if (!__syncthreads_and(g_ok) && status == SIPOC_FACTOR_SUCCESS)
@@ -794,11 +809,12 @@ riccati_backward_cta(LqrIn pm, int *status_out, double *store, double *scratch, 
 #ifdef SIPOC_CTA_TIMING
   __syncthreads();
   if (tid == 0 && b == 0) {
+    __threadfence();
     // 0 loop top, 1 staging wait, 2 affine, 3 S, 4 u-block, 5 Psi_xx, 6 G inverse (10..16 inside
     // both inverses), 7 K / V / stores, 8 F build, 9 W finish; inside the inverses: 10 entry,
     // 11 diagonal block + panel, 12 trailing update, 13 block inverses, 14 L^-1, 15 L^-T L^-1,
     // 16 mirror.
-    for (int i = 0; i < 23; ++i) printf("tick %2d  %10lld cycles / stage\n", i, g_tick[i] / T);
+    for (int i = 0; i < 23; ++i) printf("tick %2d  %10llu cycles / stage\n", i, *(volatile unsigned long long *)&g_tick[i] / T);
   }
 #endif
   if (status_out != nullptr && tid == 0) status_out[b] = status;
