@@ -227,17 +227,20 @@ bool use_fast(const sipoc_engine *e, const LqrIn &in) {
 
 int64_t lqr_in_size(const HostStructure &h, int i);
 
-// Plans whose backward kernel runs one problem per CTA read the inputs from
-// problem-major copies [problem][flat]; this transposes the arrays the call touches
-// (nine coalesced passes, a few percent of the factorization they feed).
-sipoc_error refresh_problem_major(sipoc_engine *e, const LqrIn &in, bool vectors, LqrIn *pm,
+// Plans whose kernels run one problem per CTA read the inputs from problem-major copies
+// [problem][flat]; this transposes the arrays the call touches (coalesced passes, a few
+// percent of the work they feed).  `mask` bit i selects array i of
+// {Q, M, R, q, r, A, B, c, delta}.
+constexpr unsigned kPmMatrices = 0b101100111;  // Q M R A B delta
+constexpr unsigned kPmAll = 0b111111111;
+constexpr unsigned kPmSolve = 0b111111000;     // q r A B c delta
+sipoc_error refresh_problem_major(sipoc_engine *e, const LqrIn &in, unsigned mask, LqrIn *pm,
                                   cudaStream_t s) {
   *pm = LqrIn{};
   if (e->fast == nullptr || !e->fast->problem_major_inputs) return SIPOC_OK;
   const double *src[9] = {in.Q, in.M, in.R, in.q, in.r, in.A, in.B, in.c, in.delta};
-  const bool is_vector[9] = {false, false, false, true, true, false, false, true, false};
   for (int i = 0; i < 9; ++i) {
-    if (is_vector[i] && !vectors) continue;
+    if ((mask >> i & 1u) == 0) continue;
     const int64_t size = lqr_in_size(e->hs, i);
     if (e->pm_in[i] == nullptr) {
       sipoc_error rc = dev_alloc(e, reinterpret_cast<void **>(&e->pm_in[i]),
@@ -261,7 +264,7 @@ sipoc_error lqr_factor_core(sipoc_engine *e, const LqrIn &in, int *status,
   if (use_fast(e, in)) {
     if ((rc = ensure_fast_store(e)) != SIPOC_OK) return rc;
     LqrIn pm;
-    if ((rc = refresh_problem_major(e, in, false, &pm, s)) != SIPOC_OK) return rc;
+    if ((rc = refresh_problem_major(e, in, kPmMatrices, &pm, s)) != SIPOC_OK) return rc;
     FastArgs a{in, pm, LqrOut{}, status, e->fast_store, nullptr, e->batch, e->ld, e->hs.E,
                &e->prof};
     e->launches += e->fast->factor(a, s);
@@ -288,7 +291,9 @@ sipoc_error lqr_solve_core(sipoc_engine *e, const LqrIn &in, const LqrOut &out,
                 "solve against a fast-path factorization needs 16-byte aligned arrays");
   if (e->factored == sipoc_engine::Factored::FAST) {
     if ((rc = ensure_fast_scratch(e)) != SIPOC_OK) return rc;
-    FastArgs a{in, LqrIn{}, out, nullptr, e->fast_store, e->fast_scratch, e->batch, e->ld,
+    LqrIn pm;
+    if ((rc = refresh_problem_major(e, in, kPmSolve, &pm, s)) != SIPOC_OK) return rc;
+    FastArgs a{in, pm, out, nullptr, e->fast_store, e->fast_scratch, e->batch, e->ld,
                e->hs.E, &e->prof};
     e->launches += e->fast->solve(a, s);
   } else {
@@ -308,7 +313,7 @@ sipoc_error lqr_factor_solve_core(sipoc_engine *e, const LqrIn &in, const LqrOut
     if ((rc = ensure_fast_store(e)) != SIPOC_OK) return rc;
     if ((rc = ensure_fast_scratch(e)) != SIPOC_OK) return rc;
     LqrIn pm;
-    if ((rc = refresh_problem_major(e, in, true, &pm, s)) != SIPOC_OK) return rc;
+    if ((rc = refresh_problem_major(e, in, kPmAll, &pm, s)) != SIPOC_OK) return rc;
     FastArgs a{in, pm, out, status, e->fast_store, e->fast_scratch, e->batch, e->ld, e->hs.E,
                &e->prof};
     e->launches += e->fast->factor_solve(a, s);

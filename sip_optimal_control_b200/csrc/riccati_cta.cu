@@ -543,7 +543,6 @@ riccati_backward_cta(LqrIn pm, int *status_out, double *store, double *scratch, 
   extern __shared__ __align__(16) double sm[];
   const int tid = threadIdx.x;
   const int64_t b = blockIdx.x;
-  const size_t L_ = static_cast<size_t>(ld);
   double *Wp = sm + S::oW, *Zb = sm + S::oZ, *Sb = sm + S::oS, *Pux = sm + S::oPux,
          *Puu = sm + S::oPuu, *Kb = sm + S::oK, *Gs = sm + S::oGs,
          *Dd = sm + S::oDd;
@@ -551,11 +550,13 @@ riccati_backward_cta(LqrIn pm, int *status_out, double *store, double *scratch, 
          *v_s = sm + S::vv, *dl_s = sm + S::vdl, *sd_s = sm + S::vsd, *sdi_s = sm + S::vsdi,
          *f_s = sm + S::vf, *g_s = sm + S::vg, *hw_s = sm + S::vhw, *kk_s = sm + S::vkk;
 
-  double *Wst = store + Zs::oW(T) * ld + b;
-  double *Kst = store + Zs::oK(T) * ld + b;
-  double *Gst = store + Zs::oG(T) * ld + b;
-  double *vst = SOLVE ? scratch + Zs::ov(T) * ld + b : nullptr;
-  double *kst = SOLVE ? scratch + Zs::ok(T) * ld + b : nullptr;
+  // The store (W, K, G^-1) and the spill (v, k) are private to this file's kernels and
+  // problem-major like the inputs: every store below is a contiguous run.
+  double *Wst = store + static_cast<size_t>(b) * Zs::store(T) + Zs::oW(T);
+  double *Kst = store + static_cast<size_t>(b) * Zs::store(T) + Zs::oK(T);
+  double *Gst = store + static_cast<size_t>(b) * Zs::store(T) + Zs::oG(T);
+  double *vst = SOLVE ? scratch + static_cast<size_t>(b) * Zs::scratch(T) + Zs::ov(T) : nullptr;
+  double *kst = SOLVE ? scratch + static_cast<size_t>(b) * Zs::scratch(T) + Zs::ok(T) : nullptr;
 
   // Inputs come from the problem-major copies [problem][flat]: this CTA's problem is a
   // contiguous run per array, so a warp's 32 eight-byte copies cover 8 whole sectors
@@ -644,7 +645,7 @@ riccati_backward_cta(LqrIn pm, int *status_out, double *store, double *scratch, 
       if (SOLVE) {
         const double v = hw_s[i];
         v_s[i] = v;
-        __stcs(vst + (static_cast<size_t>(k) * N + i) * L_, v);
+        vst[static_cast<size_t>(k) * N + i] = v;
       }
     }
     const bool any_bad = __syncthreads_or(!d_ok);
@@ -691,7 +692,7 @@ riccati_backward_cta(LqrIn pm, int *status_out, double *store, double *scratch, 
           const double w = sdi_s[i] * ((i == j ? 1.0 : 0.0) - val[u]) * sdi_s[j];
           Wp[j * LDN + i] = w;
           Wp[i * LDN + j] = w;
-          __stcs(Wst + (static_cast<size_t>(k) * tri(N) + pk(i, j, N)) * L_, w);
+          Wst[static_cast<size_t>(k) * tri(N) + pk(i, j, N)] = w;
         }
       }
     }
@@ -795,13 +796,13 @@ riccati_backward_cta(LqrIn pm, int *status_out, double *store, double *scratch, 
     if (SOLVE) cta_matvec<true>(hw_s, hw_s, Pux, LDM, kk_s, N, MP, 1.0);
     // stores of the edge: K (M x N), G^-1 (packed lower), k
     for (int e = tid; e < N * M; e += kThreads)
-      __stcs(Kst + (static_cast<size_t>(k) * N * M + e) * L_, Kb[(e / M) * LDM + e % M]);
+      Kst[static_cast<size_t>(k) * N * M + e] = Kb[(e / M) * LDM + e % M];
     for (int e = tid; e < M * M; e += kThreads) {
       const int i = e % M, j = e / M;
       if (i >= j)
-        __stcs(Gst + (static_cast<size_t>(k) * tri(M) + pk(i, j, M)) * L_, Puu[j * LDM + i]);
+        Gst[static_cast<size_t>(k) * tri(M) + pk(i, j, M)] = Puu[j * LDM + i];
     }
-    if (SOLVE && tid < M) __stcs(kst + (static_cast<size_t>(k) * M + tid) * L_, kk_s[tid]);
+    if (SOLVE && tid < M) kst[static_cast<size_t>(k) * M + tid] = kk_s[tid];
     __syncthreads();
     TICK(7);
     process_node(k);
@@ -820,38 +821,43 @@ riccati_backward_cta(LqrIn pm, int *status_out, double *store, double *scratch, 
   if (status_out != nullptr && tid == 0) status_out[b] = status;
 }
 
-// Backward affine sweep against a kept factorization, one CTA per problem.
+// Backward affine sweep against a kept factorization, one CTA per problem; inputs from
+// the problem-major copies, W / K / G^-1 from the problem-major store.
 template <int N, int M>
 __global__ void __launch_bounds__(kThreads)
-affine_backward_cta(LqrIn in, const double *store, double *scratch, int64_t batch, int64_t ld,
+affine_backward_cta(LqrIn pm, const double *store, double *scratch, int64_t batch, int64_t ld,
                     int T) {
   using Zs = CtaSizes<N, M>;
   __shared__ double v[N], f[N], g[N], h[M], kk[M];
   const int tid = threadIdx.x;
-  const int64_t b = blockIdx.x;
-  const size_t L_ = static_cast<size_t>(ld);
-#define G(ptr, e) __ldcs((ptr) + static_cast<size_t>(e) * L_ + b)
-  const double *Wst = store + Zs::oW(T) * ld;
-  const double *Kst = store + Zs::oK(T) * ld;
-  const double *Gst = store + Zs::oG(T) * ld;
-  double *vst = scratch + Zs::ov(T) * ld + b;
-  double *kst = scratch + Zs::ok(T) * ld + b;
+  const size_t b = blockIdx.x;
+  const double *Wst = store + b * Zs::store(T) + Zs::oW(T);
+  const double *Kst = store + b * Zs::store(T) + Zs::oK(T);
+  const double *Gst = store + b * Zs::store(T) + Zs::oG(T);
+  double *vst = scratch + b * Zs::scratch(T) + Zs::ov(T);
+  double *kst = scratch + b * Zs::scratch(T) + Zs::ok(T);
+  const double *gq = pm.q + b * (static_cast<size_t>(T + 1) * N);
+  const double *gc = pm.c + b * (static_cast<size_t>(T + 1) * N);
+  const double *gd = pm.delta + b * (static_cast<size_t>(T + 1) * N);
+  const double *gr = pm.r + b * (static_cast<size_t>(T) * M);
+  const double *gA = pm.A + b * (static_cast<size_t>(T) * N * N);
+  const double *gB = pm.B + b * (static_cast<size_t>(T) * N * M);
   for (int i = tid; i < N; i += kThreads) {
-    v[i] = G(in.q, T * N + i);
-    __stcs(vst + static_cast<size_t>(T * N + i) * L_, v[i]);
+    v[i] = gq[T * N + i];
+    vst[T * N + i] = v[i];
   }
   __syncthreads();
   const int row = tid >> 2, part = tid & 3;  // 4 threads per output row (N <= 64)
   for (int k = T - 1; k >= 0; --k) {
     for (int i = tid; i < N; i += kThreads)
-      f[i] = G(in.delta, (k + 1) * N + i) * v[i] - G(in.c, (k + 1) * N + i);
+      f[i] = gd[(k + 1) * N + i] * v[i] - gc[(k + 1) * N + i];
     __syncthreads();
     {  // g = v - W' f
       double acc = 0.0;
       if (row < N)
         for (int j = part; j < N; j += 4) {
           const int i = row;
-          acc += G(Wst, (k + 1) * tri(N) + (i >= j ? pk(i, j, N) : pk(j, i, N))) * f[j];
+          acc += __ldg(Wst + (k + 1) * tri(N) + (i >= j ? pk(i, j, N) : pk(j, i, N))) * f[j];
         }
       acc += __shfl_xor_sync(0xffffffffu, acc, 1);
       acc += __shfl_xor_sync(0xffffffffu, acc, 2);
@@ -861,10 +867,10 @@ affine_backward_cta(LqrIn in, const double *store, double *scratch, int64_t batc
     {  // h = r + B' g
       double acc = 0.0;
       if (row < M)
-        for (int p = part; p < N; p += 4) acc += G(in.B, (k * M + row) * N + p) * g[p];
+        for (int p = part; p < N; p += 4) acc += __ldg(gB + (k * M + row) * N + p) * g[p];
       acc += __shfl_xor_sync(0xffffffffu, acc, 1);
       acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-      if (row < M && part == 0) h[row] = G(in.r, k * M + row) + acc;
+      if (row < M && part == 0) h[row] = gr[k * M + row] + acc;
     }
     __syncthreads();
     {  // k = -G^-1 h
@@ -872,120 +878,231 @@ affine_backward_cta(LqrIn in, const double *store, double *scratch, int64_t batc
       if (row < M)
         for (int j = part; j < M; j += 4) {
           const int i = row;
-          acc += G(Gst, k * tri(M) + (i >= j ? pk(i, j, M) : pk(j, i, M))) * h[j];
+          acc += __ldg(Gst + k * tri(M) + (i >= j ? pk(i, j, M) : pk(j, i, M))) * h[j];
         }
       acc += __shfl_xor_sync(0xffffffffu, acc, 1);
       acc += __shfl_xor_sync(0xffffffffu, acc, 2);
       if (row < M && part == 0) {
         kk[row] = -acc;
-        __stcs(kst + static_cast<size_t>(k * M + row) * L_, -acc);
+        kst[k * M + row] = -acc;
       }
     }
     __syncthreads();
     {  // v = q + A' g + K' h
       double acc = 0.0;
       if (row < N) {
-        for (int p = part; p < N; p += 4) acc += G(in.A, (k * N + row) * N + p) * g[p];
-        for (int a = part; a < M; a += 4) acc += G(Kst, (k * N + row) * M + a) * h[a];
+        for (int p = part; p < N; p += 4) acc += __ldg(gA + (k * N + row) * N + p) * g[p];
+        for (int a = part; a < M; a += 4) acc += __ldg(Kst + (k * N + row) * M + a) * h[a];
       }
       acc += __shfl_xor_sync(0xffffffffu, acc, 1);
       acc += __shfl_xor_sync(0xffffffffu, acc, 2);
       __syncthreads();
       if (row < N && part == 0) {
-        v[row] = G(in.q, k * N + row) + acc;
-        __stcs(vst + static_cast<size_t>(k * N + row) * L_, v[row]);
+        v[row] = gq[k * N + row] + acc;
+        vst[k * N + row] = v[row];
       }
     }
     __syncthreads();
   }
-#undef G
 }
 
-// Root solve + forward rollout + costates (lqr.cpp:798-870).  FOUR problems per CTA,
-// one thread per (problem, row): the four problems are consecutive in the batch, so
-// every 32-byte sector a warp touches is fully used (4 doubles = 4 problems) and a
-// warp load covers 8 rows x 4 problems = 8 whole sectors.
+// ---- mbarrier + bulk async copy (TMA, 1-D) --------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) {
+  return static_cast<unsigned>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  unsigned done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (done == 0);
+}
+// bytes: a multiple of 16; both addresses 16-byte aligned.
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes,
+                                         unsigned long long *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::
+          "r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// Per-stage operand block of the rollout in shared memory (doubles).
+template <int N, int M>
+struct RolloutStage {
+  static constexpr int oW = 0;                 // W_{k+1}, packed lower
+  static constexpr int oK = oW + tri(N);       // K_k   (M x N)
+  static constexpr int oA = oK + N * M;        // A_k   (N x N)
+  static constexpr int oB = oA + N * N;        // B_k   (N x M)
+  static constexpr int ov = oB + N * M;        // v_{k+1}
+  static constexpr int od = ov + N;            // delta_{k+1}
+  static constexpr int oc = od + N;            // c_{k+1}
+  static constexpr int ok = oc + N;            // k_k
+  static constexpr int kDoubles = ok + round16(M);
+  static_assert(tri(N) % 2 == 0 && (N * M) % 2 == 0 && N % 2 == 0 && M % 2 == 0,
+                "every block is a whole number of 16-byte units");
+};
+
+// Root solve + forward rollout + costates (lqr.cpp:798-870), one CTA per problem.  The
+// rollout is a chain of small matrix-vector products whose operands are used once: it
+// runs at the speed its operands arrive.  Everything a stage needs is contiguous in the
+// problem-major store / spill / input copies, so one thread fetches a stage with eight
+// bulk async copies (TMA) into one of two shared-memory blocks and an mbarrier reports
+// their arrival; the fetch of stage k + 1 flies while stage k is computed.
 template <int N, int M>
 __global__ void __launch_bounds__(kThreads)
-rollout_forward_cta(LqrIn in, LqrOut out, const double *store, const double *scratch,
+rollout_forward_cta(LqrIn pm, LqrOut out, const double *store, const double *scratch,
                     int64_t batch, int64_t ld, int T) {
-  static_assert(N * 4 <= kThreads && M <= N, "one thread per (problem, row)");
+  static_assert(kThreads % N == 0 && M <= N && M <= 32, "kThreads / N threads per row");
   using Zs = CtaSizes<N, M>;
-  __shared__ double x[N * 4], u[M * 4], f[N * 4];
+  using St = RolloutStage<N, M>;
+  extern __shared__ __align__(16) double sm[];
+  __shared__ __align__(8) unsigned long long bar[2];
+  __shared__ double x[N], u[round16(M)], f[N], ax[N], red[kThreads], red2[kThreads];
   const int tid = threadIdx.x;
-  const int p = tid & 3, row = tid >> 2;
-  const int64_t b_raw = static_cast<int64_t>(blockIdx.x) * 4 + p;
-  const bool valid = b_raw < batch;
-  const int64_t b = valid ? b_raw : batch - 1;
+  const size_t b = blockIdx.x;
   const size_t L_ = static_cast<size_t>(ld);
-#define G(ptr, e) __ldg((ptr) + static_cast<size_t>(e) * L_ + b)
-  const double *Wst = store + Zs::oW(T) * ld;
-  const double *Kst = store + Zs::oK(T) * ld;
-  const double *vst = scratch + Zs::ov(T) * ld;
-  const double *kst = scratch + Zs::ok(T) * ld;
+  const double *Wst = store + b * Zs::store(T) + Zs::oW(T);
+  const double *Kst = store + b * Zs::store(T) + Zs::oK(T);
+  const double *vst = scratch + b * Zs::scratch(T) + Zs::ov(T);
+  const double *kst = scratch + b * Zs::scratch(T) + Zs::ok(T);
+  const double *gA = pm.A + b * (static_cast<size_t>(T) * N * N);
+  const double *gB = pm.B + b * (static_cast<size_t>(T) * N * M);
+  const double *gc = pm.c + b * (static_cast<size_t>(T + 1) * N);
+  const double *gd = pm.delta + b * (static_cast<size_t>(T + 1) * N);
   double *xo = out.x + b, *uo = out.u + b, *yo = out.y + b;
-  const bool xrow = row < N, urow = row < M;
 
-  auto w_row_times_f = [&](int node) {  // (W_node f)(row), W packed symmetric
+  // fetch(k, slot): operands of edge k (node k + 1); k = -1 fetches the root node only.
+  auto fetch = [&](int k, int slot) {
+    double *dst = sm + slot * St::kDoubles;
+    const unsigned vec = N * sizeof(double);
+    unsigned bytes = tri(N) * sizeof(double) + 3 * vec;
+    if (k >= 0) bytes += (2 * N * M + N * N + M) * sizeof(double);
+    mbar_expect_tx(&bar[slot], bytes);
+    bulk_g2s(dst + St::oW, Wst + static_cast<size_t>(k + 1) * tri(N), tri(N) * sizeof(double),
+             &bar[slot]);
+    bulk_g2s(dst + St::ov, vst + static_cast<size_t>(k + 1) * N, vec, &bar[slot]);
+    bulk_g2s(dst + St::od, gd + static_cast<size_t>(k + 1) * N, vec, &bar[slot]);
+    bulk_g2s(dst + St::oc, gc + static_cast<size_t>(k + 1) * N, vec, &bar[slot]);
+    if (k >= 0) {
+      bulk_g2s(dst + St::oK, Kst + static_cast<size_t>(k) * N * M, N * M * sizeof(double),
+               &bar[slot]);
+      bulk_g2s(dst + St::oA, gA + static_cast<size_t>(k) * N * N, N * N * sizeof(double),
+               &bar[slot]);
+      bulk_g2s(dst + St::oB, gB + static_cast<size_t>(k) * N * M, N * M * sizeof(double),
+               &bar[slot]);
+      bulk_g2s(dst + St::ok, kst + static_cast<size_t>(k) * M, M * sizeof(double), &bar[slot]);
+    }
+  };
+
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    fetch(-1, 0);
+    if (T > 0) fetch(0, 1);
+  }
+  // Thread (part, row): row = tid % N, part = tid / N.  A warp reads one column of an
+  // operand at consecutive rows (conflict-free); the P partial sums of a row meet in `red`.
+  constexpr int P = kThreads / N;
+  const int row = tid % N, part = tid / N;
+  // (W f)(row), this part's columns, from the packed lower triangle
+  auto w_times_f = [&](const double *Wk) {
     double acc = 0.0;
-#pragma unroll 8
-    for (int j = 0; j < N; ++j)
-      acc += G(Wst, node * tri(N) + (row >= j ? pk(row, j, N) : pk(j, row, N))) * f[j * 4 + p];
+#pragma unroll 4
+    for (int j = part; j < N; j += P) acc += Wk[row >= j ? pk(row, j, N) : pk(j, row, N)] * f[j];
+    return acc;
+  };
+  auto total = [&](const double *r, int i) {
+    double acc = 0.0;
+#pragma unroll
+    for (int q = 0; q < P; ++q) acc += r[q * N + i];
     return acc;
   };
 
-  double vv = 0.0, dd = 0.0, fi = 0.0;
-  if (xrow) {
-    vv = G(vst, row);
-    dd = G(in.delta, row);
-    fi = dd * vv - G(in.c, row);
-    f[row * 4 + p] = fi;
-  }
-  __syncthreads();
-  if (xrow) {
-    const double wf = w_row_times_f(0);
-    const double xi = dd * wf - fi;
-    x[row * 4 + p] = xi;
-    if (valid) {
-      __stcs(xo + static_cast<size_t>(row) * L_, xi);
-      __stcs(yo + static_cast<size_t>(row) * L_, vv - wf);
+  // ---- root: f = delta v - c,  x = delta (W f) - f,  y = v - W f
+  mbar_wait(&bar[0], 0);
+  {
+    const double *blk = sm;
+    if (tid < N) f[tid] = blk[St::od + tid] * blk[St::ov + tid] - blk[St::oc + tid];
+    __syncthreads();
+    red[part * N + row] = w_times_f(blk + St::oW);
+    __syncthreads();
+    if (tid < N) {
+      const double wf = total(red, tid);
+      const double xi = blk[St::od + tid] * wf - f[tid];
+      x[tid] = xi;
+      __stcs(xo + static_cast<size_t>(tid) * L_, xi);
+      __stcs(yo + static_cast<size_t>(tid) * L_, blk[St::ov + tid] - wf);
     }
+    __syncthreads();  // slot 0 is free, x is visible
   }
-  __syncthreads();
   for (int k = 0; k < T; ++k) {
-    if (urow) {  // u = k + K x
-      double acc = G(kst, k * M + row);
-#pragma unroll 8
-      for (int j = 0; j < N; ++j) acc += G(Kst, (k * N + j) * M + row) * x[j * 4 + p];
-      u[row * 4 + p] = acc;
-      if (valid) __stcs(uo + static_cast<size_t>(k * M + row) * L_, acc);
-    }
-    if (xrow) {
-      vv = G(vst, (k + 1) * N + row);
-      dd = G(in.delta, (k + 1) * N + row);
-      fi = G(in.c, (k + 1) * N + row) - dd * vv;
-#pragma unroll 8
-      for (int j = 0; j < N; ++j) fi += G(in.A, (k * N + j) * N + row) * x[j * 4 + p];
-    }
-    __syncthreads();
-    if (xrow) {  // f = c' - delta' o v' + A x + B u
-#pragma unroll 8
-      for (int a = 0; a < M; ++a) fi += G(in.B, (k * M + a) * N + row) * u[a * 4 + p];
-      f[row * 4 + p] = fi;
-    }
-    __syncthreads();
-    if (xrow) {
-      const double wf = w_row_times_f(k + 1);
-      const double xi = fi - dd * wf;
-      x[row * 4 + p] = xi;  // every thread finished reading x before the previous barrier
-      if (valid) {
-        __stcs(xo + static_cast<size_t>((k + 1) * N + row) * L_, xi);
-        __stcs(yo + static_cast<size_t>((k + 1) * N + row) * L_, vv + wf);
+    const int slot = (k + 1) & 1;  // stage k sits in slot (k + 1) % 2; the root used slot 0
+    if (tid == 0 && k + 1 < T) fetch(k + 1, slot ^ 1);
+    mbar_wait(&bar[slot], ((k + 1) >> 1) & 1);
+    const double *blk = sm + slot * St::kDoubles;
+    // A x (all rows) and K x (rows < M): both need x only.
+    {
+      double acc = 0.0, acu = 0.0;
+#pragma unroll 4
+      for (int j = part; j < N; j += P) {
+        const double xj = x[j];
+        acc += blk[St::oA + j * N + row] * xj;
+        if (row < M) acu += blk[St::oK + j * M + row] * xj;
       }
+      red[part * N + row] = acc;
+      if (row < M) red2[part * N + row] = acu;
     }
     __syncthreads();
+    if (tid < N) ax[tid] = total(red, tid);
+    if (tid >= kThreads - M) {  // u = k + K x, on threads of the last warp
+      const int a = tid - (kThreads - M);
+      const double ui = blk[St::ok + a] + total(red2, a);
+      u[a] = ui;
+      __stcs(uo + (static_cast<size_t>(k) * M + a) * L_, ui);
+    }
+    __syncthreads();
+    // f = c' - delta' o v' + A x + B u
+    {
+      double acc = 0.0;
+      for (int a = part; a < M; a += P) acc += blk[St::oB + a * N + row] * u[a];
+      red[part * N + row] = acc;
+    }
+    __syncthreads();
+    if (tid < N)
+      f[tid] = blk[St::oc + tid] - blk[St::od + tid] * blk[St::ov + tid] + ax[tid] + total(red, tid);
+    __syncthreads();
+    // x' = f - delta' o (W' f),  y' = v' + W' f
+    red2[part * N + row] = w_times_f(blk + St::oW);
+    __syncthreads();
+    if (tid < N) {
+      const double wf = total(red2, tid);
+      const double xi = f[tid] - blk[St::od + tid] * wf;
+      x[tid] = xi;
+      __stcs(xo + (static_cast<size_t>(k + 1) * N + tid) * L_, xi);
+      __stcs(yo + (static_cast<size_t>(k + 1) * N + tid) * L_, blk[St::ov + tid] + wf);
+    }
+    __syncthreads();  // this slot is free for the fetch of stage k + 2, x' is visible
   }
-#undef G
 }
 
 template <int N, int M>
@@ -1005,9 +1122,13 @@ struct CtaPlan {
                                                                  a.num_edges);
   }
   static void forward(const FastArgs &a, cudaStream_t s) {
+    auto kern = rollout_forward_cta<N, M>;
+    constexpr int bytes = 2 * RolloutStage<N, M>::kDoubles * int(sizeof(double));
+    if (bytes > 48 * 1024)
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     ProfScope ps(a.prof, "rollout_forward_cta", s);
-    rollout_forward_cta<N, M><<<static_cast<unsigned>((a.batch + 3) / 4), kThreads, 0, s>>>(
-        a.in, a.out, a.store, a.scratch, a.batch, a.ld, a.num_edges);
+    kern<<<static_cast<unsigned>(a.batch), kThreads, bytes, s>>>(a.pm, a.out, a.store, a.scratch,
+                                                                 a.batch, a.ld, a.num_edges);
   }
   static int factor(const FastArgs &a, cudaStream_t s) {
     backward<false>(a, s);
@@ -1017,7 +1138,7 @@ struct CtaPlan {
     {
       ProfScope ps(a.prof, "affine_backward_cta", s);
       affine_backward_cta<N, M><<<static_cast<unsigned>(a.batch), kThreads, 0, s>>>(
-          a.in, a.store, a.scratch, a.batch, a.ld, a.num_edges);
+          a.pm, a.store, a.scratch, a.batch, a.ld, a.num_edges);
     }
     forward(a, s);
     return 2;
