@@ -28,6 +28,7 @@
 // sector inefficiency costs L2 bandwidth only.
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 
 #include "riccati_fast.cuh"
 
@@ -98,8 +99,9 @@ __constant__ unsigned char kTriCol[36] = {0, 0, 1, 0, 1, 2, 0, 1, 2, 3, 0, 1, 2,
 
 // One 16 x 16 block (2 x 2 MMA tiles) at (i0, j0) of
 //   C (Mo x No) = (ACC ? C : 0) + sign * op(A) (Mo x K) * op(B) (K x No),
-// all in shared memory, column-major; executed by one warp.  Mo, No multiples of 8, K a
-// multiple of 4.  KTRI starts the k range at i0 (op(A) upper triangular, i.e. A' of a
+// all in shared memory, column-major; executed by one warp.  K a multiple of 4.  Mo and
+// No are rounded up to whole 8 x 8 MMA tiles (callers keep that padding zero); tiles
+// entirely beyond them are not issued.  KTRI starts the k range at i0 (op(A) upper triangular, i.e. A' of a
 // lower-triangular X).
 template <bool TA, bool TB, bool ACC, bool KTRI = false>
 __device__ __forceinline__ void gemm_block(double *C, int ldc, const double *A, int lda,
@@ -123,17 +125,28 @@ __device__ __forceinline__ void gemm_block(double *C, int ldc, const double *A, 
   const double *pb0 = TB ? B + t * ldb + j0 + g : B + (j0 + g) * ldb + t;
   const int sa = TA ? 1 : lda, sb = TB ? ldb : 1;       // stride of one k step
   const int oa = TA ? 8 * lda : 8, ob = TB ? 8 : 8 * ldb;  // offset of the second MMA tile
+  // r1, c1 are warp-uniform: one branch-free k loop per tile shape, and the MMA tiles
+  // beyond Mo / No are not issued.
+  auto k_loop = [&](auto R1, auto C1) {
 #pragma unroll 4
-  for (int k0 = KTRI ? i0 : 0; k0 < K; k0 += 4) {
-    const double a0 = pa0[k0 * sa];
-    const double a1 = r1 ? pa0[k0 * sa + oa] : 0.0;
-    const double b0 = sign * pb0[k0 * sb];
-    const double b1 = c1 ? sign * pb0[k0 * sb + ob] : 0.0;
-    dmma(acc[0][0], a0, b0);
-    dmma(acc[0][1], a0, b1);
-    dmma(acc[1][0], a1, b0);
-    dmma(acc[1][1], a1, b1);
-  }
+    for (int k0 = KTRI ? i0 : 0; k0 < K; k0 += 4) {
+      const double a0 = pa0[k0 * sa];
+      const double b0 = sign * pb0[k0 * sb];
+      double a1 = 0.0, b1 = 0.0;
+      if (decltype(R1)::value) a1 = pa0[k0 * sa + oa];
+      if (decltype(C1)::value) b1 = sign * pb0[k0 * sb + ob];
+      dmma(acc[0][0], a0, b0);
+      if (decltype(C1)::value) dmma(acc[0][1], a0, b1);
+      if (decltype(R1)::value) dmma(acc[1][0], a1, b0);
+      if (decltype(R1)::value && decltype(C1)::value) dmma(acc[1][1], a1, b1);
+    }
+  };
+  using Yes = std::true_type;
+  using No_ = std::false_type;
+  if (r1 && c1) k_loop(Yes{}, Yes{});
+  else if (r1) k_loop(Yes{}, No_{});
+  else if (c1) k_loop(No_{}, Yes{});
+  else k_loop(No_{}, No_{});
 #pragma unroll
   for (int a = 0; a < 2; ++a)
 #pragma unroll
@@ -539,7 +552,7 @@ riccati_backward_cta(LqrIn pm, int *status_out, double *store, double *scratch, 
                      int64_t ld, int T) {
   using S = CtaSmem<N, M>;
   using Zs = CtaSizes<N, M>;
-  constexpr int MP = S::MP, NZ = S::NZ, LDN = S::LDN, LDM = S::LDM;
+  constexpr int MP = S::MP, LDN = S::LDN, LDM = S::LDM;
   extern __shared__ __align__(16) double sm[];
   const int tid = threadIdx.x;
   const int64_t b = blockIdx.x;
@@ -747,7 +760,7 @@ riccati_backward_cta(LqrIn pm, int *status_out, double *store, double *scratch, 
     }
     TICK(2);
     // S = W' Z
-    cta_gemm<false, false, false, false>(Sb, LDN, Wp, LDN, Zb, LDN, N, NZ, N, 1.0);
+    cta_gemm<false, false, false, false>(Sb, LDN, Wp, LDN, Zb, LDN, N, N + M, N, 1.0);
     __syncthreads();
     TICK(3);
     // Psi_xx base: Q_k lower (prefetched, packed, in the K buffer) into the now free W' buffer.
@@ -768,10 +781,10 @@ riccati_backward_cta(LqrIn pm, int *status_out, double *store, double *scratch, 
     // Psi_ux += B' S_x,  Psi_uu += B' S_u (rows = u, K = N),  Psi_xx += A' S_x (lower
     // blocks): one deal of all their blocks over the warps.
     {
-      int slot = cta_gemm<true, false, true, false>(Pux, LDM, Zb + N * LDN, LDN, Sb, LDN, MP, N, N,
+      int slot = cta_gemm<true, false, true, false>(Pux, LDM, Zb + N * LDN, LDN, Sb, LDN, M, N, N,
                                                     1.0, 0);
-      slot = cta_gemm<true, false, true, true>(Puu, LDM, Zb + N * LDN, LDN, Sb + N * LDN, LDN, MP,
-                                               MP, N, 1.0, slot);
+      slot = cta_gemm<true, false, true, true>(Puu, LDM, Zb + N * LDN, LDN, Sb + N * LDN, LDN, M,
+                                               M, N, 1.0, slot);
       cta_gemm<true, false, true, true>(Wp, LDN, Zb, LDN, Sb, LDN, N, N, N, 1.0, slot);
     }
     __syncthreads();
@@ -788,11 +801,13 @@ riccati_backward_cta(LqrIn pm, int *status_out, double *store, double *scratch, 
       status = SIPOC_FACTOR_G_FACTORIZATION_FAILURE;
     TICK(6);
     // K = -G^-1 Psi_ux
-    cta_gemm<false, false, false, false>(Kb, LDM, Puu, LDM, Pux, LDM, MP, N, MP, -1.0);
+    // (rows and the k range stop at M: the padding block of G^-1 is the identity and the
+    // padding rows of Psi_ux are zero)
+    cta_gemm<false, false, false, false>(Kb, LDM, Puu, LDM, Pux, LDM, M, N, M, -1.0);
     if (SOLVE) cta_matvec<false>(kk_s, nullptr, Puu, LDM, hw_s + N, MP, MP, -1.0);  // k = -G^-1 h
     __syncthreads();
     // V = Psi_xx + Psi_ux' K (lower blocks);  v = w + Psi_ux' k
-    cta_gemm<true, false, true, true>(Wp, LDN, Pux, LDM, Kb, LDM, N, N, MP, 1.0);
+    cta_gemm<true, false, true, true>(Wp, LDN, Pux, LDM, Kb, LDM, N, N, M, 1.0);
     if (SOLVE) cta_matvec<true>(hw_s, hw_s, Pux, LDM, kk_s, N, MP, 1.0);
     // stores of the edge: K (M x N), G^-1 (packed lower), k
     for (int e = tid; e < N * M; e += kThreads)
@@ -1108,6 +1123,7 @@ rollout_forward_cta(LqrIn pm, LqrOut out, const double *store, const double *scr
 template <int N, int M>
 struct CtaPlan {
   static_assert(N % 16 == 0 && N <= 64, "state dimension must be a multiple of 16, at most 64");
+  static_assert(M % 4 == 0, "control dimension must be a multiple of 4 (MMA k step)");
   static int64_t store_elems(int T) { return CtaSizes<N, M>::store(T); }
   static int64_t scratch_elems(int T) { return CtaSizes<N, M>::scratch(T); }
   template <bool SOLVE>

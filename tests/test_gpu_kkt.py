@@ -60,7 +60,7 @@ def _uniform_kkt_structure(n, m, T):
                            edge_g=[g] * T)
 
 
-@pytest.mark.parametrize("n,m,T", [(4, 1, 16), (12, 4, 12), (6, 2, 20)])
+@pytest.mark.parametrize("n,m,T", [(4, 1, 16), (12, 4, 12), (6, 2, 20), (16, 4, 6)])
 @pytest.mark.parametrize("force_generic", [True, False])
 def test_newton_kkt_benchmark_shapes(n, m, T, force_generic):
     # Moderate regularization range (r2 <= 1e3) where two correct FP64
