@@ -172,6 +172,20 @@ sipoc_error sipoc_lqr_solve(sipoc_engine *engine, const sipoc_lqr_input *in,
 sipoc_error sipoc_lqr_factor_solve(sipoc_engine *engine, const sipoc_lqr_input *in,
                                    const sipoc_lqr_output *out, int *status,
                                    void *stream);
+/* The same three calls with the INPUT arrays problem-major on the device,
+ * X[problem * size + flat] -- the layout of the *_host entry points, i.e. what a
+ * caller holding one set of matrices per problem (LQR::Input's tables,
+ * lqr.hpp:76-89) has after a plain copy.  Outputs and status stay in the engine
+ * layout.  Native for the CTA-per-problem plans (state dimension >= 16), which
+ * would otherwise transpose every call's inputs; every other plan packs the
+ * arrays into the engine layout first.  Arrays must be 16-byte aligned. */
+sipoc_error sipoc_lqr_factor_pm(sipoc_engine *engine, const sipoc_lqr_input *in,
+                                int *status, void *stream);
+sipoc_error sipoc_lqr_solve_pm(sipoc_engine *engine, const sipoc_lqr_input *in,
+                               const sipoc_lqr_output *out, void *stream);
+sipoc_error sipoc_lqr_factor_solve_pm(sipoc_engine *engine, const sipoc_lqr_input *in,
+                                      const sipoc_lqr_output *out, int *status,
+                                      void *stream);
 /* residual_norm: device double[batch_stride] or NULL.  stats: device double[4]
  * or NULL, overwritten with {sum of squared norms, max norm, #failed problems
  * (status != 0; status may be NULL), #problems} over this device's batch —

@@ -114,6 +114,9 @@ def _load() -> ctypes.CDLL:
     lib.sipoc_lqr_factor.argtypes = [E, LI, P, P]
     lib.sipoc_lqr_solve.argtypes = [E, LI, LO, P]
     lib.sipoc_lqr_factor_solve.argtypes = [E, LI, LO, P, P]
+    lib.sipoc_lqr_factor_pm.argtypes = [E, LI, P, P]
+    lib.sipoc_lqr_solve_pm.argtypes = [E, LI, LO, P]
+    lib.sipoc_lqr_factor_solve_pm.argtypes = [E, LI, LO, P, P]
     lib.sipoc_lqr_residual.argtypes = [E, LI, LO, P, P, P, P]
     lib.sipoc_status_stats.argtypes = [E, P, P, P]
     lib.sipoc_pack.argtypes = [E, P, P, ctypes.c_int64, P]

@@ -45,6 +45,7 @@ struct sipoc_engine {
   // Fast-path storage (lazy).
   double *fast_store = nullptr, *fast_scratch = nullptr;
   double *pm_in[9] = {nullptr};  // problem-major input copies (plans that ask for them)
+  double *il_in[9] = {nullptr};  // interleaved copies of problem-major caller arrays (*_pm calls)
   enum class Factored { NONE, GENERIC, FAST } factored = Factored::NONE;
 
   // Newton-KKT reduction outputs (lazy).
@@ -257,14 +258,53 @@ sipoc_error refresh_problem_major(sipoc_engine *e, const LqrIn &in, unsigned mas
   return SIPOC_OK;
 }
 
+// The *_pm entry points take the input arrays problem-major.  Plans that want that
+// layout use the caller's arrays in place; for every other path the arrays `mask`
+// selects are packed into interleaved copies first.
+//   layout_pm == false: *il = in, *pm = the engine's problem-major copies (if the plan wants them)
+//   layout_pm == true : *il = {} and *pm = in (native), or *il = packed copies and *pm = {}
+sipoc_error resolve_inputs(sipoc_engine *e, const LqrIn &in, bool layout_pm, unsigned mask,
+                           LqrIn *il, LqrIn *pm, cudaStream_t s) {
+  if (!layout_pm) {
+    *il = in;
+    return use_fast(e, in) ? refresh_problem_major(e, in, mask, pm, s) : SIPOC_OK;
+  }
+  if (e->fast != nullptr && e->fast->problem_major_inputs && aligned16(in)) {
+    *il = LqrIn{};
+    *pm = in;
+    return SIPOC_OK;
+  }
+  const double *src[9] = {in.Q, in.M, in.R, in.q, in.r, in.A, in.B, in.c, in.delta};
+  for (int i = 0; i < 9; ++i) {
+    if ((mask >> i & 1u) == 0) continue;
+    const int64_t size = lqr_in_size(e->hs, i);
+    if (e->il_in[i] == nullptr) {
+      sipoc_error rc = alloc_doubles(e, &e->il_in[i], size);
+      if (rc != SIPOC_OK) return rc;
+    }
+    ProfScope ps(&e->prof, "pack_kernel", s);
+    launch_pack(src[i], e->il_in[i], size, e->batch, e->ld, s);
+    e->launches += 1;
+  }
+  *il = LqrIn{e->il_in[0], e->il_in[1], e->il_in[2], e->il_in[3], e->il_in[4],
+              e->il_in[5], e->il_in[6], e->il_in[7], e->il_in[8]};
+  *pm = LqrIn{};
+  return SIPOC_OK;
+}
+
 // --- device-path cores (shared by the device and host entry points) --------
-sipoc_error lqr_factor_core(sipoc_engine *e, const LqrIn &in, int *status,
-                            cudaStream_t s) {
+bool native_pm(const sipoc_engine *e, const LqrIn &in, bool layout_pm) {
+  return layout_pm && e->fast != nullptr && e->fast->problem_major_inputs && aligned16(in);
+}
+
+sipoc_error lqr_factor_core(sipoc_engine *e, const LqrIn &caller_in, int *status, cudaStream_t s,
+                            bool layout_pm = false) {
   sipoc_error rc;
-  if (use_fast(e, in)) {
+  LqrIn in, pm;
+  if ((rc = resolve_inputs(e, caller_in, layout_pm, kPmMatrices, &in, &pm, s)) != SIPOC_OK)
+    return rc;
+  if (native_pm(e, caller_in, layout_pm) || use_fast(e, in)) {
     if ((rc = ensure_fast_store(e)) != SIPOC_OK) return rc;
-    LqrIn pm;
-    if ((rc = refresh_problem_major(e, in, kPmMatrices, &pm, s)) != SIPOC_OK) return rc;
     FastArgs a{in, pm, LqrOut{}, status, e->fast_store, nullptr, e->batch, e->ld, e->hs.E,
                &e->prof};
     e->launches += e->fast->factor(a, s);
@@ -281,18 +321,18 @@ sipoc_error lqr_factor_core(sipoc_engine *e, const LqrIn &in, int *status,
   return check_launch(e, "lqr_factor");
 }
 
-sipoc_error lqr_solve_core(sipoc_engine *e, const LqrIn &in, const LqrOut &out,
-                           cudaStream_t s) {
+sipoc_error lqr_solve_core(sipoc_engine *e, const LqrIn &caller_in, const LqrOut &out,
+                           cudaStream_t s, bool layout_pm = false) {
   sipoc_error rc;
   if (e->factored == sipoc_engine::Factored::NONE)
     return fail(e, SIPOC_NOT_FACTORED, "solve called before a factor on this handle");
-  if (e->factored == sipoc_engine::Factored::FAST && !aligned16(in))
+  if (e->factored == sipoc_engine::Factored::FAST && !aligned16(caller_in))
     return fail(e, SIPOC_INVALID_ARGUMENT,
                 "solve against a fast-path factorization needs 16-byte aligned arrays");
+  LqrIn in, pm;
+  if ((rc = resolve_inputs(e, caller_in, layout_pm, kPmSolve, &in, &pm, s)) != SIPOC_OK) return rc;
   if (e->factored == sipoc_engine::Factored::FAST) {
     if ((rc = ensure_fast_scratch(e)) != SIPOC_OK) return rc;
-    LqrIn pm;
-    if ((rc = refresh_problem_major(e, in, kPmSolve, &pm, s)) != SIPOC_OK) return rc;
     FastArgs a{in, pm, out, nullptr, e->fast_store, e->fast_scratch, e->batch, e->ld,
                e->hs.E, &e->prof};
     e->launches += e->fast->solve(a, s);
@@ -306,14 +346,14 @@ sipoc_error lqr_solve_core(sipoc_engine *e, const LqrIn &in, const LqrOut &out,
   return check_launch(e, "lqr_solve");
 }
 
-sipoc_error lqr_factor_solve_core(sipoc_engine *e, const LqrIn &in, const LqrOut &out,
-                                  int *status, cudaStream_t s) {
+sipoc_error lqr_factor_solve_core(sipoc_engine *e, const LqrIn &caller_in, const LqrOut &out,
+                                  int *status, cudaStream_t s, bool layout_pm = false) {
   sipoc_error rc;
-  if (use_fast(e, in)) {
+  LqrIn in, pm;
+  if ((rc = resolve_inputs(e, caller_in, layout_pm, kPmAll, &in, &pm, s)) != SIPOC_OK) return rc;
+  if (native_pm(e, caller_in, layout_pm) || use_fast(e, in)) {
     if ((rc = ensure_fast_store(e)) != SIPOC_OK) return rc;
     if ((rc = ensure_fast_scratch(e)) != SIPOC_OK) return rc;
-    LqrIn pm;
-    if ((rc = refresh_problem_major(e, in, kPmAll, &pm, s)) != SIPOC_OK) return rc;
     FastArgs a{in, pm, out, status, e->fast_store, e->fast_scratch, e->batch, e->ld, e->hs.E,
                &e->prof};
     e->launches += e->fast->factor_solve(a, s);
@@ -321,6 +361,7 @@ sipoc_error lqr_factor_solve_core(sipoc_engine *e, const LqrIn &in, const LqrOut
     e->factored = sipoc_engine::Factored::FAST;
     return check_launch(e, "lqr_factor_solve");
   }
+  // `in` is interleaved here (the caller's own arrays or their packed copies).
   if ((rc = lqr_factor_core(e, in, status, s)) != SIPOC_OK) return rc;
   return lqr_solve_core(e, in, out, s);
 }
@@ -697,6 +738,34 @@ sipoc_error sipoc_lqr_factor_solve(sipoc_engine *e, const sipoc_lqr_input *in,
   DeviceGuard guard(e->device);
   return lqr_factor_solve_core(e, to_in(in), LqrOut{out->x, out->u, out->y}, status,
                                static_cast<cudaStream_t>(stream));
+}
+
+sipoc_error sipoc_lqr_factor_pm(sipoc_engine *e, const sipoc_lqr_input *in, int *status,
+                                void *stream) {
+  if (e == nullptr) return SIPOC_INVALID_ARGUMENT;
+  if (null_in(in, true, false)) return fail(e, SIPOC_INVALID_ARGUMENT, "NULL LQR input");
+  DeviceGuard guard(e->device);
+  return lqr_factor_core(e, to_in(in), status, static_cast<cudaStream_t>(stream), true);
+}
+
+sipoc_error sipoc_lqr_solve_pm(sipoc_engine *e, const sipoc_lqr_input *in,
+                               const sipoc_lqr_output *out, void *stream) {
+  if (e == nullptr) return SIPOC_INVALID_ARGUMENT;
+  if (null_in(in, false, true) || out == nullptr || !out->x || !out->u || !out->y)
+    return fail(e, SIPOC_INVALID_ARGUMENT, "NULL LQR input / output");
+  DeviceGuard guard(e->device);
+  return lqr_solve_core(e, to_in(in), LqrOut{out->x, out->u, out->y},
+                        static_cast<cudaStream_t>(stream), true);
+}
+
+sipoc_error sipoc_lqr_factor_solve_pm(sipoc_engine *e, const sipoc_lqr_input *in,
+                                      const sipoc_lqr_output *out, int *status, void *stream) {
+  if (e == nullptr) return SIPOC_INVALID_ARGUMENT;
+  if (null_in(in, true, true) || out == nullptr || !out->x || !out->u || !out->y)
+    return fail(e, SIPOC_INVALID_ARGUMENT, "NULL LQR input / output");
+  DeviceGuard guard(e->device);
+  return lqr_factor_solve_core(e, to_in(in), LqrOut{out->x, out->u, out->y}, status,
+                               static_cast<cudaStream_t>(stream), true);
 }
 
 sipoc_error sipoc_lqr_residual(sipoc_engine *e, const sipoc_lqr_input *in,

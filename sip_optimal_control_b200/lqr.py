@@ -372,6 +372,42 @@ class LQR:
                                             status.data_ptr(), e.stream_ptr(stream)))
         return status
 
+    # Problem-major device inputs (sipoc_lqr_*_pm): ``inp`` holds CUDA tensors laid out
+    # [problem][flat] -- `problem_major_input` uploads host arrays that way.  Outputs stay
+    # in the engine layout.
+    def problem_major_input(self, host: dict) -> dict:
+        e = self.engine
+        torch = e._torch()
+        return {k: torch.from_numpy(np.ascontiguousarray(host[k], dtype=np.float64)
+                                    .reshape(self.batch, -1)).to(e.torch_device())
+                for k in _capi.LQR_INPUT_FIELDS}
+
+    def factor_with_status_pm(self, inp: dict, status=None, stream=None):
+        if self.traversal_status_ != FactorStatus.SUCCESS:
+            return self._invalid()
+        e = self.engine
+        status = e.empty_int() if status is None else status
+        s = _lqr_input_struct(inp)
+        e._check(lib.sipoc_lqr_factor_pm(e._handle, ctypes.byref(s), status.data_ptr(),
+                                         e.stream_ptr(stream)))
+        return status
+
+    def solve_pm(self, inp: dict, out: dict, stream=None) -> None:
+        e = self.engine
+        si, so = _lqr_input_struct(inp), _lqr_output_struct(out)
+        e._check(lib.sipoc_lqr_solve_pm(e._handle, ctypes.byref(si), ctypes.byref(so),
+                                        e.stream_ptr(stream)))
+
+    def factor_solve_pm(self, inp: dict, out: dict, status=None, stream=None):
+        if self.traversal_status_ != FactorStatus.SUCCESS:
+            return self._invalid()
+        e = self.engine
+        status = e.empty_int() if status is None else status
+        si, so = _lqr_input_struct(inp), _lqr_output_struct(out)
+        e._check(lib.sipoc_lqr_factor_solve_pm(e._handle, ctypes.byref(si), ctypes.byref(so),
+                                               status.data_ptr(), e.stream_ptr(stream)))
+        return status
+
     def residual(self, inp: dict, out: dict, status=None, stream=None):
         """Returns (per-problem KKT residual norms, 4 all-reducible statistics)."""
         e = self.engine

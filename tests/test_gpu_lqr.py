@@ -225,6 +225,38 @@ def test_factor_once_solve_many(n, m, T):
         assert_lqr_parity(gpu, ref, REL_TOL)
 
 
+@pytest.mark.parametrize("n,m,T", [(12, 4, 9), (5, 2, 7), (16, 4, 6), (32, 8, 5), (64, 24, 3)])
+def test_problem_major_entry_points(n, m, T):
+    # sipoc_lqr_*_pm: the same three calls with problem-major device inputs -- native for
+    # the CTA-per-problem plans, packed first for every other path.
+    batch = 21
+    s, host = pg.lqr_benchmark_batch(n, m, T, batch, seed=11 + n)
+    dims, topo = to_structs(s)
+    lqr = LQR(dims, topo, batch)
+    ref = pyoracle.lqr_factor_solve(s, host)
+    pm = lqr.problem_major_input(host)
+    out = lqr.alloc_output()
+    status = lqr.factor_solve_pm(pm, out)
+    assert (status[:batch].cpu().numpy() == 0).all()
+    assert_lqr_parity(lqr.unpack_output(out), ref, REL_TOL)
+    # factor once, re-solve with new affine terms
+    out2 = lqr.alloc_output()
+    status = lqr.factor_with_status_pm(pm)
+    assert (status[:batch].cpu().numpy() == 0).all()
+    rng = np.random.default_rng(5)
+    h2 = dict(host)
+    for k in ("q", "r", "c"):
+        h2[k] = rng.standard_normal(host[k].shape)
+    lqr.solve_pm(lqr.problem_major_input(h2), out2)
+    assert_lqr_parity(lqr.unpack_output(out2), pyoracle.lqr_factor_solve(s, h2), REL_TOL)
+    # a failing problem keeps its status through the problem-major path
+    bad = {k: v.copy() for k, v in host.items()}
+    bad["delta"][3, :n] = -1.0
+    status = lqr.factor_solve_pm(lqr.problem_major_input(bad), out)
+    st = status[:batch].cpu().numpy()
+    assert st[3] != 0 and (np.delete(st, 3) == 0).all()
+
+
 def test_variable_dimension_chain_and_tree_batches():
     # per-node dims like tests/variable_dimensions_test.cpp:266-271, tiled
     # along a longer horizon, plus a deeper tree.
