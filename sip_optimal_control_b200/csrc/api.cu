@@ -452,13 +452,17 @@ sipoc_error ensure_host_lqr(sipoc_engine *e) {
   const HostStructure &h = e->hs;
   sipoc_error rc;
   int64_t biggest = 1;
-  for (int i = 0; i < 9; ++i) {
+  // (problem-major plans upload straight into their own input buffers: no interleaved copies)
+  const bool pm_path = e->fast != nullptr && e->fast->problem_major_inputs;
+  for (int i = 0; i < 9 && !pm_path; ++i) {
     if ((rc = alloc_doubles(e, &e->h_in[i], lqr_in_size(h, i))) != SIPOC_OK) return rc;
     biggest = std::max(biggest, lqr_in_size(h, i));
   }
   const int64_t out_sizes[3] = {h.n_off[h.N], h.m_off[h.E], h.n_off[h.N]};
-  for (int i = 0; i < 3; ++i)
+  for (int i = 0; i < 3; ++i) {
     if ((rc = alloc_doubles(e, &e->h_out[i], out_sizes[i])) != SIPOC_OK) return rc;
+    biggest = std::max(biggest, out_sizes[i]);
+  }
   if ((rc = ensure_stage(e, biggest)) != SIPOC_OK) return rc;
   if (e->h_status == nullptr) {
     rc = dev_alloc(e, reinterpret_cast<void **>(&e->h_status),
@@ -820,21 +824,42 @@ sipoc_error sipoc_unpack(sipoc_engine *e, const double *src, double *dst, int64_
 }
 
 // ---- host-buffer LQR --------------------------------------------------------
+// Plans that read problem-major inputs take the host arrays as they are: one H2D copy
+// per array straight into the engine's problem-major buffers, no pack, no unpack.
+static bool host_path_is_pm(const sipoc_engine *e) {
+  return e->fast != nullptr && e->fast->problem_major_inputs;
+}
+
 static sipoc_error host_upload_lqr(sipoc_engine *e, const sipoc_lqr_input *in,
                                    bool matrices, bool vectors) {
   const double *src[9] = {in->Q, in->M, in->R, in->q, in->r, in->A, in->B, in->c, in->delta};
   const bool is_vec[9] = {false, false, false, true, true, false, false, true, false};
   for (int i = 0; i < 9; ++i) {
     if ((is_vec[i] && !vectors) || (!is_vec[i] && !matrices)) continue;
-    sipoc_error rc = upload(e, src[i], e->h_in[i], lqr_in_size(e->hs, i));
+    const int64_t size = lqr_in_size(e->hs, i);
+    if (host_path_is_pm(e)) {
+      if (size == 0) continue;
+      if (src[i] == nullptr) return fail(e, SIPOC_INVALID_ARGUMENT, "NULL host input array");
+      if (e->pm_in[i] == nullptr) {
+        sipoc_error rc = dev_alloc(e, reinterpret_cast<void **>(&e->pm_in[i]),
+                                   static_cast<size_t>(size) * static_cast<size_t>(e->batch) *
+                                       sizeof(double));
+        if (rc != SIPOC_OK) return rc;
+      }
+      SIPOC_CUDA(e, cudaMemcpyAsync(e->pm_in[i], src[i],
+                                    static_cast<size_t>(size) * e->batch * sizeof(double),
+                                    cudaMemcpyHostToDevice, e->host_stream));
+      continue;
+    }
+    sipoc_error rc = upload(e, src[i], e->h_in[i], size);
     if (rc != SIPOC_OK) return rc;
   }
   return SIPOC_OK;
 }
 
 static LqrIn host_resident_in(const sipoc_engine *e) {
-  return LqrIn{e->h_in[0], e->h_in[1], e->h_in[2], e->h_in[3], e->h_in[4],
-               e->h_in[5], e->h_in[6], e->h_in[7], e->h_in[8]};
+  double *const *a = host_path_is_pm(e) ? e->pm_in : e->h_in;
+  return LqrIn{a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8]};
 }
 
 static sipoc_error host_download_out(sipoc_engine *e, const sipoc_lqr_output *out) {
@@ -856,7 +881,7 @@ sipoc_error sipoc_lqr_factor_solve_host(sipoc_engine *e, const sipoc_lqr_input *
   if ((rc = host_upload_lqr(e, in, true, true)) != SIPOC_OK) return rc;
   rc = lqr_factor_solve_core(e, host_resident_in(e),
                              LqrOut{e->h_out[0], e->h_out[1], e->h_out[2]}, e->h_status,
-                             e->host_stream);
+                             e->host_stream, host_path_is_pm(e));
   if (rc != SIPOC_OK) return rc;
   e->host_lqr_factored = false;
   if ((rc = host_download_out(e, out)) != SIPOC_OK) return rc;
@@ -874,7 +899,8 @@ sipoc_error sipoc_lqr_factor_host(sipoc_engine *e, const sipoc_lqr_input *in,
   sipoc_error rc;
   if ((rc = ensure_host_lqr(e)) != SIPOC_OK) return rc;
   if ((rc = host_upload_lqr(e, in, true, false)) != SIPOC_OK) return rc;
-  if ((rc = lqr_factor_core(e, host_resident_in(e), e->h_status, e->host_stream)) != SIPOC_OK)
+  if ((rc = lqr_factor_core(e, host_resident_in(e), e->h_status, e->host_stream,
+                            host_path_is_pm(e))) != SIPOC_OK)
     return rc;
   e->host_lqr_factored = true;
   if (host_status != nullptr)
@@ -893,7 +919,7 @@ sipoc_error sipoc_lqr_solve_host(sipoc_engine *e, const sipoc_lqr_input *in,
   sipoc_error rc;
   if ((rc = host_upload_lqr(e, in, false, true)) != SIPOC_OK) return rc;
   rc = lqr_solve_core(e, host_resident_in(e), LqrOut{e->h_out[0], e->h_out[1], e->h_out[2]},
-                      e->host_stream);
+                      e->host_stream, host_path_is_pm(e));
   if (rc != SIPOC_OK) return rc;
   if ((rc = host_download_out(e, out)) != SIPOC_OK) return rc;
   SIPOC_CUDA(e, cudaStreamSynchronize(e->host_stream));
