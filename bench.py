@@ -38,6 +38,10 @@ WORKLOADS = {
     "cartpole": dict(n=4, m=1, T=100, batch=16384),
     "quadrotor": dict(n=12, m=4, T=50, batch=65536),
     "humanoid": dict(n=64, m=24, T=32, batch=4096),
+    # Config 5's long-horizon, small-batch case at both dims SURVEY section 8d names.  The
+    # parallel-in-time scan is not built: these run the sequential-in-time kernels above.
+    "long_horizon_quadrotor": dict(n=12, m=4, T=4096, batch=64),
+    "long_horizon_humanoid": dict(n=64, m=24, T=4096, batch=64),
 }
 # Config 4: Newton-KKT with inequality constraints and variable per-stage dims — the
 # pattern of tests/variable_dimensions_test.cpp:266-271 tiled along the horizon.
