@@ -531,7 +531,8 @@ def run_kkt(args):
     torch.cuda.set_device(0)
     dev = torch.device("cuda", 0)
     sampler = ClockSampler(0)
-    cp = CallbackProvider(dims, Topology.chain(T), batch, device=0)
+    cp = CallbackProvider(dims, Topology.chain(T), batch, device=0,
+                          pad_variable_dims=getattr(args, "pad_variable_dims", False))
     eng = cp.engine
     # The shape-specialised LQR kernels reorder the arithmetic; they stay within 1e-9 of the
     # reference order for r2 <= 1e3 (tests/test_gpu_kkt.py), so the uniform workload uses
@@ -619,6 +620,9 @@ def main():
     ap.add_argument("--force-generic", action="store_true")
     ap.add_argument("--input-layout", default="interleaved", choices=["interleaved", "problem_major"],
                     help="device layout of the inputs the timed call takes (LQR workloads)")
+    ap.add_argument("--pad-variable-dims", action="store_true",
+                    help="newton_kkt: SIPOC_FLAG_PAD_VARIABLE_DIMS (shape-specialised kernels through "
+                         "decoupled padding instead of the strict-order generic kernels)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--e2e-batch", type=int, default=16384)

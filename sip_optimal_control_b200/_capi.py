@@ -28,6 +28,7 @@ ERROR_NAMES = {
 SIPOC_INVALID_TOPOLOGY = 4
 SIPOC_INVALID_DIMENSIONS = 5
 SIPOC_FLAG_FORCE_GENERIC = 1
+SIPOC_FLAG_PAD_VARIABLE_DIMS = 2
 
 
 class Structure(ctypes.Structure):

@@ -46,6 +46,11 @@ struct sipoc_engine {
   double *fast_store = nullptr, *fast_scratch = nullptr;
   double *pm_in[9] = {nullptr};  // problem-major input copies (plans that ask for them)
   double *il_in[9] = {nullptr};  // interleaved copies of problem-major caller arrays (*_pm calls)
+  // Chains whose dims vary from stage to stage run on the plan of the smallest uniform
+  // shape that holds every stage, through decoupled padding (generic_kernels.cu, pad_chain_kernel).
+  bool padded = false;
+  double *pad_in[9] = {nullptr};
+  double *pad_out[3] = {nullptr};
   enum class Factored { NONE, GENERIC, FAST } factored = Factored::NONE;
 
   // Newton-KKT reduction outputs (lazy).
@@ -293,6 +298,47 @@ sipoc_error resolve_inputs(sipoc_engine *e, const LqrIn &in, bool layout_pm, uns
 }
 
 // --- device-path cores (shared by the device and host entry points) --------
+// Padded plans: `in` (interleaved, the structure's own variable-dim layout) -> the engine's
+// uniform padded arrays; the plan then runs on those and writes padded outputs.
+sipoc_error pad_inputs(sipoc_engine *e, LqrIn *in, unsigned mask, cudaStream_t s) {
+  const int np = e->fast->n, mp = e->fast->m, N = e->hs.N, E = e->hs.E;
+  const int64_t sizes[9] = {int64_t(N) * np * np, int64_t(E) * np * mp, int64_t(E) * mp * mp,
+                            int64_t(N) * np,      int64_t(E) * mp,      int64_t(E) * np * np,
+                            int64_t(E) * np * mp, int64_t(N) * np,      int64_t(N) * np};
+  for (int i = 0; i < 9; ++i) {
+    if (e->pad_in[i] != nullptr) continue;
+    sipoc_error rc = alloc_doubles(e, &e->pad_in[i], sizes[i]);
+    if (rc != SIPOC_OK) return rc;
+  }
+  const LqrIn dst{e->pad_in[0], e->pad_in[1], e->pad_in[2], e->pad_in[3], e->pad_in[4],
+                  e->pad_in[5], e->pad_in[6], e->pad_in[7], e->pad_in[8]};
+  {
+    ProfScope ps(&e->prof, "pad_chain_kernel", s);
+    launch_pad_chain(e->dt, *in, dst, np, mp, mask, e->batch, e->ld, s);
+  }
+  e->launches += 1;
+  *in = dst;
+  return SIPOC_OK;
+}
+
+sipoc_error padded_outputs(sipoc_engine *e, LqrOut *out) {
+  const int np = e->fast->n, mp = e->fast->m, N = e->hs.N, E = e->hs.E;
+  const int64_t sizes[3] = {int64_t(N) * np, int64_t(E) * mp, int64_t(N) * np};
+  for (int i = 0; i < 3; ++i) {
+    if (e->pad_out[i] != nullptr) continue;
+    sipoc_error rc = alloc_doubles(e, &e->pad_out[i], sizes[i]);
+    if (rc != SIPOC_OK) return rc;
+  }
+  *out = LqrOut{e->pad_out[0], e->pad_out[1], e->pad_out[2]};
+  return SIPOC_OK;
+}
+
+void unpad_outputs(sipoc_engine *e, const LqrOut &padded, const LqrOut &out, cudaStream_t s) {
+  ProfScope ps(&e->prof, "unpad_chain_kernel", s);
+  launch_unpad_chain(e->dt, padded, out, e->fast->n, e->fast->m, e->batch, e->ld, s);
+  e->launches += 1;
+}
+
 bool native_pm(const sipoc_engine *e, const LqrIn &in, bool layout_pm) {
   return layout_pm && e->fast != nullptr && e->fast->problem_major_inputs && aligned16(in);
 }
@@ -305,6 +351,7 @@ sipoc_error lqr_factor_core(sipoc_engine *e, const LqrIn &caller_in, int *status
     return rc;
   if (native_pm(e, caller_in, layout_pm) || use_fast(e, in)) {
     if ((rc = ensure_fast_store(e)) != SIPOC_OK) return rc;
+    if (e->padded && (rc = pad_inputs(e, &in, kPmMatrices, s)) != SIPOC_OK) return rc;
     FastArgs a{in, pm, LqrOut{}, status, e->fast_store, nullptr, e->batch, e->ld, e->hs.E,
                &e->prof};
     e->launches += e->fast->factor(a, s);
@@ -333,9 +380,15 @@ sipoc_error lqr_solve_core(sipoc_engine *e, const LqrIn &caller_in, const LqrOut
   if ((rc = resolve_inputs(e, caller_in, layout_pm, kPmSolve, &in, &pm, s)) != SIPOC_OK) return rc;
   if (e->factored == sipoc_engine::Factored::FAST) {
     if ((rc = ensure_fast_scratch(e)) != SIPOC_OK) return rc;
-    FastArgs a{in, pm, out, nullptr, e->fast_store, e->fast_scratch, e->batch, e->ld,
+    LqrOut plan_out = out;
+    if (e->padded) {
+      if ((rc = pad_inputs(e, &in, kPmSolve, s)) != SIPOC_OK) return rc;
+      if ((rc = padded_outputs(e, &plan_out)) != SIPOC_OK) return rc;
+    }
+    FastArgs a{in, pm, plan_out, nullptr, e->fast_store, e->fast_scratch, e->batch, e->ld,
                e->hs.E, &e->prof};
     e->launches += e->fast->solve(a, s);
+    if (e->padded) unpad_outputs(e, plan_out, out, s);
   } else {
     {
       ProfScope ps(&e->prof, "generic_lqr_solve_kernel", s);
@@ -354,9 +407,15 @@ sipoc_error lqr_factor_solve_core(sipoc_engine *e, const LqrIn &caller_in, const
   if (native_pm(e, caller_in, layout_pm) || use_fast(e, in)) {
     if ((rc = ensure_fast_store(e)) != SIPOC_OK) return rc;
     if ((rc = ensure_fast_scratch(e)) != SIPOC_OK) return rc;
-    FastArgs a{in, pm, out, status, e->fast_store, e->fast_scratch, e->batch, e->ld, e->hs.E,
+    LqrOut plan_out = out;
+    if (e->padded) {
+      if ((rc = pad_inputs(e, &in, kPmAll, s)) != SIPOC_OK) return rc;
+      if ((rc = padded_outputs(e, &plan_out)) != SIPOC_OK) return rc;
+    }
+    FastArgs a{in, pm, plan_out, status, e->fast_store, e->fast_scratch, e->batch, e->ld, e->hs.E,
                &e->prof};
     e->launches += e->fast->factor_solve(a, s);
+    if (e->padded) unpad_outputs(e, plan_out, out, s);
     // The backward kernel keeps W, K and G^-1, so later solves may reuse them.
     e->factored = sipoc_engine::Factored::FAST;
     return check_launch(e, "lqr_factor_solve");
@@ -537,8 +596,8 @@ sipoc_error kkt_solve_core(sipoc_engine *e, const KktModel &mdl, const double *b
                            double *sol, cudaStream_t s) {
   if (!e->kkt_factored)
     return fail(e, SIPOC_NOT_FACTORED, "kkt_solve called before kkt_factor");
-  if (e->factored == sipoc_engine::Factored::FAST && e->fast->kkt_solve != nullptr &&
-      e->batch >= kFusedKktMinBatch) {
+  if (e->factored == sipoc_engine::Factored::FAST && !e->padded &&
+      e->fast->kkt_solve != nullptr && e->batch >= kFusedKktMinBatch) {
     // Uniform chain: rhs build fused into the affine sweep, dual recovery into the rollout.
     sipoc_error rc = ensure_fast_scratch(e);
     if (rc != SIPOC_OK) return rc;
@@ -628,6 +687,17 @@ sipoc_error sipoc_create(const sipoc_structure *s, sipoc_engine **out) {
   if (e->fast == nullptr && !(e->flags & SIPOC_FLAG_FORCE_GENERIC) && h.is_chain &&
       h.is_uniform && h.E >= 1)
     e->fast = select_cta_plan(h.n[0], h.m[0]);
+  if (e->fast == nullptr && !(e->flags & SIPOC_FLAG_FORCE_GENERIC) &&
+      (e->flags & SIPOC_FLAG_PAD_VARIABLE_DIMS) && h.is_chain && !h.is_uniform && h.E >= 1) {
+    // smallest instantiated register / sub-warp shape that holds every stage
+    const int shapes[][2] = {{4, 1}, {6, 2}, {8, 3}, {12, 4}};
+    for (const auto &sh : shapes) {
+      if (sh[0] >= h.max_n && sh[1] >= h.max_m && (e->fast = select_fast_plan(sh[0], sh[1]))) {
+        e->padded = true;
+        break;
+      }
+    }
+  }
   if (!(e->flags & SIPOC_FLAG_FORCE_GENERIC) && h.is_chain && h.is_uniform && h.E >= 1) {
     e->kkt_reduce_fast = select_kkt_reduce(h.n[0], h.m[0]);
     for (int i = 0; i < h.N; ++i) {
@@ -638,6 +708,7 @@ sipoc_error sipoc_create(const sipoc_structure *s, sipoc_engine **out) {
     if (e->kkt_max_rows * 32 * 8 > 40 * 1024) e->kkt_reduce_fast = nullptr;
   }
   e->variant = e->fast != nullptr ? e->fast->name : "generic_thread_per_problem";
+  if (e->padded) e->variant = "padded_to_" + e->variant;
   *out = e;
   return SIPOC_OK;
 }

@@ -829,6 +829,79 @@ unpack_kernel(const double *__restrict__ src, double *__restrict__ dst, int64_t 
   }
 }
 
+// ---------------------------------------------------------------------------
+// Variable-dimension chain <-> uniform chain of dims (NP, MP) >= every stage's dims.
+// A stage is padded with states / controls that are decoupled from the real ones
+// (identity on the diagonal of Q and R, delta = 1, zeros elsewhere: their terms enter
+// every product as exact zeros), so the shape-specialised kernels serve chains whose
+// dims change from stage to stage.  One thread per (stage, problem); consecutive threads
+// are consecutive problems, so every access is a full coalesced request.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+pad_chain_kernel(DevTables t, LqrIn src, LqrIn dst, int NP, int MP, unsigned mask, int64_t batch,
+                 int64_t ld) {
+  const int64_t b = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int k = blockIdx.y;  // node k, and edge k when k < E
+  if (b >= batch) return;
+  const size_t L = static_cast<size_t>(ld);
+  const int nk = t.n[k];
+  auto at = [&](const double *p, size_t flat) { return p[flat * L + b]; };
+  // (dst holds the engine's own padded buffers; LqrIn's members are const for the readers)
+  auto put = [&](const double *p, size_t flat, double v) { const_cast<double *>(p)[flat * L + b] = v; };
+  if (mask & 1u)
+    for (int j = 0; j < NP; ++j)
+      for (int i = 0; i < NP; ++i)
+        put(dst.Q, (static_cast<size_t>(k) * NP + j) * NP + i,
+            (i < nk && j < nk) ? at(src.Q, t.nn_off[k] + j * nk + i) : (i == j ? 1.0 : 0.0));
+  for (int i = 0; i < NP; ++i) {
+    const bool in = i < nk;
+    if (mask & 8u) put(dst.q, static_cast<size_t>(k) * NP + i, in ? at(src.q, t.n_off[k] + i) : 0.0);
+    if (mask & 128u) put(dst.c, static_cast<size_t>(k) * NP + i, in ? at(src.c, t.n_off[k] + i) : 0.0);
+    if (mask & 256u)
+      put(dst.delta, static_cast<size_t>(k) * NP + i, in ? at(src.delta, t.n_off[k] + i) : 1.0);
+  }
+  if (k >= t.E) return;
+  const int mk = t.m[k], nc = t.n[k + 1];
+  for (int a = 0; a < MP; ++a) {
+    if (mask & 2u)
+      for (int x = 0; x < NP; ++x)
+        put(dst.M, (static_cast<size_t>(k) * MP + a) * NP + x,
+            (x < nk && a < mk) ? at(src.M, t.nm_off[k] + a * nk + x) : 0.0);
+    if (mask & 4u)
+      for (int a1 = 0; a1 < MP; ++a1)
+        put(dst.R, (static_cast<size_t>(k) * MP + a) * MP + a1,
+            (a1 < mk && a < mk) ? at(src.R, t.mm_off[k] + a * mk + a1) : (a1 == a ? 1.0 : 0.0));
+    if (mask & 16u) put(dst.r, static_cast<size_t>(k) * MP + a, a < mk ? at(src.r, t.m_off[k] + a) : 0.0);
+    if (mask & 64u)
+      for (int i = 0; i < NP; ++i)
+        put(dst.B, (static_cast<size_t>(k) * MP + a) * NP + i,
+            (i < nc && a < mk) ? at(src.B, t.b_off[k] + a * nc + i) : 0.0);
+  }
+  if (mask & 32u)
+    for (int j = 0; j < NP; ++j)
+      for (int i = 0; i < NP; ++i)
+        put(dst.A, (static_cast<size_t>(k) * NP + j) * NP + i,
+            (i < nc && j < nk) ? at(src.A, t.a_off[k] + j * nc + i) : 0.0);
+}
+
+__global__ void __launch_bounds__(128)
+unpad_chain_kernel(DevTables t, LqrOut src, LqrOut dst, int NP, int MP, int64_t batch,
+                   int64_t ld) {
+  const int64_t b = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int k = blockIdx.y;
+  if (b >= batch) return;
+  const size_t L = static_cast<size_t>(ld);
+  const int nk = t.n[k];
+  for (int i = 0; i < nk; ++i) {
+    dst.x[(static_cast<size_t>(t.n_off[k]) + i) * L + b] = src.x[(static_cast<size_t>(k) * NP + i) * L + b];
+    dst.y[(static_cast<size_t>(t.n_off[k]) + i) * L + b] = src.y[(static_cast<size_t>(k) * NP + i) * L + b];
+  }
+  if (k >= t.E) return;
+  const int mk = t.m[k];
+  for (int a = 0; a < mk; ++a)
+    dst.u[(static_cast<size_t>(t.m_off[k]) + a) * L + b] = src.u[(static_cast<size_t>(k) * MP + a) * L + b];
+}
+
 // stats = {0, 0, #problems with status != 0, #problems}: the per-iteration
 // convergence / failure flags a multi-GPU driver all-reduces.
 __global__ void __launch_bounds__(kThreads)
@@ -931,6 +1004,18 @@ void launch_unpack(const double *src, double *dst, int64_t size, int64_t batch, 
   if (size == 0) return;
   dim3 grid(static_cast<unsigned>((size + 31) / 32), static_cast<unsigned>((ld + 31) / 32));
   unpack_kernel<<<grid, dim3(32, 8), 0, s>>>(src, dst, size, batch, ld);
+}
+
+void launch_pad_chain(const DevTables &t, const LqrIn &src, const LqrIn &dst, int np, int mp,
+                      unsigned mask, int64_t batch, int64_t ld, cudaStream_t s) {
+  dim3 grid(static_cast<unsigned>((batch + 127) / 128), static_cast<unsigned>(t.N));
+  pad_chain_kernel<<<grid, 128, 0, s>>>(t, src, dst, np, mp, mask, batch, ld);
+}
+
+void launch_unpad_chain(const DevTables &t, const LqrOut &src, const LqrOut &dst, int np, int mp,
+                        int64_t batch, int64_t ld, cudaStream_t s) {
+  dim3 grid(static_cast<unsigned>((batch + 127) / 128), static_cast<unsigned>(t.N));
+  unpad_chain_kernel<<<grid, 128, 0, s>>>(t, src, dst, np, mp, batch, ld);
 }
 
 void launch_status_stats(const int *status, double *stats, int64_t batch, cudaStream_t s) {

@@ -92,6 +92,12 @@ void launch_kkt_residual(const DevTables &t, const double *Ksol, const double *b
                          int64_t batch, int64_t ld, cudaStream_t stream);
 
 // Layout conversion: problem-major [batch][size] <-> engine [size][ld].
+// Variable-dimension chain -> uniform (np, mp) chain with decoupled padding, and the
+// outputs back.  mask bit i selects array i of {Q, M, R, q, r, A, B, c, delta}.
+void launch_pad_chain(const DevTables &t, const LqrIn &src, const LqrIn &dst, int np, int mp,
+                      unsigned mask, int64_t batch, int64_t ld, cudaStream_t s);
+void launch_unpad_chain(const DevTables &t, const LqrOut &src, const LqrOut &dst, int np, int mp,
+                        int64_t batch, int64_t ld, cudaStream_t s);
 void launch_pack(const double *src, double *dst, int64_t size, int64_t batch,
                  int64_t ld, cudaStream_t stream);
 void launch_unpack(const double *src, double *dst, int64_t size, int64_t batch,

@@ -35,8 +35,10 @@ class CallbackProvider:
     """Batched Newton-KKT linear solve behind the reference's callback names."""
 
     def __init__(self, dimensions: Dimensions, topology: Topology, batch: int = 1,
-                 device: Optional[int] = None, force_generic: bool = False):
-        self.engine = Engine(dimensions, topology, batch, device, force_generic)
+                 device: Optional[int] = None, force_generic: bool = False,
+                 pad_variable_dims: bool = False):
+        self.engine = Engine(dimensions, topology, batch, device, force_generic,
+                             pad_variable_dims)
         self.batch = int(batch)
         # validate_input(...) == SUCCESS  (helpers.cpp:25-26)
         self.input_is_valid_ = self.engine.create_status == _capi.SIPOC_OK

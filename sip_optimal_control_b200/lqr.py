@@ -154,7 +154,8 @@ class Engine:
     """Owns one ``sipoc_engine`` handle (one structure, one batch, one device)."""
 
     def __init__(self, dimensions: Dimensions, topology: Topology, batch: int,
-                 device: Optional[int] = None, force_generic: bool = False):
+                 device: Optional[int] = None, force_generic: bool = False,
+                 pad_variable_dims: bool = False):
         self.dimensions = dimensions
         self.topology = topology
         self.batch = int(batch)
@@ -169,7 +170,8 @@ class Engine:
             _ip(dimensions.node_g_dims), _ip(dimensions.edge_c_dims),
             _ip(dimensions.edge_g_dims), dimensions.theta_dim, self.batch,
             -1 if device is None else int(device),
-            _capi.SIPOC_FLAG_FORCE_GENERIC if force_generic else 0)
+            (_capi.SIPOC_FLAG_FORCE_GENERIC if force_generic else 0)
+            | (_capi.SIPOC_FLAG_PAD_VARIABLE_DIMS if pad_variable_dims else 0))
         self.create_status = int(lib.sipoc_create(ctypes.byref(s), ctypes.byref(self._handle)))
         if self.create_status != _capi.SIPOC_OK:
             self._handle = ctypes.c_void_p()
@@ -307,8 +309,10 @@ class LQR:
     FactorStatus = FactorStatus
 
     def __init__(self, dimensions: Dimensions, topology: Topology, batch: int = 1,
-                 device: Optional[int] = None, force_generic: bool = False):
-        self.engine = Engine(dimensions, topology, batch, device, force_generic)
+                 device: Optional[int] = None, force_generic: bool = False,
+                 pad_variable_dims: bool = False):
+        self.engine = Engine(dimensions, topology, batch, device, force_generic,
+                             pad_variable_dims)
         self.batch = int(batch)
         self.traversal_status_ = self.compile_topology()
 

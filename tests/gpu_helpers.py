@@ -35,11 +35,13 @@ def assert_lqr_parity(gpu: dict, ref: dict, tol: float = REL_TOL, mask=None):
         assert err.size == 0 or err.max() <= tol, (k, float(err.max()))
 
 
-def gpu_lqr_factor_solve(s: pyoracle.Structure, host: dict, force_generic=False, fused=True):
+def gpu_lqr_factor_solve(s: pyoracle.Structure, host: dict, force_generic=False, fused=True,
+                         pad_variable_dims=False):
     """Device path: pack -> (fused | factor + solve) -> unpack.  Returns dict + LQR."""
     dims, topo = to_structs(s)
     batch = host["q"].shape[0]
-    lqr = LQR(dims, topo, batch, force_generic=force_generic)
+    lqr = LQR(dims, topo, batch, force_generic=force_generic,
+              pad_variable_dims=pad_variable_dims)
     inp = lqr.pack_input(host)
     out = lqr.alloc_output()
     if fused:

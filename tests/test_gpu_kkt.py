@@ -13,10 +13,11 @@ from sip_optimal_control_b200 import CallbackProvider
 pytestmark = pytest.mark.gpu
 
 
-def _gpu_kkt(s, model, w, r1, r2, r3, rhs, force_generic=False):
+def _gpu_kkt(s, model, w, r1, r2, r3, rhs, force_generic=False, pad_variable_dims=False):
     dims, topo = to_structs(s)
     batch = rhs.shape[0]
-    cp = CallbackProvider(dims, topo, batch, force_generic=force_generic)
+    cp = CallbackProvider(dims, topo, batch, force_generic=force_generic,
+                          pad_variable_dims=pad_variable_dims)
     e = cp.engine
     dm = cp.pack_model(model)
     dw, dr1, dr2, dr3, db = (e.pack(a) for a in (w, r1, r2, r3, rhs))
@@ -121,6 +122,13 @@ def test_variable_dimension_kkt_tiling():
     assert (ref["ok"] == 1).all()
     gpu, cp, _ = _gpu_kkt(s, model, w, r1, r2, r3, rhs)
     assert "generic" in cp.engine.kernel_variant
+    assert (gpu["ok"] == 1).all()
+    assert rel_err(gpu["sol"], ref["sol"]).max() < REL_TOL
+    assert gpu["stats"][3] == batch and gpu["stats"][2] == 0
+    # SIPOC_FLAG_PAD_VARIABLE_DIMS: the same chain on the (6, 2) sub-warp kernels through
+    # decoupled padding.
+    gpu, cp, _ = _gpu_kkt(s, model, w, r1, r2, r3, rhs, pad_variable_dims=True)
+    assert cp.engine.kernel_variant == "padded_to_subwarp4_n6_m2", cp.engine.kernel_variant
     assert (gpu["ok"] == 1).all()
     assert rel_err(gpu["sol"], ref["sol"]).max() < REL_TOL
     assert gpu["stats"][3] == batch and gpu["stats"][2] == 0

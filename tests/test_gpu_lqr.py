@@ -273,6 +273,23 @@ def test_variable_dimension_chain_and_tree_batches():
             assert (gpu["status"] == 0).all()
             assert_lqr_parity(gpu, ref, 1e-11)
             assert gpu["residual"].max() < 1e-10
+    # SIPOC_FLAG_PAD_VARIABLE_DIMS: the variable-dim chain on the (6, 2) sub-warp kernels
+    # through decoupled padding; trees stay on the generic kernels.
+    host = pg.variable_tree_batch(chain, 45, seed=11)
+    ref = pyoracle.lqr_factor_solve(chain, host)
+    for fused in (True, False):
+        gpu, lqr = gpu_lqr_factor_solve(chain, host, fused=fused, pad_variable_dims=True)
+        assert lqr.engine.kernel_variant == "padded_to_subwarp4_n6_m2"
+        assert (gpu["status"] == 0).all()
+        assert_lqr_parity(gpu, ref, REL_TOL)
+        assert gpu["residual"].max() < 1e-10
+    bad = {k: v.copy() for k, v in host.items()}
+    bad["delta"][7, 2] = -1.0  # node 1 of problem 7 (node 0 has two states)
+    gpu, lqr = gpu_lqr_factor_solve(chain, bad, pad_variable_dims=True)
+    assert gpu["status"][7] == 1 and (np.delete(gpu["status"], 7) == 0).all()
+    gpu, lqr = gpu_lqr_factor_solve(tree, pg.variable_tree_batch(tree, 5, seed=1),
+                                    pad_variable_dims=True)
+    assert "generic" in lqr.engine.kernel_variant
 
 
 def test_host_buffer_entry_points():
