@@ -69,8 +69,16 @@ __device__ __forceinline__ void cp_async16(double *smem, const double *gmem) {
   const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
 }
+__device__ __forceinline__ void cp_async8(double *smem, const double *gmem) {
+  const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() {
   asm volatile("cp.async.commit_group;\n" ::: "memory");
+}
+template <int PENDING>
+__device__ __forceinline__ void cp_async_wait_group() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(PENDING) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.wait_group 0;\n" ::: "memory");
@@ -1025,6 +1033,146 @@ riccati_backward_thread(LqrIn in, int *status_out, double *store, double *scratc
 }
 
 // ===========================================================================
+// Backward affine sweep against a kept factorization (lqr.cpp:738-796), small batches:
+// one thread per problem, one warp per block, every operand of a stage copied to shared
+// memory with cp.async NBUF - 1 stages ahead of its use ([row][lane]: conflict-free, and
+// a thread only ever reads what it copied itself, so no barrier is involved).  At a few
+// thousand problems there are not enough threads to hide HBM latency by occupancy -- the
+// register-staged kernel below pays three dependent round trips per stage -- so the
+// latency is taken off the chain instead: a stage costs its arithmetic, not its loads.
+// ===========================================================================
+template <int N, int M>
+struct AffineRows {
+  static constexpr int rW = 0, rD = rW + tri(N), rC = rD + N, rB = rC + N, rK = rB + N * M,
+                       rG = rK + N * M, rR = rG + tri(M), rA = rR + M, rQ = rA + N * N,
+                       kRows = rQ + N;
+  // stages in flight: as many 32-lane buffers as fit in ~96 KB (two blocks per SM), 2..4
+  static constexpr int kBuf =
+      (96 * 1024) / (kRows * 32 * 8) >= 4 ? 4 : ((96 * 1024) / (kRows * 32 * 8) >= 3 ? 3 : 2);
+  static constexpr int kBytes = kBuf * kRows * 32 * int(sizeof(double));
+};
+
+template <int N, int M>
+__global__ void __launch_bounds__(32)
+affine_backward_staged(LqrIn in, const double *store, double *scratch, int64_t batch, int64_t ld,
+                       int T) {
+  using Z = FastSizes<N, M>;
+  using R = AffineRows<N, M>;
+  constexpr int NBUF = R::kBuf;
+  extern __shared__ __align__(16) double sm_affine[];
+  const int lane = threadIdx.x;
+  const int64_t b_raw = static_cast<int64_t>(blockIdx.x) * 32 + lane;
+  const bool valid = b_raw < batch;
+  const int64_t b = valid ? b_raw : batch - 1;
+  const size_t L_ = static_cast<size_t>(ld);
+  const double *Wst = store + Z::oW(T) * ld + b;
+  const double *Kst = store + Z::oK(T) * ld + b;
+  const double *Gst = store + Z::oG(T) * ld + b;
+  double *vst = scratch + Z::ov(T) * ld + b;
+  double *kst = scratch + Z::ok(T) * ld + b;
+
+  auto fetch = [&](int k, int buf) {
+    double *dst = sm_affine + static_cast<size_t>(buf) * R::kRows * 32 + lane;
+    const size_t kk = static_cast<size_t>(k);
+#pragma unroll
+    for (int t = 0; t < tri(N); ++t) cp_async8(dst + (R::rW + t) * 32, Wst + ((kk + 1) * tri(N) + t) * L_);
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      cp_async8(dst + (R::rD + i) * 32, in.delta + ((kk + 1) * N + i) * L_ + b);
+      cp_async8(dst + (R::rC + i) * 32, in.c + ((kk + 1) * N + i) * L_ + b);
+      cp_async8(dst + (R::rQ + i) * 32, in.q + (kk * N + i) * L_ + b);
+    }
+#pragma unroll
+    for (int t = 0; t < N * M; ++t) {
+      cp_async8(dst + (R::rB + t) * 32, in.B + (kk * N * M + t) * L_ + b);
+      cp_async8(dst + (R::rK + t) * 32, Kst + (kk * N * M + t) * L_);
+    }
+#pragma unroll
+    for (int t = 0; t < tri(M); ++t) cp_async8(dst + (R::rG + t) * 32, Gst + (kk * tri(M) + t) * L_);
+#pragma unroll
+    for (int a = 0; a < M; ++a) cp_async8(dst + (R::rR + a) * 32, in.r + (kk * M + a) * L_ + b);
+#pragma unroll
+    for (int t = 0; t < N * N; ++t) cp_async8(dst + (R::rA + t) * 32, in.A + (kk * N * N + t) * L_ + b);
+  };
+
+  // stages T-1 .. T-NBUF+1 in flight before the loop; one commit per slot keeps the group
+  // count uniform when the horizon is shorter than the pipeline
+#pragma unroll
+  for (int j = 0; j < NBUF - 1; ++j) {
+    if (T - 1 - j >= 0) fetch(T - 1 - j, j);
+    cp_async_commit();
+  }
+  double v[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    v[i] = ldcs(in.q + (static_cast<size_t>(T) * N + i) * L_ + b);
+    if (valid) stcs(vst + static_cast<int64_t>(T * N + i) * ld, v[i]);
+  }
+  int buf = 0;  // buffer of stage k = (T - 1 - k) % NBUF
+  for (int k = T - 1; k >= 0; --k) {
+    {
+      const int kf = k - (NBUF - 1);  // goes into the buffer stage k + 1 has just left
+      const int bf = buf == 0 ? NBUF - 1 : buf - 1;
+      if (kf >= 0) fetch(kf, bf);
+      cp_async_commit();
+    }
+    cp_async_wait_group<NBUF - 1>();
+    const double *S = sm_affine + static_cast<size_t>(buf) * R::kRows * 32 + lane;
+#define SR(row) S[(row) * 32]
+    double f[N], g[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      f[i] = SR(R::rD + i) * v[i] - SR(R::rC + i);
+      g[i] = v[i];
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+      for (int i = j; i < N; ++i) {
+        const double w = SR(R::rW + pk(i, j, N));
+        g[i] -= w * f[j];
+        if (i != j) g[j] -= w * f[i];
+      }
+    double h[M];
+#pragma unroll
+    for (int a = 0; a < M; ++a) {
+      double acc = SR(R::rR + a);
+#pragma unroll
+      for (int p = 0; p < N; ++p) acc += SR(R::rB + a * N + p) * g[p];
+      h[a] = acc;
+    }
+    double kk[M];
+#pragma unroll
+    for (int a = 0; a < M; ++a) kk[a] = 0.0;
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+#pragma unroll
+      for (int i = j; i < M; ++i) {
+        const double gi = SR(R::rG + pk(i, j, M));
+        kk[i] -= gi * h[j];
+        if (i != j) kk[j] -= gi * h[i];
+      }
+#pragma unroll
+    for (int a = 0; a < M; ++a)
+      if (valid) stcs(kst + static_cast<int64_t>(k * M + a) * ld, kk[a]);
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      double acc = SR(R::rQ + j);
+#pragma unroll
+      for (int p = 0; p < N; ++p) acc += SR(R::rA + j * N + p) * g[p];
+#pragma unroll
+      for (int a = 0; a < M; ++a) acc += SR(R::rK + j * M + a) * h[a];
+      v[j] = acc;
+    }
+#undef SR
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+      if (valid) stcs(vst + static_cast<int64_t>(k * N + i) * ld, v[i]);
+    buf = buf + 1 == NBUF ? 0 : buf + 1;
+  }
+}
+
+// ===========================================================================
 // Backward affine sweep against a kept factorization (lqr.cpp:738-796).
 // ===========================================================================
 template <int N, int M>
@@ -1607,12 +1755,18 @@ struct Plan {
     return 1;
   }
   static int solve(const FastArgs &a, cudaStream_t s) {
-    const int threads = a.batch >= kSmallBatch ? 128 : 32;
-    const unsigned grid = static_cast<unsigned>((a.batch + threads - 1) / threads);
-    {
+    if (a.batch < kSmallBatch) {
+      auto kern = affine_backward_staged<N, M>;
+      constexpr int bytes = AffineRows<N, M>::kBytes;
+      if (bytes > 48 * 1024)
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+      ProfScope ps(a.prof, "affine_backward_staged", s);
+      kern<<<static_cast<unsigned>((a.batch + 31) / 32), 32, bytes, s>>>(
+          a.in, a.store, a.scratch, a.batch, a.ld, a.num_edges);
+    } else {
       ProfScope ps(a.prof, "affine_backward", s);
-      affine_backward<N, M>
-          <<<grid, threads, 0, s>>>(a.in, a.store, a.scratch, a.batch, a.ld, a.num_edges);
+      affine_backward<N, M><<<static_cast<unsigned>((a.batch + 127) / 128), 128, 0, s>>>(
+          a.in, a.store, a.scratch, a.batch, a.ld, a.num_edges);
     }
     forward(a, s);
     return 2;
