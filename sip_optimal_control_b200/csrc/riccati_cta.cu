@@ -282,9 +282,11 @@ __device__ __forceinline__ bool chol8(const double *blk, int ld, double (&L)[36]
 // LLT's failure criterion).  All threads must call it.  `idle(kb, nb)` is called in
 // block step kb by the seven warps that are not on the factorization's critical path: the
 // caller uses it to issue the next stage's cp.async copies.
+// Part 1: the factor.  On return (after a CTA barrier) the lower triangle of A holds L,
+// ddiag the reciprocals of its diagonal.
 template <class Idle>
-__device__ bool cta_spd_inverse(double *A, int ld, int n, double *scratch, double *tbuf,
-                                double *ddiag, Idle idle, int n_live = -1, bool mirror = true) {
+__device__ bool cta_cholesky_lookahead(double *A, int ld, int n, double *ddiag, Idle idle,
+                                       int n_live = -1) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   bool ok = true;
   const int nb = n >> 3;
@@ -293,15 +295,6 @@ __device__ bool cta_spd_inverse(double *A, int ld, int n, double *scratch, doubl
   const int nb_live = n_live < 0 ? nb : (n_live + 7) >> 3;
   const int nl = nb_live << 3;
   for (int i = nl + tid; i < n; i += kThreads) ddiag[i] = 1.0;
-  // Blocks of `scratch` above the block diagonal: zero (read by the triangular inverse).
-  for (int blk = warp; blk < 64; blk += kWarps) {  // (bi, bj) over an 8 x 8 grid of blocks
-    const int bi = blk & 7, bj = blk >> 3;
-    if (bi < bj && bj < nb) {
-      double *z = scratch + ((bj << 3) + (lane >> 3)) * ld + (bi << 3) + (lane & 7);
-      z[0] = 0.0;
-      z[4 * ld] = 0.0;
-    }
-  }
   TICK(10);
   // Blocked Cholesky with look-ahead.  Warp 0 (the panel warp) owns the critical path:
   // factor the diagonal block kb in registers, solve the panel below it (two rows per
@@ -424,8 +417,24 @@ __device__ bool cta_spd_inverse(double *A, int ld, int n, double *scratch, doubl
   }
   __syncthreads();
   TICK(11);
+  return ok;
+}
 
-  // X = L^-1 in `scratch`.
+// Part 2: from the factor in A (lower triangle, reciprocal diagonal in ddiag) to the
+// inverse of the matrix, in A.  All threads.
+__device__ void cta_inverse_from_factor(double *A, int ld, int n, double *scratch, double *tbuf,
+                                        const double *ddiag, bool mirror) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int nb = n >> 3;
+  // X = L^-1 in `scratch`.  Its blocks above the block diagonal are read as zeros.
+  for (int blk = warp; blk < 64; blk += kWarps) {  // (bi, bj) over an 8 x 8 grid of blocks
+    const int bi = blk & 7, bj = blk >> 3;
+    if (bi < bj && bj < nb) {
+      double *z = scratch + ((bj << 3) + (lane >> 3)) * ld + (bi << 3) + (lane & 7);
+      z[0] = 0.0;
+      z[4 * ld] = 0.0;
+    }
+  }
   // Level 0: the 8 x 8 diagonal blocks.  Lane 8 q + j of a warp computes column j of the
   // inverse of the warp's q-th block by forward substitution on e_j (the entries above
   // the diagonal come out as exact zeros), four blocks per warp.
@@ -519,6 +528,71 @@ __device__ bool cta_spd_inverse(double *A, int ld, int n, double *scratch, doubl
     __syncthreads();
   }
   TICK(16);
+}
+
+template <class Idle>
+__device__ bool cta_spd_inverse(double *A, int ld, int n, double *scratch, double *tbuf,
+                                double *ddiag, Idle idle, int n_live = -1, bool mirror = true) {
+  const bool ok = cta_cholesky_lookahead(A, ld, n, ddiag, idle, n_live);
+  cta_inverse_from_factor(A, ld, n, scratch, tbuf, ddiag, mirror);
+  return ok;
+}
+
+// Cholesky of a small matrix (n_live <= 32) by ONE warp, no barrier but __syncwarp: the
+// same 8-wide panels, every tile of the trailing update done by the warp itself.  Used
+// for G, whose factorization then runs beside the Psi products of the other warps.
+__device__ bool warp_cholesky(double *A, int ld, int n, double *ddiag, int n_live) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int nl = ((n_live + 7) >> 3) << 3;
+  bool ok = true;
+  for (int i = nl + lane; i < n; i += 32) ddiag[i] = 1.0;
+  for (int c0 = 0; c0 < nl; c0 += 8) {
+    const int c1 = c0 + 8, rem = nl - c1;  // rem <= 24
+    double L[36], d[8];
+    ok = chol8(A + c0 * ld + c0, ld, L, d) && ok;
+    // lanes < rem: a row of L21; lanes 24..31: the rows of L11 itself (same recurrence)
+    const bool diag_row = lane >= 24;
+    const bool live = diag_row || lane < rem;
+    double *row = A + c0 * ld + (diag_row ? c0 + lane - 24 : c1 + lane);
+    double x[8];
+    if (live) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = row[j * ld];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      x[j] *= d[j];
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        if (c > j) x[c] -= x[j] * L[pk(c, j, 8)];
+    }
+    __syncwarp();  // every lane has read the diagonal block
+    if (live) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) row[j * ld] = (!diag_row || j <= lane - 24) ? x[j] : 0.0;
+    }
+    if (lane == 23) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ddiag[c0 + j] = d[j];
+    }
+    __syncwarp();
+    // trailing update A(c1.., c1..) -= L21 L21' on the lower 8 x 8 tiles
+    for (int ti = 0; ti < (rem >> 3); ++ti)
+      for (int tj = 0; tj <= ti; ++tj) {
+        const int r0 = c1 + (ti << 3), q0 = c1 + (tj << 3);
+        double *cblk = A + (q0 + 2 * t) * ld + r0 + g;
+        double acc[2] = {cblk[0], cblk[ld]};
+#pragma unroll
+        for (int s2 = 0; s2 < 2; ++s2) {
+          const double a = -A[(c0 + 4 * s2 + t) * ld + r0 + g];
+          const double bb = A[(c0 + 4 * s2 + t) * ld + q0 + g];
+          dmma(acc, a, bb);
+        }
+        cblk[0] = acc[0];
+        cblk[ld] = acc[1];
+      }
+    __syncwarp();
+  }
   return ok;
 }
 
@@ -778,27 +852,53 @@ riccati_backward_cta(LqrIn pm, int *status_out, double *store, double *scratch, 
       }
     }
     __syncthreads();
-    // Psi_ux += B' S_x,  Psi_uu += B' S_u (rows = u, K = N),  Psi_xx += A' S_x (lower
-    // blocks): one deal of all their blocks over the warps.
-    {
-      int slot = cta_gemm<true, false, true, false>(Pux, LDM, Zb + N * LDN, LDN, Sb, LDN, M, N, N,
-                                                    1.0, 0);
-      slot = cta_gemm<true, false, true, true>(Puu, LDM, Zb + N * LDN, LDN, Sb + N * LDN, LDN, M,
-                                               M, N, 1.0, slot);
-      cta_gemm<true, false, true, true>(Wp, LDN, Zb, LDN, Sb, LDN, N, N, N, 1.0, slot);
+    // Psi_uu += B' S_u first (three blocks, warps 0-2); as soon as it is complete warp 0
+    // factors G = Psi_uu on its own (warp_cholesky) while warps 1-7 form Psi_ux += B' S_x
+    // and Psi_xx += A' S_x (lower blocks): the 24 pivots of G run beside the two big
+    // products instead of after them.
+    constexpr int kTmU = (M + 15) / 16, kTnX = N / 16;
+    constexpr int kPuuBlocks = kTmU * (kTmU + 1) / 2, kPuxBlocks = kTmU * kTnX;
+    constexpr int kPsiBlocks = kPuxBlocks + kTnX * (kTnX + 1) / 2;
+    static_assert(kPuuBlocks <= 3, "Psi_uu is dealt to warps 0-2");
+    const int warp = tid >> 5;
+    bool g_chol_ok = true;
+    if (warp < 3) {
+      if (warp < kPuuBlocks)
+        gemm_block<true, false, true>(Puu, LDM, Zb + N * LDN, LDN, Sb + N * LDN, LDN, M, M, N, 1.0,
+                                      kTriRow[warp] << 4, kTriCol[warp] << 4);
+      asm volatile("bar.sync 8, 96;" ::: "memory");
     }
-    __syncthreads();
+    if (warp == 0) {
+      g_chol_ok = warp_cholesky(Puu, LDM, MP, Dd, M);
+    } else {
+      // Blocks in service order: warps 3-7 take the first five (warps 1-2 are still on
+      // Psi_uu), then 3-7, 1, 2 in turn.
+      for (int blk = 0; blk < kPsiBlocks; ++blk) {
+        const int r = blk < 5 ? blk : (blk - 5) % 7;
+        const int owner = r < 5 ? 3 + r : r - 4;
+        if (owner != warp) continue;
+        if (blk < kPuxBlocks) {
+          gemm_block<true, false, true>(Pux, LDM, Zb + N * LDN, LDN, Sb, LDN, M, N, N, 1.0,
+                                        (blk / kTnX) << 4, (blk % kTnX) << 4);
+        } else {
+          const int s2 = blk - kPuxBlocks;
+          gemm_block<true, false, true>(Wp, LDN, Zb, LDN, Sb, LDN, N, N, N, 1.0, kTriRow[s2] << 4,
+                                        kTriCol[s2] << 4);
+        }
+      }
+      // Z is consumed once all seven warps are through: A, B of the next stage fly during
+      // the rest of this one.
+      asm volatile("bar.sync 9, %0;" ::"r"(kThreads - 32) : "memory");
+      if (k > 0) {
+        stage_edge_z(k - 1, 32, kThreads - 32, 0, 1);
+        cp_async_commit();
+      }
+    }
+    const bool g_ok = __syncthreads_and(g_chol_ok);
     TICK(5);
-
-    // G^-1 (full, in Puu).  Z is consumed: A, B of the next stage are issued by the idle
-    // warps of the G factorization's block steps and fly during the rest of this stage.
-    const bool g_ok = cta_spd_inverse(Puu, LDM, MP, Gs, Sb, Dd, [&](int kb, int nb) {
-      if (k == 0) return;
-      stage_edge_z(k - 1, kPanelThreads, kThreads - kPanelThreads, kb, nb);
-      cp_async_commit();
-    }, M);
-    if (!__syncthreads_and(g_ok) && status == SIPOC_FACTOR_SUCCESS)
-      status = SIPOC_FACTOR_G_FACTORIZATION_FAILURE;
+    // G^-1 (full, in Puu) from its factor.
+    cta_inverse_from_factor(Puu, LDM, MP, Gs, Sb, Dd, true);
+    if (!g_ok && status == SIPOC_FACTOR_SUCCESS) status = SIPOC_FACTOR_G_FACTORIZATION_FAILURE;
     TICK(6);
     // K = -G^-1 Psi_ux
     // (rows and the k range stop at M: the padding block of G^-1 is the identity and the
