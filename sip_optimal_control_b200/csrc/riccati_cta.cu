@@ -422,10 +422,15 @@ __device__ bool cta_cholesky_lookahead(double *A, int ld, int n, double *ddiag, 
 
 // Part 2: from the factor in A (lower triangle, reciprocal diagonal in ddiag) to the
 // inverse of the matrix, in A.  All threads.
-__device__ void cta_inverse_from_factor(double *A, int ld, int n, double *scratch, double *tbuf,
+template <int NN>
+__device__ void cta_inverse_from_factor(double *A, int ld, double *scratch, double *tbuf,
                                         const double *ddiag, bool mirror) {
+  // (the size is a template argument so that the level structure below unrolls into
+  // straight-line code: at eight warps per SM every index instruction is exposed latency)
+  constexpr int n = NN;
+  static_assert(NN % 8 == 0 && NN <= 64, "n is a multiple of 8, at most 64");
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int nb = n >> 3;
+  constexpr int nb = n >> 3;
   // X = L^-1 in `scratch`.  Its blocks above the block diagonal are read as zeros.
   for (int blk = warp; blk < 64; blk += kWarps) {  // (bi, bj) over an 8 x 8 grid of blocks
     const int bi = blk & 7, bj = blk >> 3;
@@ -462,13 +467,16 @@ __device__ void cta_inverse_from_factor(double *A, int ld, int n, double *scratc
   // 2 log2(n / 8) short products instead of n / 8 block rows.  The blocks of X above
   // the diagonal were zeroed on entry, so every tile runs the full k range (equal trip
   // counts let a warp interleave its tiles).
+#pragma unroll
   for (int sz = 8; sz < n; sz <<= 1) {
-    const int tc = sz >> 3, lt = 31 - __clz(tc);  // tile columns per pair (a power of two)
+    const int tc = sz >> 3, lt = sz == 8 ? 0 : (sz == 16 ? 1 : 2);  // tile columns per pair
     const int pairs = (n + 2 * sz - 1) >> (lt + 4);
     const int total = pairs << (2 * lt);
+#pragma unroll
     for (int pass = 0; pass < 2; ++pass) {
       // Two units per warp at a time, two accumulators per unit (even / odd k steps):
       // four independent DMMA chains of sz / 8 links.
+#pragma unroll
       for (int u0 = warp; u0 < total; u0 += 2 * kWarps) {
         const double *pa[2], *pb[2];
         double *dst[2];
@@ -492,6 +500,7 @@ __device__ void cta_inverse_from_factor(double *A, int ld, int n, double *scratc
           }
         }
         double acc[2][2][2] = {};
+#pragma unroll
         for (int k0 = 0; k0 < sz; k0 += 8) {
 #pragma unroll
           for (int z = 0; z < 2; ++z) {
@@ -530,11 +539,11 @@ __device__ void cta_inverse_from_factor(double *A, int ld, int n, double *scratc
   TICK(16);
 }
 
-template <class Idle>
-__device__ bool cta_spd_inverse(double *A, int ld, int n, double *scratch, double *tbuf,
-                                double *ddiag, Idle idle, int n_live = -1, bool mirror = true) {
-  const bool ok = cta_cholesky_lookahead(A, ld, n, ddiag, idle, n_live);
-  cta_inverse_from_factor(A, ld, n, scratch, tbuf, ddiag, mirror);
+template <int NN, class Idle>
+__device__ bool cta_spd_inverse(double *A, int ld, double *scratch, double *tbuf, double *ddiag,
+                                Idle idle, int n_live = -1, bool mirror = true) {
+  const bool ok = cta_cholesky_lookahead(A, ld, NN, ddiag, idle, n_live);
+  cta_inverse_from_factor<NN>(A, ld, scratch, tbuf, ddiag, mirror);
   return ok;
 }
 
@@ -755,7 +764,7 @@ riccati_backward_cta(LqrIn pm, int *status_out, double *store, double *scratch, 
     TICK(8);
     // M, R, q, r, c, delta of the next stage (and, after the terminal node, its A and B)
     // are issued by the idle warps of the F factorization's block steps.
-    const bool f_ok = cta_spd_inverse(Wp, LDN, N, Sb, Sb + N * LDN, Dd, [&](int kb, int nb) {
+    const bool f_ok = cta_spd_inverse<N>(Wp, LDN, Sb, Sb + N * LDN, Dd, [&](int kb, int nb) {
       if (k == 0) return;
       if (kb == 0) stage_edge_rest(k - 1, kPanelThreads, kThreads - kPanelThreads);
       if (kb == 1) stage_q_packed(k - 1, kPanelThreads, kThreads - kPanelThreads);
@@ -897,7 +906,7 @@ riccati_backward_cta(LqrIn pm, int *status_out, double *store, double *scratch, 
     const bool g_ok = __syncthreads_and(g_chol_ok);
     TICK(5);
     // G^-1 (full, in Puu) from its factor.
-    cta_inverse_from_factor(Puu, LDM, MP, Gs, Sb, Dd, true);
+    cta_inverse_from_factor<MP>(Puu, LDM, Gs, Sb, Dd, true);
     if (!g_ok && status == SIPOC_FACTOR_SUCCESS) status = SIPOC_FACTOR_G_FACTORIZATION_FAILURE;
     TICK(6);
     // K = -G^-1 Psi_ux
