@@ -532,6 +532,7 @@ def run_kkt(args):
     dev = torch.device("cuda", 0)
     sampler = ClockSampler(0)
     cp = CallbackProvider(dims, Topology.chain(T), batch, device=0,
+                          force_generic=getattr(args, "force_generic", False),
                           pad_variable_dims=getattr(args, "pad_variable_dims", False))
     eng = cp.engine
     # The shape-specialised LQR kernels reorder the arithmetic; they stay within 1e-9 of the

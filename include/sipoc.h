@@ -119,12 +119,12 @@ typedef struct sipoc_structure {
 } sipoc_structure;
 
 #define SIPOC_FLAG_FORCE_GENERIC 1 /* never pick a shape-specialised kernel */
-/* Chains whose dims vary from stage to stage: run them on the shape-specialised kernels
- * of the smallest uniform shape that holds every stage, through decoupled padding,
- * instead of the generic kernels.  Off by default: the generic kernels reproduce the
- * reference's operation order, which is what keeps 1e-9 parity on ill-conditioned
- * regularization (r2 up to 1e9); the padded path is a correct FP64 solve in another
- * order. */
+/* Chains whose dims vary from stage to stage run, padded to a uniform shape with
+ * decoupled states / controls, on reference-order register kernels (same operations in
+ * the same order as the generic kernels, hence the same parity at any regularization).
+ * This flag picks the reordered shape-specialised kernels for them instead: faster
+ * still, but a correct FP64 solve in another order, which drifts from the reference on
+ * ill-conditioned regularization (r2 up to 1e9). */
 #define SIPOC_FLAG_PAD_VARIABLE_DIMS 2
 
 sipoc_error sipoc_create(const sipoc_structure *structure, sipoc_engine **out);

@@ -688,6 +688,15 @@ sipoc_error sipoc_create(const sipoc_structure *s, sipoc_engine **out) {
       h.is_uniform && h.E >= 1)
     e->fast = select_cta_plan(h.n[0], h.m[0]);
   if (e->fast == nullptr && !(e->flags & SIPOC_FLAG_FORCE_GENERIC) &&
+      !(e->flags & SIPOC_FLAG_PAD_VARIABLE_DIMS) && h.is_chain && h.E >= 1 &&
+      (e->fast = select_strict_plan(h.max_n, h.max_m)) != nullptr) {
+    // Small chains without a plan of their own (dims that change from stage to stage, or a
+    // uniform shape that is not instantiated): the reference-order register kernels on the
+    // chain padded to the smallest shape that holds every stage -- the generic kernels'
+    // operations in the same order on the real entries (riccati_strict.cu).
+    e->padded = true;
+  }
+  if (e->fast == nullptr && !(e->flags & SIPOC_FLAG_FORCE_GENERIC) &&
       (e->flags & SIPOC_FLAG_PAD_VARIABLE_DIMS) && h.is_chain && !h.is_uniform && h.E >= 1) {
     // smallest instantiated register / sub-warp shape that holds every stage
     const int shapes[][2] = {{4, 1}, {6, 2}, {8, 3}, {12, 4}};

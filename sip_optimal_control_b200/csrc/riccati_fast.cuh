@@ -66,5 +66,8 @@ const FastPlan *select_fast_plan(int n, int m);
 // CTA-per-problem DMMA kernels for large dimensions (riccati_cta.cu); nullptr when
 // (n, m) is not instantiated.
 const FastPlan *select_cta_plan(int n, int m);
+// Reference-order register kernels for small chains (riccati_strict.cu): the smallest
+// instantiated shape that holds (n, m), for chains padded to it; nullptr when none does.
+const FastPlan *select_strict_plan(int n, int m);
 
 }  // namespace sipoc

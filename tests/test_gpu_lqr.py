@@ -269,10 +269,18 @@ def test_variable_dimension_chain_and_tree_batches():
         assert (ref["status"] == 0).all()
         for fused in (True, False):
             gpu, lqr = gpu_lqr_factor_solve(s, host, fused=fused)
-            assert "generic" in lqr.engine.kernel_variant
+            # chains with per-stage dims: reference-order register kernels on the padded
+            # chain; trees: the generic kernels
+            want = "padded_to_strict_thread_n3_m2" if s is chain else "generic_thread_per_problem"
+            assert lqr.engine.kernel_variant == want, lqr.engine.kernel_variant
             assert (gpu["status"] == 0).all()
             assert_lqr_parity(gpu, ref, 1e-11)
             assert gpu["residual"].max() < 1e-10
+            if s is chain:
+                # ... which perform, on the real entries, the generic kernels' operations in
+                # the same order (only the compiler's FMA contraction may differ)
+                gen, _ = gpu_lqr_factor_solve(s, host, fused=fused, force_generic=True)
+                assert_lqr_parity(gpu, gen, 1e-13)
     # SIPOC_FLAG_PAD_VARIABLE_DIMS: the variable-dim chain on the (6, 2) sub-warp kernels
     # through decoupled padding; trees stay on the generic kernels.
     host = pg.variable_tree_batch(chain, 45, seed=11)
