@@ -12,6 +12,12 @@ python bench.py 2> $O/bench_quadrotor_n1.err | tail -1 > $O/bench_quadrotor_n1.j
 for w in cartpole humanoid newton_kkt newton_kkt_uniform; do
   python bench.py --workload $w 2> $O/bench_$w.err | tail -1 > $O/bench_$w.json
 done
+python bench.py --workload humanoid --input-layout problem_major --no-cpu-baseline 2> /dev/null | tail -1 > $O/bench_humanoid_problem_major.json
+python bench.py --workload newton_kkt --force-generic 2> /dev/null | tail -1 > $O/bench_newton_kkt_generic.json
+python bench.py --workload newton_kkt --pad-variable-dims 2> /dev/null | tail -1 > $O/bench_newton_kkt_padded.json
+for w in long_horizon_quadrotor long_horizon_humanoid; do
+  python bench.py --workload $w --steps 5 --no-e2e --no-cpu-baseline 2> /dev/null | tail -1 > $O/bench_$w.json
+done
 cut -c1-260 $O/bench_*.json
 # ncu: launch list of the humanoid step, then full captures of its two kernels (2 waves).
 H="python bench.py --workload humanoid --batch 592 --steps 2 --warmup 1 --no-e2e --no-cpu-baseline"
