@@ -1288,6 +1288,153 @@ affine_backward(LqrIn in, const double *store, double *scratch, int64_t batch, i
 }
 
 // ===========================================================================
+// Root solve + forward rollout + costates (lqr.cpp:798-870), small batches: the same
+// arithmetic as rollout_forward below with the operands of a stage copied to shared
+// memory by cp.async kBuf - 1 stages ahead ([row][lane], one warp per block, a thread
+// reads only what it copied).  At a few thousand problems -- or 64 with a horizon of
+// 4 096 -- occupancy cannot hide the HBM latency of a stage's loads; the pipeline does.
+// ===========================================================================
+template <int N, int M>
+struct ForwardRows {
+  static constexpr int rA = 0, rB = rA + N * N, rK = rB + N * M, rW = rK + N * M, rv = rW + tri(N),
+                       rd = rv + N, rc = rd + N, rk = rc + N, kRows = rk + M;
+  static constexpr int kFit = (184 * 1024) / (kRows * 32 * 8);
+  static constexpr int kBuf = kFit >= 4 ? 4 : (kFit >= 3 ? 3 : 2);
+  static constexpr int kBytes = kBuf * kRows * 32 * int(sizeof(double));
+  static_assert(kFit >= 2, "two stages of operands must fit shared memory");
+};
+
+template <int N, int M>
+__global__ void __launch_bounds__(32)
+rollout_forward_staged(LqrIn in, LqrOut out, const double *store, const double *scratch,
+                       int64_t batch, int64_t ld, int T) {
+  using Z = FastSizes<N, M>;
+  using R = ForwardRows<N, M>;
+  constexpr int NBUF = R::kBuf;
+  extern __shared__ __align__(16) double sm_forward[];
+  const int lane = threadIdx.x;
+  const int64_t b_raw = static_cast<int64_t>(blockIdx.x) * 32 + lane;
+  const bool valid = b_raw < batch;
+  const int64_t b = valid ? b_raw : batch - 1;
+  const size_t L_ = static_cast<size_t>(ld);
+  const double *Wst = store + Z::oW(T) * ld + b;
+  const double *Kst = store + Z::oK(T) * ld + b;
+  const double *vst = scratch + Z::ov(T) * ld + b;
+  const double *kst = scratch + Z::ok(T) * ld + b;
+  double *xo = out.x + b, *uo = out.u + b, *yo = out.y + b;
+
+  auto fetch = [&](int k, int buf) {  // operands of edge k / node k + 1
+    double *dst = sm_forward + static_cast<size_t>(buf) * R::kRows * 32 + lane;
+    const size_t kk = static_cast<size_t>(k);
+#pragma unroll
+    for (int t = 0; t < N * N; ++t) cp_async8(dst + (R::rA + t) * 32, in.A + (kk * N * N + t) * L_ + b);
+#pragma unroll
+    for (int t = 0; t < N * M; ++t) {
+      cp_async8(dst + (R::rB + t) * 32, in.B + (kk * N * M + t) * L_ + b);
+      cp_async8(dst + (R::rK + t) * 32, Kst + (kk * N * M + t) * L_);
+    }
+#pragma unroll
+    for (int t = 0; t < tri(N); ++t) cp_async8(dst + (R::rW + t) * 32, Wst + ((kk + 1) * tri(N) + t) * L_);
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      cp_async8(dst + (R::rv + i) * 32, vst + ((kk + 1) * N + i) * L_);
+      cp_async8(dst + (R::rd + i) * 32, in.delta + ((kk + 1) * N + i) * L_ + b);
+      cp_async8(dst + (R::rc + i) * 32, in.c + ((kk + 1) * N + i) * L_ + b);
+    }
+#pragma unroll
+    for (int a = 0; a < M; ++a) cp_async8(dst + (R::rk + a) * 32, kst + (kk * M + a) * L_);
+  };
+#pragma unroll
+  for (int j = 0; j < NBUF - 1; ++j) {
+    if (j < T) fetch(j, j);
+    cp_async_commit();
+  }
+
+  double x[N];
+  {  // root: x_0 = -(I - D W)(delta o v - c), y_0 = v - W (delta o v - c)
+    double f[N], wf[N], vv[N], dd[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      vv[i] = ldcs(vst + static_cast<size_t>(i) * L_);
+      dd[i] = ldcs(in.delta + static_cast<size_t>(i) * L_ + b);
+      f[i] = dd[i] * vv[i] - ldcs(in.c + static_cast<size_t>(i) * L_ + b);
+      wf[i] = 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+      for (int i = j; i < N; ++i) {
+        const double w = ldcs(Wst + static_cast<size_t>(pk(i, j, N)) * L_);
+        wf[i] += w * f[j];
+        if (i != j) wf[j] += w * f[i];
+      }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      x[i] = dd[i] * wf[i] - f[i];
+      if (valid) {
+        stcs(xo + static_cast<size_t>(i) * L_, x[i]);
+        stcs(yo + static_cast<size_t>(i) * L_, vv[i] - wf[i]);
+      }
+    }
+  }
+  int buf = 0;
+  for (int k = 0; k < T; ++k) {
+    {
+      const int kf = k + (NBUF - 1);  // goes into the buffer stage k - 1 has just left
+      if (kf < T) fetch(kf, buf == 0 ? NBUF - 1 : buf - 1);
+      cp_async_commit();
+    }
+    cp_async_wait_group<NBUF - 1>();
+    const double *S = sm_forward + static_cast<size_t>(buf) * R::kRows * 32 + lane;
+#define SR(row) S[(row) * 32]
+    double u[M];
+#pragma unroll
+    for (int a = 0; a < M; ++a) u[a] = SR(R::rk + a);
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+      for (int a = 0; a < M; ++a) u[a] += SR(R::rK + j * M + a) * x[j];
+#pragma unroll
+    for (int a = 0; a < M; ++a)
+      if (valid) stcs(uo + static_cast<size_t>(k * M + a) * L_, u[a]);
+    double f[N], vv[N], dd[N], wf[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      vv[i] = SR(R::rv + i);
+      dd[i] = SR(R::rd + i);
+      f[i] = SR(R::rc + i) - dd[i] * vv[i];
+      wf[i] = 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+      for (int i = 0; i < N; ++i) f[i] += SR(R::rA + j * N + i) * x[j];
+#pragma unroll
+    for (int a = 0; a < M; ++a)
+#pragma unroll
+      for (int i = 0; i < N; ++i) f[i] += SR(R::rB + a * N + i) * u[a];
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+      for (int i = j; i < N; ++i) {
+        const double w = SR(R::rW + pk(i, j, N));
+        wf[i] += w * f[j];
+        if (i != j) wf[j] += w * f[i];
+      }
+#undef SR
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      x[i] = f[i] - dd[i] * wf[i];
+      if (valid) {
+        stcs(xo + static_cast<size_t>((k + 1) * N + i) * L_, x[i]);
+        stcs(yo + static_cast<size_t>((k + 1) * N + i) * L_, vv[i] + wf[i]);
+      }
+    }
+    buf = buf + 1 == NBUF ? 0 : buf + 1;
+  }
+}
+
+// ===========================================================================
 // Root solve + forward rollout + costates (lqr.cpp:798-870).
 // ===========================================================================
 template <int N, int M, int THREADS, int MINB>
@@ -1747,8 +1894,17 @@ struct Plan {
     // No register cap: the compiler then hoists a whole stage's loads (254 registers),
     // which is what keeps HBM busy (capped variants were slower).  Small batches use
     // one-warp blocks so that every SM gets work (8 192 problems are 64 blocks of 128).
-    if (a.batch >= kSmallBatch) launch_forward<128, 1>(a, s);
-    else launch_forward<32, 1>(a, s);
+    if (a.batch >= kSmallBatch) {
+      launch_forward<128, 1>(a, s);
+    } else {
+      auto kern = rollout_forward_staged<N, M>;
+      constexpr int bytes = ForwardRows<N, M>::kBytes;
+      if (bytes > 48 * 1024)
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+      ProfScope ps(a.prof, "rollout_forward_staged", s);
+      kern<<<static_cast<unsigned>((a.batch + 31) / 32), 32, bytes, s>>>(
+          a.in, a.out, a.store, a.scratch, a.batch, a.ld, a.num_edges);
+    }
   }
   static int factor(const FastArgs &a, cudaStream_t s) {
     backward<false>(a, s);
