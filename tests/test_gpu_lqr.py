@@ -227,7 +227,7 @@ def test_factor_once_solve_many(n, m, T):
         assert_lqr_parity(gpu, ref, REL_TOL)
 
 
-@pytest.mark.parametrize("n,m,T", [(12, 4, 9), (5, 2, 7), (16, 4, 6), (32, 8, 5), (64, 24, 3)])
+@pytest.mark.parametrize("n,m,T", [(12, 4, 9), (5, 2, 7), (3, 2, 7), (16, 4, 6), (32, 8, 5), (64, 24, 3)])
 def test_problem_major_entry_points(n, m, T):
     # sipoc_lqr_*_pm: the same three calls with problem-major device inputs -- native for
     # the CTA-per-problem plans, packed first for every other path.
