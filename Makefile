@@ -45,7 +45,13 @@ $(LIBDIR)/libsipoc.so: $(OBJS)
 oracle:
 	$(MAKE) -C oracle liboracle.so
 
+# FP64 issue / latency microbenchmark (DFMA, DMMA.8x8x4, rsqrt) behind profiles/r01/microbench_fp64.txt
+microbench: build/microbench_fp64
+build/microbench_fp64: tools/microbench_fp64.cu
+	@mkdir -p build
+	$(NVCC) -O3 $(ARCH) -ccbin $(HOSTCXX) -o $@ $<
+
 clean:
 	rm -rf build $(LIBDIR)/libsipoc.so $(LIBDIR)/libsipoc_host.so oracle/liboracle.so
 
-.PHONY: all oracle clean
+.PHONY: all oracle clean microbench
