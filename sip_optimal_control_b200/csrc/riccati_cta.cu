@@ -605,6 +605,38 @@ __device__ bool warp_cholesky(double *A, int ld, int n, double *ddiag, int n_liv
   return ok;
 }
 
+// Even deal of the lower triangle of an N x N matrix over the CTA: columns j and N - 1 - j
+// together hold N + 1 entries, so the N / 2 column pairs are equal work; kThreads / (N / 2)
+// threads share a pair.  `load(i, j)` is called for all of a thread's entries first, then
+// `store(i, j, value)` -- the loads of one pass are in flight together.
+template <int N, class Load, class Store>
+__device__ __forceinline__ void for_lower_triangle(Load load, Store store) {
+  constexpr int kPairs = N / 2, kPer = kThreads / kPairs, kMax = (N + 1 + kPer - 1) / kPer;
+  static_assert(N % 2 == 0 && kThreads % kPairs == 0, "column pairs divide the CTA");
+  const int p = threadIdx.x / kPer, sub = threadIdx.x % kPer;
+  double val[kMax];
+#pragma unroll
+  for (int u = 0; u < kMax; ++u) {
+    const int idx = sub + u * kPer;
+    if (idx <= N) {
+      const bool first = idx < N - p;
+      const int j = first ? p : N - 1 - p;
+      const int i = first ? p + idx : idx - 1;  // second column: N - 1 - p + (idx - (N - p))
+      val[u] = load(i, j);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < kMax; ++u) {
+    const int idx = sub + u * kPer;
+    if (idx <= N) {
+      const bool first = idx < N - p;
+      const int j = first ? p : N - 1 - p;
+      const int i = first ? p + idx : idx - 1;
+      store(i, j, val[u]);
+    }
+  }
+}
+
 // Shared-memory map (doubles).
 template <int N, int M>
 struct CtaSmem {
@@ -746,20 +778,11 @@ riccati_backward_cta(LqrIn pm, int *status_out, double *store, double *scratch, 
     }
     const bool any_bad = __syncthreads_or(!d_ok);
     if (any_bad && status == SIPOC_FACTOR_SUCCESS) status = SIPOC_FACTOR_INVALID_DELTA;
-    // F = I + D^1/2 V D^1/2 on the lower triangle, four entries per thread in flight.
-    for (int e0 = tid; e0 < N * N; e0 += 4 * kThreads) {
-      double val[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int e = e0 + u * kThreads, i = e % N, j = e / N;
-        if (e < N * N && i >= j) val[u] = Wp[j * LDN + i];
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int e = e0 + u * kThreads, i = e % N, j = e / N;
-        if (e < N * N && i >= j) Wp[j * LDN + i] = sd_s[i] * val[u] * sd_s[j] + (i == j ? 1.0 : 0.0);
-      }
-    }
+    // F = I + D^1/2 V D^1/2 on the lower triangle.
+    for_lower_triangle<N>([&](int i, int j) { return Wp[j * LDN + i]; },
+                          [&](int i, int j, double v) {
+                            Wp[j * LDN + i] = sd_s[i] * v * sd_s[j] + (i == j ? 1.0 : 0.0);
+                          });
     __syncthreads();
     TICK(8);
     // M, R, q, r, c, delta of the next stage (and, after the terminal node, its A and B)
@@ -774,24 +797,13 @@ riccati_backward_cta(LqrIn pm, int *status_out, double *store, double *scratch, 
     if (!__syncthreads_and(f_ok) && status == SIPOC_FACTOR_SUCCESS)
       status = SIPOC_FACTOR_F_FACTORIZATION_FAILURE;
     // W = D^-1/2 (I - F^-1) D^-1/2: both triangles in shared memory, packed lower to the store.
-    for (int e0 = tid; e0 < N * N; e0 += 4 * kThreads) {
-      double val[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int e = e0 + u * kThreads, i = e % N, j = e / N;
-        if (e < N * N && i >= j) val[u] = Wp[j * LDN + i];
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int e = e0 + u * kThreads, i = e % N, j = e / N;
-        if (e < N * N && i >= j) {
-          const double w = sdi_s[i] * ((i == j ? 1.0 : 0.0) - val[u]) * sdi_s[j];
-          Wp[j * LDN + i] = w;
-          Wp[i * LDN + j] = w;
-          Wst[static_cast<size_t>(k) * tri(N) + pk(i, j, N)] = w;
-        }
-      }
-    }
+    for_lower_triangle<N>([&](int i, int j) { return Wp[j * LDN + i]; },
+                          [&](int i, int j, double v) {
+                            const double w = sdi_s[i] * ((i == j ? 1.0 : 0.0) - v) * sdi_s[j];
+                            Wp[j * LDN + i] = w;
+                            Wp[i * LDN + j] = w;
+                            Wst[static_cast<size_t>(k) * tri(N) + pk(i, j, N)] = w;
+                          });
     __syncthreads();
     TICK(9);
   };
@@ -847,19 +859,8 @@ riccati_backward_cta(LqrIn pm, int *status_out, double *store, double *scratch, 
     __syncthreads();
     TICK(3);
     // Psi_xx base: Q_k lower (prefetched, packed, in the K buffer) into the now free W' buffer.
-    for (int e0 = tid; e0 < N * N; e0 += 4 * kThreads) {
-      double val[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int e = e0 + u * kThreads, i = e % N, j = e / N;
-        if (e < N * N && i >= j) val[u] = Kb[pk(i, j, N)];
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int e = e0 + u * kThreads, i = e % N, j = e / N;
-        if (e < N * N && i >= j) Wp[j * LDN + i] = val[u];
-      }
-    }
+    for_lower_triangle<N>([&](int i, int j) { return Kb[pk(i, j, N)]; },
+                          [&](int i, int j, double v) { Wp[j * LDN + i] = v; });
     __syncthreads();
     // Psi_uu += B' S_u first (three blocks, warps 0-2); as soon as it is complete warp 0
     // factors G = Psi_uu on its own (warp_cholesky) while warps 1-7 form Psi_ux += B' S_x
