@@ -112,7 +112,8 @@ def test_single_stage_failure_fixtures():  # lqr_test.cpp:213-227 verbatim (n=m=
 
 
 
-@pytest.mark.parametrize("n,m,T", [(4, 1, 9), (12, 4, 6), (6, 2, 5), (16, 4, 4), (64, 24, 2)])
+@pytest.mark.parametrize("n,m,T", [(4, 1, 9), (12, 4, 6), (6, 2, 5), (16, 4, 4), (64, 24, 2),
+                                   (3, 2, 5), (4, 2, 6), (2, 2, 4), (4, 3, 5)])
 @pytest.mark.parametrize("fused", [True, False])
 def test_status_codes_on_specialised_kernels(n, m, T, fused):
     """Failure injection on the shape-specialised paths (thread / sub-warp / CTA):
