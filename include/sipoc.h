@@ -24,6 +24,9 @@
  *                                     (benchmarks/lqr_benchmark.cpp:653-663)
  *   sipoc_lqr_residual                compute_residual_norm
  *                                     (tests/lqr_test.cpp:152-186, :371-409)
+ *   sipoc_kkt_apply_block             CallbackProvider::add_Hx_to_y / add_Cx_to_y /
+ *                                     add_CTx_to_y / add_Gx_to_y / add_GTx_to_y
+ *                                     (helpers.hpp:17-21, helpers.cpp:979-1368)
  *   sipoc_kkt_factor                  CallbackProvider::factor, theta_dim == 0
  *                                     (helpers.hpp:11-12, helpers.cpp:242-370)
  *   sipoc_kkt_solve                   CallbackProvider::solve, theta_dim == 0
@@ -267,6 +270,21 @@ sipoc_error sipoc_kkt_apply(sipoc_engine *engine, const sipoc_kkt_model *model,
                             const double *w, const double *r1, const double *r2,
                             const double *r3, const double *x, double *y,
                             void *stream);
+/* One block of that operator on its own (add_Hx_to_y, add_Cx_to_y, add_CTx_to_y,
+ * add_Gx_to_y, add_GTx_to_y; helpers.hpp:17-21, helpers.cpp:979-1368), without the
+ * regularization terms:  y += B x  with
+ *   H : x, y of length x_dim      C : x x_dim, y y_dim      CT: x y_dim, y x_dim
+ *   G : x x_dim, y z_dim          GT: x z_dim, y x_dim
+ * (C holds the dynamics rows, node and edge equalities; G the inequalities). */
+typedef enum sipoc_kkt_block {
+  SIPOC_KKT_BLOCK_H = 0,
+  SIPOC_KKT_BLOCK_C = 1,
+  SIPOC_KKT_BLOCK_CT = 2,
+  SIPOC_KKT_BLOCK_G = 3,
+  SIPOC_KKT_BLOCK_GT = 4
+} sipoc_kkt_block;
+sipoc_error sipoc_kkt_apply_block(sipoc_engine *engine, const sipoc_kkt_model *model,
+                                  int block, const double *x, double *y, void *stream);
 /* ||K sol - b||_2 per problem and the 4 all-reducible statistics (see
  * sipoc_lqr_residual); ok may be NULL. */
 sipoc_error sipoc_kkt_residual(sipoc_engine *engine, const sipoc_kkt_model *model,
@@ -282,6 +300,11 @@ sipoc_error sipoc_kkt_solve_host(sipoc_engine *engine, const double *b, double *
 sipoc_error sipoc_kkt_apply_host(sipoc_engine *engine, const double *w, const double *r1,
                                  const double *r2, const double *r3, const double *x,
                                  double *y);
+
+/* y += B x for one block, against the model uploaded by the last
+ * sipoc_kkt_factor_host (vector lengths as for sipoc_kkt_apply_block). */
+sipoc_error sipoc_kkt_apply_block_host(sipoc_engine *engine, int block, const double *x,
+                                       double *y);
 
 /* ---- synthetic workloads (bench / test tooling) -------------------------- */
 /* Fills engine-layout device buffers with the distribution of the reference's

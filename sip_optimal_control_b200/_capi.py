@@ -29,6 +29,8 @@ SIPOC_INVALID_TOPOLOGY = 4
 SIPOC_INVALID_DIMENSIONS = 5
 SIPOC_FLAG_FORCE_GENERIC = 1
 SIPOC_FLAG_PAD_VARIABLE_DIMS = 2
+# sipoc_kkt_block
+KKT_BLOCK_H, KKT_BLOCK_C, KKT_BLOCK_CT, KKT_BLOCK_G, KKT_BLOCK_GT = range(5)
 
 
 class Structure(ctypes.Structure):
@@ -131,6 +133,8 @@ def _load() -> ctypes.CDLL:
     lib.sipoc_kkt_factor.argtypes = [E, KM, P, P, P, P, P, P]
     lib.sipoc_kkt_solve.argtypes = [E, KM, P, P, P]
     lib.sipoc_kkt_apply.argtypes = [E, KM, P, P, P, P, P, P, P]
+    lib.sipoc_kkt_apply_block.argtypes = [E, KM, ctypes.c_int, P, P, P]
+    lib.sipoc_kkt_apply_block_host.argtypes = [E, ctypes.c_int, P, P]
     lib.sipoc_kkt_residual.argtypes = [E, KM, P, P, P, P, P, P, P, P, P, P]
     lib.sipoc_kkt_factor_host.argtypes = [E, KM, P, P, P, P, P]
     lib.sipoc_kkt_solve_host.argtypes = [E, P, P]

@@ -1079,6 +1079,52 @@ sipoc_error sipoc_kkt_apply(sipoc_engine *e, const sipoc_kkt_model *model, const
   return check_launch(e, "kkt_apply");
 }
 
+namespace {
+// block -> (mask, length of x, length of y) and the launch on the right vector slots
+sipoc_error kkt_apply_block_core(sipoc_engine *e, const KktModel &mdl, int block, const double *x,
+                                 double *y, cudaStream_t s) {
+  const double *ix = nullptr, *iy = nullptr, *iz = nullptr;
+  double *ox = nullptr, *oy = nullptr, *oz = nullptr;
+  unsigned parts = 0;
+  switch (block) {
+    case SIPOC_KKT_BLOCK_H: parts = kKktH; ix = x; ox = y; break;
+    case SIPOC_KKT_BLOCK_C: parts = kKktC; ix = x; oy = y; break;
+    case SIPOC_KKT_BLOCK_CT: parts = kKktCT; iy = x; ox = y; break;
+    case SIPOC_KKT_BLOCK_G: parts = kKktG; ix = x; oz = y; break;
+    case SIPOC_KKT_BLOCK_GT: parts = kKktGT; iz = x; ox = y; break;
+    default: return fail(e, SIPOC_INVALID_ARGUMENT, "unknown KKT block");
+  }
+  {
+    ProfScope ps(&e->prof, "kkt_apply_kernel", s);
+    launch_kkt_apply_parts(e->dt, mdl, parts, ix, iy, iz, ox, oy, oz, e->batch, e->ld, s);
+  }
+  e->launches += 1;
+  return check_launch(e, "kkt_apply_block");
+}
+
+void kkt_block_dims(const sipoc_engine *e, int block, int64_t *nx, int64_t *ny) {
+  const HostStructure &h = e->hs;
+  const int64_t in[5] = {h.x_dim, h.x_dim, h.y_dim, h.x_dim, h.z_dim};
+  const int64_t out[5] = {h.x_dim, h.y_dim, h.x_dim, h.z_dim, h.x_dim};
+  *nx = in[block];
+  *ny = out[block];
+}
+}  // namespace
+
+sipoc_error sipoc_kkt_apply_block(sipoc_engine *e, const sipoc_kkt_model *model, int block,
+                                  const double *x, double *y, void *stream) {
+  if (e == nullptr) return SIPOC_INVALID_ARGUMENT;
+  if (block < SIPOC_KKT_BLOCK_H || block > SIPOC_KKT_BLOCK_GT)
+    return fail(e, SIPOC_INVALID_ARGUMENT, "unknown KKT block");
+  int64_t nx = 0, ny = 0;
+  kkt_block_dims(e, block, &nx, &ny);
+  if (nx == 0 || ny == 0) return SIPOC_OK;  // an empty block (e.g. no inequalities)
+  if (model_has_null(model) || !x || !y)
+    return fail(e, SIPOC_INVALID_ARGUMENT, "NULL KKT apply argument");
+  DeviceGuard guard(e->device);
+  return kkt_apply_block_core(e, to_model(model), block, x, y, static_cast<cudaStream_t>(stream));
+}
+
 sipoc_error sipoc_kkt_residual(sipoc_engine *e, const sipoc_kkt_model *model, const double *w,
                                const double *r1, const double *r2, const double *r3,
                                const double *sol, const double *b, const int *ok,
@@ -1177,6 +1223,28 @@ sipoc_error sipoc_kkt_apply_host(sipoc_engine *e, const double *w, const double 
   e->launches += 1;
   if ((rc = check_launch(e, "kkt_apply")) != SIPOC_OK) return rc;
   if ((rc = download(e, e->hk_vec[1], y, e->hs.kkt_dim)) != SIPOC_OK) return rc;
+  SIPOC_CUDA(e, cudaStreamSynchronize(e->host_stream));
+  return SIPOC_OK;
+}
+
+sipoc_error sipoc_kkt_apply_block_host(sipoc_engine *e, int block, const double *x, double *y) {
+  if (e == nullptr || !x || !y) return SIPOC_INVALID_ARGUMENT;
+  if (block < SIPOC_KKT_BLOCK_H || block > SIPOC_KKT_BLOCK_GT)
+    return fail(e, SIPOC_INVALID_ARGUMENT, "unknown KKT block");
+  if (!e->host_kkt_ready)
+    return fail(e, SIPOC_NOT_FACTORED,
+                "sipoc_kkt_apply_block_host needs the model uploaded by sipoc_kkt_factor_host");
+  DeviceGuard guard(e->device);
+  sipoc_error rc;
+  int64_t nx = 0, ny = 0;
+  kkt_block_dims(e, block, &nx, &ny);
+  if (nx == 0 || ny == 0) return SIPOC_OK;
+  if ((rc = upload(e, x, e->hk_vec[0], nx)) != SIPOC_OK) return rc;
+  if ((rc = upload(e, y, e->hk_vec[1], ny)) != SIPOC_OK) return rc;
+  if ((rc = kkt_apply_block_core(e, host_resident_model(e), block, e->hk_vec[0], e->hk_vec[1],
+                                 e->host_stream)) != SIPOC_OK)
+    return rc;
+  if ((rc = download(e, e->hk_vec[1], y, ny)) != SIPOC_OK) return rc;
   SIPOC_CUDA(e, cudaStreamSynchronize(e->host_stream));
   return SIPOC_OK;
 }

@@ -655,76 +655,95 @@ kkt_recover_kernel(DevTables t, KktModel mdl, KktWs ws, const double *bvec, doub
 // edges, so no two threads write the same element.
 __global__ void __launch_bounds__(kThreads)
 kkt_apply_kernel(DevTables t, KktModel mdl, const double *w, const double *r1,
-                 const double *r2, const double *r3, const double *xin, double *yout,
+                 const double *r2, const double *r3, const double *in_x, const double *in_y,
+                 const double *in_z, double *out_x, double *out_y, double *out_z, unsigned parts,
                  int64_t batch, int64_t ld) {
+  // parts: which blocks of K = [H + R1, C', G'; C, -R2, 0; G, 0, -(W + R3)] are applied
+  // (kKktH | kKktC | kKktCT | kKktG | kKktGT | kKktReg); pointers of unused vectors may be null.
   const int64_t b = problem_index();
   if (b >= batch) return;
   const int node = blockIdx.y;
   const size_t L = static_cast<size_t>(ld);
-  GCVec W{w + b, L}, R1{r1 + b, L}, R2{r2 + b, L}, R3{r3 + b, L}, x{xin + b, L};
+  const bool pH = parts & kKktH, pC = parts & kKktC, pCT = parts & kKktCT, pG = parts & kKktG,
+             pGT = parts & kKktGT, pR = parts & kKktReg;
+  GCVec W{w + b, L}, R1{r1 + b, L}, R2{r2 + b, L}, R3{r3 + b, L};
+  GCVec X{in_x + b, L}, Y{in_y + b, L}, Z{in_z + b, L};
   GCVec nh{mdl.node_hxx + b, L}, njc{mdl.node_jc + b, L}, njg{mdl.node_jg + b, L};
   GCVec eh{mdl.edge_hxx + b, L}, ehu{mdl.edge_hxu + b, L}, euu{mdl.edge_huu + b, L},
       eA{mdl.edge_A + b, L}, eB{mdl.edge_B + b, L};
   GCVec jcx{mdl.edge_jcx + b, L}, jcu{mdl.edge_jcu + b, L}, jgx{mdl.edge_jgx + b, L},
       jgu{mdl.edge_jgu + b, L};
-  GVec y{yout + b, L};
-  const int xd = t.x_dim, yd = t.y_dim;
+  GVec OX{out_x + b, L}, OY{out_y + b, L}, OZ{out_z + b, L};
   const int n = t.n[node], c = t.node_c[node], g = t.node_g[node];
   const int xs = t.x_state[node];
-  const int xy = xd, xz = xd + yd;  // start of the y / z parts inside [x|y|z]
   const int ie = t.in_edge[node];
 
   // x rows of this node's state.
-  for (int i = 0; i < n; ++i) {
-    double s = 0.0;
-    for (int j = 0; j < n; ++j) s += nh(t.nn_off[node] + i + j * n) * x(xs + j);
-    for (int k = 0; k < c; ++k)
-      s += njc(t.jc_node_off[node] + k + i * c) * x(xy + t.y_node_c[node] + k);
-    for (int k = 0; k < g; ++k)
-      s += njg(t.jg_node_off[node] + k + i * g) * x(xz + t.z_node[node] + k);
-    s -= x(xy + t.y_dyn[node] + i);  // -I of the node's own dynamics / root row
-    for (int ci = t.child_offsets[node]; ci < t.child_offsets[node + 1]; ++ci) {
-      const int e = t.child_edges[ci];
-      const int child = t.children[e];
-      const int nc = t.n[child], m = t.m[e], ec = t.edge_c[e], eg = t.edge_g[e];
-      for (int j = 0; j < n; ++j) s += eh(t.hxx_edge_off[e] + i + j * n) * x(xs + j);
-      for (int a = 0; a < m; ++a) s += ehu(t.nm_off[e] + i + a * n) * x(t.x_control[e] + a);
-      for (int p = 0; p < nc; ++p)
-        s += eA(t.a_off[e] + p + i * nc) * x(xy + t.y_dyn[child] + p);
-      for (int k = 0; k < ec; ++k)
-        s += jcx(t.jcx_off[e] + k + i * ec) * x(xy + t.y_edge_c[e] + k);
-      for (int k = 0; k < eg; ++k)
-        s += jgx(t.jgx_off[e] + k + i * eg) * x(xz + t.z_edge[e] + k);
+  if (pH || pCT || pGT || pR) {
+    for (int i = 0; i < n; ++i) {
+      double s = 0.0;
+      if (pH)
+        for (int j = 0; j < n; ++j) s += nh(t.nn_off[node] + i + j * n) * X(xs + j);
+      if (pCT)
+        for (int k = 0; k < c; ++k)
+          s += njc(t.jc_node_off[node] + k + i * c) * Y(t.y_node_c[node] + k);
+      if (pGT)
+        for (int k = 0; k < g; ++k) s += njg(t.jg_node_off[node] + k + i * g) * Z(t.z_node[node] + k);
+      if (pCT) s -= Y(t.y_dyn[node] + i);  // -I of the node's own dynamics / root row
+      for (int ci = t.child_offsets[node]; ci < t.child_offsets[node + 1]; ++ci) {
+        const int e = t.child_edges[ci];
+        const int child = t.children[e];
+        const int nc = t.n[child], m = t.m[e], ec = t.edge_c[e], eg = t.edge_g[e];
+        if (pH) {
+          for (int j = 0; j < n; ++j) s += eh(t.hxx_edge_off[e] + i + j * n) * X(xs + j);
+          for (int a = 0; a < m; ++a) s += ehu(t.nm_off[e] + i + a * n) * X(t.x_control[e] + a);
+        }
+        if (pCT) {
+          for (int p = 0; p < nc; ++p) s += eA(t.a_off[e] + p + i * nc) * Y(t.y_dyn[child] + p);
+          for (int k = 0; k < ec; ++k) s += jcx(t.jcx_off[e] + k + i * ec) * Y(t.y_edge_c[e] + k);
+        }
+        if (pGT)
+          for (int k = 0; k < eg; ++k) s += jgx(t.jgx_off[e] + k + i * eg) * Z(t.z_edge[e] + k);
+      }
+      if (pR) s += R1(xs + i) * X(xs + i);
+      OX(xs + i) += s;
     }
-    s += R1(xs + i) * x(xs + i);
-    y(xs + i) += s;
   }
   // y rows: dynamics of this node (root: -x_root; else A x_p + B u - x_node).
-  for (int i = 0; i < n; ++i) {
-    double s = -x(xs + i);
-    if (ie >= 0) {
-      const int parent = t.parents[ie];
-      const int np = t.n[parent], m = t.m[ie];
-      for (int j = 0; j < np; ++j) s += eA(t.a_off[ie] + i + j * n) * x(t.x_state[parent] + j);
-      for (int a = 0; a < m; ++a) s += eB(t.b_off[ie] + i + a * n) * x(t.x_control[ie] + a);
+  if (pC || pR) {
+    for (int i = 0; i < n; ++i) {
+      double s = 0.0;
+      if (pC) {
+        s = -X(xs + i);
+        if (ie >= 0) {
+          const int parent = t.parents[ie];
+          const int np = t.n[parent], m = t.m[ie];
+          for (int j = 0; j < np; ++j) s += eA(t.a_off[ie] + i + j * n) * X(t.x_state[parent] + j);
+          for (int a = 0; a < m; ++a) s += eB(t.b_off[ie] + i + a * n) * X(t.x_control[ie] + a);
+        }
+      }
+      const int o = t.y_dyn[node] + i;
+      if (pR) s -= R2(o) * Y(o);
+      OY(o) += s;
     }
-    const int o = t.y_dyn[node] + i;
-    s -= R2(o) * x(xy + o);
-    y(xy + o) += s;
+    for (int k = 0; k < c; ++k) {
+      double s = 0.0;
+      if (pC)
+        for (int j = 0; j < n; ++j) s += njc(t.jc_node_off[node] + k + j * c) * X(xs + j);
+      const int o = t.y_node_c[node] + k;
+      if (pR) s -= R2(o) * Y(o);
+      OY(o) += s;
+    }
   }
-  for (int k = 0; k < c; ++k) {
-    double s = 0.0;
-    for (int j = 0; j < n; ++j) s += njc(t.jc_node_off[node] + k + j * c) * x(xs + j);
-    const int o = t.y_node_c[node] + k;
-    s -= R2(o) * x(xy + o);
-    y(xy + o) += s;
-  }
-  for (int k = 0; k < g; ++k) {
-    double s = 0.0;
-    for (int j = 0; j < n; ++j) s += njg(t.jg_node_off[node] + k + j * g) * x(xs + j);
-    const int o = t.z_node[node] + k;
-    s -= (W(o) + R3(o)) * x(xz + o);
-    y(xz + o) += s;
+  if (pG || pR) {
+    for (int k = 0; k < g; ++k) {
+      double s = 0.0;
+      if (pG)
+        for (int j = 0; j < n; ++j) s += njg(t.jg_node_off[node] + k + j * g) * X(xs + j);
+      const int o = t.z_node[node] + k;
+      if (pR) s -= (W(o) + R3(o)) * Z(o);
+      OZ(o) += s;
+    }
   }
   // Rows owned by child edges: control stationarity, edge_c, edge_g.
   for (int ci = t.child_offsets[node]; ci < t.child_offsets[node + 1]; ++ci) {
@@ -732,34 +751,46 @@ kkt_apply_kernel(DevTables t, KktModel mdl, const double *w, const double *r1,
     const int child = t.children[e];
     const int nc = t.n[child], m = t.m[e], ec = t.edge_c[e], eg = t.edge_g[e];
     const int xu = t.x_control[e];
-    for (int a = 0; a < m; ++a) {
-      double s = 0.0;
-      for (int i = 0; i < n; ++i) s += ehu(t.nm_off[e] + i + a * n) * x(xs + i);
-      for (int j = 0; j < m; ++j) s += euu(t.mm_off[e] + a + j * m) * x(xu + j);
-      for (int p = 0; p < nc; ++p)
-        s += eB(t.b_off[e] + p + a * nc) * x(xy + t.y_dyn[child] + p);
-      for (int k = 0; k < ec; ++k)
-        s += jcu(t.jcu_off[e] + k + a * ec) * x(xy + t.y_edge_c[e] + k);
-      for (int k = 0; k < eg; ++k)
-        s += jgu(t.jgu_off[e] + k + a * eg) * x(xz + t.z_edge[e] + k);
-      s += R1(xu + a) * x(xu + a);
-      y(xu + a) += s;
+    if (pH || pCT || pGT || pR) {
+      for (int a = 0; a < m; ++a) {
+        double s = 0.0;
+        if (pH) {
+          for (int i = 0; i < n; ++i) s += ehu(t.nm_off[e] + i + a * n) * X(xs + i);
+          for (int j = 0; j < m; ++j) s += euu(t.mm_off[e] + a + j * m) * X(xu + j);
+        }
+        if (pCT) {
+          for (int p = 0; p < nc; ++p) s += eB(t.b_off[e] + p + a * nc) * Y(t.y_dyn[child] + p);
+          for (int k = 0; k < ec; ++k) s += jcu(t.jcu_off[e] + k + a * ec) * Y(t.y_edge_c[e] + k);
+        }
+        if (pGT)
+          for (int k = 0; k < eg; ++k) s += jgu(t.jgu_off[e] + k + a * eg) * Z(t.z_edge[e] + k);
+        if (pR) s += R1(xu + a) * X(xu + a);
+        OX(xu + a) += s;
+      }
     }
-    for (int k = 0; k < ec; ++k) {
-      double s = 0.0;
-      for (int j = 0; j < n; ++j) s += jcx(t.jcx_off[e] + k + j * ec) * x(xs + j);
-      for (int j = 0; j < m; ++j) s += jcu(t.jcu_off[e] + k + j * ec) * x(xu + j);
-      const int o = t.y_edge_c[e] + k;
-      s -= R2(o) * x(xy + o);
-      y(xy + o) += s;
+    if (pC || pR) {
+      for (int k = 0; k < ec; ++k) {
+        double s = 0.0;
+        if (pC) {
+          for (int j = 0; j < n; ++j) s += jcx(t.jcx_off[e] + k + j * ec) * X(xs + j);
+          for (int j = 0; j < m; ++j) s += jcu(t.jcu_off[e] + k + j * ec) * X(xu + j);
+        }
+        const int o = t.y_edge_c[e] + k;
+        if (pR) s -= R2(o) * Y(o);
+        OY(o) += s;
+      }
     }
-    for (int k = 0; k < eg; ++k) {
-      double s = 0.0;
-      for (int j = 0; j < n; ++j) s += jgx(t.jgx_off[e] + k + j * eg) * x(xs + j);
-      for (int j = 0; j < m; ++j) s += jgu(t.jgu_off[e] + k + j * eg) * x(xu + j);
-      const int o = t.z_edge[e] + k;
-      s -= (W(o) + R3(o)) * x(xz + o);
-      y(xz + o) += s;
+    if (pG || pR) {
+      for (int k = 0; k < eg; ++k) {
+        double s = 0.0;
+        if (pG) {
+          for (int j = 0; j < n; ++j) s += jgx(t.jgx_off[e] + k + j * eg) * X(xs + j);
+          for (int j = 0; j < m; ++j) s += jgu(t.jgu_off[e] + k + j * eg) * X(xu + j);
+        }
+        const int o = t.z_edge[e] + k;
+        if (pR) s -= (W(o) + R3(o)) * Z(o);
+        OZ(o) += s;
+      }
     }
   }
 }
@@ -980,8 +1011,20 @@ void launch_kkt_apply(const DevTables &t, const KktModel &m, const double *w,
                       const double *r1, const double *r2, const double *r3,
                       const double *x, double *y, int64_t batch, int64_t ld,
                       cudaStream_t s) {
-  kkt_apply_kernel<<<batch_grid(batch, t.N), kThreads, 0, s>>>(t, m, w, r1, r2, r3, x, y,
-                                                              batch, ld);
+  // the whole operator on [x | y | z] vectors
+  const size_t oy = static_cast<size_t>(t.x_dim) * ld, oz = oy + static_cast<size_t>(t.y_dim) * ld;
+  kkt_apply_kernel<<<batch_grid(batch, t.N), kThreads, 0, s>>>(
+      t, m, w, r1, r2, r3, x, x + oy, x + oz, y, y + oy, y + oz, kKktAll, batch, ld);
+}
+
+void launch_kkt_apply_parts(const DevTables &t, const KktModel &m, unsigned parts,
+                            const double *in_x, const double *in_y, const double *in_z,
+                            double *out_x, double *out_y, double *out_z, int64_t batch,
+                            int64_t ld, cudaStream_t s) {
+  // component blocks only (no regularization): the weight pointers are never read
+  kkt_apply_kernel<<<batch_grid(batch, t.N), kThreads, 0, s>>>(
+      t, m, nullptr, nullptr, nullptr, nullptr, in_x, in_y, in_z, out_x, out_y, out_z,
+      parts & ~kKktReg, batch, ld);
 }
 
 void launch_kkt_residual(const DevTables &t, const double *Ksol, const double *b,

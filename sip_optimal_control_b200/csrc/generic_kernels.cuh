@@ -83,6 +83,14 @@ void launch_kkt_build_rhs(const DevTables &t, const KktModel &m, const KktWs &ws
 void launch_kkt_recover(const DevTables &t, const KktModel &m, const KktWs &ws,
                         const double *b, double *sol, int64_t batch, int64_t ld,
                         cudaStream_t stream);
+// Blocks of the KKT operator K = [H + R1, C', G'; C, -R2, 0; G, 0, -(W + R3)]
+// (helpers.cpp:953-1368): add_Kx_to_y applies all of them, add_{H,C,CT,G,GT}x_to_y one each.
+constexpr unsigned kKktH = 1u, kKktC = 2u, kKktCT = 4u, kKktG = 8u, kKktGT = 16u, kKktReg = 32u,
+                   kKktAll = 63u;
+void launch_kkt_apply_parts(const DevTables &t, const KktModel &m, unsigned parts,
+                            const double *in_x, const double *in_y, const double *in_z,
+                            double *out_x, double *out_y, double *out_z, int64_t batch,
+                            int64_t ld, cudaStream_t s);
 void launch_kkt_apply(const DevTables &t, const KktModel &m, const double *w,
                       const double *r1, const double *r2, const double *r3,
                       const double *x, double *y, int64_t batch, int64_t ld,

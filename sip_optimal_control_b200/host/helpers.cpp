@@ -188,4 +188,20 @@ void CallbackProvider::add_Kx_to_y(const double *w, const double *r1, const doub
   std::copy(y.begin() + xd + yd, y.begin() + xd + yd + zd, y_z);
 }
 
+void CallbackProvider::add_Hx_to_y(const double *x, double *y) {
+  sipoc_kkt_apply_block_host(workspace_.lqr_workspace.engine, SIPOC_KKT_BLOCK_H, x, y);
+}
+void CallbackProvider::add_Cx_to_y(const double *x, double *y) {
+  sipoc_kkt_apply_block_host(workspace_.lqr_workspace.engine, SIPOC_KKT_BLOCK_C, x, y);
+}
+void CallbackProvider::add_CTx_to_y(const double *x, double *y) {
+  sipoc_kkt_apply_block_host(workspace_.lqr_workspace.engine, SIPOC_KKT_BLOCK_CT, x, y);
+}
+void CallbackProvider::add_Gx_to_y(const double *x, double *y) {
+  sipoc_kkt_apply_block_host(workspace_.lqr_workspace.engine, SIPOC_KKT_BLOCK_G, x, y);
+}
+void CallbackProvider::add_GTx_to_y(const double *x, double *y) {
+  sipoc_kkt_apply_block_host(workspace_.lqr_workspace.engine, SIPOC_KKT_BLOCK_GT, x, y);
+}
+
 }  // namespace sip::optimal_control

@@ -15,6 +15,12 @@ class CallbackProvider {
   void add_Kx_to_y(const double *w, const double *r1, const double *r2, const double *r3,
                    const double *x_x, const double *x_y, const double *x_z, double *y_x,
                    double *y_y, double *y_z);
+  // y += B x for one block of the operator (helpers.hpp:17-21 of the reference).
+  void add_Hx_to_y(const double *x, double *y);
+  void add_Cx_to_y(const double *x, double *y);
+  void add_CTx_to_y(const double *x, double *y);
+  void add_Gx_to_y(const double *x, double *y);
+  void add_GTx_to_y(const double *x, double *y);
 
  private:
   void gather_model();

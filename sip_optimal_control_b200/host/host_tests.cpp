@@ -14,6 +14,7 @@
 //   CallbackProvider.SolvesChainWithNodeAndEdgeConstraints        tests/variable_dimensions_test.cpp:77-181, 265-290
 //   CallbackProvider.SolvesBranchedSystemWithZeroDimensionalRoot  tests/variable_dimensions_test.cpp:316-336
 //   InputValidation (DAG and negative dimension rejected)         tests/variable_dimensions_test.cpp:183-224
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <functional>
@@ -352,6 +353,21 @@ static double kkt_case(int E, const std::vector<int> &parents, const std::vector
   callback_provider.add_Kx_to_y(w.data(), r1.data(), r2.data(), r3.data(), solution.data(),
                                 solution.data() + x_dim, solution.data() + x_dim + y_dim,
                                 px.data(), py.data(), pz.data());
+  {  // add_Kx_to_y is the sum of its five blocks and the diagonal terms (helpers.cpp:953-977)
+    const double *sx = solution.data(), *sy = sx + x_dim, *sz = sy + y_dim;
+    std::vector<double> qx(x_dim + 1, 0.0), qy(y_dim + 1, 0.0), qz(z_dim + 1, 0.0);
+    callback_provider.add_Hx_to_y(sx, qx.data());
+    callback_provider.add_Cx_to_y(sx, qy.data());
+    callback_provider.add_CTx_to_y(sy, qx.data());
+    callback_provider.add_Gx_to_y(sx, qz.data());
+    callback_provider.add_GTx_to_y(sz, qx.data());
+    double worst = 0.0;
+    for (int i = 0; i < x_dim; ++i) worst = std::max(worst, std::fabs(qx[i] + r1[i] * sx[i] - px[i]));
+    for (int i = 0; i < y_dim; ++i) worst = std::max(worst, std::fabs(qy[i] - r2[i] * sy[i] - py[i]));
+    for (int i = 0; i < z_dim; ++i)
+      worst = std::max(worst, std::fabs(qz[i] - (w[i] + r3[i]) * sz[i] - pz[i]));
+    CHECK(worst < 1e-12);
+  }
   double sq = 0.0;
   for (int i = 0; i < x_dim; ++i) sq += (px[i] - rhs[i]) * (px[i] - rhs[i]);
   for (int i = 0; i < y_dim; ++i) sq += (py[i] - rhs[x_dim + i]) * (py[i] - rhs[x_dim + i]);

@@ -93,6 +93,29 @@ class CallbackProvider:
                                      r2.data_ptr(), r3.data_ptr(), x.data_ptr(), y.data_ptr(),
                                      e.stream_ptr(stream)))
 
+    # The five blocks of the operator on their own (helpers.hpp:17-21): y += B x on device
+    # vectors of the block's own lengths (H: x -> x, C: x -> y, CT: y -> x, G: x -> z, GT: z -> x).
+    def _apply_block(self, block: int, model: dict, x, y, stream=None) -> None:
+        e = self.engine
+        m = _model_struct(model, False, [])
+        e._check(lib.sipoc_kkt_apply_block(e._handle, ctypes.byref(m), block, x.data_ptr(),
+                                           y.data_ptr(), e.stream_ptr(stream)))
+
+    def add_Hx_to_y(self, model: dict, x, y, stream=None) -> None:
+        self._apply_block(_capi.KKT_BLOCK_H, model, x, y, stream)
+
+    def add_Cx_to_y(self, model: dict, x, y, stream=None) -> None:
+        self._apply_block(_capi.KKT_BLOCK_C, model, x, y, stream)
+
+    def add_CTx_to_y(self, model: dict, x, y, stream=None) -> None:
+        self._apply_block(_capi.KKT_BLOCK_CT, model, x, y, stream)
+
+    def add_Gx_to_y(self, model: dict, x, y, stream=None) -> None:
+        self._apply_block(_capi.KKT_BLOCK_G, model, x, y, stream)
+
+    def add_GTx_to_y(self, model: dict, x, y, stream=None) -> None:
+        self._apply_block(_capi.KKT_BLOCK_GT, model, x, y, stream)
+
     def residual(self, model: dict, w, r1, r2, r3, sol, b, ok=None, stream=None):
         """(||K sol - b||_2 per problem, 4 all-reducible statistics)."""
         e = self.engine
@@ -125,6 +148,14 @@ class CallbackProvider:
         sol = np.zeros_like(b)
         e._check(lib.sipoc_kkt_solve_host(e._handle, _host_ptr(b), _host_ptr(sol)))
         return sol
+
+    def apply_block_host(self, block: int, x, y) -> np.ndarray:
+        """y += B x for one block against the model of the last ``factor_host``."""
+        e = self.engine
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.array(y, dtype=np.float64, order="C")
+        e._check(lib.sipoc_kkt_apply_block_host(e._handle, block, _host_ptr(x), _host_ptr(y)))
+        return y
 
     def add_Kx_to_y_host(self, w, r1, r2, r3, x, y=None) -> np.ndarray:
         e = self.engine

@@ -88,6 +88,45 @@ def test_newton_kkt_benchmark_shapes(n, m, T, force_generic):
     assert rel_err(cp.engine.unpack(dy, rhs.shape[1]), yref).max() < 1e-12
 
 
+@pytest.mark.parametrize("case", [fx.kkt_case_chain, fx.kkt_case_siblings,
+                                  fx.kkt_case_zero_dim_root])
+def test_operator_blocks(case):
+    # add_Hx_to_y / add_Cx_to_y / add_CTx_to_y / add_Gx_to_y / add_GTx_to_y
+    # (helpers.hpp:17-21, helpers.cpp:979-1368) against the oracle's operator with the
+    # regularization switched off and one slot of [x|y|z] populated at a time.
+    s = case()
+    sz = pyoracle.kkt_sizes(s)
+    xd, yd, zd = sz["x_dim"], sz["y_dim"], sz["z_dim"]
+    batch = 5
+    rng = np.random.default_rng(4)
+    model = {k: np.repeat(v, batch, axis=0) * (1.0 + 0.1 * rng.standard_normal((batch, 1)))
+             for k, v in fx.kkt_model(s).items()}
+    dims, topo = to_structs(s)
+    cp = CallbackProvider(dims, topo, batch)
+    e = cp.engine
+    dm = cp.pack_model(model)
+    zero = lambda n: np.zeros((batch, n))
+    vx, vy, vz = (rng.standard_normal((batch, n)) for n in (xd, yd, zd))
+
+    def oracle(x_x, x_y, x_z):  # K with w = r1 = r2 = r3 = 0
+        x = np.concatenate([x_x, x_y, x_z], axis=1)
+        y = pyoracle.kkt_apply(s, model, zero(zd), zero(xd), zero(yd), zero(zd), x,
+                               np.zeros_like(x))
+        return y[:, :xd], y[:, xd:xd + yd], y[:, xd + yd:]
+
+    cases = [(cp.add_Hx_to_y, vx, xd, oracle(vx, zero(yd), zero(zd))[0]),
+             (cp.add_Cx_to_y, vx, yd, oracle(vx, zero(yd), zero(zd))[1]),
+             (cp.add_CTx_to_y, vy, xd, oracle(zero(xd), vy, zero(zd))[0]),
+             (cp.add_Gx_to_y, vx, zd, oracle(vx, zero(yd), zero(zd))[2]),
+             (cp.add_GTx_to_y, vz, xd, oracle(zero(xd), zero(yd), vz)[0])]
+    for fn, vin, nout, want in cases:
+        y0 = rng.standard_normal((batch, nout))
+        dy = e.pack(y0)
+        fn(dm, e.pack(vin), dy)
+        got = e.unpack(dy, nout)
+        assert got.size == 0 or np.abs(got - (y0 + want)).max() < 1e-12, fn.__name__
+
+
 def test_full_regularization_range_generic_path():
     # newton_kkt_benchmark.cpp:231-239 as is: r2 log-uniform up to 1e9.  The
     # generic kernels follow the reference's operation order, so they must
