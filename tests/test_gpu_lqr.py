@@ -303,6 +303,29 @@ def test_variable_dimension_chain_and_tree_batches():
     assert "generic" in lqr.engine.kernel_variant
 
 
+@pytest.mark.parametrize("shape", ["heterogeneous_chain", "shallow_wide_tree", "binary_tree"])
+@pytest.mark.parametrize("num_edges,base_n", [(31, 4), (63, 4), (31, 8)])
+def test_reference_variable_benchmark_shapes(shape, num_edges, base_n):
+    # The VariableLQRProblem grid of lqr_benchmark.cpp:209-310, :547-555: per-node dims
+    # base_n + (node % 3) - 1, per-edge controls 2 + (edge % 3) - 1, on a chain, a star
+    # (every edge out of the root) and a binary tree.
+    T = num_edges
+    sd = [max(1, base_n + (i % 3) - 1) for i in range(T + 1)]
+    cd = [max(1, 2 + (e % 3) - 1) for e in range(T)]
+    children = list(range(1, T + 1))
+    parents = {"heterogeneous_chain": list(range(T)), "shallow_wide_tree": [0] * T,
+               "binary_tree": [(c - 1) // 2 for c in children]}[shape]
+    s = pyoracle.Structure(parents, children, 0, sd, cd)
+    host = pg.variable_tree_batch(s, 33, seed=17 + num_edges + base_n)
+    ref = pyoracle.lqr_factor_solve(s, host)
+    assert (ref["status"] == 0).all()
+    for fused in (True, False):
+        gpu, lqr = gpu_lqr_factor_solve(s, host, fused=fused)
+        assert (gpu["status"] == 0).all()
+        assert_lqr_parity(gpu, ref, REL_TOL)
+        assert gpu["residual"].max() < 1e-9
+
+
 def test_host_buffer_entry_points():
     # the reference-facing call: host arrays in, host arrays out
     n, m, T, batch = 6, 2, 12, 21
