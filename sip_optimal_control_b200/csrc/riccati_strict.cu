@@ -600,6 +600,8 @@ const FastPlan *select_strict_plan(int n, int m) {
   if (n <= 3 && m <= 2) return make_strict_plan<3, 2>("strict_thread_n3_m2");
   if (n <= 4 && m <= 2) return make_strict_plan<4, 2>("strict_thread_n4_m2");
   if (n <= 4 && m <= 4) return make_strict_plan<4, 4>("strict_thread_n4_m4");
+  if (n <= 5 && m <= 3) return make_strict_plan<5, 3>("strict_thread_n5_m3");
+  if (n <= 6 && m <= 3) return make_strict_plan<6, 3>("strict_thread_n6_m3");
   return nullptr;
 }
 
