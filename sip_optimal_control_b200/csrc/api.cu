@@ -354,6 +354,7 @@ sipoc_error lqr_factor_core(sipoc_engine *e, const LqrIn &caller_in, int *status
     if (e->padded && (rc = pad_inputs(e, &in, kPmMatrices, s)) != SIPOC_OK) return rc;
     FastArgs a{in, pm, LqrOut{}, status, e->fast_store, nullptr, e->batch, e->ld, e->hs.E,
                &e->prof};
+    a.tables = &e->dt;
     e->launches += e->fast->factor(a, s);
     e->factored = sipoc_engine::Factored::FAST;
   } else {
@@ -387,6 +388,7 @@ sipoc_error lqr_solve_core(sipoc_engine *e, const LqrIn &caller_in, const LqrOut
     }
     FastArgs a{in, pm, plan_out, nullptr, e->fast_store, e->fast_scratch, e->batch, e->ld,
                e->hs.E, &e->prof};
+    a.tables = &e->dt;
     e->launches += e->fast->solve(a, s);
     if (e->padded) unpad_outputs(e, plan_out, out, s);
   } else {
@@ -414,6 +416,7 @@ sipoc_error lqr_factor_solve_core(sipoc_engine *e, const LqrIn &caller_in, const
     }
     FastArgs a{in, pm, plan_out, status, e->fast_store, e->fast_scratch, e->batch, e->ld, e->hs.E,
                &e->prof};
+    a.tables = &e->dt;
     e->launches += e->fast->factor_solve(a, s);
     if (e->padded) unpad_outputs(e, plan_out, out, s);
     // The backward kernel keeps W, K and G^-1, so later solves may reuse them.
@@ -694,6 +697,11 @@ sipoc_error sipoc_create(const sipoc_structure *s, sipoc_engine **out) {
     // uniform shape that is not instantiated): the reference-order register kernels on the
     // chain padded to the smallest shape that holds every stage -- the generic kernels'
     // operations in the same order on the real entries (riccati_strict.cu).
+    e->padded = true;
+  }
+  if (e->fast == nullptr && !(e->flags & SIPOC_FLAG_FORCE_GENERIC) && !h.is_chain && h.E >= 1 &&
+      (e->fast = select_strict_tree_plan(h.max_n, h.max_m)) != nullptr) {
+    // Small trees: the same reference-order register kernels, walking the tree.
     e->padded = true;
   }
   if (e->fast == nullptr && !(e->flags & SIPOC_FLAG_FORCE_GENERIC) &&

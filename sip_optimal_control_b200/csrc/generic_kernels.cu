@@ -861,7 +861,8 @@ unpack_kernel(const double *__restrict__ src, double *__restrict__ dst, int64_t 
 }
 
 // ---------------------------------------------------------------------------
-// Variable-dimension chain <-> uniform chain of dims (NP, MP) >= every stage's dims.
+// Variable-dimension chain or tree <-> the same topology with uniform dims (NP, MP) >= every
+// stage's dims.
 // A stage is padded with states / controls that are decoupled from the real ones
 // (identity on the diagonal of Q and R, delta = 1, zeros elsewhere: their terms enter
 // every product as exact zeros), so the shape-specialised kernels serve chains whose
@@ -892,12 +893,13 @@ pad_chain_kernel(DevTables t, LqrIn src, LqrIn dst, int NP, int MP, unsigned mas
       put(dst.delta, static_cast<size_t>(k) * NP + i, in ? at(src.delta, t.n_off[k] + i) : 1.0);
   }
   if (k >= t.E) return;
-  const int mk = t.m[k], nc = t.n[k + 1];
+  // edge k: parent state dims np, child state dims nc (on a chain: nodes k and k + 1)
+  const int mk = t.m[k], np = t.n[t.parents[k]], nc = t.n[t.children[k]];
   for (int a = 0; a < MP; ++a) {
     if (mask & 2u)
       for (int x = 0; x < NP; ++x)
         put(dst.M, (static_cast<size_t>(k) * MP + a) * NP + x,
-            (x < nk && a < mk) ? at(src.M, t.nm_off[k] + a * nk + x) : 0.0);
+            (x < np && a < mk) ? at(src.M, t.nm_off[k] + a * np + x) : 0.0);
     if (mask & 4u)
       for (int a1 = 0; a1 < MP; ++a1)
         put(dst.R, (static_cast<size_t>(k) * MP + a) * MP + a1,
@@ -912,7 +914,7 @@ pad_chain_kernel(DevTables t, LqrIn src, LqrIn dst, int NP, int MP, unsigned mas
     for (int j = 0; j < NP; ++j)
       for (int i = 0; i < NP; ++i)
         put(dst.A, (static_cast<size_t>(k) * NP + j) * NP + i,
-            (i < nc && j < nk) ? at(src.A, t.a_off[k] + j * nc + i) : 0.0);
+            (i < nc && j < np) ? at(src.A, t.a_off[k] + j * nc + i) : 0.0);
 }
 
 __global__ void __launch_bounds__(128)

@@ -27,6 +27,7 @@ struct FastArgs {
   int64_t batch, ld;
   int num_edges;
   Profiler *prof;   // per-kernel event timing (may be disabled)
+  const DevTables *tables = nullptr;  // topology, for the plans that serve trees
 };
 
 // Newton-KKT solve against the plan's kept factorization (uniform chains).
@@ -69,5 +70,6 @@ const FastPlan *select_cta_plan(int n, int m);
 // Reference-order register kernels for small chains (riccati_strict.cu): the smallest
 // instantiated shape that holds (n, m), for chains padded to it; nullptr when none does.
 const FastPlan *select_strict_plan(int n, int m);
+const FastPlan *select_strict_tree_plan(int n, int m);
 
 }  // namespace sipoc

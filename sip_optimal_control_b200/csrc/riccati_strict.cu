@@ -556,6 +556,321 @@ strict_solve_thread(LqrIn in, LqrOut out, const double *store, double *scratch, 
   }
 }
 
+
+// ===========================================================================
+// The same two routines on a TREE (padded to a uniform shape like the chains): nodes in
+// post-order, every node folding in all of its child edges (lqr.cpp:660-720), the affine
+// sweep likewise (:746-795), the rollout in pre-order (:827-869).  What a chain carries
+// from one stage to the next in registers (the child's F factor, 1 / sqrt(delta), v, x) is
+// read back from the thread's own earlier stores here; operands are plain coalesced loads,
+// all of an item's loads in flight together (fully unrolled, no dependent addressing).
+// ===========================================================================
+template <int N, int M>
+__global__ void __launch_bounds__(32)
+strict_factor_tree(DevTables t, LqrIn in, int *status_out, double *store, int64_t batch,
+                   int64_t ld) {
+  const int T = t.E;
+  using Z = StrictSizes<N, M>;
+  const int64_t b = static_cast<int64_t>(blockIdx.x) * 32 + threadIdx.x;
+  if (b >= batch) return;
+  const size_t L_ = static_cast<size_t>(ld);
+  double *st = store + b;
+  auto ld1 = [&](const double *p, size_t flat) { return __ldcs(p + flat * L_ + b); };
+  auto lds = [&](size_t flat) { return st[flat * L_]; };  // own earlier stores
+  auto put = [&](size_t flat, double v) { st[flat * L_] = v; };
+
+  int status = SIPOC_FACTOR_SUCCESS;
+  for (int order = 0; order < t.N; ++order) {
+    const int node = t.postorder[order];
+    double V[N * N];
+#pragma unroll
+    for (int i = 0; i < N * N; ++i) V[i] = ld1(in.Q, static_cast<size_t>(node) * N * N + i);  // :658
+
+    for (int ci = t.child_offsets[node]; ci < t.child_offsets[node + 1]; ++ci) {
+      const size_t e = t.child_edges[ci], child = t.children[e];
+      double A[N * N], B[N * M], Ffc[N * N], sdic[N];
+#pragma unroll
+      for (int i = 0; i < N * N; ++i) {
+        A[i] = ld1(in.A, e * N * N + i);
+        Ffc[i] = lds(Z::oF(T) + child * N * N + i);
+      }
+#pragma unroll
+      for (int i = 0; i < N * M; ++i) B[i] = ld1(in.B, e * N * M + i);
+#pragma unroll
+      for (int i = 0; i < N; ++i) sdic[i] = lds(Z::oSdi(T) + child * N + i);
+      // compute_regularized_W (lqr.cpp:511-529)
+      double W[N * N];
+#pragma unroll
+      for (int i = 0; i < N * N; ++i) W[i] = 0.0;
+#pragma unroll
+      for (int i = 0; i < N; ++i) W[i + i * N] = 1.0;
+      chol_solve<N, N>(Ffc, W);
+#pragma unroll
+      for (int i = 0; i < N * N; ++i) W[i] *= -1.0;
+#pragma unroll
+      for (int i = 0; i < N; ++i) W[i + i * N] += 1.0;
+#pragma unroll
+      for (int col = 0; col < N; ++col)
+#pragma unroll
+        for (int row = 0; row < N; ++row) W[row + col * N] *= sdic[row] * sdic[col];
+      double H[M * N];
+#pragma unroll
+      for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int a = 0; a < M; ++a) {
+          double s = 0.0;
+#pragma unroll
+          for (int p = 0; p < N; ++p) s += B[p + a * N] * W[p + j * N];
+          H[a + j * M] = s;
+        }
+      double Gf[M * M];
+#pragma unroll
+      for (int j = 0; j < M; ++j)
+#pragma unroll
+        for (int a = 0; a < M; ++a) {
+          double s = ld1(in.R, e * M * M + a + j * M);
+#pragma unroll
+          for (int p = 0; p < N; ++p) s += H[a + p * M] * B[p + j * N];
+          Gf[a + j * M] = s;
+        }
+      if (!chol_lower<M>(Gf) && status == SIPOC_FACTOR_SUCCESS)
+        status = SIPOC_FACTOR_G_FACTORIZATION_FAILURE;
+      double F[N * N];
+#pragma unroll
+      for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          double s = 0.0;
+#pragma unroll
+          for (int p = 0; p < N; ++p) s += W[i + p * N] * A[p + j * N];
+          F[i + j * N] = s;
+        }
+#pragma unroll
+      for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int a = 0; a < M; ++a) {
+          double s = ld1(in.M, e * N * M + j + a * N);
+#pragma unroll
+          for (int p = 0; p < N; ++p) s += B[p + a * N] * F[p + j * N];
+          H[a + j * M] = s;
+        }
+      double K[M * N];
+#pragma unroll
+      for (int i = 0; i < M * N; ++i) K[i] = H[i];
+      chol_solve<M, N>(Gf, K);
+#pragma unroll
+      for (int i = 0; i < M * N; ++i) K[i] *= -1.0;
+#pragma unroll
+      for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          double s = V[i + j * N];
+#pragma unroll
+          for (int p = 0; p < N; ++p) s += A[p + i * N] * F[p + j * N];
+          V[i + j * N] = s;
+        }
+#pragma unroll
+      for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          double s = 0.0;
+#pragma unroll
+          for (int a = 0; a < M; ++a) s += K[a + i * M] * H[a + j * M];
+          V[i + j * N] += s;
+        }
+#pragma unroll
+      for (int i = 0; i < N * N; ++i) put(Z::oW(T) + e * N * N + i, W[i]);
+#pragma unroll
+      for (int i = 0; i < M * N; ++i) put(Z::oK(T) + e * M * N + i, K[i]);
+#pragma unroll
+      for (int i = 0; i < M * M; ++i) put(Z::oG(T) + e * M * M + i, Gf[i]);
+    }
+
+    double sd[N], sdi[N], Ff[N * N];
+    bool d_ok = true;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const double d = ld1(in.delta, static_cast<size_t>(node) * N + i);
+      d_ok = d_ok && (d > 0.0);
+      const double s = sqrt(d);
+      sd[i] = s;
+      sdi[i] = 1.0 / s;
+    }
+    if (!d_ok && status == SIPOC_FACTOR_SUCCESS) status = SIPOC_FACTOR_INVALID_DELTA;
+#pragma unroll
+    for (int col = 0; col < N; ++col) {
+#pragma unroll
+      for (int row = 0; row < N; ++row) Ff[row + col * N] = sd[row] * V[row + col * N] * sd[col];
+      Ff[col + col * N] += 1.0;
+    }
+    if (!chol_lower<N>(Ff) && status == SIPOC_FACTOR_SUCCESS)
+      status = SIPOC_FACTOR_F_FACTORIZATION_FAILURE;
+#pragma unroll
+    for (int i = 0; i < N * N; ++i) {
+      put(Z::oV(T) + static_cast<size_t>(node) * N * N + i, V[i]);
+      put(Z::oF(T) + static_cast<size_t>(node) * N * N + i, Ff[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      put(Z::oSd(T) + static_cast<size_t>(node) * N + i, sd[i]);
+      put(Z::oSdi(T) + static_cast<size_t>(node) * N + i, sdi[i]);
+    }
+  }
+  if (status_out != nullptr) status_out[b] = status;
+}
+
+template <int N, int M>
+__global__ void __launch_bounds__(32)
+strict_solve_tree(DevTables t, LqrIn in, LqrOut out, const double *store, double *scratch,
+                  int64_t batch, int64_t ld) {
+  const int T = t.E;
+  using Z = StrictSizes<N, M>;
+  const int64_t b = static_cast<int64_t>(blockIdx.x) * 32 + threadIdx.x;
+  if (b >= batch) return;
+  const size_t L_ = static_cast<size_t>(ld);
+  const double *st = store + b;
+  double *vst = scratch + Z::ov(T) * ld + b;
+  double *kst = scratch + Z::ok(T) * ld + b;
+  auto ld1 = [&](const double *p, size_t flat) { return __ldcs(p + flat * L_ + b); };
+  auto lds = [&](size_t flat) { return __ldcs(st + flat * L_); };
+
+  // backward affine sweep (:738-796)
+  for (int order = 0; order < t.N; ++order) {
+    const size_t node = t.postorder[order];
+    double v[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = ld1(in.q, node * N + i);
+    for (int ci = t.child_offsets[node]; ci < t.child_offsets[node + 1]; ++ci) {
+      const size_t e = t.child_edges[ci], child = t.children[e];
+      double vc[N], f[N], g[N], h[M];
+#pragma unroll
+      for (int i = 0; i < N; ++i) vc[i] = vst[(child * N + i) * L_];
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+        f[i] = ld1(in.delta, child * N + i) * vc[i] - ld1(in.c, child * N + i);
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < N; ++j) s += lds(Z::oW(T) + e * N * N + i + j * N) * f[j];
+        g[i] = vc[i] - s;
+      }
+#pragma unroll
+      for (int a = 0; a < M; ++a) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) s += ld1(in.B, e * N * M + i + a * N) * g[i];
+        h[a] = ld1(in.r, e * M + a) + s;
+      }
+      double Gf[M * M], kk[M];
+#pragma unroll
+      for (int i = 0; i < M * M; ++i) Gf[i] = lds(Z::oG(T) + e * M * M + i);
+#pragma unroll
+      for (int a = 0; a < M; ++a) kk[a] = h[a];
+      chol_solve<M, 1>(Gf, kk);
+#pragma unroll
+      for (int a = 0; a < M; ++a) {
+        kk[a] *= -1.0;
+        kst[(e * M + a) * L_] = kk[a];
+      }
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) s += ld1(in.A, e * N * N + i + j * N) * g[i];
+        double w2 = 0.0;
+#pragma unroll
+        for (int a = 0; a < M; ++a) w2 += lds(Z::oK(T) + e * M * N + a + j * M) * h[a];
+        v[j] += s;
+        v[j] += w2;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) vst[(node * N + i) * L_] = v[i];
+  }
+
+  auto f_inv_mult = [&](const double (&Ff)[N * N], const double (&sd)[N], const double (&sdi)[N],
+                        const double (&rhs)[N], double (&res)[N]) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) res[i] = sdi[i] * rhs[i];
+    chol_solve<N, 1>(Ff, res);
+#pragma unroll
+    for (int i = 0; i < N; ++i) res[i] *= sd[i];
+  };
+  // x, y of `node` from the right-hand side f (negate = the root's sign, :812-819)
+  auto close_node = [&](size_t node, const double (&f)[N], const double (&vn)[N], bool negate) {
+    double Ff[N * N], sd[N], sdi[N], x[N];
+#pragma unroll
+    for (int i = 0; i < N * N; ++i) Ff[i] = lds(Z::oF(T) + node * N * N + i);
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      sd[i] = lds(Z::oSd(T) + node * N + i);
+      sdi[i] = lds(Z::oSdi(T) + node * N + i);
+    }
+    f_inv_mult(Ff, sd, sdi, f, x);
+    if (negate) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) x[i] *= -1.0;
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < N; ++j) s += lds(Z::oV(T) + node * N * N + i + j * N) * x[j];
+      out.x[(node * N + i) * L_ + b] = x[i];
+      out.y[(node * N + i) * L_ + b] = vn[i] + s;
+    }
+  };
+  {  // root
+    const size_t root = t.preorder[0];
+    double f[N], vr[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      vr[i] = vst[(root * N + i) * L_];
+      f[i] = ld1(in.delta, root * N + i) * vr[i] - ld1(in.c, root * N + i);
+    }
+    close_node(root, f, vr, true);
+  }
+  // forward rollout (:821-870)
+  for (int order = 0; order < t.N; ++order) {
+    const size_t node = t.preorder[order];
+    double x[N];
+    bool have_x = false;
+    for (int ci = t.child_offsets[node]; ci < t.child_offsets[node + 1]; ++ci) {
+      const size_t e = t.child_edges[ci], child = t.children[e];
+      if (!have_x) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) x[i] = out.x[(node * N + i) * L_ + b];
+        have_x = true;
+      }
+      double u[M], f[N], vch[N];
+#pragma unroll
+      for (int a = 0; a < M; ++a) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < N; ++j) s += lds(Z::oK(T) + e * M * N + a + j * M) * x[j];
+        u[a] = kst[(e * M + a) * L_] + s;
+        out.u[(e * M + a) * L_ + b] = u[a];
+      }
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        vch[i] = vst[(child * N + i) * L_];
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < N; ++j) s += ld1(in.A, e * N * N + i + j * N) * x[j];
+        double w2 = 0.0;
+#pragma unroll
+        for (int a = 0; a < M; ++a) w2 += ld1(in.B, e * N * M + i + a * N) * u[a];
+        double fi = ld1(in.c, child * N + i) - ld1(in.delta, child * N + i) * vch[i];
+        fi += s;
+        fi += w2;
+        f[i] = fi;
+      }
+      close_node(child, f, vch, false);
+    }
+  }
+}
+
 template <int N, int M>
 struct StrictPlan {
   static int64_t store_elems(int T) { return StrictSizes<N, M>::store(T); }
@@ -581,6 +896,22 @@ struct StrictPlan {
     return 1;
   }
   static int factor_solve(const FastArgs &a, cudaStream_t s) { return factor(a, s) + solve(a, s); }
+  // trees (FastArgs::tables carries the topology)
+  static int factor_tree(const FastArgs &a, cudaStream_t s) {
+    ProfScope ps(a.prof, "strict_factor_tree", s);
+    strict_factor_tree<N, M><<<static_cast<unsigned>((a.batch + 31) / 32), 32, 0, s>>>(
+        *a.tables, a.in, a.status, a.store, a.batch, a.ld);
+    return 1;
+  }
+  static int solve_tree(const FastArgs &a, cudaStream_t s) {
+    ProfScope ps(a.prof, "strict_solve_tree", s);
+    strict_solve_tree<N, M><<<static_cast<unsigned>((a.batch + 31) / 32), 32, 0, s>>>(
+        *a.tables, a.in, a.out, a.store, a.scratch, a.batch, a.ld);
+    return 1;
+  }
+  static int factor_solve_tree(const FastArgs &a, cudaStream_t s) {
+    return factor_tree(a, s) + solve_tree(a, s);
+  }
 };
 
 template <int N, int M>
@@ -589,6 +920,15 @@ const FastPlan *make_strict_plan(const char *name) {
   static const FastPlan plan{name,         N,           M,         &P::store_elems,
                              &P::scratch_elems, &P::factor, &P::solve, &P::factor_solve,
                              nullptr, false};
+  return &plan;
+}
+
+template <int N, int M>
+const FastPlan *make_strict_tree_plan(const char *name) {
+  using P = StrictPlan<N, M>;
+  static const FastPlan plan{name,         N,           M,         &P::store_elems,
+                             &P::scratch_elems, &P::factor_tree, &P::solve_tree,
+                             &P::factor_solve_tree, nullptr, false};
   return &plan;
 }
 
@@ -602,6 +942,16 @@ const FastPlan *select_strict_plan(int n, int m) {
   if (n <= 4 && m <= 4) return make_strict_plan<4, 4>("strict_thread_n4_m4");
   if (n <= 5 && m <= 3) return make_strict_plan<5, 3>("strict_thread_n5_m3");
   if (n <= 6 && m <= 3) return make_strict_plan<6, 3>("strict_thread_n6_m3");
+  return nullptr;
+}
+
+// The same shapes on trees.
+const FastPlan *select_strict_tree_plan(int n, int m) {
+  if (n <= 2 && m <= 1) return make_strict_tree_plan<2, 1>("strict_tree_n2_m1");
+  if (n <= 3 && m <= 2) return make_strict_tree_plan<3, 2>("strict_tree_n3_m2");
+  if (n <= 4 && m <= 2) return make_strict_tree_plan<4, 2>("strict_tree_n4_m2");
+  if (n <= 4 && m <= 4) return make_strict_tree_plan<4, 4>("strict_tree_n4_m4");
+  if (n <= 5 && m <= 3) return make_strict_tree_plan<5, 3>("strict_tree_n5_m3");
   return nullptr;
 }
 

@@ -274,18 +274,18 @@ def test_variable_dimension_chain_and_tree_batches():
             gpu, lqr = gpu_lqr_factor_solve(s, host, fused=fused)
             # chains with per-stage dims: reference-order register kernels on the padded
             # chain; trees: the generic kernels
-            want = "padded_to_strict_thread_n3_m2" if s is chain else "generic_thread_per_problem"
+            want = "padded_to_strict_thread_n3_m2" if s is chain else "padded_to_strict_tree_n4_m4"
             assert lqr.engine.kernel_variant == want, lqr.engine.kernel_variant
             assert (gpu["status"] == 0).all()
             assert_lqr_parity(gpu, ref, 1e-11)
             assert gpu["residual"].max() < 1e-10
-            if s is chain:
-                # ... which perform, on the real entries, the generic kernels' operations in
-                # the same order (only the compiler's FMA contraction may differ)
-                gen, _ = gpu_lqr_factor_solve(s, host, fused=fused, force_generic=True)
-                assert_lqr_parity(gpu, gen, 1e-13)
+            # ... which perform, on the real entries, the generic kernels' operations in
+            # the same order (only the compiler's FMA contraction may differ)
+            gen, lg = gpu_lqr_factor_solve(s, host, fused=fused, force_generic=True)
+            assert lg.engine.kernel_variant == "generic_thread_per_problem"
+            assert_lqr_parity(gpu, gen, 1e-13)
     # SIPOC_FLAG_PAD_VARIABLE_DIMS: the variable-dim chain on the (6, 2) sub-warp kernels
-    # through decoupled padding; trees stay on the generic kernels.
+    # through decoupled padding; trees keep their reference-order kernels.
     host = pg.variable_tree_batch(chain, 45, seed=11)
     ref = pyoracle.lqr_factor_solve(chain, host)
     for fused in (True, False):
@@ -300,7 +300,7 @@ def test_variable_dimension_chain_and_tree_batches():
     assert gpu["status"][7] == 1 and (np.delete(gpu["status"], 7) == 0).all()
     gpu, lqr = gpu_lqr_factor_solve(tree, pg.variable_tree_batch(tree, 5, seed=1),
                                     pad_variable_dims=True)
-    assert "generic" in lqr.engine.kernel_variant
+    assert lqr.engine.kernel_variant == "padded_to_strict_tree_n4_m4"  # the flag is for chains
 
 
 @pytest.mark.parametrize("shape", ["heterogeneous_chain", "shallow_wide_tree", "binary_tree"])
