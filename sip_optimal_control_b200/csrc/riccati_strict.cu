@@ -57,7 +57,8 @@ struct StrictSizes {
 };
 
 // Unblocked left-looking lower Cholesky, column-major n x n in registers (chol_lower of
-// generic_kernels.cu, Eigen LLT semantics: a pivot <= 0 fails).
+// generic_kernels.cu, Eigen LLT semantics: a pivot <= 0 fails).  On return the strict lower
+// triangle holds L and the diagonal holds 1 / L(k, k).
 template <int n>
 __device__ __forceinline__ bool chol_lower(double (&a)[n * n]) {
   bool ok = true;
@@ -71,8 +72,12 @@ __device__ __forceinline__ bool chol_lower(double (&a)[n * n]) {
     }
     ok = ok && (x > 0.0);
     x = sqrt(x);
-    a[k + k * n] = x;
-    const double rx = 1.0 / x;  // one division per pivot; the column is scaled by its reciprocal
+    // One division per pivot: the column is scaled by the reciprocal, and the reciprocal --
+    // not the pivot -- is what is kept on the diagonal (the diagonal of a factor is only
+    // ever divided by, here and in chol_solve; the kept factorization is private to
+    // these kernels).
+    const double rx = 1.0 / x;
+    a[k + k * n] = rx;
 #pragma unroll
     for (int i = k + 1; i < n; ++i) {
       double s = a[i + k * n];
@@ -84,15 +89,13 @@ __device__ __forceinline__ bool chol_lower(double (&a)[n * n]) {
   return ok;
 }
 
-// L X = B, then L' X = B, in place, column by column (chol_solve of generic_kernels.cu).
+// L X = B, then L' X = B, in place, column by column (chol_solve of generic_kernels.cu);
+// `l` as chol_lower leaves it (reciprocal diagonal).
 template <int n, int nrhs>
 __device__ __forceinline__ void chol_solve(const double (&l)[n * n], double (&b)[n * nrhs]) {
   // The 2 n nrhs divisions by the n diagonal entries are multiplications by their
-  // reciprocals (the one place these kernels depart from the generic kernels' operations:
-  // at most an ulp per quotient).
-  double rl[n];
-#pragma unroll
-  for (int i = 0; i < n; ++i) rl[i] = 1.0 / l[i + i * n];
+  // reciprocals, which chol_lower left on the diagonal (the one place these kernels
+  // depart from the generic kernels' operations: at most an ulp per quotient).
 #pragma unroll
   for (int c = 0; c < nrhs; ++c) {
 #pragma unroll
@@ -100,14 +103,14 @@ __device__ __forceinline__ void chol_solve(const double (&l)[n * n], double (&b)
       double s = b[c * n + i];
 #pragma unroll
       for (int j = 0; j < i; ++j) s -= l[i + j * n] * b[c * n + j];
-      b[c * n + i] = s * rl[i];
+      b[c * n + i] = s * l[i + i * n];
     }
 #pragma unroll
     for (int i = n - 1; i >= 0; --i) {
       double s = b[c * n + i];
 #pragma unroll
       for (int j = i + 1; j < n; ++j) s -= l[j + i * n] * b[c * n + j];
-      b[c * n + i] = s * rl[i];
+      b[c * n + i] = s * l[i + i * n];
     }
   }
 }
