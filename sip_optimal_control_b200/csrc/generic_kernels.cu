@@ -653,6 +653,7 @@ kkt_recover_kernel(DevTables t, KktModel mdl, KktWs ws, const double *bvec, doub
 // y += K x (helpers.cpp:953-1368, theta == 0), output-driven: thread (b, node)
 // produces every row of y whose block belongs to `node` or to one of its child
 // edges, so no two threads write the same element.
+template <bool ALL>  // ALL: the whole operator, the block mask folds away at compile time
 __global__ void __launch_bounds__(kThreads)
 kkt_apply_kernel(DevTables t, KktModel mdl, const double *w, const double *r1,
                  const double *r2, const double *r3, const double *in_x, const double *in_y,
@@ -664,8 +665,8 @@ kkt_apply_kernel(DevTables t, KktModel mdl, const double *w, const double *r1,
   if (b >= batch) return;
   const int node = blockIdx.y;
   const size_t L = static_cast<size_t>(ld);
-  const bool pH = parts & kKktH, pC = parts & kKktC, pCT = parts & kKktCT, pG = parts & kKktG,
-             pGT = parts & kKktGT, pR = parts & kKktReg;
+  const bool pH = ALL || (parts & kKktH), pC = ALL || (parts & kKktC), pCT = ALL || (parts & kKktCT),
+             pG = ALL || (parts & kKktG), pGT = ALL || (parts & kKktGT), pR = ALL || (parts & kKktReg);
   GCVec W{w + b, L}, R1{r1 + b, L}, R2{r2 + b, L}, R3{r3 + b, L};
   GCVec X{in_x + b, L}, Y{in_y + b, L}, Z{in_z + b, L};
   GCVec nh{mdl.node_hxx + b, L}, njc{mdl.node_jc + b, L}, njg{mdl.node_jg + b, L};
@@ -1015,7 +1016,7 @@ void launch_kkt_apply(const DevTables &t, const KktModel &m, const double *w,
                       cudaStream_t s) {
   // the whole operator on [x | y | z] vectors
   const size_t oy = static_cast<size_t>(t.x_dim) * ld, oz = oy + static_cast<size_t>(t.y_dim) * ld;
-  kkt_apply_kernel<<<batch_grid(batch, t.N), kThreads, 0, s>>>(
+  kkt_apply_kernel<true><<<batch_grid(batch, t.N), kThreads, 0, s>>>(
       t, m, w, r1, r2, r3, x, x + oy, x + oz, y, y + oy, y + oz, kKktAll, batch, ld);
 }
 
@@ -1024,7 +1025,7 @@ void launch_kkt_apply_parts(const DevTables &t, const KktModel &m, unsigned part
                             double *out_x, double *out_y, double *out_z, int64_t batch,
                             int64_t ld, cudaStream_t s) {
   // component blocks only (no regularization): the weight pointers are never read
-  kkt_apply_kernel<<<batch_grid(batch, t.N), kThreads, 0, s>>>(
+  kkt_apply_kernel<false><<<batch_grid(batch, t.N), kThreads, 0, s>>>(
       t, m, nullptr, nullptr, nullptr, nullptr, in_x, in_y, in_z, out_x, out_y, out_z,
       parts & ~kKktReg, batch, ld);
 }
