@@ -808,7 +808,17 @@ kkt_residual_kernel(DevTables t, const double *Ksol, const double *bvec, const i
     failed = ok != nullptr && ok[b] == 0;
     if (!failed) {
       const size_t L = static_cast<size_t>(ld);
-      for (int i = 0; i < t.kkt_dim; ++i) {
+      // eight rows (sixteen loads) in flight: one thread per problem cannot hide the load
+      // latency by occupancy at Newton-KKT batch sizes
+      int i = 0;
+      for (; i + 8 <= t.kkt_dim; i += 8) {
+        double d[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) d[u] = Ksol[(i + u) * L + b] - bvec[(i + u) * L + b];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) sq += d[u] * d[u];
+      }
+      for (; i < t.kkt_dim; ++i) {
         const double d = Ksol[i * L + b] - bvec[i * L + b];
         sq += d * d;
       }
