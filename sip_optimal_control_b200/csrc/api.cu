@@ -346,6 +346,7 @@ bool native_pm(const sipoc_engine *e, const LqrIn &in, bool layout_pm) {
 sipoc_error lqr_factor_core(sipoc_engine *e, const LqrIn &caller_in, int *status, cudaStream_t s,
                             bool layout_pm = false) {
   sipoc_error rc;
+  e->kkt_factored = false;  // a new LQR factorization replaces the one a KKT solve would use
   LqrIn in, pm;
   if ((rc = resolve_inputs(e, caller_in, layout_pm, kPmMatrices, &in, &pm, s)) != SIPOC_OK)
     return rc;
@@ -369,21 +370,26 @@ sipoc_error lqr_factor_core(sipoc_engine *e, const LqrIn &caller_in, int *status
   return check_launch(e, "lqr_factor");
 }
 
+// matrices_kept: A, B, delta are the arrays the factorization was given (the Newton-KKT
+// solve right after its own factor): their problem-major / padded copies are still valid
+// and only q, r, c are refreshed.
+constexpr unsigned kPmVectors = 0b010011000;  // q r c
 sipoc_error lqr_solve_core(sipoc_engine *e, const LqrIn &caller_in, const LqrOut &out,
-                           cudaStream_t s, bool layout_pm = false) {
+                           cudaStream_t s, bool layout_pm = false, bool matrices_kept = false) {
   sipoc_error rc;
   if (e->factored == sipoc_engine::Factored::NONE)
     return fail(e, SIPOC_NOT_FACTORED, "solve called before a factor on this handle");
   if (e->factored == sipoc_engine::Factored::FAST && !aligned16(caller_in))
     return fail(e, SIPOC_INVALID_ARGUMENT,
                 "solve against a fast-path factorization needs 16-byte aligned arrays");
+  const unsigned mask = matrices_kept ? kPmVectors : kPmSolve;
   LqrIn in, pm;
-  if ((rc = resolve_inputs(e, caller_in, layout_pm, kPmSolve, &in, &pm, s)) != SIPOC_OK) return rc;
+  if ((rc = resolve_inputs(e, caller_in, layout_pm, mask, &in, &pm, s)) != SIPOC_OK) return rc;
   if (e->factored == sipoc_engine::Factored::FAST) {
     if ((rc = ensure_fast_scratch(e)) != SIPOC_OK) return rc;
     LqrOut plan_out = out;
     if (e->padded) {
-      if ((rc = pad_inputs(e, &in, kPmSolve, s)) != SIPOC_OK) return rc;
+      if ((rc = pad_inputs(e, &in, mask, s)) != SIPOC_OK) return rc;
       if ((rc = padded_outputs(e, &plan_out)) != SIPOC_OK) return rc;
     }
     FastArgs a{in, pm, plan_out, nullptr, e->fast_store, e->fast_scratch, e->batch, e->ld,
@@ -404,6 +410,7 @@ sipoc_error lqr_solve_core(sipoc_engine *e, const LqrIn &caller_in, const LqrOut
 sipoc_error lqr_factor_solve_core(sipoc_engine *e, const LqrIn &caller_in, const LqrOut &out,
                                   int *status, cudaStream_t s, bool layout_pm = false) {
   sipoc_error rc;
+  e->kkt_factored = false;
   LqrIn in, pm;
   if ((rc = resolve_inputs(e, caller_in, layout_pm, kPmAll, &in, &pm, s)) != SIPOC_OK) return rc;
   if (native_pm(e, caller_in, layout_pm) || use_fast(e, in)) {
@@ -619,7 +626,7 @@ sipoc_error kkt_solve_core(sipoc_engine *e, const KktModel &mdl, const double *b
   LqrIn in{e->kws.Q_mod, e->kws.M_mod, e->kws.R_mod, e->kws.q_mod, e->kws.r_mod,
            mdl.edge_A,   mdl.edge_B,   e->kws.c_mod, e->kws.dyn_r2};
   LqrOut out{e->kws.x, e->kws.u, e->kws.y};
-  if ((rc = lqr_solve_core(e, in, out, s)) != SIPOC_OK) return rc;
+  if ((rc = lqr_solve_core(e, in, out, s, false, /*matrices_kept=*/true)) != SIPOC_OK) return rc;
   {
     ProfScope ps(&e->prof, "kkt_recover_kernel", s);
     launch_kkt_recover(e->dt, mdl, e->kws, b, sol, e->batch, e->ld, s);
