@@ -324,6 +324,14 @@ def test_reference_variable_benchmark_shapes(shape, num_edges, base_n):
         assert (gpu["status"] == 0).all()
         assert_lqr_parity(gpu, ref, REL_TOL)
         assert gpu["residual"].max() < 1e-9
+    if shape == "heterogeneous_chain" and base_n == 8:
+        # dims up to (9, 3): too large for the reference-order shapes (generic kernels above);
+        # SIPOC_FLAG_PAD_VARIABLE_DIMS pads the chain to the (12, 4) sub-warp kernels
+        gpu, lqr = gpu_lqr_factor_solve(s, host, pad_variable_dims=True)
+        assert lqr.engine.kernel_variant == "padded_to_subwarp4_n12_m4"
+        assert (gpu["status"] == 0).all()
+        assert_lqr_parity(gpu, ref, REL_TOL)
+        assert gpu["residual"].max() < 1e-9
 
 
 def test_host_buffer_entry_points():
