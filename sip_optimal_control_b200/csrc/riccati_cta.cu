@@ -481,6 +481,7 @@ __device__ void cta_inverse_from_factor(double *A, int ld, double *scratch, doub
         const double *pa[2], *pb[2];
         double *dst[2];
         bool live[2];
+        int klim[2];  // k range: sz, or the rows the (shorter) last second block really has
 #pragma unroll
         for (int z = 0; z < 2; ++z) {
           const int unit = u0 + z * kWarps;
@@ -488,6 +489,7 @@ __device__ void cta_inverse_from_factor(double *A, int ld, double *scratch, doub
           const int ti = w >> lt, tj = w & (tc - 1);
           const int c0 = 2 * q * sz, r0 = c0 + sz;
           live[z] = unit < total && r0 + (ti << 3) < n;
+          klim[z] = (pass == 1 && n - r0 < sz) ? n - r0 : sz;
           double *tq = tbuf + (q * sz) * ld;  // T of pair q: (rows of L21) x sz
           if (pass == 0) {  // T = L21 X11
             pa[z] = A + (c0 + t) * ld + r0 + (ti << 3) + g;
@@ -504,7 +506,7 @@ __device__ void cta_inverse_from_factor(double *A, int ld, double *scratch, doub
         for (int k0 = 0; k0 < sz; k0 += 8) {
 #pragma unroll
           for (int z = 0; z < 2; ++z) {
-            if (live[z]) {
+            if (live[z] && k0 < klim[z]) {  // (klim is a multiple of 8)
               const double a0 = pa[z][k0 * ld], a1 = pa[z][(k0 + 4) * ld];
               const double b0 = pb[z][k0], b1 = pb[z][k0 + 4];
               dmma(acc[z][0], a0, b0);
@@ -907,7 +909,7 @@ riccati_backward_cta(LqrIn pm, int *status_out, double *store, double *scratch, 
     const bool g_ok = __syncthreads_and(g_chol_ok);
     TICK(5);
     // G^-1 (full, in Puu) from its factor.
-    cta_inverse_from_factor<MP>(Puu, LDM, Gs, Sb, Dd, true);
+    cta_inverse_from_factor<(M + 7) / 8 * 8>(Puu, LDM, Gs, Sb, Dd, true);  // the live part: the padding block stays I
     if (!g_ok && status == SIPOC_FACTOR_SUCCESS) status = SIPOC_FACTOR_G_FACTORIZATION_FAILURE;
     TICK(6);
     // K = -G^-1 Psi_ux
