@@ -172,11 +172,20 @@ def cpu_time_sample(wl, sample, nthreads, repeats=1, host=None):
     return out["seconds"], host
 
 
+def host_threads():
+    """All the host threads this process may use.  Not omp_get_max_threads(): torchrun exports
+    OMP_NUM_THREADS=1 to every rank, which would leave the CPU arm on one core at N > 1."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_baseline(wl, target_seconds=10.0):
     """Oracle (port of the reference) across all host cores on a bounded sample."""
     from oracle import pyoracle
 
-    cores = pyoracle.max_threads()
+    cores = host_threads()
     sample = max(cores * 8, 64)
     _, host = cpu_time_sample(wl, sample, cores)  # warm-up: page in, spin up the threads
     total, reps = 0.0, 0
@@ -197,7 +206,7 @@ def run_reference(args, wl, name):
         return 0
     from oracle import pyoracle
 
-    cores = pyoracle.max_threads()
+    cores = host_threads()
     sample = max(cores * 4, 64)
     _, host = cpu_time_sample(wl, sample, cores)
     secs, _ = cpu_time_sample(wl, sample, cores, host=host)
@@ -258,9 +267,22 @@ def run_ours(args, wl, name):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL's banner ("NCCL version ...") belongs on stderr: stdout carries the JSON line.
+        # NCCL's banner ("NCCL version ...") belongs on stderr: stdout carries the JSON line and
+        # nothing else.  NCCL_DEBUG_FILE does not catch it on every build, so file descriptor 1
+        # points at stderr while the communicator comes up (init + the first collective).
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(4, dtype=torch.float64, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     assert world == args.gpus, (world, args.gpus)
 
     from sip_optimal_control_b200.sharding import shard_range
