@@ -10,32 +10,25 @@
 
 namespace sip::optimal_control {
 
+// Model outputs of one node: value, gradient, equality / inequality residuals with their
+// state Jacobians (column-major, rows = constraints), and the Lagrangian Hessian block.
 struct NodeModelCallbackOutput {  // types.hpp:48-61 without the theta blocks
   double f;
-  double *df_dx;
-  double *c;
-  double *dc_dx;
-  double *g;
-  double *dg_dx;
-  double *d2L_dx2;
+  double *df_dx;                 // [n]
+  double *c, *dc_dx;             // [c], [c x n]
+  double *g, *dg_dx;             // [g], [g x n]
+  double *d2L_dx2;               // [n x n]
 };
 
+// Model outputs of one edge (parent state x, control u, child state): as above plus the
+// dynamics residual and its Jacobians (rows = child state) and the x-u / u-u Hessian blocks.
 struct EdgeModelCallbackOutput {  // types.hpp:66-89 without the theta blocks
   double f;
-  double *df_dx;
-  double *df_du;
-  double *dyn_res;
-  double *ddyn_dx;
-  double *ddyn_du;
-  double *c;
-  double *dc_dx;
-  double *dc_du;
-  double *g;
-  double *dg_dx;
-  double *dg_du;
-  double *d2L_dx2;
-  double *d2L_dxdu;
-  double *d2L_du2;
+  double *df_dx, *df_du;                      // [n_parent], [m]
+  double *dyn_res, *ddyn_dx, *ddyn_du;        // [n_child], [n_child x n_parent], [n_child x m]
+  double *c, *dc_dx, *dc_du;                  // [c], [c x n_parent], [c x m]
+  double *g, *dg_dx, *dg_du;                  // [g], [g x n_parent], [g x m]
+  double *d2L_dx2, *d2L_dxdu, *d2L_du2;       // [n_parent x n_parent], [n_parent x m], [m x m]
 };
 
 struct ModelCallbackOutput {  // types.hpp:91-126
