@@ -797,38 +797,61 @@ kkt_apply_kernel(DevTables t, KktModel mdl, const double *w, const double *r1,
 }
 
 // ||Ksol - b||_2 per problem (tests/variable_dimensions_test.cpp:167-180).
-__global__ void __launch_bounds__(kThreads)
+// One CTA = 32 problems x kResidualSlices row slices: slice s sums rows s, s + S, s + 2S, ...
+// of its problem (every load 256 B coalesced over the 32 problems), the partial sums meet in
+// shared memory and are added in slice order, so the result does not depend on scheduling.
+// One thread per problem cannot hide the load latency by occupancy at Newton-KKT batch sizes.
+constexpr int kResidualSlices = 8;
+
+__global__ void __launch_bounds__(32 * kResidualSlices)
 kkt_residual_kernel(DevTables t, const double *Ksol, const double *bvec, const int *ok,
                     double *residual_norm, double *stats, int64_t batch, int64_t ld) {
-  const int64_t b = problem_index();
+  __shared__ double part[kResidualSlices][32];
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int64_t b = static_cast<int64_t>(blockIdx.x) * 32 + lane;
   const bool active = b < batch;
+  const bool failed = active && ok != nullptr && ok[b] == 0;
   double sq = 0.0;
-  bool failed = false;
-  if (active) {
-    failed = ok != nullptr && ok[b] == 0;
-    if (!failed) {
-      const size_t L = static_cast<size_t>(ld);
-      // eight rows (sixteen loads) in flight: one thread per problem cannot hide the load
-      // latency by occupancy at Newton-KKT batch sizes
-      int i = 0;
-      for (; i + 8 <= t.kkt_dim; i += 8) {
-        double d[8];
+  if (active && !failed) {
+    const size_t L = static_cast<size_t>(ld);
+    constexpr int S = kResidualSlices;
+    int i = slice;
+    for (; i + 3 * S < t.kkt_dim; i += 4 * S) {  // four rows (eight loads) in flight
+      double d[4];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) d[u] = Ksol[(i + u) * L + b] - bvec[(i + u) * L + b];
+      for (int u = 0; u < 4; ++u) d[u] = Ksol[(i + u * S) * L + b] - bvec[(i + u * S) * L + b];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) sq += d[u] * d[u];
-      }
-      for (; i < t.kkt_dim; ++i) {
-        const double d = Ksol[i * L + b] - bvec[i * L + b];
-        sq += d * d;
-      }
+      for (int u = 0; u < 4; ++u) sq += d[u] * d[u];
     }
-    if (residual_norm != nullptr) residual_norm[b] = failed ? -1.0 : sqrt(sq);
+    for (; i < t.kkt_dim; i += S) {
+      const double d = Ksol[i * L + b] - bvec[i * L + b];
+      sq += d * d;
+    }
   }
-  if (stats != nullptr) {
-    const bool good = active && !failed;
-    accumulate_stats(good ? sq : 0.0, good ? sqrt(sq) : 0.0,
-                     (active && failed) ? 1.0 : 0.0, active ? 1.0 : 0.0, stats);
+  part[slice][lane] = sq;
+  __syncthreads();
+  if (slice != 0) return;
+  sq = part[0][lane];
+#pragma unroll
+  for (int s = 1; s < kResidualSlices; ++s) sq += part[s][lane];
+  if (active && residual_norm != nullptr) residual_norm[b] = failed ? -1.0 : sqrt(sq);
+  if (stats == nullptr) return;
+  const bool good = active && !failed;
+  double mx = good ? sqrt(sq) : 0.0, nfail = failed ? 1.0 : 0.0, cnt = active ? 1.0 : 0.0;
+  if (!good) sq = 0.0;
+  for (int o = 16; o > 0; o >>= 1) {
+    sq += __shfl_down_sync(0xffffffffu, sq, o);
+    mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, o));
+    nfail += __shfl_down_sync(0xffffffffu, nfail, o);
+    cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+  }
+  if (lane == 0) {
+    atomicAdd(stats + 0, sq);
+    // Non-negative doubles order like their bit patterns.
+    atomicMax(reinterpret_cast<unsigned long long *>(stats + 1),
+              static_cast<unsigned long long>(__double_as_longlong(mx)));
+    atomicAdd(stats + 2, nfail);
+    atomicAdd(stats + 3, cnt);
   }
 }
 
@@ -1044,8 +1067,9 @@ void launch_kkt_residual(const DevTables &t, const double *Ksol, const double *b
                          const int *ok, double *residual_norm, double *stats,
                          int64_t batch, int64_t ld, cudaStream_t s) {
   if (stats != nullptr) zero_stats_kernel<<<1, 32, 0, s>>>(stats);
-  kkt_residual_kernel<<<batch_grid(batch), kThreads, 0, s>>>(t, Ksol, b, ok, residual_norm,
-                                                             stats, batch, ld);
+  const unsigned grid = static_cast<unsigned>((batch + 31) / 32);
+  kkt_residual_kernel<<<grid, 32 * kResidualSlices, 0, s>>>(t, Ksol, b, ok, residual_norm, stats,
+                                                            batch, ld);
 }
 
 void launch_pack(const double *src, double *dst, int64_t size, int64_t batch, int64_t ld,
