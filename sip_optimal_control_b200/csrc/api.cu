@@ -29,6 +29,7 @@ struct sipoc_engine {
   int64_t batch = 0, ld = 0;
   const FastPlan *fast = nullptr;
   KktReduceFn kkt_reduce_fast = nullptr;
+  KktApplyFn kkt_apply_fast = nullptr;
   int kkt_max_rows = 0;
   std::string variant;
   std::string last_error;
@@ -724,6 +725,7 @@ sipoc_error sipoc_create(const sipoc_structure *s, sipoc_engine **out) {
   }
   if (!(e->flags & SIPOC_FLAG_FORCE_GENERIC) && h.is_chain && h.is_uniform && h.E >= 1) {
     e->kkt_reduce_fast = select_kkt_reduce(h.n[0], h.m[0]);
+    e->kkt_apply_fast = select_kkt_apply(h.n[0], h.m[0]);
     for (int i = 0; i < h.N; ++i) {
       int rows = h.node_c[i] + h.node_g[i];
       if (i < h.E) rows += h.edge_c[i] + h.edge_g[i];
@@ -1088,8 +1090,9 @@ sipoc_error sipoc_kkt_apply(sipoc_engine *e, const sipoc_kkt_model *model, const
   if (model_has_null(model) || !w || !r1 || !r2 || !r3 || !x || !y)
     return fail(e, SIPOC_INVALID_ARGUMENT, "NULL KKT apply argument");
   DeviceGuard guard(e->device);
-  launch_kkt_apply(e->dt, to_model(model), w, r1, r2, r3, x, y, e->batch, e->ld,
-                   static_cast<cudaStream_t>(stream));
+  (e->kkt_apply_fast != nullptr ? e->kkt_apply_fast : &launch_kkt_apply)(
+      e->dt, to_model(model), w, r1, r2, r3, x, y, e->batch, e->ld,
+      static_cast<cudaStream_t>(stream));
   e->launches += 1;
   return check_launch(e, "kkt_apply");
 }
@@ -1159,8 +1162,8 @@ sipoc_error sipoc_kkt_residual(sipoc_engine *e, const sipoc_kkt_model *model, co
                                 s));
   {
     ProfScope ps(&e->prof, "kkt_apply_kernel", s);
-    launch_kkt_apply(e->dt, to_model(model), w, r1, r2, r3, sol, e->kkt_product, e->batch,
-                     e->ld, s);
+    (e->kkt_apply_fast != nullptr ? e->kkt_apply_fast : &launch_kkt_apply)(
+        e->dt, to_model(model), w, r1, r2, r3, sol, e->kkt_product, e->batch, e->ld, s);
   }
   {
     ProfScope ps(&e->prof, "kkt_residual_kernel", s);
@@ -1233,8 +1236,9 @@ sipoc_error sipoc_kkt_apply_host(sipoc_engine *e, const double *w, const double 
     if ((rc = upload(e, reg[i], e->hk_reg[i], reg_sizes[i])) != SIPOC_OK) return rc;
   if ((rc = upload(e, x, e->hk_vec[0], e->hs.kkt_dim)) != SIPOC_OK) return rc;
   if ((rc = upload(e, y, e->hk_vec[1], e->hs.kkt_dim)) != SIPOC_OK) return rc;
-  launch_kkt_apply(e->dt, host_resident_model(e), e->hk_reg[0], e->hk_reg[1], e->hk_reg[2],
-                   e->hk_reg[3], e->hk_vec[0], e->hk_vec[1], e->batch, e->ld, e->host_stream);
+  (e->kkt_apply_fast != nullptr ? e->kkt_apply_fast : &launch_kkt_apply)(
+      e->dt, host_resident_model(e), e->hk_reg[0], e->hk_reg[1], e->hk_reg[2], e->hk_reg[3],
+      e->hk_vec[0], e->hk_vec[1], e->batch, e->ld, e->host_stream);
   e->launches += 1;
   if ((rc = check_launch(e, "kkt_apply")) != SIPOC_OK) return rc;
   if ((rc = download(e, e->hk_vec[1], y, e->hs.kkt_dim)) != SIPOC_OK) return rc;

@@ -181,7 +181,203 @@ void launch(const DevTables &t, const KktModel &m, const double *w, const double
   kkt_reduce_chain<N, M><<<grid, 32 * (N + M), smem, s>>>(t, m, w, r1, r2, r3, ws, ok, batch, ld);
 }
 
+
+// y += K x for uniform chains (helpers.cpp:953-1368, theta == 0): thread (problem, node)
+// owns the rows of the node's state, of its child edge's control, of the node / edge
+// constraints and of the CHILD's dynamics, so that every model block of the node and of
+// its child edge is read exactly once: each Jacobian / dynamics entry feeds both its C x
+// (or G x) row and its C' y (or G' z) column while it is in a register, the cross Hessian
+// feeds the state and the control rows.  x, u, the child's costate and the accumulators
+// live in registers (the generic kernel re-reads the vectors per row and every
+// off-diagonal block twice: 6.5 GB of DRAM reads per launch against 2.6 GB here at
+// n = 12, m = 4, c = 6, g = 8, batch 8 192).  The sums run in a different order than the
+// reference's row loops; the operator is a residual check, not part of the solve.
+template <int N, int M>
+__global__ void __launch_bounds__(128)
+kkt_apply_chain(DevTables t, KktModel mdl, const double *__restrict__ w,
+                const double *__restrict__ r1, const double *__restrict__ r2,
+                const double *__restrict__ r3, const double *__restrict__ in,
+                double *__restrict__ out, int64_t batch, int64_t ld) {
+  const int64_t b = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  const int node = blockIdx.y;
+  const bool has_edge = node < t.E;
+  const int e = node, child = node + 1;  // chain: edge k joins node k to node k + 1
+  const size_t L = static_cast<size_t>(ld);
+  const size_t oy = static_cast<size_t>(t.x_dim), oz = oy + static_cast<size_t>(t.y_dim);
+#define LD(ptr, off) __ldg((ptr) + static_cast<size_t>(off) * L + b)
+#define ACC(off, v) out[static_cast<size_t>(off) * L + b] += (v)
+
+  const int xs = t.x_state[node];
+  double x[N], sx[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    x[i] = LD(in, xs + i);
+    sx[i] = LD(r1, xs + i) * x[i] - LD(in, oy + t.y_dyn[node] + i);  // R1 x, -I' y_dyn
+  }
+  if (node == 0) {  // root row of C: -x_root - R2 y
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const int o = t.y_dyn[0] + i;
+      ACC(oy + o, -x[i] - LD(r2, o) * LD(in, oy + o));
+    }
+  }
+  {  // node Hessian
+    const int ho = t.nn_off[node];
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+      for (int i = 0; i < N; ++i) sx[i] += LD(mdl.node_hxx, ho + i + j * N) * x[j];
+  }
+  {  // node constraints: rows of C / G and columns of C' / G' from one read
+    const int c = t.node_c[node], g = t.node_g[node];
+    const int jo = t.jc_node_off[node], go = t.jg_node_off[node];
+    for (int k = 0; k < c; ++k) {
+      const int o = t.y_node_c[node] + k;
+      const double yk = LD(in, oy + o);
+      double acc = -LD(r2, o) * yk;
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        const double J = LD(mdl.node_jc, jo + k + j * c);
+        sx[j] += J * yk;
+        acc += J * x[j];
+      }
+      ACC(oy + o, acc);
+    }
+    for (int k = 0; k < g; ++k) {
+      const int o = t.z_node[node] + k;
+      const double zk = LD(in, oz + o);
+      double acc = -(LD(w, o) + LD(r3, o)) * zk;
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        const double J = LD(mdl.node_jg, go + k + j * g);
+        sx[j] += J * zk;
+        acc += J * x[j];
+      }
+      ACC(oz + o, acc);
+    }
+  }
+  if (has_edge) {
+    const int xu = t.x_control[e];
+    double u[M], su[M];
+#pragma unroll
+    for (int a = 0; a < M; ++a) {
+      u[a] = LD(in, xu + a);
+      su[a] = LD(r1, xu + a) * u[a];
+    }
+    {  // edge Hessian blocks
+      const int ho = t.hxx_edge_off[e], co = t.nm_off[e], uo = t.mm_off[e];
+#pragma unroll
+      for (int j = 0; j < N; ++j)
+#pragma unroll
+        for (int i = 0; i < N; ++i) sx[i] += LD(mdl.edge_hxx, ho + i + j * N) * x[j];
+#pragma unroll
+      for (int a = 0; a < M; ++a)
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          const double h = LD(mdl.edge_hxu, co + i + a * N);
+          sx[i] += h * u[a];
+          su[a] += h * x[i];
+        }
+#pragma unroll
+      for (int j = 0; j < M; ++j)
+#pragma unroll
+        for (int a = 0; a < M; ++a) su[a] += LD(mdl.edge_huu, uo + a + j * M) * u[j];
+    }
+    {  // dynamics of the child: A x + B u - x_child - R2 y_child, and A' y_child, B' y_child
+      const int yo = t.y_dyn[child], xc = t.x_state[child];
+      const int ao = t.a_off[e], bo = t.b_off[e];
+      double yc[N], dyn[N];
+#pragma unroll
+      for (int p = 0; p < N; ++p) {
+        yc[p] = LD(in, oy + yo + p);
+        dyn[p] = -LD(in, xc + p) - LD(r2, yo + p) * yc[p];
+      }
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int p = 0; p < N; ++p) {
+          const double A = LD(mdl.edge_A, ao + p + i * N);
+          sx[i] += A * yc[p];
+          dyn[p] += A * x[i];
+        }
+#pragma unroll
+      for (int a = 0; a < M; ++a)
+#pragma unroll
+        for (int p = 0; p < N; ++p) {
+          const double B = LD(mdl.edge_B, bo + p + a * N);
+          su[a] += B * yc[p];
+          dyn[p] += B * u[a];
+        }
+#pragma unroll
+      for (int p = 0; p < N; ++p) ACC(oy + yo + p, dyn[p]);
+    }
+    {  // edge constraints
+      const int c = t.edge_c[e], g = t.edge_g[e];
+      const int cx = t.jcx_off[e], cu = t.jcu_off[e], gx = t.jgx_off[e], gu = t.jgu_off[e];
+      for (int k = 0; k < c; ++k) {
+        const int o = t.y_edge_c[e] + k;
+        const double yk = LD(in, oy + o);
+        double acc = -LD(r2, o) * yk;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          const double J = LD(mdl.edge_jcx, cx + k + j * c);
+          sx[j] += J * yk;
+          acc += J * x[j];
+        }
+#pragma unroll
+        for (int a = 0; a < M; ++a) {
+          const double J = LD(mdl.edge_jcu, cu + k + a * c);
+          su[a] += J * yk;
+          acc += J * u[a];
+        }
+        ACC(oy + o, acc);
+      }
+      for (int k = 0; k < g; ++k) {
+        const int o = t.z_edge[e] + k;
+        const double zk = LD(in, oz + o);
+        double acc = -(LD(w, o) + LD(r3, o)) * zk;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          const double J = LD(mdl.edge_jgx, gx + k + j * g);
+          sx[j] += J * zk;
+          acc += J * x[j];
+        }
+#pragma unroll
+        for (int a = 0; a < M; ++a) {
+          const double J = LD(mdl.edge_jgu, gu + k + a * g);
+          su[a] += J * zk;
+          acc += J * u[a];
+        }
+        ACC(oz + o, acc);
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < M; ++a) ACC(xu + a, su[a]);
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) ACC(xs + i, sx[i]);
+#undef LD
+#undef ACC
+}
+
+template <int N, int M>
+void launch_apply(const DevTables &t, const KktModel &m, const double *w, const double *r1,
+                  const double *r2, const double *r3, const double *x, double *y, int64_t batch,
+                  int64_t ld, cudaStream_t s) {
+  dim3 grid(static_cast<unsigned>((batch + 127) / 128), static_cast<unsigned>(t.N));
+  kkt_apply_chain<N, M><<<grid, 128, 0, s>>>(t, m, w, r1, r2, r3, x, y, batch, ld);
+}
+
 }  // namespace
+
+KktApplyFn select_kkt_apply(int n, int m) {
+  if (n == 12 && m == 4) return &launch_apply<12, 4>;
+  if (n == 4 && m == 1) return &launch_apply<4, 1>;
+  if (n == 6 && m == 2) return &launch_apply<6, 2>;
+  if (n == 8 && m == 3) return &launch_apply<8, 3>;
+  return nullptr;
+}
 
 KktReduceFn select_kkt_reduce(int n, int m) {
   if (n == 12 && m == 4) return &launch<12, 4>;

@@ -19,4 +19,10 @@ using KktReduceFn = void (*)(const DevTables &, const KktModel &, const double *
 // nullptr when (n, m) is not instantiated.
 KktReduceFn select_kkt_reduce(int n, int m);
 
+// Same contract as launch_kkt_apply: y += K x on [x | y | z] vectors in the engine layout.
+using KktApplyFn = void (*)(const DevTables &, const KktModel &, const double *w,
+                            const double *r1, const double *r2, const double *r3,
+                            const double *x, double *y, int64_t batch, int64_t ld, cudaStream_t);
+KktApplyFn select_kkt_apply(int n, int m);
+
 }  // namespace sipoc

@@ -88,6 +88,35 @@ def test_newton_kkt_benchmark_shapes(n, m, T, force_generic):
     assert rel_err(cp.engine.unpack(dy, rhs.shape[1]), yref).max() < 1e-12
 
 
+@pytest.mark.parametrize("n,m", [(4, 1), (6, 2), (8, 3), (12, 4)])
+def test_chain_operator_kernel_constraints_on_every_node(n, m):
+    # kkt_apply_chain (kkt_fast.cu) reads each model block once and feeds the C x / C' y
+    # (G x / G' z) sums from the same register; constraint counts vary per node and per
+    # edge here (including none), unlike the benchmark shapes.  Checked against the oracle
+    # and against the generic output-driven kernel.
+    T = 7
+    node_c = [(k * 2 + 1) % 4 for k in range(T + 1)]
+    node_g = [(k + 2) % 3 for k in range(T + 1)]
+    edge_c = [(k + 1) % 3 for k in range(T)]
+    edge_g = [(3 * k) % 4 for k in range(T)]
+    s = Structure.chain(T, n, m, node_c=node_c, node_g=node_g, edge_c=edge_c, edge_g=edge_g)
+    batch = 37
+    model, w, r1, r2, r3, rhs = pg.newton_kkt_batch(s, batch, seed=n + m, r2_max=1e3)
+    xv = np.random.default_rng(5).standard_normal(rhs.shape)
+    y0 = np.random.default_rng(6).standard_normal(rhs.shape)
+    yref = pyoracle.kkt_apply(s, model, w, r1, r2, r3, xv, y0)
+    dims, topo = to_structs(s)
+    got = {}
+    for force_generic in (False, True):
+        cp = CallbackProvider(dims, topo, batch, force_generic=force_generic)
+        e = cp.engine
+        dy = e.pack(y0)
+        cp.add_Kx_to_y(cp.pack_model(model), *(e.pack(a) for a in (w, r1, r2, r3, xv)), dy)
+        got[force_generic] = e.unpack(dy, rhs.shape[1])
+        assert rel_err(got[force_generic], yref).max() < 1e-12
+    assert rel_err(got[False], got[True]).max() < 1e-12
+
+
 @pytest.mark.parametrize("case", [fx.kkt_case_chain, fx.kkt_case_siblings,
                                   fx.kkt_case_zero_dim_root])
 def test_operator_blocks(case):
