@@ -731,7 +731,8 @@ sipoc_error sipoc_create(const sipoc_structure *s, sipoc_engine **out) {
       if (i < h.E) rows += h.edge_c[i] + h.edge_g[i];
       e->kkt_max_rows = std::max(e->kkt_max_rows, rows);
     }
-    if (e->kkt_max_rows * 32 * 8 > 40 * 1024) e->kkt_reduce_fast = nullptr;
+    if (kkt_reduce_smem_bytes(h.n[0], h.m[0], std::max(1, e->kkt_max_rows)) > 200 * 1024)
+      e->kkt_reduce_fast = nullptr;
   }
   e->variant = e->fast != nullptr ? e->fast->name : "generic_thread_per_problem";
   if (e->padded) e->variant = "padded_to_" + e->variant;

@@ -7,24 +7,120 @@
 // Gram products in REGISTERS and writes it once (the generic kernel read-modify-
 // writes HBM per product).  The 1/r2 and 1/(w + r3) weights of the node and of its
 // child edge are computed once per CTA into shared memory (and into the workspace
-// the rhs build / dual recovery read later).  The 16 column-threads of a problem sit
-// in 16 different warps of the same CTA, so every Jacobian entry they share is an
-// L1 hit after its first use; all global accesses are 256 B coalesced across the 32
-// problems of a warp.  Exact-zero Jacobian entries are not skipped (adding the
-// zero products changes nothing for finite data).
+// the rhs build / dual recovery read later).  The column-threads of a problem sit in
+// different warps of the same CTA: each copies its own column of every Jacobian row into
+// shared memory ([row][column][problem], so a row's entries sit at compile-time offsets
+// from one pointer) and the Gram loops read them from there; the loops are instantiated
+// per column so that only the lower-triangle iterations exist.  All global accesses
+// are 256 B coalesced across the 32 problems of a warp.  Exact-zero Jacobian entries are
+// not skipped (adding the zero products changes nothing for finite data).
 #include "generic_kernels.cuh"
 #include "kkt_fast.cuh"
 
 namespace sipoc {
 namespace {
 
+// Phase B of kkt_reduce_chain for one column, J = the column index (warp-uniform, so the
+// dispatch below costs no divergence and the unrolled loops hold live iterations only).
+// Jrow points at this lane's entry of Jacobian row 0, column 0: [row][column][32 lanes].
+template <int N, int M, int J>
+__device__ __forceinline__ void reduce_state_column(const DevTables &t, const KktModel &mdl,
+                                                    const double *__restrict__ r1,
+                                                    const KktWs &ws, const double *wrow,
+                                                    const double *Jrow, int rows, int node,
+                                                    bool has_edge, size_t L, int64_t b) {
+  constexpr int NZ = N + M;
+  constexpr int LIVE = N - J;  // rows J .. N - 1 of column J (lower triangle)
+#define LD(ptr, off) __ldg((ptr) + static_cast<size_t>(off) * L + b)
+  const int qo = t.nn_off[node], e = node;
+  double accq[LIVE], accm[M];
+#pragma unroll
+  for (int i = 0; i < LIVE; ++i) accq[i] = LD(mdl.node_hxx, qo + (J + i) + J * N);
+#pragma unroll
+  for (int a = 0; a < M; ++a) accm[a] = 0.0;
+  if (has_edge) {
+#pragma unroll
+    for (int i = 0; i < LIVE; ++i) accq[i] += LD(mdl.edge_hxx, t.hxx_edge_off[e] + (J + i) + J * N);
+#pragma unroll
+    for (int a = 0; a < M; ++a) accm[a] = LD(mdl.edge_hxu, t.nm_off[e] + J + a * N);
+  }
+  accq[0] += LD(r1, t.x_state[node] + J);
+  // J' diag(weights) J over the node's and the child edge's constraint rows
+  for (int q = 0; q < rows; ++q) {
+    const double *row = Jrow + q * (NZ * 32);
+    const double wj = wrow[q * 32] * row[J * 32];
+#pragma unroll
+    for (int i = 0; i < LIVE; ++i) accq[i] += wj * row[(J + i) * 32];
+#pragma unroll
+    for (int a = 0; a < M; ++a) accm[a] += wj * row[(N + a) * 32];  // zero on node rows
+  }
+#pragma unroll
+  for (int i = 0; i < LIVE; ++i) {
+    ws.Q_mod[static_cast<size_t>(qo + (J + i) + J * N) * L + b] = accq[i];
+    if (i != 0) ws.Q_mod[static_cast<size_t>(qo + J + (J + i) * N) * L + b] = accq[i];  // mirror
+  }
+  if (has_edge) {
+#pragma unroll
+    for (int a = 0; a < M; ++a)
+      ws.M_mod[static_cast<size_t>(t.nm_off[e] + J + a * N) * L + b] = accm[a];
+  }
+#undef LD
+}
+
+template <int N, int M, int A>
+__device__ __forceinline__ void reduce_control_column(const DevTables &t, const KktModel &mdl,
+                                                      const double *__restrict__ r1,
+                                                      const KktWs &ws, const double *wrow,
+                                                      const double *Jrow, int first_row, int rows,
+                                                      int e, size_t L, int64_t b) {
+  constexpr int NZ = N + M;
+  constexpr int LIVE = M - A;
+#define LD(ptr, off) __ldg((ptr) + static_cast<size_t>(off) * L + b)
+  const int ro = t.mm_off[e];
+  double accr[LIVE];
+#pragma unroll
+  for (int i = 0; i < LIVE; ++i) accr[i] = LD(mdl.edge_huu, ro + (A + i) + A * M);
+  accr[0] += LD(r1, t.x_control[e] + A);
+  for (int q = first_row; q < rows; ++q) {  // edge rows only: node rows have no control part
+    const double *row = Jrow + q * (NZ * 32);
+    const double wa = wrow[q * 32] * row[(N + A) * 32];
+#pragma unroll
+    for (int i = 0; i < LIVE; ++i) accr[i] += wa * row[(N + A + i) * 32];
+  }
+#pragma unroll
+  for (int i = 0; i < LIVE; ++i) {
+    ws.R_mod[static_cast<size_t>(ro + (A + i) + A * M) * L + b] = accr[i];
+    if (i != 0) ws.R_mod[static_cast<size_t>(ro + A + (A + i) * M) * L + b] = accr[i];
+  }
+#undef LD
+}
+
+template <int N, int M, int J, typename... Args>
+__device__ __forceinline__ void dispatch_state_column(int col, const Args &...args) {
+  if (col == J) {
+    reduce_state_column<N, M, J>(args...);
+  } else if constexpr (J + 1 < N) {
+    dispatch_state_column<N, M, J + 1>(col, args...);
+  }
+}
+template <int N, int M, int A, typename... Args>
+__device__ __forceinline__ void dispatch_control_column(int a, const Args &...args) {
+  if (a == A) {
+    reduce_control_column<N, M, A>(args...);
+  } else if constexpr (A + 1 < M) {
+    dispatch_control_column<N, M, A + 1>(a, args...);
+  }
+}
+
 template <int N, int M>
 __global__ void __launch_bounds__(32 * (N + M))
 kkt_reduce_chain(DevTables t, KktModel mdl, const double *__restrict__ w,
                  const double *__restrict__ r1, const double *__restrict__ r2,
-                 const double *__restrict__ r3, KktWs ws, int *ok, int64_t batch, int64_t ld) {
+                 const double *__restrict__ r3, KktWs ws, int *ok, int64_t batch, int64_t ld,
+                 int max_rows) {
   constexpr int NZ = N + M;
-  extern __shared__ double wsm[];  // [row][32 problems]
+  extern __shared__ double wsm[];       // weights [row][32 problems], then
+  double *jsm = wsm + max_rows * 32;    // Jacobian rows [row][column][32 problems]
   const int lane = threadIdx.x & 31, col = threadIdx.x >> 5;
   const int64_t b = static_cast<int64_t>(blockIdx.x) * 32 + lane;  // < ld by construction
   const int node = blockIdx.y;
@@ -35,7 +131,7 @@ kkt_reduce_chain(DevTables t, KktModel mdl, const double *__restrict__ w,
 
   const int c_n = t.node_c[node], g_n = t.node_g[node];
   const int c_e = has_edge ? t.edge_c[e] : 0, g_e = has_edge ? t.edge_g[e] : 0;
-  const int o_cn = 0, o_gn = c_n, o_ce = c_n + g_n, o_ge = o_ce + c_e, rows = o_ge + g_e;
+  const int o_gn = c_n, o_ce = c_n + g_n, o_ge = o_ce + c_e, rows = o_ge + g_e;
 
   // ---- phase A: weights and the dynamics regularization (helpers.cpp:251-295) ----
   bool good = true;
@@ -70,103 +166,33 @@ kkt_reduce_chain(DevTables t, KktModel mdl, const double *__restrict__ w,
     }
   }
   if (!good && b < batch) ok[b] = 0;  // benign race: every writer stores 0
+
+  // ---- this thread's column of every Jacobian row -> shared memory (each entry is read
+  // from HBM once; node rows have no control part) ----
+  {
+    double *dst = jsm + col * 32 + lane;
+    const bool state = col < N;
+    const int a = col - N;
+    for (int k = 0; k < c_n; ++k)
+      dst[k * (NZ * 32)] = state ? LD(mdl.node_jc, t.jc_node_off[node] + k + col * c_n) : 0.0;
+    for (int k = 0; k < g_n; ++k)
+      dst[(o_gn + k) * (NZ * 32)] =
+          state ? LD(mdl.node_jg, t.jg_node_off[node] + k + col * g_n) : 0.0;
+    for (int k = 0; k < c_e; ++k)
+      dst[(o_ce + k) * (NZ * 32)] = state ? LD(mdl.edge_jcx, t.jcx_off[e] + k + col * c_e)
+                                          : LD(mdl.edge_jcu, t.jcu_off[e] + k + a * c_e);
+    for (int k = 0; k < g_e; ++k)
+      dst[(o_ge + k) * (NZ * 32)] = state ? LD(mdl.edge_jgx, t.jgx_off[e] + k + col * g_e)
+                                          : LD(mdl.edge_jgu, t.jgu_off[e] + k + a * g_e);
+  }
   __syncthreads();
 
   // ---- phase B: one column of [Q M; M' R] per thread (helpers.cpp:297-360) ----
-  const int qo = t.nn_off[node];
+  const double *wrow = wsm + lane, *Jrow = jsm + lane;
   if (col < N) {
-    const int j = col;
-    double accq[N], accm[M];
-#pragma unroll
-    for (int i = 0; i < N; ++i) accq[i] = (i >= j) ? LD(mdl.node_hxx, qo + i + j * N) : 0.0;
-    if (has_edge) {
-#pragma unroll
-      for (int i = 0; i < N; ++i)
-        if (i >= j) accq[i] += LD(mdl.edge_hxx, t.hxx_edge_off[e] + i + j * N);
-#pragma unroll
-      for (int a = 0; a < M; ++a) accm[a] = LD(mdl.edge_hxu, t.nm_off[e] + j + a * N);
-    }
-    const double r1j = LD(r1, t.x_state[node] + j);
-#pragma unroll
-    for (int i = 0; i < N; ++i)
-      if (i == j) accq[i] += r1j;
-    // node constraints: J' diag(weights) J
-    for (int k = 0; k < c_n; ++k) {
-      const int jo = t.jc_node_off[node];
-      const double wj = wsm[(o_cn + k) * 32 + lane] * LD(mdl.node_jc, jo + k + j * c_n);
-#pragma unroll
-      for (int i = 0; i < N; ++i)
-        if (i >= j) accq[i] += wj * LD(mdl.node_jc, jo + k + i * c_n);
-    }
-    for (int k = 0; k < g_n; ++k) {
-      const int jo = t.jg_node_off[node];
-      const double wj = wsm[(o_gn + k) * 32 + lane] * LD(mdl.node_jg, jo + k + j * g_n);
-#pragma unroll
-      for (int i = 0; i < N; ++i)
-        if (i >= j) accq[i] += wj * LD(mdl.node_jg, jo + k + i * g_n);
-    }
-    // edge constraints
-    for (int k = 0; k < c_e; ++k) {
-      const int jx = t.jcx_off[e], ju = t.jcu_off[e];
-      const double wj = wsm[(o_ce + k) * 32 + lane] * LD(mdl.edge_jcx, jx + k + j * c_e);
-#pragma unroll
-      for (int i = 0; i < N; ++i)
-        if (i >= j) accq[i] += wj * LD(mdl.edge_jcx, jx + k + i * c_e);
-#pragma unroll
-      for (int a = 0; a < M; ++a) accm[a] += wj * LD(mdl.edge_jcu, ju + k + a * c_e);
-    }
-    for (int k = 0; k < g_e; ++k) {
-      const int jx = t.jgx_off[e], ju = t.jgu_off[e];
-      const double wj = wsm[(o_ge + k) * 32 + lane] * LD(mdl.edge_jgx, jx + k + j * g_e);
-#pragma unroll
-      for (int i = 0; i < N; ++i)
-        if (i >= j) accq[i] += wj * LD(mdl.edge_jgx, jx + k + i * g_e);
-#pragma unroll
-      for (int a = 0; a < M; ++a) accm[a] += wj * LD(mdl.edge_jgu, ju + k + a * g_e);
-    }
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-      if (i >= j) {
-        ws.Q_mod[static_cast<size_t>(qo + i + j * N) * L + b] = accq[i];
-        if (i != j) ws.Q_mod[static_cast<size_t>(qo + j + i * N) * L + b] = accq[i];  // mirror
-      }
-    }
-    if (has_edge) {
-#pragma unroll
-      for (int a = 0; a < M; ++a)
-        ws.M_mod[static_cast<size_t>(t.nm_off[e] + j + a * N) * L + b] = accm[a];
-    }
+    dispatch_state_column<N, M, 0>(col, t, mdl, r1, ws, wrow, Jrow, rows, node, has_edge, L, b);
   } else if (has_edge) {
-    const int a = col - N;
-    const int ro = t.mm_off[e];
-    double accr[M];
-#pragma unroll
-    for (int i = 0; i < M; ++i) accr[i] = (i >= a) ? LD(mdl.edge_huu, ro + i + a * M) : 0.0;
-    const double r1a = LD(r1, t.x_control[e] + a);
-#pragma unroll
-    for (int i = 0; i < M; ++i)
-      if (i == a) accr[i] += r1a;
-    for (int k = 0; k < c_e; ++k) {
-      const int ju = t.jcu_off[e];
-      const double wa = wsm[(o_ce + k) * 32 + lane] * LD(mdl.edge_jcu, ju + k + a * c_e);
-#pragma unroll
-      for (int i = 0; i < M; ++i)
-        if (i >= a) accr[i] += wa * LD(mdl.edge_jcu, ju + k + i * c_e);
-    }
-    for (int k = 0; k < g_e; ++k) {
-      const int ju = t.jgu_off[e];
-      const double wa = wsm[(o_ge + k) * 32 + lane] * LD(mdl.edge_jgu, ju + k + a * g_e);
-#pragma unroll
-      for (int i = 0; i < M; ++i)
-        if (i >= a) accr[i] += wa * LD(mdl.edge_jgu, ju + k + i * g_e);
-    }
-#pragma unroll
-    for (int i = 0; i < M; ++i) {
-      if (i >= a) {
-        ws.R_mod[static_cast<size_t>(ro + i + a * M) * L + b] = accr[i];
-        if (i != a) ws.R_mod[static_cast<size_t>(ro + a + i * M) * L + b] = accr[i];
-      }
-    }
+    dispatch_control_column<N, M, 0>(col - N, t, mdl, r1, ws, wrow, Jrow, o_ce, rows, e, L, b);
   }
 #undef LD
 }
@@ -177,10 +203,13 @@ void launch(const DevTables &t, const KktModel &m, const double *w, const double
             int64_t ld, int max_rows, cudaStream_t s) {
   launch_fill_int(ok, 1, ld, s);
   dim3 grid(static_cast<unsigned>(ld / 32), static_cast<unsigned>(t.N));
-  const size_t smem = static_cast<size_t>(max_rows > 0 ? max_rows : 1) * 32 * sizeof(double);
-  kkt_reduce_chain<N, M><<<grid, 32 * (N + M), smem, s>>>(t, m, w, r1, r2, r3, ws, ok, batch, ld);
+  const int rows = max_rows > 0 ? max_rows : 1;
+  const size_t smem = kkt_reduce_smem_bytes(N, M, rows);
+  auto kern = kkt_reduce_chain<N, M>;
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  kern<<<grid, 32 * (N + M), smem, s>>>(t, m, w, r1, r2, r3, ws, ok, batch, ld, rows);
 }
-
 
 // y += K x for uniform chains (helpers.cpp:953-1368, theta == 0): thread (problem, node)
 // owns the rows of the node's state, of its child edge's control, of the node / edge

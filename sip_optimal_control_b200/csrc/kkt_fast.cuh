@@ -18,6 +18,10 @@ using KktReduceFn = void (*)(const DevTables &, const KktModel &, const double *
 
 // nullptr when (n, m) is not instantiated.
 KktReduceFn select_kkt_reduce(int n, int m);
+// Dynamic shared memory of the reduction kernel: weights + Jacobian rows of 32 problems.
+inline size_t kkt_reduce_smem_bytes(int n, int m, int max_rows) {
+  return static_cast<size_t>(max_rows) * (n + m + 1) * 32 * sizeof(double);
+}
 
 // Same contract as launch_kkt_apply: y += K x on [x | y | z] vectors in the engine layout.
 using KktApplyFn = void (*)(const DevTables &, const KktModel &, const double *w,

@@ -115,6 +115,13 @@ def test_chain_operator_kernel_constraints_on_every_node(n, m):
         got[force_generic] = e.unpack(dy, rhs.shape[1])
         assert rel_err(got[force_generic], yref).max() < 1e-12
     assert rel_err(got[False], got[True]).max() < 1e-12
+    # the reduction kernel of the same structure (kkt_reduce_chain: node rows on every node)
+    ref = pyoracle.kkt_factor_solve(s, model, w, r1, r2, r3, rhs)
+    assert (ref["ok"] == 1).all()
+    gpu, _, _ = _gpu_kkt(s, model, w, r1, r2, r3, rhs)
+    assert (gpu["ok"] == 1).all()
+    assert rel_err(gpu["sol"], ref["sol"]).max() < REL_TOL
+    assert (gpu["residual"] / np.linalg.norm(rhs, axis=1)).max() < 1e-9
 
 
 @pytest.mark.parametrize("case", [fx.kkt_case_chain, fx.kkt_case_siblings,
