@@ -1162,7 +1162,7 @@ sipoc_error sipoc_kkt_residual(sipoc_engine *e, const sipoc_kkt_model *model, co
                                     sizeof(double),
                                 s));
   {
-    ProfScope ps(&e->prof, "kkt_apply_kernel", s);
+    ProfScope ps(&e->prof, e->kkt_apply_fast != nullptr ? "kkt_apply_chain" : "kkt_apply_kernel", s);
     (e->kkt_apply_fast != nullptr ? e->kkt_apply_fast : &launch_kkt_apply)(
         e->dt, to_model(model), w, r1, r2, r3, sol, e->kkt_product, e->batch, e->ld, s);
   }

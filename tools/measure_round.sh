@@ -26,3 +26,10 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 ncu --set full --clock-control none --import-source on -k regex:riccati_backward_cta -c 1 -f -o $O/hum_backward $H > $O/ncu_bwd.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:rollout_forward_cta -c 1 -f -o $O/hum_forward $H > $O/ncu_fwd.log 2>&1
 ls -la $O | tail -20
+# ncu: the uniform Newton-KKT step (launch list + the operator and reduction kernels).
+K="python bench.py --workload newton_kkt_uniform --steps 2 --warmup 1 --no-e2e --no-cpu-baseline"
+$K > $O/kkt_plain.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_newton_kkt_uniform.csv $K > $O/ncu_kkt_launch.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:kkt_apply_chain -c 1 -f -o $O/kkt_apply_chain $K > $O/ncu_kkt_a.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:kkt_reduce_chain -c 1 -f -o $O/kkt_reduce_chain $K > $O/ncu_kkt_r.log 2>&1
+ls -la $O | tail -8
