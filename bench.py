@@ -569,7 +569,14 @@ def run_kkt(args):
     ok = eng.empty_int()
     stream = torch.cuda.current_stream(dev)
 
+    captured = None
+    if getattr(args, "graph", False):
+        # the step recorded once as a CUDA graph, replayed with one driver call per step
+        captured = cp.capture_step(model, w, r1, r2, r3, b, sol, ok=ok)
+
     def step():
+        if captured is not None:
+            return captured.replay()
         cp.factor(model, w, r1, r2, r3, ok=ok, stream=stream)
         cp.solve(model, b, sol, stream=stream)
         return cp.residual(model, w, r1, r2, r3, sol, b, ok=ok, stream=stream)
@@ -578,7 +585,8 @@ def run_kkt(args):
         step()
     torch.cuda.synchronize(dev)
     launches0 = eng.launch_count
-    lib.sipoc_profile_enable(eng._handle, 1)
+    if captured is None:
+        lib.sipoc_profile_enable(eng._handle, 1)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.time()
     ev0.record(stream)
@@ -590,7 +598,12 @@ def run_kkt(args):
     ms_per_step = ev0.elapsed_time(ev1) / args.steps
     gpu_launches = eng.launch_count - launches0
     kernels = {}
-    for i in range(lib.sipoc_profile_collect(eng._handle)):
+    if captured is not None:
+        # replays launch from the graph, not through the C ABI: count what was recorded, and
+        # (no per-kernel events inside a graph) attribute the step's device time as a whole
+        gpu_launches = captured.launches * args.steps
+        kernels["captured_step"] = {"ms_per_launch": ms_per_step, "ms_per_step": ms_per_step}
+    for i in range(0 if captured is not None else lib.sipoc_profile_collect(eng._handle)):
         nm, ms, cnt = ctypes.c_char_p(), ctypes.c_double(), ctypes.c_int64()
         lib.sipoc_profile_get(eng._handle, i, ctypes.byref(nm), ctypes.byref(ms),
                               ctypes.byref(cnt))
@@ -616,6 +629,7 @@ def run_kkt(args):
         "config": {"workload": args.workload, "r2_max": r2_max, **{k: (list(v) if isinstance(v, tuple) else v)
                                                 for k, v in wl.items()},
                    "kkt_dim": int(b_h.shape[1]), "kernel_variant": eng.kernel_variant,
+                   "launch": "cuda_graph" if captured is not None else "eager",
                    "generator": "newton_kkt_benchmark.cpp:171-240 distribution"},
         "clocks": sampler.summary(t0, t1), "e2e": None, "gpu_launches": int(gpu_launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -646,6 +660,9 @@ def main():
     ap.add_argument("--pad-variable-dims", action="store_true",
                     help="newton_kkt: SIPOC_FLAG_PAD_VARIABLE_DIMS (shape-specialised kernels through "
                          "decoupled padding instead of the strict-order generic kernels)")
+    ap.add_argument("--graph", action="store_true",
+                    help="newton_kkt workloads: replay the step as one CUDA graph "
+                         "(CallbackProvider.capture_step) instead of launching its kernels eagerly")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--e2e-batch", type=int, default=16384)

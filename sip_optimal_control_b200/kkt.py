@@ -31,6 +31,23 @@ def _model_struct(model: dict, host: bool, keep: list) -> _capi.KktModel:
     return s
 
 
+class CapturedKktStep:
+    """A recorded factor + solve + residual sequence (CallbackProvider.capture_step).
+
+    ``ok`` / ``norms`` / ``stats`` are the step's outputs, rewritten by every replay;
+    ``launches`` is the number of engine kernels one replay runs."""
+
+    def __init__(self, graph, ok, norms, stats, launches: int, keep=()):
+        self.graph, self.ok, self.norms, self.stats = graph, ok, norms, stats
+        self._keep = keep  # the graph holds raw device pointers into these tensors
+        self.launches = int(launches)
+
+    def replay(self):
+        """Enqueue the whole step on the current stream; returns (norms, stats)."""
+        self.graph.replay()
+        return self.norms, self.stats
+
+
 class CallbackProvider:
     """Batched Newton-KKT linear solve behind the reference's callback names."""
 
@@ -129,6 +146,37 @@ class CallbackProvider:
             None if ok is None else ok.data_ptr(), norms.data_ptr(), stats.data_ptr(),
             e.stream_ptr(stream)))
         return norms, stats
+
+    def capture_step(self, model: dict, w, r1, r2, r3, b, sol, ok=None) -> "CapturedKktStep":
+        """factor + solve + residual (one Newton-KKT iteration's linear algebra,
+        sip_optimal_control.cpp:129-145) recorded once as a CUDA graph over the given device
+        tensors.  ``replay()`` relaunches the whole kernel sequence with one driver call;
+        the caller refreshes the tensors' contents in place between replays."""
+        e = self.engine
+        if not self.input_is_valid_:
+            raise SipocError(self.engine.create_status, "capture_step on an invalid structure")
+        torch = e._torch()
+        dev = e.torch_device()
+        ok = e.empty_int() if ok is None else ok
+
+        def step(stream):
+            self.factor(model, w, r1, r2, r3, ok=ok, stream=stream)
+            self.solve(model, b, sol, stream=stream)
+            return self.residual(model, w, r1, r2, r3, sol, b, ok=ok, stream=stream)
+
+        # One eager pass on the capture stream first: the engine sizes its workspaces and
+        # sets kernel attributes on first use, neither of which may happen under capture.
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            step(side)
+        side.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        launches0 = e.launch_count
+        with torch.cuda.graph(graph, stream=side, capture_error_mode="thread_local"):
+            norms, stats = step(torch.cuda.current_stream(dev))
+        return CapturedKktStep(graph, ok, norms, stats, e.launch_count - launches0,
+                               keep=(model, w, r1, r2, r3, b, sol))
 
     # -- host path ----------------------------------------------------------------
     def factor_host(self, model: dict, w, r1, r2, r3) -> np.ndarray:

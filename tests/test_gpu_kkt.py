@@ -268,3 +268,41 @@ def test_fused_kkt_solve_path_large_batch():
     assert rel_err(gpu["sol"][sample], ref["sol"]).max() < 1e-9
     scale = np.linalg.norm(rhs, axis=1)
     assert (gpu["residual"] / scale).max() < 1e-9
+
+
+@pytest.mark.parametrize("uniform", [True, False])
+def test_captured_step_replays_bit_exact(uniform):
+    """CallbackProvider.capture_step: the CUDA-graph replay of factor + solve + residual
+    returns exactly what the eager calls return, and follows in-place input updates."""
+    import torch
+
+    if uniform:
+        s = _uniform_kkt_structure(4, 2, 8)
+    else:
+        s = fx.kkt_case_chain()
+    batch = 96
+    model, w, r1, r2, r3, rhs = pg.newton_kkt_batch(s, batch, seed=5, r2_max=1e3)
+    eager, cp, (dm, dw, dr1, dr2, dr3, db) = _gpu_kkt(s, model, w, r1, r2, r3, rhs)
+    e = cp.engine
+    sol = e.zeros(cp.sizes["kkt_dim"])
+    cap = cp.capture_step(dm, dw, dr1, dr2, dr3, db, sol)
+    assert cap.launches >= 3
+    launches = e.launch_count
+    sol.zero_()
+    norms, stats = cap.replay()
+    torch.cuda.synchronize()
+    assert e.launch_count == launches  # nothing launched from the host side
+    assert np.array_equal(e.unpack(sol, cp.sizes["kkt_dim"]), eager["sol"])
+    assert np.array_equal(norms[:batch].cpu().numpy(), eager["residual"])
+    # stats[0] is an atomic sum over problems (order not fixed); max / counts are exact
+    st = stats.cpu().numpy()
+    assert np.array_equal(st[1:], eager["stats"][1:])
+    assert abs(st[0] - eager["stats"][0]) <= 1e-12 * eager["stats"][0]
+    assert np.array_equal(cap.ok[:batch].cpu().numpy(), eager["ok"])
+    # a new right-hand side written in place is what the next replay solves
+    rhs2 = rhs[::-1].copy()
+    db.copy_(e.pack(rhs2))
+    cap.replay()
+    torch.cuda.synchronize()
+    ref2, *_ = _gpu_kkt(s, model, w, r1, r2, r3, rhs2)
+    assert np.array_equal(e.unpack(sol, cp.sizes["kkt_dim"]), ref2["sol"])
