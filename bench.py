@@ -599,9 +599,8 @@ def run_kkt(args):
     gpu_launches = eng.launch_count - launches0
     kernels = {}
     if captured is not None:
-        # replays launch from the graph, not through the C ABI: count what was recorded, and
-        # (no per-kernel events inside a graph) attribute the step's device time as a whole
-        gpu_launches = captured.launches * args.steps
+        # no per-kernel events inside a graph: the step's device time is attributed as a whole
+        # (sipoc_graph_launch adds the recorded kernels to the launch count)
         kernels["captured_step"] = {"ms_per_launch": ms_per_step, "ms_per_step": ms_per_step}
     for i in range(0 if captured is not None else lib.sipoc_profile_collect(eng._handle)):
         nm, ms, cnt = ctypes.c_char_p(), ctypes.c_double(), ctypes.c_int64()

@@ -154,6 +154,22 @@ int sipoc_profile_collect(sipoc_engine *engine);
 sipoc_error sipoc_profile_get(const sipoc_engine *engine, int index, const char **name,
                               double *total_ms, int64_t *launches);
 
+/* ---- CUDA graphs --------------------------------------------------------
+ * The device entry points below only enqueue kernels on the caller's stream, so
+ * any sequence of them -- e.g. one Newton-KKT iteration, sipoc_kkt_factor +
+ * sipoc_kkt_solve + sipoc_kkt_residual (sip_optimal_control.cpp:129-145) -- can
+ * be recorded once and relaunched with a single driver call.  Run the sequence
+ * eagerly once first (workspaces are sized on first use, which may not happen
+ * under capture); `stream` must be a non-default stream; the arrays the recorded
+ * calls were given must stay allocated, their contents may change between
+ * launches.  sipoc_graph_launch adds the recorded kernels to sipoc_launch_count. */
+typedef struct sipoc_graph sipoc_graph;
+sipoc_error sipoc_graph_begin(sipoc_engine *engine, void *stream);
+sipoc_error sipoc_graph_end(sipoc_engine *engine, void *stream, sipoc_graph **out);
+sipoc_error sipoc_graph_launch(sipoc_engine *engine, sipoc_graph *graph, void *stream);
+int64_t sipoc_graph_kernel_count(const sipoc_graph *graph);
+void sipoc_graph_destroy(sipoc_graph *graph);
+
 /* ---- sizes ------------------------------------------------------------- */
 typedef struct sipoc_lqr_sizes {
   int64_t Q, M, R, q, r, A, B, c, delta; /* inputs, elements per problem  */

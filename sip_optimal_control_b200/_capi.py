@@ -102,6 +102,13 @@ def _load() -> ctypes.CDLL:
     lib.sipoc_get_topology.argtypes = [E, c_int_p, c_int_p, c_int_p, c_int_p]
     lib.sipoc_launch_count.argtypes = [E]
     lib.sipoc_launch_count.restype = ctypes.c_int64
+    lib.sipoc_graph_begin.argtypes = [E, ctypes.c_void_p]
+    lib.sipoc_graph_end.argtypes = [E, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]
+    lib.sipoc_graph_launch.argtypes = [E, ctypes.c_void_p, ctypes.c_void_p]
+    lib.sipoc_graph_kernel_count.argtypes = [ctypes.c_void_p]
+    lib.sipoc_graph_kernel_count.restype = ctypes.c_int64
+    lib.sipoc_graph_destroy.argtypes = [ctypes.c_void_p]
+    lib.sipoc_graph_destroy.restype = None
     lib.sipoc_profile_enable.argtypes = [E, ctypes.c_int]
     lib.sipoc_profile_collect.argtypes = [E]
     lib.sipoc_profile_collect.restype = ctypes.c_int

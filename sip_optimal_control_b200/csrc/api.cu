@@ -34,6 +34,8 @@ struct sipoc_engine {
   std::string variant;
   std::string last_error;
   int64_t launches = 0;
+  bool capturing = false;          // between sipoc_graph_begin and sipoc_graph_end
+  int64_t capture_launches0 = 0;
   Profiler prof;
   cudaStream_t host_stream = nullptr;
 
@@ -760,6 +762,73 @@ const char *sipoc_kernel_variant(const sipoc_engine *e) {
 }
 
 int64_t sipoc_launch_count(const sipoc_engine *e) { return e == nullptr ? 0 : e->launches; }
+
+// ---- CUDA graphs ------------------------------------------------------------
+// The device entry points only enqueue work on the caller's stream (workspaces are
+// sized on first use, so one eager pass precedes a capture); any sequence of them can
+// therefore be recorded once and relaunched with a single driver call.
+struct sipoc_graph {
+  cudaGraphExec_t exec = nullptr;
+  int device = 0;
+  int64_t launches = 0;  // engine kernels inside one launch of the graph
+};
+
+sipoc_error sipoc_graph_begin(sipoc_engine *e, void *stream) {
+  if (e == nullptr) return SIPOC_INVALID_ARGUMENT;
+  if (e->capturing) return fail(e, SIPOC_INVALID_ARGUMENT, "sipoc_graph_begin: already capturing");
+  if (e->prof.enabled())
+    return fail(e, SIPOC_INVALID_ARGUMENT,
+                "sipoc_graph_begin: per-kernel profiling records events; disable it first");
+  DeviceGuard guard(e->device);
+  SIPOC_CUDA(e, cudaStreamBeginCapture(static_cast<cudaStream_t>(stream),
+                                       cudaStreamCaptureModeThreadLocal));
+  e->capturing = true;
+  e->capture_launches0 = e->launches;
+  return SIPOC_OK;
+}
+
+sipoc_error sipoc_graph_end(sipoc_engine *e, void *stream, sipoc_graph **out) {
+  if (e == nullptr || out == nullptr) return SIPOC_INVALID_ARGUMENT;
+  *out = nullptr;
+  if (!e->capturing) return fail(e, SIPOC_INVALID_ARGUMENT, "sipoc_graph_end: not capturing");
+  DeviceGuard guard(e->device);
+  e->capturing = false;
+  cudaGraph_t graph = nullptr;
+  SIPOC_CUDA(e, cudaStreamEndCapture(static_cast<cudaStream_t>(stream), &graph));
+  cudaGraphExec_t exec = nullptr;
+  cudaError_t err = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (err != cudaSuccess)
+    return fail(e, SIPOC_CUDA_ERROR,
+                std::string("cudaGraphInstantiate: ") + cudaGetErrorString(err));
+  sipoc_graph *g = new sipoc_graph;
+  g->exec = exec;
+  g->device = e->device;
+  g->launches = e->launches - e->capture_launches0;
+  *out = g;
+  return SIPOC_OK;
+}
+
+sipoc_error sipoc_graph_launch(sipoc_engine *e, sipoc_graph *g, void *stream) {
+  if (e == nullptr || g == nullptr || g->exec == nullptr) return SIPOC_INVALID_ARGUMENT;
+  if (g->device != e->device)
+    return fail(e, SIPOC_INVALID_ARGUMENT, "sipoc_graph_launch: graph of another device");
+  DeviceGuard guard(e->device);
+  SIPOC_CUDA(e, cudaGraphLaunch(g->exec, static_cast<cudaStream_t>(stream)));
+  e->launches += g->launches;
+  return SIPOC_OK;
+}
+
+int64_t sipoc_graph_kernel_count(const sipoc_graph *g) { return g == nullptr ? 0 : g->launches; }
+
+void sipoc_graph_destroy(sipoc_graph *g) {
+  if (g == nullptr) return;
+  if (g->exec != nullptr) {
+    DeviceGuard guard(g->device);
+    cudaGraphExecDestroy(g->exec);
+  }
+  delete g;
+}
 
 sipoc_error sipoc_profile_enable(sipoc_engine *e, int on) {
   if (e == nullptr) return SIPOC_INVALID_ARGUMENT;

@@ -32,20 +32,29 @@ def _model_struct(model: dict, host: bool, keep: list) -> _capi.KktModel:
 
 
 class CapturedKktStep:
-    """A recorded factor + solve + residual sequence (CallbackProvider.capture_step).
+    """A recorded factor + solve + residual sequence (CallbackProvider.capture_step;
+    sipoc_graph_* in include/sipoc.h).
 
     ``ok`` / ``norms`` / ``stats`` are the step's outputs, rewritten by every replay;
     ``launches`` is the number of engine kernels one replay runs."""
 
-    def __init__(self, graph, ok, norms, stats, launches: int, keep=()):
-        self.graph, self.ok, self.norms, self.stats = graph, ok, norms, stats
+    def __init__(self, engine: Engine, handle, ok, norms, stats, keep=()):
+        self._engine, self._graph = engine, handle
+        self.ok, self.norms, self.stats = ok, norms, stats
+        self.launches = int(lib.sipoc_graph_kernel_count(handle))
         self._keep = keep  # the graph holds raw device pointers into these tensors
-        self.launches = int(launches)
 
-    def replay(self):
-        """Enqueue the whole step on the current stream; returns (norms, stats)."""
-        self.graph.replay()
+    def replay(self, stream=None):
+        """Enqueue the whole step on ``stream`` (default: torch's current, which must not be
+        the legacy default stream's capture); returns (norms, stats)."""
+        e = self._engine
+        e._check(lib.sipoc_graph_launch(e._handle, self._graph, e.stream_ptr(stream)))
         return self.norms, self.stats
+
+    def __del__(self):
+        if getattr(self, "_graph", None):
+            lib.sipoc_graph_destroy(self._graph)
+            self._graph = None
 
 
 class CallbackProvider:
@@ -133,12 +142,16 @@ class CallbackProvider:
     def add_GTx_to_y(self, model: dict, x, y, stream=None) -> None:
         self._apply_block(_capi.KKT_BLOCK_GT, model, x, y, stream)
 
-    def residual(self, model: dict, w, r1, r2, r3, sol, b, ok=None, stream=None):
-        """(||K sol - b||_2 per problem, 4 all-reducible statistics)."""
+    def residual(self, model: dict, w, r1, r2, r3, sol, b, ok=None, stream=None, out=None):
+        """(||K sol - b||_2 per problem, 4 all-reducible statistics); ``out`` = zeroed
+        (norms, stats) tensors to write into instead of new ones."""
         e = self.engine
         torch = e._torch()
-        norms = torch.zeros((e.batch_stride,), dtype=torch.float64, device=e.torch_device())
-        stats = torch.zeros((4,), dtype=torch.float64, device=e.torch_device())
+        if out is None:
+            norms = torch.zeros((e.batch_stride,), dtype=torch.float64, device=e.torch_device())
+            stats = torch.zeros((4,), dtype=torch.float64, device=e.torch_device())
+        else:
+            norms, stats = out
         m = _model_struct(model, False, [])
         e._check(lib.sipoc_kkt_residual(
             e._handle, ctypes.byref(m), w.data_ptr(), r1.data_ptr(), r2.data_ptr(),
@@ -159,24 +172,32 @@ class CallbackProvider:
         dev = e.torch_device()
         ok = e.empty_int() if ok is None else ok
 
+        norms = torch.zeros((e.batch_stride,), dtype=torch.float64, device=dev)
+        stats = torch.zeros((4,), dtype=torch.float64, device=dev)
+
         def step(stream):
             self.factor(model, w, r1, r2, r3, ok=ok, stream=stream)
             self.solve(model, b, sol, stream=stream)
-            return self.residual(model, w, r1, r2, r3, sol, b, ok=ok, stream=stream)
+            with torch.cuda.stream(stream):
+                norms.zero_()
+                stats.zero_()
+            self.residual(model, w, r1, r2, r3, sol, b, ok=ok, stream=stream,
+                          out=(norms, stats))
 
         # One eager pass on the capture stream first: the engine sizes its workspaces and
         # sets kernel attributes on first use, neither of which may happen under capture.
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            step(side)
+        step(side)
         side.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        launches0 = e.launch_count
-        with torch.cuda.graph(graph, stream=side, capture_error_mode="thread_local"):
-            norms, stats = step(torch.cuda.current_stream(dev))
-        return CapturedKktStep(graph, ok, norms, stats, e.launch_count - launches0,
-                               keep=(model, w, r1, r2, r3, b, sol))
+        handle = ctypes.c_void_p()
+        e._check(lib.sipoc_graph_begin(e._handle, int(side.cuda_stream)))
+        try:
+            step(side)
+        finally:
+            rc = lib.sipoc_graph_end(e._handle, int(side.cuda_stream), ctypes.byref(handle))
+        e._check(rc)
+        return CapturedKktStep(e, handle, ok, norms, stats, keep=(model, w, r1, r2, r3, b, sol))
 
     # -- host path ----------------------------------------------------------------
     def factor_host(self, model: dict, w, r1, r2, r3) -> np.ndarray:

