@@ -84,3 +84,14 @@ def test_dimension_queries_match_reference_formulas():
     t.set_chain()
     assert t.edge_parents.tolist() == [0, 1, 2] and t.edge_children.tolist() == [1, 2, 3]
     assert t.num_nodes() == 4
+
+
+def test_graph_entry_points_reject_null_handles():
+    # argument checks (SIPOC_INVALID_ARGUMENT = 1) come before any CUDA call
+    lib = _capi.lib
+    out = ctypes.c_void_p()
+    assert lib.sipoc_graph_begin(None, None) == 1
+    assert lib.sipoc_graph_end(None, None, ctypes.byref(out)) == 1
+    assert lib.sipoc_graph_launch(None, None, None) == 1
+    assert lib.sipoc_graph_kernel_count(None) == 0
+    lib.sipoc_graph_destroy(None)

@@ -420,3 +420,60 @@ def test_specialised_kernels_at_scale_are_deterministic(n, m, T, batch):
         outs.append(out)
     for k in ("x", "u", "y"):
         assert torch.equal(outs[0][k], outs[1][k]), k
+
+
+# --- CUDA graphs over the device entry points (sipoc_graph_*) ----------------------
+@pytest.mark.parametrize("n,m,T", [(4, 1, 20), (12, 4, 10), (5, 2, 7), (64, 24, 3)])
+def test_lqr_factor_solve_replays_from_a_graph(n, m, T):
+    """Every kernel family (thread, sub-warp, generic, CTA per problem) only enqueues on the
+    caller's stream: factor + solve recorded once replays bit-exactly on new inputs."""
+    import ctypes
+
+    import torch
+    from sip_optimal_control_b200._capi import lib
+
+    batch = 37
+    s, host = pg.lqr_benchmark_batch(n, m, T, batch, seed=11)
+    dims, topo = to_structs(s)
+    lqr = LQR(dims, topo, batch)
+    e = lqr.engine
+    inp, out = lqr.pack_input(host), lqr.alloc_output()
+    status = e.empty_int()
+    side = torch.cuda.Stream()
+    torch.cuda.synchronize()  # the packs above ran on torch's current stream
+    lqr.factor_solve(inp, out, status=status, stream=side)  # eager pass: sizes the workspaces
+    side.synchronize()
+    eager = lqr.unpack_output(out)
+    g = ctypes.c_void_p()
+    # misuse is reported, not fatal
+    assert lib.sipoc_graph_end(e._handle, int(side.cuda_stream), ctypes.byref(g)) == 1
+    lib.sipoc_profile_enable(e._handle, 1)
+    assert lib.sipoc_graph_begin(e._handle, int(side.cuda_stream)) == 1
+    lib.sipoc_profile_enable(e._handle, 0)
+    e._check(lib.sipoc_graph_begin(e._handle, int(side.cuda_stream)))
+    assert lib.sipoc_graph_begin(e._handle, int(side.cuda_stream)) == 1
+    lqr.factor_solve(inp, out, status=status, stream=side)
+    e._check(lib.sipoc_graph_end(e._handle, int(side.cuda_stream), ctypes.byref(g)))
+    kernels = lib.sipoc_graph_kernel_count(g)
+    assert kernels >= 1
+    for k in out:
+        out[k].zero_()
+    torch.cuda.synchronize()
+    before = e.launch_count
+    e._check(lib.sipoc_graph_launch(e._handle, g, int(side.cuda_stream)))
+    side.synchronize()
+    assert e.launch_count == before + kernels
+    replay = lqr.unpack_output(out)
+    for k in ("x", "u", "y"):
+        assert np.array_equal(replay[k], eager[k]), k
+    # new right-hand sides written in place
+    _, host2 = pg.lqr_benchmark_batch(n, m, T, batch, seed=12)
+    for k in ("q", "r", "c"):
+        inp[k].copy_(e.pack(host2[k]))
+    torch.cuda.synchronize()
+    e._check(lib.sipoc_graph_launch(e._handle, g, int(side.cuda_stream)))
+    side.synchronize()
+    h3 = dict(host)
+    h3.update({k: host2[k] for k in ("q", "r", "c")})
+    assert_lqr_parity(lqr.unpack_output(out), pyoracle.lqr_factor_solve(s, h3), REL_TOL)
+    lib.sipoc_graph_destroy(g)
