@@ -804,7 +804,9 @@ riccati_backward_cta(LqrIn pm, int *status_out, double *store, double *scratch, 
                             const double w = sdi_s[i] * ((i == j ? 1.0 : 0.0) - v) * sdi_s[j];
                             Wp[j * LDN + i] = w;
                             Wp[i * LDN + j] = w;
-                            Wst[static_cast<size_t>(k) * tri(N) + pk(i, j, N)] = w;
+                            // the store keeps P = F^-1: the rollout applies (I + D V)^-1 as
+                            // D^1/2 P D^-1/2 (lqr.cpp:531-549), which does not cancel at large delta
+                            Wst[static_cast<size_t>(k) * tri(N) + pk(i, j, N)] = v;
                           });
     __syncthreads();
     TICK(9);
@@ -955,7 +957,7 @@ __global__ void __launch_bounds__(kThreads)
 affine_backward_cta(LqrIn pm, const double *store, double *scratch, int64_t batch, int64_t ld,
                     int T) {
   using Zs = CtaSizes<N, M>;
-  __shared__ double v[N], f[N], g[N], h[M], kk[M];
+  __shared__ double v[N], f[N], g[N], h[M], kk[M], sdi[N];
   const int tid = threadIdx.x;
   const size_t b = blockIdx.x;
   const double *Wst = store + b * Zs::store(T) + Zs::oW(T);
@@ -976,10 +978,13 @@ affine_backward_cta(LqrIn pm, const double *store, double *scratch, int64_t batc
   __syncthreads();
   const int row = tid >> 2, part = tid & 3;  // 4 threads per output row (N <= 64)
   for (int k = T - 1; k >= 0; --k) {
-    for (int i = tid; i < N; i += kThreads)
-      f[i] = gd[(k + 1) * N + i] * v[i] - gc[(k + 1) * N + i];
+    for (int i = tid; i < N; i += kThreads) {
+      const double d = gd[(k + 1) * N + i];
+      sdi[i] = rsqrt(d);
+      f[i] = sdi[i] * (d * v[i] - gc[(k + 1) * N + i]);  // s = D^-1/2 (delta' o v' - c')
+    }
     __syncthreads();
-    {  // g = v - W' f
+    {  // g = v - W' (delta' o v' - c'),  W' z = D^-1/2 (s - P s) with the kept P = F^-1
       double acc = 0.0;
       if (row < N)
         for (int j = part; j < N; j += 4) {
@@ -988,7 +993,7 @@ affine_backward_cta(LqrIn pm, const double *store, double *scratch, int64_t batc
         }
       acc += __shfl_xor_sync(0xffffffffu, acc, 1);
       acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-      if (row < N && part == 0) g[row] = v[row] - acc;
+      if (row < N && part == 0) g[row] = v[row] - sdi[row] * (f[row] - acc);
     }
     __syncthreads();
     {  // h = r + B' g
@@ -1100,7 +1105,7 @@ rollout_forward_cta(LqrIn pm, LqrOut out, const double *store, const double *scr
   using St = RolloutStage<N, M>;
   extern __shared__ __align__(16) double sm[];
   __shared__ __align__(8) unsigned long long bar[2];
-  __shared__ double x[N], u[round16(M)], f[N], ax[N], red[kThreads], red2[kThreads];
+  __shared__ double x[N], u[round16(M)], f[N], ax[N], sdi[N], red[kThreads], red2[kThreads];
   const int tid = threadIdx.x;
   const size_t b = blockIdx.x;
   const size_t L_ = static_cast<size_t>(ld);
@@ -1165,20 +1170,26 @@ rollout_forward_cta(LqrIn pm, LqrOut out, const double *store, const double *scr
     return acc;
   };
 
-  // ---- root: f = delta v - c,  x = delta (W f) - f,  y = v - W f
+  // The store keeps P = F^-1 per node.  With s = D^-1/2 f and t = P s:
+  //   (I + D V)^-1 f = D^1/2 t (lqr.cpp:531-549),  W f = D^-1/2 (s - t).
+  // ---- root: f = delta v - c,  x = -(I + D V)^-1 f,  y = v - W f
   mbar_wait(&bar[0], 0);
   {
     const double *blk = sm;
-    if (tid < N) f[tid] = blk[St::od + tid] * blk[St::ov + tid] - blk[St::oc + tid];
+    if (tid < N) {
+      const double d = blk[St::od + tid];
+      sdi[tid] = rsqrt(d);
+      f[tid] = sdi[tid] * (d * blk[St::ov + tid] - blk[St::oc + tid]);
+    }
     __syncthreads();
     red[part * N + row] = w_times_f(blk + St::oW);
     __syncthreads();
     if (tid < N) {
-      const double wf = total(red, tid);
-      const double xi = blk[St::od + tid] * wf - f[tid];
+      const double t = total(red, tid);
+      const double xi = -blk[St::od + tid] * sdi[tid] * t;
       x[tid] = xi;
       __stcs(xo + static_cast<size_t>(tid) * L_, xi);
-      __stcs(yo + static_cast<size_t>(tid) * L_, blk[St::ov + tid] - wf);
+      __stcs(yo + static_cast<size_t>(tid) * L_, blk[St::ov + tid] - sdi[tid] * (f[tid] - t));
     }
     __syncthreads();  // slot 0 is free, x is visible
   }
@@ -1215,18 +1226,22 @@ rollout_forward_cta(LqrIn pm, LqrOut out, const double *store, const double *scr
       red[part * N + row] = acc;
     }
     __syncthreads();
-    if (tid < N)
-      f[tid] = blk[St::oc + tid] - blk[St::od + tid] * blk[St::ov + tid] + ax[tid] + total(red, tid);
+    if (tid < N) {
+      const double d = blk[St::od + tid];
+      sdi[tid] = rsqrt(d);
+      f[tid] = sdi[tid] * (blk[St::oc + tid] - d * blk[St::ov + tid] + ax[tid] + total(red, tid));
+    }
     __syncthreads();
-    // x' = f - delta' o (W' f),  y' = v' + W' f
+    // x' = D^1/2 P D^-1/2 f,  y' = v' + W' f
     red2[part * N + row] = w_times_f(blk + St::oW);
     __syncthreads();
     if (tid < N) {
-      const double wf = total(red2, tid);
-      const double xi = f[tid] - blk[St::od + tid] * wf;
+      const double t = total(red2, tid);
+      const double xi = blk[St::od + tid] * sdi[tid] * t;
       x[tid] = xi;
       __stcs(xo + (static_cast<size_t>(k + 1) * N + tid) * L_, xi);
-      __stcs(yo + (static_cast<size_t>(k + 1) * N + tid) * L_, blk[St::ov + tid] + wf);
+      __stcs(yo + (static_cast<size_t>(k + 1) * N + tid) * L_,
+             blk[St::ov + tid] + sdi[tid] * (f[tid] - t));
     }
     __syncthreads();  // this slot is free for the fetch of stage k + 2, x' is visible
   }

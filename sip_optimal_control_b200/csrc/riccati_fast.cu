@@ -88,6 +88,38 @@ __device__ __forceinline__ void cp_async_wait_all() {
 __device__ __forceinline__ double ldcs(const double *p) { return __ldcs(p); }
 __device__ __forceinline__ void stcs(double *p, double v) { __stcs(p, v); }
 
+// What the kept factorization holds per node is P = F^-1 = (I + D^1/2 V D^1/2)^-1 (packed
+// lower), not W: with s = D^-1/2 z and t = P s,
+//     (I + D V)^-1 z = D^1/2 t             the reference's F-solve form, lqr.cpp:531-549
+//     W z            = D^-1/2 (s - t)      W = D^-1/2 (I - P) D^-1/2, lqr.cpp:511-529
+// The rollout's x' = (I + D V)^-1 f formed as f - delta o (W f) cancels at large delta
+// (Newton-KKT: r2 up to 1e9 -> 1e-7 relative); D^1/2 P D^-1/2 f does not.
+// On return z holds W z and fz holds (I + D V)^-1 z.
+template <int N, class LoadP>
+__device__ __forceinline__ void apply_node(double (&z)[N], const double (&dd)[N], LoadP loadP,
+                                           double (&fz)[N]) {
+  double sdi[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    sdi[i] = rsqrt(dd[i]);
+    z[i] *= sdi[i];
+    fz[i] = 0.0;
+  }
+#pragma unroll
+  for (int j = 0; j < N; ++j)
+#pragma unroll
+    for (int i = j; i < N; ++i) {
+      const double p = loadP(pk(i, j, N));
+      fz[i] += p * z[j];
+      if (i != j) fz[j] += p * z[i];
+    }
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    z[i] = sdi[i] * (z[i] - fz[i]);
+    fz[i] *= dd[i] * sdi[i];
+  }
+}
+
 // ===========================================================================
 // Shared-memory map of one warp (rows of kTile doubles = 64 B).
 // ===========================================================================
@@ -703,7 +735,7 @@ riccati_backward_subwarp(LqrIn in, int *status_out, double *store, double *scrat
         if (xok[s] && i >= xj[s]) {
           SM(S::rW + xj[s] * S::P + i) = w;
           SM(S::rW + i * S::P + xj[s]) = w;
-          if (valid) stcs(dst, w);
+          if (valid) stcs(dst, y[i]);  // the store keeps P = F^-1
         }
         dst += ld;
       }
@@ -793,7 +825,7 @@ riccati_backward_thread(LqrIn in, int *status_out, double *store, double *scratc
         for (int p = i; p < N; ++p) fin += Li[pk(p, i, N)] * Li[pk(p, j, N)];
         const double w = sdi[i] * ((i == j ? 1.0 : 0.0) - fin) * sdi[j];
         W[pk(i, j, N)] = w;
-        stcs(Wst + (static_cast<int64_t>(k) * tri(N) + pk(i, j, N)) * ld, w);
+        stcs(Wst + (static_cast<int64_t>(k) * tri(N) + pk(i, j, N)) * ld, fin);  // P = F^-1
       }
 #pragma unroll
     for (int i = 0; i < N; ++i) {
@@ -1119,20 +1151,18 @@ affine_backward_staged(LqrIn in, const double *store, double *scratch, int64_t b
     cp_async_wait_group<NBUF - 1>();
     const double *S = sm_affine + static_cast<size_t>(buf) * R::kRows * 32 + lane;
 #define SR(row) S[(row) * 32]
-    double f[N], g[N];
+    double f[N], g[N], dd[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      f[i] = SR(R::rD + i) * v[i] - SR(R::rC + i);
-      g[i] = v[i];
+      dd[i] = SR(R::rD + i);
+      f[i] = dd[i] * v[i] - SR(R::rC + i);
+    }
+    {
+      double fz[N];
+      apply_node<N>(f, dd, [&](int t) { return SR(R::rW + t); }, fz);  // f <- W f
     }
 #pragma unroll
-    for (int j = 0; j < N; ++j)
-#pragma unroll
-      for (int i = j; i < N; ++i) {
-        const double w = SR(R::rW + pk(i, j, N));
-        g[i] -= w * f[j];
-        if (i != j) g[j] -= w * f[i];
-      }
+    for (int i = 0; i < N; ++i) g[i] = v[i] - f[i];
     double h[M];
 #pragma unroll
     for (int a = 0; a < M; ++a) {
@@ -1212,18 +1242,13 @@ affine_backward(LqrIn in, const double *store, double *scratch, int64_t batch, i
     }
     double f[N], g[N];
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-      f[i] = dv[i] * v[i] - cv[i];
-      g[i] = v[i];
+    for (int i = 0; i < N; ++i) f[i] = dv[i] * v[i] - cv[i];
+    {
+      double fz[N];
+      apply_node<N>(f, dv, [&](int t) { return wv[t]; }, fz);  // f <- W f
     }
 #pragma unroll
-    for (int j = 0; j < N; ++j)
-#pragma unroll
-      for (int i = j; i < N; ++i) {
-        const double w = wv[pk(i, j, N)];
-        g[i] -= w * f[j];
-        if (i != j) g[j] -= w * f[i];
-      }
+    for (int i = 0; i < N; ++i) g[i] = v[i] - f[i];
     double bv[N * M], kv[N * M], gv[tri(M)], rv[M];
 #pragma unroll
     for (int t = 0; t < N * M; ++t) {
@@ -1352,28 +1377,20 @@ rollout_forward_staged(LqrIn in, LqrOut out, const double *store, const double *
 
   double x[N];
   {  // root: x_0 = -(I - D W)(delta o v - c), y_0 = v - W (delta o v - c)
-    double f[N], wf[N], vv[N], dd[N];
+    double f[N], fz[N], vv[N], dd[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       vv[i] = ldcs(vst + static_cast<size_t>(i) * L_);
       dd[i] = ldcs(in.delta + static_cast<size_t>(i) * L_ + b);
       f[i] = dd[i] * vv[i] - ldcs(in.c + static_cast<size_t>(i) * L_ + b);
-      wf[i] = 0.0;
     }
-#pragma unroll
-    for (int j = 0; j < N; ++j)
-#pragma unroll
-      for (int i = j; i < N; ++i) {
-        const double w = ldcs(Wst + static_cast<size_t>(pk(i, j, N)) * L_);
-        wf[i] += w * f[j];
-        if (i != j) wf[j] += w * f[i];
-      }
+    apply_node<N>(f, dd, [&](int t) { return ldcs(Wst + static_cast<size_t>(t) * L_); }, fz);
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      x[i] = dd[i] * wf[i] - f[i];
+      x[i] = -fz[i];
       if (valid) {
         stcs(xo + static_cast<size_t>(i) * L_, x[i]);
-        stcs(yo + static_cast<size_t>(i) * L_, vv[i] - wf[i]);
+        stcs(yo + static_cast<size_t>(i) * L_, vv[i] - f[i]);
       }
     }
   }
@@ -1397,13 +1414,12 @@ rollout_forward_staged(LqrIn in, LqrOut out, const double *store, const double *
 #pragma unroll
     for (int a = 0; a < M; ++a)
       if (valid) stcs(uo + static_cast<size_t>(k * M + a) * L_, u[a]);
-    double f[N], vv[N], dd[N], wf[N];
+    double f[N], vv[N], dd[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       vv[i] = SR(R::rv + i);
       dd[i] = SR(R::rd + i);
       f[i] = SR(R::rc + i) - dd[i] * vv[i];
-      wf[i] = 0.0;
     }
 #pragma unroll
     for (int j = 0; j < N; ++j)
@@ -1413,21 +1429,13 @@ rollout_forward_staged(LqrIn in, LqrOut out, const double *store, const double *
     for (int a = 0; a < M; ++a)
 #pragma unroll
       for (int i = 0; i < N; ++i) f[i] += SR(R::rB + a * N + i) * u[a];
-#pragma unroll
-    for (int j = 0; j < N; ++j)
-#pragma unroll
-      for (int i = j; i < N; ++i) {
-        const double w = SR(R::rW + pk(i, j, N));
-        wf[i] += w * f[j];
-        if (i != j) wf[j] += w * f[i];
-      }
+    apply_node<N>(f, dd, [&](int t) { return SR(R::rW + t); }, x);  // x' = (I + D V)^-1 f, f <- W f
 #undef SR
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      x[i] = f[i] - dd[i] * wf[i];
       if (valid) {
         stcs(xo + static_cast<size_t>((k + 1) * N + i) * L_, x[i]);
-        stcs(yo + static_cast<size_t>((k + 1) * N + i) * L_, vv[i] + wf[i]);
+        stcs(yo + static_cast<size_t>((k + 1) * N + i) * L_, vv[i] + f[i]);
       }
     }
     buf = buf + 1 == NBUF ? 0 : buf + 1;
@@ -1454,27 +1462,19 @@ rollout_forward(LqrIn in, LqrOut out, const double *store, const double *scratch
 
   double x[N];
   {  // root: x_0 = -(I - D W)(delta o v - c), y_0 = v - W (delta o v - c)
-    double f[N], wf[N], vv[N], dd[N];
+    double f[N], fz[N], vv[N], dd[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       vv[i] = G(vst, i);
       dd[i] = G(in.delta, i);
       f[i] = dd[i] * vv[i] - G(in.c, i);
-      wf[i] = 0.0;
     }
-#pragma unroll
-    for (int j = 0; j < N; ++j)
-#pragma unroll
-      for (int i = j; i < N; ++i) {
-        const double w = G(Wst, pk(i, j, N));
-        wf[i] += w * f[j];
-        if (i != j) wf[j] += w * f[i];
-      }
+    apply_node<N>(f, dd, [&](int t) { return G(Wst, t); }, fz);
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      x[i] = dd[i] * wf[i] - f[i];
+      x[i] = -fz[i];
       stcs(xo + static_cast<size_t>(i) * L_, x[i]);
-      stcs(yo + static_cast<size_t>(i) * L_, vv[i] - wf[i]);
+      stcs(yo + static_cast<size_t>(i) * L_, vv[i] - f[i]);
     }
   }
   // Small shapes (the whole stage fits the register file twice): operands of stage
@@ -1539,13 +1539,12 @@ rollout_forward(LqrIn in, LqrOut out, const double *store, const double *scratch
         u[a] += (PREFETCH ? cK[j * M + a] : G(Kst, (k * N + j) * M + a)) * x[j];
 #pragma unroll
     for (int a = 0; a < M; ++a) stcs(uo + static_cast<size_t>(k * M + a) * L_, u[a]);
-    double f[N], vv[N], dd[N], wf[N];
+    double f[N], vv[N], dd[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       vv[i] = PREFETCH ? cv[i] : G(vst, (k + 1) * N + i);
       dd[i] = PREFETCH ? cd[i] : G(in.delta, (k + 1) * N + i);
       f[i] = (PREFETCH ? cc[i] : G(in.c, (k + 1) * N + i)) - dd[i] * vv[i];
-      wf[i] = 0.0;
     }
 #pragma unroll
     for (int j = 0; j < N; ++j)
@@ -1557,20 +1556,13 @@ rollout_forward(LqrIn in, LqrOut out, const double *store, const double *scratch
 #pragma unroll
       for (int i = 0; i < N; ++i)
         f[i] += (PREFETCH ? cB[a * N + i] : G(in.B, (k * M + a) * N + i)) * u[a];
-#pragma unroll
-    for (int j = 0; j < N; ++j)
-#pragma unroll
-      for (int i = j; i < N; ++i) {
-        const double w =
-            PREFETCH ? cW[pk(i, j, N)] : G(Wst, (k + 1) * tri(N) + pk(i, j, N));
-        wf[i] += w * f[j];
-        if (i != j) wf[j] += w * f[i];
-      }
+    // x' = (I + D V)^-1 f, f <- W f
+    apply_node<N>(
+        f, dd, [&](int t) { return PREFETCH ? cW[t] : G(Wst, (k + 1) * tri(N) + t); }, x);
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      x[i] = f[i] - dd[i] * wf[i];
       stcs(xo + static_cast<size_t>((k + 1) * N + i) * L_, x[i]);
-      stcs(yo + static_cast<size_t>((k + 1) * N + i) * L_, vv[i] + wf[i]);
+      stcs(yo + static_cast<size_t>((k + 1) * N + i) * L_, vv[i] + f[i]);
     }
   }
 #undef G
@@ -1651,23 +1643,21 @@ affine_backward_kkt(KktView kv, const double *store, double *scratch, int64_t ba
 #pragma unroll
   for (int i = 0; i < N; ++i) stcs(vst + static_cast<int64_t>(T * N + i) * ld, v[i]);
   for (int k = T - 1; k >= 0; --k) {
-    double wv[tri(N)], f[N], g[N];
+    double wv[tri(N)], f[N], g[N], dd[N];
 #pragma unroll
     for (int u = 0; u < tri(N); ++u) wv[u] = G(Wst, (k + 1) * tri(N) + u);
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       // c_mod = -b_ydyn (helpers.cpp:777), delta = dyn_r2
-      f[i] = G(kv.ws.dyn_r2, (k + 1) * N + i) * v[i] + G(kv.b, xd + t.y_dyn[k + 1] + i);
-      g[i] = v[i];
+      dd[i] = G(kv.ws.dyn_r2, (k + 1) * N + i);
+      f[i] = dd[i] * v[i] + G(kv.b, xd + t.y_dyn[k + 1] + i);
+    }
+    {
+      double fz[N];
+      apply_node<N>(f, dd, [&](int u) { return wv[u]; }, fz);  // f <- W f
     }
 #pragma unroll
-    for (int j = 0; j < N; ++j)
-#pragma unroll
-      for (int i = j; i < N; ++i) {
-        const double w = wv[pk(i, j, N)];
-        g[i] -= w * f[j];
-        if (i != j) g[j] -= w * f[i];
-      }
+    for (int i = 0; i < N; ++i) g[i] = v[i] - f[i];
     double qv[N], rv[M];
     node_q(k, qv);
     edge_qr(k, qv, rv);
@@ -1775,27 +1765,19 @@ rollout_forward_kkt(KktView kv, const double *store, const double *scratch, int6
 
   double x[N];
   {  // root
-    double f[N], wf[N], vv[N], dd[N];
+    double f[N], fz[N], vv[N], dd[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       vv[i] = G(vst, i);
       dd[i] = G(kv.ws.dyn_r2, i);
       f[i] = dd[i] * vv[i] + G(kv.b, xd + t.y_dyn[0] + i);  // delta o v - c, c = -b_ydyn
-      wf[i] = 0.0;
     }
-#pragma unroll
-    for (int j = 0; j < N; ++j)
-#pragma unroll
-      for (int i = j; i < N; ++i) {
-        const double w = G(Wst, pk(i, j, N));
-        wf[i] += w * f[j];
-        if (i != j) wf[j] += w * f[i];
-      }
+    apply_node<N>(f, dd, [&](int u) { return G(Wst, u); }, fz);
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      x[i] = dd[i] * wf[i] - f[i];
+      x[i] = -fz[i];
       SOL(t.x_state[0] + i) = x[i];
-      SOL(xd + t.y_dyn[0] + i) = vv[i] - wf[i];
+      SOL(xd + t.y_dyn[0] + i) = vv[i] - f[i];
     }
   }
   for (int k = 0; k < T; ++k) {
@@ -1810,13 +1792,12 @@ rollout_forward_kkt(KktView kv, const double *store, const double *scratch, int6
     for (int a = 0; a < M; ++a) SOL(t.x_control[k] + a) = u[a];
     recover_node(k, x);
     recover_edge(k, x, u);
-    double f[N], vv[N], dd[N], wf[N];
+    double f[N], vv[N], dd[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       vv[i] = G(vst, (k + 1) * N + i);
       dd[i] = G(kv.ws.dyn_r2, (k + 1) * N + i);
       f[i] = -G(kv.b, xd + t.y_dyn[k + 1] + i) - dd[i] * vv[i];  // c' - delta' o v'
-      wf[i] = 0.0;
     }
 #pragma unroll
     for (int j = 0; j < N; ++j)
@@ -1826,19 +1807,12 @@ rollout_forward_kkt(KktView kv, const double *store, const double *scratch, int6
     for (int a = 0; a < M; ++a)
 #pragma unroll
       for (int i = 0; i < N; ++i) f[i] += G(kv.mdl.edge_B, (k * M + a) * N + i) * u[a];
-#pragma unroll
-    for (int j = 0; j < N; ++j)
-#pragma unroll
-      for (int i = j; i < N; ++i) {
-        const double w = G(Wst, (k + 1) * tri(N) + pk(i, j, N));
-        wf[i] += w * f[j];
-        if (i != j) wf[j] += w * f[i];
-      }
+    // x' = (I + D V)^-1 f, f <- W f
+    apply_node<N>(f, dd, [&](int u) { return G(Wst, (k + 1) * tri(N) + u); }, x);
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      x[i] = f[i] - dd[i] * wf[i];
       SOL(t.x_state[k + 1] + i) = x[i];
-      SOL(xd + t.y_dyn[k + 1] + i) = vv[i] + wf[i];
+      SOL(xd + t.y_dyn[k + 1] + i) = vv[i] + f[i];
     }
   }
   recover_node(T, x);

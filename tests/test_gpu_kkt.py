@@ -61,23 +61,40 @@ def _uniform_kkt_structure(n, m, T):
                            edge_g=[g] * T)
 
 
-@pytest.mark.parametrize("n,m,T", [(4, 1, 16), (12, 4, 12), (6, 2, 20), (16, 4, 6)])
+def _oracle_residual(s, model, w, r1, r2, r3, sol, rhs):
+    return np.linalg.norm(pyoracle.kkt_apply(s, model, w, r1, r2, r3, sol, np.zeros_like(sol))
+                          - rhs, axis=1)
+
+
+@pytest.mark.parametrize("n,m,T", [(4, 1, 16), (12, 4, 12), (6, 2, 20), (8, 3, 9), (16, 4, 6),
+                                   (32, 8, 3)])
 @pytest.mark.parametrize("force_generic", [True, False])
-def test_newton_kkt_benchmark_shapes(n, m, T, force_generic):
-    # Moderate regularization range (r2 <= 1e3) where two correct FP64
-    # orderings agree to 1e-9; the full 1e9 range is covered below against
-    # the residual instead ("parity on ill-conditioned
-    # regularization").
+@pytest.mark.parametrize("r2_max", [1e3, 1e9])
+def test_newton_kkt_benchmark_shapes(n, m, T, force_generic, r2_max):
+    # r2_max = 1e9 is the reference benchmark's own regularization range
+    # (newton_kkt_benchmark.cpp:231-233).  The shape-specialised kernels apply
+    # (I + D V)^-1 in the reference's F-solve form (lqr.cpp:531-549), so the DEFAULT
+    # dispatch stays within 1e-9 of the oracle over the whole range, like the
+    # reference-order generic kernels.
     s = _uniform_kkt_structure(n, m, T)
     batch = 33
-    model, w, r1, r2, r3, rhs = pg.newton_kkt_batch(s, batch, seed=n * 100 + m, r2_max=1e3)
+    model, w, r1, r2, r3, rhs = pg.newton_kkt_batch(s, batch, seed=n * 100 + m, r2_max=r2_max)
     ref = pyoracle.kkt_factor_solve(s, model, w, r1, r2, r3, rhs)
-    assert (ref["ok"] == 1).all()
+    good = ref["ok"] == 1
+    assert good.sum() >= batch - 2
     gpu, cp, dev = _gpu_kkt(s, model, w, r1, r2, r3, rhs, force_generic=force_generic)
-    assert (gpu["ok"] == 1).all()
-    assert rel_err(gpu["sol"], ref["sol"]).max() < REL_TOL
+    if not force_generic:
+        assert "generic" not in cp.engine.kernel_variant, cp.engine.kernel_variant
+    assert (gpu["ok"] == ref["ok"]).all()
+    assert rel_err(gpu["sol"][good], ref["sol"][good]).max() < REL_TOL
     scale = np.linalg.norm(rhs, axis=1)
-    assert (gpu["residual"] / scale).max() < 1e-9
+    if r2_max <= 1e3:
+        assert (gpu["residual"] / scale)[good].max() < 1e-9
+    else:
+        # at r2 up to 1e9 the residual is the conditioning of the problem (the reference's
+        # own order leaves ~1e-6): the device path must not be worse than the oracle's
+        ref_res = _oracle_residual(s, model, w, r1, r2, r3, ref["sol"], rhs)
+        assert (gpu["residual"][good] / scale[good]).max() <= 10.0 * (ref_res[good] / scale[good]).max()
     # add_Kx_to_y parity on an arbitrary vector
     dm, dw, dr1, dr2, dr3, _ = dev
     xv = np.random.default_rng(1).standard_normal(rhs.shape)
@@ -219,6 +236,30 @@ def test_variable_dimension_kkt_tiling():
     assert (gpu["ok"] == 1).all()
     assert rel_err(gpu["sol"], ref["sol"]).max() < REL_TOL
     assert gpu["stats"][3] == batch and gpu["stats"][2] == 0
+    fpad, _, _ = _gpu_kkt(s, fm, fw, fr1, fr2, fr3, frhs, pad_variable_dims=True)
+    assert (fpad["ok"] == fref["ok"]).all()
+    assert rel_err(fpad["sol"][good], fref["sol"][good]).max() < REL_TOL
+
+
+def test_config4_full_horizon_matches_oracle():
+    # BASELINE config 4 at the horizon bench.py runs it on (T = 48), r2 up to 1e9.
+    reps = 16
+    sd = [2, 1, 3] * reps + [2]
+    T = len(sd) - 1
+    cd = ([1, 2, 1] * reps)[:T]
+    s = Structure.chain(T, sd, cd, node_c=([1, 0, 2] * reps + [1])[:T + 1],
+                        node_g=([0, 2, 1] * reps + [0])[:T + 1], edge_c=([1, 2, 0] * reps)[:T],
+                        edge_g=([2, 1, 1] * reps)[:T])
+    assert T == 48
+    batch = 64
+    model, w, r1, r2, r3, rhs = pg.newton_kkt_batch(s, batch, seed=48, r2_max=1e9)
+    ref = pyoracle.kkt_factor_solve(s, model, w, r1, r2, r3, rhs)
+    good = ref["ok"] == 1
+    assert good.sum() >= batch - 2
+    gpu, cp, _ = _gpu_kkt(s, model, w, r1, r2, r3, rhs)
+    assert cp.engine.kernel_variant == "padded_to_strict_thread_n3_m2", cp.engine.kernel_variant
+    assert (gpu["ok"] == ref["ok"]).all()
+    assert rel_err(gpu["sol"][good], ref["sol"][good]).max() < REL_TOL
 
 
 def test_factor_rejects_nonpositive_regularization_per_problem():
@@ -257,17 +298,22 @@ def test_fused_kkt_solve_path_large_batch():
     build inside the affine sweep, dual recovery inside the rollout); same parity bar."""
     n, m, T, batch = 4, 1, 6, 32768 + 5
     s = _uniform_kkt_structure(n, m, T)
-    model, w, r1, r2, r3, rhs = pg.newton_kkt_batch(s, batch, seed=21, r2_max=1e3)
+    model, w, r1, r2, r3, rhs = pg.newton_kkt_batch(s, batch, seed=21, r2_max=1e9)
     sample = np.r_[0:64, batch - 64:batch]
     sub = lambda a: a[sample]
     ref = pyoracle.kkt_factor_solve(s, {k: sub(v) for k, v in model.items()}, sub(w), sub(r1),
                                     sub(r2), sub(r3), sub(rhs))
     gpu, cp, dev = _gpu_kkt(s, model, w, r1, r2, r3, rhs)
     assert "generic" not in cp.engine.kernel_variant
-    assert gpu["ok"].all()
-    assert rel_err(gpu["sol"][sample], ref["sol"]).max() < 1e-9
-    scale = np.linalg.norm(rhs, axis=1)
-    assert (gpu["residual"] / scale).max() < 1e-9
+    good = ref["ok"] == 1
+    assert good.sum() >= sample.size - 4
+    assert (gpu["ok"][sample] == ref["ok"]).all()
+    assert rel_err(gpu["sol"][sample][good], ref["sol"][good]).max() < 1e-9
+    ref_res = _oracle_residual(s, {k: sub(v) for k, v in model.items()}, sub(w), sub(r1), sub(r2),
+                               sub(r3), ref["sol"], sub(rhs))
+    scale = np.linalg.norm(rhs, axis=1)[sample]
+    assert (gpu["residual"][sample][good] / scale[good]).max() <= \
+        10.0 * (ref_res[good] / scale[good]).max()
 
 
 @pytest.mark.parametrize("uniform", [True, False])

@@ -204,6 +204,20 @@ def test_benchmark_chains_match_oracle(n, m, T, force_generic):
         assert "generic" not in lqr.engine.kernel_variant, lqr.engine.kernel_variant
 
 
+@pytest.mark.parametrize("n,m,T,batch", [(64, 24, 32, 4), (12, 4, 50, 24), (4, 1, 100, 40)])
+@pytest.mark.parametrize("fused", [True, False])
+def test_baseline_horizons_match_oracle(n, m, T, batch, fused):
+    # The BASELINE configs at their full horizon (humanoid T = 32, quadrotor T = 50,
+    # cartpole T = 100) on a small batch, element-wise against the oracle.
+    s, host = pg.lqr_benchmark_batch(n, m, T, batch, seed=n + T)
+    ref = pyoracle.lqr_factor_solve(s, host)
+    assert (ref["status"] == 0).all()
+    gpu, lqr = gpu_lqr_factor_solve(s, host, fused=fused)
+    assert "generic" not in lqr.engine.kernel_variant
+    assert (gpu["status"] == 0).all()
+    assert_lqr_parity(gpu, ref, REL_TOL)
+
+
 @pytest.mark.parametrize("n,m,T", [(4, 1, 20), (12, 4, 10), (5, 2, 7), (16, 4, 6), (64, 24, 3)])
 def test_factor_once_solve_many(n, m, T):
     # BM_LQRSolve semantics (lqr_benchmark.cpp:611-638): re-solve with new
