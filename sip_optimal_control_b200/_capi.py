@@ -12,7 +12,8 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libsipoc.so")
+# SIPOC_LIB_PATH: development override (tools/build_variant.sh), another build of the same library
+LIB_PATH = os.environ.get("SIPOC_LIB_PATH") or os.path.join(_HERE, "lib", "libsipoc.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "sipoc.h")
 
 c_int_p = ctypes.POINTER(ctypes.c_int)

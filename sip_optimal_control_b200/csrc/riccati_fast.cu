@@ -39,10 +39,14 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 
 namespace sipoc {
 namespace {
 
+#ifndef SIPOC_FUSED_PF
+#define SIPOC_FUSED_PF 0
+#endif
 constexpr int kGroup = 4;  // lanes per problem
 constexpr int kTile = 8;   // problems per warp
 
@@ -52,6 +56,8 @@ __host__ __device__ constexpr int pk(int i, int j, int n) {
   return j * n - j * (j - 1) / 2 + (i - j);
 }
 __host__ __device__ constexpr int cdiv(int a, int b) { return (a + b - 1) / b; }
+// Packed lower, column-major: first row of column j minus j, so that (i, j) is colbase(j) + i.
+__host__ __device__ constexpr int colbase(int j, int n) { return j * n - j * (j - 1) / 2 - j; }
 
 // Per-problem element counts of the kept factorization and the rollout spill.
 template <int N, int M>
@@ -72,6 +78,9 @@ __device__ __forceinline__ void cp_async16(double *smem, const double *gmem) {
 __device__ __forceinline__ void cp_async8(double *smem, const double *gmem) {
   const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const double *gmem) {
+  asm volatile("prefetch.global.L2 [%0];\n" ::"l"(gmem));
 }
 __device__ __forceinline__ void cp_async_commit() {
   asm volatile("cp.async.commit_group;\n" ::: "memory");
@@ -123,14 +132,17 @@ __device__ __forceinline__ void apply_node(double (&z)[N], const double (&dd)[N]
 // ===========================================================================
 // Shared-memory map of one warp (rows of kTile doubles = 64 B).
 // ===========================================================================
-template <int N, int M>
+// PACKW: W packed and no pitch padding -- 494 rows at (12, 4), seven warps per SM -- for
+// grids of a few waves (and the fused rollout); otherwise W full with an odd column pitch,
+// 592 rows, six warps per SM, the faster map when the grid is many waves deep.
+template <int N, int M, bool PACKW>
 struct Smem {
   static constexpr int NZ = N + M;
   // Column pitch of every array whose columns are read by different lanes of a problem
   // at the same time (Z, M, W, Psi_xu): an ODD number of 64-byte rows, so the four
-  // lanes' rows alternate between the two halves of the 32 banks (pitch N = 12 put them
-  // all in one half: 4 wavefronts per load instead of 2).
-  static constexpr int P = (N % 2 == 0) ? N + 1 : N;
+  // lanes' rows alternate between the two halves of the 32 banks (pitch N = 12 puts them
+  // all in one half: 4 wavefronts per load instead of 2).  No padding in the packed map.
+  static constexpr int P = (N % 2 == 0 && !PACKW) ? N + 1 : N;
   static constexpr int rZ = 0;                // [B | A], column-major, pitch P
   static constexpr int rQ = rZ + NZ * P;      // Q_k, packed lower
   static constexpr int rM = rQ + tri(N);      // M_k, N x M column-major, pitch P
@@ -140,9 +152,11 @@ struct Smem {
   static constexpr int rc = rr + M;           // c_{k+1}
   static constexpr int rd = rc + N;           // delta_k (as staged)
   static constexpr int kStaged = rd + N;
-  static constexpr int rW = kStaged;          // W of the last processed node, full, pitch P
+  // W of the last processed node: full (pitch P), or PACKED lower (column-major): entry
+  // (i, j), i >= j, at row colbase(j) + i, colbase(j) = pk(j, j) - j.
+  static constexpr int rW = kStaged;
   static constexpr int rG = rc;               // g overwrites c (dead once f is formed)
-  static constexpr int rV = rW + N * P;       // v of the last processed node
+  static constexpr int rV = rW + (PACKW ? tri(N) : N * P);  // v of the last processed node
   static constexpr int rDl = rV + N;          // delta of the last processed node
   static constexpr int rSd = rDl + N;         // sqrt(delta), 1/sqrt(delta) of the node in flight
   static constexpr int rSdi = rSd + N;
@@ -172,11 +186,10 @@ __device__ __forceinline__ void stage_run(double *dst, const double *src, int64_
 }
 
 // `count` consecutive flat elements of a column-major block with N rows per column
-// -> shared-memory columns of pitch N + 1 (even N) rows.
-template <int N>
+// -> shared-memory columns of pitch P rows.
+template <int N, int P>
 __device__ __forceinline__ void stage_cols(double *dst0, const double *src, int64_t ld8,
                                            int count, int lane) {
-  constexpr int P = (N % 2 == 0) ? N + 1 : N;
   const int sub = lane & 3, rr = lane >> 2;
 #pragma unroll
   for (int i0 = 0; i0 < count; i0 += 8) {
@@ -201,11 +214,21 @@ __device__ __forceinline__ void stage_lower(double *dst, const double *src, int6
 // ===========================================================================
 // Backward sweep, four lanes per problem, WARPS warps (8 problems each) per CTA.
 // ===========================================================================
-template <int N, int M, bool SOLVE, int WARPS>
+//
+// FUSED (factor + solve in one call): the warp rolls its own eight problems forward
+// right after their backward sweep -- root solve, rollout, costates (lqr.cpp:798-870) --
+// with the four lanes of a problem sharing the matrix-vector products and the operands
+// of every stage (A, B from the inputs; K, k, P, v from the spill the sweep has just
+// written; c, delta) brought in by cp.async one half-stage ahead of their use.  The
+// rollout of one tile hides under the DFMA-bound sweeps of the other tiles of the SM:
+// the step costs the backward sweep plus a few per cent instead of sweep + rollout, and
+// a shard of a few thousand problems no longer pays a latency-bound rollout kernel.
+template <int N, int M, bool SOLVE, int WARPS, bool FUSED = false, bool PACKW = FUSED>
 __global__ void __launch_bounds__(32 * WARPS)
-riccati_backward_subwarp(LqrIn in, int *status_out, double *store, double *scratch,
+riccati_backward_subwarp(LqrIn in, LqrOut out, int *status_out, double *store, double *scratch,
                          int64_t batch, int64_t ld, int T) {
-  using S = Smem<N, M>;
+  static_assert(SOLVE || !FUSED, "the fused rollout needs the affine sweep");
+  using S = Smem<N, M, PACKW>;
   using Z = FastSizes<N, M>;
   constexpr int SX = cdiv(N, kGroup);  // own state columns per lane
   constexpr int SU = cdiv(M, kGroup);  // own control columns per lane
@@ -270,8 +293,8 @@ riccati_backward_subwarp(LqrIn in, int *status_out, double *store, double *scrat
       pq -= static_cast<int64_t>(N) * ld;
     }
     if (with_edge) {
-      stage_cols<N>(sm + S::rZ * kTile, pB, ld8, N * M, lane);
-      stage_cols<N>(sm + (S::rZ + M * S::P) * kTile, pA, ld8, N * N, lane);
+      stage_cols<N, S::P>(sm + S::rZ * kTile, pB, ld8, N * M, lane);
+      stage_cols<N, S::P>(sm + (S::rZ + M * S::P) * kTile, pA, ld8, N * N, lane);
       pB -= static_cast<int64_t>(N) * M * ld;
       pA -= static_cast<int64_t>(N) * N * ld;
       if (SOLVE) {
@@ -289,7 +312,7 @@ riccati_backward_subwarp(LqrIn in, int *status_out, double *store, double *scrat
     stage_lower<N>(sdst + S::rQ * kTile, pQ, ld, ld8, rr);
     pQ -= static_cast<int64_t>(N) * N * ld;
     if (with_edge) {
-      stage_cols<N>(sm + S::rM * kTile, pM, ld8, N * M, lane);
+      stage_cols<N, S::P>(sm + S::rM * kTile, pM, ld8, N * M, lane);
       stage_lower<M>(sdst + S::rR * kTile, pR, ld, ld8, rr);
       pM -= static_cast<int64_t>(N) * M * ld;
       pR -= static_cast<int64_t>(M) * M * ld;
@@ -360,7 +383,11 @@ riccati_backward_subwarp(LqrIn in, int *status_out, double *store, double *scrat
         for (int s = 0; s < SX; ++s) {
           double acc = 0.0;
 #pragma unroll
-          for (int q = 0; q < N; ++q) acc += SM(S::rW + q * S::P + xj[s]) * f[q];  // W' symmetric
+          for (int q = 0; q < N; ++q) {  // W'(xj, q): symmetric / from the packed lower triangle
+            const int idx = !PACKW ? q * S::P + xj[s]
+                                   : ((q < xj[s]) ? colbase(q, N) + xj[s] : qcol[s] + q);
+            acc += SM(S::rW + idx) * f[q];
+          }
           if (xok[s]) SM(S::rG + xj[s]) = SM(S::rV + xj[s]) - acc;
         }
       }
@@ -407,79 +434,180 @@ riccati_backward_subwarp(LqrIn in, int *status_out, double *store, double *scrat
           for (int s = 0; s < SX; ++s) vv[s] += zx[s][q] * gq;
         }
       }
-      // The first half of each W' row is fetched one iteration ahead (wpre), so the
-      // dot products start without waiting on shared memory; the second half and the
-      // Z row are in flight while they run.
-      constexpr int H = N / 2;
-      double wpre[H];
+      if constexpr (PACKW) {
+        // The first half of each W' row is fetched one iteration ahead (wpre), so the
+        // dot products start without waiting on shared memory; the second half and the
+        // Z row are in flight while they run.  W' is packed: entry (p, q) sits at row
+        // colbase(q) + p left of the diagonal and at colbase(p) + q from the diagonal on, so
+        // the rolled loop over p runs in blocks of four rows -- for every q outside the block
+        // the side of the diagonal is known at compile time, inside it is one select.
+        constexpr int H = N / 2;
+        double wpre[H];
 #pragma unroll
-      for (int q = 0; q < H; ++q) wpre[q] = sm[(S::rW + q) * kTile + prob];
+        for (int q = 0; q < H; ++q) wpre[q] = sm[(S::rW + q) * kTile + prob];  // row 0
+        const double *smW = sm + S::rW * kTile + prob;
+        auto p_block = [&](auto pb_tag) {
+          constexpr int LO = 4 * decltype(pb_tag)::value;
+          constexpr int HI = LO + 3 < N - 1 ? LO + 3 : N - 1;  // rows LO .. HI
+          int cb = colbase(LO, N);                              // colbase(p)
 #pragma unroll 1
-      for (int p = 0; p < N; ++p) {
-        const double *wrow = sm + (S::rW + p * S::P) * kTile + prob;
-        const double *zrow = sm + (S::rZ + p) * kTile + prob;
-        double wlate[N - H];
+          for (int p = LO; p <= HI; ++p) {
+            const double *zrow = sm + (S::rZ + p) * kTile + prob;
+            double wlate[N - H];
 #pragma unroll
-        for (int q = H; q < N; ++q) wlate[q - H] = wrow[q * kTile];
-        double su[SU], sx[SX], su2[SU], sx2[SX];
+            for (int q = H; q < N; ++q) {
+              const int idx = (q < LO) ? colbase(q, N) + p
+                                       : ((q >= HI) ? cb + q : (q < p ? colbase(q, N) + p : cb + q));
+              wlate[q - H] = smW[idx * kTile];
+            }
+            double su[SU], sx[SX], su2[SU], sx2[SX];
 #pragma unroll
-        for (int s = 0; s < SU; ++s) su[s] = su2[s] = 0.0;
+            for (int s = 0; s < SU; ++s) su[s] = su2[s] = 0.0;
 #pragma unroll
-        for (int s = 0; s < SX; ++s) sx[s] = sx2[s] = 0.0;
+            for (int s = 0; s < SX; ++s) sx[s] = sx2[s] = 0.0;
 #pragma unroll
-        for (int q = 0; q < H; ++q) {
-          const double w = wpre[q];
-          if (q & 1) {
+            for (int q = 0; q < H; ++q) {
+              const double w = wpre[q];
+              if (q & 1) {
 #pragma unroll
-            for (int s = 0; s < SU; ++s) su2[s] += w * zu[s][q];
+                for (int s = 0; s < SU; ++s) su2[s] += w * zu[s][q];
 #pragma unroll
-            for (int s = 0; s < SX; ++s) sx2[s] += w * zx[s][q];
-          } else {
+                for (int s = 0; s < SX; ++s) sx2[s] += w * zx[s][q];
+              } else {
 #pragma unroll
-            for (int s = 0; s < SU; ++s) su[s] += w * zu[s][q];
+                for (int s = 0; s < SU; ++s) su[s] += w * zu[s][q];
 #pragma unroll
-            for (int s = 0; s < SX; ++s) sx[s] += w * zx[s][q];
+                for (int s = 0; s < SX; ++s) sx[s] += w * zx[s][q];
+              }
+            }
+            if (p + 1 < N) {  // prefetch the head of the next row, pn = p + 1 in LO + 1 .. HI + 1
+              const int pn = p + 1, cbn = cb + (N - 1 - p);
+#pragma unroll
+              for (int q = 0; q < H; ++q) {
+                const int idx = (q < LO + 1) ? colbase(q, N) + pn
+                                             : ((q >= HI + 1) ? cbn + q
+                                                              : (q < pn ? colbase(q, N) + pn : cbn + q));
+                wpre[q] = smW[idx * kTile];
+              }
+            }
+#pragma unroll
+            for (int q = H; q < N; ++q) {
+              const double w = wlate[q - H];
+              if (q & 1) {
+#pragma unroll
+                for (int s = 0; s < SU; ++s) su2[s] += w * zu[s][q];
+#pragma unroll
+                for (int s = 0; s < SX; ++s) sx2[s] += w * zx[s][q];
+              } else {
+#pragma unroll
+                for (int s = 0; s < SU; ++s) su[s] += w * zu[s][q];
+#pragma unroll
+                for (int s = 0; s < SX; ++s) sx[s] += w * zx[s][q];
+              }
+            }
+#pragma unroll
+            for (int s = 0; s < SU; ++s) su[s] += su2[s];
+#pragma unroll
+            for (int s = 0; s < SX; ++s) sx[s] += sx2[s];
+#pragma unroll
+            for (int i = 0; i < M; ++i) {  // B(p, i)
+              const double z = zrow[i * S::P * kTile];
+#pragma unroll
+              for (int s = 0; s < SU; ++s)
+                if (i >= kGroup * s) Puu[s][i] += z * su[s];
+            }
+#pragma unroll
+            for (int x = 0; x < N; ++x) {  // A(p, x)
+              const double z = zrow[(M + x) * S::P * kTile];
+#pragma unroll
+              for (int s = 0; s < SU; ++s) Pxu[s][x] += z * su[s];
+#pragma unroll
+              for (int s = 0; s < SX; ++s)
+                if (x >= kGroup * s) V[s][x] += z * sx[s];
+            }
+            cb += N - 1 - p;
           }
-        }
-        {  // prefetch the head of the next row (row 0 again on the last iteration)
-          const double *wnext = sm + (S::rW + (p + 1 < N ? p + 1 : 0) * S::P) * kTile + prob;
+        };
+        p_block(std::integral_constant<int, 0>{});
+        if constexpr (N > 4) p_block(std::integral_constant<int, 1>{});
+        if constexpr (N > 8) p_block(std::integral_constant<int, 2>{});
+        if constexpr (N > 12) p_block(std::integral_constant<int, 3>{});
+        static_assert(N <= 16, "p loop blocks cover N <= 16");
+      } else {
+        // The first half of each W' row is fetched one iteration ahead (wpre), so the
+        // dot products start without waiting on shared memory; the second half and the
+        // Z row are in flight while they run.
+        constexpr int H = N / 2;
+        double wpre[H];
 #pragma unroll
-          for (int q = 0; q < H; ++q) wpre[q] = wnext[q * kTile];
-        }
+        for (int q = 0; q < H; ++q) wpre[q] = sm[(S::rW + q) * kTile + prob];
+#pragma unroll 1
+        for (int p = 0; p < N; ++p) {
+          const double *wrow = sm + (S::rW + p * S::P) * kTile + prob;
+          const double *zrow = sm + (S::rZ + p) * kTile + prob;
+          double wlate[N - H];
 #pragma unroll
-        for (int q = H; q < N; ++q) {
-          const double w = wlate[q - H];
-          if (q & 1) {
+          for (int q = H; q < N; ++q) wlate[q - H] = wrow[q * kTile];
+          double su[SU], sx[SX], su2[SU], sx2[SX];
 #pragma unroll
-            for (int s = 0; s < SU; ++s) su2[s] += w * zu[s][q];
+          for (int s = 0; s < SU; ++s) su[s] = su2[s] = 0.0;
 #pragma unroll
-            for (int s = 0; s < SX; ++s) sx2[s] += w * zx[s][q];
-          } else {
+          for (int s = 0; s < SX; ++s) sx[s] = sx2[s] = 0.0;
 #pragma unroll
-            for (int s = 0; s < SU; ++s) su[s] += w * zu[s][q];
+          for (int q = 0; q < H; ++q) {
+            const double w = wpre[q];
+            if (q & 1) {
 #pragma unroll
-            for (int s = 0; s < SX; ++s) sx[s] += w * zx[s][q];
+              for (int s = 0; s < SU; ++s) su2[s] += w * zu[s][q];
+#pragma unroll
+              for (int s = 0; s < SX; ++s) sx2[s] += w * zx[s][q];
+            } else {
+#pragma unroll
+              for (int s = 0; s < SU; ++s) su[s] += w * zu[s][q];
+#pragma unroll
+              for (int s = 0; s < SX; ++s) sx[s] += w * zx[s][q];
+            }
           }
-        }
+          {  // prefetch the head of the next row (row 0 again on the last iteration)
+            const double *wnext = sm + (S::rW + (p + 1 < N ? p + 1 : 0) * S::P) * kTile + prob;
 #pragma unroll
-        for (int s = 0; s < SU; ++s) su[s] += su2[s];
+            for (int q = 0; q < H; ++q) wpre[q] = wnext[q * kTile];
+          }
 #pragma unroll
-        for (int s = 0; s < SX; ++s) sx[s] += sx2[s];
+          for (int q = H; q < N; ++q) {
+            const double w = wlate[q - H];
+            if (q & 1) {
 #pragma unroll
-        for (int i = 0; i < M; ++i) {  // B(p, i)
-          const double z = zrow[i * S::P * kTile];
+              for (int s = 0; s < SU; ++s) su2[s] += w * zu[s][q];
 #pragma unroll
-          for (int s = 0; s < SU; ++s)
-            if (i >= kGroup * s) Puu[s][i] += z * su[s];
-        }
+              for (int s = 0; s < SX; ++s) sx2[s] += w * zx[s][q];
+            } else {
 #pragma unroll
-        for (int x = 0; x < N; ++x) {  // A(p, x)
-          const double z = zrow[(M + x) * S::P * kTile];
+              for (int s = 0; s < SU; ++s) su[s] += w * zu[s][q];
 #pragma unroll
-          for (int s = 0; s < SU; ++s) Pxu[s][x] += z * su[s];
+              for (int s = 0; s < SX; ++s) sx[s] += w * zx[s][q];
+            }
+          }
 #pragma unroll
-          for (int s = 0; s < SX; ++s)
-            if (x >= kGroup * s) V[s][x] += z * sx[s];
+          for (int s = 0; s < SU; ++s) su[s] += su2[s];
+#pragma unroll
+          for (int s = 0; s < SX; ++s) sx[s] += sx2[s];
+#pragma unroll
+          for (int i = 0; i < M; ++i) {  // B(p, i)
+            const double z = zrow[i * S::P * kTile];
+#pragma unroll
+            for (int s = 0; s < SU; ++s)
+              if (i >= kGroup * s) Puu[s][i] += z * su[s];
+          }
+#pragma unroll
+          for (int x = 0; x < N; ++x) {  // A(p, x)
+            const double z = zrow[(M + x) * S::P * kTile];
+#pragma unroll
+            for (int s = 0; s < SU; ++s) Pxu[s][x] += z * su[s];
+#pragma unroll
+            for (int s = 0; s < SX; ++s)
+              if (x >= kGroup * s) V[s][x] += z * sx[s];
+          }
         }
       }
 #pragma unroll
@@ -733,8 +861,12 @@ riccati_backward_subwarp(LqrIn in, int *status_out, double *store, double *scrat
       for (int i = kGroup * s; i < N; ++i) {
         const double w = SM(S::rSdi + i) * ((i == xj[s] ? 1.0 : 0.0) - y[i]) * sdio[s];
         if (xok[s] && i >= xj[s]) {
-          SM(S::rW + xj[s] * S::P + i) = w;
-          SM(S::rW + i * S::P + xj[s]) = w;
+          if constexpr (PACKW) {
+            SM(S::rW + qcol[s] + i) = w;
+          } else {
+            SM(S::rW + xj[s] * S::P + i) = w;
+            SM(S::rW + i * S::P + xj[s]) = w;
+          }
           if (valid) stcs(dst, y[i]);  // the store keeps P = F^-1
         }
         dst += ld;
@@ -745,6 +877,221 @@ riccati_backward_subwarp(LqrIn in, int *status_out, double *store, double *scrat
   }
 
   if (status_out != nullptr && valid && r == 0) status_out[b] = status;
+
+  if constexpr (FUSED) {
+    // ---- forward phase ------------------------------------------------------------
+    // Shared-memory rows (of 8 problems), over the staging area of the sweep:
+    // block 1 = what u and A x + B u need, block 2 = what the node solve needs.
+    constexpr int fA = 0, fB = fA + N * N, fK = fB + N * M, fk = fK + N * M;
+    constexpr int fP = fk + M, fv = fP + tri(N), fd = fv + N, fc = fd + N;
+    constexpr int fx = fc + N, fu = fx + N, fs = fu + M;
+    static_assert(fs + N <= S::kRows, "rollout operands fit the sweep's shared memory");
+    __threadfence_block();
+    __syncwarp();  // the spill of every lane is visible to the copies below
+    const double *gA = in.A + lane_goff, *gB = in.B + lane_goff;
+    const double *gc = in.c + lane_goff, *gd = in.delta + lane_goff;
+    const double *gK = store + Z::oK(T) * ld + lane_goff;
+    const double *gP = store + Z::oW(T) * ld + lane_goff;
+    const double *gv = scratch + Z::ov(T) * ld + lane_goff;
+    const double *gk = scratch + Z::ok(T) * ld + lane_goff;
+    // The copies have half a stage of lead; what they fetch is pulled into L2 kPF stages
+    // earlier (prefetch.global.L2: no registers, no shared memory), so that they pay an
+    // L2 round trip, not an HBM one.
+    constexpr int kPF = SIPOC_FUSED_PF;
+    auto l2_run = [&](const double *src, int count) {
+#pragma unroll
+      for (int i0 = 0; i0 < count; i0 += 8) {
+        if ((lane & 1) == 0 && (i0 + 8 <= count || i0 + rr < count)) prefetch_l2(src);
+        src += ld8;
+      }
+    };
+    auto prefetch_edge = [&]() {  // edge kPF stages past the one the pointers stand on
+      l2_run(gA + static_cast<int64_t>(kPF) * N * N * ld, N * N);
+      l2_run(gB + static_cast<int64_t>(kPF) * N * M * ld, N * M);
+      l2_run(gK + static_cast<int64_t>(kPF) * N * M * ld, N * M);
+      l2_run(gk + static_cast<int64_t>(kPF) * M * ld, M);
+    };
+    auto prefetch_node = [&]() {
+      l2_run(gP + static_cast<int64_t>(kPF) * tri(N) * ld, tri(N));
+      l2_run(gv + static_cast<int64_t>(kPF) * N * ld, N);
+      l2_run(gd + static_cast<int64_t>(kPF) * N * ld, N);
+      l2_run(gc + static_cast<int64_t>(kPF) * N * ld, N);
+    };
+    auto issue_edge = [&]() {  // A_k, B_k, K_k, k_k; then step to edge k + 1
+      stage_run(sdst + fA * kTile, gA, ld8, N * N, rr);
+      stage_run(sdst + fB * kTile, gB, ld8, N * M, rr);
+      stage_run(sdst + fK * kTile, gK, ld8, N * M, rr);
+      stage_run(sdst + fk * kTile, gk, ld8, M, rr);
+      gA += static_cast<int64_t>(N) * N * ld;
+      gB += static_cast<int64_t>(N) * M * ld;
+      gK += static_cast<int64_t>(N) * M * ld;
+      gk += static_cast<int64_t>(M) * ld;
+    };
+    auto issue_node = [&]() {  // P, v, delta, c of the node the pointers stand on
+      stage_run(sdst + fP * kTile, gP, ld8, tri(N), rr);
+      stage_run(sdst + fv * kTile, gv, ld8, N, rr);
+      stage_run(sdst + fd * kTile, gd, ld8, N, rr);
+      stage_run(sdst + fc * kTile, gc, ld8, N, rr);
+      gP += static_cast<int64_t>(tri(N)) * ld;
+      gv += static_cast<int64_t>(N) * ld;
+      gd += static_cast<int64_t>(N) * ld;
+      gc += static_cast<int64_t>(N) * ld;
+    };
+    // Node solve on the own rows i = xj[s], given f (own rows) in fo[]:
+    //   s = D^-1/2 f, t = P s, (I + D V)^-1 f = D^1/2 t, W f = D^-1/2 (s - t)
+    // (the F-solve form of lqr.cpp:531-549; P = F^-1 from the store).  Returns t and
+    // leaves s in fo; ends with the exchange rows free again.
+    double fo[SX], to[SX], sdi_o[SX];
+    auto node_solve = [&]() {
+#pragma unroll
+      for (int s = 0; s < SX; ++s) {
+        sdi_o[s] = rsqrt(SM(fd + xj[s]));
+        fo[s] *= sdi_o[s];
+        if (xok[s]) SM(fs + xj[s]) = fo[s];
+      }
+      __syncwarp();
+      double sv[N];
+#pragma unroll
+      for (int j = 0; j < N; ++j) sv[j] = SM(fs + j);
+#pragma unroll
+      for (int s = 0; s < SX; ++s) {
+        double acc = 0.0, acc2 = 0.0;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          // packed lower index of (xj, j): below the diagonal j * N - j (j - 1) / 2 + xj - j
+          const int below = j * N - j * (j - 1) / 2 - j + xj[s];
+          const int idx = (j < xj[s]) ? below : qcol[s] + j;
+          if (j & 1) acc2 += SM(fP + idx) * sv[j]; else acc += SM(fP + idx) * sv[j];
+        }
+        to[s] = acc + acc2;
+      }
+    };
+    double *xo = out.x + b, *uo = out.u + b, *yo = out.y + b;
+
+    if (kPF > 0) {
+      // edges 1 .. kPF and nodes 2 .. kPF + 1 (the loop below keeps the distance)
+      for (int j = 1; j <= kPF; ++j) {
+        if (j < T) {
+          l2_run(gA + static_cast<int64_t>(j) * N * N * ld, N * N);
+          l2_run(gB + static_cast<int64_t>(j) * N * M * ld, N * M);
+          l2_run(gK + static_cast<int64_t>(j) * N * M * ld, N * M);
+          l2_run(gk + static_cast<int64_t>(j) * M * ld, M);
+        }
+        if (j + 1 <= T) {
+          l2_run(gP + static_cast<int64_t>(j + 1) * tri(N) * ld, tri(N));
+          l2_run(gv + static_cast<int64_t>(j + 1) * N * ld, N);
+          l2_run(gd + static_cast<int64_t>(j + 1) * N * ld, N);
+          l2_run(gc + static_cast<int64_t>(j + 1) * N * ld, N);
+        }
+      }
+    }
+    issue_node();  // root
+    cp_async_commit();
+    if (T > 0) issue_edge();
+    cp_async_commit();
+    cp_async_wait_group<1>();
+    __syncwarp();
+    // root: f = delta v - c, x = -(I + D V)^-1 f, y = v - W f     (lqr.cpp:798-819)
+#pragma unroll
+    for (int s = 0; s < SX; ++s)
+      fo[s] = SM(fd + xj[s]) * SM(fv + xj[s]) - SM(fc + xj[s]);
+    node_solve();
+#pragma unroll
+    for (int s = 0; s < SX; ++s) {
+      const double xi = -SM(fd + xj[s]) * sdi_o[s] * to[s];
+      const double yi = SM(fv + xj[s]) - sdi_o[s] * (fo[s] - to[s]);
+      if (xok[s]) {
+        SM(fx + xj[s]) = xi;
+        if (valid) {
+          stcs(xo + static_cast<int64_t>(xj[s]) * ld, xi);
+          stcs(yo + static_cast<int64_t>(xj[s]) * ld, yi);
+        }
+      }
+    }
+    __syncwarp();  // x_0 visible; every lane is done with the node block
+    if (T > 0) issue_node();
+    cp_async_commit();
+    xo += static_cast<int64_t>(N) * ld;
+    yo += static_cast<int64_t>(N) * ld;
+
+#ifdef SIPOC_EXP_SKIP_FWD
+    if (T > 0) { cp_async_wait_all(); return; }
+#endif
+    for (int k = 0; k < T; ++k) {
+#ifndef SIPOC_EXP_NOWAIT
+      cp_async_wait_group<1>();  // edge block of stage k
+#endif
+      __syncwarp();
+      double xr[N];
+#pragma unroll
+      for (int j = 0; j < N; ++j) xr[j] = SM(fx + j);
+      // u = k + K x, own controls                                   (lqr.cpp:856-857)
+#pragma unroll
+      for (int s = 0; s < SU; ++s) {
+        double acc = SM(fk + uj[s]), acc2 = 0.0;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          if (j & 1) acc2 += SM(fK + j * M + uj[s]) * xr[j]; else acc += SM(fK + j * M + uj[s]) * xr[j];
+        }
+        acc += acc2;
+        if (uok[s]) {
+          SM(fu + uj[s]) = acc;
+          if (valid) stcs(uo + static_cast<int64_t>(uj[s]) * ld, acc);
+        }
+      }
+      uo += static_cast<int64_t>(M) * ld;
+      // A x, own rows (needs x only: runs while the lanes' u meet below)
+#pragma unroll
+      for (int s = 0; s < SX; ++s) {
+        double acc = 0.0, acc2 = 0.0;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          if (j & 1) acc2 += SM(fA + j * N + xj[s]) * xr[j]; else acc += SM(fA + j * N + xj[s]) * xr[j];
+        }
+        fo[s] = acc + acc2;
+      }
+      __syncwarp();  // u visible
+#pragma unroll
+      for (int s = 0; s < SX; ++s) {
+        double acc = 0.0;
+#pragma unroll
+        for (int a = 0; a < M; ++a) acc += SM(fB + a * N + xj[s]) * SM(fu + a);
+        fo[s] += acc;
+      }
+      __syncwarp();  // every lane is done with the edge block
+      if (kPF > 0 && k + 1 + kPF < T) prefetch_edge();
+      if (k + 1 < T) issue_edge();
+      cp_async_commit();
+#ifndef SIPOC_EXP_NOWAIT
+      cp_async_wait_group<1>();  // node block of stage k (node k + 1)
+#endif
+      __syncwarp();
+      // f = c' - delta' o v' + A x + B u ; x' = (I + D V)^-1 f ; y' = v' + W f   (:859-868)
+#pragma unroll
+      for (int s = 0; s < SX; ++s)
+        fo[s] += SM(fc + xj[s]) - SM(fd + xj[s]) * SM(fv + xj[s]);
+      node_solve();
+#pragma unroll
+      for (int s = 0; s < SX; ++s) {
+        const double xi = SM(fd + xj[s]) * sdi_o[s] * to[s];
+        const double yi = SM(fv + xj[s]) + sdi_o[s] * (fo[s] - to[s]);
+        if (xok[s]) {
+          SM(fx + xj[s]) = xi;
+          if (valid) {
+            stcs(xo + static_cast<int64_t>(xj[s]) * ld, xi);
+            stcs(yo + static_cast<int64_t>(xj[s]) * ld, yi);
+          }
+        }
+      }
+      xo += static_cast<int64_t>(N) * ld;
+      yo += static_cast<int64_t>(N) * ld;
+      __syncwarp();  // x' visible; node block free
+      if (kPF > 0 && k + 2 + kPF <= T) prefetch_node();  // pointers stand on node k + 2
+      if (k + 1 < T) issue_node();
+      cp_async_commit();
+    }
+    cp_async_wait_all();
+  }
 #undef SM
 }
 
@@ -1558,7 +1905,12 @@ rollout_forward(LqrIn in, LqrOut out, const double *store, const double *scratch
         f[i] += (PREFETCH ? cB[a * N + i] : G(in.B, (k * M + a) * N + i)) * u[a];
     // x' = (I + D V)^-1 f, f <- W f
     apply_node<N>(
-        f, dd, [&](int t) { return PREFETCH ? cW[t] : G(Wst, (k + 1) * tri(N) + t); }, x);
+        f, dd,
+        [&](int t) {
+          if constexpr (PREFETCH) return cW[t];
+          else return G(Wst, (k + 1) * tri(N) + t);
+        },
+        x);
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       stcs(xo + static_cast<size_t>((k + 1) * N + i) * L_, x[i]);
@@ -1825,21 +2177,27 @@ rollout_forward_kkt(KktView kv, const double *store, const double *scratch, int6
 // ===========================================================================
 // Below this many problems a thread-per-problem kernel launches one-warp blocks.
 constexpr int64_t kSmallBatch = 148 * 128 * 2;
+// Up to this many problems factor + solve runs as the fused sweep + rollout kernel.
+#ifndef SIPOC_FUSED_MAX_BATCH
+#define SIPOC_FUSED_MAX_BATCH 40960
+#endif
+constexpr int64_t kFusedMaxBatch = SIPOC_FUSED_MAX_BATCH;
 
 template <int N, int M, bool SUBWARP>
 struct Plan {
   static int64_t store_elems(int T) { return FastSizes<N, M>::store(T); }
   static int64_t scratch_elems(int T) { return FastSizes<N, M>::scratch(T); }
 
-  template <bool SOLVE, int W>
+  template <bool SOLVE, int W, bool FUSED = false, bool PACKW = FUSED>
   static void launch_subwarp(const FastArgs &a, cudaStream_t s) {
-    auto kern = riccati_backward_subwarp<N, M, SOLVE, W>;
-    constexpr int bytes = Smem<N, M>::kBytes * W;
+    auto kern = riccati_backward_subwarp<N, M, SOLVE, W, FUSED, PACKW>;
+    using Sm = Smem<N, M, PACKW>;
+    constexpr int bytes = Sm::kBytes * W;
     if (bytes > 48 * 1024)
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     const unsigned grid = static_cast<unsigned>((a.batch + kTile * W - 1) / (kTile * W));
-    ProfScope ps(a.prof, "riccati_backward_subwarp", s);
-    kern<<<grid, 32 * W, bytes, s>>>(a.in, a.status, a.store, a.scratch, a.batch, a.ld,
+    ProfScope ps(a.prof, FUSED ? "riccati_fused_subwarp" : "riccati_backward_subwarp", s);
+    kern<<<grid, 32 * W, bytes, s>>>(a.in, a.out, a.status, a.store, a.scratch, a.batch, a.ld,
                                      a.num_edges);
   }
 
@@ -1849,7 +2207,10 @@ struct Plan {
       // One warp (8 problems) per CTA: warps of different CTAs drift apart, so the
       // DFMA-heavy and the latency-bound phases of different tiles overlap on an SM
       // (measured: 1 warp / CTA 5.97 ms, 4 warps / CTA in lockstep 7.40 ms).
-      launch_subwarp<SOLVE, 1>(a, s);
+      // Up to ~3 waves of tiles: the packed map, seven warps per SM (8 192 problems are
+      // one wave); deeper grids: the padded map at six.
+      if (a.batch <= kFusedMaxBatch) launch_subwarp<SOLVE, 1, false, true>(a, s);
+      else launch_subwarp<SOLVE, 1, false, false>(a, s);
     } else {
       const unsigned grid = static_cast<unsigned>((a.batch + 63) / 64);
       ProfScope ps(a.prof, "riccati_backward_thread", s);
@@ -1902,9 +2263,21 @@ struct Plan {
     return 2;
   }
   static int factor_solve(const FastArgs &a, cudaStream_t s) {
-    backward<true>(a, s);
-    forward(a, s);
-    return 2;
+    if (SUBWARP && a.batch <= kFusedMaxBatch) {
+      // One kernel: each warp rolls its tile forward right after its backward sweep.  Pays
+      // up to about four waves of tiles (quadrotor: 3.10 against 3.56 ms at 32 768 problems,
+      // 1.50 against 1.64 ms at 16 384, 0.74 against 1.10 ms at 8 192 -- the per-GPU shard of
+      // the 65 536-problem batch on eight GPUs, one wave at seven warps per SM); at 65 536
+      // the sweep + the streaming thread-per-problem rollout is faster (5.8 against 6.1 ms:
+      // a tile's rollout costs its warp ~4 us per stage during which the slot does no sweep
+      // work, and the sweep runs faster on the padded map at six warps per SM).
+      if constexpr (SUBWARP) launch_subwarp<true, 1, true>(a, s);
+      return 1;
+    } else {
+      backward<true>(a, s);
+      forward(a, s);
+      return 2;
+    }
   }
   static int kkt_solve(const FastKktArgs &k, cudaStream_t s) {
     const unsigned grid = static_cast<unsigned>((k.batch + 127) / 128);

@@ -169,9 +169,8 @@ def test_status_stats_and_kernel_profile():
         eng._check(lib.sipoc_profile_get(eng._handle, i, ctypes.byref(nm), ctypes.byref(ms),
                                          ctypes.byref(cnt)))
         names[nm.value.decode()] = (ms.value, cnt.value)
-    # (70 problems: the small-batch, cp.async-staged rollout)
-    assert set(names) == {"riccati_backward_subwarp", "rollout_forward_staged",
-                          "status_stats_kernel"}
+    # (factor + solve in one call: the sweep and the rollout are one kernel)
+    assert set(names) == {"riccati_fused_subwarp", "status_stats_kernel"}
     assert all(ms > 0.0 and cnt == 1 for ms, cnt in names.values())
     lib.sipoc_profile_enable(eng._handle, 0)
     assert lib.sipoc_profile_collect(eng._handle) == 0
