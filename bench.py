@@ -207,30 +207,40 @@ def run_reference(args, wl, name):
     from oracle import pyoracle
 
     cores = host_threads()
-    sample = max(cores * 4, 64)
-    _, host = cpu_time_sample(wl, sample, cores)
-    secs, _ = cpu_time_sample(wl, sample, cores, host=host)
-    # size one step to about one second of wall time
-    per_problem = secs / sample
-    sample = int(max(cores, min(65536, 1.0 / max(per_problem, 1e-9))))
-    sample = (sample + cores - 1) // cores * cores
-    host = host_problems(wl["n"], wl["m"], wl["T"], sample, seed=1234)
-    for _ in range(args.warmup):
-        cpu_time_sample(wl, sample, cores, host=host)
+    # One step = the workload's whole batch (the GPU arm's config: same_config), as
+    # `passes` sweeps over a pool of distinct problems: 65 536 quadrotor problems would be
+    # 11.6 GB of host arrays, the pool (<= 2 048 problems, 360 MB, far beyond the CPU caches) keeps
+    # the arm's set-up to seconds.  Steps are bounded to what a few minutes allow.
+    batch = wl["batch"]
+    pool = min(batch, 2048)
+    while batch % pool:
+        pool -= 1
+    passes = batch // pool
+    host = host_problems(wl["n"], wl["m"], wl["T"], pool, seed=1234)
+    secs, _ = cpu_time_sample(wl, pool, cores, host=host)  # warm-up pass, sizes the run
+    step_s = secs * passes
+    budget_s = 150.0
+    steps = max(1, min(args.steps, int(budget_s / max(step_s, 1e-9))))
+    warm = max(0, min(args.warmup, int(30.0 / max(step_s, 1e-9))))
+    for _ in range(warm):
+        cpu_time_sample(wl, pool, cores, repeats=passes, host=host)
     total = 0.0
-    for _ in range(args.steps):
-        s, _ = cpu_time_sample(wl, sample, cores, host=host)
+    for _ in range(steps):
+        s, _ = cpu_time_sample(wl, pool, cores, repeats=passes, host=host)
         total += s
-    value = sample * args.steps / total
-    desc = (f"{sample} problems per step, one problem per OpenMP thread over {cores} threads; "
+    value = batch * steps / total
+    sample = batch
+    desc = (f"{batch} problems per step ({passes} passes over {pool} distinct problems), {steps} timed "
+            f"steps, one problem per OpenMP thread over {cores} threads; "
             "Eigen-free port of lqr.cpp (the reference itself needs Eigen, absent here)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": 1e3 * total / steps, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": name, **wl, "batch": sample,
-                   "note": "host CPU arm: bounded sample of the workload per step"},
+        "config": {"workload": name, **wl, "batch": sample, "global_batch": sample,
+                   "note": "host CPU arm: the workload's whole batch per step; steps bounded to "
+                           "a few minutes of CPU time"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -285,7 +295,7 @@ def run_ours(args, wl, name):
             os.close(saved_stdout)
     assert world == args.gpus, (world, args.gpus)
 
-    from sip_optimal_control_b200.sharding import shard_range
+    from sip_optimal_control_b200.sharding import allgather_stats, fold_stats, shard_range
 
     n, m, T = wl["n"], wl["m"], wl["T"]
     # weak: every GPU gets the workload's batch; strong: the workload's batch is
@@ -302,6 +312,7 @@ def run_ours(args, wl, name):
     out = lqr.alloc_output()
     status = eng.empty_int()
     stats = torch.zeros(4, dtype=torch.float64, device=dev)
+    gathered = torch.zeros((world, 4), dtype=torch.float64, device=dev)
     stream = torch.cuda.current_stream(dev)
     sp = eng.stream_ptr(stream)
 
@@ -324,7 +335,9 @@ def run_ours(args, wl, name):
             lqr.factor_solve(inp, out, status=status, stream=stream)
         eng._check(lib.sipoc_status_stats(eng._handle, status.data_ptr(), stats.data_ptr(), sp))
         if world > 1:
-            dist.all_reduce(stats)
+            # ONE collective per step: every rank's 4 numbers are gathered; sum / max / counts
+            # are folded where they are read (sharding.fold_stats)
+            allgather_stats(stats, gathered)
 
     def barrier():
         if world > 1:
@@ -347,7 +360,8 @@ def run_ours(args, wl, name):
     t1 = time.time()
     ms_total = ev0.elapsed_time(ev1)
     gpu_launches = eng.launch_count - launches0
-    failed_total, count_total = float(stats[2].item()), float(stats[3].item())
+    folded = fold_stats(gathered) if world > 1 else stats
+    failed_total, count_total = float(folded[2].item()), float(folded[3].item())
 
     # per-kernel device time over the same timed region
     kernels = {}
@@ -374,12 +388,12 @@ def run_ours(args, wl, name):
     max_residual = float(rstats[1].item())
 
     # ---- e2e: host buffers through the C-ABI, copies inside the timed region ----
-    # The call is PCIe-bound (189 KB cross the bus per problem), so it is measured on
-    # calls of at most --e2e-batch problems per GPU: same throughput per problem, and the
-    # pinned host buffers stay small enough for 8 ranks on one host.
+    # One call solves the GPU's whole shard (65 536 problems at N = 1: 11.6 GB of pinned
+    # host inputs); --e2e-batch caps the call size.  The call is PCIe-bound (189 KB cross
+    # the bus per problem).
     e2e = None
     if not args.no_e2e:
-        hb = min(batch, args.e2e_batch)
+        hb = min(batch, args.e2e_batch) if args.e2e_batch > 0 else batch
         lqr_h = lqr if hb == batch else LQR(Dimensions.uniform(T, n, m), Topology.chain(T), hb,
                                             device=local_rank, force_generic=args.force_generic)
         eng_h = lqr_h.engine
@@ -651,7 +665,9 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS) + ["newton_kkt", "newton_kkt_uniform"])
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
     ap.add_argument("--horizon", type=int, default=0, help="override the horizon T")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+                    help="strong (default, BASELINE's config): the workload's batch is sharded over "
+                         "the GPUs; weak: every GPU gets the workload's batch")
     ap.add_argument("--seed", type=int, default=2026)
     ap.add_argument("--force-generic", action="store_true")
     ap.add_argument("--input-layout", default="interleaved", choices=["interleaved", "problem_major"],
@@ -664,7 +680,8 @@ def main():
                          "(CallbackProvider.capture_step) instead of launching its kernels eagerly")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--e2e-batch", type=int, default=16384)
+    ap.add_argument("--e2e-batch", type=int, default=0,
+                    help="problems per host-buffer call per GPU (0 = the GPU's whole shard)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
