@@ -295,7 +295,7 @@ def run_ours(args, wl, name):
             os.close(saved_stdout)
     assert world == args.gpus, (world, args.gpus)
 
-    from sip_optimal_control_b200.sharding import allgather_stats, fold_stats, shard_range
+    from sip_optimal_control_b200.sharding import Communicator, shard_range
 
     n, m, T = wl["n"], wl["m"], wl["T"]
     # weak: every GPU gets the workload's batch; strong: the workload's batch is
@@ -312,9 +312,15 @@ def run_ours(args, wl, name):
     out = lqr.alloc_output()
     status = eng.empty_int()
     stats = torch.zeros(4, dtype=torch.float64, device=dev)
-    gathered = torch.zeros((world, 4), dtype=torch.float64, device=dev)
     stream = torch.cuda.current_stream(dev)
     sp = eng.stream_ptr(stream)
+    comm = None
+    if world > 1:
+        # The per-iteration exchange belongs to the engine: with its communicator attached
+        # (include/sipoc.h, sipoc_attach_comm) sipoc_status_stats ends with the all-reduce of
+        # the 4 statistics -- one NCCL all-gather + a one-warp fold kernel on the step's stream.
+        comm = Communicator(device=local_rank)
+        comm.attach(eng)
 
     inp_pm = None
     if args.input_layout == "problem_major":
@@ -333,11 +339,8 @@ def run_ours(args, wl, name):
             lqr.factor_solve_pm(inp_pm, out, status=status, stream=stream)
         else:
             lqr.factor_solve(inp, out, status=status, stream=stream)
+        # (all-reduced over the ranks inside the call when world > 1)
         eng._check(lib.sipoc_status_stats(eng._handle, status.data_ptr(), stats.data_ptr(), sp))
-        if world > 1:
-            # ONE collective per step: every rank's 4 numbers are gathered; sum / max / counts
-            # are folded where they are read (sharding.fold_stats)
-            allgather_stats(stats, gathered)
 
     def barrier():
         if world > 1:
@@ -360,8 +363,7 @@ def run_ours(args, wl, name):
     t1 = time.time()
     ms_total = ev0.elapsed_time(ev1)
     gpu_launches = eng.launch_count - launches0
-    folded = fold_stats(gathered) if world > 1 else stats
-    failed_total, count_total = float(folded[2].item()), float(folded[3].item())
+    failed_total, count_total = float(stats[2].item()), float(stats[3].item())
 
     # per-kernel device time over the same timed region
     kernels = {}
@@ -382,9 +384,7 @@ def run_ours(args, wl, name):
     value = total_batch / (ms_per_step * 1e-3)
 
     # correctness outside the timed region: KKT residual of every problem
-    norms, rstats = lqr.residual(inp, out, status)
-    if world > 1:
-        dist.all_reduce(rstats[1:2], op=dist.ReduceOp.MAX)
+    norms, rstats = lqr.residual(inp, out, status)  # (all-reduced inside the call too)
     max_residual = float(rstats[1].item())
 
     # ---- e2e: host buffers through the C-ABI, copies inside the timed region ----
@@ -487,6 +487,8 @@ def run_ours(args, wl, name):
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(wl)
         print(json.dumps(line))
+    if comm is not None:
+        comm.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

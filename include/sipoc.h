@@ -27,10 +27,10 @@
  *   sipoc_kkt_apply_block             CallbackProvider::add_Hx_to_y / add_Cx_to_y /
  *                                     add_CTx_to_y / add_Gx_to_y / add_GTx_to_y
  *                                     (helpers.hpp:17-21, helpers.cpp:979-1368)
- *   sipoc_kkt_factor                  CallbackProvider::factor, theta_dim == 0
- *                                     (helpers.hpp:11-12, helpers.cpp:242-370)
- *   sipoc_kkt_solve                   CallbackProvider::solve, theta_dim == 0
- *                                     (helpers.hpp:13, helpers.cpp:749-900)
+ *   sipoc_kkt_factor                  CallbackProvider::factor
+ *                                     (helpers.hpp:11-12, helpers.cpp:190-407)
+ *   sipoc_kkt_solve                   CallbackProvider::solve
+ *                                     (helpers.hpp:13, helpers.cpp:749-951)
  *   sipoc_kkt_apply                   CallbackProvider::add_Kx_to_y
  *                                     (helpers.hpp:14-16, helpers.cpp:953-977)
  *   sipoc_kkt_residual                the ||K sol - rhs|| harness
@@ -77,7 +77,7 @@
 extern "C" {
 #endif
 
-#define SIPOC_VERSION 100
+#define SIPOC_VERSION 200
 
 typedef struct sipoc_engine sipoc_engine;
 
@@ -103,7 +103,7 @@ typedef enum sipoc_factor_status {
 
 /* Topology (lqr.hpp:5-22) + Dimensions (lqr.hpp:24-33), shared by the batch.
  * The four constraint-dimension arrays may be NULL (= all zero, lqr.cpp:98-112).
- * theta_dim > 0 (Schur variables) is not supported by this engine. */
+ * theta_dim (global / Schur variables, at most 32) closes the x vector. */
 typedef struct sipoc_structure {
   int num_edges;
   int root;
@@ -115,7 +115,7 @@ typedef struct sipoc_structure {
   const int *node_g_dims;   /* [num_edges + 1] or NULL */
   const int *edge_c_dims;   /* [num_edges]     or NULL */
   const int *edge_g_dims;   /* [num_edges]     or NULL */
-  int theta_dim;            /* must be 0 */
+  int theta_dim;            /* 0 .. 32 */
   int64_t batch;            /* number of problems on this device */
   int device;               /* CUDA ordinal, -1 = current device */
   int flags;                /* SIPOC_FLAG_* */
@@ -130,6 +130,9 @@ typedef struct sipoc_structure {
  * ill-conditioned regularization (r2 up to 1e9). */
 #define SIPOC_FLAG_PAD_VARIABLE_DIMS 2
 
+/* validate_input (types.cpp:68-134) on its own: SIPOC_OK, SIPOC_INVALID_DIMENSIONS or
+ * SIPOC_INVALID_TOPOLOGY, dimension checks first.  Needs no device (batch is ignored). */
+sipoc_error sipoc_validate(const sipoc_structure *structure);
 sipoc_error sipoc_create(const sipoc_structure *structure, sipoc_engine **out);
 void sipoc_destroy(sipoc_engine *engine);
 int sipoc_version(void);
@@ -248,9 +251,13 @@ sipoc_error sipoc_lqr_factor_host(sipoc_engine *engine, const sipoc_lqr_input *h
 sipoc_error sipoc_lqr_solve_host(sipoc_engine *engine, const sipoc_lqr_input *host_in,
                                  const sipoc_lqr_output *host_out);
 
-/* ---- Newton-KKT (theta_dim == 0) ---------------------------------------- */
-/* Flat vectors use the reference wire format (types.cpp:24-64):
- *   x = [x_0,u_0,...,x_{E-1},u_{E-1},x_E]
+/* ---- Newton-KKT ---------------------------------------------------------- */
+/* With theta_dim > 0 the factor adds the Schur complement on the global variables
+ * (helpers.cpp:372-407: J_theta, K_s^-1 J_theta by theta_dim stagewise solves against the
+ * kept factorization, Cholesky of S) and solve / apply carry the theta rows
+ * (helpers.cpp:902-951, theta branches of :1019-1368).
+ * Flat vectors use the reference wire format (types.cpp:24-64):
+ *   x = [x_0,u_0,...,x_{E-1},u_{E-1},x_E,theta]
  *   y = [dyn_0,node_c_0,...,dyn_E,node_c_E, edge_c_0..edge_c_{E-1}]
  *   z = [node_g_0..node_g_E, edge_g_0..edge_g_{E-1}],  KKT vectors = [x|y|z]. */
 typedef struct sipoc_kkt_sizes {
@@ -259,6 +266,10 @@ typedef struct sipoc_kkt_sizes {
   int64_t node_hxx, node_jc, node_jg;
   int64_t edge_hxx, edge_hxu, edge_huu, edge_A, edge_B;
   int64_t edge_jcx, edge_jcu, edge_jgx, edge_jgu;
+  /* theta (all zero when theta_dim == 0): x_dim = stagewise_x_dim + theta_dim */
+  int64_t theta_dim, stagewise_x_dim;
+  int64_t node_hxt, node_jct, node_jgt, node_htt;
+  int64_t edge_hxt, edge_hut, edge_dynt, edge_jct, edge_jgt, edge_htt;
 } sipoc_kkt_sizes;
 sipoc_error sipoc_kkt_get_sizes(const sipoc_engine *engine, sipoc_kkt_sizes *out);
 /* Offsets of every node / edge block in x, y, z (arrays sized E+1 or E). */
@@ -269,10 +280,19 @@ sipoc_error sipoc_kkt_offsets(const sipoc_engine *engine, int *x_state, int *x_c
 /* The ModelCallbackOutput blocks the reduction reads (types.hpp:48-89):
  * node d2L_dx2, dc_dx, dg_dx; edge d2L_dx2, d2L_dxdu, d2L_du2, ddyn_dx,
  * ddyn_du, dc_dx, dc_du, dg_dx, dg_du — flat, column-major per block. */
+/* theta blocks of ModelCallbackOutput, p = theta_dim columns each, column-major:
+ * node d2L_dxdtheta [n x p], dc_dtheta [c x p], dg_dtheta [g x p], d2L_dtheta2 [p x p];
+ * edge d2L_dxdtheta [n_parent x p], d2L_dudtheta [m x p], ddyn_dtheta [n_child x p],
+ * dc_dtheta [c x p], dg_dtheta [g x p], d2L_dtheta2 [p x p]   (helpers.cpp:190-240). */
+typedef struct sipoc_kkt_theta_model {
+  const double *node_hxt, *node_jct, *node_jgt, *node_htt;
+  const double *edge_hxt, *edge_hut, *edge_dynt, *edge_jct, *edge_jgt, *edge_htt;
+} sipoc_kkt_theta_model;
 typedef struct sipoc_kkt_model {
   const double *node_hxx, *node_jc, *node_jg;
   const double *edge_hxx, *edge_hxu, *edge_huu, *edge_A, *edge_B;
   const double *edge_jcx, *edge_jcu, *edge_jgx, *edge_jgu;
+  const sipoc_kkt_theta_model *theta; /* NULL when theta_dim == 0 */
 } sipoc_kkt_model;
 
 /* ok: device int[batch_stride]; 1 where CallbackProvider::factor returns true. */
@@ -313,6 +333,10 @@ sipoc_error sipoc_kkt_factor_host(sipoc_engine *engine, const sipoc_kkt_model *h
                                   const double *w, const double *r1, const double *r2,
                                   const double *r3, int *host_ok);
 sipoc_error sipoc_kkt_solve_host(sipoc_engine *engine, const double *b, double *sol);
+/* Uploads the model alone: what sipoc_kkt_apply_host / sipoc_kkt_apply_block_host read.  The
+ * reference's add_*x_to_y read the CURRENT model_callback_output (helpers.cpp:1161-1183), so
+ * a shim calls this whenever the model callback has run since the last upload. */
+sipoc_error sipoc_kkt_set_model_host(sipoc_engine *engine, const sipoc_kkt_model *host_model);
 sipoc_error sipoc_kkt_apply_host(sipoc_engine *engine, const double *w, const double *r1,
                                  const double *r2, const double *r3, const double *x,
                                  double *y);
@@ -321,6 +345,42 @@ sipoc_error sipoc_kkt_apply_host(sipoc_engine *engine, const double *w, const do
  * sipoc_kkt_factor_host (vector lengths as for sipoc_kkt_apply_block). */
 sipoc_error sipoc_kkt_apply_block_host(sipoc_engine *engine, int block, const double *x,
                                        double *y);
+
+/* ---- several devices ------------------------------------------------------
+ * The path shards trivially: problems are independent, so a batch is cut into contiguous
+ * slices, one engine handle per device, with no data-path collective.  The only exchange
+ * per Newton iteration is the all-reduce of the 4 statistics the residual / status entry
+ * points write ({sum of squared norms, max norm, #failed, #problems}: slots 0, 2, 3 are
+ * summed, slot 1 is max-reduced).  A communicator is one rank's endpoint of an NCCL
+ * clique (NCCL is loaded with dlopen on first use; SIPOC_UNSUPPORTED if absent):
+ *   one process per GPU : rank 0 calls sipoc_comm_unique_id and ships the 128 bytes to the
+ *                         other ranks by whatever channel the host has (MPI, torch.distributed,
+ *                         a file); every rank calls sipoc_comm_create.
+ *   one process, n GPUs : sipoc_comm_create_all; collectives issued for several
+ *                         communicators from one thread go between sipoc_comm_group_begin / _end.
+ * sipoc_attach_comm makes the engine finish every `stats` it writes (sipoc_lqr_residual,
+ * sipoc_kkt_residual, sipoc_status_stats) with that all-reduce, on the call's stream --
+ * one all-gather of 4 doubles per rank plus a one-warp fold kernel, capturable in a graph. */
+#define SIPOC_COMM_ID_BYTES 128
+typedef struct sipoc_comm sipoc_comm;
+sipoc_error sipoc_shard_range(int64_t total, int rank, int world, int64_t *begin, int64_t *end);
+sipoc_error sipoc_comm_unique_id(void *id_out /* SIPOC_COMM_ID_BYTES */);
+sipoc_error sipoc_comm_create(const void *id, int rank, int world, int device /* -1 = current */,
+                              sipoc_comm **out);
+sipoc_error sipoc_comm_create_all(const int *device_ids, int n_dev, sipoc_comm **out /* [n_dev] */);
+void sipoc_comm_destroy(sipoc_comm *comm);
+int sipoc_comm_rank(const sipoc_comm *comm);
+int sipoc_comm_size(const sipoc_comm *comm);
+sipoc_error sipoc_comm_group_begin(void);
+sipoc_error sipoc_comm_group_end(void);
+/* stats: device double[4] on the communicator's device, reduced in place. */
+sipoc_error sipoc_comm_allreduce_stats(sipoc_comm *comm, double *stats, void *stream);
+/* The two halves, for several communicators driven by one thread: all gathers inside one
+ * group, then the folds. */
+sipoc_error sipoc_comm_allgather_stats(sipoc_comm *comm, const double *stats, void *stream);
+sipoc_error sipoc_comm_fold_stats(sipoc_comm *comm, double *stats, void *stream);
+/* comm may be NULL (detach).  The communicator must outlive the engine's calls. */
+sipoc_error sipoc_attach_comm(sipoc_engine *engine, sipoc_comm *comm);
 
 /* ---- synthetic workloads (bench / test tooling) -------------------------- */
 /* Fills engine-layout device buffers with the distribution of the reference's

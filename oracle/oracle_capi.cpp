@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "kkt_oracle.hpp"
+#include "theta_oracle.hpp"
 #include "riccati_oracle.hpp"
 
 using namespace sipoc_oracle;
@@ -326,6 +327,71 @@ int oracle_kkt_apply_batch(int E, int root, const int *parents,
     kkt_apply(ct, K, mdl, w + i * sz[2], r1 + i * sz[0], r2 + i * sz[1],
               r3 + i * sz[2], xs, xs + K.x_dim, xs + K.x_dim + K.y_dim, ys,
               ys + K.x_dim, ys + K.x_dim + K.y_dim);
+  }
+  return SUCCESS;
+}
+
+// ---- theta (global / Schur variables): theta_oracle.hpp ------------------------------
+// model: the 12 stagewise block arrays in KktModel order; theta: the 10 arrays in ThetaModel
+// order; every array [batch][size].  r1 is [batch][x_dim + p]; b, sol, x, y are
+// [batch][kkt_dim + p] in the full layout [x_s, theta | y | z].
+// mode: 1 = factor, 2 = + solve, 8 = apply y += K x (b = x, sol = y) instead of factor / solve.
+void oracle_kkt_theta_sizes(int E, int root, const int *parents, const int *children,
+                            const int *state_dims, const int *control_dims, const int *node_c,
+                            const int *node_g, const int *edge_c, const int *edge_g, int p,
+                            int64_t *out) {
+  Tree t{E, root, parents, children};
+  ConstraintDims cd{node_c, node_g, edge_c, edge_g};
+  KktLayout K = make_kkt_layout(t, state_dims, control_dims, cd);
+  long long z[10];
+  theta_sizes(K, t, p, z);
+  for (int i = 0; i < 10; ++i) out[i] = z[i];
+}
+
+int oracle_kkt_theta_batch(int E, int root, const int *parents, const int *children,
+                           const int *state_dims, const int *control_dims, const int *node_c,
+                           const int *node_g, const int *edge_c, const int *edge_g, int p,
+                           int64_t batch, const double *const *model,
+                           const double *const *theta, const double *w, const double *r1,
+                           const double *r2, const double *r3, const double *b, double *sol,
+                           int *ok, int mode) {
+  Tree t{E, root, parents, children};
+  CompiledTree ct = compile_tree(t);
+  if (ct.status != SUCCESS) {
+    for (int64_t i = 0; i < batch && ok; ++i) ok[i] = 0;
+    return ct.status;
+  }
+  ConstraintDims cd{node_c, node_g, edge_c, edge_g};
+  KktLayout K = make_kkt_layout(t, state_dims, control_dims, cd);
+  int64_t sz[16];
+  oracle_kkt_sizes(E, root, parents, children, state_dims, control_dims, node_c, node_g, edge_c,
+                   edge_g, sz);
+  long long tz[10];
+  theta_sizes(K, t, p, tz);
+  const int64_t kd = K.kkt_dim + p, xd = K.x_dim + p;
+  const int nthreads = omp_get_max_threads();
+  std::vector<ThetaWorkspace> ws(nthreads);
+  for (auto &wk : ws) wk.kkt.reserve(K, ct);
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+  for (int64_t i = 0; i < batch; ++i) {
+    ThetaWorkspace &wk = ws[omp_get_thread_num()];
+    KktModel mdl{model[0] + i * sz[3],   model[1] + i * sz[4],   model[2] + i * sz[5],
+                 model[3] + i * sz[6],   model[4] + i * sz[7],   model[5] + i * sz[8],
+                 model[6] + i * sz[9],   model[7] + i * sz[10],  model[8] + i * sz[11],
+                 model[9] + i * sz[12],  model[10] + i * sz[13], model[11] + i * sz[14]};
+    ThetaModel tm{theta[0] + i * tz[0], theta[1] + i * tz[1], theta[2] + i * tz[2],
+                  theta[3] + i * tz[3], theta[4] + i * tz[4], theta[5] + i * tz[5],
+                  theta[6] + i * tz[6], theta[7] + i * tz[7], theta[8] + i * tz[8],
+                  theta[9] + i * tz[9]};
+    const double *wi = w + i * sz[2], *r1i = r1 + i * xd, *r2i = r2 + i * sz[1],
+                 *r3i = r3 + i * sz[2];
+    if (mode & 8) {
+      theta_apply(ct, t, K, p, mdl, tm, wi, r1i, r2i, r3i, b + i * kd, sol + i * kd);
+      continue;
+    }
+    const bool good = theta_factor(ct, t, K, p, mdl, tm, wi, r1i, r2i, r3i, wk);
+    ok[i] = good ? 1 : 0;
+    if ((mode & 2) && good) theta_solve(ct, K, p, mdl, b + i * kd, sol + i * kd, wk);
   }
   return SUCCESS;
 }

@@ -234,5 +234,57 @@ def kkt_apply(s: Structure, model: dict, w, r1, r2, r3, x, y=None) -> np.ndarray
     return y
 
 
+THETA_MODEL_NAMES = ("node_hxt", "node_jct", "node_jgt", "node_htt", "edge_hxt", "edge_hut",
+                     "edge_dynt", "edge_jct", "edge_jgt", "edge_htt")
+
+
+def theta_sizes(s: Structure, p: int) -> dict:
+    """Per-problem element counts of the ten theta block arrays (theta_oracle.hpp)."""
+    out = np.zeros(10, np.int64)
+    lib().oracle_kkt_theta_sizes(*s._topo_args(), *s._dim_args(), *s._cg_args(),
+                                 ctypes.c_int(p), out.ctypes.data_as(_c_i64_p))
+    return {k: int(out[i]) for i, k in enumerate(THETA_MODEL_NAMES)}
+
+
+def _theta_call(s, p, model, theta, w, r1, r2, r3, vec_in, vec_out, ok, mode):
+    mdl = [_f64(model[k]) for k in KKT_MODEL_NAMES]
+    th = [_f64(theta[k]) for k in THETA_MODEL_NAMES]
+    tz = theta_sizes(s, p)
+    batch = vec_in.shape[0]
+    for k, a in zip(THETA_MODEL_NAMES, th):
+        assert a.shape == (batch, tz[k]), (k, a.shape, (batch, tz[k]))
+    arr_m = (_c_dbl_p * 12)(*[_dp(a) for a in mdl])
+    arr_t = (_c_dbl_p * 10)(*[_dp(a) for a in th])
+    st = lib().oracle_kkt_theta_batch(
+        *s._topo_args(), *s._dim_args(), *s._cg_args(), ctypes.c_int(p), ctypes.c_int64(batch),
+        arr_m, arr_t, _dp(w), _dp(r1), _dp(r2), _dp(r3), _dp(vec_in), _dp(vec_out), _ip(ok),
+        ctypes.c_int(mode))
+    assert st == 0
+    return mdl, th  # keep the arrays alive until the call has returned
+
+
+def kkt_theta_factor_solve(s: Structure, p: int, model: dict, theta: dict, w, r1, r2, r3, b,
+                           solve=True):
+    """CallbackProvider::factor (+ solve) with theta_dim = p; vectors in the full layout
+    [x_s, theta | y | z], r1 of length x_dim + p."""
+    sz = kkt_sizes(s)
+    w, r1, r2, r3, b = (_f64(v) for v in (w, r1, r2, r3, b))
+    batch = b.shape[0]
+    assert r1.shape == (batch, sz["x_dim"] + p) and b.shape == (batch, sz["kkt_dim"] + p)
+    sol = np.zeros_like(b)
+    ok = np.zeros(batch, np.int32)
+    _theta_call(s, p, model, theta, w, r1, r2, r3, b, sol, ok, 1 | (2 if solve else 0))
+    return dict(sol=sol, ok=ok)
+
+
+def kkt_theta_apply(s: Structure, p: int, model: dict, theta: dict, w, r1, r2, r3, x, y=None):
+    """y += K x with the theta rows / columns (add_Kx_to_y, theta_dim = p)."""
+    w, r1, r2, r3, x = (_f64(v) for v in (w, r1, r2, r3, x))
+    y = np.zeros_like(x) if y is None else _f64(y).copy()
+    ok = np.zeros(x.shape[0], np.int32)
+    _theta_call(s, p, model, theta, w, r1, r2, r3, x, y, ok, 8)
+    return y
+
+
 def max_threads() -> int:
     return int(lib().oracle_max_threads())

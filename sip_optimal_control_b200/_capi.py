@@ -28,6 +28,7 @@ ERROR_NAMES = {
 }
 SIPOC_INVALID_TOPOLOGY = 4
 SIPOC_INVALID_DIMENSIONS = 5
+SIPOC_COMM_ID_BYTES = 128
 SIPOC_FLAG_FORCE_GENERIC = 1
 SIPOC_FLAG_PAD_VARIABLE_DIMS = 2
 # sipoc_kkt_block
@@ -64,13 +65,22 @@ class LqrOutput(ctypes.Structure):
     _fields_ = [(k, c_void_p) for k in LQR_OUTPUT_FIELDS]
 
 
+KKT_THETA_FIELDS = ("node_hxt", "node_jct", "node_jgt", "node_htt", "edge_hxt", "edge_hut",
+                    "edge_dynt", "edge_jct", "edge_jgt", "edge_htt")
+
+
 class KktSizes(ctypes.Structure):
     _fields_ = [(k, ctypes.c_int64) for k in ("x_dim", "y_dim", "z_dim", "kkt_dim") +
-                KKT_MODEL_FIELDS]
+                KKT_MODEL_FIELDS + ("theta_dim", "stagewise_x_dim") + KKT_THETA_FIELDS]
+
+
+class KktThetaModel(ctypes.Structure):
+    _fields_ = [(k, c_void_p) for k in KKT_THETA_FIELDS]
 
 
 class KktModel(ctypes.Structure):
-    _fields_ = [(k, c_void_p) for k in KKT_MODEL_FIELDS]
+    _fields_ = [(k, c_void_p) for k in KKT_MODEL_FIELDS] + \
+        [("theta", ctypes.POINTER(KktThetaModel))]
 
 
 def declared_symbols() -> list[str]:
@@ -92,6 +102,7 @@ def _load() -> ctypes.CDLL:
 
     E = c_void_p  # sipoc_engine*
     P = c_void_p  # any device / host data pointer
+    lib.sipoc_validate.argtypes = [ctypes.POINTER(Structure)]
     lib.sipoc_create.argtypes = [ctypes.POINTER(Structure), ctypes.POINTER(E)]
     lib.sipoc_destroy.argtypes = [E]
     lib.sipoc_destroy.restype = None
@@ -146,7 +157,25 @@ def _load() -> ctypes.CDLL:
     lib.sipoc_kkt_residual.argtypes = [E, KM, P, P, P, P, P, P, P, P, P, P]
     lib.sipoc_kkt_factor_host.argtypes = [E, KM, P, P, P, P, P]
     lib.sipoc_kkt_solve_host.argtypes = [E, P, P]
+    lib.sipoc_kkt_set_model_host.argtypes = [E, KM]
     lib.sipoc_kkt_apply_host.argtypes = [E, P, P, P, P, P, P]
+    C = c_void_p  # sipoc_comm*
+    lib.sipoc_shard_range.argtypes = [ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+                                      ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]
+    lib.sipoc_comm_unique_id.argtypes = [P]
+    lib.sipoc_comm_create.argtypes = [P, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                      ctypes.POINTER(C)]
+    lib.sipoc_comm_create_all.argtypes = [c_int_p, ctypes.c_int, ctypes.POINTER(C)]
+    lib.sipoc_comm_destroy.argtypes = [C]
+    lib.sipoc_comm_destroy.restype = None
+    lib.sipoc_comm_rank.argtypes = [C]
+    lib.sipoc_comm_size.argtypes = [C]
+    lib.sipoc_comm_group_begin.argtypes = []
+    lib.sipoc_comm_group_end.argtypes = []
+    lib.sipoc_comm_allreduce_stats.argtypes = [C, P, P]
+    lib.sipoc_comm_allgather_stats.argtypes = [C, P, P]
+    lib.sipoc_comm_fold_stats.argtypes = [C, P, P]
+    lib.sipoc_attach_comm.argtypes = [E, C]
     lib.sipoc_generate_lqr_benchmark.argtypes = [E, ctypes.c_uint64, ctypes.c_int64] + [P] * 9 + [P]
     for name in declared_symbols():
         fn = getattr(lib, name)

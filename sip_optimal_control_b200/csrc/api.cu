@@ -13,6 +13,7 @@
 #include "../../include/sipoc.h"
 #include "generic_kernels.cuh"
 #include "kkt_fast.cuh"
+#include "kkt_theta.cuh"
 #include "profile.hpp"
 #include "riccati_fast.cuh"
 #include "structure.hpp"
@@ -62,6 +63,8 @@ struct sipoc_engine {
   int *kkt_lqr_status = nullptr;
   bool kkt_factored = false;
   double *kkt_product = nullptr;  // K * sol scratch of sipoc_kkt_residual
+  // theta (Schur) layer (lazy): J and K_s^-1 J [kkt_dim x p], the factor of S [p x p], p scratch
+  double *theta_J = nullptr, *theta_KinvJ = nullptr, *theta_S = nullptr, *theta_t = nullptr;
 
   // Host-API resident buffers (lazy).
   double *h_in[9] = {nullptr};
@@ -72,9 +75,12 @@ struct sipoc_engine {
   bool host_lqr_ready = false;
   bool host_lqr_factored = false;
   double *hk_model[12] = {nullptr};
+  double *hk_theta[10] = {nullptr};
   double *hk_reg[4] = {nullptr};  // w, r1, r2, r3
   double *hk_vec[2] = {nullptr};  // b / x, sol / y
   bool host_kkt_ready = false;
+  bool host_model_resident = false;  // hk_model / hk_theta hold a caller's model
+  sipoc_comm *comm = nullptr;        // attached communicator: stats outputs are all-reduced
 };
 
 namespace {
@@ -138,7 +144,8 @@ void rebase(DevTables &t, const int *base) {
       &t.node_g,       &t.edge_c,      &t.edge_g,     &t.x_state,     &t.y_dyn,
       &t.y_node_c,     &t.z_node,      &t.x_control,  &t.y_edge_c,    &t.z_edge,
       &t.jc_node_off,  &t.jg_node_off, &t.jcx_off,    &t.jcu_off,     &t.jgx_off,
-      &t.jgu_off,      &t.node_c_off,  &t.node_g_off, &t.edge_c_off,  &t.edge_g_off};
+      &t.jgu_off,      &t.node_c_off,  &t.node_g_off, &t.edge_c_off,  &t.edge_g_off,
+      &t.pn_off,       &t.cn_off};
   for (const int **f : fields) {
     const size_t byte_off = reinterpret_cast<size_t>(*f);
     *f = reinterpret_cast<const int *>(reinterpret_cast<const char *>(base) + byte_off);
@@ -478,6 +485,23 @@ int64_t kkt_model_size(const HostStructure &h, int i) {
   }
 }
 
+// theta blocks (KktThetaModel order): node hxt, jct, jgt, htt; edge hxt, hut, dynt, jct, jgt, htt
+int64_t kkt_theta_size(const HostStructure &h, int i) {
+  const int64_t p = h.theta_dim;
+  switch (i) {
+    case 0: return h.n_off[h.N] * p;
+    case 1: return h.node_c_off[h.N] * p;
+    case 2: return h.node_g_off[h.N] * p;
+    case 3: return h.N * p * p;
+    case 4: return h.pn_off[h.E] * p;
+    case 5: return h.m_off[h.E] * p;
+    case 6: return h.cn_off[h.E] * p;
+    case 7: return h.edge_c_off[h.E] * p;
+    case 8: return h.edge_g_off[h.E] * p;
+    default: return h.E * p * p;
+  }
+}
+
 sipoc_error ensure_stage(sipoc_engine *e, int64_t elems_per_problem) {
   if (e->h_stage_elems >= elems_per_problem) return SIPOC_OK;
   // Never shrinks; the old buffer stays owned by the handle until destroy.
@@ -559,6 +583,10 @@ sipoc_error ensure_host_kkt(sipoc_engine *e) {
     if ((rc = alloc_doubles(e, &e->hk_reg[i], reg_sizes[i])) != SIPOC_OK) return rc;
   for (int i = 0; i < 2; ++i)
     if ((rc = alloc_doubles(e, &e->hk_vec[i], h.kkt_dim)) != SIPOC_OK) return rc;
+  for (int i = 0; i < 10 && h.theta_dim > 0; ++i) {
+    if ((rc = alloc_doubles(e, &e->hk_theta[i], kkt_theta_size(h, i))) != SIPOC_OK) return rc;
+    biggest = std::max(biggest, kkt_theta_size(h, i));
+  }
   if ((rc = ensure_stage(e, biggest)) != SIPOC_OK) return rc;
   if (e->h_status == nullptr) {
     rc = dev_alloc(e, reinterpret_cast<void **>(&e->h_status),
@@ -574,15 +602,47 @@ KktModel to_model(const sipoc_kkt_model *m) {
                   m->edge_A,   m->edge_B,   m->edge_jcx, m->edge_jcu, m->edge_jgx, m->edge_jgu};
 }
 
+// Zero-sized blocks may be NULL; the kernels never dereference them.
+KktThetaModel to_theta(const sipoc_kkt_model *m) {
+  const sipoc_kkt_theta_model *t = m->theta;
+  if (t == nullptr) return KktThetaModel{};
+  return KktThetaModel{t->node_hxt, t->node_jct, t->node_jgt, t->node_htt, t->edge_hxt,
+                       t->edge_hut, t->edge_dynt, t->edge_jct, t->edge_jgt, t->edge_htt};
+}
+
+bool theta_has_null(const sipoc_engine *e, const sipoc_kkt_model *m) {
+  if (e->hs.theta_dim == 0) return false;
+  if (m == nullptr || m->theta == nullptr) return true;
+  const sipoc_kkt_theta_model *t = m->theta;
+  const double *ptr[10] = {t->node_hxt, t->node_jct, t->node_jgt, t->node_htt, t->edge_hxt,
+                           t->edge_hut, t->edge_dynt, t->edge_jct, t->edge_jgt, t->edge_htt};
+  for (int i = 0; i < 10; ++i)
+    if (ptr[i] == nullptr && kkt_theta_size(e->hs, i) > 0) return true;
+  return false;
+}
+
+sipoc_error ensure_theta_ws(sipoc_engine *e) {
+  if (e->theta_J != nullptr || e->hs.theta_dim == 0) return SIPOC_OK;
+  const int64_t p = e->hs.theta_dim, kd = e->hs.kkt_dim;
+  sipoc_error rc;
+  if ((rc = alloc_doubles(e, &e->theta_KinvJ, kd * p)) != SIPOC_OK) return rc;
+  if ((rc = alloc_doubles(e, &e->theta_S, p * p)) != SIPOC_OK) return rc;
+  if ((rc = alloc_doubles(e, &e->theta_t, p)) != SIPOC_OK) return rc;
+  return alloc_doubles(e, &e->theta_J, kd * p);
+}
+
 bool model_has_null(const sipoc_kkt_model *m) {
   return m == nullptr || !m->node_hxx || !m->node_jc || !m->node_jg || !m->edge_hxx ||
          !m->edge_hxu || !m->edge_huu || !m->edge_A || !m->edge_B || !m->edge_jcx ||
          !m->edge_jcu || !m->edge_jgx || !m->edge_jgu;
 }
 
-sipoc_error kkt_factor_core(sipoc_engine *e, const KktModel &mdl, const double *w,
-                            const double *r1, const double *r2, const double *r3, int *ok,
-                            cudaStream_t s) {
+sipoc_error kkt_solve_stagewise(sipoc_engine *e, const KktModel &mdl, const double *b,
+                                double *sol, cudaStream_t s);
+
+sipoc_error kkt_factor_core(sipoc_engine *e, const KktModel &mdl, const KktThetaModel &tm,
+                            const double *w, const double *r1, const double *r2,
+                            const double *r3, int *ok, cudaStream_t s) {
   sipoc_error rc;
   if ((rc = ensure_kkt_ws(e)) != SIPOC_OK) return rc;
   if (e->kkt_reduce_fast != nullptr) {
@@ -602,11 +662,36 @@ sipoc_error kkt_factor_core(sipoc_engine *e, const KktModel &mdl, const double *
   launch_kkt_finish_factor(e->kkt_lqr_status, ok, e->batch, s);
   e->launches += 1;
   e->kkt_factored = true;
-  return check_launch(e, "kkt_finish_factor");
+  if ((rc = check_launch(e, "kkt_finish_factor")) != SIPOC_OK) return rc;
+  const int p = e->hs.theta_dim;
+  if (p == 0) return SIPOC_OK;
+  // helpers.cpp:372-407: J, K_s^-1 J column by column against the factorization just kept
+  // (the reference's multi-RHS stagewise solve, :422-747), S and its Cholesky factor.
+  if ((rc = ensure_theta_ws(e)) != SIPOC_OK) return rc;
+  {
+    ProfScope ps(&e->prof, "theta_jacobian_kernel", s);
+    launch_theta_jacobian(e->dt, tm, e->theta_J, e->batch, e->ld, s);
+  }
+  e->launches += 1;
+  if ((rc = check_launch(e, "theta_jacobian")) != SIPOC_OK) return rc;
+  const size_t col = static_cast<size_t>(e->hs.kkt_dim) * e->ld;
+  for (int j = 0; j < p; ++j)
+    if ((rc = kkt_solve_stagewise(e, mdl, e->theta_J + j * col, e->theta_KinvJ + j * col, s)) !=
+        SIPOC_OK)
+      return rc;
+  {
+    ProfScope ps(&e->prof, "theta_schur_kernel", s);
+    launch_theta_schur(e->dt, tm, r1, e->theta_J, e->theta_KinvJ, e->theta_S, ok, e->batch, e->ld,
+                       s);
+  }
+  e->launches += 2;
+  return check_launch(e, "theta_schur");
 }
 
-sipoc_error kkt_solve_core(sipoc_engine *e, const KktModel &mdl, const double *b,
-                           double *sol, cudaStream_t s) {
+// CallbackProvider::solve_stagewise_kkt (helpers.cpp:411-413, 749-894): K_s^-1 on the
+// stagewise rows of full-layout vectors; theta rows are neither read nor written.
+sipoc_error kkt_solve_stagewise(sipoc_engine *e, const KktModel &mdl, const double *b,
+                                double *sol, cudaStream_t s) {
   if (!e->kkt_factored)
     return fail(e, SIPOC_NOT_FACTORED, "kkt_solve called before kkt_factor");
   if (e->factored == sipoc_engine::Factored::FAST && !e->padded &&
@@ -638,12 +723,70 @@ sipoc_error kkt_solve_core(sipoc_engine *e, const KktModel &mdl, const double *b
   return check_launch(e, "kkt_recover");
 }
 
+// CallbackProvider::solve (helpers.cpp:896-951).
+sipoc_error kkt_solve_core(sipoc_engine *e, const KktModel &mdl, const double *b, double *sol,
+                           cudaStream_t s) {
+  sipoc_error rc = kkt_solve_stagewise(e, mdl, b, sol, s);
+  if (rc != SIPOC_OK || e->hs.theta_dim == 0) return rc;
+  {
+    ProfScope ps(&e->prof, "theta_solve_kernels", s);
+    launch_theta_solve(e->dt, b, e->theta_J, e->theta_KinvJ, e->theta_S, e->theta_t, sol,
+                       e->batch, e->ld, s);
+  }
+  e->launches += 3;
+  return check_launch(e, "theta_solve");
+}
+
+// y += K x on full [x | y | z] vectors: the stagewise operator, then the theta terms.
+sipoc_error kkt_apply_core(sipoc_engine *e, const KktModel &mdl, const KktThetaModel &tm,
+                           const double *w, const double *r1, const double *r2,
+                           const double *r3, const double *x, double *y, cudaStream_t s) {
+  {
+    ProfScope ps(&e->prof, e->kkt_apply_fast != nullptr ? "kkt_apply_chain" : "kkt_apply_kernel", s);
+    (e->kkt_apply_fast != nullptr ? e->kkt_apply_fast : &launch_kkt_apply)(
+        e->dt, mdl, w, r1, r2, r3, x, y, e->batch, e->ld, s);
+  }
+  e->launches += 1;
+  if (e->hs.theta_dim > 0) {
+    const size_t oy = static_cast<size_t>(e->hs.x_dim) * e->ld,
+                 oz = oy + static_cast<size_t>(e->hs.y_dim) * e->ld;
+    ProfScope ps(&e->prof, "theta_apply_kernel", s);
+    launch_theta_apply(e->dt, tm, kKktAll, r1, x, x + oy, x + oz, y, y + oy, y + oz, e->batch,
+                       e->ld, s);
+    e->launches += 1;
+  }
+  return check_launch(e, "kkt_apply");
+}
+
 }  // namespace
 
 // ===========================================================================
 extern "C" {
 
 int sipoc_version(void) { return SIPOC_VERSION; }
+
+sipoc_error sipoc_attach_comm(sipoc_engine *e, sipoc_comm *comm) {
+  if (e == nullptr) return SIPOC_INVALID_ARGUMENT;
+  e->comm = comm;
+  return SIPOC_OK;
+}
+
+// The per-iteration exchange: with a communicator attached, every `stats`
+// the engine writes is all-reduced over the ranks on the same stream.
+static sipoc_error reduce_stats(sipoc_engine *e, double *stats, void *stream) {
+  if (e->comm == nullptr || stats == nullptr) return SIPOC_OK;
+  const sipoc_error rc = sipoc_comm_allreduce_stats(e->comm, stats, stream);
+  if (rc != SIPOC_OK) return fail(e, rc, "all-reduce of the statistics failed");
+  e->launches += 1;  // the fold kernel (the all-gather is NCCL's)
+  return SIPOC_OK;
+}
+
+sipoc_error sipoc_validate(const sipoc_structure *s) {
+  if (s == nullptr) return SIPOC_INVALID_ARGUMENT;
+  HostStructure hs;
+  std::string err;
+  return hs.build(*s, err);
+}
 
 sipoc_error sipoc_create(const sipoc_structure *s, sipoc_engine **out) {
   if (out == nullptr) return SIPOC_INVALID_ARGUMENT;
@@ -953,7 +1096,8 @@ sipoc_error sipoc_lqr_residual(sipoc_engine *e, const sipoc_lqr_input *in,
                         static_cast<cudaStream_t>(stream));
   }
   e->launches += stats != nullptr ? 2 : 1;
-  return check_launch(e, "lqr_residual");
+  sipoc_error rc = check_launch(e, "lqr_residual");
+  return rc != SIPOC_OK ? rc : reduce_stats(e, stats, stream);
 }
 
 sipoc_error sipoc_status_stats(sipoc_engine *e, const int *status, double *stats,
@@ -967,7 +1111,8 @@ sipoc_error sipoc_status_stats(sipoc_engine *e, const int *status, double *stats
     launch_status_stats(status, stats, e->batch, static_cast<cudaStream_t>(stream));
   }
   e->launches += 2;
-  return check_launch(e, "status_stats");
+  sipoc_error rc = check_launch(e, "status_stats");
+  return rc != SIPOC_OK ? rc : reduce_stats(e, stats, stream);
 }
 
 sipoc_error sipoc_pack(sipoc_engine *e, const double *src, double *dst, int64_t size,
@@ -1113,6 +1258,11 @@ sipoc_error sipoc_kkt_get_sizes(const sipoc_engine *e, sipoc_kkt_sizes *o) {
   o->edge_jcu = kkt_model_size(h, 9);
   o->edge_jgx = kkt_model_size(h, 10);
   o->edge_jgu = kkt_model_size(h, 11);
+  o->theta_dim = h.theta_dim;
+  o->stagewise_x_dim = h.sx_dim;
+  int64_t *ts[10] = {&o->node_hxt, &o->node_jct, &o->node_jgt, &o->node_htt, &o->edge_hxt,
+                     &o->edge_hut, &o->edge_dynt, &o->edge_jct, &o->edge_jgt, &o->edge_htt};
+  for (int i = 0; i < 10; ++i) *ts[i] = kkt_theta_size(h, i);
   return SIPOC_OK;
 }
 
@@ -1137,10 +1287,10 @@ sipoc_error sipoc_kkt_factor(sipoc_engine *e, const sipoc_kkt_model *model, cons
                              const double *r1, const double *r2, const double *r3, int *ok,
                              void *stream) {
   if (e == nullptr) return SIPOC_INVALID_ARGUMENT;
-  if (model_has_null(model) || !w || !r1 || !r2 || !r3 || !ok)
+  if (model_has_null(model) || theta_has_null(e, model) || !w || !r1 || !r2 || !r3 || !ok)
     return fail(e, SIPOC_INVALID_ARGUMENT, "NULL KKT factor argument");
   DeviceGuard guard(e->device);
-  return kkt_factor_core(e, to_model(model), w, r1, r2, r3, ok,
+  return kkt_factor_core(e, to_model(model), to_theta(model), w, r1, r2, r3, ok,
                          static_cast<cudaStream_t>(stream));
 }
 
@@ -1157,20 +1307,17 @@ sipoc_error sipoc_kkt_apply(sipoc_engine *e, const sipoc_kkt_model *model, const
                             const double *r1, const double *r2, const double *r3,
                             const double *x, double *y, void *stream) {
   if (e == nullptr) return SIPOC_INVALID_ARGUMENT;
-  if (model_has_null(model) || !w || !r1 || !r2 || !r3 || !x || !y)
+  if (model_has_null(model) || theta_has_null(e, model) || !w || !r1 || !r2 || !r3 || !x || !y)
     return fail(e, SIPOC_INVALID_ARGUMENT, "NULL KKT apply argument");
   DeviceGuard guard(e->device);
-  (e->kkt_apply_fast != nullptr ? e->kkt_apply_fast : &launch_kkt_apply)(
-      e->dt, to_model(model), w, r1, r2, r3, x, y, e->batch, e->ld,
-      static_cast<cudaStream_t>(stream));
-  e->launches += 1;
-  return check_launch(e, "kkt_apply");
+  return kkt_apply_core(e, to_model(model), to_theta(model), w, r1, r2, r3, x, y,
+                        static_cast<cudaStream_t>(stream));
 }
 
 namespace {
 // block -> (mask, length of x, length of y) and the launch on the right vector slots
-sipoc_error kkt_apply_block_core(sipoc_engine *e, const KktModel &mdl, int block, const double *x,
-                                 double *y, cudaStream_t s) {
+sipoc_error kkt_apply_block_core(sipoc_engine *e, const KktModel &mdl, const KktThetaModel &tm,
+                                 int block, const double *x, double *y, cudaStream_t s) {
   const double *ix = nullptr, *iy = nullptr, *iz = nullptr;
   double *ox = nullptr, *oy = nullptr, *oz = nullptr;
   unsigned parts = 0;
@@ -1187,6 +1334,11 @@ sipoc_error kkt_apply_block_core(sipoc_engine *e, const KktModel &mdl, int block
     launch_kkt_apply_parts(e->dt, mdl, parts, ix, iy, iz, ox, oy, oz, e->batch, e->ld, s);
   }
   e->launches += 1;
+  if (e->hs.theta_dim > 0) {  // theta branches of helpers.cpp:1019-1368
+    ProfScope ps(&e->prof, "theta_apply_kernel", s);
+    launch_theta_apply(e->dt, tm, parts, nullptr, ix, iy, iz, ox, oy, oz, e->batch, e->ld, s);
+    e->launches += 1;
+  }
   return check_launch(e, "kkt_apply_block");
 }
 
@@ -1207,10 +1359,11 @@ sipoc_error sipoc_kkt_apply_block(sipoc_engine *e, const sipoc_kkt_model *model,
   int64_t nx = 0, ny = 0;
   kkt_block_dims(e, block, &nx, &ny);
   if (nx == 0 || ny == 0) return SIPOC_OK;  // an empty block (e.g. no inequalities)
-  if (model_has_null(model) || !x || !y)
+  if (model_has_null(model) || theta_has_null(e, model) || !x || !y)
     return fail(e, SIPOC_INVALID_ARGUMENT, "NULL KKT apply argument");
   DeviceGuard guard(e->device);
-  return kkt_apply_block_core(e, to_model(model), block, x, y, static_cast<cudaStream_t>(stream));
+  return kkt_apply_block_core(e, to_model(model), to_theta(model), block, x, y,
+                              static_cast<cudaStream_t>(stream));
 }
 
 sipoc_error sipoc_kkt_residual(sipoc_engine *e, const sipoc_kkt_model *model, const double *w,
@@ -1218,7 +1371,7 @@ sipoc_error sipoc_kkt_residual(sipoc_engine *e, const sipoc_kkt_model *model, co
                                const double *sol, const double *b, const int *ok,
                                double *residual_norm, double *stats, void *stream) {
   if (e == nullptr) return SIPOC_INVALID_ARGUMENT;
-  if (model_has_null(model) || !w || !r1 || !r2 || !r3 || !sol || !b)
+  if (model_has_null(model) || theta_has_null(e, model) || !w || !r1 || !r2 || !r3 || !sol || !b)
     return fail(e, SIPOC_INVALID_ARGUMENT, "NULL KKT residual argument");
   DeviceGuard guard(e->device);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -1230,18 +1383,22 @@ sipoc_error sipoc_kkt_residual(sipoc_engine *e, const sipoc_kkt_model *model, co
                                 static_cast<size_t>(std::max(1, e->hs.kkt_dim)) * e->ld *
                                     sizeof(double),
                                 s));
-  {
-    ProfScope ps(&e->prof, e->kkt_apply_fast != nullptr ? "kkt_apply_chain" : "kkt_apply_kernel", s);
-    (e->kkt_apply_fast != nullptr ? e->kkt_apply_fast : &launch_kkt_apply)(
-        e->dt, to_model(model), w, r1, r2, r3, sol, e->kkt_product, e->batch, e->ld, s);
-  }
+  if ((rc = kkt_apply_core(e, to_model(model), to_theta(model), w, r1, r2, r3, sol,
+                           e->kkt_product, s)) != SIPOC_OK)
+    return rc;
   {
     ProfScope ps(&e->prof, "kkt_residual_kernel", s);
     launch_kkt_residual(e->dt, e->kkt_product, b, ok, residual_norm, stats, e->batch, e->ld,
                         s);
   }
-  e->launches += stats != nullptr ? 3 : 2;
-  return check_launch(e, "kkt_residual");
+  e->launches += stats != nullptr ? 2 : 1;
+  if ((rc = check_launch(e, "kkt_residual")) != SIPOC_OK) return rc;
+  return reduce_stats(e, stats, stream);
+}
+
+static KktThetaModel host_resident_theta(const sipoc_engine *e) {
+  const double *const *t = e->hk_theta;
+  return KktThetaModel{t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7], t[8], t[9]};
 }
 
 static KktModel host_resident_model(const sipoc_engine *e) {
@@ -1263,18 +1420,37 @@ sipoc_error sipoc_kkt_factor_host(sipoc_engine *e, const sipoc_kkt_model *m, con
   for (int i = 0; i < 12; ++i)
     if ((rc = upload(e, src[i], e->hk_model[i], kkt_model_size(e->hs, i))) != SIPOC_OK)
       return rc;
+  if (e->hs.theta_dim > 0) {
+    if (theta_has_null(e, m)) return fail(e, SIPOC_INVALID_ARGUMENT, "NULL theta model block");
+    const sipoc_kkt_theta_model *t = m->theta;
+    const double *tsrc[10] = {t->node_hxt, t->node_jct, t->node_jgt, t->node_htt, t->edge_hxt,
+                              t->edge_hut, t->edge_dynt, t->edge_jct, t->edge_jgt, t->edge_htt};
+    for (int i = 0; i < 10; ++i)
+      if ((rc = upload(e, tsrc[i], e->hk_theta[i], kkt_theta_size(e->hs, i))) != SIPOC_OK)
+        return rc;
+  }
+  e->host_model_resident = true;
+  if (w == nullptr && r1 == nullptr && r2 == nullptr && r3 == nullptr && host_ok == nullptr) {
+    // sipoc_kkt_set_model_host: the model only (the operator entry points read it)
+    SIPOC_CUDA(e, cudaStreamSynchronize(e->host_stream));
+    return SIPOC_OK;
+  }
   const double *reg[4] = {w, r1, r2, r3};
   const int64_t reg_sizes[4] = {e->hs.z_dim, e->hs.x_dim, e->hs.y_dim, e->hs.z_dim};
   for (int i = 0; i < 4; ++i)
     if ((rc = upload(e, reg[i], e->hk_reg[i], reg_sizes[i])) != SIPOC_OK) return rc;
-  rc = kkt_factor_core(e, host_resident_model(e), e->hk_reg[0], e->hk_reg[1], e->hk_reg[2],
-                       e->hk_reg[3], e->h_status, e->host_stream);
+  rc = kkt_factor_core(e, host_resident_model(e), host_resident_theta(e), e->hk_reg[0],
+                       e->hk_reg[1], e->hk_reg[2], e->hk_reg[3], e->h_status, e->host_stream);
   if (rc != SIPOC_OK) return rc;
   if (host_ok != nullptr)
     SIPOC_CUDA(e, cudaMemcpyAsync(host_ok, e->h_status, e->batch * sizeof(int),
                                   cudaMemcpyDeviceToHost, e->host_stream));
   SIPOC_CUDA(e, cudaStreamSynchronize(e->host_stream));
   return SIPOC_OK;
+}
+
+sipoc_error sipoc_kkt_set_model_host(sipoc_engine *e, const sipoc_kkt_model *m) {
+  return sipoc_kkt_factor_host(e, m, nullptr, nullptr, nullptr, nullptr, nullptr);
 }
 
 sipoc_error sipoc_kkt_solve_host(sipoc_engine *e, const double *b, double *sol) {
@@ -1295,9 +1471,10 @@ sipoc_error sipoc_kkt_apply_host(sipoc_engine *e, const double *w, const double 
                                  const double *r2, const double *r3, const double *x,
                                  double *y) {
   if (e == nullptr || !w || !r1 || !r2 || !r3 || !x || !y) return SIPOC_INVALID_ARGUMENT;
-  if (!e->host_kkt_ready)
+  if (!e->host_kkt_ready || !e->host_model_resident)
     return fail(e, SIPOC_NOT_FACTORED,
-                "sipoc_kkt_apply_host needs the model uploaded by sipoc_kkt_factor_host");
+                "sipoc_kkt_apply_host needs the model uploaded by sipoc_kkt_factor_host / "
+                "sipoc_kkt_set_model_host");
   DeviceGuard guard(e->device);
   sipoc_error rc;
   const double *reg[4] = {w, r1, r2, r3};
@@ -1306,11 +1483,10 @@ sipoc_error sipoc_kkt_apply_host(sipoc_engine *e, const double *w, const double 
     if ((rc = upload(e, reg[i], e->hk_reg[i], reg_sizes[i])) != SIPOC_OK) return rc;
   if ((rc = upload(e, x, e->hk_vec[0], e->hs.kkt_dim)) != SIPOC_OK) return rc;
   if ((rc = upload(e, y, e->hk_vec[1], e->hs.kkt_dim)) != SIPOC_OK) return rc;
-  (e->kkt_apply_fast != nullptr ? e->kkt_apply_fast : &launch_kkt_apply)(
-      e->dt, host_resident_model(e), e->hk_reg[0], e->hk_reg[1], e->hk_reg[2], e->hk_reg[3],
-      e->hk_vec[0], e->hk_vec[1], e->batch, e->ld, e->host_stream);
-  e->launches += 1;
-  if ((rc = check_launch(e, "kkt_apply")) != SIPOC_OK) return rc;
+  if ((rc = kkt_apply_core(e, host_resident_model(e), host_resident_theta(e), e->hk_reg[0],
+                           e->hk_reg[1], e->hk_reg[2], e->hk_reg[3], e->hk_vec[0], e->hk_vec[1],
+                           e->host_stream)) != SIPOC_OK)
+    return rc;
   if ((rc = download(e, e->hk_vec[1], y, e->hs.kkt_dim)) != SIPOC_OK) return rc;
   SIPOC_CUDA(e, cudaStreamSynchronize(e->host_stream));
   return SIPOC_OK;
@@ -1320,9 +1496,10 @@ sipoc_error sipoc_kkt_apply_block_host(sipoc_engine *e, int block, const double 
   if (e == nullptr || !x || !y) return SIPOC_INVALID_ARGUMENT;
   if (block < SIPOC_KKT_BLOCK_H || block > SIPOC_KKT_BLOCK_GT)
     return fail(e, SIPOC_INVALID_ARGUMENT, "unknown KKT block");
-  if (!e->host_kkt_ready)
+  if (!e->host_kkt_ready || !e->host_model_resident)
     return fail(e, SIPOC_NOT_FACTORED,
-                "sipoc_kkt_apply_block_host needs the model uploaded by sipoc_kkt_factor_host");
+                "sipoc_kkt_apply_block_host needs the model uploaded by sipoc_kkt_factor_host / "
+                "sipoc_kkt_set_model_host");
   DeviceGuard guard(e->device);
   sipoc_error rc;
   int64_t nx = 0, ny = 0;
@@ -1330,8 +1507,8 @@ sipoc_error sipoc_kkt_apply_block_host(sipoc_engine *e, int block, const double 
   if (nx == 0 || ny == 0) return SIPOC_OK;
   if ((rc = upload(e, x, e->hk_vec[0], nx)) != SIPOC_OK) return rc;
   if ((rc = upload(e, y, e->hk_vec[1], ny)) != SIPOC_OK) return rc;
-  if ((rc = kkt_apply_block_core(e, host_resident_model(e), block, e->hk_vec[0], e->hk_vec[1],
-                                 e->host_stream)) != SIPOC_OK)
+  if ((rc = kkt_apply_block_core(e, host_resident_model(e), host_resident_theta(e), block,
+                                 e->hk_vec[0], e->hk_vec[1], e->host_stream)) != SIPOC_OK)
     return rc;
   if ((rc = download(e, e->hk_vec[1], y, ny)) != SIPOC_OK) return rc;
   SIPOC_CUDA(e, cudaStreamSynchronize(e->host_stream));

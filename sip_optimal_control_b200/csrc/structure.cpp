@@ -23,10 +23,11 @@ sipoc_error HostStructure::build(const sipoc_structure &s, std::string &err) {
     err = "negative num_edges or theta_dim";
     return SIPOC_INVALID_DIMENSIONS;
   }
-  if (s.theta_dim != 0) {
-    err = "theta_dim > 0 (Schur variables) is outside this engine's scope";
+  if (s.theta_dim > kMaxThetaDim) {
+    err = "theta_dim above the engine's limit (32)";
     return SIPOC_UNSUPPORTED;
   }
+  theta_dim = s.theta_dim;
   if (s.state_dims == nullptr || (E > 0 && s.control_dims == nullptr)) {
     err = "state_dims / control_dims must not be NULL";
     return SIPOC_INVALID_ARGUMENT;
@@ -155,8 +156,9 @@ sipoc_error HostStructure::build(const sipoc_structure &s, std::string &err) {
       off += m[i];
     }
   }
-  x_dim = n[E];
-  for (int e = 0; e < E; ++e) x_dim += n[e] + m[e];
+  sx_dim = n[E];
+  for (int e = 0; e < E; ++e) sx_dim += n[e] + m[e];
+  x_dim = sx_dim + theta_dim;  // theta closes the x vector (types.cpp:24-64)
   y_dyn.assign(N, 0);
   y_node_c.assign(N, 0);
   y_edge_c.assign(E, 0);
@@ -202,6 +204,12 @@ sipoc_error HostStructure::build(const sipoc_structure &s, std::string &err) {
     jcu_off[e + 1] = jcu_off[e] + edge_c[e] * m[e];
     jgx_off[e + 1] = jgx_off[e] + edge_g[e] * np;
     jgu_off[e + 1] = jgu_off[e] + edge_g[e] * m[e];
+  }
+  pn_off.assign(E + 1, 0);
+  cn_off.assign(E + 1, 0);
+  for (int e = 0; e < E; ++e) {
+    pn_off[e + 1] = pn_off[e] + n[parents[e]];
+    cn_off[e + 1] = cn_off[e] + n[children[e]];
   }
   node_c_off = prefix(node_c);
   node_g_off = prefix(node_g);
@@ -271,6 +279,10 @@ std::vector<int> HostStructure::serialise(DevTables &t) const {
   t.node_g_off = put(node_g_off);
   t.edge_c_off = put(edge_c_off);
   t.edge_g_off = put(edge_g_off);
+  t.pn_off = put(pn_off);
+  t.cn_off = put(cn_off);
+  t.theta_dim = theta_dim;
+  t.sx_dim = sx_dim;
   t.x_dim = x_dim;
   t.y_dim = y_dim;
   t.z_dim = z_dim;

@@ -14,6 +14,9 @@
 
 namespace sipoc {
 
+// Largest theta_dim (Schur / global variables) the theta kernels keep in registers.
+constexpr int kMaxThetaDim = 32;
+
 // Device-visible index tables.  All pointers point into one int32 device
 // allocation owned by the engine.
 struct DevTables {
@@ -38,7 +41,10 @@ struct DevTables {
   const int *jcx_off, *jcu_off, *jgx_off, *jgu_off;  // [E+1]
   const int *node_c_off, *node_g_off;     // [N+1] prefix sums of node_c / node_g
   const int *edge_c_off, *edge_g_off;     // [E+1]
+  const int *pn_off, *cn_off;             // [E+1] prefix sums of the parent / child state dims
+  // x = [x_0, u_0, ..., x_E, theta]: x_dim counts theta, sx_dim does not (types.cpp:24-64).
   int x_dim, y_dim, z_dim, kkt_dim;
+  int theta_dim, sx_dim;
 };
 
 struct HostStructure {
@@ -49,8 +55,8 @@ struct HostStructure {
       hxx_edge_off;
   std::vector<int> x_state, x_control, y_dyn, y_node_c, y_edge_c, z_node, z_edge;
   std::vector<int> jc_node_off, jg_node_off, jcx_off, jcu_off, jgx_off, jgu_off;
-  std::vector<int> node_c_off, node_g_off, edge_c_off, edge_g_off;
-  int x_dim = 0, y_dim = 0, z_dim = 0, kkt_dim = 0;
+  std::vector<int> node_c_off, node_g_off, edge_c_off, edge_g_off, pn_off, cn_off;
+  int x_dim = 0, y_dim = 0, z_dim = 0, kkt_dim = 0, theta_dim = 0, sx_dim = 0;
   int max_n = 0, max_m = 0;
   bool is_chain = false;    // parent[e] == e, child[e] == e + 1, root == 0
   bool is_uniform = false;  // all n equal, all m equal

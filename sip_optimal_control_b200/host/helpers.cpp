@@ -1,9 +1,10 @@
-// See helpers.hpp / types.hpp.  Marshalling only; every number is computed on the GPU.
+// See helpers.hpp.  Marshalling only; every number is computed on the GPU.
 #include "helpers.hpp"
 
 #include <algorithm>
 
 #include "../../include/sipoc.h"
+#include "device_state.hpp"
 
 namespace sip::optimal_control {
 
@@ -27,108 +28,76 @@ sipoc_structure describe(const Dimensions &d, const Topology &t) {
   return s;
 }
 
-double *block(int count) { return new double[std::max(count, 1)](); }
-
 }  // namespace
 
-// ---- ModelCallbackOutput (types.cpp:136-383, dynamic allocation mode only) -------------
-void ModelCallbackOutput::reserve(const Dimensions &d, const Topology &t) {
-  const int N = t.num_nodes(), E = t.num_edges;
-  nodes = new NodeModelCallbackOutput[N]();
-  edges = new EdgeModelCallbackOutput[std::max(E, 1)]();
-  for (int i = 0; i < N; ++i) {
-    const int n = d.get_state_dim(i), c = d.get_node_c_dim(i), g = d.get_node_g_dim(i);
-    nodes[i] = NodeModelCallbackOutput{0.0,          block(n), block(c),    block(c * n),
-                                       block(g),     block(g * n), block(n * n)};
-  }
-  for (int e = 0; e < E; ++e) {
-    const int np = d.get_state_dim(t.edge_parents[e]), nc = d.get_state_dim(t.edge_children[e]);
-    const int m = d.get_control_dim(e), c = d.get_edge_c_dim(e), g = d.get_edge_g_dim(e);
-    edges[e] = EdgeModelCallbackOutput{0.0,           block(np),     block(m),      block(nc),
-                                       block(nc * np), block(nc * m), block(c),      block(c * np),
-                                       block(c * m),   block(g),      block(g * np), block(g * m),
-                                       block(np * np), block(np * m), block(m * m)};
-  }
-}
-
-void ModelCallbackOutput::free(const Topology &t) {
-  if (nodes != nullptr) {
-    for (int i = 0; i < t.num_nodes(); ++i) {
-      NodeModelCallbackOutput &o = nodes[i];
-      for (double *p : {o.df_dx, o.c, o.dc_dx, o.g, o.dg_dx, o.d2L_dx2}) delete[] p;
-    }
-  }
-  if (edges != nullptr) {
-    for (int e = 0; e < t.num_edges; ++e) {
-      EdgeModelCallbackOutput &o = edges[e];
-      for (double *p : {o.df_dx, o.df_du, o.dyn_res, o.ddyn_dx, o.ddyn_du, o.c, o.dc_dx, o.dc_du,
-                        o.g, o.dg_dx, o.dg_du, o.d2L_dx2, o.d2L_dxdu, o.d2L_du2})
-        delete[] p;
-    }
-  }
-  delete[] nodes;
-  delete[] edges;
-  nodes = nullptr;
-  edges = nullptr;
-}
-
-// The engine validates on creation with the reference's rules (types.cpp:68-134).
-auto validate_input(const Dimensions &dimensions, const Topology &topology)
-    -> InputValidationStatus {
-  sipoc_engine *probe = nullptr;
-  const sipoc_structure s = describe(dimensions, topology);
-  const sipoc_error rc = sipoc_create(&s, &probe);
-  if (probe != nullptr) sipoc_destroy(probe);
-  if (rc == SIPOC_INVALID_DIMENSIONS) return InputValidationStatus::INVALID_DIMENSIONS;
-  if (rc == SIPOC_INVALID_TOPOLOGY) return InputValidationStatus::INVALID_TOPOLOGY;
-  return InputValidationStatus::SUCCESS;
-}
-
-void Workspace::reserve(const Dimensions &dimensions, const Topology &topology) {
-  model_callback_output.reserve(dimensions, topology);
-}
-void Workspace::free(const Topology &topology) {
-  model_callback_output.free(topology);
-  lqr_workspace.free();
-}
-
-// ---- CallbackProvider (helpers.cpp:11-26, 242-370, 749-900, 953-977) -----------------------
+// ---- CallbackProvider (helpers.cpp:11-26, 190-407, 749-951, 953-1368) ----------------------
 CallbackProvider::CallbackProvider(const Input &input, Workspace &workspace)
     : input_(input), workspace_(workspace), input_is_valid_(false) {
-  sipoc_engine *&engine = workspace_.lqr_workspace.engine;
-  if (engine != nullptr) sipoc_destroy(engine);
-  engine = nullptr;
+  LQR::Workspace &lw = workspace_.lqr_workspace;
+  lw.release_device();
+  delete workspace_.staging;
+  workspace_.staging = nullptr;
+  auto *dev = new LQR::DeviceState();
   const sipoc_structure s = describe(input.dimensions, input.topology);
-  input_is_valid_ = sipoc_create(&s, &engine) == SIPOC_OK;
+  last_error_ = sipoc_create(&s, &dev->engine);
+  input_is_valid_ = last_error_ == SIPOC_OK;
   if (!input_is_valid_) {
-    engine = nullptr;
+    dev->engine = nullptr;
+    delete dev;
     return;
   }
+  lw.device = dev;
   sipoc_kkt_sizes z{};
-  sipoc_kkt_get_sizes(engine, &z);
+  sipoc_kkt_get_sizes(dev->engine, &z);
+  auto *st = new Workspace::Staging();
   const int64_t sizes[12] = {z.node_hxx, z.node_jc,  z.node_jg,  z.edge_hxx,
                              z.edge_hxu, z.edge_huu, z.edge_A,   z.edge_B,
                              z.edge_jcx, z.edge_jcu, z.edge_jgx, z.edge_jgu};
+  const int64_t tsizes[10] = {z.node_hxt, z.node_jct,  z.node_jgt, z.node_htt, z.edge_hxt,
+                              z.edge_hut, z.edge_dynt, z.edge_jct, z.edge_jgt, z.edge_htt};
   for (int i = 0; i < 12; ++i)
-    workspace_.model[i].assign(static_cast<size_t>(std::max<int64_t>(sizes[i], 1)), 0.0);
-  for (auto &v : workspace_.vec) v.assign(static_cast<size_t>(std::max<int64_t>(z.kkt_dim, 1)), 0.0);
+    st->model[i].assign(static_cast<size_t>(std::max<int64_t>(sizes[i], 1)), 0.0);
+  for (int i = 0; i < 10; ++i)
+    st->theta[i].assign(static_cast<size_t>(std::max<int64_t>(tsizes[i], 1)), 0.0);
+  for (auto &v : st->vec) v.assign(static_cast<size_t>(std::max<int64_t>(z.kkt_dim, 1)), 0.0);
+  workspace_.staging = st;
+  // the compiled topology, for callers that read it from the workspace (helpers.cpp:218-219)
+  if (lw.child_offsets != nullptr) {
+    const int E = input.topology.num_edges;
+    sipoc_get_topology(dev->engine, lw.child_offsets, lw.child_edges, lw.preorder_nodes,
+                       lw.postorder_nodes);
+    std::copy(input.topology.edge_parents, input.topology.edge_parents + E, lw.edge_parents);
+    std::copy(input.topology.edge_children, input.topology.edge_children + E, lw.edge_children);
+  }
 }
 
-// Per-node / per-edge blocks -> the flat arrays of sipoc_kkt_model.
+// Per-node / per-edge blocks -> the flat arrays of sipoc_kkt_model (+ theta).
 void CallbackProvider::gather_model() {
   const Dimensions &d = input_.dimensions;
   const Topology &t = input_.topology;
   const ModelCallbackOutput &mco = workspace_.model_callback_output;
-  size_t o[12] = {0};
+  Workspace::Staging &st = *workspace_.staging;
+  const int p = d.theta_dim;
+  size_t o[12] = {0}, ot[10] = {0};
   auto put = [&](int which, const double *src, int count) {
-    std::copy(src, src + count, workspace_.model[which].begin() + o[which]);
+    std::copy(src, src + count, st.model[which].begin() + o[which]);
     o[which] += count;
   };
+  auto putt = [&](int which, const double *src, int count) {
+    if (count == 0) return;
+    std::copy(src, src + count, st.theta[which].begin() + ot[which]);
+    ot[which] += count;
+  };
   for (int i = 0; i < t.num_nodes(); ++i) {
-    const int n = d.get_state_dim(i);
-    put(0, mco.nodes[i].d2L_dx2, n * n);
-    put(1, mco.nodes[i].dc_dx, d.get_node_c_dim(i) * n);
-    put(2, mco.nodes[i].dg_dx, d.get_node_g_dim(i) * n);
+    const int n = d.get_state_dim(i), c = d.get_node_c_dim(i), g = d.get_node_g_dim(i);
+    const NodeModelCallbackOutput &no = mco.nodes[i];
+    put(0, no.d2L_dx2, n * n);
+    put(1, no.dc_dx, c * n);
+    put(2, no.dg_dx, g * n);
+    putt(0, no.d2L_dxdtheta, n * p);
+    putt(1, no.dc_dtheta, c * p);
+    putt(2, no.dg_dtheta, g * p);
+    putt(3, no.d2L_dtheta2, p * p);
   }
   for (int e = 0; e < t.num_edges; ++e) {
     const int np = d.get_state_dim(t.edge_parents[e]), nc = d.get_state_dim(t.edge_children[e]);
@@ -143,37 +112,71 @@ void CallbackProvider::gather_model() {
     put(9, eo.dc_du, c * m);
     put(10, eo.dg_dx, g * np);
     put(11, eo.dg_du, g * m);
+    putt(4, eo.d2L_dxdtheta, np * p);
+    putt(5, eo.d2L_dudtheta, m * p);
+    putt(6, eo.ddyn_dtheta, nc * p);
+    putt(7, eo.dc_dtheta, c * p);
+    putt(8, eo.dg_dtheta, g * p);
+    putt(9, eo.d2L_dtheta2, p * p);
   }
 }
+
+namespace {
+struct ModelView {
+  sipoc_kkt_theta_model theta;
+  sipoc_kkt_model model;
+  explicit ModelView(Workspace::Staging &st, int p) {
+    auto &m = st.model;
+    auto &t = st.theta;
+    theta = sipoc_kkt_theta_model{t[0].data(), t[1].data(), t[2].data(), t[3].data(), t[4].data(),
+                                  t[5].data(), t[6].data(), t[7].data(), t[8].data(), t[9].data()};
+    model = sipoc_kkt_model{m[0].data(), m[1].data(), m[2].data(),  m[3].data(),
+                            m[4].data(), m[5].data(), m[6].data(),  m[7].data(),
+                            m[8].data(), m[9].data(), m[10].data(), m[11].data(),
+                            p > 0 ? &theta : nullptr};
+  }
+  ModelView(const ModelView &) = delete;
+};
+}  // namespace
 
 bool CallbackProvider::factor(const double *w, const double *r1, const double *r2,
                               const double *r3) {
   if (!input_is_valid_) return false;  // helpers.cpp:244-246
   gather_model();
-  auto &mm = workspace_.model;
-  const sipoc_kkt_model model{mm[0].data(), mm[1].data(), mm[2].data(),  mm[3].data(),
-                              mm[4].data(), mm[5].data(), mm[6].data(),  mm[7].data(),
-                              mm[8].data(), mm[9].data(), mm[10].data(), mm[11].data()};
+  const ModelView view(*workspace_.staging, input_.dimensions.theta_dim);
   // Zero-length regularization vectors still need a valid pointer.
   static const double none = 0.0;
   int ok = 0;
-  const sipoc_error rc = sipoc_kkt_factor_host(workspace_.lqr_workspace.engine, &model,
-                                               w ? w : &none, r1 ? r1 : &none, r2 ? r2 : &none,
-                                               r3 ? r3 : &none, &ok);
-  return rc == SIPOC_OK && ok != 0;
+  last_error_ = sipoc_kkt_factor_host(engine_of(workspace_.lqr_workspace), &view.model,
+                                      w ? w : &none, r1 ? r1 : &none, r2 ? r2 : &none,
+                                      r3 ? r3 : &none, &ok);
+  model_is_current_ = false;  // the next operator call reads the workspace's model again
+  return last_error_ == SIPOC_OK && ok != 0;
 }
 
 void CallbackProvider::solve(const double *b, double *sol) {
-  sipoc_kkt_solve_host(workspace_.lqr_workspace.engine, b, sol);
+  if (!input_is_valid_) return;
+  last_error_ = sipoc_kkt_solve_host(engine_of(workspace_.lqr_workspace), b, sol);
+}
+
+// The operators read the current model_callback_output (helpers.cpp:1161-1183).
+bool CallbackProvider::upload_model() {
+  if (!input_is_valid_) return false;
+  if (model_is_current_) return true;
+  gather_model();
+  const ModelView view(*workspace_.staging, input_.dimensions.theta_dim);
+  last_error_ = sipoc_kkt_set_model_host(engine_of(workspace_.lqr_workspace), &view.model);
+  return last_error_ == SIPOC_OK;
 }
 
 void CallbackProvider::add_Kx_to_y(const double *w, const double *r1, const double *r2,
                                    const double *r3, const double *x_x, const double *x_y,
                                    const double *x_z, double *y_x, double *y_y, double *y_z) {
+  if (!upload_model()) return;
   const int E = input_.topology.num_edges;
   const int xd = input_.dimensions.get_x_dim(E), yd = input_.dimensions.get_y_dim(E),
             zd = input_.dimensions.get_z_dim(E);
-  std::vector<double> &x = workspace_.vec[0], &y = workspace_.vec[1];
+  std::vector<double> &x = workspace_.staging->vec[0], &y = workspace_.staging->vec[1];
   std::copy(x_x, x_x + xd, x.begin());
   std::copy(x_y, x_y + yd, x.begin() + xd);
   std::copy(x_z, x_z + zd, x.begin() + xd + yd);
@@ -181,27 +184,22 @@ void CallbackProvider::add_Kx_to_y(const double *w, const double *r1, const doub
   std::copy(y_y, y_y + yd, y.begin() + xd);
   std::copy(y_z, y_z + zd, y.begin() + xd + yd);
   static const double none = 0.0;
-  sipoc_kkt_apply_host(workspace_.lqr_workspace.engine, w ? w : &none, r1, r2, r3 ? r3 : &none,
-                       x.data(), y.data());
+  last_error_ = sipoc_kkt_apply_host(engine_of(workspace_.lqr_workspace), w ? w : &none, r1,
+                                     r2, r3 ? r3 : &none, x.data(), y.data());
+  if (last_error_ != SIPOC_OK) return;
   std::copy(y.begin(), y.begin() + xd, y_x);
   std::copy(y.begin() + xd, y.begin() + xd + yd, y_y);
   std::copy(y.begin() + xd + yd, y.begin() + xd + yd + zd, y_z);
 }
 
-void CallbackProvider::add_Hx_to_y(const double *x, double *y) {
-  sipoc_kkt_apply_block_host(workspace_.lqr_workspace.engine, SIPOC_KKT_BLOCK_H, x, y);
+void CallbackProvider::apply_block(int block, const double *x, double *y) {
+  if (!upload_model()) return;
+  last_error_ = sipoc_kkt_apply_block_host(engine_of(workspace_.lqr_workspace), block, x, y);
 }
-void CallbackProvider::add_Cx_to_y(const double *x, double *y) {
-  sipoc_kkt_apply_block_host(workspace_.lqr_workspace.engine, SIPOC_KKT_BLOCK_C, x, y);
-}
-void CallbackProvider::add_CTx_to_y(const double *x, double *y) {
-  sipoc_kkt_apply_block_host(workspace_.lqr_workspace.engine, SIPOC_KKT_BLOCK_CT, x, y);
-}
-void CallbackProvider::add_Gx_to_y(const double *x, double *y) {
-  sipoc_kkt_apply_block_host(workspace_.lqr_workspace.engine, SIPOC_KKT_BLOCK_G, x, y);
-}
-void CallbackProvider::add_GTx_to_y(const double *x, double *y) {
-  sipoc_kkt_apply_block_host(workspace_.lqr_workspace.engine, SIPOC_KKT_BLOCK_GT, x, y);
-}
+void CallbackProvider::add_Hx_to_y(const double *x, double *y) { apply_block(SIPOC_KKT_BLOCK_H, x, y); }
+void CallbackProvider::add_Cx_to_y(const double *x, double *y) { apply_block(SIPOC_KKT_BLOCK_C, x, y); }
+void CallbackProvider::add_CTx_to_y(const double *x, double *y) { apply_block(SIPOC_KKT_BLOCK_CT, x, y); }
+void CallbackProvider::add_Gx_to_y(const double *x, double *y) { apply_block(SIPOC_KKT_BLOCK_G, x, y); }
+void CallbackProvider::add_GTx_to_y(const double *x, double *y) { apply_block(SIPOC_KKT_BLOCK_GT, x, y); }
 
 }  // namespace sip::optimal_control

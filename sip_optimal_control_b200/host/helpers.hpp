@@ -1,14 +1,20 @@
-// Host-side stand-in for the reference's CallbackProvider (helpers.hpp:7-33), theta_dim == 0:
-// the Newton-KKT linear-solve callbacks SIP invokes once per interior-point iteration.  Every
-// method forwards to one C-ABI entry point of libsipoc.so (include/sipoc.h); the arithmetic
-// runs on the GPU, this class only gathers / scatters the caller's per-block pointers.
+// Host-side stand-in for the reference's CallbackProvider (helpers.hpp:7-33): the Newton-KKT
+// linear-solve callbacks SIP invokes once per interior-point iteration, theta (Schur)
+// variables included.  Every method forwards to one C-ABI entry point of libsipoc.so
+// (include/sipoc.h); the arithmetic runs on the GPU, this class only gathers / scatters the
+// caller's per-block pointers.
 //
 //   method                      C ABI call                       reference
 //   --------------------------  -------------------------------  ------------------------
-//   factor                      sipoc_kkt_factor_host            helpers.cpp:242-370
-//   solve                       sipoc_kkt_solve_host             helpers.cpp:749-900
+//   factor                      sipoc_kkt_factor_host            helpers.cpp:190-407
+//   solve                       sipoc_kkt_solve_host             helpers.cpp:749-951
 //   add_Kx_to_y                 sipoc_kkt_apply_host             helpers.cpp:953-977
 //   add_{H,C,CT,G,GT}x_to_y     sipoc_kkt_apply_block_host       helpers.cpp:979-1368
+//
+// The operator methods read the CURRENT workspace.model_callback_output, like the reference
+// (helpers.cpp:1161-1183): the model is gathered and uploaded again on every call unless the
+// caller has declared it unchanged (model_unchanged()).  The reference's void methods cannot
+// report a failing call; the last error is latched and readable through last_error().
 #pragma once
 
 #include "types.hpp"
@@ -22,8 +28,8 @@ class CallbackProvider {
   CallbackProvider(const Input &input, Workspace &workspace);
 
   // KKT -> LQR reduction with the diagonal weights (w, r3 indexed like z; r1 like x; r2
-  // like y) and the regularized LQR factorization.  False when a weight is not positive
-  // or the factorization fails.
+  // like y), the regularized LQR factorization and, with theta_dim > 0, the Schur
+  // complement on theta.  False when a weight is not positive or a factorization fails.
   bool factor(const double *w, const double *r1, const double *r2, const double *r3);
 
   // sol = K^-1 b on flat [x | y | z] vectors, against the last successful factor.
@@ -43,12 +49,21 @@ class CallbackProvider {
   void add_Gx_to_y(const double *x, double *y);
   void add_GTx_to_y(const double *x, double *y);
 
+  // Not in the reference.  model_unchanged(): the model blocks have not changed since the
+  // last upload (skips the gather + upload of the next operator calls; any factor resets it).
+  void model_unchanged() { model_is_current_ = true; }
+  int last_error() const { return last_error_; }
+
  private:
-  void gather_model();  // per-block model pointers -> the flat arrays the C ABI takes
+  void gather_model();       // per-block model pointers -> the flat arrays the C ABI takes
+  bool upload_model();       // gather + sipoc_kkt_set_model_host unless declared current
+  void apply_block(int block, const double *x, double *y);
 
   const Input &input_;
   Workspace &workspace_;
   bool input_is_valid_;
+  bool model_is_current_ = false;
+  int last_error_ = 0;
 };
 
 }  // namespace sip::optimal_control

@@ -13,8 +13,14 @@
 //   LQRFactor.RejectsInvalidTreeTopology                          tests/lqr_test.cpp:452-464
 //   CallbackProvider.SolvesChainWithNodeAndEdgeConstraints        tests/variable_dimensions_test.cpp:77-181, 265-290
 //   CallbackProvider.SolvesBranchedSystemWithZeroDimensionalRoot  tests/variable_dimensions_test.cpp:316-336
-//   InputValidation (DAG and negative dimension rejected)         tests/variable_dimensions_test.cpp:183-224
+//   InputValidation.AcceptsSeparateNodeAndEdgeDimensions          tests/variable_dimensions_test.cpp:183-224
+//   Workspace.UniformStaticAndDynamicMemorySizesMatch             tests/variable_dimensions_test.cpp:226-263
+//   CallbackProvider on a mem_assign'ed arena (size == num_bytes) tests/variable_dimensions_test.cpp:281-287
+//   CallbackProvider.SolvesBranchedSystemWithSchurVariables       tests/variable_dimensions_test.cpp:338-363
+// (Workspace::num_bytes / mem_assign are used in their form without the un-vendored SIP outer
+// loop's own workspace term: sip::Workspace and sip::Settings do not exist in this image.)
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdio>
 #include <functional>
@@ -175,29 +181,32 @@ static void test_factor_status_api() {
     Problem p = identity_chain(2, 1, 2);
     LQR::Input in = p.input();
     LQR::Workspace ws;
+    ws.reserve(p.dimensions, p.topology);
     LQR lqr(in, ws);
     CHECK(lqr.factor_with_status() == LQR::FactorStatus::SUCCESS);
     CHECK(lqr.factor());
-    ws.free();
+    ws.free(p.topology.num_edges);
   }
   {  // delta[T][0] = 0 -> INVALID_DELTA
     Problem p = identity_chain(2, 1, 2);
     p.delta[2][0] = 0.0;
     LQR::Input in = p.input();
     LQR::Workspace ws;
+    ws.reserve(p.dimensions, p.topology);
     LQR lqr(in, ws);
     CHECK(lqr.factor_with_status() == LQR::FactorStatus::INVALID_DELTA);
     CHECK(!lqr.factor());
-    ws.free();
+    ws.free(p.topology.num_edges);
   }
   {  // n = m = T = 1, Q[T] = -2 -> F failure
     Problem p = identity_chain(1, 1, 1);
     p.Q[1][0] = -2.0;
     LQR::Input in = p.input();
     LQR::Workspace ws;
+    ws.reserve(p.dimensions, p.topology);
     LQR lqr(in, ws);
     CHECK(lqr.factor_with_status() == LQR::FactorStatus::F_FACTORIZATION_FAILURE);
-    ws.free();
+    ws.free(p.topology.num_edges);
   }
   {  // Q[T] = 0, R = -1 -> G failure
     Problem p = identity_chain(1, 1, 1);
@@ -205,9 +214,10 @@ static void test_factor_status_api() {
     p.R[0][0] = -1.0;
     LQR::Input in = p.input();
     LQR::Workspace ws;
+    ws.reserve(p.dimensions, p.topology);
     LQR lqr(in, ws);
     CHECK(lqr.factor_with_status() == LQR::FactorStatus::G_FACTORIZATION_FAILURE);
-    ws.free();
+    ws.free(p.topology.num_edges);
   }
 }
 
@@ -231,8 +241,13 @@ static void test_nonuniform_delta_chain() {  // tests/lqr_test.cpp:229-263
   p.delta[T] = {0.07, 0.17, 0.29};
   p.link();
   LQR::Input in = p.input();
+  // the workspace on a caller arena (lqr.hpp:142-186): sized by num_bytes, carved by mem_assign
   LQR::Workspace ws;
+  std::vector<unsigned char> arena(LQR::Workspace::num_bytes(p.dimensions, p.topology));
+  CHECK(LQR::Workspace::num_bytes(p.dimensions, p.topology) == LQR::Workspace::num_bytes(n, m, T));
+  CHECK(ws.mem_assign(p.dimensions, p.topology, arena.data()) == static_cast<int>(arena.size()));
   LQR lqr(in, ws);
+  CHECK(ws.postorder_nodes[0] == T && ws.preorder_nodes[0] == 0);  // compiled into the arena
   CHECK(lqr.factor());
   LQR::Output out = p.output();
   lqr.solve(out);
@@ -244,7 +259,7 @@ static void test_nonuniform_delta_chain() {  // tests/lqr_test.cpp:229-263
   CHECK(lqr.factor());
   lqr.solve(out);
   CHECK(p.x[1] == x1);
-  ws.free();
+  ws.release_device();  // an arena user drops the GPU engine explicitly
 }
 
 static void test_branching_tree() {  // tests/lqr_test.cpp:300-335, 411-429
@@ -267,6 +282,7 @@ static void test_branching_tree() {  // tests/lqr_test.cpp:300-335, 411-429
   p.link();
   LQR::Input in = p.input();
   LQR::Workspace ws;
+  ws.reserve(p.dimensions, p.topology);
   LQR lqr(in, ws);
   CHECK(lqr.factor_with_status() == LQR::FactorStatus::SUCCESS);
   LQR::Output out = p.output();
@@ -274,17 +290,18 @@ static void test_branching_tree() {  // tests/lqr_test.cpp:300-335, 411-429
   const double res = residual_norm(p);
   std::printf("  branching tree residual %.3e\n", res);
   CHECK(res < 1e-12);
-  ws.free();
+  ws.free(p.topology.num_edges);
 }
 
 static void test_rejects_invalid_topology() {  // tests/lqr_test.cpp:452-464
   Problem p(2, 0, {0, 0}, {1, 1}, {2, 2, 2}, {1, 1});  // two edges into node 1
   LQR::Input in = p.input();
   LQR::Workspace ws;
+  ws.reserve(p.dimensions, p.topology);
   LQR lqr(in, ws);
   CHECK(lqr.factor_with_status() == LQR::FactorStatus::INVALID_TOPOLOGY);
   CHECK(!lqr.factor());
-  ws.free();
+  ws.free(p.topology.num_edges);
 }
 
 // ---- Newton-KKT (tests/variable_dimensions_test.cpp) ------------------------------------
@@ -296,59 +313,64 @@ static void identity_scaled(double *v, int n, double s) {
   for (int i = 0; i < n; ++i) v[i * n + i] = s;
 }
 
-static double kkt_case(int E, const std::vector<int> &parents, const std::vector<int> &children,
-                       const std::vector<int> &n, const std::vector<int> &m,
-                       const std::vector<int> &nc, const std::vector<int> &ng,
-                       const std::vector<int> &ec, const std::vector<int> &eg) {
-  Input input;
-  input.topology.num_edges = E;
-  input.topology.reserve(E);
-  input.topology.set_tree(0, parents.data(), children.data());
-  input.dimensions.reserve(E);
-  auto fill = [](const int *dst, const std::vector<int> &src) {
-    for (size_t i = 0; i < src.size(); ++i) const_cast<int *>(dst)[i] = src[i];
-  };
-  fill(input.dimensions.state_dims, n);
-  fill(input.dimensions.control_dims, m);
-  fill(input.dimensions.node_c_dims, nc);
-  fill(input.dimensions.node_g_dims, ng);
-  fill(input.dimensions.edge_c_dims, ec);
-  fill(input.dimensions.edge_g_dims, eg);
-  CHECK(validate_input(input.dimensions, input.topology) == InputValidationStatus::SUCCESS);
-
-  Workspace workspace;
-  workspace.reserve(input.dimensions, input.topology);
+// initialize_model (:77-133) + expect_kkt_solve (:135-181) on a workspace the caller set up.
+static double kkt_solve_residual(const Input &input, Workspace &workspace, double theta_diagonal) {
+  const Dimensions &d = input.dimensions;
+  const Topology &t = input.topology;
+  const int E = t.num_edges, p = d.theta_dim;
   auto &mco = workspace.model_callback_output;
-  for (int node = 0; node <= E; ++node) {  // initialize_model, :77-133
-    const int nn = n[node];
-    fill_sequence(mco.nodes[node].dc_dx, nc[node] * nn, 0.013 * (node + 1));
-    fill_sequence(mco.nodes[node].dg_dx, ng[node] * nn, -0.011 * (node + 1));
-    identity_scaled(mco.nodes[node].d2L_dx2, nn, 2.5 + 0.2 * node);
+  for (int node = 0; node <= E; ++node) {
+    const int n = d.get_state_dim(node), c = d.get_node_c_dim(node), g = d.get_node_g_dim(node);
+    auto &o = mco.nodes[node];
+    fill_sequence(o.dc_dx, c * n, 0.013 * (node + 1));
+    fill_sequence(o.dc_dtheta, c * p, 0.001 * (node + 1));
+    fill_sequence(o.dg_dx, g * n, -0.011 * (node + 1));
+    fill_sequence(o.dg_dtheta, g * p, -0.0007 * (node + 1));
+    identity_scaled(o.d2L_dx2, n, 2.5 + 0.2 * node);
+    fill_sequence(o.d2L_dxdtheta, n * p, 0.0005 * (node + 1));
+    identity_scaled(o.d2L_dtheta2, p, theta_diagonal);
   }
   for (int e = 0; e < E; ++e) {
-    const int np = n[parents[e]], nch = n[children[e]], mm = m[e];
-    fill_sequence(mco.edges[e].ddyn_dx, nch * np, 0.025 + 0.004 * e);
-    fill_sequence(mco.edges[e].ddyn_du, nch * mm, -0.031 - 0.003 * e);
-    fill_sequence(mco.edges[e].dc_dx, ec[e] * np, 0.017 * (e + 1));
-    fill_sequence(mco.edges[e].dc_du, ec[e] * mm, 0.019 * (e + 1));
-    fill_sequence(mco.edges[e].dg_dx, eg[e] * np, -0.014 * (e + 1));
-    fill_sequence(mco.edges[e].dg_du, eg[e] * mm, 0.016 * (e + 1));
-    identity_scaled(mco.edges[e].d2L_dx2, np, 0.3 + 0.05 * e);
-    fill_sequence(mco.edges[e].d2L_dxdu, np * mm, 0.009 * (e + 1));
-    identity_scaled(mco.edges[e].d2L_du2, mm, 3.0 + 0.2 * e);
+    const int np = d.get_state_dim(t.edge_parents[e]), nch = d.get_state_dim(t.edge_children[e]);
+    const int mm = d.get_control_dim(e), c = d.get_edge_c_dim(e), g = d.get_edge_g_dim(e);
+    auto &o = mco.edges[e];
+    fill_sequence(o.ddyn_dx, nch * np, 0.025 + 0.004 * e);
+    fill_sequence(o.ddyn_du, nch * mm, -0.031 - 0.003 * e);
+    fill_sequence(o.ddyn_dtheta, nch * p, 0.0009 * (e + 1));
+    fill_sequence(o.dc_dx, c * np, 0.017 * (e + 1));
+    fill_sequence(o.dc_du, c * mm, 0.019 * (e + 1));
+    fill_sequence(o.dc_dtheta, c * p, 0.0008 * (e + 1));
+    fill_sequence(o.dg_dx, g * np, -0.014 * (e + 1));
+    fill_sequence(o.dg_du, g * mm, 0.016 * (e + 1));
+    fill_sequence(o.dg_dtheta, g * p, -0.0006 * (e + 1));
+    identity_scaled(o.d2L_dx2, np, 0.3 + 0.05 * e);
+    fill_sequence(o.d2L_dxdu, np * mm, 0.009 * (e + 1));
+    identity_scaled(o.d2L_du2, mm, 3.0 + 0.2 * e);
+    fill_sequence(o.d2L_dxdtheta, np * p, 0.0004 * (e + 1));
+    fill_sequence(o.d2L_dudtheta, mm * p, -0.0003 * (e + 1));
+    identity_scaled(o.d2L_dtheta2, p, theta_diagonal);
   }
 
-  // expect_kkt_solve, :135-181
   CallbackProvider callback_provider(input, workspace);
-  const int x_dim = input.dimensions.get_x_dim(E), y_dim = input.dimensions.get_y_dim(E),
-            z_dim = input.dimensions.get_z_dim(E), kkt_dim = x_dim + y_dim + z_dim;
+  const int x_dim = d.get_x_dim(E), y_dim = d.get_y_dim(E), z_dim = d.get_z_dim(E),
+            kkt_dim = x_dim + y_dim + z_dim;
+  CHECK(workspace.x_dim == x_dim && workspace.stagewise_kkt_dim == kkt_dim - p);
   std::vector<double> w(z_dim + 1, 1.3), r2(y_dim + 1, 0.9), r3(z_dim + 1, 0.4), r1(x_dim + 1);
   fill_sequence(r1.data(), x_dim, 0.03);
   for (double &v : r1) v += 0.2;
+  {  // the operator works before any factor: it reads the workspace's current model
+    std::vector<double> ones(x_dim + 1, 1.0), hx(x_dim + 1, 0.0);
+    callback_provider.add_Hx_to_y(ones.data(), hx.data());
+    CHECK(callback_provider.last_error() == 0);
+    double total = 0.0;
+    for (int i = 0; i < x_dim; ++i) total += std::fabs(hx[i]);
+    CHECK(total > 0.0);
+  }
   CHECK(callback_provider.factor(w.data(), r1.data(), r2.data(), r3.data()));
   std::vector<double> rhs(kkt_dim), solution(kkt_dim, 0.0);
   fill_sequence(rhs.data(), kkt_dim, 0.01);
   callback_provider.solve(rhs.data(), solution.data());
+  CHECK(callback_provider.last_error() == 0);
   std::vector<double> px(x_dim + 1, 0.0), py(y_dim + 1, 0.0), pz(z_dim + 1, 0.0);
   callback_provider.add_Kx_to_y(w.data(), r1.data(), r2.data(), r3.data(), solution.data(),
                                 solution.data() + x_dim, solution.data() + x_dim + y_dim,
@@ -356,6 +378,7 @@ static double kkt_case(int E, const std::vector<int> &parents, const std::vector
   {  // add_Kx_to_y is the sum of its five blocks and the diagonal terms (helpers.cpp:953-977)
     const double *sx = solution.data(), *sy = sx + x_dim, *sz = sy + y_dim;
     std::vector<double> qx(x_dim + 1, 0.0), qy(y_dim + 1, 0.0), qz(z_dim + 1, 0.0);
+    callback_provider.model_unchanged();  // five operator calls on one upload
     callback_provider.add_Hx_to_y(sx, qx.data());
     callback_provider.add_Cx_to_y(sx, qy.data());
     callback_provider.add_CTx_to_y(sy, qx.data());
@@ -373,42 +396,141 @@ static double kkt_case(int E, const std::vector<int> &parents, const std::vector
   for (int i = 0; i < y_dim; ++i) sq += (py[i] - rhs[x_dim + i]) * (py[i] - rhs[x_dim + i]);
   for (int i = 0; i < z_dim; ++i)
     sq += (pz[i] - rhs[x_dim + y_dim + i]) * (pz[i] - rhs[x_dim + y_dim + i]);
-  workspace.free(input.topology);
-  input.topology.free();
-  input.dimensions.free();
   return std::sqrt(sq);
 }
 
+struct ChainTopology {
+  std::array<int, 2> parent = {0, 1};
+  std::array<int, 2> child = {1, 2};
+};
+struct BranchTopology {
+  std::array<int, 2> parent = {0, 0};
+  std::array<int, 2> child = {1, 2};
+};
+
+// `arena`: the workspace on caller memory (mem_assign) instead of reserve / free.
+static double kkt_case(int theta_dim, const std::array<int, 2> &parent,
+                       const std::array<int, 2> &child, const std::array<int, 3> &state_dims,
+                       const std::array<int, 2> &control_dims, const std::array<int, 3> &node_c,
+                       const std::array<int, 3> &node_g, const std::array<int, 2> &edge_c,
+                       const std::array<int, 2> &edge_g, bool arena, double theta_diagonal = 0.0) {
+  // aggregate initialisation, as the reference's tests write it
+  Input input{
+      .dimensions = {theta_dim, state_dims.data(), control_dims.data(), node_c.data(),
+                     node_g.data(), edge_c.data(), edge_g.data()},
+      .topology = {2, 0, parent.data(), child.data()},
+      .model_callback = [](const ModelCallbackInput &, ModelCallbackOutput &) {},
+      .timeout_callback = []() { return false; },
+  };
+  CHECK(validate_input(input.dimensions, input.topology) == InputValidationStatus::SUCCESS);
+  CHECK(input.num_bound_sides() == 0);
+  Workspace workspace;
+  std::vector<unsigned char> memory;
+  if (arena) {
+    memory.resize(Workspace::num_bytes(input.dimensions, input.topology));
+    CHECK(workspace.mem_assign(input.dimensions, input.topology, memory.data()) ==
+          static_cast<int>(memory.size()));
+  } else {
+    workspace.reserve(input.dimensions, input.topology);
+  }
+  const double res = kkt_solve_residual(input, workspace, theta_diagonal);
+  if (arena) {
+    workspace.lqr_workspace.release_device();
+    delete workspace.staging;
+  } else {
+    workspace.free(input.topology);
+  }
+  return res;
+}
+
 static void test_callback_provider() {
-  const double chain = kkt_case(2, {0, 1}, {1, 2}, {2, 1, 3}, {1, 2}, {1, 0, 2}, {0, 2, 1},
-                                {1, 2}, {2, 1});  // :265-290
-  std::printf("  KKT chain residual %.3e\n", chain);
+  const ChainTopology chain_t;
+  const BranchTopology branch_t;
+  const double chain = kkt_case(0, chain_t.parent, chain_t.child, {2, 1, 3}, {1, 2}, {1, 0, 2},
+                                {0, 2, 1}, {1, 2}, {2, 1}, /*arena=*/true);  // :265-290
+  std::printf("  KKT chain (arena workspace) residual %.3e\n", chain);
   CHECK(chain < 1e-9);
-  const double siblings = kkt_case(2, {0, 0}, {1, 2}, {2, 1, 3}, {1, 2}, {1, 0, 1}, {1, 1, 0},
-                                   {2, 1}, {1, 2});  // :292-314
+  const double siblings = kkt_case(0, branch_t.parent, branch_t.child, {2, 1, 3}, {1, 2},
+                                   {1, 0, 1}, {1, 1, 0}, {2, 1}, {1, 2}, false);  // :292-314
   std::printf("  KKT sibling-edges residual %.3e\n", siblings);
   CHECK(siblings < 1e-9);
-  const double zero_root = kkt_case(2, {0, 0}, {1, 2}, {0, 1, 3}, {1, 2}, {0, 0, 0}, {0, 0, 0},
-                                    {0, 0}, {0, 0});  // :316-336
+  const double zero_root = kkt_case(0, branch_t.parent, branch_t.child, {0, 1, 3}, {1, 2},
+                                    {0, 0, 0}, {0, 0, 0}, {0, 0}, {0, 0}, false);  // :316-336
   std::printf("  KKT zero-dimensional-root residual %.3e\n", zero_root);
   CHECK(zero_root < 1e-9);
+  const double schur = kkt_case(2, branch_t.parent, branch_t.child, {2, 1, 3}, {1, 2}, {1, 0, 1},
+                                {0, 1, 1}, {1, 2}, {2, 1}, true, 6.0);  // :338-363
+  std::printf("  KKT Schur-variables (theta_dim 2, arena) residual %.3e\n", schur);
+  CHECK(schur < 1e-8);
 }
 
 static void test_input_validation() {  // :183-224
-  Topology dag;
-  dag.num_edges = 2;
-  dag.reserve(2);
-  const int parents[2] = {0, 1}, children[2] = {1, 1};
-  dag.set_tree(0, parents, children);
+  const std::array<int, 3> state_dims = {2, 1, 3};
+  const std::array<int, 2> control_dims = {1, 2};
+  const std::array<int, 3> node_c_dims = {0, 1, 0}, node_g_dims = {1, 0, 2};
+  const std::array<int, 2> edge_c_dims = {2, 1}, edge_g_dims = {1, 3};
+  const Dimensions dimensions{2, state_dims.data(), control_dims.data(), node_c_dims.data(),
+                              node_g_dims.data(), edge_c_dims.data(), edge_g_dims.data()};
+  const ChainTopology chain_topology;
+  const Topology chain{2, 0, chain_topology.parent.data(), chain_topology.child.data()};
+  CHECK(validate_input(dimensions, chain) == InputValidationStatus::SUCCESS);
+  const BranchTopology tree_topology;
+  const Topology tree{2, 0, tree_topology.parent.data(), tree_topology.child.data()};
+  CHECK(validate_input(dimensions, tree) == InputValidationStatus::SUCCESS);
+  const std::array<int, 2> dag_parent = {0, 1}, dag_child = {2, 2};
+  const Topology dag{2, 0, dag_parent.data(), dag_child.data()};
+  CHECK(validate_input(dimensions, dag) == InputValidationStatus::INVALID_TOPOLOGY);
+  const std::array<int, 2> negative_edge_c_dims = {-1, 1};
+  const Dimensions invalid{2, state_dims.data(), control_dims.data(), node_c_dims.data(),
+                           node_g_dims.data(), negative_edge_c_dims.data(), edge_g_dims.data()};
+  CHECK(validate_input(invalid, tree) == InputValidationStatus::INVALID_DIMENSIONS);
+  // reserve / set_uniform / mem_assign of the two structure types (lqr.hpp:12-18, 35-44)
   Dimensions d;
+  d.reserve(2);
   d.set_uniform(2, 2, 1, 0, 0, 0, 0);
-  CHECK(validate_input(d, dag) == InputValidationStatus::INVALID_TOPOLOGY);
-  dag.set_chain();
-  CHECK(validate_input(d, dag) == InputValidationStatus::SUCCESS);
-  const_cast<int *>(d.state_dims)[1] = -1;
-  CHECK(validate_input(d, dag) == InputValidationStatus::INVALID_DIMENSIONS);
-  dag.free();
+  CHECK(d.max_state_dim(3) == 2 && d.get_stagewise_kkt_dim(2) == 14);
+  std::array<unsigned char, Topology::num_bytes(2) + Dimensions::num_bytes(2)> arena{};
+  Topology t2;
+  CHECK(t2.mem_assign(2, arena.data()) == Topology::num_bytes(2));
+  t2.set_chain();
+  Dimensions d2;
+  CHECK(d2.mem_assign(2, arena.data() + Topology::num_bytes(2)) == Dimensions::num_bytes(2));
+  d2.set_uniform(2, 2, 1, 0, 0, 0, 0);
+  CHECK(validate_input(d2, t2) == InputValidationStatus::SUCCESS);
   d.free();
+}
+
+static void test_memory_sizes() {  // :226-263, and the values themselves
+  constexpr int E = 2, n = 2, m = 1, nc = 1, ng = 2, ec = 3, eg = 1, p = 2;
+  const std::array<int, 3> state_dims = {n, n, n}, node_c = {nc, nc, nc}, node_g = {ng, ng, ng};
+  const std::array<int, 2> control_dims = {m, m}, edge_c = {ec, ec}, edge_g = {eg, eg};
+  const Dimensions dimensions{p, state_dims.data(), control_dims.data(), node_c.data(),
+                              node_g.data(), edge_c.data(), edge_g.data()};
+  const BranchTopology tree;
+  const Topology topology{E, 0, tree.parent.data(), tree.child.data()};
+  CHECK(ModelCallbackOutput::num_bytes(n, m, E, nc, ng, ec, eg, p) ==
+        ModelCallbackOutput::num_bytes(dimensions, topology));
+  CHECK(Workspace::RegularizedLQRData::num_bytes(n, m, E, nc, ng, ec, eg, p) ==
+        Workspace::RegularizedLQRData::num_bytes(dimensions, E));
+  CHECK(LQR::Workspace::num_bytes(n, m, E) == LQR::Workspace::num_bytes(dimensions, topology));
+  // The reference's constexpr formulas evaluated by hand at these dims (types.hpp:104-123,
+  // 193-235; lqr.hpp:16-18, 38-40, 104-106, 146-184) on an LP64 target:
+  static_assert(Topology::num_bytes(E) == 16 && Dimensions::num_bytes(E) == 60);
+  static_assert(LQR::Output::num_bytes(E) == 64);
+  static_assert(LQR::Workspace::num_bytes(n, m, E) == 820);
+  static_assert(ModelCallbackOutput::num_bytes(n, m, E, nc, ng, ec, eg, p) ==
+                3 * 96 + 2 * 176 + (3 * 31 + 2 * 58) * 8);
+  static_assert(Workspace::RegularizedLQRData::num_bytes(n, m, E, nc, ng, ec, eg, p) == 2048);
+  static_assert(ModelCallbackInput::num_bytes(E) == 3 * 32 + 2 * 64);
+  // mem_assign consumes exactly num_bytes, for every view type
+  std::vector<unsigned char> arena(Workspace::num_bytes(dimensions, topology));
+  Workspace workspace;
+  CHECK(workspace.mem_assign(dimensions, topology, arena.data()) == static_cast<int>(arena.size()));
+  CHECK(workspace.x_state_offsets[2] == 2 * (n + m) && workspace.z_edge_offsets[1] == 3 * ng + eg);
+  CHECK(workspace.ddyn_dx[1] == workspace.model_callback_output.edges[1].ddyn_dx);
+  LQR::Output out;
+  std::vector<unsigned char> small(LQR::Output::num_bytes(E));
+  CHECK(out.mem_assign(E, small.data()) == LQR::Output::num_bytes(E));
 }
 
 int main() {
@@ -418,7 +540,8 @@ int main() {
       {"LQRSolve branching tree", test_branching_tree},
       {"LQRFactor rejects invalid topology", test_rejects_invalid_topology},
       {"CallbackProvider KKT cases", test_callback_provider},
-      {"InputValidation", test_input_validation},
+      {"InputValidation + structure allocation modes", test_input_validation},
+      {"Workspace memory sizes (static == dynamic == reference values)", test_memory_sizes},
   };
   for (const auto &t : tests) {
     const int before = g_failures;

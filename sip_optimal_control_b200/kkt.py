@@ -1,9 +1,11 @@
 """Host-side mirror of the reference's ``CallbackProvider`` (helpers.hpp:7-33).
 
-Batched and restricted to ``theta_dim == 0``: ``factor`` / ``solve`` /
-``add_Kx_to_y`` keep the reference's argument meaning; flat vectors use the
-reference wire format ``[x | y | z]`` (types.cpp:24-64) and every array gains a
-batch axis.  All computation goes through the C ABI (sipoc_kkt_*).
+Batched: ``factor`` / ``solve`` / ``add_Kx_to_y`` keep the reference's argument
+meaning; flat vectors use the reference wire format ``[x | y | z]`` with
+``x = [x_0, u_0, ..., x_E, theta]`` (types.cpp:24-64) and every array gains a
+batch axis.  With ``theta_dim > 0`` the model dict also carries the ten theta
+block arrays (``_capi.KKT_THETA_FIELDS``).  All computation goes through the C
+ABI (sipoc_kkt_*).
 """
 from __future__ import annotations
 
@@ -17,17 +19,29 @@ from ._capi import lib
 from .lqr import Dimensions, Engine, SipocError, Topology, _host_ptr, _ip
 
 
-def _model_struct(model: dict, host: bool, keep: list) -> _capi.KktModel:
-    s = _capi.KktModel()
-    for k in _capi.KKT_MODEL_FIELDS:
+def _fill(struct, fields, model: dict, host: bool, keep: list) -> None:
+    for k in fields:
         a = model[k]
         if host:
             a = np.ascontiguousarray(a, dtype=np.float64)
+            if not a.size:  # ctypes needs a non-NULL pointer even for empty blocks
+                a = np.zeros(1)
             keep.append(a)
-            # ctypes needs a non-NULL pointer even for empty blocks.
-            setattr(s, k, _host_ptr(a) if a.size else _host_ptr(np.zeros(1)))
+            setattr(struct, k, _host_ptr(a))
         else:
-            setattr(s, k, a.data_ptr())
+            setattr(struct, k, a.data_ptr())
+
+
+def _model_struct(model: dict, host: bool, keep: list) -> _capi.KktModel:
+    """sipoc_kkt_model over device tensors (or host arrays); the theta blocks ride along when
+    the dict has them.  Everything the struct points at is appended to ``keep``."""
+    s = _capi.KktModel()
+    _fill(s, _capi.KKT_MODEL_FIELDS, model, host, keep)
+    if all(k in model for k in _capi.KKT_THETA_FIELDS):
+        t = _capi.KktThetaModel()
+        _fill(t, _capi.KKT_THETA_FIELDS, model, host, keep)
+        keep.append(t)
+        s.theta = ctypes.pointer(t)
     return s
 
 
@@ -91,7 +105,10 @@ class CallbackProvider:
 
     # -- device path ------------------------------------------------------------
     def pack_model(self, host_model: dict) -> dict:
-        return {k: self.engine.pack(host_model[k]) for k in _capi.KKT_MODEL_FIELDS}
+        fields = _capi.KKT_MODEL_FIELDS
+        if self.engine.kkt_sizes["theta_dim"] > 0:
+            fields = fields + _capi.KKT_THETA_FIELDS
+        return {k: self.engine.pack(host_model[k]) for k in fields}
 
     def factor(self, model: dict, w, r1, r2, r3, ok=None, stream=None):
         """Returns a device int32 tensor: 1 where the reference's factor returns true."""
@@ -99,7 +116,8 @@ class CallbackProvider:
         if not self.input_is_valid_:
             return np.zeros(self.batch, np.int32)  # helpers.cpp:244-246
         ok = e.empty_int() if ok is None else ok
-        m = _model_struct(model, False, [])
+        keep = []
+        m = _model_struct(model, False, keep)
         e._check(lib.sipoc_kkt_factor(e._handle, ctypes.byref(m), w.data_ptr(), r1.data_ptr(),
                                       r2.data_ptr(), r3.data_ptr(), ok.data_ptr(),
                                       e.stream_ptr(stream)))
@@ -107,14 +125,16 @@ class CallbackProvider:
 
     def solve(self, model: dict, b, sol, stream=None) -> None:
         e = self.engine
-        m = _model_struct(model, False, [])
+        keep = []
+        m = _model_struct(model, False, keep)
         e._check(lib.sipoc_kkt_solve(e._handle, ctypes.byref(m), b.data_ptr(), sol.data_ptr(),
                                      e.stream_ptr(stream)))
 
     def add_Kx_to_y(self, model: dict, w, r1, r2, r3, x, y, stream=None) -> None:
         """y += K(w, r1, r2, r3) x on [x|y|z] vectors (helpers.cpp:953-977)."""
         e = self.engine
-        m = _model_struct(model, False, [])
+        keep = []
+        m = _model_struct(model, False, keep)
         e._check(lib.sipoc_kkt_apply(e._handle, ctypes.byref(m), w.data_ptr(), r1.data_ptr(),
                                      r2.data_ptr(), r3.data_ptr(), x.data_ptr(), y.data_ptr(),
                                      e.stream_ptr(stream)))
@@ -123,7 +143,8 @@ class CallbackProvider:
     # vectors of the block's own lengths (H: x -> x, C: x -> y, CT: y -> x, G: x -> z, GT: z -> x).
     def _apply_block(self, block: int, model: dict, x, y, stream=None) -> None:
         e = self.engine
-        m = _model_struct(model, False, [])
+        keep = []
+        m = _model_struct(model, False, keep)
         e._check(lib.sipoc_kkt_apply_block(e._handle, ctypes.byref(m), block, x.data_ptr(),
                                            y.data_ptr(), e.stream_ptr(stream)))
 
@@ -152,7 +173,8 @@ class CallbackProvider:
             stats = torch.zeros((4,), dtype=torch.float64, device=e.torch_device())
         else:
             norms, stats = out
-        m = _model_struct(model, False, [])
+        keep = []
+        m = _model_struct(model, False, keep)
         e._check(lib.sipoc_kkt_residual(
             e._handle, ctypes.byref(m), w.data_ptr(), r1.data_ptr(), r2.data_ptr(),
             r3.data_ptr(), sol.data_ptr(), b.data_ptr(),
@@ -210,6 +232,13 @@ class CallbackProvider:
         e._check(lib.sipoc_kkt_factor_host(e._handle, ctypes.byref(m),
                                            *[_host_ptr(a) for a in regs], _host_ptr(ok)))
         return ok
+
+    def set_model_host(self, model: dict) -> None:
+        """Uploads the model alone (sipoc_kkt_set_model_host): what the host operator entry
+        points read, e.g. after the model callback has run again."""
+        e, keep = self.engine, []
+        m = _model_struct(model, True, keep)
+        e._check(lib.sipoc_kkt_set_model_host(e._handle, ctypes.byref(m)))
 
     def solve_host(self, b: np.ndarray) -> np.ndarray:
         e = self.engine

@@ -254,29 +254,36 @@ class Engine:
         return int(s.cuda_stream)
 
     def pack(self, host_array: np.ndarray, stream=None):
-        """Problem-major host array [batch, size] -> engine-layout device tensor."""
+        """Problem-major host array [batch, size] -> engine-layout device tensor.  The copy,
+        the transpose and the wait all happen on ``stream`` (default: torch's current)."""
         torch = self._torch()
         a = np.ascontiguousarray(host_array, dtype=np.float64)
         assert a.shape[0] == self.batch, (a.shape, self.batch)
         size = a.shape[1]
-        dst = self.zeros(size)
-        if size == 0:
-            return dst
-        src = torch.from_numpy(a).to(self.torch_device())
-        self._check(lib.sipoc_pack(self._handle, src.data_ptr(), dst.data_ptr(), size,
-                                   self.stream_ptr(stream)))
-        torch.cuda.current_stream(self.torch_device()).synchronize()
+        st = stream if stream is not None else torch.cuda.current_stream(self.torch_device())
+        with torch.cuda.stream(st):
+            dst = self.zeros(size)
+            if size == 0:
+                return dst
+            src = torch.from_numpy(a).to(self.torch_device())
+            self._check(lib.sipoc_pack(self._handle, src.data_ptr(), dst.data_ptr(), size,
+                                       int(st.cuda_stream)))
+        st.synchronize()  # src may be recycled once this returns
         return dst
 
     def unpack(self, dev_tensor, size: int, stream=None) -> np.ndarray:
         """Engine-layout device tensor -> problem-major host array [batch, size]."""
         torch = self._torch()
-        out = torch.empty((self.batch, max(size, 1)), dtype=torch.float64,
-                          device=self.torch_device())
-        if size > 0:
-            self._check(lib.sipoc_unpack(self._handle, dev_tensor.data_ptr(), out.data_ptr(),
-                                         size, self.stream_ptr(stream)))
-        return out.cpu().numpy()[:, :size]
+        st = stream if stream is not None else torch.cuda.current_stream(self.torch_device())
+        with torch.cuda.stream(st):
+            out = torch.empty((self.batch, max(size, 1)), dtype=torch.float64,
+                              device=self.torch_device())
+            if size > 0:
+                self._check(lib.sipoc_unpack(self._handle, dev_tensor.data_ptr(), out.data_ptr(),
+                                             size, int(st.cuda_stream)))
+            host = out.cpu()  # on `st`: ordered after the transpose
+        st.synchronize()
+        return host.numpy()[:, :size]
 
 
 def _lqr_input_struct(inp: dict) -> _capi.LqrInput:

@@ -119,3 +119,28 @@ def newton_kkt_batch(s: Structure, batch, seed=0, r2_max=1e9):
     r3 = logu((batch, sz["z_dim"]), 1e-3, 1e1)
     rhs = rng.standard_normal((batch, sz["kkt_dim"]))
     return model, w, r1, r2, r3, rhs
+
+
+def newton_kkt_theta_batch(s: Structure, p: int, batch, seed=0, r2_max=1e9):
+    """newton_kkt_batch plus the theta blocks of the reference's theta benchmark problems
+    (newton_kkt_benchmark.cpp:180-225): every coupling block 1e-3 N(0,1), d2L_dtheta2 zero
+    except Z'Z + 100 I on the last node.  Returns (model, theta, w, r1, r2, r3, rhs) with r1
+    and rhs in the full layout [x_s, theta | y | z]."""
+    from oracle.pyoracle import theta_sizes
+
+    model, w, r1, r2, r3, rhs = newton_kkt_batch(s, batch, seed=seed, r2_max=r2_max)
+    rng = np.random.default_rng(seed + 7919)
+    sz = kkt_sizes(s)
+    tz = theta_sizes(s, p)
+    theta = {k: 1e-3 * rng.standard_normal((batch, n)) for k, n in tz.items()}
+    N = len(s.state_dims)
+    Z = rng.standard_normal((batch, p, p))
+    last = np.einsum("bkj,bki->bij", Z, Z) + 100.0 * np.eye(p)
+    htt = np.zeros((batch, N, p * p))
+    htt[:, N - 1] = np.ascontiguousarray(np.swapaxes(last, -1, -2)).reshape(batch, -1)
+    theta["node_htt"] = htt.reshape(batch, -1)
+    theta["edge_htt"] = np.zeros((batch, tz["edge_htt"]))
+    sx = sz["x_dim"]
+    r1_full = np.concatenate([r1, np.full((batch, p), 1e-8)], axis=1)
+    rhs_full = np.concatenate([rhs[:, :sx], rng.standard_normal((batch, p)), rhs[:, sx:]], axis=1)
+    return model, theta, w, r1_full, r2, r3, rhs_full

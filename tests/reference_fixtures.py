@@ -242,6 +242,40 @@ def kkt_model(s: Structure):
     return {k: (np.concatenate(v) if len(v) else np.zeros(0))[None, :] for k, v in m.items()}
 
 
+def kkt_theta_model(s: Structure, p: int, theta_diagonal: float):
+    """The theta blocks of initialize_model (:77-133): flat [1, size] arrays in
+    oracle.pyoracle.THETA_MODEL_NAMES order."""
+    sd, cd = s.state_dims, s.control_dims
+    N, E = len(sd), len(cd)
+    nc = s.node_c if s.node_c is not None else np.zeros(N, np.int32)
+    ng = s.node_g if s.node_g is not None else np.zeros(N, np.int32)
+    ec = s.edge_c if s.edge_c is not None else np.zeros(E, np.int32)
+    eg = s.edge_g if s.edge_g is not None else np.zeros(E, np.int32)
+    t = {k: [] for k in ("node_hxt", "node_jct", "node_jgt", "node_htt", "edge_hxt", "edge_hut",
+                         "edge_dynt", "edge_jct", "edge_jgt", "edge_htt")}
+    htt = (np.eye(p) * theta_diagonal).flatten(order="F")
+    for node in range(N):
+        t["node_jct"].append(fill_sequence(nc[node] * p, 0.001 * (node + 1)))
+        t["node_jgt"].append(fill_sequence(ng[node] * p, -0.0007 * (node + 1)))
+        t["node_hxt"].append(fill_sequence(sd[node] * p, 0.0005 * (node + 1)))
+        t["node_htt"].append(htt)
+    for e in range(E):
+        npar, nch, mm = sd[s.parents[e]], sd[s.children[e]], cd[e]
+        t["edge_dynt"].append(fill_sequence(nch * p, 0.0009 * (e + 1)))
+        t["edge_jct"].append(fill_sequence(ec[e] * p, 0.0008 * (e + 1)))
+        t["edge_jgt"].append(fill_sequence(eg[e] * p, -0.0006 * (e + 1)))
+        t["edge_hxt"].append(fill_sequence(npar * p, 0.0004 * (e + 1)))
+        t["edge_hut"].append(fill_sequence(mm * p, -0.0003 * (e + 1)))
+        t["edge_htt"].append(htt)
+    return {k: (np.concatenate(v) if len(v) else np.zeros(0))[None, :] for k, v in t.items()}
+
+
+def kkt_case_schur():  # :338-363, theta_dim = 2, theta_diagonal = 6.0, tolerance 1e-8
+    s = Structure([0, 0], [1, 2], 0, [2, 1, 3], [1, 2], node_c=[1, 0, 1], node_g=[0, 1, 1],
+                  edge_c=[1, 2], edge_g=[2, 1])
+    return s, 2, 6.0
+
+
 def kkt_regularization(x_dim, y_dim, z_dim):
     """expect_kkt_solve (:143-155): w=1.3, r2=0.9, r3=0.4, r1=0.2+0.03(i+1), rhs=0.01(i+1)."""
     w = np.full((1, z_dim), 1.3)

@@ -17,12 +17,12 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 25
     for name in names:
         assert hasattr(lib, name), name
-    assert _capi.lib.sipoc_version() == 100
+    assert _capi.lib.sipoc_version() == 200
 
 
 def test_header_cites_the_reference_interfaces():
     text = open(_capi.HEADER_PATH).read()
-    for needle in ("lqr.hpp:192-193", "lqr.cpp:735-871", "helpers.cpp:242-370",
+    for needle in ("lqr.hpp:192-193", "lqr.cpp:735-871", "helpers.cpp:190-407",
                    "helpers.cpp:953-977", "types.cpp:24-64"):
         assert needle in text
 
@@ -58,8 +58,8 @@ def test_rejects_invalid_structures_before_touching_cuda():
     dneg = Dimensions(0, [2, 1, 3], [1, 2], [0, 1, 0], [1, 0, 2], [-1, 1], [1, 3])
     assert _create_status(Topology(2, 0, [0, 0], [1, 2]), dneg) == \
         _capi.SIPOC_INVALID_DIMENSIONS
-    # theta (Schur) variables are out of scope and must be refused, not ignored
-    dth = Dimensions(2, [2, 1, 3], [1, 2])
+    # theta (Schur) variables beyond the engine's limit are refused, not ignored
+    dth = Dimensions(33, [2, 1, 3], [1, 2])
     assert _create_status(Topology(2, 0, [0, 0], [1, 2]), dth) == 6  # SIPOC_UNSUPPORTED
 
 
@@ -95,3 +95,41 @@ def test_graph_entry_points_reject_null_handles():
     assert lib.sipoc_graph_launch(None, None, None) == 1
     assert lib.sipoc_graph_kernel_count(None) == 0
     lib.sipoc_graph_destroy(None)
+
+
+def _structure(topology, dims, batch=1):
+    keep = [np.ascontiguousarray(a, dtype=np.int32) for a in
+            (topology.edge_parents, topology.edge_children, dims.state_dims, dims.control_dims)]
+    ip = lambda a: a.ctypes.data_as(_capi.c_int_p)
+    s = _capi.Structure()
+    s.num_edges, s.root = topology.num_edges, topology.root
+    s.edge_parents, s.edge_children, s.state_dims, s.control_dims = (ip(a) for a in keep)
+    s.theta_dim, s.batch, s.device, s.flags = dims.theta_dim, batch, -1, 0
+    return s, keep
+
+
+def test_validate_runs_without_a_device():
+    # sipoc_validate == validate_input (types.cpp:68-134): what the C++ shim calls
+    s, keep = _structure(Topology(2, 0, [0, 0], [1, 2]), Dimensions(2, [2, 1, 3], [1, 2]))
+    assert _capi.lib.sipoc_validate(ctypes.byref(s)) == _capi.SIPOC_OK
+    s, keep = _structure(Topology(2, 0, [0, 1], [2, 2]), Dimensions(0, [2, 1, 3], [1, 2]))
+    assert _capi.lib.sipoc_validate(ctypes.byref(s)) == _capi.SIPOC_INVALID_TOPOLOGY
+    s, keep = _structure(Topology(2, 0, [0, 0], [1, 2]), Dimensions(0, [2, -1, 3], [1, 2]))
+    assert _capi.lib.sipoc_validate(ctypes.byref(s)) == _capi.SIPOC_INVALID_DIMENSIONS
+
+
+def test_shard_range_of_the_c_abi_matches_the_python_one():
+    from sip_optimal_control_b200.sharding import shard_range
+
+    b, e = ctypes.c_int64(), ctypes.c_int64()
+    for total in (0, 1, 7, 64, 65536, 65537):
+        for world in (1, 2, 3, 8):
+            for rank in range(world):
+                assert _capi.lib.sipoc_shard_range(total, rank, world, ctypes.byref(b),
+                                                   ctypes.byref(e)) == 0
+                assert (b.value, e.value) == shard_range(total, rank, world)
+    assert _capi.lib.sipoc_shard_range(8, 2, 2, ctypes.byref(b), ctypes.byref(e)) == 1
+    # communicator entry points check their arguments before touching NCCL / CUDA
+    assert _capi.lib.sipoc_comm_allreduce_stats(None, None, None) == 1
+    assert _capi.lib.sipoc_attach_comm(None, None) == 1
+    assert _capi.lib.sipoc_comm_size(None) == 0
