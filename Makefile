@@ -10,7 +10,8 @@ LIBDIR := sip_optimal_control_b200/lib
 OBJDIR := build/obj
 SRCS := $(CSRC)/api.cu $(CSRC)/generic_kernels.cu $(CSRC)/riccati_fast.cu $(CSRC)/riccati_cta.cu $(CSRC)/riccati_strict.cu $(CSRC)/kkt_fast.cu $(CSRC)/kkt_theta.cu $(CSRC)/comm.cu \
         $(CSRC)/workload.cu $(CSRC)/structure.cpp
-OBJS := $(patsubst $(CSRC)/%,$(OBJDIR)/%.o,$(SRCS))
+OBJS := $(patsubst $(CSRC)/%,$(OBJDIR)/%.o,$(SRCS)) $(OBJDIR)/riccati_fast_part1.cu.o \
+        $(OBJDIR)/riccati_fast_part2.cu.o $(OBJDIR)/riccati_fast_part3.cu.o
 HDRS := $(wildcard $(CSRC)/*.cuh $(CSRC)/*.hpp) include/sipoc.h
 
 HOSTDIR := sip_optimal_control_b200/host
@@ -33,6 +34,12 @@ build/host_tests: $(HOSTDIR)/host_tests.cpp $(LIBDIR)/libsipoc_host.so
 $(OBJDIR)/%.cu.o: $(CSRC)/%.cu $(HDRS)
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVCCFLAGS) $(EXTRA) -c $< -o $@
+
+# riccati_fast.cu instantiates its shapes in four parts (-DSIPOC_FAST_PART) so they build in
+# parallel; part 0 is the plain object above.
+$(OBJDIR)/riccati_fast_part%.cu.o: $(CSRC)/riccati_fast.cu $(HDRS)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVCCFLAGS) $(EXTRA) -DSIPOC_FAST_PART=$* -c $< -o $@
 
 $(OBJDIR)/%.cpp.o: $(CSRC)/%.cpp $(HDRS)
 	@mkdir -p $(OBJDIR)

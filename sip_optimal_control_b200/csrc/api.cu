@@ -242,6 +242,15 @@ bool use_fast(const sipoc_engine *e, const LqrIn &in) {
 }
 
 int64_t lqr_in_size(const HostStructure &h, int i);
+// Elements per problem of input array i as the plan's kernels see it: the uniform padded
+// shape on padded plans, the structure's own sizes otherwise.
+int64_t plan_in_size(const sipoc_engine *e, int i) {
+  if (!e->padded) return lqr_in_size(e->hs, i);
+  const int64_t np = e->fast->n, mp = e->fast->m, N = e->hs.N, E = e->hs.E;
+  const int64_t sizes[9] = {N * np * np, E * np * mp, E * mp * mp, N * np, E * mp,
+                            E * np * np, E * np * mp, N * np,      N * np};
+  return sizes[i];
+}
 
 // Plans whose kernels run one problem per CTA read the inputs from problem-major copies
 // [problem][flat]; this transposes the arrays the call touches (coalesced passes, a few
@@ -257,7 +266,7 @@ sipoc_error refresh_problem_major(sipoc_engine *e, const LqrIn &in, unsigned mas
   const double *src[9] = {in.Q, in.M, in.R, in.q, in.r, in.A, in.B, in.c, in.delta};
   for (int i = 0; i < 9; ++i) {
     if ((mask >> i & 1u) == 0) continue;
-    const int64_t size = lqr_in_size(e->hs, i);
+    const int64_t size = plan_in_size(e, i);
     if (e->pm_in[i] == nullptr) {
       sipoc_error rc = dev_alloc(e, reinterpret_cast<void **>(&e->pm_in[i]),
                                  static_cast<size_t>(std::max<int64_t>(size, 1)) *
@@ -280,11 +289,13 @@ sipoc_error refresh_problem_major(sipoc_engine *e, const LqrIn &in, unsigned mas
 //   layout_pm == true : *il = {} and *pm = in (native), or *il = packed copies and *pm = {}
 sipoc_error resolve_inputs(sipoc_engine *e, const LqrIn &in, bool layout_pm, unsigned mask,
                            LqrIn *il, LqrIn *pm, cudaStream_t s) {
+  *pm = LqrIn{};
   if (!layout_pm) {
     *il = in;
-    return use_fast(e, in) ? refresh_problem_major(e, in, mask, pm, s) : SIPOC_OK;
+    // (padded plans transpose after the padding: pad_inputs)
+    return use_fast(e, in) && !e->padded ? refresh_problem_major(e, in, mask, pm, s) : SIPOC_OK;
   }
-  if (e->fast != nullptr && e->fast->problem_major_inputs && aligned16(in)) {
+  if (e->fast != nullptr && e->fast->problem_major_inputs && !e->padded && aligned16(in)) {
     *il = LqrIn{};
     *pm = in;
     return SIPOC_OK;
@@ -310,7 +321,8 @@ sipoc_error resolve_inputs(sipoc_engine *e, const LqrIn &in, bool layout_pm, uns
 // --- device-path cores (shared by the device and host entry points) --------
 // Padded plans: `in` (interleaved, the structure's own variable-dim layout) -> the engine's
 // uniform padded arrays; the plan then runs on those and writes padded outputs.
-sipoc_error pad_inputs(sipoc_engine *e, LqrIn *in, unsigned mask, cudaStream_t s) {
+sipoc_error pad_inputs(sipoc_engine *e, LqrIn *in, unsigned mask, cudaStream_t s,
+                       LqrIn *pm = nullptr) {
   const int np = e->fast->n, mp = e->fast->m, N = e->hs.N, E = e->hs.E;
   const int64_t sizes[9] = {int64_t(N) * np * np, int64_t(E) * np * mp, int64_t(E) * mp * mp,
                             int64_t(N) * np,      int64_t(E) * mp,      int64_t(E) * np * np,
@@ -328,6 +340,9 @@ sipoc_error pad_inputs(sipoc_engine *e, LqrIn *in, unsigned mask, cudaStream_t s
   }
   e->launches += 1;
   *in = dst;
+  // CTA-per-problem plans read problem-major copies: transposed from the padded arrays
+  if (pm != nullptr && e->fast->problem_major_inputs)
+    return refresh_problem_major(e, dst, mask, pm, s);
   return SIPOC_OK;
 }
 
@@ -350,7 +365,8 @@ void unpad_outputs(sipoc_engine *e, const LqrOut &padded, const LqrOut &out, cud
 }
 
 bool native_pm(const sipoc_engine *e, const LqrIn &in, bool layout_pm) {
-  return layout_pm && e->fast != nullptr && e->fast->problem_major_inputs && aligned16(in);
+  return layout_pm && e->fast != nullptr && e->fast->problem_major_inputs && !e->padded &&
+         aligned16(in);
 }
 
 sipoc_error lqr_factor_core(sipoc_engine *e, const LqrIn &caller_in, int *status, cudaStream_t s,
@@ -362,7 +378,7 @@ sipoc_error lqr_factor_core(sipoc_engine *e, const LqrIn &caller_in, int *status
     return rc;
   if (native_pm(e, caller_in, layout_pm) || use_fast(e, in)) {
     if ((rc = ensure_fast_store(e)) != SIPOC_OK) return rc;
-    if (e->padded && (rc = pad_inputs(e, &in, kPmMatrices, s)) != SIPOC_OK) return rc;
+    if (e->padded && (rc = pad_inputs(e, &in, kPmMatrices, s, &pm)) != SIPOC_OK) return rc;
     FastArgs a{in, pm, LqrOut{}, status, e->fast_store, nullptr, e->batch, e->ld, e->hs.E,
                &e->prof};
     a.tables = &e->dt;
@@ -399,7 +415,7 @@ sipoc_error lqr_solve_core(sipoc_engine *e, const LqrIn &caller_in, const LqrOut
     if ((rc = ensure_fast_scratch(e)) != SIPOC_OK) return rc;
     LqrOut plan_out = out;
     if (e->padded) {
-      if ((rc = pad_inputs(e, &in, mask, s)) != SIPOC_OK) return rc;
+      if ((rc = pad_inputs(e, &in, mask, s, &pm)) != SIPOC_OK) return rc;
       if ((rc = padded_outputs(e, &plan_out)) != SIPOC_OK) return rc;
     }
     FastArgs a{in, pm, plan_out, nullptr, e->fast_store, e->fast_scratch, e->batch, e->ld,
@@ -428,7 +444,7 @@ sipoc_error lqr_factor_solve_core(sipoc_engine *e, const LqrIn &caller_in, const
     if ((rc = ensure_fast_scratch(e)) != SIPOC_OK) return rc;
     LqrOut plan_out = out;
     if (e->padded) {
-      if ((rc = pad_inputs(e, &in, kPmAll, s)) != SIPOC_OK) return rc;
+      if ((rc = pad_inputs(e, &in, kPmAll, s, &pm)) != SIPOC_OK) return rc;
       if ((rc = padded_outputs(e, &plan_out)) != SIPOC_OK) return rc;
     }
     FastArgs a{in, pm, plan_out, status, e->fast_store, e->fast_scratch, e->batch, e->ld, e->hs.E,
@@ -867,6 +883,21 @@ sipoc_error sipoc_create(const sipoc_structure *s, sipoc_engine **out) {
         break;
       }
     }
+  }
+  if (e->fast == nullptr && !(e->flags & SIPOC_FLAG_FORCE_GENERIC) && h.is_chain &&
+      h.is_uniform && h.E >= 1) {
+    // A uniform shape that is not instantiated (e.g. n = 16 with m < 4 of the reference
+    // grid, lqr_benchmark.cpp:537-545): padded up to the next shape that is, sub-warp shapes
+    // first, then the CTA-per-problem ones.
+    const int shapes[][2] = {{6, 1}, {6, 2}, {6, 3}, {6, 4}, {8, 1}, {8, 2}, {8, 3}, {8, 4}, {12, 4}};
+    for (const auto &sh : shapes)
+      if (sh[0] >= h.max_n && sh[1] >= h.max_m && (e->fast = select_fast_plan(sh[0], sh[1])))
+        break;
+    const int cta_shapes[][2] = {{16, 4}, {32, 8}, {64, 24}};
+    for (const auto &sh : cta_shapes)
+      if (e->fast == nullptr && sh[0] >= h.max_n && sh[1] >= h.max_m)
+        e->fast = select_cta_plan(sh[0], sh[1]);
+    e->padded = e->fast != nullptr;
   }
   if (!(e->flags & SIPOC_FLAG_FORCE_GENERIC) && h.is_chain && h.is_uniform && h.E >= 1) {
     e->kkt_reduce_fast = select_kkt_reduce(h.n[0], h.m[0]);

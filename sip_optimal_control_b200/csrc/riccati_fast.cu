@@ -2307,12 +2307,51 @@ const FastPlan *make_plan(const char *name) {
 
 }  // namespace
 
+// The shapes are compiled in four parts (the same file with -DSIPOC_FAST_PART=0..3, see the
+// Makefile) so that the translation units build in parallel.  Together they cover the
+// reference benchmark grid for n <= 8 (lqr_benchmark.cpp:537-545: n in {4, 6, 8} x
+// m in {1, 2, 3, 4}) plus the quadrotor shape; n = 16 runs on the CTA-per-problem plans
+// (riccati_cta.cu), every other uniform shape is padded up to the next shape of either set.
+#ifndef SIPOC_FAST_PART
+#define SIPOC_FAST_PART 0
+#endif
+#define SIPOC_CAT2(a, b) a##b
+#define SIPOC_CAT(a, b) SIPOC_CAT2(a, b)
+const FastPlan *select_fast_plan_part1(int n, int m);
+const FastPlan *select_fast_plan_part2(int n, int m);
+const FastPlan *select_fast_plan_part3(int n, int m);
+
+#if SIPOC_FAST_PART == 0
 const FastPlan *select_fast_plan(int n, int m) {
-  if (n == 4 && m == 1) return make_plan<4, 1, false>("thread_per_problem_n4_m1");
   if (n == 12 && m == 4) return make_plan<12, 4, true>("subwarp4_n12_m4");
+  if (n == 4 && m == 1) return make_plan<4, 1, false>("thread_per_problem_n4_m1");
+  if (n == 4 && m == 2) return make_plan<4, 2, false>("thread_per_problem_n4_m2");
+  if (n == 4 && m == 3) return make_plan<4, 3, false>("thread_per_problem_n4_m3");
+  if (n == 4 && m == 4) return make_plan<4, 4, false>("thread_per_problem_n4_m4");
+  if (const FastPlan *p = select_fast_plan_part1(n, m)) return p;
+  if (const FastPlan *p = select_fast_plan_part2(n, m)) return p;
+  return select_fast_plan_part3(n, m);
+}
+#elif SIPOC_FAST_PART == 1
+const FastPlan *select_fast_plan_part1(int n, int m) {
+  if (n == 6 && m == 1) return make_plan<6, 1, true>("subwarp4_n6_m1");
   if (n == 6 && m == 2) return make_plan<6, 2, true>("subwarp4_n6_m2");
-  if (n == 8 && m == 3) return make_plan<8, 3, true>("subwarp4_n8_m3");
+  if (n == 6 && m == 3) return make_plan<6, 3, true>("subwarp4_n6_m3");
   return nullptr;
 }
+#elif SIPOC_FAST_PART == 2
+const FastPlan *select_fast_plan_part2(int n, int m) {
+  if (n == 6 && m == 4) return make_plan<6, 4, true>("subwarp4_n6_m4");
+  if (n == 8 && m == 1) return make_plan<8, 1, true>("subwarp4_n8_m1");
+  if (n == 8 && m == 2) return make_plan<8, 2, true>("subwarp4_n8_m2");
+  return nullptr;
+}
+#else
+const FastPlan *select_fast_plan_part3(int n, int m) {
+  if (n == 8 && m == 3) return make_plan<8, 3, true>("subwarp4_n8_m3");
+  if (n == 8 && m == 4) return make_plan<8, 4, true>("subwarp4_n8_m4");
+  return nullptr;
+}
+#endif
 
 }  // namespace sipoc

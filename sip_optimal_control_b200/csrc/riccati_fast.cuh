@@ -1,9 +1,13 @@
 // Shape-specialised Riccati kernels for uniform chains (interface).
 //
 // A FastPlan is a set of kernels compiled for one (state_dim, control_dim)
-// pair; riccati_fast.cu instantiates the template for the BASELINE shapes and
-// the reference benchmark grid.  The engine falls back to the generic
-// thread-per-problem kernels for every other structure.
+// pair.  riccati_fast.cu instantiates n in {4, 6, 8} x m in {1, 2, 3, 4} (the
+// reference benchmark grid below n = 16, lqr_benchmark.cpp:537-545) and the
+// quadrotor shape (12, 4); riccati_cta.cu (16, 4), (32, 8) and (64, 24); every
+// other uniform chain is padded up to the next of these with decoupled states /
+// controls (api.cu, sipoc_create), small chains / trees with varying dims run the
+// reference-order plans of riccati_strict.cu, and the generic thread-per-problem
+// kernels take whatever is left.
 #pragma once
 
 #include <cuda_runtime.h>

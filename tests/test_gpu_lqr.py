@@ -217,6 +217,35 @@ def test_baseline_horizons_match_oracle(n, m, T, batch, fused):
     assert_lqr_parity(gpu, ref, REL_TOL)
 
 
+@pytest.mark.parametrize("n", [4, 6, 8, 16])
+@pytest.mark.parametrize("m", [1, 2, 3, 4])
+def test_reference_benchmark_grid_runs_on_shape_specialised_kernels(n, m):
+    # lqr_benchmark.cpp:537-545: T in {16, 32, 64, 128} x n in {4, 6, 8, 16} x m in {1, 2, 3, 4}.
+    # Every uniform shape of the grid has a compiled plan (n = 16 with m < 4 through decoupled
+    # padding to the (16, 4) CTA plan); fused factor + solve and factor-then-solve both checked.
+    T, batch = 16, 29
+    s, host = pg.lqr_benchmark_batch(n, m, T, batch, seed=11 * n + m, dense_M=True)
+    ref = pyoracle.lqr_factor_solve(s, host)
+    assert (ref["status"] == 0).all()
+    for fused in (True, False):
+        gpu, lqr = gpu_lqr_factor_solve(s, host, fused=fused)
+        assert "generic" not in lqr.engine.kernel_variant, lqr.engine.kernel_variant
+        assert (gpu["status"] == 0).all()
+        assert_lqr_parity(gpu, ref, REL_TOL)
+
+
+@pytest.mark.parametrize("n,m,T", [(10, 3, 9), (7, 4, 12), (24, 6, 5), (40, 20, 3)])
+def test_other_uniform_shapes_are_padded_to_the_next_plan(n, m, T):
+    batch = 13
+    s, host = pg.lqr_benchmark_batch(n, m, T, batch, seed=n + m)
+    host["delta"][3, n] = -1.0  # status codes survive the padding
+    ref = pyoracle.lqr_factor_solve(s, host)
+    gpu, lqr = gpu_lqr_factor_solve(s, host)
+    assert lqr.engine.kernel_variant.startswith("padded_to_"), lqr.engine.kernel_variant
+    assert (gpu["status"] == ref["status"]).all() and gpu["status"][3] == 1
+    assert_lqr_parity(gpu, ref, REL_TOL, mask=ref["status"] == 0)
+
+
 @pytest.mark.parametrize("n,m,T", [(4, 1, 20), (12, 4, 10), (5, 2, 7), (16, 4, 6), (64, 24, 3)])
 def test_factor_once_solve_many(n, m, T):
     # BM_LQRSolve semantics (lqr_benchmark.cpp:611-638): re-solve with new

@@ -11,6 +11,6 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 ARCH="-gencode arch=compute_100a,code=sm_100a"
 $NVCC -std=c++17 -O3 -lineinfo $ARCH -ccbin /usr/bin/g++ -Xcompiler -fPIC -cudart static --expt-relaxed-constexpr \
   "$@" -c sip_optimal_control_b200/csrc/riccati_fast.cu -o build/variants/riccati_fast_$TAG.o
-OBJS=$(ls build/obj/*.o | grep -v riccati_fast.cu.o)
+OBJS=$(ls build/obj/*.o | grep -v "/riccati_fast.cu.o")
 $NVCC $ARCH -ccbin /usr/bin/g++ -shared -cudart static -o build/variants/libsipoc_$TAG.so $OBJS build/variants/riccati_fast_$TAG.o -ldl
 echo build/variants/libsipoc_$TAG.so
