@@ -129,6 +129,17 @@ typedef struct sipoc_structure {
  * still, but a correct FP64 solve in another order, which drifts from the reference on
  * ill-conditioned regularization (r2 up to 1e9). */
 #define SIPOC_FLAG_PAD_VARIABLE_DIMS 2
+/* Parallel-in-time factor + solve (sipoc_lqr_factor_solve on uniform chains with a
+ * sub-warp plan): the horizon is cut into segments whose conditional value functions are
+ * combined by an associative scan, then every (problem, segment) tile is swept and rolled out
+ * at once -- depth 2 (L + S) stage times instead of 2 N.  Chosen automatically for long
+ * horizons with small batches (N >= 512 edges, batch <= 512); _PARALLEL_IN_TIME forces it,
+ * _SERIAL_IN_TIME forbids it.  It needs R > 0 (a non-positive pivot of R reports
+ * G_FACTORIZATION_FAILURE) and agrees with the serial recursion to rounding times the
+ * conditioning of the segments, not bit for bit; the factorization it keeps is per segment,
+ * so a later sipoc_lqr_solve needs its own sipoc_lqr_factor. */
+#define SIPOC_FLAG_PARALLEL_IN_TIME 4
+#define SIPOC_FLAG_SERIAL_IN_TIME 8
 
 /* validate_input (types.cpp:68-134) on its own: SIPOC_OK, SIPOC_INVALID_DIMENSIONS or
  * SIPOC_INVALID_TOPOLOGY, dimension checks first.  Needs no device (batch is ignored). */

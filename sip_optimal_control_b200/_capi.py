@@ -31,6 +31,8 @@ SIPOC_INVALID_DIMENSIONS = 5
 SIPOC_COMM_ID_BYTES = 128
 SIPOC_FLAG_FORCE_GENERIC = 1
 SIPOC_FLAG_PAD_VARIABLE_DIMS = 2
+SIPOC_FLAG_PARALLEL_IN_TIME = 4
+SIPOC_FLAG_SERIAL_IN_TIME = 8
 # sipoc_kkt_block
 KKT_BLOCK_H, KKT_BLOCK_C, KKT_BLOCK_CT, KKT_BLOCK_G, KKT_BLOCK_GT = range(5)
 

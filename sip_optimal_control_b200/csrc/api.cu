@@ -14,6 +14,7 @@
 #include "generic_kernels.cuh"
 #include "kkt_fast.cuh"
 #include "kkt_theta.cuh"
+#include "scan.cuh"
 #include "profile.hpp"
 #include "riccati_fast.cuh"
 #include "structure.hpp"
@@ -81,6 +82,15 @@ struct sipoc_engine {
   bool host_kkt_ready = false;
   bool host_model_resident = false;  // hk_model / hk_theta hold a caller's model
   sipoc_comm *comm = nullptr;        // attached communicator: stats outputs are all-reduced
+
+  // Parallel-in-time factor + solve (scan.cu): long uniform chains, small batches.
+  struct Scan {
+    bool enabled = false;
+    int L = 0, S = 0;  // edges per segment, segments
+    double *elems = nullptr, *maps = nullptr, *Vb = nullptr, *vb = nullptr, *xb = nullptr;
+    double *store = nullptr, *scratch = nullptr;
+    int *seg_status = nullptr, *sweep_status = nullptr;
+  } scan;
 };
 
 namespace {
@@ -433,11 +443,59 @@ sipoc_error lqr_solve_core(sipoc_engine *e, const LqrIn &caller_in, const LqrOut
   return check_launch(e, "lqr_solve");
 }
 
+sipoc_error ensure_scan_ws(sipoc_engine *e) {
+  sipoc_engine::Scan &sc = e->scan;
+  if (sc.elems != nullptr) return SIPOC_OK;
+  const int n = e->fast->n;
+  const int64_t S = sc.S;
+  sipoc_error rc;
+  auto plain = [&](double **p, int64_t doubles) {
+    return dev_alloc(e, reinterpret_cast<void **>(p), static_cast<size_t>(doubles) * sizeof(double));
+  };
+  if ((rc = plain(&sc.elems, e->batch * S * scan_elem_doubles(n))) != SIPOC_OK) return rc;
+  if ((rc = plain(&sc.maps, e->batch * S * scan_map_doubles(n))) != SIPOC_OK) return rc;
+  if ((rc = alloc_doubles(e, &sc.Vb, (S + 1) * n * n)) != SIPOC_OK) return rc;
+  if ((rc = alloc_doubles(e, &sc.vb, (S + 1) * n)) != SIPOC_OK) return rc;
+  if ((rc = alloc_doubles(e, &sc.xb, (S + 1) * n)) != SIPOC_OK) return rc;
+  if ((rc = alloc_doubles(e, &sc.store, S * e->fast->store_elems(sc.L))) != SIPOC_OK) return rc;
+  if ((rc = alloc_doubles(e, &sc.scratch, S * e->fast->scratch_elems(sc.L))) != SIPOC_OK) return rc;
+  const size_t ints = static_cast<size_t>(S) * e->ld * sizeof(int);
+  if ((rc = dev_alloc(e, reinterpret_cast<void **>(&sc.seg_status), ints)) != SIPOC_OK) return rc;
+  return dev_alloc(e, reinterpret_cast<void **>(&sc.sweep_status), ints);
+}
+
+// Parallel in time: segment elements and boundary data (scan.cu), then the fused sweep +
+// rollout of every (problem, segment) tile at once.
+sipoc_error lqr_factor_solve_scan(sipoc_engine *e, const LqrIn &in, const LqrOut &out,
+                                  int *status, cudaStream_t s) {
+  sipoc_error rc;
+  if ((rc = ensure_scan_ws(e)) != SIPOC_OK) return rc;
+  sipoc_engine::Scan &sc = e->scan;
+  const ScanArgs sa{in,       e->fast->n, e->fast->m, sc.L,  sc.S,  e->batch,      e->ld,
+                    sc.elems, sc.maps,    sc.Vb,      sc.vb, sc.xb, sc.seg_status, &e->prof};
+  const int front = launch_scan_front(sa, s);
+  if (front < 0) return fail(e, SIPOC_UNSUPPORTED, "no scan kernels for this shape");
+  e->launches += front;
+  if ((rc = check_launch(e, "scan front")) != SIPOC_OK) return rc;
+  FastArgs a{in, LqrIn{}, out, sc.sweep_status, sc.store, sc.scratch, e->batch, e->ld, sc.L,
+             &e->prof};
+  e->launches += e->fast->factor_solve_segments(a, sc.Vb, sc.vb, sc.xb, sc.S, s);
+  if (status != nullptr) {
+    launch_scan_status(sc.sweep_status, sc.seg_status, sc.S, e->batch, e->ld, status, s);
+    e->launches += 1;
+  }
+  // The factorization is kept per segment, not in the layout sipoc_lqr_solve reads.
+  e->factored = sipoc_engine::Factored::NONE;
+  return check_launch(e, "lqr_factor_solve (parallel in time)");
+}
+
 sipoc_error lqr_factor_solve_core(sipoc_engine *e, const LqrIn &caller_in, const LqrOut &out,
                                   int *status, cudaStream_t s, bool layout_pm = false) {
   sipoc_error rc;
   e->kkt_factored = false;
   LqrIn in, pm;
+  if (e->scan.enabled && !layout_pm && use_fast(e, caller_in))
+    return lqr_factor_solve_scan(e, caller_in, out, status, s);
   if ((rc = resolve_inputs(e, caller_in, layout_pm, kPmAll, &in, &pm, s)) != SIPOC_OK) return rc;
   if (native_pm(e, caller_in, layout_pm) || use_fast(e, in)) {
     if ((rc = ensure_fast_store(e)) != SIPOC_OK) return rc;
@@ -910,7 +968,26 @@ sipoc_error sipoc_create(const sipoc_structure *s, sipoc_engine **out) {
     if (kkt_reduce_smem_bytes(h.n[0], h.m[0], std::max(1, e->kkt_max_rows)) > 200 * 1024)
       e->kkt_reduce_fast = nullptr;
   }
+  if (e->fast != nullptr && !e->padded && e->fast->factor_solve_segments != nullptr &&
+      !(e->flags & SIPOC_FLAG_SERIAL_IN_TIME) && scan_supports(e->fast->n, e->fast->m)) {
+    // Parallel in time pays when the serial sweep cannot fill the GPU: a long horizon and a
+    // batch far below one wave of tiles.  The segment length is the divisor of the horizon
+    // nearest 64 (depth 2 L + 2 S stage times); SIPOC_SCAN_SEGMENT overrides it.
+    const bool wanted = (e->flags & SIPOC_FLAG_PARALLEL_IN_TIME) != 0 ||
+                        (h.E >= 512 && e->batch <= 512);
+    int target = 64;
+    if (const char *env = getenv("SIPOC_SCAN_SEGMENT")) target = std::max(1, atoi(env));
+    int best = 0;
+    for (int L = 2; L <= h.E / 2; ++L)
+      if (h.E % L == 0 && (best == 0 || std::abs(L - target) < std::abs(best - target))) best = L;
+    if (wanted && best >= 2) {
+      e->scan.enabled = true;
+      e->scan.L = best;
+      e->scan.S = h.E / best;
+    }
+  }
   e->variant = e->fast != nullptr ? e->fast->name : "generic_thread_per_problem";
+  if (e->scan.enabled) e->variant = "scan_" + e->variant;
   if (e->padded) e->variant = "padded_to_" + e->variant;
   *out = e;
   return SIPOC_OK;

@@ -223,13 +223,44 @@ __device__ __forceinline__ void stage_lower(double *dst, const double *src, int6
 // rollout of one tile hides under the DFMA-bound sweeps of the other tiles of the SM:
 // the step costs the backward sweep plus a few per cent instead of sweep + rollout, and
 // a shard of a few thousand problems no longer pays a latency-bound rollout kernel.
-template <int N, int M, bool SOLVE, int WARPS, bool FUSED = false, bool PACKW = FUSED>
+//
+// SEGMENTED (parallel in time, scan.cu): blockIdx.y is a segment of T edges of a longer
+// horizon.  The tile sweeps its segment from the boundary value function (V, v at the
+// segment's last node, from the scan) instead of (Q, q) of that node, and rolls forward from
+// the boundary state instead of the root solve; every array is addressed at the segment's
+// offset, the kept factorization and the status are per (segment, problem).
+struct SegmentArgs {
+  const double *Vb, *vb, *xb;  // [S + 1][N N | N | N][ld], engine layout
+};
+
+template <int N, int M, bool SOLVE, int WARPS, bool FUSED = false, bool PACKW = FUSED,
+          bool SEGMENTED = false>
 __global__ void __launch_bounds__(32 * WARPS)
 riccati_backward_subwarp(LqrIn in, LqrOut out, int *status_out, double *store, double *scratch,
-                         int64_t batch, int64_t ld, int T) {
+                         int64_t batch, int64_t ld, int T, SegmentArgs sg) {
   static_assert(SOLVE || !FUSED, "the fused rollout needs the affine sweep");
+  static_assert(FUSED || !SEGMENTED, "segments run the fused sweep + rollout");
   using S = Smem<N, M, PACKW>;
   using Z = FastSizes<N, M>;
+  const int seg = SEGMENTED ? blockIdx.y : 0;
+  if constexpr (SEGMENTED) {
+    const int64_t node0 = static_cast<int64_t>(seg) * T;  // first node / edge of the segment
+    in.Q += node0 * N * N * ld;
+    in.q += node0 * N * ld;
+    in.c += node0 * N * ld;
+    in.delta += node0 * N * ld;
+    in.A += node0 * N * N * ld;
+    in.B += node0 * N * M * ld;
+    in.M += node0 * N * M * ld;
+    in.R += node0 * M * M * ld;
+    in.r += node0 * M * ld;
+    out.x += node0 * N * ld;
+    out.y += node0 * N * ld;
+    out.u += node0 * M * ld;
+    store += static_cast<int64_t>(seg) * Z::store(T) * ld;
+    scratch += static_cast<int64_t>(seg) * Z::scratch(T) * ld;
+    status_out += static_cast<int64_t>(seg) * ld;
+  }
   constexpr int SX = cdiv(N, kGroup);  // own state columns per lane
   constexpr int SU = cdiv(M, kGroup);  // own control columns per lane
   extern __shared__ __align__(16) double sm_all[];
@@ -345,9 +376,18 @@ riccati_backward_subwarp(LqrIn in, LqrOut out, int *status_out, double *store, d
     }
   };
 
+  if constexpr (SEGMENTED) {
+    // terminal node of the segment: the boundary value function stands in for (Q, q)
+    pQ = sg.Vb + static_cast<int64_t>(seg + 1) * N * N * ld + lane_goff;
+    pq = sg.vb + static_cast<int64_t>(seg + 1) * N * ld + lane_goff;
+  }
   issue_z_vec(false);
   issue_qmr(false);
   cp_async_commit();
+  if constexpr (SEGMENTED) {
+    pQ = in.Q + static_cast<int64_t>(T - 1) * N * N * ld + lane_goff;
+    pq = in.q + static_cast<int64_t>(T - 1) * N * ld + lane_goff;
+  }
 
   for (int k = T; k >= 0; --k) {
     cp_async_wait_all();
@@ -991,20 +1031,29 @@ riccati_backward_subwarp(LqrIn in, LqrOut out, int *status_out, double *store, d
     cp_async_commit();
     cp_async_wait_group<1>();
     __syncwarp();
-    // root: f = delta v - c, x = -(I + D V)^-1 f, y = v - W f     (lqr.cpp:798-819)
+    if (SEGMENTED && seg > 0) {
+      // the segment starts from the boundary state; its first node's x, y are the previous
+      // segment's last and are written there
 #pragma unroll
-    for (int s = 0; s < SX; ++s)
-      fo[s] = SM(fd + xj[s]) * SM(fv + xj[s]) - SM(fc + xj[s]);
-    node_solve();
+      for (int s = 0; s < SX; ++s)
+        if (xok[s])
+          SM(fx + xj[s]) = __ldg(sg.xb + (static_cast<int64_t>(seg) * N + xj[s]) * ld + b);
+    } else {
+      // root: f = delta v - c, x = -(I + D V)^-1 f, y = v - W f     (lqr.cpp:798-819)
 #pragma unroll
-    for (int s = 0; s < SX; ++s) {
-      const double xi = -SM(fd + xj[s]) * sdi_o[s] * to[s];
-      const double yi = SM(fv + xj[s]) - sdi_o[s] * (fo[s] - to[s]);
-      if (xok[s]) {
-        SM(fx + xj[s]) = xi;
-        if (valid) {
-          stcs(xo + static_cast<int64_t>(xj[s]) * ld, xi);
-          stcs(yo + static_cast<int64_t>(xj[s]) * ld, yi);
+      for (int s = 0; s < SX; ++s)
+        fo[s] = SM(fd + xj[s]) * SM(fv + xj[s]) - SM(fc + xj[s]);
+      node_solve();
+#pragma unroll
+      for (int s = 0; s < SX; ++s) {
+        const double xi = -SM(fd + xj[s]) * sdi_o[s] * to[s];
+        const double yi = SM(fv + xj[s]) - sdi_o[s] * (fo[s] - to[s]);
+        if (xok[s]) {
+          SM(fx + xj[s]) = xi;
+          if (valid) {
+            stcs(xo + static_cast<int64_t>(xj[s]) * ld, xi);
+            stcs(yo + static_cast<int64_t>(xj[s]) * ld, yi);
+          }
         }
       }
     }
@@ -2198,7 +2247,7 @@ struct Plan {
     const unsigned grid = static_cast<unsigned>((a.batch + kTile * W - 1) / (kTile * W));
     ProfScope ps(a.prof, FUSED ? "riccati_fused_subwarp" : "riccati_backward_subwarp", s);
     kern<<<grid, 32 * W, bytes, s>>>(a.in, a.out, a.status, a.store, a.scratch, a.batch, a.ld,
-                                     a.num_edges);
+                                     a.num_edges, SegmentArgs{});
   }
 
   template <bool SOLVE>
@@ -2279,6 +2328,25 @@ struct Plan {
       return 2;
     }
   }
+  // Parallel in time: S segments of a.num_edges edges each, from the scan's boundary data.
+  // a.status is [S][ld]; a.store / a.scratch hold S segment-sized regions.
+  static int factor_solve_segments(const FastArgs &a, const double *Vb, const double *vb,
+                                   const double *xb, int S, cudaStream_t s) {
+    if constexpr (SUBWARP) {
+      auto kern = riccati_backward_subwarp<N, M, true, 1, true, true, true>;
+      using Sm = Smem<N, M, true>;
+      constexpr int bytes = Sm::kBytes;
+      if (bytes > 48 * 1024)
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+      const dim3 grid(static_cast<unsigned>((a.batch + kTile - 1) / kTile), static_cast<unsigned>(S));
+      ProfScope ps(a.prof, "riccati_fused_subwarp_segments", s);
+      kern<<<grid, 32, bytes, s>>>(a.in, a.out, a.status, a.store, a.scratch, a.batch, a.ld,
+                                   a.num_edges, SegmentArgs{Vb, vb, xb});
+      return 1;
+    } else {
+      return -1;
+    }
+  }
   static int kkt_solve(const FastKktArgs &k, cudaStream_t s) {
     const unsigned grid = static_cast<unsigned>((k.batch + 127) / 128);
     const KktView view{*k.tables, *k.model, *k.ws, k.b, k.sol};
@@ -2301,7 +2369,8 @@ const FastPlan *make_plan(const char *name) {
   using P = Plan<N, M, SUBWARP>;
   static const FastPlan plan{name,         N,           M,         &P::store_elems,
                              &P::scratch_elems, &P::factor, &P::solve, &P::factor_solve,
-                             &P::kkt_solve, false};
+                             &P::kkt_solve, false,
+                             SUBWARP ? &P::factor_solve_segments : nullptr};
   return &plan;
 }
 

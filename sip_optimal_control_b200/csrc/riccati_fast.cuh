@@ -64,6 +64,10 @@ struct FastPlan {
   // from a problem-major copy instead of 8 bytes per 32-byte sector of the
   // batch-interleaved layout.
   bool problem_major_inputs;
+  // Parallel in time (scan.cu): the fused sweep + rollout of S segments of a.num_edges edges,
+  // each from the boundary value function / state the scan computed; nullptr = not provided.
+  int (*factor_solve_segments)(const FastArgs &, const double *Vb, const double *vb,
+                               const double *xb, int S, cudaStream_t) = nullptr;
 };
 
 // nullptr when no specialised kernel exists for (n, m).

@@ -155,7 +155,7 @@ class Engine:
 
     def __init__(self, dimensions: Dimensions, topology: Topology, batch: int,
                  device: Optional[int] = None, force_generic: bool = False,
-                 pad_variable_dims: bool = False):
+                 pad_variable_dims: bool = False, parallel_in_time: Optional[bool] = None):
         self.dimensions = dimensions
         self.topology = topology
         self.batch = int(batch)
@@ -171,7 +171,10 @@ class Engine:
             _ip(dimensions.edge_g_dims), dimensions.theta_dim, self.batch,
             -1 if device is None else int(device),
             (_capi.SIPOC_FLAG_FORCE_GENERIC if force_generic else 0)
-            | (_capi.SIPOC_FLAG_PAD_VARIABLE_DIMS if pad_variable_dims else 0))
+            | (_capi.SIPOC_FLAG_PAD_VARIABLE_DIMS if pad_variable_dims else 0)
+            # None: the engine decides (long horizon, small batch); True / False: forced
+            | (_capi.SIPOC_FLAG_PARALLEL_IN_TIME if parallel_in_time is True else 0)
+            | (_capi.SIPOC_FLAG_SERIAL_IN_TIME if parallel_in_time is False else 0))
         self.create_status = int(lib.sipoc_create(ctypes.byref(s), ctypes.byref(self._handle)))
         if self.create_status != _capi.SIPOC_OK:
             self._handle = ctypes.c_void_p()
@@ -317,9 +320,9 @@ class LQR:
 
     def __init__(self, dimensions: Dimensions, topology: Topology, batch: int = 1,
                  device: Optional[int] = None, force_generic: bool = False,
-                 pad_variable_dims: bool = False):
+                 pad_variable_dims: bool = False, parallel_in_time: Optional[bool] = None):
         self.engine = Engine(dimensions, topology, batch, device, force_generic,
-                             pad_variable_dims)
+                             pad_variable_dims, parallel_in_time)
         self.batch = int(batch)
         self.traversal_status_ = self.compile_topology()
 

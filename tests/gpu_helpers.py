@@ -36,12 +36,12 @@ def assert_lqr_parity(gpu: dict, ref: dict, tol: float = REL_TOL, mask=None):
 
 
 def gpu_lqr_factor_solve(s: pyoracle.Structure, host: dict, force_generic=False, fused=True,
-                         pad_variable_dims=False):
+                         pad_variable_dims=False, parallel_in_time=None):
     """Device path: pack -> (fused | factor + solve) -> unpack.  Returns dict + LQR."""
     dims, topo = to_structs(s)
     batch = host["q"].shape[0]
     lqr = LQR(dims, topo, batch, force_generic=force_generic,
-              pad_variable_dims=pad_variable_dims)
+              pad_variable_dims=pad_variable_dims, parallel_in_time=parallel_in_time)
     inp = lqr.pack_input(host)
     out = lqr.alloc_output()
     if fused:
