@@ -86,8 +86,8 @@ struct sipoc_engine {
   // Parallel-in-time factor + solve (scan.cu): long uniform chains, small batches.
   struct Scan {
     bool enabled = false;
-    int L = 0, S = 0;  // edges per segment, segments
-    double *elems = nullptr, *maps = nullptr, *Vb = nullptr, *vb = nullptr, *xb = nullptr;
+    int L = 0, S = 0, Sg = 0;  // edges per segment, segments, segments per group
+    double *elems = nullptr, *gelems = nullptr, *maps = nullptr, *Vb = nullptr, *vb = nullptr, *xb = nullptr;
     double *store = nullptr, *scratch = nullptr;
     int *seg_status = nullptr, *sweep_status = nullptr;
   } scan;
@@ -453,7 +453,9 @@ sipoc_error ensure_scan_ws(sipoc_engine *e) {
     return dev_alloc(e, reinterpret_cast<void **>(p), static_cast<size_t>(doubles) * sizeof(double));
   };
   if ((rc = plain(&sc.elems, e->batch * S * scan_elem_doubles(n))) != SIPOC_OK) return rc;
-  if ((rc = plain(&sc.maps, e->batch * S * scan_map_doubles(n))) != SIPOC_OK) return rc;
+  const int64_t G = S / sc.Sg;
+  if ((rc = plain(&sc.gelems, e->batch * G * scan_elem_doubles(n))) != SIPOC_OK) return rc;
+  if ((rc = plain(&sc.maps, e->batch * (S + G) * scan_map_doubles(n))) != SIPOC_OK) return rc;
   if ((rc = alloc_doubles(e, &sc.Vb, (S + 1) * n * n)) != SIPOC_OK) return rc;
   if ((rc = alloc_doubles(e, &sc.vb, (S + 1) * n)) != SIPOC_OK) return rc;
   if ((rc = alloc_doubles(e, &sc.xb, (S + 1) * n)) != SIPOC_OK) return rc;
@@ -471,8 +473,8 @@ sipoc_error lqr_factor_solve_scan(sipoc_engine *e, const LqrIn &in, const LqrOut
   sipoc_error rc;
   if ((rc = ensure_scan_ws(e)) != SIPOC_OK) return rc;
   sipoc_engine::Scan &sc = e->scan;
-  const ScanArgs sa{in,       e->fast->n, e->fast->m, sc.L,  sc.S,  e->batch,      e->ld,
-                    sc.elems, sc.maps,    sc.Vb,      sc.vb, sc.xb, sc.seg_status, &e->prof};
+  const ScanArgs sa{in,       e->fast->n, e->fast->m, sc.L,    sc.S,  sc.Sg, e->batch,      e->ld,
+                    sc.elems, sc.gelems,  sc.maps,    sc.Vb,   sc.vb, sc.xb, sc.seg_status, &e->prof};
   const int front = launch_scan_front(sa, s);
   if (front < 0) return fail(e, SIPOC_UNSUPPORTED, "no scan kernels for this shape");
   e->launches += front;
@@ -984,6 +986,9 @@ sipoc_error sipoc_create(const sipoc_structure *s, sipoc_engine **out) {
       e->scan.enabled = true;
       e->scan.L = best;
       e->scan.S = h.E / best;
+      e->scan.Sg = scan_group_size(e->scan.S);
+      if (const char *env = getenv("SIPOC_SCAN_GROUP"))
+        if (atoi(env) >= 1 && e->scan.S % atoi(env) == 0) e->scan.Sg = atoi(env);
     }
   }
   e->variant = e->fast != nullptr ? e->fast->name : "generic_thread_per_problem";

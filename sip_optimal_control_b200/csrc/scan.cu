@@ -31,9 +31,14 @@
 // Depth: 2 L + 2 S stage times instead of 2 N.  Needs R > 0 (the reference only needs
 // R + B'WB > 0): a non-positive pivot of R is reported as G_FACTORIZATION_FAILURE.
 //
-// Mapping of 1 and 2: one WARP per problem (an element is five small dense objects; 32 lanes
-// share each product), four problems per CTA so that global reads are whole 32-byte sectors
-// of the batch-interleaved layout; all operands in shared memory.
+// Mapping of 1 and 2: one WARP per problem (an element is five small dense objects), four
+// problems per CTA so that global reads are whole 32-byte sectors of the batch-interleaved
+// layout; all operands in shared memory.  Every N x N product runs on the FP64 tensor cores
+// (`mma.sync.m8n8k4.f64`, SASS DMMA.8x8x4: one 8-byte shared-memory load per operand per 256
+// FMA, against two loads per FMA for a lane-per-element product), the two inverses of a combine
+// are symmetric sweeps (Gauss-Jordan on the lower triangle, three entries per lane in
+// registers, one pivot per step -- positive pivots <=> the Cholesky pivots of Eigen::LLT).
+// Kernel 1 stages edge k - 1 with cp.async while edge k is absorbed.
 #include "scan.cuh"
 
 #include <cstdio>
@@ -43,79 +48,139 @@ namespace {
 
 constexpr int kWarps = 4;  // problems per CTA (32-byte sectors of the interleaved layout)
 
-// ---- warp-level dense helpers on column-major N x N blocks in shared memory -------------
-// C = alpha * op(A) * op(B) (+ C0).  TA / TB: use the transpose.
-template <int N, bool TA, bool TB>
-__device__ __forceinline__ void wmm(const double *A, const double *B, double *C, int lane,
-                                    double alpha = 1.0, const double *C0 = nullptr) {
-  for (int e = lane; e < N * N; e += 32) {
-    const int i = e % N, j = e / N;
-    double acc = 0.0, acc2 = 0.0;
-#pragma unroll
-    for (int k = 0; k < N; k += 2) {
-      acc += (TA ? A[i * N + k] : A[k * N + i]) * (TB ? B[k * N + j] : B[j * N + k]);
-      if (k + 1 < N)
-        acc2 += (TA ? A[i * N + k + 1] : A[(k + 1) * N + i]) *
-                (TB ? B[(k + 1) * N + j] : B[j * N + k + 1]);
-    }
-    C[e] = alpha * (acc + acc2) + (C0 != nullptr ? C0[e] : 0.0);
-  }
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+  const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
 }
+__device__ __forceinline__ void cp_async_commit() {
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+}
+
+// D(8x8) += A(8x4) B(4x8).  Lane l (g = l / 4, t = l % 4) holds A(g, t), B(t, g) and
+// D(g, 2t), D(g, 2t + 1).
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};\n"
+               : "+d"(c[0]), "+d"(c[1])
+               : "d"(a), "d"(b));
+}
+
+// N x N product with inner dimension K on the tensor cores: out(i, j) <- sum_k fa(i, k) fb(k, j)
+// through fs(i, j, sum).  Every operand fragment is read before any result is stored (with a
+// warp barrier between), so fs may overwrite an operand.
+template <int N, int K, class FA, class FB, class FS>
+__device__ __forceinline__ void tile_product(int lane, FA fa, FB fb, FS fs) {
+  constexpr int RT = (N + 7) / 8, KS = (K + 3) / 4;
+  const int g = lane >> 2, t = lane & 3;
+  double af[RT][KS], bf[RT][KS];
+#pragma unroll
+  for (int r = 0; r < RT; ++r)
+#pragma unroll
+    for (int s = 0; s < KS; ++s) {
+      const int i = 8 * r + g, k = 4 * s + t;
+      const bool in = (N % 8 == 0 || i < N) && (K % 4 == 0 || k < K);
+      af[r][s] = in ? fa(i, k) : 0.0;
+      bf[r][s] = in ? fb(k, i) : 0.0;
+    }
+  __syncwarp();
+#pragma unroll
+  for (int r = 0; r < RT; ++r)
+#pragma unroll
+    for (int c = 0; c < RT; ++c) {
+      double acc[2] = {0.0, 0.0};
+#pragma unroll
+      for (int s = 0; s < KS; ++s) dmma(acc, af[r][s], bf[c][s]);
+      const int i = 8 * r + g, j = 8 * c + 2 * t;
+      if (N % 8 == 0 || i < N) {
+        if (N % 8 == 0 || j < N) fs(i, j, acc[0]);
+        if (N % 8 == 0 || j + 1 < N) fs(i, j + 1, acc[1]);
+      }
+    }
+}
+
 // y = alpha * op(A) x (+ y0), lanes over rows.
 template <int N, bool TA>
 __device__ __forceinline__ void wmv(const double *A, const double *x, double *y, int lane,
                                     double alpha = 1.0, const double *y0 = nullptr) {
   if (lane < N) {
-    double acc = 0.0;
+    double acc = 0.0, acc2 = 0.0;
 #pragma unroll
-    for (int k = 0; k < N; ++k) acc += (TA ? A[lane * N + k] : A[k * N + lane]) * x[k];
-    y[lane] = alpha * acc + (y0 != nullptr ? y0[lane] : 0.0);
+    for (int k = 0; k < N; k += 2) {
+      acc += (TA ? A[lane * N + k] : A[k * N + lane]) * x[k];
+      if (k + 1 < N) acc2 += (TA ? A[lane * N + k + 1] : A[(k + 1) * N + lane]) * x[k + 1];
+    }
+    y[lane] = alpha * (acc + acc2) + (y0 != nullptr ? y0[lane] : 0.0);
   }
 }
 
-// In-place inverse of a symmetric positive definite n x n block (n <= N runtime, column-major
-// with leading dimension n): right-looking Cholesky shared by the lanes, the inverse of the
-// factor one column per lane, then L^-T L^-1.  `work` holds n * n + n doubles.  Returns
-// false (warp-uniform) on a pivot <= 0 -- Eigen::LLT's failure rule.
-__device__ __forceinline__ bool spd_inverse(double *A, double *work, int n, int lane) {
-  double *X = work, *dinv = work + n * n;
-  bool ok = true;
-  for (int j = 0; j < n; ++j) {
-    const double piv = A[j * n + j];
-    ok = ok && (piv > 0.0);
-    const double s = rsqrt(piv);
-    __syncwarp();
-    if (lane == 0) dinv[j] = s;
-    for (int i = j + lane; i < n; i += 32) A[j * n + i] *= s;  // column j of L (diag = sqrt)
-    __syncwarp();
-    const int rem = n - j - 1;
-    for (int e = lane; e < rem * rem; e += 32) {  // trailing update, lower part
-      const int c = j + 1 + e / rem, i = j + 1 + e % rem;
-      if (i >= c) A[c * n + i] -= A[j * n + i] * A[j * n + c];
-    }
-    __syncwarp();
+// In-place inverse of a symmetric positive definite NS x NS block (column-major, leading
+// dimension NS, stored in full, 16-byte aligned): NS symmetric sweeps
+//   d = a_jj;  a_jj <- -1/d;  a_ij <- a_ij / d;  a_ik <- a_ik - a_ij a_kj / d   (i, k != j)
+// leave -A^-1; the pivots are those of the Cholesky factorization squared, so `all pivots > 0`
+// is Eigen::LLT's success rule.  Lane i < NS keeps row i in registers (by symmetry it is
+// stored contiguously as column i); the pivot row travels through `buf` (2 NS doubles, one
+// half per step parity, so one warp barrier per step); the loop over the pivots is unrolled,
+// every register index is static.  Returns false (warp-uniform) on a pivot <= 0.
+template <int NS>
+__device__ __forceinline__ bool sweep_inverse(double *A, double *buf, int lane) {
+  static_assert(NS % 2 == 0, "rows move as 16-byte pairs");
+  const int i = lane < NS ? lane : 0;  // lanes beyond NS shadow row 0 and never store
+  double a[NS];
+  double2 *row = reinterpret_cast<double2 *>(A + i * NS);
+#pragma unroll
+  for (int c = 0; c < NS; c += 2) {
+    const double2 v = row[c / 2];
+    a[c] = v.x;
+    a[c + 1] = v.y;
   }
-  // X = L^-1, lane c owns column c
-  for (int c = lane; c < n; c += 32) {
-    for (int i = 0; i < c; ++i) X[c * n + i] = 0.0;
-    X[c * n + c] = dinv[c];
-    for (int i = c + 1; i < n; ++i) {
-      double acc = 0.0;
-      for (int k = c; k < i; ++k) acc += A[k * n + i] * X[c * n + k];
-      X[c * n + i] = -acc * dinv[i];
-    }
+  if (lane == 0) {
+#pragma unroll
+    for (int c = 0; c < NS; c += 2)
+      reinterpret_cast<double2 *>(buf)[c / 2] = make_double2(a[c], a[c + 1]);
   }
   __syncwarp();
-  // A^-1 = X' X
-  for (int e = lane; e < n * n; e += 32) {
-    const int i = e % n, j = e / n;
-    double acc = 0.0;
-    for (int k = (i > j ? i : j); k < n; ++k) acc += X[i * n + k] * X[j * n + k];
-    A[e] = acc;
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < NS; ++j) {
+    const double2 *uj = reinterpret_cast<const double2 *>(buf + (j & 1) * NS);
+    double u[NS];
+#pragma unroll
+    for (int c = 0; c < NS; c += 2) {
+      const double2 v = uj[c / 2];
+      u[c] = v.x;
+      u[c + 1] = v.y;
+    }
+    ok = ok && (u[j] > 0.0);
+    const double p = __drcp_rn(u[j]);
+    if (lane == j) {
+#pragma unroll
+      for (int c = 0; c < NS; ++c) a[c] = c == j ? -p : u[c] * p;
+    } else {
+      const double t = -a[j] * p;
+#pragma unroll
+      for (int c = 0; c < NS; ++c) a[c] = c == j ? -t : fma(t, u[c], a[c]);
+    }
+    if (j + 1 < NS && lane == j + 1) {
+      double2 *nx = reinterpret_cast<double2 *>(buf + ((j + 1) & 1) * NS);
+#pragma unroll
+      for (int c = 0; c < NS; c += 2) nx[c / 2] = make_double2(a[c], a[c + 1]);
+    }
+    __syncwarp();
+  }
+  if (lane < NS) {
+#pragma unroll
+    for (int c = 0; c < NS; c += 2) row[c / 2] = make_double2(-a[c], -a[c + 1]);
   }
   __syncwarp();
   return ok;
 }
+
+// Doubles of one element (A, C, J, b, eta) -- the order of the slots of ScanSmem and of the
+// element arrays in global memory.
+template <int N>
+constexpr int kElem = 3 * N * N + 2 * N;
 
 // One problem's working set in shared memory.
 template <int N>
@@ -125,117 +190,142 @@ struct ScanSmem {
   double A2[NN], C2[NN], J2[NN], b2[N], e2[N];
   double A1[NN], C1[NN], J1[NN], b1[N], e1[N];
   double Ci[NN], Xi[NN], CiA[NN], XA[NN], T[NN];
-  double work[NN + N];
   double v0[N], v1[N], v2[N], v3[N];
 };
 
 // acc (2) <- combine(incoming (1), acc (2)).  Returns false if a factorization failed.
-template <int N>
-__device__ __forceinline__ bool combine(ScanSmem<N> &w, int lane, bool need_AC) {
+template <int N, bool NEED_AC>
+__device__ __forceinline__ bool combine(ScanSmem<N> &w, int lane) {
   constexpr int NN = N * N;
   for (int e = lane; e < NN; e += 32) w.Ci[e] = w.C1[e];
   __syncwarp();
-  bool ok = spd_inverse(w.Ci, w.work, N, lane);                    // C1^-1
+  bool ok = sweep_inverse<N>(w.Ci, w.v2, lane);                   // C1^-1
   for (int e = lane; e < NN; e += 32) w.Xi[e] = w.Ci[e] + w.J2[e];
-  __syncwarp();
-  ok = spd_inverse(w.Xi, w.work, N, lane) && ok;                   // Xi = (C1^-1 + J2)^-1
-  wmm<N, false, false>(w.Ci, w.A1, w.CiA, lane);                   // C1^-1 A1
-  // v0 = C1^-1 b1 + eta2 ; v1 = eta2 - J2 b1
-  wmv<N, false>(w.Ci, w.b1, w.v0, lane, 1.0, w.e2);
+  // v1 = eta2 - J2 b1
   wmv<N, false>(w.J2, w.b1, w.v1, lane, -1.0, w.e2);
   __syncwarp();
-  wmm<N, false, false>(w.Xi, w.CiA, w.XA, lane);                   // X A1 = Xi C1^-1 A1
-  wmv<N, false>(w.Xi, w.v0, w.v2, lane);                           // Xi (C1^-1 b1 + eta2)
+  ok = sweep_inverse<N>(w.Xi, w.v2, lane) && ok;                  // Xi = (C1^-1 + J2)^-1
+  tile_product<N, N>(lane, [&](int i, int k) { return w.Ci[k * N + i]; },
+                     [&](int k, int j) { return w.A1[j * N + k]; },
+                     [&](int i, int j, double v) { w.CiA[j * N + i] = v; });   // C1^-1 A1
+  wmv<N, false>(w.Ci, w.b1, w.v0, lane, 1.0, w.e2);                // v0 = C1^-1 b1 + eta2
   wmv<N, false>(w.Xi, w.v1, w.v3, lane);                           // Xi (eta2 - J2 b1)
   __syncwarp();
-  // J = A1' C1^-1 A1 - (C1^-1 A1)' (X A1) + J1   (into T, then J2)
-  wmm<N, true, false>(w.A1, w.CiA, w.T, lane, 1.0, w.J1);
-  __syncwarp();
-  wmm<N, true, false>(w.CiA, w.XA, w.J2, lane, -1.0, w.T);
-  // eta = (C1^-1 A1)' Xi (eta2 - J2 b1) + eta1 ; b = A2 Xi (C1^-1 b1 + eta2) + b2
+  tile_product<N, N>(lane, [&](int i, int k) { return w.Xi[k * N + i]; },
+                     [&](int k, int j) { return w.CiA[j * N + k]; },
+                     [&](int i, int j, double v) { w.XA[j * N + i] = v; });    // Xi C1^-1 A1
+  wmv<N, false>(w.Xi, w.v0, w.v2, lane);                           // Xi (C1^-1 b1 + eta2)
+  // eta = (C1^-1 A1)' Xi (eta2 - J2 b1) + eta1   (into v1, published below)
   wmv<N, true>(w.CiA, w.v3, w.v1, lane, 1.0, w.e1);
-  if (need_AC) wmv<N, false>(w.A2, w.v2, w.v0, lane, 1.0, w.b2);
   __syncwarp();
-  if (lane < N) {
-    w.e2[lane] = w.v1[lane];
-    if (need_AC) w.b2[lane] = w.v0[lane];
-  }
-  if (need_AC) {
-    wmm<N, false, false>(w.A2, w.Xi, w.T, lane);                   // A2 Xi
+  // J = J1 + A1' (C1^-1 A1) - (C1^-1 A1)' (Xi C1^-1 A1): one accumulation over 2 N terms
+  tile_product<N, 2 * N>(
+      lane, [&](int i, int k) { return k < N ? w.A1[i * N + k] : -w.CiA[i * N + k - N]; },
+      [&](int k, int j) { return k < N ? w.CiA[j * N + k] : w.XA[j * N + k - N]; },
+      [&](int i, int j, double v) { w.J2[j * N + i] = v + w.J1[j * N + i]; });
+  if (lane < N) w.e2[lane] = w.v1[lane];
+  if (NEED_AC) {
+    wmv<N, false>(w.A2, w.v2, w.v0, lane, 1.0, w.b2);               // b = A2 Xi (...) + b2
+    tile_product<N, N>(lane, [&](int i, int k) { return w.A2[k * N + i]; },
+                       [&](int k, int j) { return w.Xi[j * N + k]; },
+                       [&](int i, int j, double v) { w.T[j * N + i] = v; });   // A2 Xi
     __syncwarp();
-    wmm<N, false, true>(w.T, w.A2, w.Ci, lane, 1.0, w.C2);         // C = A2 Xi A2' + C2
-    wmm<N, false, false>(w.A2, w.XA, w.CiA, lane);                 // A = A2 X A1
+    if (lane < N) w.b2[lane] = w.v0[lane];
+    tile_product<N, N>(lane, [&](int i, int k) { return w.T[k * N + i]; },
+                       [&](int k, int j) { return w.A2[k * N + j]; },
+                       [&](int i, int j, double v) { w.C2[j * N + i] += v; }); // C = A2 Xi A2' + C2
     __syncwarp();
-    for (int e = lane; e < NN; e += 32) {
-      w.C2[e] = w.Ci[e];
-      w.A2[e] = w.CiA[e];
-    }
+    tile_product<N, N>(lane, [&](int i, int k) { return w.A2[k * N + i]; },
+                       [&](int k, int j) { return w.XA[j * N + k]; },
+                       [&](int i, int j, double v) { w.A2[j * N + i] = v; });  // A = A2 Xi C1^-1 A1
   }
   __syncwarp();
   return ok;
 }
 
-// Element of edge k into slot 1 from the batch-interleaved inputs of problem b.
-// `raw` (shared, >= 2 N N + 2 N M + M M + 3 N + 2 M + M M doubles) receives the stage first.
+// Flat offsets of one edge's operands in the staging buffer (doubles per problem).
+struct EdgeMap {
+  int A, B, Q, M, R, c, q, d, r, total;
+  __device__ __host__ EdgeMap(int n, int m) {
+    A = 0;
+    B = A + n * n;
+    Q = B + n * m;
+    M = Q + n * n;
+    R = M + n * m;
+    c = R + m * m;
+    q = c + n;
+    d = q + n;
+    r = d + n;
+    total = r + m;
+  }
+};
+
+// Edge k of the four problems of the CTA -> raw[flat][4] (16-byte copies, whole sectors).
+__device__ __forceinline__ void stage_edge(double *raw, const LqrIn &in, const EdgeMap &mp, int n,
+                                           int m, int k, int64_t b0, int64_t ld) {
+  const size_t L = static_cast<size_t>(ld), kk = static_cast<size_t>(k);
+  const int half = threadIdx.x & 1;
+  for (int f = threadIdx.x >> 1; f < mp.total; f += (32 * kWarps) >> 1) {
+    const double *src;
+    if (f < mp.B) src = in.A + (kk * n * n + (f - mp.A)) * L;
+    else if (f < mp.Q) src = in.B + (kk * n * m + (f - mp.B)) * L;
+    else if (f < mp.M) src = in.Q + (kk * n * n + (f - mp.Q)) * L;
+    else if (f < mp.R) src = in.M + (kk * n * m + (f - mp.M)) * L;
+    else if (f < mp.c) src = in.R + (kk * m * m + (f - mp.R)) * L;
+    else if (f < mp.q) src = in.c + ((kk + 1) * n + (f - mp.c)) * L;
+    else if (f < mp.d) src = in.q + (kk * n + (f - mp.q)) * L;
+    else if (f < mp.r) src = in.delta + ((kk + 1) * n + (f - mp.d)) * L;
+    else src = in.r + (kk * m + (f - mp.r)) * L;
+    cp_async16(raw + f * kWarps + 2 * half, src + b0 + 2 * half);
+  }
+}
+
+// Element of the staged edge into slot 1 (raw is this warp's column of the staging buffer:
+// entry f at raw[f * kWarps]).
 template <int N>
-__device__ __forceinline__ bool load_edge_element(ScanSmem<N> &w, const LqrIn &in, int M, int k,
-                                                  int64_t b, int64_t ld, int lane) {
-  const size_t L = static_cast<size_t>(ld);
-  auto G = [&](const double *p, size_t flat) { return __ldg(p + flat * L + b); };
-  double *Bm = w.Ci, *Mm = w.Xi, *Ri = w.T, *BRi = w.CiA, *MRi = w.XA;  // scratch views
-  const size_t kk = static_cast<size_t>(k);
-  for (int e = lane; e < N * N; e += 32) {
-    w.A1[e] = G(in.A, kk * N * N + e);
-    const int i = e % N, j = e / N;  // symmetric Q from its lower triangle
-    w.J1[e] = G(in.Q, kk * N * N + (i >= j ? j * N + i : i * N + j));
+__device__ __forceinline__ bool build_edge_element(ScanSmem<N> &w, const double *raw,
+                                                   const EdgeMap &mp, int M, int lane) {
+  auto R = [&](int f) { return raw[f * kWarps]; };
+  double *Ri = w.T, *BRi = w.CiA, *MRi = w.XA;  // scratch views
+  if (lane < 16) {  // symmetric R from its lower triangle, padded to 4 x 4 with the identity
+    const int i = lane & 3, j = lane >> 2;
+    Ri[lane] = (i < M && j < M) ? R(mp.R + (i >= j ? j * M + i : i * M + j)) : (i == j ? 1.0 : 0.0);
   }
-  for (int e = lane; e < N * M; e += 32) {
-    Bm[e] = G(in.B, kk * N * M + e);
-    Mm[e] = G(in.M, kk * N * M + e);
-  }
-  for (int e = lane; e < M * M; e += 32) {
-    const int i = e % M, j = e / M;
-    Ri[e] = G(in.R, kk * M * M + (i >= j ? j * M + i : i * M + j));
-  }
-  if (lane < N) {
-    w.b1[lane] = G(in.c, (kk + 1) * N + lane);
-    w.e1[lane] = -G(in.q, kk * N + lane);
-    w.v0[lane] = G(in.delta, (kk + 1) * N + lane);
-  }
-  if (lane < M) w.v1[lane] = G(in.r, kk * M + lane);
   __syncwarp();
-  const bool ok = spd_inverse(Ri, w.work, M, lane);  // R^-1
-  for (int e = lane; e < N * M; e += 32) {           // B R^-1 and M R^-1 (N x M)
+  const bool ok = sweep_inverse<4>(Ri, w.v2, lane);  // R^-1
+  for (int e = lane; e < N * M; e += 32) {             // B R^-1 and M R^-1 (N x M)
     const int i = e % N, a = e / N;
     double sb = 0.0, sm = 0.0;
     for (int c = 0; c < M; ++c) {
-      sb += Bm[c * N + i] * Ri[a * M + c];
-      sm += Mm[c * N + i] * Ri[a * M + c];
+      sb += R(mp.B + c * N + i) * Ri[a * 4 + c];
+      sm += R(mp.M + c * N + i) * Ri[a * 4 + c];
     }
     BRi[e] = sb;
     MRi[e] = sm;
   }
   __syncwarp();
-  for (int e = lane; e < N * N; e += 32) {
-    const int i = e % N, j = e / N;
-    double sa = 0.0, sc = 0.0, sj = 0.0;
-    for (int a = 0; a < M; ++a) {
-      sa += BRi[a * N + i] * Mm[a * N + j];   // B R^-1 M'
-      sc += BRi[a * N + i] * Bm[a * N + j];   // B R^-1 B'
-      sj += MRi[a * N + i] * Mm[a * N + j];   // M R^-1 M'
-    }
-    w.A1[e] -= sa;
-    w.C1[e] = sc + (i == j ? w.v0[i] : 0.0);
-    w.J1[e] -= sj;
-  }
+  // A = A_k - B R^-1 M',  C = B R^-1 B' + diag(delta'),  J = Q_k - M R^-1 M'  (inner dim M <= 4)
+  tile_product<N, 4>(lane, [&](int i, int k) { return k < M ? BRi[k * N + i] : 0.0; },
+                     [&](int k, int j) { return k < M ? R(mp.M + k * N + j) : 0.0; },
+                     [&](int i, int j, double v) { w.A1[j * N + i] = R(mp.A + j * N + i) - v; });
+  tile_product<N, 4>(lane, [&](int i, int k) { return k < M ? BRi[k * N + i] : 0.0; },
+                     [&](int k, int j) { return k < M ? R(mp.B + k * N + j) : 0.0; },
+                     [&](int i, int j, double v) {
+                       w.C1[j * N + i] = v + (i == j ? R(mp.d + i) : 0.0);
+                     });
+  tile_product<N, 4>(lane, [&](int i, int k) { return k < M ? MRi[k * N + i] : 0.0; },
+                     [&](int k, int j) { return k < M ? R(mp.M + k * N + j) : 0.0; },
+                     [&](int i, int j, double v) {
+                       w.J1[j * N + i] = R(mp.Q + (i >= j ? j * N + i : i * N + j)) - v;
+                     });
   if (lane < N) {
     double sb = 0.0, sm = 0.0;
     for (int a = 0; a < M; ++a) {
-      sb += BRi[a * N + lane] * w.v1[a];
-      sm += MRi[a * N + lane] * w.v1[a];
+      sb += BRi[a * N + lane] * R(mp.r + a);
+      sm += MRi[a * N + lane] * R(mp.r + a);
     }
-    w.b1[lane] -= sb;   // c' - B R^-1 r
-    w.e1[lane] += sm;   // -(q - M R^-1 r)
+    w.b1[lane] = R(mp.c + lane) - sb;   // c' - B R^-1 r
+    w.e1[lane] = sm - R(mp.q + lane);   // -(q - M R^-1 r)
   }
   __syncwarp();
   return ok;
@@ -249,32 +339,33 @@ scan_segment_kernel(LqrIn in, int M, int L, int64_t batch, int64_t ld, double *e
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   ScanSmem<N> &w = reinterpret_cast<ScanSmem<N> *>(smem_raw)[warp];
-  const int64_t b = static_cast<int64_t>(blockIdx.x) * kWarps + warp;
+  double *raw = reinterpret_cast<double *>(smem_raw + sizeof(ScanSmem<N>) * kWarps);
+  const int64_t b0 = static_cast<int64_t>(blockIdx.x) * kWarps, b = b0 + warp;
   const int seg = blockIdx.y, S = gridDim.y;
-  if (b >= batch) return;
-  constexpr int NN = N * N;
-  for (int e = lane; e < NN; e += 32) {  // identity element
-    w.A2[e] = (e % N == e / N) ? 1.0 : 0.0;
-    w.C2[e] = 0.0;
-    w.J2[e] = 0.0;
-  }
-  if (lane < N) w.b2[lane] = w.e2[lane] = 0.0;
-  __syncwarp();
+  const bool active = b < batch;  // idle warps still take part in the CTA barriers
+  const EdgeMap mp(N, M);
+  const int k_last = (seg + 1) * L - 1, k_first = seg * L;
+  stage_edge(raw, in, mp, N, M, k_last, b0, ld);
+  cp_async_commit();
   bool ok = true, r_ok = true;
-  for (int k = (seg + 1) * L - 1; k >= seg * L; --k) {
-    r_ok = load_edge_element(w, in, M, k, b, ld, lane) && r_ok;
-    ok = combine(w, lane, true) && ok;
+  for (int k = k_last; k >= k_first; --k) {
+    cp_async_wait_all();
+    __syncthreads();
+    if (active) r_ok = build_edge_element(w, raw + warp, mp, M, lane) && r_ok;
+    __syncthreads();  // every warp is done with the staging buffer
+    if (k > k_first) stage_edge(raw, in, mp, N, M, k - 1, b0, ld);
+    cp_async_commit();
+    if (!active) continue;
+    if (k == k_last) {  // the run starts as the last edge's own element
+      for (int e = lane; e < kElem<N>; e += 32) w.A2[e] = w.A1[e];
+      __syncwarp();
+    } else {
+      ok = combine<N, true>(w, lane) && ok;
+    }
   }
-  double *out = elems + (static_cast<size_t>(b) * S + seg) * (3 * NN + 2 * N);
-  for (int e = lane; e < NN; e += 32) {
-    out[e] = w.A2[e];
-    out[NN + e] = w.C2[e];
-    out[2 * NN + e] = w.J2[e];
-  }
-  if (lane < N) {
-    out[3 * NN + lane] = w.b2[lane];
-    out[3 * NN + N + lane] = w.e2[lane];
-  }
+  if (!active) return;
+  double *out = elems + (static_cast<size_t>(b) * S + seg) * kElem<N>;
+  for (int e = lane; e < kElem<N>; e += 32) out[e] = w.A2[e];
   if (lane == 0)
     seg_status[static_cast<size_t>(seg) * ld + b] =
         !r_ok ? SIPOC_FACTOR_G_FACTORIZATION_FAILURE
@@ -282,86 +373,142 @@ scan_segment_kernel(LqrIn in, int M, int L, int64_t batch, int64_t ld, double *e
 }
 
 // ---- 2. boundary values and states --------------------------------------------------------
-// Vb [S + 1][N N][ld], vb / xb [S + 1][N][ld] in the engine layout (what the segmented sweep
-// stages); T1 / t2 per (problem, segment) scratch, problem-major.
+// Two levels so that the dependent chain is 2 Sg + G combines instead of S = Sg G:
+//   2a. scan_group_kernel   every (problem, group of Sg segments): the group's element.
+//   2b. scan_chain_kernel   (top) per problem, the chain over the G group elements from the
+//       terminal node: (V, v) and x at the group boundaries.
+//   2c. scan_chain_kernel   every (problem, group): the chain over its Sg segment elements from
+//       the group's end boundary: (V, v) and x at the boundaries inside the group.
+// With G == 1 only 2b runs, on the segment elements.
 template <int N>
 __global__ void __launch_bounds__(32 * kWarps)
-scan_boundary_kernel(LqrIn in, int L, int S, int64_t batch, int64_t ld, const double *elems,
-                     double *maps, double *Vb, double *vb, double *xb, int *seg_status) {
+scan_group_kernel(int Sg, int G, int64_t batch, int64_t ld, const double *elems, double *gelems,
+                  int *seg_status) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   ScanSmem<N> &w = reinterpret_cast<ScanSmem<N> *>(smem_raw)[warp];
   const int64_t b = static_cast<int64_t>(blockIdx.x) * kWarps + warp;
+  const int g = blockIdx.y;
   if (b >= batch) return;
-  constexpr int NN = N * N;
+  constexpr int EL = kElem<N>, PER = (EL + 31) / 32;
+  const double *el = elems + (static_cast<size_t>(b) * G * Sg + static_cast<size_t>(g + 1) * Sg - 1) * EL;
+  for (int e = lane; e < EL; e += 32) w.A2[e] = el[e];
+  bool ok = true;
+  double pre[PER];
+  for (int t = Sg - 2; t >= 0; --t) {
+    el -= EL;
+#pragma unroll
+    for (int q = 0; q < PER; ++q) pre[q] = lane + 32 * q < EL ? el[lane + 32 * q] : 0.0;
+#pragma unroll
+    for (int q = 0; q < PER; ++q)
+      if (lane + 32 * q < EL) w.A1[lane + 32 * q] = pre[q];
+    __syncwarp();
+    ok = combine<N, true>(w, lane) && ok;
+  }
+  __syncwarp();
+  double *out = gelems + (static_cast<size_t>(b) * G + g) * EL;
+  for (int e = lane; e < EL; e += 32) out[e] = w.A2[e];
+  const size_t first = static_cast<size_t>(g) * Sg * ld + b;
+  if (!ok && lane == 0 && seg_status[first] == 0) seg_status[first] = SIPOC_FACTOR_F_FACTORIZATION_FAILURE;
+}
+
+// Vb [S + 1][N N][ld], vb / xb [S + 1][N][ld] in the engine layout (what the segmented sweep
+// stages).  Chain h of problem b runs over elements el[b][h cnt .. (h + 1) cnt), each spanning
+// `span` segments; maps (x_end = T1 x_start + t2 per element) are scratch, problem-major.
+template <int N, bool TOP>
+__global__ void __launch_bounds__(32 * kWarps)
+scan_chain_kernel(LqrIn in, int L, int cnt, int span, int H, int64_t batch, int64_t ld,
+                  const double *elems, double *maps, double *Vb, double *vb, double *xb,
+                  int *seg_status) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  ScanSmem<N> &w = reinterpret_cast<ScanSmem<N> *>(smem_raw)[warp];
+  const int64_t b = static_cast<int64_t>(blockIdx.x) * kWarps + warp;
+  const int h = blockIdx.y;
+  if (b >= batch) return;
+  constexpr int NN = N * N, EL = kElem<N>, PER = (EL + 31) / 32;
   const size_t Ld = static_cast<size_t>(ld);
-  const size_t T = static_cast<size_t>(L) * S;
-  // terminal value: V = Q_T, v = q_T  (lqr.cpp:658, 744)
-  for (int e = lane; e < NN; e += 32) {
-    const int i = e % N, j = e / N;
-    w.J2[e] = __ldg(in.Q + (T * NN + (i >= j ? j * N + i : i * N + j)) * Ld + b);
-    w.A2[e] = 0.0;
-    w.C2[e] = 0.0;
+  const size_t e0 = static_cast<size_t>(h) * cnt;        // first element of the chain
+  const size_t bnd_end = (e0 + cnt) * span;              // boundary index of the chain's end
+  if (TOP) {
+    // terminal value: V = Q_T, v = q_T  (lqr.cpp:658, 744)
+    const size_t T = bnd_end * L;  // the chain of the top level ends at the last node
+    for (int e = lane; e < NN; e += 32) {
+      const int i = e % N, j = e / N;
+      w.J2[e] = __ldg(in.Q + (T * NN + (i >= j ? j * N + i : i * N + j)) * Ld + b);
+    }
+    if (lane < N) w.e2[lane] = -__ldg(in.q + (T * N + lane) * Ld + b);
+  } else {
+    for (int e = lane; e < NN; e += 32) w.J2[e] = Vb[(bnd_end * NN + e) * Ld + b];
+    if (lane < N) w.e2[lane] = -vb[(bnd_end * N + lane) * Ld + b];
   }
-  if (lane < N) {
-    w.e2[lane] = -__ldg(in.q + (T * N + lane) * Ld + b);
-    w.b2[lane] = 0.0;
-  }
+  const double *el = elems + (static_cast<size_t>(b) * H * cnt + e0 + cnt - 1) * EL;
+  double *mp = maps + (static_cast<size_t>(b) * H * cnt + e0 + cnt - 1) * (NN + N);
+  double pre[PER];
+#pragma unroll
+  for (int q = 0; q < PER; ++q) pre[q] = lane + 32 * q < EL ? el[lane + 32 * q] : 0.0;
   __syncwarp();
   bool ok = true;
-  for (int seg = S; seg >= 0; --seg) {
-    // publish (V, v) at boundary node seg * L
-    for (int e = lane; e < NN; e += 32) Vb[(static_cast<size_t>(seg) * NN + e) * Ld + b] = w.J2[e];
-    if (lane < N) vb[(static_cast<size_t>(seg) * N + lane) * Ld + b] = -w.e2[lane];
-    if (seg == 0) break;
-    const double *el = elems + (static_cast<size_t>(b) * S + (seg - 1)) * (3 * NN + 2 * N);
-    for (int e = lane; e < NN; e += 32) {
-      w.A1[e] = el[e];
-      w.C1[e] = el[NN + e];
-      w.J1[e] = el[2 * NN + e];
+  for (int t = cnt; t >= 0; --t) {
+    // publish (V, v) at boundary (e0 + t) span -- the chain's ends are the parent level's
+    if (TOP || (t > 0 && t < cnt)) {
+      const size_t bnd = (e0 + t) * span;
+      for (int e = lane; e < NN; e += 32) Vb[(bnd * NN + e) * Ld + b] = w.J2[e];
+      if (lane < N) vb[(bnd * N + lane) * Ld + b] = -w.e2[lane];
     }
-    if (lane < N) {
-      w.b1[lane] = el[3 * NN + lane];
-      w.e1[lane] = el[3 * NN + N + lane];
+    if (t == 0) break;
+#pragma unroll
+    for (int q = 0; q < PER; ++q)
+      if (lane + 32 * q < EL) w.A1[lane + 32 * q] = pre[q];
+    if (t > 1) {  // the next element loads under the combine
+      el -= EL;
+#pragma unroll
+      for (int q = 0; q < PER; ++q) pre[q] = lane + 32 * q < EL ? el[lane + 32 * q] : 0.0;
     }
     __syncwarp();
-    ok = combine(w, lane, false) && ok;
+    ok = combine<N, false>(w, lane) && ok;
     // After combine: Xi = (C1^-1 + V_e)^-1, XA = Xi C1^-1 A1, v2 = Xi (C1^-1 b1 - v_e):
-    // x_e = XA x_a + v2 (the state at the segment's end from the state at its start).
-    double *mp = maps + (static_cast<size_t>(b) * S + (seg - 1)) * (NN + N);
+    // x_e = XA x_a + v2 (the state at the element's end from the state at its start).
     for (int e = lane; e < NN; e += 32) mp[e] = w.XA[e];
     if (lane < N) mp[NN + lane] = w.v2[lane];
-    if (!ok && lane == 0 && seg_status[static_cast<size_t>(seg - 1) * Ld + b] == 0)
-      seg_status[static_cast<size_t>(seg - 1) * Ld + b] = SIPOC_FACTOR_F_FACTORIZATION_FAILURE;
+    mp -= NN + N;
+    const size_t first = (e0 + t - 1) * span * Ld + b;
+    if (!ok && lane == 0 && seg_status[first] == 0)
+      seg_status[first] = SIPOC_FACTOR_F_FACTORIZATION_FAILURE;
     __syncwarp();
   }
-  // root: x_0 = -(I + D_0 V_0)^-1 (delta_0 o v_0 - c_0) = -(V_0 + D_0^-1)^-1 (v_0 - c_0 / delta_0)
-  // (lqr.cpp:798-819; V_0 = J2, v_0 = -e2)
-  if (lane < N) {
-    const double d0 = __ldg(in.delta + static_cast<size_t>(lane) * Ld + b);
-    const double c0 = __ldg(in.c + static_cast<size_t>(lane) * Ld + b);
-    w.v0[lane] = 1.0 / d0;
-    w.v1[lane] = -w.e2[lane] - c0 / d0;
+  mp += NN + N;  // map of the chain's first element
+  if (TOP) {
+    // root: x_0 = -(I + D_0 V_0)^-1 (delta_0 o v_0 - c_0) = -(V_0 + D_0^-1)^-1 (v_0 - c_0 / delta_0)
+    // (lqr.cpp:798-819; V_0 = J2, v_0 = -e2)
+    if (lane < N) {
+      const double d0 = __ldg(in.delta + static_cast<size_t>(lane) * Ld + b);
+      const double c0 = __ldg(in.c + static_cast<size_t>(lane) * Ld + b);
+      w.v0[lane] = 1.0 / d0;
+      w.v1[lane] = -w.e2[lane] - c0 / d0;
+    }
+    __syncwarp();
+    for (int e = lane; e < NN; e += 32) w.Xi[e] = w.J2[e] + (e % N == e / N ? w.v0[e % N] : 0.0);
+    __syncwarp();
+    sweep_inverse<N>(w.Xi, w.v2, lane);
+    wmv<N, false>(w.Xi, w.v1, w.v0, lane, -1.0);
+    __syncwarp();
+    if (lane < N) xb[static_cast<size_t>(lane) * Ld + b] = w.v0[lane];
+  } else {
+    if (lane < N) w.v0[lane] = xb[(e0 * span * N + lane) * Ld + b];
   }
   __syncwarp();
-  for (int e = lane; e < NN; e += 32) w.Xi[e] = w.J2[e] + (e % N == e / N ? w.v0[e % N] : 0.0);
-  __syncwarp();
-  spd_inverse(w.Xi, w.work, N, lane);
-  wmv<N, false>(w.Xi, w.v1, w.v2, lane, -1.0);
-  __syncwarp();
-  if (lane < N) xb[static_cast<size_t>(lane) * Ld + b] = w.v2[lane];
-  for (int seg = 0; seg < S; ++seg) {
-    const double *mp = maps + (static_cast<size_t>(b) * S + seg) * (NN + N);
+  for (int t = 0; t < cnt; ++t, mp += NN + N) {
     if (lane < N) {
       double acc = mp[NN + lane];
 #pragma unroll
-      for (int k = 0; k < N; ++k) acc += mp[k * N + lane] * w.v2[k];
-      w.v0[lane] = acc;
+      for (int k = 0; k < N; ++k) acc += mp[k * N + lane] * w.v0[k];
+      w.v1[lane] = acc;
     }
     __syncwarp();
     if (lane < N) {
-      w.v2[lane] = w.v0[lane];
-      xb[(static_cast<size_t>(seg + 1) * N + lane) * Ld + b] = w.v0[lane];
+      w.v0[lane] = w.v1[lane];
+      if (TOP || t + 1 < cnt) xb[((e0 + t + 1) * span * N + lane) * Ld + b] = w.v1[lane];
     }
     __syncwarp();
   }
@@ -385,31 +532,63 @@ template <int N>
 int launch_front(const ScanArgs &a, cudaStream_t s) {
   const unsigned groups = static_cast<unsigned>((a.batch + kWarps - 1) / kWarps);
   const int bytes = static_cast<int>(sizeof(ScanSmem<N>)) * kWarps;
+  const int bytes1 = bytes + EdgeMap(N, a.M).total * kWarps * static_cast<int>(sizeof(double));
   auto k1 = scan_segment_kernel<N>;
-  auto k2 = scan_boundary_kernel<N>;
-  cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  auto k2a = scan_group_kernel<N>;
+  auto k2b = scan_chain_kernel<N, true>;
+  auto k2c = scan_chain_kernel<N, false>;
+  cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes1);
+  cudaFuncSetAttribute(k2a, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  cudaFuncSetAttribute(k2b, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  cudaFuncSetAttribute(k2c, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   {
     ProfScope ps(a.prof, "scan_segment_kernel", s);
-    k1<<<dim3(groups, a.S), 32 * kWarps, bytes, s>>>(a.in, a.M, a.L, a.batch, a.ld, a.elems,
-                                                     a.seg_status);
+    k1<<<dim3(groups, a.S), 32 * kWarps, bytes1, s>>>(a.in, a.M, a.L, a.batch, a.ld, a.elems,
+                                                      a.seg_status);
+  }
+  const int Sg = a.Sg, G = a.S / a.Sg;
+  if (G == 1) {
+    ProfScope ps(a.prof, "scan_chain_kernel", s);
+    k2b<<<groups, 32 * kWarps, bytes, s>>>(a.in, a.L, a.S, 1, 1, a.batch, a.ld, a.elems, a.maps, a.Vb,
+                                           a.vb, a.xb, a.seg_status);
+    return 2;
+  }
+  double *gmaps = a.maps + a.batch * a.S * scan_map_doubles(N);
+  {
+    ProfScope ps(a.prof, "scan_group_kernel", s);
+    k2a<<<dim3(groups, G), 32 * kWarps, bytes, s>>>(Sg, G, a.batch, a.ld, a.elems, a.gelems,
+                                                    a.seg_status);
   }
   {
-    ProfScope ps(a.prof, "scan_boundary_kernel", s);
-    k2<<<groups, 32 * kWarps, bytes, s>>>(a.in, a.L, a.S, a.batch, a.ld, a.elems, a.maps, a.Vb,
-                                          a.vb, a.xb, a.seg_status);
+    ProfScope ps(a.prof, "scan_chain_kernel(groups)", s);
+    k2b<<<groups, 32 * kWarps, bytes, s>>>(a.in, a.L, G, Sg, 1, a.batch, a.ld, a.gelems, gmaps, a.Vb,
+                                           a.vb, a.xb, a.seg_status);
   }
-  return 2;
+  {
+    ProfScope ps(a.prof, "scan_chain_kernel(segments)", s);
+    k2c<<<dim3(groups, G), 32 * kWarps, bytes, s>>>(a.in, a.L, Sg, 1, G, a.batch, a.ld, a.elems, a.maps,
+                                                    a.Vb, a.vb, a.xb, a.seg_status);
+  }
+  return 4;
 }
 
 }  // namespace
 
 int64_t scan_elem_doubles(int n) { return 3LL * n * n + 2 * n; }
+
+// Segments per group of the two-level boundary pass: the divisor of S that minimises the
+// dependent chain 2 Sg + S / Sg (S itself -- one level -- for short chains).
+int scan_group_size(int S) {
+  if (S <= 12) return S;
+  int best = S;
+  for (int sg = 2; sg < S; ++sg)
+    if (S % sg == 0 && 2 * sg + S / sg < (best == S ? S : 2 * best + S / best)) best = sg;
+  return best;
+}
 int64_t scan_map_doubles(int n) { return 1LL * n * n + n; }
 
 int launch_scan_front(const ScanArgs &a, cudaStream_t s) {
   switch (a.N) {
-    case 4: return launch_front<4>(a, s);
     case 6: return launch_front<6>(a, s);
     case 8: return launch_front<8>(a, s);
     case 12: return launch_front<12>(a, s);
@@ -417,7 +596,7 @@ int launch_scan_front(const ScanArgs &a, cudaStream_t s) {
   }
 }
 
-bool scan_supports(int n, int m) { return (n == 4 || n == 6 || n == 8 || n == 12) && m >= 1 && m <= n; }
+bool scan_supports(int n, int m) { return (n == 6 || n == 8 || n == 12) && m >= 1 && m <= 4; }
 
 void launch_scan_status(const int *sweep_status, const int *seg_status, int S, int64_t batch,
                         int64_t ld, int *status, cudaStream_t s) {

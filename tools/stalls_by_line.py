@@ -42,7 +42,9 @@ for ln in sass.splitlines():
         continue
     if re.match(r"\s+/\*[0-9a-f]{4,}\*/", ln):
         lines.append(cur)
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True,
+# NCU_KERNEL=<regex> picks one kernel of a report that holds several
+pick = ["-k", "regex:" + os.environ["NCU_KERNEL"]] if os.environ.get("NCU_KERNEL") else []
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + pick, capture_output=True,
                      text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
