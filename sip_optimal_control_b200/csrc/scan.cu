@@ -123,9 +123,16 @@ __device__ __forceinline__ void wmv(const double *A, const double *x, double *y,
 // stored contiguously as column i); the pivot row travels through `buf` (2 NS doubles, one
 // half per step parity, so one warp barrier per step); the loop over the pivots is unrolled,
 // every register index is static.  Returns false (warp-uniform) on a pivot <= 0.
-template <int NS>
-__device__ __forceinline__ bool sweep_inverse(double *A, double *buf, int lane) {
+// DUAL: lanes 16.. sweep a second block at A + NS NS with the buffer at buf + 2 NS.
+template <int NS, bool DUAL = false>
+__device__ __forceinline__ bool sweep_inverse(double *A, double *buf, int full_lane) {
   static_assert(NS % 2 == 0, "rows move as 16-byte pairs");
+  static_assert(!DUAL || NS <= 16, "two blocks share the warp");
+  const int lane = DUAL ? full_lane & 15 : full_lane;
+  if (DUAL && full_lane >= 16) {
+    A += NS * NS;
+    buf += 2 * NS;
+  }
   const int i = lane < NS ? lane : 0;  // lanes beyond NS shadow row 0 and never store
   double a[NS];
   double2 *row = reinterpret_cast<double2 *>(A + i * NS);
@@ -174,7 +181,7 @@ __device__ __forceinline__ bool sweep_inverse(double *A, double *buf, int lane) 
     for (int c = 0; c < NS; c += 2) row[c / 2] = make_double2(-a[c], -a[c + 1]);
   }
   __syncwarp();
-  return ok;
+  return DUAL ? __all_sync(0xffffffffu, ok) : ok;
 }
 
 // Doubles of one element (A, C, J, b, eta) -- the order of the slots of ScanSmem and of the
@@ -186,34 +193,42 @@ constexpr int kElem = 3 * N * N + 2 * N;
 template <int N>
 struct ScanSmem {
   static constexpr int NN = N * N;
-  // accumulated element (the later run), incoming element (the earlier run), temporaries
+  static constexpr int kTmp = NN > 8 * N ? NN : 8 * N;  // also holds two N x 4 build operands
+  // accumulated element (the later run), incoming element (the earlier run), temporaries.
+  // Regions are reused inside a combine: C1 is inverted in place (Ci), then receives
+  // XA = Xi C1^-1 A1 once C1^-1 has been applied; T = A2 Xi lands on CiA once that is dead.
   double A2[NN], C2[NN], J2[NN], b2[N], e2[N];
   double A1[NN], C1[NN], J1[NN], b1[N], e1[N];
-  double Ci[NN], Xi[NN], CiA[NN], XA[NN], T[NN];
+  double Xi[kTmp], CiA[kTmp];
   double v0[N], v1[N], v2[N], v3[N];
+  double small[48];  // R, R + B' D^-1 B (4 x 4 each) and their sweep buffers
+  __device__ __forceinline__ double *Ci() { return C1; }
+  __device__ __forceinline__ double *XA() { return C1; }
+  __device__ __forceinline__ double *T() { return CiA; }
 };
 
 // acc (2) <- combine(incoming (1), acc (2)).  Returns false if a factorization failed.
-template <int N, bool NEED_AC>
+// HAVE_CI: slot C1 already holds C1^-1 (the edge builder forms it by the Woodbury identity).
+template <int N, bool NEED_AC, bool HAVE_CI = false>
 __device__ __forceinline__ bool combine(ScanSmem<N> &w, int lane) {
   constexpr int NN = N * N;
-  for (int e = lane; e < NN; e += 32) w.Ci[e] = w.C1[e];
-  __syncwarp();
-  bool ok = sweep_inverse<N>(w.Ci, w.v2, lane);                   // C1^-1
-  for (int e = lane; e < NN; e += 32) w.Xi[e] = w.Ci[e] + w.J2[e];
+  double *Ci = w.Ci(), *XA = w.XA(), *T = w.T();
+  bool ok = true;
+  if (!HAVE_CI) ok = sweep_inverse<N>(Ci, w.v2, lane);             // C1^-1, in place
+  for (int e = lane; e < NN; e += 32) w.Xi[e] = Ci[e] + w.J2[e];
   // v1 = eta2 - J2 b1
   wmv<N, false>(w.J2, w.b1, w.v1, lane, -1.0, w.e2);
   __syncwarp();
   ok = sweep_inverse<N>(w.Xi, w.v2, lane) && ok;                  // Xi = (C1^-1 + J2)^-1
-  tile_product<N, N>(lane, [&](int i, int k) { return w.Ci[k * N + i]; },
+  tile_product<N, N>(lane, [&](int i, int k) { return Ci[k * N + i]; },
                      [&](int k, int j) { return w.A1[j * N + k]; },
                      [&](int i, int j, double v) { w.CiA[j * N + i] = v; });   // C1^-1 A1
-  wmv<N, false>(w.Ci, w.b1, w.v0, lane, 1.0, w.e2);                // v0 = C1^-1 b1 + eta2
+  wmv<N, false>(Ci, w.b1, w.v0, lane, 1.0, w.e2);                  // v0 = C1^-1 b1 + eta2
   wmv<N, false>(w.Xi, w.v1, w.v3, lane);                           // Xi (eta2 - J2 b1)
   __syncwarp();
   tile_product<N, N>(lane, [&](int i, int k) { return w.Xi[k * N + i]; },
                      [&](int k, int j) { return w.CiA[j * N + k]; },
-                     [&](int i, int j, double v) { w.XA[j * N + i] = v; });    // Xi C1^-1 A1
+                     [&](int i, int j, double v) { XA[j * N + i] = v; });      // Xi C1^-1 A1
   wmv<N, false>(w.Xi, w.v0, w.v2, lane);                           // Xi (C1^-1 b1 + eta2)
   // eta = (C1^-1 A1)' Xi (eta2 - J2 b1) + eta1   (into v1, published below)
   wmv<N, true>(w.CiA, w.v3, w.v1, lane, 1.0, w.e1);
@@ -221,22 +236,22 @@ __device__ __forceinline__ bool combine(ScanSmem<N> &w, int lane) {
   // J = J1 + A1' (C1^-1 A1) - (C1^-1 A1)' (Xi C1^-1 A1): one accumulation over 2 N terms
   tile_product<N, 2 * N>(
       lane, [&](int i, int k) { return k < N ? w.A1[i * N + k] : -w.CiA[i * N + k - N]; },
-      [&](int k, int j) { return k < N ? w.CiA[j * N + k] : w.XA[j * N + k - N]; },
+      [&](int k, int j) { return k < N ? w.CiA[j * N + k] : XA[j * N + k - N]; },
       [&](int i, int j, double v) { w.J2[j * N + i] = v + w.J1[j * N + i]; });
   if (lane < N) w.e2[lane] = w.v1[lane];
   if (NEED_AC) {
     wmv<N, false>(w.A2, w.v2, w.v0, lane, 1.0, w.b2);               // b = A2 Xi (...) + b2
     tile_product<N, N>(lane, [&](int i, int k) { return w.A2[k * N + i]; },
                        [&](int k, int j) { return w.Xi[j * N + k]; },
-                       [&](int i, int j, double v) { w.T[j * N + i] = v; });   // A2 Xi
+                       [&](int i, int j, double v) { T[j * N + i] = v; });     // A2 Xi
     __syncwarp();
     if (lane < N) w.b2[lane] = w.v0[lane];
-    tile_product<N, N>(lane, [&](int i, int k) { return w.T[k * N + i]; },
+    tile_product<N, N>(lane, [&](int i, int k) { return T[k * N + i]; },
                        [&](int k, int j) { return w.A2[k * N + j]; },
                        [&](int i, int j, double v) { w.C2[j * N + i] += v; }); // C = A2 Xi A2' + C2
     __syncwarp();
     tile_product<N, N>(lane, [&](int i, int k) { return w.A2[k * N + i]; },
-                       [&](int k, int j) { return w.XA[j * N + k]; },
+                       [&](int k, int j) { return XA[j * N + k]; },
                        [&](int i, int j, double v) { w.A2[j * N + i] = v; });  // A = A2 Xi C1^-1 A1
   }
   __syncwarp();
@@ -281,43 +296,73 @@ __device__ __forceinline__ void stage_edge(double *raw, const LqrIn &in, const E
 }
 
 // Element of the staged edge into slot 1 (raw is this warp's column of the staging buffer:
-// entry f at raw[f * kWarps]).
-template <int N>
+// entry f at raw[f * kWarps]).  FIRST: slot C1 receives C = B R^-1 B' + D (the run starts as
+// this element); otherwise it receives C^-1 by the Woodbury identity
+//   C^-1 = D^-1 - D^-1 B (R + B' D^-1 B)^-1 B' D^-1
+// -- a second 4 x 4 inverse (swept beside R^-1 by the upper half of the warp) instead of an
+// N x N one.
+template <int N, bool FIRST>
 __device__ __forceinline__ bool build_edge_element(ScanSmem<N> &w, const double *raw,
                                                    const EdgeMap &mp, int M, int lane) {
   auto R = [&](int f) { return raw[f * kWarps]; };
-  double *Ri = w.T, *BRi = w.CiA, *MRi = w.XA;  // scratch views
-  if (lane < 16) {  // symmetric R from its lower triangle, padded to 4 x 4 with the identity
-    const int i = lane & 3, j = lane >> 2;
-    Ri[lane] = (i < M && j < M) ? R(mp.R + (i >= j ? j * M + i : i * M + j)) : (i == j ? 1.0 : 0.0);
+  double *Ri = w.small, *Rt = w.small + 16, *buf = w.small + 32;
+  double *BRi = w.Xi, *MRi = w.Xi + 4 * N, *Bd = w.CiA, *BG = w.CiA + 4 * N;  // N x 4 each
+  if (!FIRST) {
+    for (int e = lane; e < N * M; e += 32) Bd[e] = R(mp.B + e) / R(mp.d + e % N);  // D^-1 B
+    __syncwarp();
+  }
+  {  // symmetric R from its lower triangle, padded to 4 x 4 with the identity; R + B' D^-1 B
+    const int l = lane & 15, i = l & 3, j = l >> 2;
+    const bool live = i < M && j < M;
+    double v = live ? R(mp.R + (i >= j ? j * M + i : i * M + j)) : (i == j ? 1.0 : 0.0);
+    if (lane >= 16 && !FIRST && live) {
+      double acc = 0.0, acc2 = 0.0;
+#pragma unroll
+      for (int k = 0; k < N; k += 2) {
+        acc += R(mp.B + i * N + k) * Bd[j * N + k];
+        acc2 += R(mp.B + i * N + k + 1) * Bd[j * N + k + 1];
+      }
+      v += acc + acc2;
+    }
+    w.small[lane] = v;
   }
   __syncwarp();
-  const bool ok = sweep_inverse<4>(Ri, w.v2, lane);  // R^-1
-  for (int e = lane; e < N * M; e += 32) {             // B R^-1 and M R^-1 (N x M)
+  const bool ok = sweep_inverse<4, !FIRST>(Ri, buf, lane);  // R^-1 (and (R + B' D^-1 B)^-1)
+  for (int e = lane; e < N * M; e += 32) {                  // B R^-1, M R^-1, D^-1 B G~ (N x M)
     const int i = e % N, a = e / N;
-    double sb = 0.0, sm = 0.0;
+    double sb = 0.0, sm = 0.0, sg = 0.0;
     for (int c = 0; c < M; ++c) {
       sb += R(mp.B + c * N + i) * Ri[a * 4 + c];
       sm += R(mp.M + c * N + i) * Ri[a * 4 + c];
+      if (!FIRST) sg += Bd[c * N + i] * Rt[a * 4 + c];
     }
     BRi[e] = sb;
     MRi[e] = sm;
+    if (!FIRST) BG[e] = sg;
   }
   __syncwarp();
-  // A = A_k - B R^-1 M',  C = B R^-1 B' + diag(delta'),  J = Q_k - M R^-1 M'  (inner dim M <= 4)
+  // A = A_k - B R^-1 M',  J = Q_k - M R^-1 M',  C = B R^-1 B' + diag(delta')  (inner dim M <= 4)
   tile_product<N, 4>(lane, [&](int i, int k) { return k < M ? BRi[k * N + i] : 0.0; },
                      [&](int k, int j) { return k < M ? R(mp.M + k * N + j) : 0.0; },
                      [&](int i, int j, double v) { w.A1[j * N + i] = R(mp.A + j * N + i) - v; });
-  tile_product<N, 4>(lane, [&](int i, int k) { return k < M ? BRi[k * N + i] : 0.0; },
-                     [&](int k, int j) { return k < M ? R(mp.B + k * N + j) : 0.0; },
-                     [&](int i, int j, double v) {
-                       w.C1[j * N + i] = v + (i == j ? R(mp.d + i) : 0.0);
-                     });
   tile_product<N, 4>(lane, [&](int i, int k) { return k < M ? MRi[k * N + i] : 0.0; },
                      [&](int k, int j) { return k < M ? R(mp.M + k * N + j) : 0.0; },
                      [&](int i, int j, double v) {
                        w.J1[j * N + i] = R(mp.Q + (i >= j ? j * N + i : i * N + j)) - v;
                      });
+  if (FIRST) {
+    tile_product<N, 4>(lane, [&](int i, int k) { return k < M ? BRi[k * N + i] : 0.0; },
+                       [&](int k, int j) { return k < M ? R(mp.B + k * N + j) : 0.0; },
+                       [&](int i, int j, double v) {
+                         w.C1[j * N + i] = v + (i == j ? R(mp.d + i) : 0.0);
+                       });
+  } else {
+    tile_product<N, 4>(lane, [&](int i, int k) { return k < M ? BG[k * N + i] : 0.0; },
+                       [&](int k, int j) { return k < M ? Bd[k * N + j] : 0.0; },
+                       [&](int i, int j, double v) {
+                         w.C1[j * N + i] = (i == j ? 1.0 / R(mp.d + i) : 0.0) - v;
+                       });
+  }
   if (lane < N) {
     double sb = 0.0, sm = 0.0;
     for (int a = 0; a < M; ++a) {
@@ -351,7 +396,9 @@ scan_segment_kernel(LqrIn in, int M, int L, int64_t batch, int64_t ld, double *e
   for (int k = k_last; k >= k_first; --k) {
     cp_async_wait_all();
     __syncthreads();
-    if (active) r_ok = build_edge_element(w, raw + warp, mp, M, lane) && r_ok;
+    if (active)
+      r_ok = (k == k_last ? build_edge_element<N, true>(w, raw + warp, mp, M, lane)
+                          : build_edge_element<N, false>(w, raw + warp, mp, M, lane)) && r_ok;
     __syncthreads();  // every warp is done with the staging buffer
     if (k > k_first) stage_edge(raw, in, mp, N, M, k - 1, b0, ld);
     cp_async_commit();
@@ -360,7 +407,7 @@ scan_segment_kernel(LqrIn in, int M, int L, int64_t batch, int64_t ld, double *e
       for (int e = lane; e < kElem<N>; e += 32) w.A2[e] = w.A1[e];
       __syncwarp();
     } else {
-      ok = combine<N, true>(w, lane) && ok;
+      ok = combine<N, true, true>(w, lane) && ok;
     }
   }
   if (!active) return;
@@ -469,7 +516,7 @@ scan_chain_kernel(LqrIn in, int L, int cnt, int span, int H, int64_t batch, int6
     ok = combine<N, false>(w, lane) && ok;
     // After combine: Xi = (C1^-1 + V_e)^-1, XA = Xi C1^-1 A1, v2 = Xi (C1^-1 b1 - v_e):
     // x_e = XA x_a + v2 (the state at the element's end from the state at its start).
-    for (int e = lane; e < NN; e += 32) mp[e] = w.XA[e];
+    for (int e = lane; e < NN; e += 32) mp[e] = w.XA()[e];
     if (lane < N) mp[NN + lane] = w.v2[lane];
     mp -= NN + N;
     const size_t first = (e0 + t - 1) * span * Ld + b;
