@@ -115,23 +115,37 @@ __device__ __forceinline__ void wmv(const double *A, const double *x, double *y,
   }
 }
 
+// 1 / d to about an ulp: MUFU.RCP64H seed and two Newton steps (no special cases: d is a
+// pivot, and a pivot <= 0 is reported, not used).
+__device__ __forceinline__ double fast_rcp(double d) {
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+  double e = fma(-d, x, 1.0);
+  x = fma(x, e, x);
+  e = fma(-d, x, 1.0);
+  return fma(x, e, x);
+}
+
 // In-place inverse of a symmetric positive definite NS x NS block (column-major, leading
-// dimension NS, stored in full, 16-byte aligned): NS symmetric sweeps
-//   d = a_jj;  a_jj <- -1/d;  a_ij <- a_ij / d;  a_ik <- a_ik - a_ij a_kj / d   (i, k != j)
-// leave -A^-1; the pivots are those of the Cholesky factorization squared, so `all pivots > 0`
-// is Eigen::LLT's success rule.  Lane i < NS keeps row i in registers (by symmetry it is
-// stored contiguously as column i); the pivot row travels through `buf` (2 NS doubles, one
-// half per step parity, so one warp barrier per step); the loop over the pivots is unrolled,
-// every register index is static.  Returns false (warp-uniform) on a pivot <= 0.
-// DUAL: lanes 16.. sweep a second block at A + NS NS with the buffer at buf + 2 NS.
+// dimension NS, stored in full, 16-byte aligned) by symmetric sweeps on 2 x 2 pivot blocks
+// J = {j, j + 1}:
+//   A_JJ <- -P^-1;  A_iJ <- A_iJ P^-1;  A_ic <- A_ic - A_iJ P^-1 A_Jc   (i, c not in J),  P = A_JJ
+// which leave -A^-1 after NS / 2 steps (half the dependent chain of one-pivot sweeps).  Both
+// pivots of a block are positive (a_jj > 0 and det P > 0) exactly when the two Cholesky pivots
+// are, so `all positive` is Eigen::LLT's success rule.  Lane i < NS keeps row i in registers
+// (by symmetry it is stored contiguously as column i); the two pivot rows travel through `buf`
+// (4 NS doubles, one half per step parity, so one warp barrier per step); the loop over the
+// blocks is unrolled, every register index is static.  Returns false (warp-uniform) on a
+// non-positive pivot.
+// DUAL: lanes 16.. sweep a second block at A + NS NS with the buffer at buf + 4 NS.
 template <int NS, bool DUAL = false>
 __device__ __forceinline__ bool sweep_inverse(double *A, double *buf, int full_lane) {
-  static_assert(NS % 2 == 0, "rows move as 16-byte pairs");
+  static_assert(NS % 2 == 0, "rows move as 16-byte pairs, pivots as 2 x 2 blocks");
   static_assert(!DUAL || NS <= 16, "two blocks share the warp");
   const int lane = DUAL ? full_lane & 15 : full_lane;
   if (DUAL && full_lane >= 16) {
     A += NS * NS;
-    buf += 2 * NS;
+    buf += 4 * NS;
   }
   const int i = lane < NS ? lane : 0;  // lanes beyond NS shadow row 0 and never store
   double a[NS];
@@ -142,35 +156,44 @@ __device__ __forceinline__ bool sweep_inverse(double *A, double *buf, int full_l
     a[c] = v.x;
     a[c + 1] = v.y;
   }
-  if (lane == 0) {
+  if (lane < 2) {
 #pragma unroll
     for (int c = 0; c < NS; c += 2)
-      reinterpret_cast<double2 *>(buf)[c / 2] = make_double2(a[c], a[c + 1]);
+      reinterpret_cast<double2 *>(buf + lane * NS)[c / 2] = make_double2(a[c], a[c + 1]);
   }
   __syncwarp();
   bool ok = true;
 #pragma unroll
-  for (int j = 0; j < NS; ++j) {
-    const double2 *uj = reinterpret_cast<const double2 *>(buf + (j & 1) * NS);
-    double u[NS];
+  for (int jb = 0; jb < NS / 2; ++jb) {
+    const int j = 2 * jb, k = j + 1;
+    const double2 *uj = reinterpret_cast<const double2 *>(buf + (jb & 1) * 2 * NS);
+    const double2 *uk = uj + NS / 2;
+    double u[NS], w[NS];
 #pragma unroll
     for (int c = 0; c < NS; c += 2) {
-      const double2 v = uj[c / 2];
+      const double2 v = uj[c / 2], z = uk[c / 2];
       u[c] = v.x;
       u[c + 1] = v.y;
+      w[c] = z.x;
+      w[c + 1] = z.y;
     }
-    ok = ok && (u[j] > 0.0);
-    const double p = __drcp_rn(u[j]);
-    if (lane == j) {
+    const double det = fma(u[j], w[k], -u[k] * u[k]);
+    ok = ok && (u[j] > 0.0) && (det > 0.0);
+    const double r = fast_rcp(det);
+    const double p00 = w[k] * r, p01 = -u[k] * r, p11 = u[j] * r;  // P^-1
+    if (lane == j || lane == k) {
+      const double s0 = lane == j ? p00 : p01, s1 = lane == j ? p01 : p11;
 #pragma unroll
-      for (int c = 0; c < NS; ++c) a[c] = c == j ? -p : u[c] * p;
+      for (int c = 0; c < NS; ++c)
+        a[c] = c == j ? -s0 : (c == k ? -s1 : fma(s0, u[c], s1 * w[c]));
     } else {
-      const double t = -a[j] * p;
+      const double g0 = fma(a[j], p00, a[k] * p01), g1 = fma(a[j], p01, a[k] * p11);
 #pragma unroll
-      for (int c = 0; c < NS; ++c) a[c] = c == j ? -t : fma(t, u[c], a[c]);
+      for (int c = 0; c < NS; ++c)
+        a[c] = c == j ? g0 : (c == k ? g1 : fma(-g0, u[c], fma(-g1, w[c], a[c])));
     }
-    if (j + 1 < NS && lane == j + 1) {
-      double2 *nx = reinterpret_cast<double2 *>(buf + ((j + 1) & 1) * NS);
+    if (jb + 1 < NS / 2 && (lane == j + 2 || lane == j + 3)) {
+      double2 *nx = reinterpret_cast<double2 *>(buf + (((jb + 1) & 1) * 2 + (lane - j - 2)) * NS);
 #pragma unroll
       for (int c = 0; c < NS; c += 2) nx[c / 2] = make_double2(a[c], a[c + 1]);
     }
@@ -201,7 +224,7 @@ struct ScanSmem {
   double A1[NN], C1[NN], J1[NN], b1[N], e1[N];
   double Xi[kTmp], CiA[kTmp];
   double v0[N], v1[N], v2[N], v3[N];
-  double small[48];  // R, R + B' D^-1 B (4 x 4 each) and their sweep buffers
+  double small[64];  // R, R + B' D^-1 B (4 x 4 each) and their sweep buffers
   __device__ __forceinline__ double *Ci() { return C1; }
   __device__ __forceinline__ double *XA() { return C1; }
   __device__ __forceinline__ double *T() { return CiA; }
@@ -214,12 +237,12 @@ __device__ __forceinline__ bool combine(ScanSmem<N> &w, int lane) {
   constexpr int NN = N * N;
   double *Ci = w.Ci(), *XA = w.XA(), *T = w.T();
   bool ok = true;
-  if (!HAVE_CI) ok = sweep_inverse<N>(Ci, w.v2, lane);             // C1^-1, in place
+  if (!HAVE_CI) ok = sweep_inverse<N>(Ci, w.v0, lane);             // C1^-1, in place
   for (int e = lane; e < NN; e += 32) w.Xi[e] = Ci[e] + w.J2[e];
-  // v1 = eta2 - J2 b1
-  wmv<N, false>(w.J2, w.b1, w.v1, lane, -1.0, w.e2);
   __syncwarp();
-  ok = sweep_inverse<N>(w.Xi, w.v2, lane) && ok;                  // Xi = (C1^-1 + J2)^-1
+  ok = sweep_inverse<N>(w.Xi, w.v0, lane) && ok;                  // Xi = (C1^-1 + J2)^-1
+  wmv<N, false>(w.J2, w.b1, w.v1, lane, -1.0, w.e2);               // v1 = eta2 - J2 b1
+  __syncwarp();
   tile_product<N, N>(lane, [&](int i, int k) { return Ci[k * N + i]; },
                      [&](int k, int j) { return w.A1[j * N + k]; },
                      [&](int i, int j, double v) { w.CiA[j * N + i] = v; });   // C1^-1 A1
@@ -531,14 +554,14 @@ scan_chain_kernel(LqrIn in, int L, int cnt, int span, int H, int64_t batch, int6
     if (lane < N) {
       const double d0 = __ldg(in.delta + static_cast<size_t>(lane) * Ld + b);
       const double c0 = __ldg(in.c + static_cast<size_t>(lane) * Ld + b);
-      w.v0[lane] = 1.0 / d0;
-      w.v1[lane] = -w.e2[lane] - c0 / d0;
+      w.b1[lane] = 1.0 / d0;
+      w.e1[lane] = -w.e2[lane] - c0 / d0;
     }
     __syncwarp();
-    for (int e = lane; e < NN; e += 32) w.Xi[e] = w.J2[e] + (e % N == e / N ? w.v0[e % N] : 0.0);
+    for (int e = lane; e < NN; e += 32) w.Xi[e] = w.J2[e] + (e % N == e / N ? w.b1[e % N] : 0.0);
     __syncwarp();
-    sweep_inverse<N>(w.Xi, w.v2, lane);
-    wmv<N, false>(w.Xi, w.v1, w.v0, lane, -1.0);
+    sweep_inverse<N>(w.Xi, w.v0, lane);
+    wmv<N, false>(w.Xi, w.e1, w.v0, lane, -1.0);
     __syncwarp();
     if (lane < N) xb[static_cast<size_t>(lane) * Ld + b] = w.v0[lane];
   } else {
