@@ -974,10 +974,10 @@ sipoc_error sipoc_create(const sipoc_structure *s, sipoc_engine **out) {
       !(e->flags & SIPOC_FLAG_SERIAL_IN_TIME) && scan_supports(e->fast->n, e->fast->m)) {
     // Parallel in time pays when the serial sweep cannot fill the GPU: a long horizon and a
     // batch far below one wave of tiles.  The segment length is the divisor of the horizon
-    // nearest 64 (depth 2 L + 2 S stage times); SIPOC_SCAN_SEGMENT overrides it.
+    // nearest 32 (measured best at N = 4 096: 16 -> 2.29, 32 -> 1.96, 64 -> 2.14 ms); SIPOC_SCAN_SEGMENT overrides it.
     const bool wanted = (e->flags & SIPOC_FLAG_PARALLEL_IN_TIME) != 0 ||
                         (h.E >= 512 && e->batch <= 512);
-    int target = 64;
+    int target = 32;
     if (const char *env = getenv("SIPOC_SCAN_SEGMENT")) target = std::max(1, atoi(env));
     int best = 0;
     for (int L = 2; L <= h.E / 2; ++L)

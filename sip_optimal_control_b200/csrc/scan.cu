@@ -62,7 +62,7 @@ __device__ __forceinline__ void cp_async_wait_all() {
 // D(8x8) += A(8x4) B(4x8).  Lane l (g = l / 4, t = l % 4) holds A(g, t), B(t, g) and
 // D(g, 2t), D(g, 2t + 1).
 __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};\n"
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};\n"
                : "+d"(c[0]), "+d"(c[1])
                : "d"(a), "d"(b));
 }
@@ -85,17 +85,26 @@ __device__ __forceinline__ void tile_product(int lane, FA fa, FB fb, FS fs) {
       bf[r][s] = in ? fb(k, i) : 0.0;
     }
   __syncwarp();
+  // the RT x RT output tiles advance together, one k-step at a time: independent accumulators
+  double acc[RT][RT][2];
+#pragma unroll
+  for (int r = 0; r < RT; ++r)
+#pragma unroll
+    for (int c = 0; c < RT; ++c) acc[r][c][0] = acc[r][c][1] = 0.0;
+#pragma unroll
+  for (int s = 0; s < KS; ++s)
+#pragma unroll
+    for (int r = 0; r < RT; ++r)
+#pragma unroll
+      for (int c = 0; c < RT; ++c) dmma(acc[r][c], af[r][s], bf[c][s]);
 #pragma unroll
   for (int r = 0; r < RT; ++r)
 #pragma unroll
     for (int c = 0; c < RT; ++c) {
-      double acc[2] = {0.0, 0.0};
-#pragma unroll
-      for (int s = 0; s < KS; ++s) dmma(acc, af[r][s], bf[c][s]);
       const int i = 8 * r + g, j = 8 * c + 2 * t;
       if (N % 8 == 0 || i < N) {
-        if (N % 8 == 0 || j < N) fs(i, j, acc[0]);
-        if (N % 8 == 0 || j + 1 < N) fs(i, j + 1, acc[1]);
+        if (N % 8 == 0 || j < N) fs(i, j, acc[r][c][0]);
+        if (N % 8 == 0 || j + 1 < N) fs(i, j + 1, acc[r][c][1]);
       }
     }
 }
@@ -586,16 +595,33 @@ scan_chain_kernel(LqrIn in, int L, int cnt, int span, int H, int64_t batch, int6
 
 // The status of a problem is its first failure in post-order (lqr.cpp:696-700, 722-727): the
 // failing segment with the largest index, sweep failures before scan failures of the same one.
+// One warp per problem, lanes over the segments.
 __global__ void scan_status_kernel(const int *sweep_status, const int *seg_status, int S,
                                    int64_t batch, int64_t ld, int *status) {
-  const int64_t b = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t b = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (b >= batch) return;
-  int st = SIPOC_FACTOR_SUCCESS;
-  for (int seg = S - 1; seg >= 0 && st == SIPOC_FACTOR_SUCCESS; --seg) {
-    st = sweep_status[static_cast<size_t>(seg) * ld + b];
-    if (st == SIPOC_FACTOR_SUCCESS) st = seg_status[static_cast<size_t>(seg) * ld + b];
+  int key = -1, code = SIPOC_FACTOR_SUCCESS;  // key = 2 seg + (1 for a sweep failure)
+  for (int seg = lane; seg < S; seg += 32) {
+    const int sw = sweep_status[static_cast<size_t>(seg) * ld + b];
+    const int sc = seg_status[static_cast<size_t>(seg) * ld + b];
+    if (sw != SIPOC_FACTOR_SUCCESS) {
+      key = 2 * seg + 1;
+      code = sw;
+    } else if (sc != SIPOC_FACTOR_SUCCESS) {
+      key = 2 * seg;
+      code = sc;
+    }
   }
-  status[b] = st;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const int k2 = __shfl_xor_sync(0xffffffffu, key, o), c2 = __shfl_xor_sync(0xffffffffu, code, o);
+    if (k2 > key) {
+      key = k2;
+      code = c2;
+    }
+  }
+  if (lane == 0) status[b] = code;
 }
 
 template <int N>
@@ -670,7 +696,7 @@ bool scan_supports(int n, int m) { return (n == 6 || n == 8 || n == 12) && m >= 
 
 void launch_scan_status(const int *sweep_status, const int *seg_status, int S, int64_t batch,
                         int64_t ld, int *status, cudaStream_t s) {
-  scan_status_kernel<<<static_cast<unsigned>((batch + 127) / 128), 128, 0, s>>>(
+  scan_status_kernel<<<static_cast<unsigned>((batch + 3) / 4), 128, 0, s>>>(
       sweep_status, seg_status, S, batch, ld, status);
 }
 
