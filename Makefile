@@ -8,15 +8,15 @@ NVCCFLAGS := -std=c++17 -O3 -lineinfo $(ARCH) -ccbin $(HOSTCXX) -Xcompiler -fPIC
 CSRC := sip_optimal_control_b200/csrc
 LIBDIR := sip_optimal_control_b200/lib
 OBJDIR := build/obj
-SRCS := $(CSRC)/api.cu $(CSRC)/generic_kernels.cu $(CSRC)/riccati_fast.cu $(CSRC)/riccati_cta.cu $(CSRC)/riccati_strict.cu $(CSRC)/kkt_fast.cu $(CSRC)/kkt_theta.cu $(CSRC)/comm.cu $(CSRC)/scan.cu \
+SRCS := $(CSRC)/api.cu $(CSRC)/generic_kernels.cu $(CSRC)/riccati_fast.cu $(CSRC)/riccati_cta.cu $(CSRC)/riccati_strict.cu $(CSRC)/kkt_fast.cu $(CSRC)/kkt_theta.cu $(CSRC)/comm.cu $(CSRC)/scan.cu $(CSRC)/model_scatter.cu \
         $(CSRC)/workload.cu $(CSRC)/structure.cpp
 OBJS := $(patsubst $(CSRC)/%,$(OBJDIR)/%.o,$(SRCS)) $(OBJDIR)/riccati_fast_part1.cu.o \
         $(OBJDIR)/riccati_fast_part2.cu.o $(OBJDIR)/riccati_fast_part3.cu.o
 HDRS := $(wildcard $(CSRC)/*.cuh $(CSRC)/*.hpp) include/sipoc.h
 
 HOSTDIR := sip_optimal_control_b200/host
-HOSTSRC := $(HOSTDIR)/lqr.cpp $(HOSTDIR)/types.cpp $(HOSTDIR)/helpers.cpp
-HOSTHDR := $(HOSTDIR)/lqr.hpp $(HOSTDIR)/types.hpp $(HOSTDIR)/helpers.hpp $(HOSTDIR)/device_state.hpp include/sipoc.h
+HOSTSRC := $(HOSTDIR)/lqr.cpp $(HOSTDIR)/types.cpp $(HOSTDIR)/helpers.cpp $(HOSTDIR)/sip_optimal_control.cpp
+HOSTHDR := $(HOSTDIR)/lqr.hpp $(HOSTDIR)/types.hpp $(HOSTDIR)/helpers.hpp $(HOSTDIR)/sip_optimal_control.hpp $(HOSTDIR)/device_state.hpp include/sipoc.h
 HOSTFLAGS := -std=c++17 -O2 -Wall -Wextra -fPIC
 
 all: $(LIBDIR)/libsipoc.so $(LIBDIR)/libsipoc_host.so build/host_tests oracle

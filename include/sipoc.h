@@ -339,6 +339,37 @@ sipoc_error sipoc_kkt_residual(sipoc_engine *engine, const sipoc_kkt_model *mode
                                const double *r3, const double *sol, const double *b,
                                const int *ok, double *residual_norm, double *stats,
                                void *stream);
+/* ---- model-callback scatter ----------------------------------------------------------
+ * The model_callback lambda of sip_optimal_control.cpp:13-127, after the user's callback has
+ * produced the node / edge values of one evaluation: objective f = sum of the node and edge
+ * f (:44-50); gradient_f = df_dx, df_du, df_dtheta scattered to the x layout (:54-85);
+ * c = [initial_state - x_root | node c | edge dyn_res | edge c] in the y layout (:87-109);
+ * g = node / edge g in the z layout (:111-122).  Value arrays concatenate the per-node
+ * (per-edge) vectors in index order (NodeModelCallbackOutput / EdgeModelCallbackOutput,
+ * types.hpp:48-89); sipoc_model_value_sizes gives the elements per problem of each.
+ * new_x == 0 computes f only (the reference's `if (mci.new_x)`, :52).  Sums are formed in
+ * the reference's order, so the result is bit-identical to it. */
+typedef struct sipoc_model_value_sizes_t {
+  int64_t node_f, node_df_dx, node_df_dtheta, node_c, node_g;
+  int64_t edge_f, edge_df_dx, edge_df_du, edge_df_dtheta, edge_dyn_res, edge_c, edge_g;
+} sipoc_model_value_sizes_t;
+typedef struct sipoc_model_values {
+  const double *node_f, *node_df_dx, *node_df_dtheta, *node_c, *node_g;
+  const double *edge_f, *edge_df_dx, *edge_df_du, *edge_df_dtheta, *edge_dyn_res, *edge_c,
+      *edge_g;
+} sipoc_model_values;
+sipoc_error sipoc_model_value_sizes(const sipoc_engine *engine, sipoc_model_value_sizes_t *out);
+/* Device arrays, engine layout: x [x_dim], initial_state [n_root], f [1], gradient_f [x_dim],
+ * c [y_dim], g [z_dim] elements per problem. */
+sipoc_error sipoc_model_scatter(sipoc_engine *engine, const sipoc_model_values *values,
+                                const double *x, const double *initial_state, int new_x,
+                                double *f, double *gradient_f, double *c, double *g,
+                                void *stream);
+/* Host buffers, problem-major ([batch][elements per problem]), synchronous. */
+sipoc_error sipoc_model_scatter_host(sipoc_engine *engine, const sipoc_model_values *values,
+                                     const double *x, const double *initial_state, int new_x,
+                                     double *f, double *gradient_f, double *c, double *g);
+
 /* Host-buffer variants (problem-major), synchronous. */
 sipoc_error sipoc_kkt_factor_host(sipoc_engine *engine, const sipoc_kkt_model *host_model,
                                   const double *w, const double *r1, const double *r2,

@@ -396,6 +396,87 @@ int oracle_kkt_theta_batch(int E, int root, const int *parents, const int *child
   return SUCCESS;
 }
 
+// ---- model-callback scatter: sip_optimal_control.cpp:44-123 --------------------------
+// The node / edge values of one model evaluation scattered into the flat objective, gradient,
+// equality and inequality vectors the interior-point loop reads (get_f / get_grad_f / get_c /
+// get_g).  vals: twelve arrays, problem-major [batch][size]:
+//   0 node f [N]            1 node df_dx [sum n]        2 node df_dtheta [N p]
+//   3 node c [sum node_c]   4 node g [sum node_g]
+//   5 edge f [E]            6 edge df_dx [sum n_parent] 7 edge df_du [sum m]
+//   8 edge df_dtheta [E p]  9 edge dyn_res [sum n_child] 10 edge c [sum edge_c]
+//   11 edge g [sum edge_g]
+// x [batch][x_dim + p], x0 [batch][n_root]; f [batch], grad [batch][x_dim + p],
+// c [batch][y_dim], g [batch][z_dim].  new_x == 0 computes f only (:54).
+int oracle_model_scatter_batch(int E, int root, const int *parents, const int *children,
+                               const int *state_dims, const int *control_dims,
+                               const int *node_c, const int *node_g, const int *edge_c,
+                               const int *edge_g, int p, int64_t batch,
+                               const double *const *vals, const double *x, const double *x0,
+                               int new_x, double *f, double *grad, double *c, double *g) {
+  Tree t{E, root, parents, children};
+  ConstraintDims cd{node_c, node_g, edge_c, edge_g};
+  KktLayout K = make_kkt_layout(t, state_dims, control_dims, cd);
+  const int N = E + 1;
+  std::vector<int> n_off(N + 1, 0), nc_off(N + 1, 0), ng_off(N + 1, 0);
+  std::vector<int> pn_off(E + 1, 0), cn_off(E + 1, 0), m_off(E + 1, 0), ec_off(E + 1, 0),
+      eg_off(E + 1, 0);
+  for (int i = 0; i < N; ++i) {
+    n_off[i + 1] = n_off[i] + state_dims[i];
+    nc_off[i + 1] = nc_off[i] + node_c[i];
+    ng_off[i + 1] = ng_off[i] + node_g[i];
+  }
+  for (int e = 0; e < E; ++e) {
+    pn_off[e + 1] = pn_off[e] + state_dims[parents[e]];
+    cn_off[e + 1] = cn_off[e] + state_dims[children[e]];
+    m_off[e + 1] = m_off[e] + control_dims[e];
+    ec_off[e + 1] = ec_off[e] + edge_c[e];
+    eg_off[e + 1] = eg_off[e] + edge_g[e];
+  }
+  const int64_t size[12] = {N,         n_off[N],  int64_t(N) * p, nc_off[N], ng_off[N], E,
+                            pn_off[E], m_off[E],  int64_t(E) * p, cn_off[E], ec_off[E], eg_off[E]};
+  const int xd = K.x_dim + p;
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < batch; ++i) {
+    const double *v[12];
+    for (int k = 0; k < 12; ++k) v[k] = vals[k] + i * size[k];
+    const double *xi = x + i * xd;
+    double *gi = grad + i * xd, *ci = c + i * K.y_dim, *zi = g + i * K.z_dim;
+    double fi = 0.0;                                              // :44-50
+    for (int node = 0; node < N; ++node) fi += v[0][node];
+    for (int e = 0; e < E; ++e) fi += v[5][e];
+    f[i] = fi;
+    if (!new_x) continue;                                         // :52
+    for (int k = 0; k < xd; ++k) gi[k] = 0.0;                     // :54
+    for (int node = 0; node < N; ++node) {                        // :55-66
+      for (int row = 0; row < state_dims[node]; ++row)
+        gi[K.x_state[node] + row] += v[1][n_off[node] + row];
+      for (int row = 0; row < p; ++row) gi[K.x_dim + row] += v[2][node * p + row];
+    }
+    for (int e = 0; e < E; ++e) {                                 // :67-84
+      const int parent = parents[e];
+      for (int row = 0; row < state_dims[parent]; ++row)
+        gi[K.x_state[parent] + row] += v[6][pn_off[e] + row];
+      for (int row = 0; row < control_dims[e]; ++row)
+        gi[K.x_control[e] + row] += v[7][m_off[e] + row];
+      for (int row = 0; row < p; ++row) gi[K.x_dim + row] += v[8][e * p + row];
+    }
+    for (int row = 0; row < state_dims[root]; ++row)              // :88-94
+      ci[K.y_dyn[root] + row] = x0[i * state_dims[root] + row] - xi[K.x_state[root] + row];
+    for (int node = 0; node < N; ++node)                          // :95-99
+      for (int r = 0; r < node_c[node]; ++r) ci[K.y_node_c[node] + r] = v[3][nc_off[node] + r];
+    for (int e = 0; e < E; ++e) {                                 // :100-108
+      const int child = children[e];
+      for (int r = 0; r < state_dims[child]; ++r) ci[K.y_dyn[child] + r] = v[9][cn_off[e] + r];
+      for (int r = 0; r < edge_c[e]; ++r) ci[K.y_edge_c[e] + r] = v[10][ec_off[e] + r];
+    }
+    for (int node = 0; node < N; ++node)                          // :112-116
+      for (int r = 0; r < node_g[node]; ++r) zi[K.z_node[node] + r] = v[4][ng_off[node] + r];
+    for (int e = 0; e < E; ++e)                                   // :117-121
+      for (int r = 0; r < edge_g[e]; ++r) zi[K.z_edge[e] + r] = v[11][eg_off[e] + r];
+  }
+  return SUCCESS;
+}
+
 int oracle_max_threads() { return omp_get_max_threads(); }
 
 }  // extern "C"

@@ -286,5 +286,45 @@ def kkt_theta_apply(s: Structure, p: int, model: dict, theta: dict, w, r1, r2, r
     return y
 
 
+MODEL_VALUE_NAMES = ("node_f", "node_df_dx", "node_df_dtheta", "node_c", "node_g", "edge_f",
+                     "edge_df_dx", "edge_df_du", "edge_df_dtheta", "edge_dyn_res", "edge_c",
+                     "edge_g")
+
+
+def model_value_sizes(s: Structure, p: int = 0) -> dict:
+    """Per-problem element counts of the twelve value arrays of one model evaluation."""
+    E, N = s.num_edges, s.num_edges + 1
+    n = np.asarray(s.state_dims)
+    par, chi = np.asarray(s.parents)[:E], np.asarray(s.children)[:E]
+    return dict(node_f=N, node_df_dx=int(n.sum()), node_df_dtheta=N * p,
+                node_c=int(np.sum(s.node_c)), node_g=int(np.sum(s.node_g)), edge_f=E,
+                edge_df_dx=int(n[par].sum()) if E else 0,
+                edge_df_du=int(np.sum(np.asarray(s.control_dims)[:E])), edge_df_dtheta=E * p,
+                edge_dyn_res=int(n[chi].sum()) if E else 0,
+                edge_c=int(np.sum(np.asarray(s.edge_c)[:E])),
+                edge_g=int(np.sum(np.asarray(s.edge_g)[:E])))
+
+
+def model_scatter(s: Structure, values: dict, x, initial_state, p: int = 0, new_x: bool = True):
+    """The model callback's scatter (sip_optimal_control.cpp:44-123): f, gradient_f, c, g."""
+    sz, ksz = model_value_sizes(s, p), kkt_sizes(s)
+    vals = [_f64(values[k]) for k in MODEL_VALUE_NAMES]
+    x, x0 = _f64(x), _f64(initial_state)
+    batch = x.shape[0]
+    for k, a in zip(MODEL_VALUE_NAMES, vals):
+        assert a.shape == (batch, sz[k]), (k, a.shape, (batch, sz[k]))
+    assert x.shape == (batch, ksz["x_dim"] + p)
+    f = np.zeros(batch)
+    grad = np.zeros((batch, ksz["x_dim"] + p))
+    c = np.zeros((batch, ksz["y_dim"]))
+    g = np.zeros((batch, ksz["z_dim"]))
+    arr = (_c_dbl_p * 12)(*[_dp(a) for a in vals])
+    st = lib().oracle_model_scatter_batch(
+        *s._topo_args(), *s._dim_args(), *s._cg_args(), ctypes.c_int(p), ctypes.c_int64(batch),
+        arr, _dp(x), _dp(x0), ctypes.c_int(1 if new_x else 0), _dp(f), _dp(grad), _dp(c), _dp(g))
+    assert st == 0
+    return dict(f=f, gradient_f=grad, c=c, g=g)
+
+
 def max_threads() -> int:
     return int(lib().oracle_max_threads())

@@ -85,6 +85,19 @@ class KktModel(ctypes.Structure):
         [("theta", ctypes.POINTER(KktThetaModel))]
 
 
+MODEL_VALUE_FIELDS = ("node_f", "node_df_dx", "node_df_dtheta", "node_c", "node_g", "edge_f",
+                      "edge_df_dx", "edge_df_du", "edge_df_dtheta", "edge_dyn_res", "edge_c",
+                      "edge_g")
+
+
+class ModelValueSizes(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_int64) for k in MODEL_VALUE_FIELDS]
+
+
+class ModelValues(ctypes.Structure):
+    _fields_ = [(k, c_void_p) for k in MODEL_VALUE_FIELDS]
+
+
 def declared_symbols() -> list[str]:
     """Every function name include/sipoc.h declares."""
     text = open(HEADER_PATH).read()
@@ -156,6 +169,10 @@ def _load() -> ctypes.CDLL:
     lib.sipoc_kkt_apply.argtypes = [E, KM, P, P, P, P, P, P, P]
     lib.sipoc_kkt_apply_block.argtypes = [E, KM, ctypes.c_int, P, P, P]
     lib.sipoc_kkt_apply_block_host.argtypes = [E, ctypes.c_int, P, P]
+    MV = ctypes.POINTER(ModelValues)
+    lib.sipoc_model_value_sizes.argtypes = [E, ctypes.POINTER(ModelValueSizes)]
+    lib.sipoc_model_scatter.argtypes = [E, MV, P, P, ctypes.c_int, P, P, P, P, P]
+    lib.sipoc_model_scatter_host.argtypes = [E, MV, P, P, ctypes.c_int, P, P, P, P]
     lib.sipoc_kkt_residual.argtypes = [E, KM, P, P, P, P, P, P, P, P, P, P]
     lib.sipoc_kkt_factor_host.argtypes = [E, KM, P, P, P, P, P]
     lib.sipoc_kkt_solve_host.argtypes = [E, P, P]

@@ -15,6 +15,7 @@
 #include "kkt_fast.cuh"
 #include "kkt_theta.cuh"
 #include "scan.cuh"
+#include "model_scatter.cuh"
 #include "profile.hpp"
 #include "riccati_fast.cuh"
 #include "structure.hpp"
@@ -82,6 +83,9 @@ struct sipoc_engine {
   bool host_kkt_ready = false;
   bool host_model_resident = false;  // hk_model / hk_theta hold a caller's model
   sipoc_comm *comm = nullptr;        // attached communicator: stats outputs are all-reduced
+  // model-callback scatter, host-buffer variant: values, x, x0 | f, gradient_f, c, g
+  double *hm_vals[12] = {}, *hm_x = nullptr, *hm_x0 = nullptr, *hm_out[4] = {};
+  bool host_scatter_ready = false;
 
   // Parallel-in-time factor + solve (scan.cu): long uniform chains, small batches.
   struct Scan {
@@ -1644,6 +1648,103 @@ sipoc_error sipoc_generate_lqr_benchmark(sipoc_engine *e, uint64_t seed, int64_t
                                                q, r, A, B, c, delta,
                                                static_cast<cudaStream_t>(stream));
   return check_launch(e, "generate_lqr_benchmark");
+}
+
+}  // extern "C"
+
+// ---- model-callback scatter (sip_optimal_control.cpp:13-127) --------------------------
+namespace {
+int64_t model_value_size(const HostStructure &h, int i) {
+  const int64_t p = h.theta_dim;
+  switch (i) {
+    case 0: return h.N;
+    case 1: return h.n_off[h.N];
+    case 2: return h.N * p;
+    case 3: return h.node_c_off[h.N];
+    case 4: return h.node_g_off[h.N];
+    case 5: return h.E;
+    case 6: return h.pn_off[h.E];
+    case 7: return h.m_off[h.E];
+    case 8: return h.E * p;
+    case 9: return h.cn_off[h.E];
+    case 10: return h.edge_c_off[h.E];
+    default: return h.edge_g_off[h.E];
+  }
+}
+}  // namespace
+
+extern "C" {
+
+sipoc_error sipoc_model_value_sizes(const sipoc_engine *e, sipoc_model_value_sizes_t *o) {
+  if (e == nullptr || o == nullptr) return SIPOC_INVALID_ARGUMENT;
+  int64_t *fields[12] = {&o->node_f,      &o->node_df_dx, &o->node_df_dtheta, &o->node_c,
+                         &o->node_g,      &o->edge_f,     &o->edge_df_dx,     &o->edge_df_du,
+                         &o->edge_df_dtheta, &o->edge_dyn_res, &o->edge_c,    &o->edge_g};
+  for (int i = 0; i < 12; ++i) *fields[i] = model_value_size(e->hs, i);
+  return SIPOC_OK;
+}
+
+sipoc_error sipoc_model_scatter(sipoc_engine *e, const sipoc_model_values *v, const double *x,
+                                const double *initial_state, int new_x, double *f,
+                                double *gradient_f, double *c, double *g, void *stream) {
+  if (e == nullptr || v == nullptr) return SIPOC_INVALID_ARGUMENT;
+  if (f == nullptr || (new_x && (!x || !initial_state || !gradient_f || !c || !g)))
+    return fail(e, SIPOC_INVALID_ARGUMENT, "sipoc_model_scatter: NULL vector");
+  if (e->hs.N + e->hs.E + 1 > 65535)
+    return fail(e, SIPOC_UNSUPPORTED, "sipoc_model_scatter: more than 32 767 edges");
+  DeviceGuard guard(e->device);
+  const ModelValues mv{v->node_f, v->node_df_dx, v->node_df_dtheta, v->node_c, v->node_g,
+                       v->edge_f, v->edge_df_dx, v->edge_df_du, v->edge_df_dtheta,
+                       v->edge_dyn_res, v->edge_c, v->edge_g};
+  e->launches += launch_model_scatter(e->dt, mv, x, initial_state, new_x != 0, f, gradient_f, c, g,
+                                      e->batch, e->ld, static_cast<cudaStream_t>(stream));
+  return check_launch(e, "model_scatter");
+}
+
+sipoc_error sipoc_model_scatter_host(sipoc_engine *e, const sipoc_model_values *v,
+                                     const double *x, const double *initial_state, int new_x,
+                                     double *f, double *gradient_f, double *c, double *g) {
+  if (e == nullptr || v == nullptr || f == nullptr) return SIPOC_INVALID_ARGUMENT;
+  DeviceGuard guard(e->device);
+  const HostStructure &h = e->hs;
+  sipoc_error rc;
+  const int64_t out_sizes[4] = {1, h.x_dim, h.y_dim, h.z_dim};
+  if (!e->host_scatter_ready) {
+    int64_t biggest = std::max<int64_t>(h.x_dim, std::max(h.y_dim, h.z_dim));
+    for (int i = 0; i < 12; ++i) {
+      if ((rc = alloc_doubles(e, &e->hm_vals[i], model_value_size(h, i))) != SIPOC_OK) return rc;
+      biggest = std::max(biggest, model_value_size(h, i));
+    }
+    if ((rc = alloc_doubles(e, &e->hm_x, h.x_dim)) != SIPOC_OK) return rc;
+    if ((rc = alloc_doubles(e, &e->hm_x0, h.n[h.root])) != SIPOC_OK) return rc;
+    for (int i = 0; i < 4; ++i)
+      if ((rc = alloc_doubles(e, &e->hm_out[i], out_sizes[i])) != SIPOC_OK) return rc;
+    if ((rc = ensure_stage(e, biggest)) != SIPOC_OK) return rc;
+    e->host_scatter_ready = true;
+  }
+  const double *src[12] = {v->node_f, v->node_df_dx, v->node_df_dtheta, v->node_c, v->node_g,
+                           v->edge_f, v->edge_df_dx, v->edge_df_du, v->edge_df_dtheta,
+                           v->edge_dyn_res, v->edge_c, v->edge_g};
+  for (int i = 0; i < 12; ++i) {
+    const bool needed = new_x || i == 0 || i == 5;  // f alone reads the two f arrays
+    if (needed && (rc = upload(e, src[i], e->hm_vals[i], model_value_size(h, i))) != SIPOC_OK)
+      return rc;
+  }
+  if (new_x) {
+    if ((rc = upload(e, x, e->hm_x, h.x_dim)) != SIPOC_OK) return rc;
+    if ((rc = upload(e, initial_state, e->hm_x0, h.n[h.root])) != SIPOC_OK) return rc;
+  }
+  const sipoc_model_values dv{e->hm_vals[0], e->hm_vals[1], e->hm_vals[2],  e->hm_vals[3],
+                              e->hm_vals[4], e->hm_vals[5], e->hm_vals[6],  e->hm_vals[7],
+                              e->hm_vals[8], e->hm_vals[9], e->hm_vals[10], e->hm_vals[11]};
+  if ((rc = sipoc_model_scatter(e, &dv, e->hm_x, e->hm_x0, new_x, e->hm_out[0], e->hm_out[1],
+                                e->hm_out[2], e->hm_out[3], e->host_stream)) != SIPOC_OK)
+    return rc;
+  double *dst[4] = {f, gradient_f, c, g};
+  for (int i = 0; i < (new_x ? 4 : 1); ++i)
+    if ((rc = download(e, e->hm_out[i], dst[i], out_sizes[i])) != SIPOC_OK) return rc;
+  SIPOC_CUDA(e, cudaStreamSynchronize(e->host_stream));
+  return SIPOC_OK;
 }
 
 }  // extern "C"

@@ -28,6 +28,7 @@
 #include <vector>
 
 #include "helpers.hpp"
+#include "sip_optimal_control.hpp"
 
 using namespace sip::optimal_control;
 
@@ -533,6 +534,119 @@ static void test_memory_sizes() {  // :226-263, and the values themselves
   CHECK(out.mem_assign(E, small.data()) == LQR::Output::num_bytes(E));
 }
 
+// The model_callback lambda of sip_optimal_control.cpp:13-127 (evaluate_model) against the
+// reference's own loops restated here, on the sibling-edges structure with theta.
+static void test_model_evaluation() {
+  const BranchTopology bt;
+  const std::array<int, 3> state_dims = {2, 1, 3}, node_c = {1, 0, 1}, node_g = {0, 1, 1};
+  const std::array<int, 2> control_dims = {1, 2}, edge_c = {1, 2}, edge_g = {2, 1};
+  const int p = 2;
+  const std::array<double, 2> x_init = {0.25, -0.5};
+  int calls = 0;
+  Input input{
+      .dimensions = {p, state_dims.data(), control_dims.data(), node_c.data(), node_g.data(),
+                     edge_c.data(), edge_g.data()},
+      .topology = {2, 0, bt.parent.data(), bt.child.data()},
+      .initial_state = x_init.data(),
+      .model_callback = {},
+      .timeout_callback = []() { return false; },
+  };
+  // values that depend on the views, so that wrong view pointers show up in the result
+  input.model_callback = [&](const ModelCallbackInput &in, ModelCallbackOutput &out) {
+    ++calls;
+    const Dimensions &d = input.dimensions;
+    for (int node = 0; node < 3; ++node) {
+      auto &o = out.nodes[node];
+      const int n = d.get_state_dim(node);
+      o.f = 0.5 + node;
+      for (int i = 0; i < n; ++i) {
+        o.f += in.nodes[node].state[i] * in.nodes[node].state[i];
+        o.df_dx[i] = 2.0 * in.nodes[node].state[i] + 0.01 * node;
+      }
+      for (int i = 0; i < p; ++i) o.df_dtheta[i] = in.theta[i] * (node + 1);
+      for (int i = 0; i < d.get_node_c_dim(node); ++i)
+        o.c[i] = 1.5 * node + i + in.nodes[node].equality_constraint_multipliers[i];
+      for (int i = 0; i < d.get_node_g_dim(node); ++i)
+        o.g[i] = -2.0 * node - i + in.nodes[node].inequality_constraint_multipliers[i];
+    }
+    for (int e = 0; e < 2; ++e) {
+      auto &o = out.edges[e];
+      const int np = d.get_state_dim(in.edges[e].parent), nc = d.get_state_dim(in.edges[e].child);
+      o.f = 0.125 * (e + 1);
+      for (int i = 0; i < np; ++i) o.df_dx[i] = 0.3 * in.edges[e].parent_state[i] - e;
+      for (int i = 0; i < d.get_control_dim(e); ++i) {
+        o.f += in.edges[e].control[i];
+        o.df_du[i] = 1.0 + 0.5 * in.edges[e].control[i];
+      }
+      for (int i = 0; i < p; ++i) o.df_dtheta[i] = -in.theta[i] * (e + 2);
+      for (int i = 0; i < nc; ++i)
+        o.dyn_res[i] = in.edges[e].child_state[i] - 0.9 * in.edges[e].costate[i];
+      for (int i = 0; i < d.get_edge_c_dim(e); ++i)
+        o.c[i] = 7.0 + e + i + in.edges[e].equality_constraint_multipliers[i];
+      for (int i = 0; i < d.get_edge_g_dim(e); ++i)
+        o.g[i] = -7.0 - e - i + in.edges[e].inequality_constraint_multipliers[i];
+    }
+  };
+  Workspace workspace;
+  workspace.reserve(input.dimensions, input.topology);
+  CallbackProvider provider(input, workspace);
+  std::vector<double> x(workspace.x_dim), y(workspace.y_dim), z(workspace.z_dim);
+  fill_sequence(x.data(), workspace.x_dim, 0.07);
+  fill_sequence(y.data(), workspace.y_dim, -0.03);
+  fill_sequence(z.data(), workspace.z_dim, 0.011);
+  std::fill_n(workspace.gradient_f, workspace.x_dim, -1.0);
+  std::fill_n(workspace.c, workspace.y_dim, -1.0);
+  std::fill_n(workspace.g, workspace.z_dim, -1.0);
+  CHECK(evaluate_model(input, workspace, {x.data(), y.data(), z.data(), true}) == 0);
+  CHECK(calls == 1);
+
+  // sip_optimal_control.cpp:44-123 on the same callback output
+  const Dimensions &d = input.dimensions;
+  const Topology &t = input.topology;
+  const auto &mco = workspace.model_callback_output;
+  double f = 0.0;
+  for (int node = 0; node < 3; ++node) f += mco.nodes[node].f;
+  for (int e = 0; e < 2; ++e) f += mco.edges[e].f;
+  std::vector<double> grad(workspace.x_dim, 0.0), c(workspace.y_dim, 0.0), g(workspace.z_dim, 0.0);
+  for (int node = 0; node < 3; ++node) {
+    for (int r = 0; r < d.get_state_dim(node); ++r)
+      grad[workspace.x_state_offsets[node] + r] += mco.nodes[node].df_dx[r];
+    for (int r = 0; r < p; ++r) grad[workspace.stagewise_x_dim + r] += mco.nodes[node].df_dtheta[r];
+  }
+  for (int e = 0; e < 2; ++e) {
+    const int parent = t.edge_parents[e];
+    for (int r = 0; r < d.get_state_dim(parent); ++r)
+      grad[workspace.x_state_offsets[parent] + r] += mco.edges[e].df_dx[r];
+    for (int r = 0; r < d.get_control_dim(e); ++r)
+      grad[workspace.x_control_offsets[e] + r] += mco.edges[e].df_du[r];
+    for (int r = 0; r < p; ++r) grad[workspace.stagewise_x_dim + r] += mco.edges[e].df_dtheta[r];
+  }
+  for (int r = 0; r < d.get_state_dim(t.root); ++r)
+    c[workspace.y_dyn_offsets[t.root] + r] = x_init[r] - x[workspace.x_state_offsets[t.root] + r];
+  for (int node = 0; node < 3; ++node)
+    std::copy_n(mco.nodes[node].c, d.get_node_c_dim(node), c.data() + workspace.y_node_c_offsets[node]);
+  for (int e = 0; e < 2; ++e) {
+    const int child = t.edge_children[e];
+    std::copy_n(mco.edges[e].dyn_res, d.get_state_dim(child), c.data() + workspace.y_dyn_offsets[child]);
+    std::copy_n(mco.edges[e].c, d.get_edge_c_dim(e), c.data() + workspace.y_edge_c_offsets[e]);
+  }
+  for (int node = 0; node < 3; ++node)
+    std::copy_n(mco.nodes[node].g, d.get_node_g_dim(node), g.data() + workspace.z_node_offsets[node]);
+  for (int e = 0; e < 2; ++e)
+    std::copy_n(mco.edges[e].g, d.get_edge_g_dim(e), g.data() + workspace.z_edge_offsets[e]);
+
+  CHECK(workspace.f == f);
+  CHECK(std::equal(grad.begin(), grad.end(), workspace.gradient_f));
+  CHECK(std::equal(c.begin(), c.end(), workspace.c));
+  CHECK(std::equal(g.begin(), g.end(), workspace.g));
+  // new_x == false: only the objective is refreshed (sip_optimal_control.cpp:52)
+  workspace.gradient_f[0] = 123.0;
+  workspace.f = 0.0;
+  CHECK(evaluate_model(input, workspace, {x.data(), y.data(), z.data(), false}) == 0);
+  CHECK(workspace.f == f && workspace.gradient_f[0] == 123.0);
+  workspace.free(input.topology);
+}
+
 int main() {
   const std::pair<const char *, std::function<void()>> tests[] = {
       {"LQRFactor status API", test_factor_status_api},
@@ -542,6 +656,7 @@ int main() {
       {"CallbackProvider KKT cases", test_callback_provider},
       {"InputValidation + structure allocation modes", test_input_validation},
       {"Workspace memory sizes (static == dynamic == reference values)", test_memory_sizes},
+      {"Model evaluation scatter (sip_optimal_control.cpp:13-127)", test_model_evaluation},
   };
   for (const auto &t : tests) {
     const int before = g_failures;

@@ -262,3 +262,43 @@ class CallbackProvider:
         e._check(lib.sipoc_kkt_apply_host(e._handle, *[_host_ptr(a) for a in arrs],
                                           _host_ptr(y)))
         return y
+
+    # -- model-callback scatter (sip_optimal_control.cpp:13-127) -----------------------
+    @property
+    def model_value_sizes(self) -> dict:
+        z = _capi.ModelValueSizes()
+        self.engine._check(lib.sipoc_model_value_sizes(self.engine._handle, ctypes.byref(z)))
+        return {k: int(getattr(z, k)) for k in _capi.MODEL_VALUE_FIELDS}
+
+    def model_callback_scatter(self, values: dict, x, initial_state, new_x: bool = True,
+                               stream=None) -> dict:
+        """f, gradient_f, c, g of one model evaluation from its node / edge values (device
+        tensors in the engine layout, ``engine.pack`` of [batch, size] arrays)."""
+        e, keep = self.engine, []
+        v = _capi.ModelValues()
+        _fill(v, _capi.MODEL_VALUE_FIELDS, values, False, keep)
+        sz = self.sizes
+        out = dict(f=e.empty(1), gradient_f=e.empty(sz["x_dim"]), c=e.empty(sz["y_dim"]),
+                   g=e.empty(sz["z_dim"]))
+        e._check(lib.sipoc_model_scatter(
+            e._handle, ctypes.byref(v), x.data_ptr(), initial_state.data_ptr(), int(new_x),
+            out["f"].data_ptr(), out["gradient_f"].data_ptr(), out["c"].data_ptr(),
+            out["g"].data_ptr(), e.stream_ptr(stream)))
+        return out
+
+    def model_callback_scatter_host(self, values: dict, x, initial_state,
+                                    new_x: bool = True) -> dict:
+        """The same through host buffers ([batch, size] numpy arrays), synchronous."""
+        e, keep = self.engine, []
+        v = _capi.ModelValues()
+        _fill(v, _capi.MODEL_VALUE_FIELDS, values, True, keep)
+        sz = self.sizes
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        x0 = np.ascontiguousarray(initial_state, dtype=np.float64)
+        out = dict(f=np.zeros(self.batch), gradient_f=np.zeros((self.batch, sz["x_dim"])),
+                   c=np.zeros((self.batch, sz["y_dim"])), g=np.zeros((self.batch, sz["z_dim"])))
+        ptr = lambda a: _host_ptr(a if a.size else np.zeros(1))
+        e._check(lib.sipoc_model_scatter_host(
+            e._handle, ctypes.byref(v), _host_ptr(x), _host_ptr(x0), int(new_x),
+            _host_ptr(out["f"]), ptr(out["gradient_f"]), ptr(out["c"]), ptr(out["g"])))
+        return out
