@@ -573,11 +573,11 @@ def run_kkt(args):
                           force_generic=getattr(args, "force_generic", False),
                           pad_variable_dims=getattr(args, "pad_variable_dims", False))
     eng = cp.engine
-    # The shape-specialised LQR kernels reorder the arithmetic; they stay within 1e-9 of the
-    # reference order for r2 <= 1e3 (tests/test_gpu_kkt.py), so the uniform workload uses
-    # that range; the variable-dimension workload runs the strict-order generic kernels on
-    # the reference's full range.
-    r2_max = 1e3 if uniform else 1e9
+    # The reference benchmark's full regularization range (newton_kkt_benchmark.cpp:231-233) on
+    # both workloads: the rollout of the shape-specialised kernels applies (I + D V)^-1 in the
+    # reference's F-solve form, so the default path holds 1e-9 against the oracle up to
+    # r2 = 1e9 (tests/test_gpu_kkt.py::test_newton_kkt_benchmark_shapes).
+    r2_max = 1e9
     model_h, w_h, r1_h, r2_h, r3_h, b_h = kkt_host_problem(dims, batch, args.seed, r2_max)
     model = cp.pack_model(model_h)
     w, r1, r2, r3, b = (eng.pack(a) for a in (w_h, r1_h, r2_h, r3_h, b_h))

@@ -176,7 +176,13 @@ sipoc_error sipoc_profile_get(const sipoc_engine *engine, int index, const char 
  * eagerly once first (workspaces are sized on first use, which may not happen
  * under capture); `stream` must be a non-default stream; the arrays the recorded
  * calls were given must stay allocated, their contents may change between
- * launches.  sipoc_graph_launch adds the recorded kernels to sipoc_launch_count. */
+ * launches.  sipoc_graph_launch adds the recorded kernels to sipoc_launch_count.
+ * While recording nothing executes: the handle's "a factorization exists" state is what it
+ * was at sipoc_graph_begin again after sipoc_graph_end, and a call that would have to
+ * allocate a workspace fails with SIPOC_INVALID_ARGUMENT (and a message saying so) instead
+ * of breaking the capture.  A graph belongs to the handle it was recorded on (its kernels
+ * point into that handle's workspaces): sipoc_destroy(engine) invalidates the engine's
+ * graphs -- destroy them first, or at least never launch them afterwards. */
 typedef struct sipoc_graph sipoc_graph;
 sipoc_error sipoc_graph_begin(sipoc_engine *engine, void *stream);
 sipoc_error sipoc_graph_end(sipoc_engine *engine, void *stream, sipoc_graph **out);

@@ -39,6 +39,13 @@ struct sipoc_engine {
   int64_t launches = 0;
   bool capturing = false;          // between sipoc_graph_begin and sipoc_graph_end
   int64_t capture_launches0 = 0;
+  // What a capture must not change: nothing runs while recording, so the "a factorization
+  // exists" flags are put back at sipoc_graph_end.
+  struct CaptureSaved {
+    int factored = 0;
+    bool kkt_factored = false, host_lqr_factored = false;
+  } capture_saved;
+  std::vector<struct sipoc_graph *> graphs;  // live graphs recorded on this handle
   Profiler prof;
   cudaStream_t host_stream = nullptr;
 
@@ -64,6 +71,9 @@ struct sipoc_engine {
   bool kws_ready = false;
   int *kkt_lqr_status = nullptr;
   bool kkt_factored = false;
+  // The padded / problem-major copies of A, B, delta were made by kkt_factor from the model
+  // it was given (so kkt_solve may skip refreshing them); any other solve overwrites them.
+  bool kept_copies_are_kkt = false;
   double *kkt_product = nullptr;  // K * sol scratch of sipoc_kkt_residual
   // theta (Schur) layer (lazy): J and K_s^-1 J [kkt_dim x p], the factor of S [p x p], p scratch
   double *theta_J = nullptr, *theta_KinvJ = nullptr, *theta_S = nullptr, *theta_t = nullptr;
@@ -131,6 +141,10 @@ struct DeviceGuard {
 sipoc_error dev_alloc(sipoc_engine *e, void **out, size_t bytes) {
   *out = nullptr;
   if (bytes == 0) bytes = 16;
+  if (e->capturing)  // cudaMalloc would invalidate the capture (thread-local mode)
+    return fail(e, SIPOC_INVALID_ARGUMENT,
+                "a workspace would be allocated while a graph is being recorded: run the same "
+                "sequence of calls eagerly once before sipoc_graph_begin");
   SIPOC_CUDA(e, cudaMalloc(out, bytes));
   e->allocations.push_back(*out);
   return SIPOC_OK;
@@ -422,7 +436,9 @@ sipoc_error lqr_solve_core(sipoc_engine *e, const LqrIn &caller_in, const LqrOut
   if (e->factored == sipoc_engine::Factored::FAST && !aligned16(caller_in))
     return fail(e, SIPOC_INVALID_ARGUMENT,
                 "solve against a fast-path factorization needs 16-byte aligned arrays");
+  if (matrices_kept && !e->kept_copies_are_kkt) matrices_kept = false;  // refresh them
   const unsigned mask = matrices_kept ? kPmVectors : kPmSolve;
+  if (!matrices_kept) e->kept_copies_are_kkt = false;
   LqrIn in, pm;
   if ((rc = resolve_inputs(e, caller_in, layout_pm, mask, &in, &pm, s)) != SIPOC_OK) return rc;
   if (e->factored == sipoc_engine::Factored::FAST) {
@@ -742,6 +758,8 @@ sipoc_error kkt_factor_core(sipoc_engine *e, const KktModel &mdl, const KktTheta
   launch_kkt_finish_factor(e->kkt_lqr_status, ok, e->batch, s);
   e->launches += 1;
   e->kkt_factored = true;
+  e->kept_copies_are_kkt = true;
+  e->host_lqr_factored = false;  // the factorization sipoc_lqr_solve_host would read is gone
   if ((rc = check_launch(e, "kkt_finish_factor")) != SIPOC_OK) return rc;
   const int p = e->hs.theta_dim;
   if (p == 0) return SIPOC_OK;
@@ -1002,11 +1020,14 @@ sipoc_error sipoc_create(const sipoc_structure *s, sipoc_engine **out) {
   return SIPOC_OK;
 }
 
+void invalidate_graph(struct sipoc_graph *g);  // below, with the graph type
+
 void sipoc_destroy(sipoc_engine *e) {
   if (e == nullptr) return;
   {
     DeviceGuard guard(e->device);
     cudaDeviceSynchronize();
+    for (sipoc_graph *g : e->graphs) invalidate_graph(g);
     for (void *p : e->allocations) cudaFree(p);
     if (e->host_stream != nullptr) cudaStreamDestroy(e->host_stream);
   }
@@ -1031,7 +1052,16 @@ struct sipoc_graph {
   cudaGraphExec_t exec = nullptr;
   int device = 0;
   int64_t launches = 0;  // engine kernels inside one launch of the graph
+  // The kernels of the graph point into this handle's workspaces: sipoc_destroy(owner)
+  // invalidates the graph (exec destroyed, owner cleared) instead of leaving it dangling.
+  sipoc_engine *owner = nullptr;
 };
+
+void invalidate_graph(sipoc_graph *g) {  // its engine is going away
+  if (g->exec != nullptr) cudaGraphExecDestroy(g->exec);
+  g->exec = nullptr;
+  g->owner = nullptr;
+}
 
 sipoc_error sipoc_graph_begin(sipoc_engine *e, void *stream) {
   if (e == nullptr) return SIPOC_INVALID_ARGUMENT;
@@ -1044,6 +1074,7 @@ sipoc_error sipoc_graph_begin(sipoc_engine *e, void *stream) {
                                        cudaStreamCaptureModeThreadLocal));
   e->capturing = true;
   e->capture_launches0 = e->launches;
+  e->capture_saved = {static_cast<int>(e->factored), e->kkt_factored, e->host_lqr_factored};
   return SIPOC_OK;
 }
 
@@ -1053,6 +1084,9 @@ sipoc_error sipoc_graph_end(sipoc_engine *e, void *stream, sipoc_graph **out) {
   if (!e->capturing) return fail(e, SIPOC_INVALID_ARGUMENT, "sipoc_graph_end: not capturing");
   DeviceGuard guard(e->device);
   e->capturing = false;
+  e->factored = static_cast<sipoc_engine::Factored>(e->capture_saved.factored);
+  e->kkt_factored = e->capture_saved.kkt_factored;
+  e->host_lqr_factored = e->capture_saved.host_lqr_factored;
   cudaGraph_t graph = nullptr;
   SIPOC_CUDA(e, cudaStreamEndCapture(static_cast<cudaStream_t>(stream), &graph));
   cudaGraphExec_t exec = nullptr;
@@ -1065,14 +1099,16 @@ sipoc_error sipoc_graph_end(sipoc_engine *e, void *stream, sipoc_graph **out) {
   g->exec = exec;
   g->device = e->device;
   g->launches = e->launches - e->capture_launches0;
+  g->owner = e;
+  e->graphs.push_back(g);
   *out = g;
   return SIPOC_OK;
 }
 
 sipoc_error sipoc_graph_launch(sipoc_engine *e, sipoc_graph *g, void *stream) {
   if (e == nullptr || g == nullptr || g->exec == nullptr) return SIPOC_INVALID_ARGUMENT;
-  if (g->device != e->device)
-    return fail(e, SIPOC_INVALID_ARGUMENT, "sipoc_graph_launch: graph of another device");
+  if (g->owner != e)
+    return fail(e, SIPOC_INVALID_ARGUMENT, "sipoc_graph_launch: graph recorded on another handle");
   DeviceGuard guard(e->device);
   SIPOC_CUDA(e, cudaGraphLaunch(g->exec, static_cast<cudaStream_t>(stream)));
   e->launches += g->launches;
@@ -1083,6 +1119,10 @@ int64_t sipoc_graph_kernel_count(const sipoc_graph *g) { return g == nullptr ? 0
 
 void sipoc_graph_destroy(sipoc_graph *g) {
   if (g == nullptr) return;
+  if (g->owner != nullptr) {
+    auto &live = g->owner->graphs;
+    live.erase(std::remove(live.begin(), live.end(), g), live.end());
+  }
   if (g->exec != nullptr) {
     DeviceGuard guard(g->device);
     cudaGraphExecDestroy(g->exec);
