@@ -251,12 +251,18 @@ def run_reference(args, wl, name):
 
 
 # --------------------------------------------------------------------------
-def load_traffic(variant, name):
-    """Per-launch DRAM traffic of the dominant kernel from the committed ncu capture."""
+def load_traffic(name, kernels, batch):
+    """DRAM traffic (dram__bytes_read + dram__bytes_write) of the hot-path kernels of one step
+    on this rank, from the committed ncu captures: profiles/traffic.json holds bytes per
+    problem for every kernel of a workload; the kernels that ran this step are summed."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         with open(path) as f:
-            return json.load(f).get(name, {}).get(variant)
+            per_problem = json.load(f).get(name, {})
+        known = [per_problem[k] for k in kernels if k in per_problem]
+        if not known or len(known) < sum(1 for k in kernels if k != "status_stats_kernel"):
+            return None
+        return float(sum(known)) * batch
     except Exception:
         return None
 
@@ -306,7 +312,8 @@ def run_ours(args, wl, name):
     sampler = ClockSampler(local_rank) if rank == 0 else None
 
     lqr = LQR(Dimensions.uniform(T, n, m), Topology.chain(T), batch, device=local_rank,
-              force_generic=args.force_generic)
+              force_generic=args.force_generic,
+              parallel_in_time=False if args.serial_in_time else None)
     eng = lqr.engine
     inp = lqr.generate_benchmark(seed=args.seed, problem_offset=first)
     out = lqr.alloc_output()
@@ -458,7 +465,7 @@ def run_ours(args, wl, name):
                     "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS}
         roof.update({
             "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs; FP64 = DFMA microbench)",
-            "traffic": load_traffic(eng.kernel_variant, name),
+            "traffic": load_traffic(name, hot, batch),
             "algorithmic_bytes_per_solve": inb + outb,
             "algorithmic_flops_per_solve": flops,
             "basis": "algorithmic bytes of one factor+solve x problems per step / device time of "
@@ -680,6 +687,9 @@ def main():
     ap.add_argument("--graph", action="store_true",
                     help="newton_kkt workloads: replay the step as one CUDA graph "
                          "(CallbackProvider.capture_step) instead of launching its kernels eagerly")
+    ap.add_argument("--serial-in-time", action="store_true",
+                    help="long-horizon workloads: forbid the parallel-in-time scan "
+                         "(SIPOC_FLAG_SERIAL_IN_TIME), i.e. time the serial sweep + rollout")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--e2e-batch", type=int, default=0,
