@@ -341,8 +341,20 @@ def run_ours(args, wl, name):
             inp_pm[k] = dst
         torch.cuda.synchronize(dev)
 
+    inp32 = out32 = None
+    if args.fp32:
+        # Optional FP32 mode (north_star; sipoc_lqr_factor_solve_f32): every array in single
+        # precision, narrowed once outside the timed region.  Reported as its own line
+        # (dtype f32, the algorithmic bytes halve), never mixed with the FP64 numbers.
+        if not lqr.f32_supported:
+            raise SystemExit("--fp32: the FP32 mode covers uniform chains with n = 4, m = 1..4 "
+                             "(workload cartpole)")
+        inp32, out32 = lqr.narrow_f32(inp), lqr.alloc_output_f32()
+
     def step():
-        if inp_pm is not None:
+        if inp32 is not None:
+            lqr.factor_solve_f32(inp32, out32, status=status, stream=stream)
+        elif inp_pm is not None:
             lqr.factor_solve_pm(inp_pm, out, status=status, stream=stream)
         else:
             lqr.factor_solve(inp, out, status=status, stream=stream)
@@ -391,6 +403,11 @@ def run_ours(args, wl, name):
     value = total_batch / (ms_per_step * 1e-3)
 
     # correctness outside the timed region: KKT residual of every problem
+    if inp32 is not None:
+        # FP32 mode: the residual of the single-precision solution, evaluated in FP64 against
+        # the float-rounded problem it solved
+        inp = {k: v.double() for k, v in inp32.items()}
+        out = {k: v.double() for k, v in out32.items()}
     norms, rstats = lqr.residual(inp, out, status)  # (all-reduced inside the call too)
     max_residual = float(rstats[1].item())
 
@@ -399,7 +416,7 @@ def run_ours(args, wl, name):
     # host inputs); --e2e-batch caps the call size.  The call is PCIe-bound (189 KB cross
     # the bus per problem).
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and not args.fp32:
         hb = min(batch, args.e2e_batch) if args.e2e_batch > 0 else batch
         lqr_h = lqr if hb == batch else LQR(Dimensions.uniform(T, n, m), Topology.chain(T), hb,
                                             device=local_rank, force_generic=args.force_generic)
@@ -445,6 +462,8 @@ def run_ours(args, wl, name):
         sampler.stop()
         clocks = sampler.summary(t0, t1)
         inb, outb = algorithmic_bytes(n, m, T)
+        if args.fp32:
+            inb, outb = inb // 2, outb // 2  # the same element counts, four bytes each
         flops = algorithmic_flops(n, m, T)
         peak, peak_kind = measured_peaks()
         hot = {k: v for k, v in kernels.items() if k != "status_stats_kernel"}
@@ -476,10 +495,12 @@ def run_ours(args, wl, name):
             "kernels": kernels,
         })
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+            "metric": METRIC.replace("FP64", "FP32 mode, reported separately") if args.fp32
+            else METRIC,
+            "value": value, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
+            "dtype": "f32" if args.fp32 else "f64", "data": "synthetic",
             "config": {"workload": name, "n": n, "m": m, "T": T, "batch_per_gpu": batch,
                        "global_batch": total_batch, "parallelism": f"batch-sharded x{world}",
                        "kernel_variant": eng.kernel_variant, "input_layout": args.input_layout,
@@ -687,6 +708,9 @@ def main():
     ap.add_argument("--graph", action="store_true",
                     help="newton_kkt workloads: replay the step as one CUDA graph "
                          "(CallbackProvider.capture_step) instead of launching its kernels eagerly")
+    ap.add_argument("--fp32", action="store_true",
+                    help="the optional FP32 mode (sipoc_lqr_factor_solve_f32; workload cartpole): "
+                         "a separate line with dtype f32, tolerance 5e-4 against the FP64 oracle")
     ap.add_argument("--serial-in-time", action="store_true",
                     help="long-horizon workloads: forbid the parallel-in-time scan "
                          "(SIPOC_FLAG_SERIAL_IN_TIME), i.e. time the serial sweep + rollout")

@@ -345,6 +345,31 @@ sipoc_error sipoc_kkt_residual(sipoc_engine *engine, const sipoc_kkt_model *mode
                                const double *r3, const double *sol, const double *b,
                                const int *ok, double *residual_norm, double *stats,
                                void *stream);
+/* ---- optional FP32 mode ----------------------------------------------------------------
+ * north_star: "an optional FP32 mode is reported separately with its own stated tolerance".
+ * Factor + solve (LQR::factor + LQR::solve, lqr.hpp:192-194) entirely in single precision:
+ * every array is float in the engine layout X[flat * batch_stride + problem].  Covered:
+ * uniform chains with state dimension 4 and 1..4 controls (the cartpole row of the
+ * reference benchmark grid, lqr_benchmark.cpp:537-545) -- sipoc_f32_supported tells.
+ * Stated tolerance: 5e-4 relative on (x, u, y) against the FP64 oracle run on the same
+ * (float-rounded) inputs, on the benchmark distribution (delta in [1e-3, 0.101]); the same
+ * per-problem FactorStatus values as the FP64 path.  The kept factorization is private to the
+ * call (no separate solve).  sipoc_lqr_factor_solve_thread_f64 runs the SAME kernels
+ * instantiated on double: their numerical control, held to the FP64 tolerance by the tests. */
+typedef struct sipoc_lqr_input_f32 {
+  const float *Q, *M, *R, *q, *r, *A, *B, *c, *delta;
+} sipoc_lqr_input_f32;
+typedef struct sipoc_lqr_output_f32 {
+  float *x, *u, *y;
+} sipoc_lqr_output_f32;
+int sipoc_f32_supported(const sipoc_engine *engine);
+sipoc_error sipoc_lqr_factor_solve_f32(sipoc_engine *engine, const sipoc_lqr_input_f32 *in,
+                                       const sipoc_lqr_output_f32 *out, int *status,
+                                       void *stream);
+sipoc_error sipoc_lqr_factor_solve_thread_f64(sipoc_engine *engine, const sipoc_lqr_input *in,
+                                              const sipoc_lqr_output *out, int *status,
+                                              void *stream);
+
 /* ---- model-callback scatter ----------------------------------------------------------
  * The model_callback lambda of sip_optimal_control.cpp:13-127, after the user's callback has
  * produced the node / edge values of one evaluation: objective f = sum of the node and edge

@@ -16,6 +16,7 @@
 #include "kkt_theta.cuh"
 #include "scan.cuh"
 #include "model_scatter.cuh"
+#include "riccati_f32.cuh"
 #include "profile.hpp"
 #include "riccati_fast.cuh"
 #include "structure.hpp"
@@ -96,6 +97,10 @@ struct sipoc_engine {
   // model-callback scatter, host-buffer variant: values, x, x0 | f, gradient_f, c, g
   double *hm_vals[12] = {}, *hm_x = nullptr, *hm_x0 = nullptr, *hm_out[4] = {};
   bool host_scatter_ready = false;
+  // Optional FP32 mode (riccati_f32.cu): kept factorization + spill in single precision, and
+  // the double instantiation of the same kernels (numerical control)
+  float *f32_store = nullptr;
+  double *f64t_store = nullptr;
 
   // Parallel-in-time factor + solve (scan.cu): long uniform chains, small batches.
   struct Scan {
@@ -1785,6 +1790,64 @@ sipoc_error sipoc_model_scatter_host(sipoc_engine *e, const sipoc_model_values *
     if ((rc = download(e, e->hm_out[i], dst[i], out_sizes[i])) != SIPOC_OK) return rc;
   SIPOC_CUDA(e, cudaStreamSynchronize(e->host_stream));
   return SIPOC_OK;
+}
+
+}  // extern "C"
+
+// ---- optional FP32 mode (riccati_f32.cu) ---------------------------------------------
+extern "C" {
+
+int sipoc_f32_supported(const sipoc_engine *e) {
+  if (e == nullptr) return 0;
+  const HostStructure &h = e->hs;
+  return h.is_chain && h.is_uniform && h.E > 0 && f32_supports(h.n[0], h.m[0]) ? 1 : 0;
+}
+
+sipoc_error sipoc_lqr_factor_solve_f32(sipoc_engine *e, const sipoc_lqr_input_f32 *in,
+                                       const sipoc_lqr_output_f32 *out, int *status,
+                                       void *stream) {
+  if (e == nullptr || in == nullptr || out == nullptr) return SIPOC_INVALID_ARGUMENT;
+  if (!sipoc_f32_supported(e))
+    return fail(e, SIPOC_UNSUPPORTED,
+                "the FP32 mode covers uniform chains with state dimension 4 and 1..4 controls");
+  if (!in->Q || !in->M || !in->R || !in->q || !in->r || !in->A || !in->B || !in->c || !in->delta ||
+      !out->x || !out->u || !out->y)
+    return fail(e, SIPOC_INVALID_ARGUMENT, "sipoc_lqr_factor_solve_f32: NULL array");
+  DeviceGuard guard(e->device);
+  const HostStructure &h = e->hs;
+  sipoc_error rc;
+  if (e->f32_store == nullptr &&
+      (rc = dev_alloc(e, reinterpret_cast<void **>(&e->f32_store),
+                      static_cast<size_t>(f32_store_elems(h.n[0], h.m[0], h.E)) * e->ld *
+                          sizeof(float))) != SIPOC_OK)
+    return rc;
+  const LqrInT<float> i{in->Q, in->M, in->R, in->q, in->r, in->A, in->B, in->c, in->delta};
+  const LqrOutT<float> o{out->x, out->u, out->y};
+  e->launches += launch_lqr_factor_solve_f32(h.n[0], h.m[0], i, o, status, e->f32_store, e->batch,
+                                             e->ld, h.E, &e->prof,
+                                             static_cast<cudaStream_t>(stream));
+  return check_launch(e, "lqr_factor_solve_f32");
+}
+
+sipoc_error sipoc_lqr_factor_solve_thread_f64(sipoc_engine *e, const sipoc_lqr_input *in,
+                                              const sipoc_lqr_output *out, int *status,
+                                              void *stream) {
+  if (e == nullptr || in == nullptr || out == nullptr) return SIPOC_INVALID_ARGUMENT;
+  if (!sipoc_f32_supported(e))
+    return fail(e, SIPOC_UNSUPPORTED,
+                "the FP32 mode covers uniform chains with state dimension 4 and 1..4 controls");
+  DeviceGuard guard(e->device);
+  const HostStructure &h = e->hs;
+  sipoc_error rc;
+  if (e->f64t_store == nullptr &&
+      (rc = alloc_doubles(e, &e->f64t_store, f32_store_elems(h.n[0], h.m[0], h.E))) != SIPOC_OK)
+    return rc;
+  const LqrInT<double> i{in->Q, in->M, in->R, in->q, in->r, in->A, in->B, in->c, in->delta};
+  const LqrOutT<double> o{out->x, out->u, out->y};
+  e->launches += launch_lqr_factor_solve_thread_f64(h.n[0], h.m[0], i, o, status, e->f64t_store,
+                                                    e->batch, e->ld, h.E, &e->prof,
+                                                    static_cast<cudaStream_t>(stream));
+  return check_launch(e, "lqr_factor_solve_thread_f64");
 }
 
 }  // extern "C"

@@ -386,6 +386,40 @@ class LQR:
                                             status.data_ptr(), e.stream_ptr(stream)))
         return status
 
+    # -- optional FP32 mode (sipoc_lqr_factor_solve_f32; include/sipoc.h) -------------------
+    @property
+    def f32_supported(self) -> bool:
+        return bool(lib.sipoc_f32_supported(self.engine._handle))
+
+    def narrow_f32(self, arrays: dict) -> dict:
+        """Engine-layout float64 device tensors -> float32 copies (plumbing, not timed)."""
+        torch = self.engine._torch()
+        return {k: v.to(torch.float32).contiguous() for k, v in arrays.items()}
+
+    def alloc_output_f32(self) -> dict:
+        e, sz = self.engine, self.engine.lqr_sizes
+        torch = e._torch()
+        return {k: e.empty(sz[k], dtype=torch.float32) for k in _capi.LQR_OUTPUT_FIELDS}
+
+    def factor_solve_f32(self, inp32: dict, out32: dict, status=None, stream=None):
+        """Factor + solve in single precision; every tensor float32 in the engine layout."""
+        e = self.engine
+        status = e.empty_int() if status is None else status
+        si, so = _lqr_input_struct(inp32), _lqr_output_struct(out32)
+        e._check(lib.sipoc_lqr_factor_solve_f32(e._handle, ctypes.byref(si), ctypes.byref(so),
+                                                status.data_ptr(), e.stream_ptr(stream)))
+        return status
+
+    def factor_solve_thread_f64(self, inp: dict, out: dict, status=None, stream=None):
+        """The FP32 mode's kernels instantiated on double (their numerical control)."""
+        e = self.engine
+        status = e.empty_int() if status is None else status
+        si, so = _lqr_input_struct(inp), _lqr_output_struct(out)
+        e._check(lib.sipoc_lqr_factor_solve_thread_f64(
+            e._handle, ctypes.byref(si), ctypes.byref(so), status.data_ptr(),
+            e.stream_ptr(stream)))
+        return status
+
     # Problem-major device inputs (sipoc_lqr_*_pm): ``inp`` holds CUDA tensors laid out
     # [problem][flat] -- `problem_major_input` uploads host arrays that way.  Outputs stay
     # in the engine layout.
