@@ -41,6 +41,7 @@
 // Kernel 1 stages edge k - 1 with cp.async while edge k is absorbed.
 #include "scan.cuh"
 
+#include <cstddef>
 #include <cstdio>
 
 namespace sipoc {
@@ -238,6 +239,22 @@ struct ScanSmem {
   __device__ __forceinline__ double *XA() { return C1; }
   __device__ __forceinline__ double *T() { return CiA; }
 };
+// Elements move between global memory and a slot as one run of kElem doubles starting at
+// A2 / A1, and the sweeps use v0..v3 as one 4 N buffer: the members must be contiguous.
+template <int N>
+constexpr bool scan_smem_layout_ok() {
+  using S = ScanSmem<N>;
+  constexpr size_t d = sizeof(double), NN = N * N;
+  return offsetof(S, C2) == offsetof(S, A2) + NN * d && offsetof(S, J2) == offsetof(S, C2) + NN * d &&
+         offsetof(S, b2) == offsetof(S, J2) + NN * d && offsetof(S, e2) == offsetof(S, b2) + N * d &&
+         offsetof(S, A1) == offsetof(S, e2) + N * d && offsetof(S, C1) == offsetof(S, A1) + NN * d &&
+         offsetof(S, J1) == offsetof(S, C1) + NN * d && offsetof(S, b1) == offsetof(S, J1) + NN * d &&
+         offsetof(S, e1) == offsetof(S, b1) + N * d && offsetof(S, v1) == offsetof(S, v0) + N * d &&
+         offsetof(S, v2) == offsetof(S, v1) + N * d && offsetof(S, v3) == offsetof(S, v2) + N * d &&
+         sizeof(S) % 16 == 0 && offsetof(S, v0) % 16 == 0 && offsetof(S, small) % 16 == 0;
+}
+static_assert(scan_smem_layout_ok<6>() && scan_smem_layout_ok<8>() && scan_smem_layout_ok<12>(),
+              "ScanSmem members are addressed as contiguous runs");
 
 // acc (2) <- combine(incoming (1), acc (2)).  Returns false if a factorization failed.
 // HAVE_CI: slot C1 already holds C1^-1 (the edge builder forms it by the Woodbury identity).
