@@ -457,6 +457,34 @@ def run_ours(args, wl, name):
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                "problems_per_call_per_gpu": hb,
                "call": "sipoc_lqr_factor_solve_host (pinned host buffers, problem-major)"}
+        if args.e2e_packed and n < 16:
+            # The same call through sipoc_lqr_factor_solve_host_packed: Q / R as packed lower
+            # triangles, M not sent (the reference benchmark's M is zero, lqr_benchmark.cpp:61-96).
+            # NOT the reference's dense interface: an extra key, never the headline e2e.
+            packed_in = dict(host_in)
+            for k, dim in (("Q", n), ("R", m)):
+                tri = LQR.pack_symmetric(host_in[k], dim)
+                pinned = torch.empty(tri.shape, dtype=torch.float64, pin_memory=True)
+                pinned.numpy()[...] = tri
+                packed_in[k] = pinned.numpy()
+                keep.append(pinned)
+            packed_in["M"] = None
+            res = lqr_h.factor_solve_host_packed(packed_in, host_out)
+            barrier()
+            tp0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                res = lqr_h.factor_solve_host_packed(packed_in, host_out)
+            torch.cuda.synchronize(dev)
+            tp = torch.tensor([time.perf_counter() - tp0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+            assert (res["status"] == 0).all()
+            h2dp = sum(hb * packed_in[k].shape[1] * 8 for k in _capi.LQR_INPUT_FIELDS
+                       if packed_in[k] is not None)
+            e2e["packed"] = {"value": hb * world * e2e_steps / float(tp.item()), "unit": UNIT,
+                             "h2d_bytes_per_step": h2dp, "d2h_bytes_per_step": d2h,
+                             "call": "sipoc_lqr_factor_solve_host_packed (Q, R packed lower "
+                                     "triangles, M = NULL; not the reference's dense interface)"}
 
     if rank == 0:
         sampler.stop()
@@ -718,6 +746,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--e2e-batch", type=int, default=0,
                     help="problems per host-buffer call per GPU (0 = the GPU's whole shard)")
+    ap.add_argument("--e2e-packed", action="store_true",
+                    help="also time sipoc_lqr_factor_solve_host_packed (e2e.packed: Q / R as packed "
+                         "lower triangles, M not sent)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -260,6 +260,16 @@ sipoc_error sipoc_lqr_factor_solve_host(sipoc_engine *engine,
                                         const sipoc_lqr_input *host_in,
                                         const sipoc_lqr_output *host_out,
                                         int *host_status);
+/* The same call for a caller who can hand over less: the host-buffer path is bound by the
+ * bus (177 KB per quadrotor problem), and a third of those bytes are the upper triangles of
+ * the symmetric Q / R blocks and a cross term M that the reference's own benchmark sets to
+ * zero (lqr_benchmark.cpp:61-96).  Here in->Q and in->R hold the PACKED LOWER TRIANGLES of
+ * their blocks (column-major: entry (i, j), i >= j, of an n x n block at j n - j (j - 1) / 2
+ * + (i - j); n (n + 1) / 2 doubles per block), in->M may be NULL (= 0); everything else as in
+ * sipoc_lqr_factor_solve_host.  Uniform dims, plans on the interleaved layout (state
+ * dimension < 16).  Not a reference interface: LQR::Input carries dense blocks. */
+sipoc_error sipoc_lqr_factor_solve_host_packed(sipoc_engine *engine, const sipoc_lqr_input *in,
+                                               const sipoc_lqr_output *out, int *host_status);
 /* factor-once / solve-many on host buffers (BM_LQRSolve semantics,
  * lqr_benchmark.cpp:611-638): factor keeps the inputs and the factorization
  * resident; solve re-reads only q, r, c from host_in. */

@@ -169,6 +169,7 @@ def _load() -> ctypes.CDLL:
     lib.sipoc_kkt_apply.argtypes = [E, KM, P, P, P, P, P, P, P]
     lib.sipoc_kkt_apply_block.argtypes = [E, KM, ctypes.c_int, P, P, P]
     lib.sipoc_kkt_apply_block_host.argtypes = [E, ctypes.c_int, P, P]
+    lib.sipoc_lqr_factor_solve_host_packed.argtypes = [E, LI, LO, P]
     lib.sipoc_f32_supported.argtypes = [E]
     lib.sipoc_f32_supported.restype = ctypes.c_int
     lib.sipoc_lqr_factor_solve_f32.argtypes = [E, LI, LO, P, P]

@@ -101,6 +101,7 @@ struct sipoc_engine {
   // the double instantiation of the same kernels (numerical control)
   float *f32_store = nullptr;
   double *f64t_store = nullptr;
+  double *h_packed = nullptr;  // packed-symmetric host entry: Q / R triangles before expansion
 
   // Parallel-in-time factor + solve (scan.cu): long uniform chains, small batches.
   struct Scan {
@@ -1851,3 +1852,88 @@ sipoc_error sipoc_lqr_factor_solve_thread_f64(sipoc_engine *e, const sipoc_lqr_i
 }
 
 }  // extern "C"
+
+// ---- packed-symmetric host entry ---------------------------------------------------------
+namespace {
+
+// Symmetric n x n blocks from their packed lower triangles, both in the engine layout:
+// dense[(blk n n + j n + i) ld + b] = packed[(blk tri + pk(max(i, j), min(i, j))) ld + b].
+__global__ void __launch_bounds__(128)
+expand_symmetric_kernel(const double *__restrict__ packed, double *__restrict__ dense, int n,
+                        int64_t batch, int64_t ld) {
+  const int64_t b = static_cast<int64_t>(blockIdx.x) * 128 + threadIdx.x;
+  if (b >= batch) return;
+  const int nn = n * n, tri = n * (n + 1) / 2;
+  const int f = blockIdx.y, blk = f / nn, rem = f % nn, i = rem % n, j = rem / n;
+  const int r = i > j ? i : j, c = i > j ? j : i;
+  const size_t src = static_cast<size_t>(blk) * tri + c * n - c * (c - 1) / 2 + (r - c);
+  dense[static_cast<size_t>(f) * ld + b] = __ldcs(packed + src * ld + b);
+}
+
+sipoc_error upload_packed_symmetric(sipoc_engine *e, const double *host, double *dense, int n,
+                                    int blocks) {
+  if (blocks == 0 || n == 0) return SIPOC_OK;
+  const int64_t tri = static_cast<int64_t>(n) * (n + 1) / 2;
+  sipoc_error rc = upload(e, host, e->h_packed, blocks * tri);
+  if (rc != SIPOC_OK) return rc;
+  const dim3 grid(static_cast<unsigned>((e->batch + 127) / 128),
+                  static_cast<unsigned>(blocks * n * n));
+  {
+    ProfScope ps(&e->prof, "expand_symmetric_kernel", e->host_stream);
+    expand_symmetric_kernel<<<grid, 128, 0, e->host_stream>>>(e->h_packed, dense, n, e->batch,
+                                                              e->ld);
+  }
+  e->launches += 1;
+  return check_launch(e, "expand_symmetric");
+}
+
+}  // namespace
+
+extern "C" sipoc_error sipoc_lqr_factor_solve_host_packed(sipoc_engine *e,
+                                                          const sipoc_lqr_input *in,
+                                                          const sipoc_lqr_output *out,
+                                                          int *host_status) {
+  if (e == nullptr || in == nullptr || out == nullptr) return SIPOC_INVALID_ARGUMENT;
+  const HostStructure &h = e->hs;
+  if (!h.is_uniform)
+    return fail(e, SIPOC_UNSUPPORTED, "the packed host entry needs uniform state / control dims");
+  if (host_path_is_pm(e))
+    return fail(e, SIPOC_UNSUPPORTED,
+                "the packed host entry serves the plans on the interleaved layout (state dim < 16)");
+  const int n = h.n[0], m = h.E > 0 ? h.m[0] : 0;
+  if (static_cast<int64_t>(h.N) * n * n > 65535)
+    return fail(e, SIPOC_UNSUPPORTED, "the packed host entry: more than 65 535 dense Q entries");
+  DeviceGuard guard(e->device);
+  sipoc_error rc;
+  if ((rc = ensure_host_lqr(e)) != SIPOC_OK) return rc;
+  const int64_t tq = static_cast<int64_t>(h.N) * n * (n + 1) / 2,
+                tr = static_cast<int64_t>(h.E) * m * (m + 1) / 2;
+  if (e->h_packed == nullptr) {
+    if ((rc = alloc_doubles(e, &e->h_packed, std::max(tq, tr))) != SIPOC_OK) return rc;
+    if ((rc = ensure_stage(e, std::max(tq, tr))) != SIPOC_OK) return rc;
+  }
+  // Q, R: lower triangles over the bus, expanded on the device; M: NULL means zero
+  if ((rc = upload_packed_symmetric(e, in->Q, e->h_in[0], n, h.N)) != SIPOC_OK) return rc;
+  if ((rc = upload_packed_symmetric(e, in->R, e->h_in[2], m, h.E)) != SIPOC_OK) return rc;
+  if (in->M != nullptr) {
+    if ((rc = upload(e, in->M, e->h_in[1], lqr_in_size(h, 1))) != SIPOC_OK) return rc;
+  } else if (lqr_in_size(h, 1) > 0) {
+    SIPOC_CUDA(e, cudaMemsetAsync(e->h_in[1], 0,
+                                  static_cast<size_t>(lqr_in_size(h, 1)) * e->ld * sizeof(double),
+                                  e->host_stream));
+  }
+  const double *rest[9] = {nullptr, nullptr, nullptr, in->q, in->r, in->A, in->B, in->c, in->delta};
+  for (int i = 3; i < 9; ++i)
+    if ((rc = upload(e, rest[i], e->h_in[i], lqr_in_size(h, i))) != SIPOC_OK) return rc;
+  rc = lqr_factor_solve_core(e, host_resident_in(e),
+                             LqrOut{e->h_out[0], e->h_out[1], e->h_out[2]}, e->h_status,
+                             e->host_stream, false);
+  if (rc != SIPOC_OK) return rc;
+  e->host_lqr_factored = false;
+  if ((rc = host_download_out(e, out)) != SIPOC_OK) return rc;
+  if (host_status != nullptr)
+    SIPOC_CUDA(e, cudaMemcpyAsync(host_status, e->h_status, e->batch * sizeof(int),
+                                  cudaMemcpyDeviceToHost, e->host_stream));
+  SIPOC_CUDA(e, cudaStreamSynchronize(e->host_stream));
+  return SIPOC_OK;
+}

@@ -516,6 +516,43 @@ class LQR:
                                                  _host_ptr(status)))
         return dict(x=out["x"], u=out["u"], y=out["y"], status=status)
 
+    @staticmethod
+    def pack_symmetric(blocks: np.ndarray, n: int) -> np.ndarray:
+        """[batch, count n n] dense column-major symmetric blocks -> [batch, count n (n+1)/2]
+        packed lower triangles (the layout sipoc_lqr_factor_solve_host_packed takes)."""
+        if n == 0:
+            return np.zeros((blocks.shape[0], 0))
+        count = blocks.shape[1] // (n * n)
+        idx = np.array([j * n + i for j in range(n) for i in range(j, n)])
+        return np.ascontiguousarray(blocks.reshape(blocks.shape[0], count, n * n)[:, :, idx]
+                                    .reshape(blocks.shape[0], -1))
+
+    def factor_solve_host_packed(self, host: dict, out: Optional[dict] = None) -> dict:
+        """factor + solve on host arrays with Q, R as packed lower triangles and M optional
+        (None = zero): fewer bytes over the bus than the reference's dense blocks."""
+        e, keep = self.engine, []
+        si = _capi.LqrInput()
+        for k in _capi.LQR_INPUT_FIELDS:
+            a = host.get(k)
+            if a is None:
+                setattr(si, k, None)
+                continue
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            if not a.size:
+                a = np.zeros(1)
+            keep.append(a)
+            setattr(si, k, _host_ptr(a))
+        if out is None:
+            out, so = self._host_out(keep)
+        else:
+            so = _capi.LqrOutput()
+            for k in _capi.LQR_OUTPUT_FIELDS:
+                setattr(so, k, _host_ptr(out[k]))
+        status = np.zeros(self.batch, np.int32)
+        e._check(lib.sipoc_lqr_factor_solve_host_packed(e._handle, ctypes.byref(si),
+                                                        ctypes.byref(so), _host_ptr(status)))
+        return dict(x=out["x"], u=out["u"], y=out["y"], status=status)
+
     def factor_host(self, host: dict) -> np.ndarray:
         if self.traversal_status_ != FactorStatus.SUCCESS:
             return self._invalid()

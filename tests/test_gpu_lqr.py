@@ -519,3 +519,26 @@ def test_lqr_factor_solve_replays_from_a_graph(n, m, T):
     h3.update({k: host2[k] for k in ("q", "r", "c")})
     assert_lqr_parity(lqr.unpack_output(out), pyoracle.lqr_factor_solve(s, h3), REL_TOL)
     lib.sipoc_graph_destroy(g)
+
+
+@pytest.mark.parametrize("n,m,T,dense_M", [(12, 4, 10, False), (6, 2, 7, True), (4, 1, 20, False)])
+def test_packed_symmetric_host_entry(n, m, T, dense_M):
+    # sipoc_lqr_factor_solve_host_packed: Q, R as packed lower triangles, M optional (NULL = 0);
+    # the same kernels on the same numbers as the dense host entry, so bit for bit the same
+    batch = 37
+    s, host = pg.lqr_benchmark_batch(n, m, T, batch, seed=n + T, dense_M=dense_M)
+    dims, topo = to_structs(s)
+    lqr = LQR(dims, topo, batch)
+    dense = lqr.factor_solve_host(host)
+    packed_in = dict(host)
+    packed_in["Q"] = LQR.pack_symmetric(host["Q"], n)
+    packed_in["R"] = LQR.pack_symmetric(host["R"], m)
+    if not dense_M:
+        packed_in["M"] = None
+    assert packed_in["Q"].shape[1] == (T + 1) * n * (n + 1) // 2
+    got = lqr.factor_solve_host_packed(packed_in)
+    assert (got["status"] == 0).all()
+    for k in ("x", "u", "y"):
+        assert np.array_equal(got[k], dense[k]), k
+    ref = pyoracle.lqr_factor_solve(s, host)
+    assert_lqr_parity({**got, "status": got["status"]}, ref, REL_TOL)
