@@ -1801,7 +1801,10 @@ extern "C" {
 int sipoc_f32_supported(const sipoc_engine *e) {
   if (e == nullptr) return 0;
   const HostStructure &h = e->hs;
-  return h.is_chain && h.is_uniform && h.E > 0 && f32_supports(h.n[0], h.m[0]) ? 1 : 0;
+  return h.is_chain && h.is_uniform && h.E > 0 && f32_supports(h.n[0], h.m[0]) &&
+                 f32_fits_index(h.n[0], h.m[0], h.E, e->ld)
+             ? 1
+             : 0;
 }
 
 sipoc_error sipoc_lqr_factor_solve_f32(sipoc_engine *e, const sipoc_lqr_input_f32 *in,

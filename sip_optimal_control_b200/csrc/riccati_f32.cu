@@ -58,7 +58,10 @@ struct StageInputs {
 template <class T, int N, int M>
 __device__ __forceinline__ void fetch_stage(StageInputs<T, N, M> &s, const LqrInT<T> &in, int k,
                                             size_t L, int64_t b) {
-  auto G = [&](const T *p, int e) { return __ldcs(p + static_cast<size_t>(e) * L + b); };
+  // 32-bit element indices (the launcher checks that every array has fewer than 2^31 elements):
+  // one IMAD for the index and one IMAD.WIDE for the address per load
+  const unsigned L32 = static_cast<unsigned>(L), b32 = static_cast<unsigned>(b);
+  auto G = [&](const T *p, int e) { return __ldcs(p + (static_cast<unsigned>(e) * L32 + b32)); };
 #pragma unroll
   for (int t = 0; t < N * N; ++t) s.A[t] = G(in.A, k * N * N + t);
 #pragma unroll
@@ -142,7 +145,10 @@ lqr_thread_backward(LqrInT<T> in, int *status_out, T *store, int64_t batch, int6
   const size_t L = static_cast<size_t>(ld);
   T *Pst = store + Z::oP(Tn) * ld + b, *Kst = store + Z::oK(Tn) * ld + b;
   T *vst = store + Z::ov(Tn) * ld + b, *kst = store + Z::ok(Tn) * ld + b;
-  auto G = [&](const T *p, int e) { return __ldcs(p + static_cast<size_t>(e) * L + b); };
+  const unsigned L32 = static_cast<unsigned>(L);
+  auto G = [&](const T *p, int e) {
+    return __ldcs(p + (static_cast<unsigned>(e) * L32 + static_cast<unsigned>(b)));
+  };
   int status = SIPOC_FACTOR_SUCCESS;
   T W[tri(N)], v[N], dl[N];
 
@@ -183,12 +189,12 @@ lqr_thread_backward(LqrInT<T> in, int *status_out, T *store, int64_t batch, int6
 #pragma unroll
         for (int p = i; p < N; ++p) fin += Li[pk(p, i, N)] * Li[pk(p, j, N)];
         W[pk(i, j, N)] = sdi[i] * ((i == j ? T(1) : T(0)) - fin) * sdi[j];
-        __stcs(Pst + (static_cast<size_t>(k) * tri(N) + pk(i, j, N)) * L, fin);
+        __stcs(Pst + static_cast<unsigned>(k * tri(N) + pk(i, j, N)) * L32, fin);
       }
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       v[i] = vv[i];
-      __stcs(vst + static_cast<size_t>(k * N + i) * L, vv[i]);
+      __stcs(vst + static_cast<unsigned>(k * N + i) * L32, vv[i]);
     }
   };
 
@@ -291,7 +297,7 @@ lqr_thread_backward(LqrInT<T> in, int *status_out, T *store, int64_t batch, int6
       }
 #pragma unroll
       for (int a = 0; a < M; ++a)
-        __stcs(Kst + (static_cast<size_t>(k) * N * M + a + i * M) * L, -kap[a]);
+        __stcs(Kst + static_cast<unsigned>(k * N * M + a + i * M) * L32, -kap[a]);
     }
     // V = Psi_xx - Lam Lam'
 #pragma unroll
@@ -343,7 +349,7 @@ lqr_thread_backward(LqrInT<T> in, int *status_out, T *store, int64_t batch, int6
       kk[a] = t * gdinv[a];
     }
 #pragma unroll
-    for (int a = 0; a < M; ++a) __stcs(kst + static_cast<size_t>(k * M + a) * L, -kk[a]);
+    for (int a = 0; a < M; ++a) __stcs(kst + static_cast<unsigned>(k * M + a) * L32, -kk[a]);
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       T s = w[i];
@@ -365,7 +371,8 @@ template <class T, int N, int M>
 __device__ __forceinline__ void fetch_roll(RollInputs<T, N, M> &s, const LqrInT<T> &in,
                                            const T *store, int k, int Tn, size_t L, int64_t b) {
   using Z = F32Sizes<N, M>;
-  auto G = [&](const T *p, size_t e) { return __ldcs(p + e * L + b); };
+  const unsigned L32 = static_cast<unsigned>(L), b32 = static_cast<unsigned>(b);
+  auto G = [&](const T *p, size_t e) { return __ldcs(p + (static_cast<unsigned>(e) * L32 + b32)); };
 #pragma unroll
   for (int t = 0; t < N * N; ++t) s.A[t] = G(in.A, static_cast<size_t>(k) * N * N + t);
 #pragma unroll
@@ -393,7 +400,9 @@ lqr_thread_rollout(LqrInT<T> in, LqrOutT<T> out, const T *store, int64_t batch, 
   const int64_t b = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (b >= batch) return;
   const size_t L = static_cast<size_t>(ld);
-  auto G = [&](const T *p, size_t e) { return __ldcs(p + e * L + b); };
+  const unsigned L32 = static_cast<unsigned>(L), b32 = static_cast<unsigned>(b);
+  auto G = [&](const T *p, size_t e) { return __ldcs(p + (static_cast<unsigned>(e) * L32 + b32)); };
+  auto S = [&](T *p, int e, T val) { __stcs(p + (static_cast<unsigned>(e) * L32 + b32), val); };
   RollInputs<T, N, M> cur, nxt;
   if (Tn > 0) fetch_roll<T, N, M>(nxt, in, store, 0, Tn, L, b);
   T x[N];
@@ -411,8 +420,8 @@ lqr_thread_rollout(LqrInT<T> in, LqrOutT<T> out, const T *store, int64_t batch, 
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       x[i] = fz[i];
-      __stcs(out.x + static_cast<size_t>(i) * L + b, fz[i]);
-      __stcs(out.y + static_cast<size_t>(i) * L + b, v0[i] + wz[i]);
+      S(out.x, i, fz[i]);
+      S(out.y, i, v0[i] + wz[i]);
     }
   }
   for (int k = 0; k < Tn; ++k) {
@@ -425,7 +434,7 @@ lqr_thread_rollout(LqrInT<T> in, LqrOutT<T> out, const T *store, int64_t batch, 
 #pragma unroll
       for (int i = 0; i < N; ++i) s += cur.K[a + i * M] * x[i];
       u[a] = s;
-      __stcs(out.u + (static_cast<size_t>(k) * M + a) * L + b, s);
+      S(out.u, k * M + a, s);
     }
 #pragma unroll
     for (int i = 0; i < N; ++i) {
@@ -440,8 +449,8 @@ lqr_thread_rollout(LqrInT<T> in, LqrOutT<T> out, const T *store, int64_t batch, 
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       x[i] = fz[i];
-      __stcs(out.x + (static_cast<size_t>(k + 1) * N + i) * L + b, fz[i]);
-      __stcs(out.y + (static_cast<size_t>(k + 1) * N + i) * L + b, cur.v[i] + wz[i]);
+      S(out.x, (k + 1) * N + i, fz[i]);
+      S(out.y, (k + 1) * N + i, cur.v[i] + wz[i]);
     }
   }
 }
@@ -477,6 +486,12 @@ int launch_any(int n, int m, const LqrInT<T> &in, const LqrOutT<T> &out, int *st
 }  // namespace
 
 bool f32_supports(int n, int m) { return n == 4 && m >= 1 && m <= 4; }
+
+// The kernels index every array with 32 bits: the largest one (the kept factorization) must
+// stay below 2^31 elements.
+bool f32_fits_index(int n, int m, int T, int64_t ld) {
+  return f32_store_elems(n, m, T) * ld < (int64_t(1) << 31);
+}
 
 int64_t f32_store_elems(int n, int m, int T) {
   // the same for every instantiated m: computed from the formula, not from a template

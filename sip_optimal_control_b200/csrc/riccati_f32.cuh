@@ -22,6 +22,7 @@ struct LqrOutT {
 };
 
 bool f32_supports(int n, int m);
+bool f32_fits_index(int n, int m, int T, int64_t ld);
 // Elements per problem of the kept factorization + affine spill (P, K, v, k).
 int64_t f32_store_elems(int n, int m, int T);
 // Launch count, or -1 for an unsupported shape.  Arrays in the engine layout [flat][ld].
