@@ -19,9 +19,9 @@
 // Failure order as the reference's (lqr.cpp:696-700, 722-727): G of an edge, then delta of
 // its parent node, then F; the first failure in post-order is reported per problem.
 //
-// Why FP32 pays here: at 16 384 problems x 100 stages the step is bound by the dependent
-// chain of one thread per stage (FP64: 1.7 us per stage); single-precision FMA and MUFU.RSQ
-// latencies roughly halve that chain, and the bytes halve too.
+// Why FP32 pays here: at 16 384 problems x 100 stages (under one warp per scheduler) the step is
+// bound by each thread's own stalls per stage; registers hold three to four stages of float
+// operands in flight where they hold one of doubles, and the bytes halve.
 #include "riccati_f32.cuh"
 
 namespace sipoc {
@@ -54,7 +54,8 @@ struct StageInputs {
   T A[N * N], B[N * M], Q[tri(N)], Mx[N * M], R[tri(M)], q[N], r[M], c[N], d[N];
 };
 
-// Edge k's matrices and vectors (Q, q of node k; c, delta of node k + 1).
+// Edge k's matrices and vectors (Q, q, delta of node k -- what the stage's node step reads
+// last; c of node k + 1; delta of node k + 1 is carried over from the previous stage).
 template <class T, int N, int M>
 __device__ __forceinline__ void fetch_stage(StageInputs<T, N, M> &s, const LqrInT<T> &in, int k,
                                             size_t L, int64_t b) {
@@ -81,7 +82,7 @@ __device__ __forceinline__ void fetch_stage(StageInputs<T, N, M> &s, const LqrIn
   for (int i = 0; i < N; ++i) {
     s.q[i] = G(in.q, k * N + i);
     s.c[i] = G(in.c, (k + 1) * N + i);
-    s.d[i] = G(in.delta, (k + 1) * N + i);
+    s.d[i] = G(in.delta, k * N + i);
   }
 #pragma unroll
   for (int a = 0; a < M; ++a) s.r[a] = G(in.r, k * M + a);
@@ -198,8 +199,16 @@ lqr_thread_backward(LqrInT<T> in, int *status_out, T *store, int64_t batch, int6
     }
   };
 
-  StageInputs<T, N, M> cur, nxt;
-  if (Tn > 0) fetch_stage<T, N, M>(nxt, in, Tn - 1, L, b);
+  // kBufs rotating register buffers (float: 3, double: 2 -- what the register file holds):
+  // edge k is computed from its buffer while the edges behind it are in flight, and the buffer
+  // is refilled with edge k - kBufs as soon as the stage is done with it.  One stage of
+  // compute (~0.5 us) is shorter than the memory latency under load, so a single stage of
+  // look-ahead leaves every stage waiting on its loads.
+  constexpr int kBufs = sizeof(T) == 4 ? 3 : 2;
+  StageInputs<T, N, M> buf[kBufs];
+#pragma unroll
+  for (int d = 0; d < kBufs; ++d)
+    if (Tn - 1 - d >= 0) fetch_stage<T, N, M>(buf[d], in, Tn - 1 - d, L, b);
   {  // terminal node: V = Q_T, v = q_T  (lqr.cpp:658, 744)
     T V[tri(N)], vv[N], dk[N];
 #pragma unroll
@@ -209,17 +218,11 @@ lqr_thread_backward(LqrInT<T> in, int *status_out, T *store, int64_t batch, int6
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       vv[i] = G(in.q, Tn * N + i);
-      dk[i] = Tn > 0 ? nxt.d[i] : G(in.delta, Tn * N + i);
+      dk[i] = G(in.delta, Tn * N + i);
     }
     process_node(Tn, V, vv, dk);
   }
-  for (int k = Tn - 1; k >= 0; --k) {
-    cur = nxt;
-    if (k > 0) fetch_stage<T, N, M>(nxt, in, k - 1, L, b);  // lands while this stage computes
-    // delta of node k: the child's delta of edge k - 1 (node 0: its own row)
-    T dk[N];
-#pragma unroll
-    for (int i = 0; i < N; ++i) dk[i] = k > 0 ? nxt.d[i] : G(in.delta, i);
+  auto stage = [&](int k, StageInputs<T, N, M> &cur) {
     // S = W' [B | A]
     T SB[N * M], SA[N * N];
 #pragma unroll
@@ -357,7 +360,19 @@ lqr_thread_backward(LqrInT<T> in, int *status_out, T *store, int64_t batch, int6
       for (int a = 0; a < M; ++a) s -= Lam[i + a * N] * tt[a];
       vv[i] = s;
     }
+    // delta of node k came with this stage's own operands (a value out of another buffer's
+    // fetch made the stage wait on that buffer's scoreboard, i.e. on loads issued later)
+    T dk[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) dk[i] = cur.d[i];
+    if (k - kBufs >= 0) fetch_stage<T, N, M>(cur, in, k - kBufs, L, b);  // the buffer is free
     process_node(k, V, vv, dk);
+  };
+  for (int k0 = Tn - 1; k0 >= 0; k0 -= kBufs) {
+#pragma unroll
+    for (int slot = 0; slot < kBufs; ++slot)
+      if (k0 - slot >= 0) stage(k0 - slot, buf[slot]);  // (a guard, not a break: the loop must
+                                                         // unroll for buf[] to stay in registers)
   }
   if (status_out != nullptr) status_out[b] = status;
 }
@@ -403,8 +418,13 @@ lqr_thread_rollout(LqrInT<T> in, LqrOutT<T> out, const T *store, int64_t batch, 
   const unsigned L32 = static_cast<unsigned>(L), b32 = static_cast<unsigned>(b);
   auto G = [&](const T *p, size_t e) { return __ldcs(p + (static_cast<unsigned>(e) * L32 + b32)); };
   auto S = [&](T *p, int e, T val) { __stcs(p + (static_cast<unsigned>(e) * L32 + b32), val); };
-  RollInputs<T, N, M> cur, nxt;
-  if (Tn > 0) fetch_roll<T, N, M>(nxt, in, store, 0, Tn, L, b);
+  // kDepth rotating register buffers: a stage of the rollout is ~100 FMAs, far shorter than
+  // the memory latency, so the kernel runs at latency / kDepth per stage until the FMAs bound it.
+  constexpr int kDepth = sizeof(T) == 4 ? 4 : 2;
+  RollInputs<T, N, M> buf[kDepth];
+#pragma unroll
+  for (int d = 0; d < kDepth; ++d)
+    if (d < Tn) fetch_roll<T, N, M>(buf[d], in, store, d, Tn, L, b);
   T x[N];
   {  // root (lqr.cpp:798-819): x = -(I + D V)^-1 (delta o v - c),  y = v + V x = v - W (delta o v - c)
     T P0[tri(N)], d0[N], z[N], fz[N], wz[N], v0[N];
@@ -424,9 +444,12 @@ lqr_thread_rollout(LqrInT<T> in, LqrOutT<T> out, const T *store, int64_t batch, 
       S(out.y, i, v0[i] + wz[i]);
     }
   }
-  for (int k = 0; k < Tn; ++k) {
-    cur = nxt;
-    if (k + 1 < Tn) fetch_roll<T, N, M>(nxt, in, store, k + 1, Tn, L, b);
+  for (int k0 = 0; k0 < Tn; k0 += kDepth) {
+#pragma unroll
+    for (int slot = 0; slot < kDepth; ++slot) {
+    const int k = k0 + slot;
+    if (k < Tn) {  // (a guard, not a break: the loop must unroll for buf[] to stay in registers)
+    RollInputs<T, N, M> &cur = buf[slot];
     T u[M], f[N], fz[N], wz[N];
 #pragma unroll
     for (int a = 0; a < M; ++a) {
@@ -451,6 +474,9 @@ lqr_thread_rollout(LqrInT<T> in, LqrOutT<T> out, const T *store, int64_t batch, 
       x[i] = fz[i];
       S(out.x, (k + 1) * N + i, fz[i]);
       S(out.y, (k + 1) * N + i, cur.v[i] + wz[i]);
+    }
+    if (k + kDepth < Tn) fetch_roll<T, N, M>(cur, in, store, k + kDepth, Tn, L, b);
+    }
     }
   }
 }
