@@ -370,9 +370,10 @@ lqr_thread_backward(LqrInT<T> in, int *status_out, T *store, int64_t batch, int6
   };
   for (int k0 = Tn - 1; k0 >= 0; k0 -= kBufs) {
 #pragma unroll
-    for (int slot = 0; slot < kBufs; ++slot)
-      if (k0 - slot >= 0) stage(k0 - slot, buf[slot]);  // (a guard, not a break: the loop must
-                                                         // unroll for buf[] to stay in registers)
+    for (int slot = 0; slot < kBufs; ++slot) {
+      if (k0 - slot < 0) break;
+      stage(k0 - slot, buf[slot]);
+    }
   }
   if (status_out != nullptr) status_out[b] = status;
 }
@@ -448,7 +449,7 @@ lqr_thread_rollout(LqrInT<T> in, LqrOutT<T> out, const T *store, int64_t batch, 
 #pragma unroll
     for (int slot = 0; slot < kDepth; ++slot) {
     const int k = k0 + slot;
-    if (k < Tn) {  // (a guard, not a break: the loop must unroll for buf[] to stay in registers)
+    if (k >= Tn) break;
     RollInputs<T, N, M> &cur = buf[slot];
     T u[M], f[N], fz[N], wz[N];
 #pragma unroll
@@ -476,7 +477,6 @@ lqr_thread_rollout(LqrInT<T> in, LqrOutT<T> out, const T *store, int64_t batch, 
       S(out.y, (k + 1) * N + i, cur.v[i] + wz[i]);
     }
     if (k + kDepth < Tn) fetch_roll<T, N, M>(cur, in, store, k + kDepth, Tn, L, b);
-    }
     }
   }
 }

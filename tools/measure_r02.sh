@@ -18,12 +18,14 @@ python bench.py --workload long_horizon_quadrotor --steps 10 --no-e2e --no-cpu-b
 python bench.py --workload long_horizon_quadrotor --serial-in-time --steps 5 --no-e2e --no-cpu-baseline 2> /dev/null | tail -1 > $O/bench_long_horizon_quadrotor_serial.json
 python bench.py --workload long_horizon_humanoid --steps 3 --no-e2e --no-cpu-baseline 2> /dev/null | tail -1 > $O/bench_long_horizon_humanoid.json
 python bench.py --batch 8192 --no-e2e --no-cpu-baseline 2> /dev/null | tail -1 > $O/bench_quadrotor_shard8192.json
+python bench.py --workload cartpole --fp32 --no-cpu-baseline 2> /dev/null | tail -1 > $O/bench_cartpole_fp32.json
+python bench.py --e2e-packed --e2e-steps 3 --no-cpu-baseline 2> /dev/null | tail -1 > $O/bench_quadrotor_n1_e2e_packed.json
 cut -c1-230 $O/bench_*.json
 # ncu: quadrotor step at batch 16 384 (two kernels) and at 8 192 (fused): launch lists + full captures
-Q="python bench.py --batch 16384 --steps 2 --warmup 1 --no-e2e --no-cpu-baseline"
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_quadrotor_b16384.csv $Q > $O/ncu_q_launch.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:riccati_backward_subwarp -c 1 -f -o $O/quad_backward $Q > $O/ncu_q_b.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:rollout_forward -c 1 -f -o $O/quad_forward $Q > $O/ncu_q_f.log 2>&1
+Q="python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline"
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_quadrotor_b65536.csv $Q > $O/ncu_q_launch.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:riccati_backward_subwarp -c 1 -f -o $O/quad_backward65536 $Q > $O/ncu_q_b.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:rollout_forward -c 1 -f -o $O/quad_forward65536 $Q > $O/ncu_q_f.log 2>&1
 F="python bench.py --batch 8192 --steps 2 --warmup 1 --no-e2e --no-cpu-baseline"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_quadrotor_b8192_fused.csv $F > $O/ncu_f_launch.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:riccati_backward_subwarp -c 1 -f -o $O/quad_fused $F > $O/ncu_f.log 2>&1
